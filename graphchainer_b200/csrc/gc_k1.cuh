@@ -1,0 +1,932 @@
+// K1 -- banded bit-parallel graph extension from one seed cell, one direction.
+//
+// One work item = the reference's
+//   GraphAlignerBitvectorBanded::getReverseTraceFromSeed(sequence, node, offset)
+// (GraphAlignerBitvectorBanded.h:46-71) with the default parameters of the colinear
+// pipeline (bandwidth 10, ramp 0, no precise clipping, no forced global, low-memory
+// slices, component-ordered queue -- AlignerMain.cpp:145-209):
+//   forward pass   getViterbiSlices/fillDPSlice/calculateSlice   (Banded.h:206-701)
+//   node sweep     calculateNodeInner / getNextSlice             (BVCommon.h:243-263,885-1168)
+//   last slice     flattenLastSliceEnd + phmap slot order        (BVCommon.h:1171-1229)
+//   Viterbi cut    NextState / removeWronglyAlignedEnd           (AlignmentCorrectnessEstimation.cpp:105-129, BVCommon.h:1231-1241)
+//   backtrace      getReverseTraceFromTable + pickBacktrace*     (BVCommon.h:392-804)
+//
+// Design (B200): one thread owns one work item.  Everything a work item touches
+// lives in its own slab of HBM (slice metadata, 64-byte node items, a small
+// binary heap) so no inter-thread communication is needed; parallelism comes from
+// the millions of independent (fragment, seed, direction) items of a read batch.
+// The reference's hash maps / priority queue with per-target lists become:
+//   * a slice = node items stored in processing order, which on a DAG is strictly
+//     ascending componentNumber => membership tests are binary searches;
+//   * the queue = a binary min-heap of (componentNumber,node) keys, duplicates
+//     dropped at pop; a node's incoming columns are re-derived from its
+//     in-neighbours' stored end columns + a `pushed` flag (merge is an element-wise
+//     minimum, so the order of merging does not matter).
+#pragma once
+#include "gc_common.cuh"
+
+// one node of one 64-row slice (reference: NodeSliceMapItemStruct, NodeSlice.h:15-47)
+struct __attribute__((aligned(16))) GcNodeItem
+{
+	uint64_t startVP, startVN;
+	uint64_t endVP, endVN;
+	uint64_t HP, HN;
+	int32_t startScore, endScore;
+	int32_t minScore;
+	uint32_t nodeAndFlag; // bit31 = end column was pushed to the out-neighbours
+};
+
+struct GcSliceMeta
+{
+	double correctLogOdds, falseLogOdds;
+	int32_t minScore;
+	uint32_t minScoreNode;
+	uint32_t minScoreNodeOffset;
+	int32_t bandwidth;
+	uint32_t firstItem;
+	uint32_t numItems;
+	uint8_t correctFromCorrect, falseFromCorrect;
+	uint8_t pad[6];
+};
+
+// constants of AlignmentCorrectnessEstimation.cpp:39-70, computed on the host with
+// libm (exactly as the reference's static initialisers do) and uploaded
+struct GcViterbiTables
+{
+	double correctLogOdds[64];
+	double wrongLogOdds[64];
+	double falseToCorrect, falseToFalse, correctToFalse, correctToCorrect;
+	double initialCorrect, initialFalse; // log(0.8), log(0.2)
+};
+
+// per work item memory, carved from one slab by the host (see gcgpu.cu)
+struct GcK1Workspace
+{
+	GcSliceMeta* slices;   // [numSlices + 1]
+	GcNodeItem* items;     // [itemCap]
+	uint64_t* heap;        // [heapCap]
+	uint32_t itemCap;
+	uint32_t heapCap;
+};
+
+struct GcK1Result
+{
+	int32_t status;      // GcStatus
+	int32_t score;
+	uint32_t traceLen;   // entries written to the trace buffer (reverse order, as the reference builds it)
+	uint32_t itemsUsed;
+	uint64_t columns;    // work counter: Myers column steps (cellsProcessed semantics, BVCommon.h:1162)
+};
+
+// trace entry: node(32) | nodeOffset(6) << 32 | nodeSwitch(1) << 38 | (seqPos+1)(25) << 39
+GC_HD uint64_t gc_pack_trace(uint32_t node, uint32_t offset, int32_t seqPos, bool nodeSwitch)
+{
+	return (uint64_t)node | ((uint64_t)offset << 32) | ((uint64_t)(nodeSwitch ? 1 : 0) << 38) | ((uint64_t)(uint32_t)(seqPos + 1) << 39);
+}
+
+GC_HD GcWord gc_item_start(const GcNodeItem& it) { GcWord w; w.VP = it.startVP; w.VN = it.startVN; w.scoreEnd = it.startScore; return w; }
+GC_HD GcWord gc_item_end(const GcNodeItem& it) { GcWord w; w.VP = it.endVP; w.VN = it.endVN; w.scoreEnd = it.endScore; return w; }
+GC_HD uint32_t gc_item_node(const GcNodeItem& it) { return it.nodeAndFlag & 0x7FFFFFFFu; }
+
+// binary search of `node` in a slice (items sorted by componentNumber)
+GC_HD const GcNodeItem* gc_find_item(const GcGraphView& g, const GcNodeItem* items, uint32_t n, uint32_t node)
+{
+	uint32_t key = g.componentNumber[node];
+	uint32_t lo = 0, hi = n;
+	while (lo < hi)
+	{
+		uint32_t mid = (lo + hi) >> 1;
+		uint32_t k = g.componentNumber[gc_item_node(items[mid])];
+		if (k < key) lo = mid + 1; else hi = mid;
+	}
+	if (lo < n && gc_item_node(items[lo]) == node) return &items[lo];
+	return nullptr;
+}
+
+// ---- heap of (componentNumber << 32 | node)
+GC_HD bool gc_heap_push(uint64_t* heap, uint32_t& size, uint32_t cap, uint64_t key)
+{
+	if (size >= cap) return false;
+	uint32_t i = size++;
+	while (i > 0)
+	{
+		uint32_t p = (i - 1) >> 1;
+		if (heap[p] <= key) break;
+		heap[i] = heap[p];
+		i = p;
+	}
+	heap[i] = key;
+	return true;
+}
+GC_HD uint64_t gc_heap_pop(uint64_t* heap, uint32_t& size)
+{
+	uint64_t top = heap[0];
+	uint64_t last = heap[--size];
+	uint32_t i = 0;
+	while (true)
+	{
+		uint32_t c = 2 * i + 1;
+		if (c >= size) break;
+		if (c + 1 < size && heap[c + 1] < heap[c]) c++;
+		if (heap[c] >= last) break;
+		heap[i] = heap[c];
+		i = c;
+	}
+	if (size > 0) heap[i] = last;
+	return top;
+}
+
+// Columns 1..len-1 of a node from its start column (the tail of calculateNodeInner,
+// BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
+// (recalcNodeWordslice, BVCommon.h:828-852).
+GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t eq[4], GcWord ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
+	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols)
+{
+	uint32_t len = g.nodeLength[node];
+	uint32_t forceUntil = 0;
+	if (prevExists)
+	{
+		int32_t scoreBefore = gc_sbs(ws);
+		int32_t scoreComparison = prevStartScore;
+		if (scoreBefore < scoreComparison)
+		{
+			for (uint32_t fixoffset = 1; fixoffset < 64; fixoffset++)
+			{
+				int32_t newScoreComparison = scoreComparison;
+				newScoreComparison += (int32_t)((prevHP >> fixoffset) & 1);
+				newScoreComparison -= (int32_t)((prevHN >> fixoffset) & 1);
+				uint64_t mask = 1ULL << fixoffset;
+				if (scoreBefore < newScoreComparison)
+				{
+					prevHP |= mask;
+					prevHN &= ~mask;
+					forceUntil = fixoffset;
+				}
+				if (scoreBefore == newScoreComparison)
+				{
+					prevHP &= ~mask;
+					prevHN &= ~mask;
+				}
+				scoreBefore++;
+				scoreComparison = newScoreComparison;
+				if (scoreBefore >= scoreComparison) break;
+			}
+		}
+	}
+	else
+	{
+		forceUntil = len;
+	}
+	if (cols) cols[0] = ws;
+	uint64_t forceEq = ~0ULL;
+	if (!prevExists) forceEq ^= 1;
+	minScore = ws.scoreEnd;
+	minOffset = 0;
+	uint64_t HP = 0, HN = 0;
+	uint64_t chunk0 = g.nodeSeq[2 * (uint64_t)node], chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
+	for (uint32_t pos = 1; pos < len; pos++)
+	{
+		uint64_t chunk = pos < 32 ? chunk0 : chunk1;
+		int base = (int)((chunk >> ((pos & 31) * 2)) & 3);
+		uint64_t Eq = eq[base] & forceEq;
+		uint64_t hP, hN;
+		ws = gc_next_column(Eq, ws, (prevHP >> pos) & 1, (prevHN >> pos) & 1, hP, hN);
+		if (forceUntil >= pos)
+		{
+			ws.VP &= ~1ULL;
+			ws.VN |= 1;
+		}
+		if (ws.scoreEnd < minScore)
+		{
+			minScore = ws.scoreEnd;
+			minOffset = pos;
+		}
+		if (cols) cols[pos] = ws;
+		HP |= hP << pos;
+		HN |= hN << pos;
+	}
+	endOut = ws;
+	HPout = HP;
+	HNout = HN;
+}
+
+// recalcNodeWordslice (BVCommon.h:828-852): all columns of a stored node
+GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const uint64_t eq[4], const GcNodeItem* prev, GcWord* cols)
+{
+	GcWord ws = gc_item_start(item);
+	bool prevExists = prev != nullptr;
+	int32_t prevStart = prevExists ? prev->startScore : 0;
+	if (prevExists && gc_sbs(ws) > prevStart)
+	{
+		GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
+		ws = gc_merge(ws, src);
+	}
+	GcWord endOut; uint64_t hp, hn; int32_t ms; uint32_t mo;
+	gc_node_columns(g, gc_item_node(item), eq, ws, prevExists, prevStart, prevExists ? prev->HP : ~0ULL, prevExists ? prev->HN : 0ULL, endOut, hp, hn, ms, mo, cols);
+}
+
+// phmap::flat_hash_map<size_t,...> slot assignment (phmap.h:487-517,1869-1896,
+// 2008-2020, phmap_utils.h:68-79): returns in `order[]` the indices 0..n-1 of the keys
+// in the iteration order of a table created with reserve(reserveN) and filled by
+// inserting keys[0..n-1] in that order.  `slots` is scratch of >= 2*max(n,reserveN)+2 entries.
+GC_HD uint64_t gc_phmap_hash(uint64_t key)
+{
+#if defined(__CUDA_ARCH__)
+	const uint64_t k = 0xde5fb9d2630458e9ULL;
+	return __umul64hi(key, k) + key * k;
+#else
+	unsigned __int128 p = (unsigned __int128)key * 0xde5fb9d2630458e9ULL;
+	return (uint64_t)(p >> 64) + (uint64_t)p;
+#endif
+}
+GC_HD uint32_t gc_phmap_find_slot(const uint32_t* slots, uint32_t capacity, uint64_t hash)
+{
+	// probe_seq<16>: groups of 16 control bytes starting at H1 & capacity, triangular steps.
+	// Control index `capacity` is the sentinel; indices above it mirror the first 15 slots,
+	// bytes beyond the mirror are always empty (they can only be reached when the table has
+	// a free real slot earlier in the same group, see tests/test_phmap_order).
+	uint64_t offset = (hash >> 7) & capacity;
+	uint64_t index = 0;
+	while (true)
+	{
+		for (uint32_t i = 0; i < 16; i++)
+		{
+			uint64_t ctrl = offset + i;
+			if (ctrl == capacity) continue; // sentinel
+			uint64_t slot = ctrl > capacity ? ctrl - capacity - 1 : ctrl;
+			if (slot >= capacity) return (uint32_t)((offset + i) & capacity);
+			if (slots[slot] == 0xFFFFFFFFu) return (uint32_t)((offset + i) & capacity);
+		}
+		index += 16;
+		offset = (offset + index) & capacity;
+	}
+}
+GC_HD uint32_t gc_phmap_normalize_capacity(uint64_t n)
+{
+	if (n == 0) return 1;
+	uint32_t c = 1;
+	while (c < n) c = c * 2 + 1;
+	return c;
+}
+// keys = node ids of items[0..n-1], inserted in that order.  Returns false if scratch is too small.
+GC_HD bool gc_phmap_order(const GcNodeItem* items, uint32_t n, uint32_t reserveN, uint32_t* slots, uint32_t scratchCap, uint32_t* capacityOut)
+{
+	// reserve(n): rehash(GrowthToLowerboundCapacity(n)) -> capacity NormalizeCapacity(n + (n-1)/7)
+	uint32_t capacity = 0;
+	if (reserveN > 0)
+	{
+		uint64_t lower = (uint64_t)reserveN + (uint64_t)(((int64_t)reserveN - 1) / 7);
+		capacity = gc_phmap_normalize_capacity(lower);
+	}
+	uint32_t size = 0;
+	uint32_t growthLeft = capacity - capacity / 8;
+	if (capacity > scratchCap) return false;
+	for (uint32_t s = 0; s < capacity; s++) slots[s] = 0xFFFFFFFFu;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		if (growthLeft == 0)
+		{
+			// rehash_and_grow_if_necessary: no deletions ever happen here, so it always grows
+			uint32_t newCap = capacity == 0 ? 1 : capacity * 2 + 1;
+			if ((uint64_t)newCap + capacity > scratchCap) return false;
+			// re-insert in old slot order into a fresh table placed after the old one
+			uint32_t* fresh = slots + capacity;
+			for (uint32_t s = 0; s < newCap; s++) fresh[s] = 0xFFFFFFFFu;
+			for (uint32_t s = 0; s < capacity; s++)
+			{
+				if (slots[s] == 0xFFFFFFFFu) continue;
+				uint32_t t = gc_phmap_find_slot(fresh, newCap, gc_phmap_hash((uint64_t)gc_item_node(items[slots[s]])));
+				fresh[t] = slots[s];
+			}
+			for (uint32_t s = 0; s < newCap; s++) slots[s] = fresh[s];
+			capacity = newCap;
+			growthLeft = (capacity - capacity / 8) - size;
+		}
+		uint32_t t = gc_phmap_find_slot(slots, capacity, gc_phmap_hash((uint64_t)gc_item_node(items[i])));
+		slots[t] = i;
+		size++;
+		growthLeft--;
+	}
+	*capacityOut = capacity;
+	return true;
+}
+
+// AlignmentCorrectnessEstimationState::NextState (AlignmentCorrectnessEstimation.cpp:105-129)
+GC_HD void gc_viterbi_next(const GcViterbiTables& t, const GcSliceMeta& prev, int32_t mismatches, GcSliceMeta& out)
+{
+	double cc = prev.correctLogOdds + t.correctToCorrect;
+	double fc = prev.falseLogOdds + t.falseToCorrect;
+	double cf = prev.correctLogOdds + t.correctToFalse;
+	double ff = prev.falseLogOdds + t.falseToFalse;
+	out.correctFromCorrect = cc >= fc;
+	out.falseFromCorrect = cf >= ff;
+	double newCorrect = (cc < fc) ? fc : cc; // std::max(a,b) returns b only if a < b
+	double newFalse = (cf < ff) ? ff : cf;
+	int idx = mismatches < 64 ? mismatches : 63;
+	newCorrect += t.correctLogOdds[idx];
+	newFalse += t.wrongLogOdds[idx];
+	out.correctLogOdds = newCorrect;
+	out.falseLogOdds = newFalse;
+}
+
+struct GcK1Params
+{
+	int32_t bandwidth; // params.initialBandwidth (10)
+};
+
+// ------------------------------------------------------------------------------------
+// Forward pass.  Returns the number of slices kept (index of the last slice in ws.slices),
+// after removeWronglyAlignedEnd; <= 0 means the extension failed.
+GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, const uint8_t* seq, int32_t seqLen, uint32_t startNode, uint32_t startOffset,
+	GcK1Workspace& ws, GcK1Result& res)
+{
+	res.status = GC_OK;
+	res.columns = 0;
+	uint32_t itemsUsed = 0;
+	int32_t numSlices = (seqLen + 63) / 64;
+	// ---- getInitialSliceExactPosition (BVCommon.h:1243-1279)
+	{
+		if (ws.itemCap < 1) { res.status = GC_OVERFLOW_ITEMS; return 0; }
+		GcSliceMeta& m = ws.slices[0];
+		m.correctLogOdds = vt.initialCorrect;
+		m.falseLogOdds = vt.initialFalse;
+		m.correctFromCorrect = 0;
+		m.falseFromCorrect = 0;
+		m.minScore = 0;
+		m.minScoreNode = startNode;
+		m.minScoreNodeOffset = startOffset;
+		m.bandwidth = 1;
+		m.firstItem = 0;
+		m.numItems = 1;
+		GcNodeItem& it = ws.items[0];
+		uint32_t len = g.nodeLength[startNode];
+		it.startVP = 0; it.startVN = 0; it.startScore = (int32_t)startOffset;
+		it.endVP = 0; it.endVN = 0; it.endScore = (int32_t)len - 1 - (int32_t)startOffset;
+		it.minScore = 0;
+		it.nodeAndFlag = startNode;
+		uint64_t HN = 0, HP = 0;
+		for (uint32_t i = 1; i <= startOffset; i++) HN |= 1ULL << i;
+		for (uint32_t i = startOffset + 1; i < len; i++) HP |= 1ULL << i;
+		it.HP = HP; it.HN = HN;
+		itemsUsed = 1;
+	}
+	int32_t lastSlice = 0;
+	for (int32_t slice = 0; slice < numSlices; slice++)
+	{
+		const GcSliceMeta& pm = ws.slices[lastSlice];
+		const GcNodeItem* prevItems = ws.items + pm.firstItem;
+		uint32_t prevN = pm.numItems;
+		int32_t j = slice * 64;
+		int32_t previousMinScore = pm.minScore;
+		int32_t previousQuitScore = pm.minScore + pm.bandwidth;
+		int32_t bandwidth = prm.bandwidth;
+		uint64_t eq[4];
+		gc_eq_vector(seq, seqLen, j, eq);
+		// ---- seed the queue from the previous slice (Banded.h:235-277)
+		uint32_t heapSize = 0;
+		for (uint32_t k = 0; k < prevN; k++)
+		{
+			const GcNodeItem& pn = prevItems[k];
+			uint32_t node = gc_item_node(pn);
+			if (j > 0)
+			{
+				if (pn.minScore > previousQuitScore) continue;
+				if (g.linearizable[node])
+				{
+					uint32_t nb = g.inNbr[g.inStart[node]];
+					const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
+					if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) continue;
+				}
+			}
+			if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[node] << 32) | node)) { res.status = GC_OVERFLOW_HEAP; return 0; }
+		}
+		uint32_t firstItem = itemsUsed;
+		uint32_t curN = 0;
+		GcNodeItem* curItems = ws.items + firstItem;
+		int32_t sliceMinScore = GC_INT_MAX - bandwidth - 1;
+		uint32_t sliceMinNode = 0xFFFFFFFFu, sliceMinOffset = 0xFFFFFFFFu;
+		int32_t currentMinScoreAtEndRow = sliceMinScore;
+		uint64_t lastKey = ~0ULL;
+		while (heapSize > 0)
+		{
+			uint64_t key = gc_heap_pop(ws.heap, heapSize);
+			if (key == lastKey) continue;
+			lastKey = key;
+			uint32_t i = (uint32_t)key;
+			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, i);
+			bool prevExists = prevItem != nullptr;
+			int32_t prevStart = prevExists ? prevItem->startScore : 0;
+			// ---- incoming columns (BVCommon.h:903-964)
+			GcWord w; bool hasWs = false;
+			w.VP = 0; w.VN = 0; w.scoreEnd = 0;
+			bool seeded = false;
+			if (prevExists)
+			{
+				seeded = true;
+				if (j > 0)
+				{
+					if (prevItem->minScore > previousQuitScore) seeded = false;
+					else if (g.linearizable[i])
+					{
+						uint32_t nb = g.inNbr[g.inStart[i]];
+						const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
+						if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) seeded = false;
+					}
+				}
+			}
+			if (seeded)
+			{
+				w.VP = ~0ULL; w.VN = 0; w.scoreEnd = prevStart + 64; // getSourceSliceFromScore
+				hasWs = true;
+			}
+			uint64_t Eq0 = eq[gc_node_base(g, i, 0)];
+			for (uint32_t e = g.inStart[i]; e < g.inStart[i + 1]; e++)
+			{
+				uint32_t p = g.inNbr[e];
+				const GcNodeItem* pit = gc_find_item(g, curItems, curN, p);
+				if (!pit || !(pit->nodeAndFlag & 0x80000000u)) continue;
+				GcWord inc = gc_item_end(*pit);
+				uint64_t hinP, hinN;
+				if (prevExists)
+				{
+					int32_t incSbs = gc_sbs(inc);
+					if (prevStart < incSbs) { hinP = 0; hinN = 1; }
+					else if (prevStart > incSbs) { hinP = 1; hinN = 0; }
+					else { hinP = 0; hinN = 0; }
+				}
+				else { hinP = 1; hinN = 0; }
+				uint64_t oP, oN;
+				GcWord nw = gc_next_column(Eq0, inc, hinP, hinN, oP, oN);
+				if (!prevExists || gc_sbs(nw) < prevStart)
+				{
+					nw.VP &= ~1ULL;
+					nw.VN |= 1;
+				}
+				if (!hasWs) { w = nw; hasWs = true; }
+				else w = gc_merge(w, nw);
+				res.columns++;
+			}
+			if (!hasWs) { res.status = GC_INTERNAL; return 0; }
+			if (prevExists && gc_sbs(w) > prevStart)
+			{
+				GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
+				w = gc_merge(w, src);
+			}
+			if (itemsUsed >= ws.itemCap) { res.status = GC_OVERFLOW_ITEMS; return 0; }
+			GcNodeItem& item = ws.items[itemsUsed++];
+			curN++;
+			GcWord endW; uint64_t HP, HN; int32_t nodeMin; uint32_t nodeMinOffset;
+			gc_node_columns(g, i, eq, w, prevExists, prevStart, prevExists ? prevItem->HP : ~0ULL, prevExists ? prevItem->HN : 0ULL, endW, HP, HN, nodeMin, nodeMinOffset, nullptr);
+			res.columns += g.nodeLength[i];
+			item.startVP = w.VP; item.startVN = w.VN; item.startScore = w.scoreEnd;
+			item.endVP = endW.VP; item.endVN = endW.VN; item.endScore = endW.scoreEnd;
+			item.HP = HP; item.HN = HN;
+			item.minScore = nodeMin;
+			item.nodeAndFlag = i;
+			if (nodeMin < currentMinScoreAtEndRow) currentMinScoreAtEndRow = nodeMin;
+			// ---- push to the out-neighbours (Banded.h:363-387); old end = {0,0,INT_MAX}
+			{
+				int32_t sbsEnd = gc_sbs(endW);
+				uint64_t VP = endW.VP, VN = endW.VN;
+				uint64_t plm = (VP & (VN - VP));
+				plm >>= 1;
+				plm |= 0x8000000000000000ULL & (VN | ~(VN - VP)) & ~VP;
+				int32_t newEndMinScore = sbsEnd;
+				while (plm != 0)
+				{
+					uint64_t cm = plm ^ (plm - 1);
+					int32_t sh = sbsEnd + gc_popc(VP & cm) - gc_popc(VN & cm);
+					if (sh < newEndMinScore) newEndMinScore = sh;
+					plm &= ~cm;
+				}
+				if (newEndMinScore <= currentMinScoreAtEndRow + bandwidth)
+				{
+					item.nodeAndFlag |= 0x80000000u;
+					for (uint32_t e = g.outStart[i]; e < g.outStart[i + 1]; e++)
+					{
+						uint32_t nb = g.outNbr[e];
+						if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[nb] << 32) | nb)) { res.status = GC_OVERFLOW_HEAP; return 0; }
+					}
+				}
+			}
+			if (nodeMin < sliceMinScore)
+			{
+				sliceMinScore = nodeMin;
+				sliceMinNode = i;
+				sliceMinOffset = nodeMinOffset;
+			}
+		}
+		if (sliceMinNode == 0xFFFFFFFFu) { res.status = GC_INTERNAL; return 0; }
+		// ---- flattenLastSliceEnd (BVCommon.h:1171-1229) for a partial last slice
+		if (j + 64 > seqLen)
+		{
+			uint32_t rows = (uint32_t)(seqLen - j);
+			uint64_t rowMask = ~(~0ULL << rows);
+			// phmap iteration order of the slice's node map: reserve(previous size), insert in processing order
+			uint32_t* slots = (uint32_t*)ws.heap;
+			uint32_t capacity = 0;
+			if (!gc_phmap_order(curItems, curN, prevN, slots, ws.heapCap * 2, &capacity)) { res.status = GC_OVERFLOW_HEAP; return 0; }
+			sliceMinScore = GC_INT_MAX;
+			sliceMinNode = 0xFFFFFFFFu;
+			sliceMinOffset = 0xFFFFFFFFu;
+			GcWord cols[64];
+			for (uint32_t s = 0; s < capacity; s++)
+			{
+				uint32_t k = slots[s];
+				if (k == 0xFFFFFFFFu) continue;
+				const GcNodeItem& it = curItems[k];
+				uint32_t node = gc_item_node(it);
+				const GcNodeItem* old = gc_find_item(g, prevItems, prevN, node);
+				gc_recalc_node(g, it, eq, old, cols);
+				uint32_t len = g.nodeLength[node];
+				res.columns += len;
+				for (uint32_t c = 0; c < len; c++)
+				{
+					// flattenWordSlice (BVCommon.h:265-273)
+					int32_t sc = cols[c].scoreEnd - gc_popc(cols[c].VP & ~rowMask) + gc_popc(cols[c].VN & ~rowMask);
+					if (sc < sliceMinScore)
+					{
+						sliceMinScore = sc;
+						sliceMinNode = node;
+						sliceMinOffset = c;
+					}
+				}
+			}
+		}
+		GcSliceMeta& nm = ws.slices[lastSlice + 1];
+		nm.minScore = sliceMinScore;
+		nm.minScoreNode = sliceMinNode;
+		nm.minScoreNodeOffset = sliceMinOffset;
+		nm.bandwidth = bandwidth;
+		nm.firstItem = firstItem;
+		nm.numItems = curN;
+		gc_viterbi_next(vt, pm, sliceMinScore - previousMinScore, nm);
+		if (!nm.correctFromCorrect) break; // Banded.h:589-607: the new slice is dropped
+		lastSlice++;
+	}
+	res.itemsUsed = itemsUsed;
+	// ---- removeWronglyAlignedEnd (BVCommon.h:1231-1241)
+	int32_t count = lastSlice + 1;
+	{
+		bool currentlyCorrect = ws.slices[count - 1].correctLogOdds > ws.slices[count - 1].falseLogOdds;
+		while (!currentlyCorrect)
+		{
+			currentlyCorrect = ws.slices[count - 1].falseFromCorrect;
+			count--;
+			if (count == 0) break;
+		}
+	}
+	return count - 1;
+}
+
+// ------------------------------------------------------------------------------------
+// Backtrace (BVCommon.h:392-544).  `last` = index of the last kept slice (>= 1).
+struct GcTraceWriter
+{
+	uint64_t* out;
+	uint32_t cap;
+	uint32_t n;
+	uint32_t node; uint32_t offset; int32_t seqPos; // trace.back()
+	bool overflow;
+	GC_HD void push(uint32_t nd, uint32_t off, int32_t sp, bool sw)
+	{
+		if (n < cap) out[n] = gc_pack_trace(nd, off, sp, sw); else overflow = true;
+		n++;
+		node = nd; offset = off; seqPos = sp;
+	}
+};
+
+struct GcBtPos { uint32_t node; uint32_t offset; int32_t seqPos; bool nodeSwitch; };
+
+// pickBacktraceCorner (BVCommon.h:710-804); scoresNotValid is always false here
+GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t curN, const GcNodeItem* prev, uint32_t prevN, uint32_t node, int32_t j, const uint8_t* seq, int32_t quitScore, int32_t previousQuitScore, GcBtPos& out)
+{
+	const GcNodeItem* me = gc_find_item(g, cur, curN, node);
+	int32_t scoreHere = gc_value(gc_item_start(*me), 0);
+	const GcNodeItem* prevMe = gc_find_item(g, prev, prevN, node);
+	if (scoreHere > quitScore)
+	{
+		int32_t smallestFound = scoreHere + 1;
+		out.node = 0; out.offset = 0; out.seqPos = 0; out.nodeSwitch = false;
+		if (prevMe)
+		{
+			smallestFound = prevMe->startScore;
+			out.node = node; out.offset = 0; out.seqPos = j - 1; out.nodeSwitch = false;
+		}
+		for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
+		{
+			uint32_t nb = g.inNbr[e];
+			const GcNodeItem* pn = gc_find_item(g, prev, prevN, nb);
+			if (pn)
+			{
+				if (pn->endScore <= smallestFound)
+				{
+					smallestFound = pn->endScore;
+					out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j - 1; out.nodeSwitch = true;
+				}
+			}
+			const GcNodeItem* cn = gc_find_item(g, cur, curN, nb);
+			if (cn && nb != node)
+			{
+				int32_t v = gc_value(gc_item_end(*cn), 0);
+				if (v < smallestFound)
+				{
+					smallestFound = v;
+					out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j; out.nodeSwitch = true;
+				}
+			}
+		}
+		return true;
+	}
+	bool eq = gc_char_match(seq[j], gc_node_base(g, node, 0));
+	if (prevMe && prevMe->startScore == scoreHere - 1)
+	{
+		out.node = node; out.offset = 0; out.seqPos = j - 1; out.nodeSwitch = false;
+		return true;
+	}
+	bool haveInvalid = false;
+	GcBtPos bestInvalid; bestInvalid.node = 0; bestInvalid.offset = 0; bestInvalid.seqPos = 0; bestInvalid.nodeSwitch = true;
+	int32_t bestInvalidScore = scoreHere + 1;
+	for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
+	{
+		uint32_t nb = g.inNbr[e];
+		const GcNodeItem* cn = gc_find_item(g, cur, curN, nb);
+		if (cn && gc_value(gc_item_end(*cn), 0) == scoreHere - 1)
+		{
+			out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j; out.nodeSwitch = true;
+			return true;
+		}
+		const GcNodeItem* pn = gc_find_item(g, prev, prevN, nb);
+		if (pn)
+		{
+			int32_t cornerScore = pn->endScore;
+			if (cornerScore > previousQuitScore)
+			{
+				if (cornerScore < bestInvalidScore)
+				{
+					bestInvalidScore = cornerScore;
+					bestInvalid.node = nb; bestInvalid.offset = g.nodeLength[nb] - 1; bestInvalid.seqPos = j - 1;
+					haveInvalid = true;
+				}
+			}
+			else if (cornerScore == scoreHere - (eq ? 0 : 1))
+			{
+				out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j - 1; out.nodeSwitch = true;
+				return true;
+			}
+		}
+	}
+	if (bestInvalidScore < scoreHere + 1 && haveInvalid)
+	{
+		out = bestInvalid;
+		return true;
+	}
+	return false; // the reference asserts here
+}
+
+GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seqLen, GcK1Workspace& ws, int32_t last, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
+{
+	GcTraceWriter tw;
+	tw.out = traceOut; tw.cap = traceCap; tw.n = 0; tw.overflow = false;
+	const GcSliceMeta& lm = ws.slices[last];
+	res.score = lm.minScore;
+	{
+		int32_t sp = (last - 1) * 64 + 63;
+		if (sp > seqLen - 1) sp = seqLen - 1;
+		tw.push(lm.minScoreNode, lm.minScoreNodeOffset, sp, false);
+	}
+	uint32_t currentNode = 0xFFFFFFFFu;
+	int32_t currentSlice = -1;
+	GcWord cols[64];
+	uint64_t eq[4];
+	uint32_t guard = 0;
+	uint32_t guardMax = (uint32_t)seqLen * 4 + 1024 + traceCap;
+	while (tw.seqPos != -1)
+	{
+		if (++guard > guardMax) { res.status = GC_INTERNAL; return; }
+		int32_t newSlice = tw.seqPos / 64 + 1;
+		uint32_t newNode = tw.node;
+		const GcSliceMeta& cm = ws.slices[newSlice];
+		const GcSliceMeta& pmeta = ws.slices[newSlice - 1];
+		const GcNodeItem* cur = ws.items + cm.firstItem;
+		const GcNodeItem* prev = ws.items + pmeta.firstItem;
+		int32_t j = (newSlice - 1) * 64;
+		if (newSlice != currentSlice || newNode != currentNode)
+		{
+			if (newSlice != currentSlice) gc_eq_vector(seq, seqLen, j, eq);
+			currentSlice = newSlice;
+			currentNode = newNode;
+			const GcNodeItem* me = gc_find_item(g, cur, cm.numItems, currentNode);
+			if (!me) { res.status = GC_INTERNAL; return; }
+			const GcNodeItem* pme = gc_find_item(g, prev, pmeta.numItems, currentNode);
+			gc_recalc_node(g, *me, eq, pme, cols);
+			res.columns += g.nodeLength[currentNode];
+		}
+		int32_t quitScore = cm.minScore + cm.bandwidth;
+		int32_t previousQuitScore = pmeta.minScore + pmeta.bandwidth;
+		if ((tw.seqPos & 63) == 0 && tw.offset == 0)
+		{
+			GcBtPos bt;
+			if (!gc_bt_corner(g, cur, cm.numItems, prev, pmeta.numItems, currentNode, j, seq, quitScore, previousQuitScore, bt)) { res.status = GC_INTERNAL; return; }
+			tw.push(bt.node, bt.offset, bt.seqPos, bt.nodeSwitch);
+			continue;
+		}
+		if ((tw.seqPos & 63) == 0)
+		{
+			// vertical crossing (BVCommon.h:451-477, 665-708)
+			const GcNodeItem* pme = gc_find_item(g, prev, pmeta.numItems, currentNode);
+			if (!pme)
+			{
+				tw.push(currentNode, 0, tw.seqPos, false);
+				continue;
+			}
+			uint32_t off = tw.offset;
+			int32_t sp = tw.seqPos;
+			uint32_t origOff = off;
+			while (off > 0 && gc_value(cols[off - 1], 0) == gc_value(cols[off], 0) - 1) off--;
+			GcBtPos second;
+			if (off == 0)
+			{
+				if (!gc_bt_corner(g, cur, cm.numItems, prev, pmeta.numItems, currentNode, j, seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; return; }
+			}
+			else
+			{
+				bool eqc = gc_char_match(seq[sp], gc_node_base(g, currentNode, off));
+				int32_t scoreHere = gc_value(cols[off], 0);
+				int32_t scoreDiagonal = pme->startScore;
+				for (uint32_t i = 1; i + 1 <= off; i++)
+				{
+					scoreDiagonal += (int32_t)((pme->HP >> i) & 1);
+					scoreDiagonal -= (int32_t)((pme->HN >> i) & 1);
+				}
+				int32_t scoreUp = scoreDiagonal;
+				scoreUp += (int32_t)((pme->HP >> off) & 1);
+				scoreUp -= (int32_t)((pme->HN >> off) & 1);
+				second.node = currentNode; second.seqPos = sp - 1; second.nodeSwitch = false;
+				if (scoreHere > quitScore || scoreDiagonal > previousQuitScore || scoreUp > previousQuitScore)
+				{
+					second.offset = (scoreDiagonal < scoreUp) ? off - 1 : off;
+				}
+				else if (scoreUp == scoreHere - 1) second.offset = off;
+				else
+				{
+					if (scoreDiagonal != scoreHere - (eqc ? 0 : 1)) { res.status = GC_INTERNAL; return; }
+					second.offset = off - 1;
+				}
+			}
+			if (off != origOff)
+			{
+				for (uint32_t o = origOff - 1; o != off; o--) tw.push(currentNode, o, sp, false);
+			}
+			if (off != tw.offset || sp != tw.seqPos) tw.push(currentNode, off, sp, false);
+			tw.push(second.node, second.offset, second.seqPos, second.nodeSwitch);
+			continue;
+		}
+		if (tw.offset == 0)
+		{
+			// horizontal crossing (BVCommon.h:478-499, 599-663)
+			const GcNodeItem* me = gc_find_item(g, cur, cm.numItems, currentNode);
+			GcWord startSlice = gc_item_start(*me);
+			int32_t sp = tw.seqPos;
+			int32_t origSp = sp;
+			while ((sp & 63) != 0 && (startSlice.VP & (1ULL << (sp & 63)))) sp--;
+			int32_t offset = sp & 63;
+			GcBtPos second;
+			if (offset == 0)
+			{
+				if (!gc_bt_corner(g, cur, cm.numItems, prev, pmeta.numItems, currentNode, j, seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; return; }
+			}
+			else
+			{
+				bool eqc = gc_char_match(seq[sp], gc_node_base(g, currentNode, 0));
+				int32_t scoreHere = gc_value(startSlice, offset);
+				bool found = false;
+				if (scoreHere > quitScore)
+				{
+					int32_t smallestFound = gc_value(startSlice, offset - 1);
+					second.node = currentNode; second.offset = 0; second.seqPos = sp - 1; second.nodeSwitch = false;
+					for (uint32_t e = g.inStart[currentNode]; e < g.inStart[currentNode + 1]; e++)
+					{
+						uint32_t nb = g.inNbr[e];
+						const GcNodeItem* cn = gc_find_item(g, cur, cm.numItems, nb);
+						if (!cn) continue;
+						GcWord ns = gc_item_end(*cn);
+						int32_t v1 = gc_value(ns, offset - 1);
+						if (v1 <= smallestFound)
+						{
+							smallestFound = v1;
+							second.node = nb; second.offset = g.nodeLength[nb] - 1; second.seqPos = sp - 1; second.nodeSwitch = true;
+						}
+						int32_t v0 = gc_value(ns, offset);
+						if (v0 < smallestFound && nb != currentNode)
+						{
+							smallestFound = v0;
+							second.node = nb; second.offset = g.nodeLength[nb] - 1; second.seqPos = sp; second.nodeSwitch = true;
+						}
+					}
+					found = true;
+				}
+				else
+				{
+					for (uint32_t e = g.inStart[currentNode]; e < g.inStart[currentNode + 1] && !found; e++)
+					{
+						uint32_t nb = g.inNbr[e];
+						const GcNodeItem* cn = gc_find_item(g, cur, cm.numItems, nb);
+						if (!cn) continue;
+						GcWord ns = gc_item_end(*cn);
+						if (gc_value(ns, offset) == scoreHere - 1)
+						{
+							second.node = nb; second.offset = g.nodeLength[nb] - 1; second.seqPos = sp; second.nodeSwitch = true;
+							found = true;
+						}
+						else if (gc_value(ns, offset - 1) == scoreHere - (eqc ? 0 : 1))
+						{
+							second.node = nb; second.offset = g.nodeLength[nb] - 1; second.seqPos = sp - 1; second.nodeSwitch = true;
+							found = true;
+						}
+					}
+				}
+				if (!found) { res.status = GC_INTERNAL; return; }
+			}
+			if (sp != origSp)
+			{
+				for (int32_t s = origSp - 1; s != sp; s--) tw.push(currentNode, 0, s, false);
+			}
+			if (sp != tw.seqPos) tw.push(currentNode, 0, sp, false);
+			tw.push(second.node, second.offset, second.seqPos, second.nodeSwitch);
+			continue;
+		}
+		// inside the node (BVCommon.h:556-597)
+		{
+			uint32_t hori = tw.offset;
+			int32_t vert = tw.seqPos - j;
+			while (hori > 0 && vert > 0)
+			{
+				int32_t scoreHere = gc_value(cols[hori], vert);
+				int32_t verticalScore = gc_value(cols[hori], vert - 1);
+				int32_t diagonalScore = gc_value(cols[hori - 1], vert - 1);
+				bool eqc = gc_char_match(seq[vert + j], gc_node_base(g, currentNode, hori));
+				if (verticalScore == scoreHere - 1)
+				{
+					vert--;
+				}
+				else if (diagonalScore == scoreHere - (eqc ? 0 : 1))
+				{
+					hori--;
+					vert--;
+				}
+				else
+				{
+					hori--;
+				}
+				tw.push(currentNode, hori, vert + j, false);
+			}
+		}
+	}
+	// ---- slide left in row -1 (BVCommon.h:508-542); the do/while(false) runs once
+	{
+		const GcSliceMeta& m0 = ws.slices[0];
+		const GcNodeItem* s0 = ws.items + m0.firstItem;
+		const GcNodeItem* it = gc_find_item(g, s0, m0.numItems, tw.node);
+		if (!it) { res.status = GC_INTERNAL; return; }
+		// beforeSliceScores[i] = startScore + sum_{k=1..i} (HP_k - HN_k)
+		uint32_t off = tw.offset;
+		int32_t here = it->startScore + gc_popc(it->HP & ((2ULL << off) - 2)) - gc_popc(it->HN & ((2ULL << off) - 2));
+		while (here != 0 && off > 0)
+		{
+			int32_t before = here - (int32_t)((it->HP >> off) & 1) + (int32_t)((it->HN >> off) & 1);
+			if (before != here - 1) break;
+			off--;
+			here = before;
+			tw.push(tw.node, off, tw.seqPos, false);
+		}
+		if (off == 0 && here != 0)
+		{
+			for (uint32_t e = g.inStart[tw.node]; e < g.inStart[tw.node + 1]; e++)
+			{
+				uint32_t nb = g.inNbr[e];
+				const GcNodeItem* nit = gc_find_item(g, s0, m0.numItems, nb);
+				if (nit && gc_sbs(gc_item_end(*nit)) == here - 1)
+				{
+					tw.push(nb, g.nodeLength[nb] - 1, tw.seqPos, true);
+					break;
+				}
+			}
+		}
+	}
+	res.traceLen = tw.n;
+	if (tw.overflow) res.status = GC_OVERFLOW_TRACE;
+}
+
+// one complete work item
+GC_HD void gc_k1_extend(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, const uint8_t* seq, int32_t seqLen, uint32_t startNode, uint32_t startOffset,
+	GcK1Workspace& ws, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
+{
+	res.score = GC_INT_MAX;
+	res.traceLen = 0;
+	res.itemsUsed = 0;
+	int32_t last = gc_k1_forward(g, vt, prm, seq, seqLen, startNode, startOffset, ws, res);
+	if (res.status != GC_OK) return;
+	if (last < 1) { res.status = GC_FAILED; return; }
+	gc_k1_backtrace(g, seq, seqLen, ws, last, traceOut, traceCap, res);
+}
