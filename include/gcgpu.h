@@ -1,0 +1,143 @@
+/* libgcgpu -- C ABI of the B200 (sm_100a) GraphChainer alignment hot path.
+ *
+ * Drop-in boundary: the reference reaches this path by direct
+ * C++ calls from the per-read loop body runComponentMappings (src/Aligner.cpp:492-1062).
+ * Each entry point below is the batch form of one of those seams; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers (pinned if the
+ * caller wants asynchronous copies), no exceptions across the boundary -- every call
+ * returns 0 on success or a negative gcgpu_status, with text in gcgpu_last_error().
+ * One gcgpu_ctx per device; calls on one ctx are serialised by the caller.
+ * There is no CPU fallback: without a CUDA device gcgpu_create() fails.
+ */
+#ifndef GCGPU_H
+#define GCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcgpu_ctx gcgpu_ctx;
+
+enum gcgpu_status
+{
+	GCGPU_OK = 0,
+	GCGPU_ERR_CUDA = -1,      /* a CUDA runtime call failed                       */
+	GCGPU_ERR_ARG = -2,       /* invalid argument                                 */
+	GCGPU_ERR_NOMEM = -3,     /* device or host memory exhausted                  */
+	GCGPU_ERR_INTERNAL = -4   /* a work item hit a state the reference asserts on */
+};
+
+/* per work item outcome (K1), mirrors OnewayTrace::failed() (GraphAlignerCommon.h:164-171) */
+enum gcgpu_item_status
+{
+	GCGPU_ITEM_OK = 0,
+	GCGPU_ITEM_FAILED = 1,    /* the reference's TraceFailed(): <= 1 slice survived        */
+	GCGPU_ITEM_INTERNAL = 5   /* assert-class condition; the reference would drop the read */
+};
+
+/* Split-node alignment graph + MPC index: flat arrays in REFERENCE numbering, i.e. the
+ * members of AlignmentGraph (src/AlignmentGraph.h:145-172) after Finalize() and buildMPC():
+ *   node_length[i]      = nodeLength[i]              (1..64, SPLIT_NODE_SIZE, AlignmentGraph.h:20)
+ *   node_seq[2i..2i+1]  = nodeSequences[i].s[0..1]   (2 bit/base A0 C1 G2 T3, AlignmentGraph.cpp:114-142)
+ *   in_/out_ CSR        = inNeighbors / outNeighbors in stored (insertion) order
+ *   component_number    = componentNumber            (AlignmentGraph.cpp:1008-1105)
+ *   linearizable        = linearizable               (AlignmentGraph.cpp:644-736)
+ *   comp_map/comp_idx   = component_map / component_idx           (AlignmentGraph.cpp:1430-1463)
+ *   comp_start          = prefix sums of component_ids[c].size()  (C+1 entries)
+ *   topo_ids            = topo_ids[c][idx] at comp_start[c]+idx   (AlignmentGraph.cpp:1351-1364)
+ *   paths_* / back_*    = CSR over (comp_start[c]+idx) of paths[c][idx] and backwards[c][idx]
+ * All host pointers; gcgpu_create() copies them to the device.  Graphs with ambiguous
+ * bases (firstAmbiguous < N) are not supported by this path.                              */
+typedef struct gcgpu_graph
+{
+	uint32_t num_nodes;
+	const uint8_t* node_length;
+	const uint64_t* node_seq;
+	const uint32_t* in_start;
+	const uint32_t* in_nbr;
+	const uint32_t* out_start;
+	const uint32_t* out_nbr;
+	const uint32_t* component_number;
+	const uint8_t* linearizable;
+	/* MPC index (may be all NULL / 0 if gcgpu_chain is not used) */
+	uint32_t num_components;
+	const uint32_t* comp_map;
+	const uint32_t* comp_idx;
+	const uint32_t* comp_start;
+	const uint32_t* topo_ids;
+	const uint32_t* paths_start;
+	const uint32_t* paths_k;
+	const uint32_t* back_start;
+	const uint32_t* back_node;
+	const uint32_t* back_k;
+} gcgpu_graph;
+
+/* The constants of GraphAlignerCommon::Params the path honours (GraphAlignerCommon.h:92-126);
+ * defaults = AlignerMain.cpp:145-209 (vg preset + colinear defaults).                     */
+typedef struct gcgpu_params
+{
+	int32_t initial_bandwidth;   /* -b / params.initialBandwidth, default 10 */
+} gcgpu_params;
+
+int gcgpu_version(void);
+const char* gcgpu_last_error(void);
+
+/* Replaces: AlignmentGraph construction hand-over + AlignerGraphsizedState (Aligner.cpp:469). */
+int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_params* params, gcgpu_ctx** out);
+void gcgpu_destroy(gcgpu_ctx* ctx);
+
+/* ---- K1: banded bit-parallel graph extension ------------------------------------------
+ * One item replaces one call of
+ *   GraphAlignerBitvectorBanded::getReverseTraceFromSeed(sequence, bigraphNodeId, nodeOffset, ...)
+ * (src/GraphAlignerBitvectorBanded.h:46-71), reached from AlignOneWay -> getAlignmentFromSeed
+ * -> getTwoDirectionalTrace (src/GraphAligner.h:114-203,480-525,567-626).
+ * `seq` = concatenated IUPAC-mask codes (bit0 A, bit1 C, bit2 G, bit3 T), one byte per base;
+ * an item aligns seq[seq_offset .. seq_offset+seq_len) starting from the cell (node, offset)
+ * where node is a SPLIT node index (AlignmentGraph::GetUnitigNode already applied).       */
+typedef struct gcgpu_ext_item
+{
+	uint64_t seq_offset;
+	int32_t seq_len;
+	uint32_t node;
+	uint32_t offset;
+	uint32_t reserved;
+} gcgpu_ext_item;
+
+typedef struct gcgpu_ext_result
+{
+	int32_t status;         /* gcgpu_item_status */
+	int32_t score;          /* OnewayTrace::score */
+	uint32_t trace_len;     /* number of trace entries */
+	uint32_t reserved;
+	uint64_t trace_offset;  /* index of the first entry in the trace buffer */
+	uint64_t columns;       /* work counter: 64-row Myers column steps (BVCommon.h:1162 semantics) */
+} gcgpu_ext_result;
+
+/* Trace entries are in the order the reference builds them (end of alignment first, the
+ * seed cell with seqPos -1 last; getReverseTraceFromTable, BVCommon.h:392-544), packed:
+ *   bits 0-31 split node | 32-37 offset in node | 38 nodeSwitch | 39-63 seqPos+1          */
+#define GCGPU_TRACE_NODE(t) ((uint32_t)((t) & 0xFFFFFFFFu))
+#define GCGPU_TRACE_OFFSET(t) ((uint32_t)(((t) >> 32) & 63))
+#define GCGPU_TRACE_SWITCH(t) ((int)(((t) >> 38) & 1))
+#define GCGPU_TRACE_SEQPOS(t) ((int32_t)(((t) >> 39) & 0x1FFFFFF) - 1)
+
+/* results[n]; traces[trace_capacity] receives all traces back to back; *trace_used = entries
+ * written (if it exceeds trace_capacity the call fails with GCGPU_ERR_ARG and *trace_used
+ * tells the required size).  All buffers are host memory.                                  */
+int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
+                 gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used);
+
+/* device time of the kernels of the last call on this ctx, in milliseconds (CUDA events) */
+float gcgpu_last_kernel_ms(gcgpu_ctx* ctx);
+/* number of kernel launches issued by this ctx so far */
+uint64_t gcgpu_launch_count(gcgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
