@@ -64,6 +64,17 @@ GC_HD bool gc_k2_reaches(const GcMpcView& m, uint32_t e, uint32_t s)
 
 GC_HD int64_t gc_k2_key(int32_t score, int32_t idx) { return ((int64_t)score << 32) | (uint32_t)(idx + 1); }
 
+// candidate key of predecessor i for anchor j (both in the same component), or INT64_MIN
+GC_HD int64_t gc_k2_candidate(const GcMpcView& m, const GcAnchor& ai, const GcAnchor& aj, uint32_t i, int32_t scoreI)
+{
+	if (!gc_k2_reaches(m, ai.endNode, aj.startNode)) return (int64_t)0x8000000000000000LL;
+	int32_t len = aj.y - aj.x + 1;
+	int32_t val = (ai.y <= aj.x - 1) ? len + scoreI : aj.y - ai.y + scoreI;
+	return gc_k2_key(val, (int32_t)i);
+}
+
+GC_HD uint32_t gc_k2_select(const GcMpcView& m, const GcAnchor* a, uint32_t n, const int32_t* score, const int32_t* pred, uint32_t* chainOut, int64_t* bestScoreOut);
+
 // Sequential form (host checks, and the single-thread tail of the kernel).  order[] = anchor
 // indices sorted by (y, index); score[]/pred[] are outputs; chainOut receives the chain
 // (anchor indices in read order), returns its length.  bestScore = covered read bases.
@@ -88,7 +99,13 @@ GC_HD uint32_t gc_k2_chain_seq(const GcMpcView& m, const GcAnchor* a, uint32_t n
 		score[j] = (int32_t)(best >> 32);
 		pred[j] = (int32_t)(uint32_t)(best & 0xFFFFFFFFu) - 1;
 	}
-	// best chain end: per component max (C, j); first component (ascending id) with a strictly larger score
+	return gc_k2_select(m, a, n, score, pred, chainOut, bestScoreOut);
+}
+
+// best chain end + backtrack (AlignmentGraph.cpp:1848-1862 and :1717-1733)
+GC_HD uint32_t gc_k2_select(const GcMpcView& m, const GcAnchor* a, uint32_t n, const int32_t* score, const int32_t* pred, uint32_t* chainOut, int64_t* bestScoreOut)
+{
+	// per component max (C, j); first component (ascending id) with a strictly larger score
 	int64_t bestKey = -1; uint32_t bestComp = 0xFFFFFFFFu; bool first = true;
 	// components in ascending order: scan for the smallest unseen component id repeatedly (n is small)
 	uint32_t lastComp = 0; bool haveLast = false;

@@ -9,6 +9,8 @@
 #include "../../include/gcgpu.h"
 #include "gc_common.cuh"
 #include "gc_k1.cuh"
+#include "gc_k2.cuh"
+#include "gc_k3.cuh"
 #include "gc_host_graph.h"
 
 #define GCGPU_VERSION 1
@@ -60,6 +62,11 @@ struct gcgpu_ctx
 	uint32_t* d_componentNumber = nullptr; uint8_t* d_linearizable = nullptr;
 	GcViterbiTables* d_vt = nullptr;
 	GcGraphView view;
+	// MPC index (K2)
+	uint32_t* d_compMap = nullptr; uint32_t* d_compIdx = nullptr; uint32_t* d_compStart = nullptr; uint32_t* d_topoIds = nullptr;
+	uint32_t* d_pathsStart = nullptr; uint32_t* d_pathsK = nullptr; uint32_t* d_backStart = nullptr; uint32_t* d_backNode = nullptr; uint32_t* d_backK = nullptr;
+	bool haveMpc = false;
+	GcMpcView mpc;
 	DevBuf seqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc;
 	float lastKernelMs = 0;
 	uint64_t launches = 0;
@@ -128,6 +135,8 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->d_nodeLength); cudaFree(ctx->d_nodeSeq); cudaFree(ctx->d_inStart); cudaFree(ctx->d_inNbr); cudaFree(ctx->d_outStart); cudaFree(ctx->d_outNbr);
 	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt);
+	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
+	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
 	ctx->seqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -166,6 +175,19 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	chk(uploadArray(graph->linearizable, N, &ctx->d_linearizable));
 	GcViterbiTables vt = gcMakeViterbiTables();
 	chk(uploadArray(&vt, 1, &ctx->d_vt));
+	if (graph->comp_map && graph->comp_idx && graph->comp_start && graph->topo_ids && graph->paths_start && graph->back_start)
+	{
+		chk(uploadArray(graph->comp_map, N, &ctx->d_compMap));
+		chk(uploadArray(graph->comp_idx, N, &ctx->d_compIdx));
+		chk(uploadArray(graph->comp_start, (size_t)graph->num_components + 1, &ctx->d_compStart));
+		chk(uploadArray(graph->topo_ids, N, &ctx->d_topoIds));
+		chk(uploadArray(graph->paths_start, (size_t)N + 1, &ctx->d_pathsStart));
+		chk(uploadArray(graph->paths_k, graph->paths_start[N], &ctx->d_pathsK));
+		chk(uploadArray(graph->back_start, (size_t)N + 1, &ctx->d_backStart));
+		chk(uploadArray(graph->back_node, graph->back_start[N], &ctx->d_backNode));
+		chk(uploadArray(graph->back_k, graph->back_start[N], &ctx->d_backK));
+		ctx->haveMpc = true;
+	}
 	if (err != cudaSuccess)
 	{
 		std::string msg = std::string("gcgpu_create: ") + cudaGetErrorString(err);
@@ -176,6 +198,8 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.nodeLength = ctx->d_nodeLength; ctx->view.nodeSeq = ctx->d_nodeSeq;
 	ctx->view.inStart = ctx->d_inStart; ctx->view.inNbr = ctx->d_inNbr; ctx->view.outStart = ctx->d_outStart; ctx->view.outNbr = ctx->d_outNbr;
 	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable;
+	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
+	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
 	*out = ctx;
 	return GCGPU_OK;
 }
@@ -302,5 +326,314 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		ctx->lastKernelMs += ms;
 	}
 	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_extend: a work item reached a state the reference asserts on (see per-item status)");
+	return GCGPU_OK;
+}
+
+// ------------------------------------------------------------------ K3 kernels
+__global__ void gc_k3_encode_kernel(uint8_t* seq, uint64_t n)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride)
+	{
+		uint8_t c = seq[i];
+		seq[i] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+	}
+}
+
+struct GcK3Desc
+{
+	uint64_t qOff, tOff, wsOff, opsOff;
+	int32_t q, t, kHint, best;
+	uint32_t resultIndex, opsCap;
+};
+struct GcK3Out { int32_t status; int32_t distance; uint32_t opsLen; uint32_t pad; uint64_t blocks; };
+
+static size_t k3DistWorkspaceBytes(int32_t q) { size_t nb = (size_t)(q + 63) / 64 + 1; return alignUp(nb * 4 * 8 + nb * sizeof(GcK3Block), 128); }
+static const uint32_t K3_STORE_CAP = 52432, K3_COL_CAP = 37456, K3_STACK_CAP = 96;
+static size_t k3PathWorkspaceBytes(int32_t q)
+{
+	size_t nb = (size_t)(q + 63) / 64 + 1;
+	return alignUp(2 * nb * 4 * 8 + 2 * nb * sizeof(GcK3Block) + (size_t)K3_STORE_CAP * sizeof(GcK3Block) + (size_t)K3_COL_CAP * 4 + (size_t)K3_STACK_CAP * sizeof(GcK3Frame) + 64, 128);
+}
+
+// one thread = one edlib NW distance
+__global__ void __launch_bounds__(64) gc_k3_distance_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK3Out* out)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	GcK3Desc d = descs[t];
+	GcK3Out o; o.status = GC_OK; o.opsLen = 0; o.pad = 0; o.blocks = 0;
+	int32_t nb = (d.q + 63) / 64; if (nb < 1) nb = 1;
+	uint64_t* peq = (uint64_t*)(arena + d.wsOff);
+	GcK3Block* blocks = (GcK3Block*)(peq + 4 * (size_t)nb);
+	gc_k3_build_peq(seq + d.qOff, d.q, peq, nb);
+	uint64_t work = 0;
+	o.distance = gc_k3_distance(peq, nb, d.q, seq + d.tOff, d.t, blocks, d.kHint, work);
+	o.blocks = work;
+	out[d.resultIndex] = o;
+}
+
+// one thread = one edlib NW path (Hirschberg + leaf tracebacks) for a known distance
+__global__ void __launch_bounds__(64) gc_k3_path_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint8_t* opsArena, GcK3Out* out)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	GcK3Desc d = descs[t];
+	GcK3Out o = out[d.resultIndex];
+	int32_t nb = (d.q + 63) / 64; if (nb < 1) nb = 1;
+	uint8_t* base = arena + d.wsOff;
+	uint64_t* peq = (uint64_t*)base;
+	uint64_t* rpeq = peq + 4 * (size_t)nb;
+	GcK3Block* blocksA = (GcK3Block*)(rpeq + 4 * (size_t)nb);
+	GcK3Block* blocksB = blocksA + nb;
+	GcK3Block* store = blocksB + nb;
+	uint32_t* colStart = (uint32_t*)(store + K3_STORE_CAP);
+	GcK3Frame* stack = (GcK3Frame*)(colStart + K3_COL_CAP);
+	const uint8_t* query = seq + d.qOff;
+	gc_k3_build_peq(query, d.q, peq, nb);
+	for (int32_t b = 0; b < 4 * nb; b++) rpeq[b] = 0;
+	for (int32_t i = 0; i < d.q; i++)
+	{
+		uint8_t c = query[d.q - 1 - i];
+		if (c < 4) rpeq[(int32_t)c * nb + (i >> 6)] |= 1ULL << (i & 63);
+	}
+	GcK3PathWorkspace w;
+	w.peq = peq; w.rpeq = rpeq; w.nbTotal = nb; w.qTotal = d.q; w.tTotal = d.t;
+	w.blocksA = blocksA; w.blocksB = blocksB; w.store = store; w.colStart = colStart; w.storeCap = K3_STORE_CAP; w.colCap = K3_COL_CAP; w.stack = stack; w.stackCap = K3_STACK_CAP;
+	uint64_t work = 0;
+	uint32_t nOps = 0;
+	bool ok = gc_k3_path(w, seq + d.tOff, d.best, opsArena + d.opsOff, nOps, d.opsCap, work);
+	o.opsLen = ok ? nOps : 0;
+	if (!ok) o.status = GC_INTERNAL;
+	o.blocks += work;
+	out[d.resultIndex] = o;
+}
+
+struct GcByteCopyDesc { uint64_t src; uint64_t dst; uint32_t len; uint32_t pad; };
+__global__ void gc_bytes_gather_kernel(const GcByteCopyDesc* __restrict__ descs, uint32_t n, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst)
+{
+	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t lane = threadIdx.x & 31;
+	if (warp >= n) return;
+	GcByteCopyDesc d = descs[warp];
+	for (uint32_t i = lane; i < d.len; i += 32) dst[d.dst + i] = src[d.src + i];
+}
+
+extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, const gcgpu_nw_item* items, uint32_t n,
+	gcgpu_nw_result* results, uint8_t* ops, uint64_t ops_capacity, uint64_t* ops_used)
+{
+	if (!ctx || (!items && n) || (!results && n) || !ops_used) return setError(GCGPU_ERR_ARG, "gcgpu_nw: null argument");
+	*ops_used = 0;
+	ctx->lastKernelMs = 0;
+	if (n == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const gcgpu_nw_item& it = items[i];
+		if (it.query_len < 0 || it.target_len < 0 || it.query_offset + (uint64_t)it.query_len > seq_bytes || it.target_offset + (uint64_t)it.target_len > seq_bytes)
+			return setError(GCGPU_ERR_ARG, "gcgpu_nw: item " + std::to_string(i) + " out of range");
+	}
+	CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
+	float ms = 0;
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (seq_bytes)
+	{
+		CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		gc_k3_encode_kernel<<<1184, 256, 0, ctx->stream>>>((uint8_t*)ctx->seqBuf.p, seq_bytes);
+		ctx->launches++;
+	}
+	// ---- distance pass, longest first
+	std::vector<uint32_t> order(n);
+	for (uint32_t i = 0; i < n; i++) order[i] = i;
+	std::sort(order.begin(), order.end(), [items](uint32_t a, uint32_t b) { int64_t wa = (int64_t)items[a].query_len + items[a].target_len, wb = (int64_t)items[b].query_len + items[b].target_len; return wa != wb ? wa > wb : a < b; });
+	std::vector<GcK3Desc> descs(n);
+	size_t wsTotal = 0;
+	for (uint32_t k = 0; k < n; k++)
+	{
+		const gcgpu_nw_item& it = items[order[k]];
+		GcK3Desc& d = descs[k];
+		d.qOff = it.query_offset; d.tOff = it.target_offset; d.q = it.query_len; d.t = it.target_len; d.kHint = it.k_hint; d.best = 0;
+		d.resultIndex = order[k]; d.opsCap = 0; d.opsOff = 0;
+		d.wsOff = wsTotal;
+		wsTotal += k3DistWorkspaceBytes(it.query_len);
+	}
+	CUDA_TRY(ctx->arena.ensure(wsTotal));
+	CUDA_TRY(ctx->descBuf.ensure((size_t)n * sizeof(GcK3Desc)));
+	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK3Out)));
+	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+	gc_k3_distance_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	std::vector<GcK3Out> hout(n);
+	CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs += ms;
+	// ---- path pass for the items that asked for it
+	std::vector<uint32_t> want;
+	for (uint32_t k = 0; k < n; k++) if (items[order[k]].want_path && items[order[k]].query_len > 0 && items[order[k]].target_len > 0) want.push_back(order[k]);
+	std::vector<uint64_t> opsOffOfItem(n, 0);
+	if (!want.empty())
+	{
+		std::vector<GcK3Desc> pd(want.size());
+		size_t ws = 0; uint64_t opsTotal = 0;
+		for (size_t k = 0; k < want.size(); k++)
+		{
+			const gcgpu_nw_item& it = items[want[k]];
+			GcK3Desc& d = pd[k];
+			d.qOff = it.query_offset; d.tOff = it.target_offset; d.q = it.query_len; d.t = it.target_len; d.kHint = 0; d.best = hout[want[k]].distance;
+			d.resultIndex = want[k];
+			d.opsCap = (uint32_t)(it.query_len + it.target_len + 8);
+			d.opsOff = opsTotal; opsOffOfItem[want[k]] = opsTotal; opsTotal += d.opsCap;
+			d.wsOff = ws; ws += k3PathWorkspaceBytes(it.query_len);
+		}
+		CUDA_TRY(ctx->arena.ensure(ws));
+		CUDA_TRY(ctx->traceArena.ensure(opsTotal + 16));
+		CUDA_TRY(ctx->descBuf.ensure(pd.size() * sizeof(GcK3Desc)));
+		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+		uint32_t m = (uint32_t)pd.size();
+		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+		gc_k3_path_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
+		ctx->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		ctx->lastKernelMs += ms;
+	}
+	uint64_t used = 0;
+	bool internal = false;
+	std::vector<GcByteCopyDesc> copies;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		results[i].status = hout[i].status == GC_OK ? 0 : GCGPU_ITEM_INTERNAL;
+		if (results[i].status) internal = true;
+		results[i].distance = hout[i].distance;
+		results[i].ops_len = hout[i].opsLen;
+		results[i].reserved = 0;
+		results[i].ops_offset = used;
+		results[i].blocks = hout[i].blocks;
+		if (hout[i].opsLen)
+		{
+			GcByteCopyDesc c; c.src = opsOffOfItem[i]; c.dst = used; c.len = hout[i].opsLen; c.pad = 0;
+			copies.push_back(c);
+			used += hout[i].opsLen;
+		}
+	}
+	*ops_used = used;
+	if (used > ops_capacity) return setError(GCGPU_ERR_ARG, "gcgpu_nw: ops buffer too small, need " + std::to_string(used) + " bytes");
+	if (used)
+	{
+		if (!ops) return setError(GCGPU_ERR_ARG, "gcgpu_nw: null ops buffer");
+		CUDA_TRY(ctx->compact.ensure(used + 16));
+		CUDA_TRY(ctx->copyDesc.ensure(copies.size() * sizeof(GcByteCopyDesc)));
+		CUDA_TRY(cudaMemcpyAsync(ctx->copyDesc.p, copies.data(), copies.size() * sizeof(GcByteCopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+		uint32_t m = (uint32_t)copies.size();
+		gc_bytes_gather_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const GcByteCopyDesc*)ctx->copyDesc.p, m, (const uint8_t*)ctx->traceArena.p, (uint8_t*)ctx->compact.p);
+		ctx->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(ops, ctx->compact.p, used, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	}
+	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_nw: an alignment path could not be reconstructed");
+	return GCGPU_OK;
+}
+
+// ------------------------------------------------------------------ K2 kernel
+// One block = one read.  Anchors are evaluated by increasing y; for each anchor the threads
+// stride over its candidate predecessors and a block-wide max picks (value, index).
+#define GC_K2_THREADS 128
+__global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m, const GcAnchor* __restrict__ anchors, const uint64_t* __restrict__ readOffsets, uint32_t numReads,
+	uint32_t* order, int32_t* score, int32_t* pred, uint32_t* chain, uint32_t* chainLen, int64_t* chainScore)
+{
+	uint32_t r = blockIdx.x;
+	if (r >= numReads) return;
+	uint64_t base = readOffsets[r];
+	uint32_t n = (uint32_t)(readOffsets[r + 1] - base);
+	const GcAnchor* a = anchors + base;
+	uint32_t* ord = order + base;
+	int32_t* sc = score + base;
+	int32_t* pr = pred + base;
+	__shared__ long long warpBest[GC_K2_THREADS / 32];
+	__shared__ long long blockBest;
+	// rank sort by (y, index)
+	for (uint32_t j = threadIdx.x; j < n; j += blockDim.x)
+	{
+		uint32_t rank = 0;
+		int32_t yj = a[j].y;
+		for (uint32_t i = 0; i < n; i++) { int32_t yi = a[i].y; rank += (yi < yj || (yi == yj && i < j)) ? 1 : 0; }
+		ord[rank] = j;
+	}
+	__syncthreads();
+	for (uint32_t oj = 0; oj < n; oj++)
+	{
+		uint32_t j = ord[oj];
+		GcAnchor aj = a[j];
+		uint32_t cj = m.compMap[aj.endNode];
+		long long best = gc_k2_key(aj.y - aj.x + 1, -1);
+		for (uint32_t oi = threadIdx.x; oi < oj; oi += blockDim.x)
+		{
+			uint32_t i = ord[oi];
+			GcAnchor ai = a[i];
+			if (ai.y >= aj.y) continue;
+			if (m.compMap[ai.endNode] != cj) continue;
+			long long key = gc_k2_candidate(m, ai, aj, i, sc[i]);
+			if (key > best) best = key;
+		}
+		for (int off = 16; off > 0; off >>= 1) { long long o = __shfl_down_sync(0xFFFFFFFFu, best, off); if (o > best) best = o; }
+		if ((threadIdx.x & 31) == 0) warpBest[threadIdx.x >> 5] = best;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			long long b = warpBest[0];
+			for (int w = 1; w < GC_K2_THREADS / 32; w++) if (warpBest[w] > b) b = warpBest[w];
+			blockBest = b;
+			sc[j] = (int32_t)(b >> 32);
+			pr[j] = (int32_t)(uint32_t)(b & 0xFFFFFFFFu) - 1;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		long long bs = 0;
+		chainLen[r] = gc_k2_select(m, a, n, sc, pr, chain + base, (int64_t*)&bs);
+		chainScore[r] = bs;
+	}
+}
+
+extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* read_offsets, uint32_t num_reads, uint32_t* chain, uint32_t* chain_len, int64_t* chain_score)
+{
+	if (!ctx || !read_offsets || (!chain_len && num_reads) || (!chain_score && num_reads)) return setError(GCGPU_ERR_ARG, "gcgpu_chain: null argument");
+	if (!ctx->haveMpc) return setError(GCGPU_ERR_ARG, "gcgpu_chain: the context was created without an MPC index");
+	ctx->lastKernelMs = 0;
+	if (num_reads == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	uint64_t total = read_offsets[num_reads];
+	if (total && (!anchors || !chain)) return setError(GCGPU_ERR_ARG, "gcgpu_chain: null anchor/chain buffer");
+	for (uint64_t i = 0; i < total; i++) if (anchors[i].start_node >= ctx->numNodes || anchors[i].end_node >= ctx->numNodes) return setError(GCGPU_ERR_ARG, "gcgpu_chain: anchor node out of range");
+	static_assert(sizeof(gcgpu_anchor) == sizeof(GcAnchor), "anchor layout");
+	// layout in arena: anchors | offsets | order | score | pred | chain | chainLen | chainScore
+	size_t offA = 0, offO = alignUp(offA + total * sizeof(GcAnchor), 128), offOrd = alignUp(offO + ((size_t)num_reads + 1) * 8, 128), offSc = alignUp(offOrd + total * 4, 128), offPr = alignUp(offSc + total * 4, 128);
+	size_t offCh = alignUp(offPr + total * 4, 128), offLen = alignUp(offCh + total * 4, 128), offScore = alignUp(offLen + (size_t)num_reads * 4, 128), end = offScore + (size_t)num_reads * 8;
+	CUDA_TRY(ctx->arena.ensure(end));
+	uint8_t* A = (uint8_t*)ctx->arena.p;
+	if (total) CUDA_TRY(cudaMemcpyAsync(A + offA, anchors, total * sizeof(GcAnchor), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(cudaMemcpyAsync(A + offO, read_offsets, ((size_t)num_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	gc_k2_chain_kernel<<<num_reads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads,
+		(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	if (total) CUDA_TRY(cudaMemcpyAsync(chain, A + offCh, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaMemcpyAsync(chain_len, A + offLen, (size_t)num_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaMemcpyAsync(chain_score, A + offScore, (size_t)num_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	float ms = 0;
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs = ms;
 	return GCGPU_OK;
 }

@@ -72,6 +72,10 @@ class ParamsStruct(C.Structure):
 EXT_ITEM = np.dtype([("seq_offset", "<u8"), ("seq_len", "<i4"), ("node", "<u4"), ("offset", "<u4"), ("reserved", "<u4")])
 EXT_RESULT = np.dtype([("status", "<i4"), ("score", "<i4"), ("trace_len", "<u4"), ("reserved", "<u4"), ("trace_offset", "<u8"), ("columns", "<u8")])
 
+NW_ITEM = np.dtype([("query_offset", "<u8"), ("target_offset", "<u8"), ("query_len", "<i4"), ("target_len", "<i4"), ("k_hint", "<i4"), ("want_path", "<i4")])
+NW_RESULT = np.dtype([("status", "<i4"), ("distance", "<i4"), ("ops_len", "<u4"), ("reserved", "<u4"), ("ops_offset", "<u8"), ("blocks", "<u8")])
+ANCHOR = np.dtype([("start_node", "<u4"), ("end_node", "<u4"), ("x", "<i4"), ("y", "<i4")])
+
 _lib = None
 
 
@@ -91,6 +95,10 @@ def load() -> C.CDLL:
     lib.gcgpu_destroy.restype = None
     lib.gcgpu_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.gcgpu_extend.restype = C.c_int
+    lib.gcgpu_nw.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.gcgpu_nw.restype = C.c_int
+    lib.gcgpu_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gcgpu_chain.restype = C.c_int
     lib.gcgpu_last_kernel_ms.argtypes = [C.c_void_p]
     lib.gcgpu_last_kernel_ms.restype = C.c_float
     lib.gcgpu_launch_count.argtypes = [C.c_void_p]
@@ -185,6 +193,34 @@ class Context:
         if rc != 0 and not (allow_internal and rc == -4):
             raise GcgpuError(f"gcgpu_extend failed ({rc}): {self.lib.gcgpu_last_error().decode()}")
         return results, traces[:used.value]
+
+    def nw(self, seqs: bytes, items: np.ndarray):
+        """K3: batch of edlib-style NW alignments over raw characters; returns (results, ops)."""
+        buf = np.frombuffer(seqs, dtype=np.uint8) if isinstance(seqs, (bytes, bytearray)) else np.ascontiguousarray(seqs, dtype=np.uint8)
+        items = np.ascontiguousarray(items, dtype=NW_ITEM)
+        n = len(items)
+        results = np.zeros(n, dtype=NW_RESULT)
+        want = items["want_path"] != 0
+        cap = int((items["query_len"].astype(np.int64) + items["target_len"] + 8)[want].sum()) + 1
+        ops = np.zeros(cap, dtype=np.uint8)
+        used = C.c_uint64(0)
+        rc = self.lib.gcgpu_nw(self.handle, _ptr(buf), buf.size, _ptr(items), n, _ptr(results), _ptr(ops), cap, C.byref(used))
+        if rc != 0:
+            raise GcgpuError(f"gcgpu_nw failed ({rc}): {self.lib.gcgpu_last_error().decode()}")
+        return results, ops[:used.value]
+
+    def chain(self, anchors: np.ndarray, read_offsets: np.ndarray):
+        """K2: co-linear chaining per read; returns (chain, chain_len, chain_score)."""
+        anchors = np.ascontiguousarray(anchors, dtype=ANCHOR)
+        read_offsets = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        nreads = len(read_offsets) - 1
+        chain = np.zeros(max(1, len(anchors)), dtype=np.uint32)
+        chain_len = np.zeros(max(1, nreads), dtype=np.uint32)
+        chain_score = np.zeros(max(1, nreads), dtype=np.int64)
+        rc = self.lib.gcgpu_chain(self.handle, _ptr(anchors), _ptr(read_offsets), nreads, _ptr(chain), _ptr(chain_len), _ptr(chain_score))
+        if rc != 0:
+            raise GcgpuError(f"gcgpu_chain failed ({rc}): {self.lib.gcgpu_last_error().decode()}")
+        return chain, chain_len[:nreads], chain_score[:nreads]
 
     @property
     def last_kernel_ms(self) -> float:

@@ -132,6 +132,58 @@ typedef struct gcgpu_ext_result
 int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
                  gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used);
 
+
+/* ---- K3: global (NW) sequence alignment, Myers bit-vector ------------------------------
+ * One item replaces one call of
+ *   edlibAlign(query, qlen, target, tlen, edlibNewAlignConfig(-1, EDLIB_MODE_NW, task, NULL, 0))
+ * (edlib/include/edlib.h, edlib/src/edlib.cpp:141-296) as made at src/Aligner.cpp:645
+ * (TASK_DISTANCE, query = whole-read path) and src/Aligner.cpp:845 (TASK_PATH, query =
+ * chained path, target = read).  `seqs` holds raw characters (compared byte-wise like edlib,
+ * only upper-case A C G T can match).  want_path != 0 also returns the edit operations
+ * 0 match / 1 insert / 2 delete / 3 mismatch (EDLIB_EDOP_*), identical to edlib's.         */
+typedef struct gcgpu_nw_item
+{
+	uint64_t query_offset;
+	uint64_t target_offset;
+	int32_t query_len;
+	int32_t target_len;
+	int32_t k_hint;       /* optional first band guess (<= 0: start at 64 like edlib)      */
+	int32_t want_path;
+} gcgpu_nw_item;
+
+typedef struct gcgpu_nw_result
+{
+	int32_t status;       /* 0 ok, 5 internal */
+	int32_t distance;     /* EdlibAlignResult::editDistance */
+	uint32_t ops_len;     /* EdlibAlignResult::alignmentLength */
+	uint32_t reserved;
+	uint64_t ops_offset;  /* into the ops buffer */
+	uint64_t blocks;      /* work counter: 64-row block column steps */
+} gcgpu_nw_result;
+
+int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, const gcgpu_nw_item* items, uint32_t n,
+             gcgpu_nw_result* results, uint8_t* ops, uint64_t ops_capacity, uint64_t* ops_used);
+
+/* ---- K2: co-linear chaining over the minimum path cover ---------------------------------
+ * One read replaces one call of
+ *   AlignmentGraph::colinearChaining(const std::vector<Anchor>&, long long sep_limit)
+ * (src/AlignmentGraph.h:121, src/AlignmentGraph.cpp:1712-1863; sep_limit is not read by the
+ * reference).  An anchor is given by the split nodes of Anchor::path.front()/back() and its
+ * fragment bounds x,y (src/Aligner.cpp:707).  Anchors of read r are
+ * anchors[read_offsets[r] .. read_offsets[r+1]); the chain (anchor indices local to the read,
+ * in read order) is written at chain[read_offsets[r] ..] with its length in chain_len[r]
+ * and the covered-bases score in chain_score[r].                                            */
+typedef struct gcgpu_anchor
+{
+	uint32_t start_node;
+	uint32_t end_node;
+	int32_t x;
+	int32_t y;
+} gcgpu_anchor;
+
+int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* read_offsets, uint32_t num_reads,
+                uint32_t* chain, uint32_t* chain_len, int64_t* chain_score);
+
 /* device time of the kernels of the last call on this ctx, in milliseconds (CUDA events) */
 float gcgpu_last_kernel_ms(gcgpu_ctx* ctx);
 /* number of kernel launches issued by this ctx so far */
