@@ -1,0 +1,241 @@
+// S7: final traces -> vg::Alignment messages -> GAM / JSON records.
+//   GraphAlignerVGAlignment::traceToAlignment        (src/GraphAlignerVGAlignment.h:37-165)
+//   GraphAligner::AddAlignment                       (src/GraphAligner.h:205-212)
+//   replaceDigraphNodeIdsWithOriginalNodeIds         (src/Aligner.cpp:152-165)
+//   writeGAMToQueue / writeJSONToQueue               (src/Aligner.cpp:261-298)
+// protobuf is not available in this image, so the proto3 wire format of the few messages
+// involved (src/vg.proto:52-126) is written by hand; GAM framing = one gzip member per read
+// holding varint64 count + {varint32 size, message}* (src/stream.hpp:24-51).
+#pragma once
+#include <zlib.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "gc_pipeline.h"
+
+namespace gcout {
+
+struct Edit { int32_t from_length = 0, to_length = 0; std::string sequence; };
+struct Mapping { int64_t node_id = 0, offset = 0; bool is_reverse = false; std::string name; std::vector<Edit> edits; int64_t rank = 0; };
+struct Alignment { std::string sequence, name; std::vector<Mapping> mappings; int32_t score = 0, query_position = 0; double identity = 0; };
+
+inline bool characterMatch(char sequenceCharacter, char graphCharacter)
+{
+	// Common::characterMatch (GraphAlignerCommon.h:193-217) restricted to graphs without ambiguous bases
+	if (sequenceCharacter == graphCharacter) return true;
+	uint8_t m = gcEncodeBase(sequenceCharacter);
+	int b = graphCharacter == 'A' ? 0 : graphCharacter == 'C' ? 1 : graphCharacter == 'G' ? 2 : graphCharacter == 'T' ? 3 : -1;
+	if (sequenceCharacter == '-' || b < 0) return false;
+	return (m >> b) & 1;
+}
+
+// traceToAlignment + AddAlignment + replaceDigraphNodeIdsWithOriginalNodeIds
+inline Alignment toAlignment(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const GcAlnItem& item)
+{
+	enum EditType { Match, Mismatch, Insertion, Deletion, Empty };
+	const std::vector<GcTraceItem>& trace = item.trace;
+	Alignment result;
+	result.name = seq_id;
+	result.score = item.traceScore;
+	int curNode = trace[0].node; bool curReverse = (trace[0].node % 2) == 1; size_t curOffset = trace[0].nodeOffset;
+	int rank = 0;
+	result.mappings.emplace_back();
+	Mapping* vgmapping = &result.mappings.back();
+	vgmapping->rank = rank;
+	vgmapping->edits.emplace_back();
+	Edit* edit = &vgmapping->edits.back();
+	EditType currentEdit = Empty;
+	size_t mismatches = 0, deletions = 0, insertions = 0, matches = 0;
+	if (characterMatch(trace[0].sequenceCharacter, trace[0].graphCharacter))
+	{
+		currentEdit = Match; edit->from_length++; edit->to_length++; matches++;
+	}
+	else
+	{
+		currentEdit = Mismatch; edit->from_length++; edit->to_length++;
+		edit->sequence = std::string { sequence[0] }; // sic: sequence[0], GraphAlignerVGAlignment.h:75
+		mismatches++;
+	}
+	vgmapping->node_id = curNode; vgmapping->is_reverse = curReverse; vgmapping->offset = (int64_t)curOffset;
+	for (size_t pos = 1; pos < trace.size(); pos++)
+	{
+		int newNode = trace[pos].node; bool newReverse = (trace[pos].node % 2) == 1; size_t newOffset = trace[pos].nodeOffset;
+		bool insideNode = !trace[pos - 1].nodeSwitch || (newNode == curNode && newReverse == curReverse && newOffset > curOffset);
+		if (!insideNode)
+		{
+			rank++;
+			curNode = newNode; curReverse = newReverse; curOffset = newOffset;
+			result.mappings.emplace_back();
+			vgmapping = &result.mappings.back();
+			vgmapping->rank = rank;
+			vgmapping->offset = (int64_t)curOffset; vgmapping->node_id = curNode; vgmapping->is_reverse = curReverse;
+			vgmapping->edits.emplace_back();
+			edit = &vgmapping->edits.back();
+			currentEdit = Empty;
+		}
+		if (trace[pos - 1].seqPos == trace[pos].seqPos)
+		{
+			if (currentEdit == Empty) currentEdit = Deletion;
+			if (currentEdit != Deletion) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Deletion; }
+			edit->from_length++;
+			deletions++;
+		}
+		else if (insideNode && trace[pos - 1].nodeOffset == trace[pos].nodeOffset)
+		{
+			if (currentEdit == Empty) currentEdit = Insertion;
+			if (currentEdit != Insertion) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Insertion; }
+			edit->to_length++;
+			edit->sequence += trace[pos].sequenceCharacter;
+			insertions++;
+		}
+		else if (characterMatch(trace[pos].sequenceCharacter, trace[pos].graphCharacter))
+		{
+			if (currentEdit == Empty) currentEdit = Match;
+			if (currentEdit != Match) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Match; }
+			edit->from_length++; edit->to_length++;
+			matches++;
+		}
+		else
+		{
+			if (currentEdit == Empty) currentEdit = Mismatch;
+			if (currentEdit != Mismatch) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Mismatch; }
+			edit->from_length++; edit->to_length++;
+			edit->sequence += trace[pos].sequenceCharacter;
+			mismatches++;
+		}
+	}
+	result.identity = (double)matches / (double)(matches + mismatches + insertions + deletions);
+	// AddAlignment (GraphAligner.h:210-211)
+	result.sequence = sequence.substr(item.alignmentStart, item.alignmentEnd - item.alignmentStart);
+	result.query_position = (int32_t)item.alignmentStart;
+	// replaceDigraphNodeIdsWithOriginalNodeIds (Aligner.cpp:152-165)
+	for (Mapping& m : result.mappings)
+	{
+		int digraphNodeId = (int)m.node_id;
+		m.node_id = digraphNodeId / 2;
+		m.name = g.originalNodeName(digraphNodeId);
+	}
+	return result;
+}
+
+// ---- proto3 wire encoding (vg.proto:52-126)
+inline void putVarint(std::string& out, uint64_t v) { while (v >= 0x80) { out.push_back((char)((v & 0x7F) | 0x80)); v >>= 7; } out.push_back((char)v); }
+inline void putTag(std::string& out, int field, int wire) { putVarint(out, ((uint64_t)field << 3) | (uint64_t)wire); }
+inline void putInt(std::string& out, int field, int64_t v) { if (v == 0) return; putTag(out, field, 0); putVarint(out, (uint64_t)v); }
+inline void putStr(std::string& out, int field, const std::string& s) { if (s.empty()) return; putTag(out, field, 2); putVarint(out, s.size()); out += s; }
+inline void putMsg(std::string& out, int field, const std::string& s) { putTag(out, field, 2); putVarint(out, s.size()); out += s; }
+
+inline std::string serialize(const Alignment& a)
+{
+	std::string path;
+	for (const Mapping& m : a.mappings)
+	{
+		std::string mm, pos;
+		putInt(pos, 1, m.node_id); putInt(pos, 2, m.offset); if (m.is_reverse) { putTag(pos, 4, 0); putVarint(pos, 1); } putStr(pos, 5, m.name);
+		putMsg(mm, 1, pos);
+		for (const Edit& e : m.edits) { std::string ee; putInt(ee, 1, e.from_length); putInt(ee, 2, e.to_length); putStr(ee, 3, e.sequence); putMsg(mm, 2, ee); }
+		putInt(mm, 5, m.rank);
+		putMsg(path, 2, mm);
+	}
+	std::string out;
+	putStr(out, 1, a.sequence);
+	putMsg(out, 2, path);
+	putStr(out, 3, a.name);
+	putInt(out, 6, a.score);
+	putInt(out, 7, a.query_position);
+	uint64_t bits; std::memcpy(&bits, &a.identity, 8);
+	if (bits != 0) { putTag(out, 16, 1); for (int i = 0; i < 8; i++) out.push_back((char)((bits >> (8 * i)) & 0xFF)); }
+	return out;
+}
+
+inline std::string gzipMember(const std::string& raw)
+{
+	z_stream zs; std::memset(&zs, 0, sizeof(zs));
+	deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+	std::string out;
+	out.resize(deflateBound(&zs, raw.size()) + 32);
+	zs.next_in = (Bytef*)raw.data(); zs.avail_in = (uInt)raw.size();
+	zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
+	deflate(&zs, Z_FINISH);
+	out.resize(out.size() - zs.avail_out);
+	deflateEnd(&zs);
+	return out;
+}
+
+// one read's GAM record (writeGAMToQueue, Aligner.cpp:261-281)
+inline std::string gamRecord(const std::vector<Alignment>& alns)
+{
+	std::string raw;
+	putVarint(raw, alns.size());
+	for (const Alignment& a : alns) { std::string s = serialize(a); putVarint(raw, s.size()); raw += s; }
+	return gzipMember(raw);
+}
+
+inline std::string jsonEscape(const std::string& s)
+{
+	std::string r = "\"";
+	for (unsigned char c : s)
+	{
+		if (c == '"') r += "\\\""; else if (c == '\\') r += "\\\\"; else if (c == '\n') r += "\\n"; else if (c == '\t') r += "\\t"; else if (c == '\r') r += "\\r";
+		else if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); r += b; } else r.push_back((char)c);
+	}
+	return r + "\"";
+}
+inline std::string jsonDouble(double d)
+{
+	char b[64];
+	for (int prec = 15; prec <= 17; prec++) { snprintf(b, sizeof(b), "%.*g", prec, d); if (strtod(b, nullptr) == d) break; }
+	return b;
+}
+// MessageToJsonString with preserve_proto_field_names (Aligner.cpp:283-298): one line per alignment
+inline std::string jsonLine(const Alignment& a)
+{
+	std::string o = "{";
+	bool first = true;
+	auto sep = [&o](bool& f) { if (!f) o += ","; f = false; };
+	if (!a.sequence.empty()) { sep(first); o += "\"sequence\":" + jsonEscape(a.sequence); }
+	sep(first); o += "\"path\":{";
+	if (!a.mappings.empty())
+	{
+		o += "\"mapping\":[";
+		for (size_t i = 0; i < a.mappings.size(); i++)
+		{
+			if (i) o += ",";
+			const Mapping& m = a.mappings[i];
+			o += "{\"position\":{"; bool qf = true;
+			if (m.node_id) { sep(qf); o += "\"node_id\":\"" + std::to_string(m.node_id) + "\""; }
+			if (m.offset) { sep(qf); o += "\"offset\":\"" + std::to_string(m.offset) + "\""; }
+			if (m.is_reverse) { sep(qf); o += "\"is_reverse\":true"; }
+			if (!m.name.empty()) { sep(qf); o += "\"name\":" + jsonEscape(m.name); }
+			o += "}";
+			if (!m.edits.empty())
+			{
+				o += ",\"edit\":[";
+				for (size_t e = 0; e < m.edits.size(); e++)
+				{
+					if (e) o += ",";
+					o += "{"; bool ef = true;
+					if (m.edits[e].from_length) { sep(ef); o += "\"from_length\":" + std::to_string(m.edits[e].from_length); }
+					if (m.edits[e].to_length) { sep(ef); o += "\"to_length\":" + std::to_string(m.edits[e].to_length); }
+					if (!m.edits[e].sequence.empty()) { sep(ef); o += "\"sequence\":" + jsonEscape(m.edits[e].sequence); }
+					o += "}";
+				}
+				o += "]";
+			}
+			if (m.rank) o += ",\"rank\":\"" + std::to_string(m.rank) + "\"";
+			o += "}";
+		}
+		o += "]";
+	}
+	o += "}";
+	if (!a.name.empty()) { sep(first); o += "\"name\":" + jsonEscape(a.name); }
+	if (a.score) { sep(first); o += "\"score\":" + std::to_string(a.score); }
+	if (a.query_position) { sep(first); o += "\"query_position\":" + std::to_string(a.query_position); }
+	if (a.identity != 0) { sep(first); o += "\"identity\":" + jsonDouble(a.identity); }
+	o += "}";
+	return o;
+}
+
+}

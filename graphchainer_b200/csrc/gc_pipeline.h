@@ -1,0 +1,773 @@
+// Host driver of the per-read pipeline: the body of runComponentMappings
+// (src/Aligner.cpp:492-1062, colinear mode) re-organised for batches of reads, with the
+// three dynamic-programming stages delegated to libgcgpu through its C ABI:
+//   S0  seeding + clustering               host   (gc_seeder.h)
+//   S1  whole-read seed-and-extend         host seed loop (GraphAligner.h:114-203) in ROUNDS,
+//                                          extensions = gcgpu_extend (K1)
+//   S1b distance(GA path, read)            gcgpu_nw (K3)                     Aligner.cpp:642-654
+//   S2  fragment anchoring                 all window seeds extended speculatively by one
+//                                          gcgpu_extend call, then the reference's in-order
+//                                          exactAlignmentPart filter      Aligner.cpp:668-730
+//   S3  co-linear chaining                 gcgpu_chain (K2)                  Aligner.cpp:735
+//   S4  chain -> node path                 host BFS getChainPath             Aligner.cpp:748-822
+//   S5  NW(path, read)                     gcgpu_nw (K3): distance for every read, the edit
+//                                          path only when the chained alignment wins (S6)
+//   S6  decision, S7 vg::Alignment         host                              Aligner.cpp:880-1013
+// There is no CPU implementation of K1/K2/K3 here: without libgcgpu nothing aligns.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <vector>
+#include "../../include/gcgpu.h"
+#include "gc_host_graph.h"
+#include "gc_seeder.h"
+
+struct GcRead
+{
+	std::string name;     // full FASTA/FASTQ header after '>' / '@'
+	std::string sequence;
+};
+
+// GraphAlignerCommon::TraceItem (GraphAlignerCommon.h:127-160) after the seqPos/node fix-ups
+struct GcTraceItem
+{
+	int32_t node;          // digraph node id (2*id + strand)
+	uint32_t nodeOffset;   // offset in the original node
+	int64_t seqPos;
+	bool nodeSwitch;
+	char sequenceCharacter;
+	char graphCharacter;
+};
+
+struct GcAlnItem
+{
+	std::vector<GcTraceItem> trace;
+	int32_t traceScore = 0;       // OnewayTrace::score (what AddAlignment serialises)
+	size_t alignmentStart = 0, alignmentEnd = 0;
+	size_t alignmentScore = 0;
+	size_t seedGoodness = 0;
+};
+
+struct GcReadResult
+{
+	std::vector<GcAlnItem> alignments; // final, sorted by alignmentStart
+	bool usedChain = false;            // S6: the chained (CLC) alignment was strictly better
+	bool dropped = false;              // assertion-class failure: the reference drops the read
+	// the fields of the reference's --short-verbose line (Aligner.cpp:909-915)
+	size_t anchors = 0, chained = 0, pathBp = 0, clcScore = 0, longEditDistance = 0;
+	bool hasLong = false;
+	size_t seedsFound = 0, seedsExtended = 0;
+};
+
+struct GcPipelineParams
+{
+	double minimizerSeedDensity = 10;
+	size_t seedClusterMinSize = 1;
+	long long colinearGap = 10000;
+	long long colinearSplitLen = 35;
+	long long colinearSplitGap = 35;
+	bool tryAllSeeds = true;
+};
+
+struct GcPipelineStats
+{
+	uint64_t k1Items = 0, k1Columns = 0, k1Launches = 0;
+	uint64_t k3Items = 0, k3Blocks = 0;
+	uint64_t k2Reads = 0, k2Anchors = 0;
+	double k1Ms = 0, k2Ms = 0, k3Ms = 0;
+	double hostSeedMs = 0, hostS1Ms = 0, hostS2Ms = 0, hostConnectMs = 0;
+	uint64_t s1Rounds = 0;
+};
+
+namespace gcpipe {
+
+inline char complementChar(char c)
+{
+	switch (c)
+	{
+		case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'T': case 't': return 'A'; case 'G': case 'g': return 'C';
+		case 'N': case 'n': return 'N'; case 'U': case 'u': return 'A'; case 'R': case 'r': return 'Y'; case 'Y': case 'y': return 'R';
+		case 'K': case 'k': return 'M'; case 'M': case 'm': return 'K'; case 'S': case 's': return 'S'; case 'W': case 'w': return 'W';
+		case 'B': case 'b': return 'V'; case 'V': case 'v': return 'B'; case 'D': case 'd': return 'H'; case 'H': case 'h': return 'D';
+	}
+	return 0; // the reference asserts (CommonUtils.cpp:131)
+}
+inline uint8_t complementMask(uint8_t m) { return (uint8_t)(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)); }
+
+// exactAlignmentPart (GraphAligner.h:407-461): is the seed cell on the trace of `aln`?
+inline bool exactAlignmentPart(const GcAlnItem& aln, const GcSeedHit& seed, bool& assertion)
+{
+	const std::vector<GcTraceItem>& trace = aln.trace;
+	if (trace.empty() || !(trace.back().seqPos > trace[0].seqPos)) { assertion = true; return false; }
+	int64_t sp = (int64_t)seed.seqPos;
+	if (trace.back().seqPos < sp) return false;
+	if (trace[0].seqPos > sp) return false;
+	// seqPos is non-decreasing with unit steps: find the run of items at seqPos == sp
+	size_t lo = 0, hi = trace.size();
+	while (lo < hi) { size_t mid = (lo + hi) / 2; if (trace[mid].seqPos < sp) lo = mid + 1; else hi = mid; }
+	int compareNode = seed.nodeID * 2 + (seed.reverse ? 1 : 0);
+	for (size_t i = lo; i < trace.size() && trace[i].seqPos == sp; i++)
+		if (trace[i].node == compareNode && trace[i].nodeOffset == seed.nodeOffset) return true;
+	return false;
+}
+
+// AlignmentSelection::alignmentIncompatible (AlignmentSelection.cpp:13-31)
+inline bool alignmentIncompatible(const GcAlnItem& left, const GcAlnItem& right)
+{
+	const float OverlapIncompatibleFractionCutoff = 0.05;
+	auto minOverlapLen = std::min((left.alignmentEnd - left.alignmentStart), (right.alignmentEnd - right.alignmentStart)) * OverlapIncompatibleFractionCutoff;
+	size_t leftStart = left.alignmentStart, leftEnd = left.alignmentEnd, rightStart = right.alignmentStart, rightEnd = right.alignmentEnd;
+	if (leftStart > rightStart) { std::swap(leftStart, rightStart); std::swap(leftEnd, rightEnd); }
+	int overlap = 0;
+	if (leftEnd > rightStart) overlap = leftEnd - rightStart;
+	return overlap > minOverlapLen;
+}
+// GreedySelectAlignments with alignmentLengthCompare (AlignmentSelection.h:36-55, .cpp:45-51)
+inline std::vector<GcAlnItem> selectGreedyLength(const std::vector<GcAlnItem>& alignments)
+{
+	std::vector<size_t> items;
+	for (size_t i = 0; i < alignments.size(); i++) items.push_back(i);
+	std::sort(items.begin(), items.end(), [&alignments](size_t l, size_t r)
+	{
+		const GcAlnItem& left = alignments[l]; const GcAlnItem& right = alignments[r];
+		if ((left.alignmentEnd - left.alignmentStart) > (right.alignmentEnd - right.alignmentStart)) return true;
+		if ((right.alignmentEnd - right.alignmentStart) > (left.alignmentEnd - left.alignmentStart)) return false;
+		if (left.alignmentScore < right.alignmentScore) return true;
+		return false;
+	});
+	std::vector<GcAlnItem> result;
+	for (auto i : items)
+	{
+		if (!std::any_of(result.begin(), result.end(), [&alignments, i](const GcAlnItem& existing) { return alignmentIncompatible(existing, alignments[i]); }))
+			result.push_back(alignments[i]);
+	}
+	return result;
+}
+
+// traceToPoses + traceToSequence (Aligner.cpp:376-408, 425-428): the padded graph path of a GA alignment
+inline std::string traceToSequence(const GcHostGraph& g, const GcAlnItem& aln)
+{
+	std::string ret;
+	size_t lastNode = 0, lastOffset = 0, lastLength = 0;
+	for (size_t j = 0; j < aln.trace.size(); j++)
+	{
+		size_t node = g.unitigNode(aln.trace[j].node, aln.trace[j].nodeOffset);
+		size_t nodeOffset = aln.trace[j].nodeOffset - g.nodeOffset[node];
+		if (j == 0)
+		{
+			lastNode = node; lastOffset = nodeOffset; lastLength = g.nodeLength[node];
+			ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset));
+			lastOffset++;
+		}
+		else
+		{
+			if (node != lastNode)
+			{
+				while (lastOffset < lastLength) { ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset)); lastOffset++; }
+				lastNode = node; lastLength = g.nodeLength[node]; lastOffset = 0;
+			}
+			while (lastOffset <= nodeOffset) { ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset)); lastOffset++; }
+		}
+	}
+	return ret;
+}
+
+struct MatrixPos { size_t node; size_t nodeOffset; size_t seqPos; };
+
+// pathToTrace (Aligner.cpp:409-424), including its single-node quirk
+inline std::vector<MatrixPos> pathToTrace(const GcHostGraph& g, const std::vector<size_t>& path, size_t firstNodeOffset, size_t lastNodeOffset)
+{
+	std::vector<MatrixPos> ret;
+	for (size_t node : path)
+	{
+		size_t S = 0, L = g.nodeLength[node];
+		if (node == path[0]) S = firstNodeOffset;
+		else if (node == path.back()) L = lastNodeOffset + 1;
+		MatrixPos p { node, S, 0 };
+		while (p.nodeOffset < L) { ret.push_back(p); p.nodeOffset++; }
+	}
+	return ret;
+}
+
+// AlignmentGraph::getChainPath (AlignmentGraph.cpp:1866-1916): FIFO BFS with the unsigned distance prune
+struct ChainPathScratch { std::vector<size_t> vis, dis, Q, pre; size_t flag = 1; };
+inline std::vector<size_t> getChainPath(const GcHostGraph& g, ChainPathScratch& s, size_t S, size_t T, long long sep_limit)
+{
+	size_t N = g.numNodes();
+	if (s.vis.size() < N) { s.vis.resize(N, 0); s.pre.resize(N); s.dis.resize(N); s.Q.reserve(1024); }
+	s.Q.clear();
+	s.Q.push_back(S);
+	s.vis[S] = ++s.flag;
+	s.dis[S] = 0;
+	for (size_t i = 0; s.vis[T] != s.flag && i < s.Q.size(); )
+	{
+		size_t v = s.Q[i++];
+		if (s.dis[v] > (size_t)sep_limit) continue; // size_t vs long long comparison, AlignmentGraph.cpp:1897
+		for (uint32_t e = g.outStart[v]; e < g.outStart[v + 1]; e++)
+		{
+			size_t t = g.outNbr[e];
+			if (s.vis[t] != s.flag)
+			{
+				s.Q.push_back(t);
+				s.vis[t] = s.flag;
+				s.dis[t] = s.dis[v] + g.nodeLength[t];
+				s.pre[t] = v;
+			}
+		}
+	}
+	std::vector<size_t> tmp;
+	if (s.vis[T] != s.flag) return tmp;
+	for (size_t i = T; i != S; i = s.pre[i]) tmp.push_back(i);
+	tmp.push_back(S);
+	std::reverse(tmp.begin(), tmp.end());
+	return tmp;
+}
+
+}
+
+class GcPipeline
+{
+public:
+	GcPipeline(const GcHostGraph& graph, gcgpu_ctx* ctx, const GcPipelineParams& params) : g(graph), ctx(ctx), params(params) {}
+	GcPipelineStats stats;
+
+	void alignBatch(const std::vector<GcRead>& reads, std::vector<GcReadResult>& out);
+
+private:
+	const GcHostGraph& g;
+	gcgpu_ctx* ctx;
+	GcPipelineParams params;
+
+	struct ExtRef { int32_t item[2]; }; // indices of the backward / forward work items, -1 if absent
+	struct Batch
+	{
+		std::vector<uint8_t> codes;          // per read: forward masks then reverse-complement masks
+		std::vector<uint64_t> fwdOff, rcOff; // offsets into codes
+	};
+
+	void check(int rc, const char* what)
+	{
+		if (rc != GCGPU_OK) throw std::runtime_error(std::string(what) + " failed: " + gcgpu_last_error());
+	}
+
+	// the two K1 work items of one seed (getTwoDirectionalTrace, GraphAligner.h:480-525).
+	// seqStart/seqLen delimit `sequence` inside the read (whole read, or one fragment).
+	ExtRef makeItems(const Batch& b, size_t r, size_t readLen, size_t seqStart, size_t seqLen, const GcSeedHit& seed, std::vector<gcgpu_ext_item>& items) const
+	{
+		ExtRef ref; ref.item[0] = ref.item[1] = -1;
+		int forwardNodeId = seed.nodeID * 2 + (seed.reverse ? 1 : 0);
+		if (seed.seqPos > 0)
+		{
+			auto reversePos = g.reversePosition(forwardNodeId, seed.nodeOffset);
+			uint32_t node = g.unitigNode(reversePos.first, reversePos.second);
+			gcgpu_ext_item it;
+			// revcomp(sequence) = rc(read)[readLen - seqStart - seqLen, readLen - seqStart); its last seqPos characters
+			it.seq_offset = b.rcOff[r] + (readLen - seqStart - seed.seqPos);
+			it.seq_len = (int32_t)seed.seqPos;
+			it.node = node;
+			it.offset = (uint32_t)(reversePos.second - g.nodeOffset[node]);
+			it.reserved = 0;
+			ref.item[0] = (int32_t)items.size();
+			items.push_back(it);
+		}
+		if (seed.seqPos < seqLen - 1)
+		{
+			uint32_t node = g.unitigNode(forwardNodeId, seed.nodeOffset);
+			gcgpu_ext_item it;
+			it.seq_offset = b.fwdOff[r] + seqStart + seed.seqPos + 1;
+			it.seq_len = (int32_t)(seqLen - seed.seqPos - 1);
+			it.node = node;
+			it.offset = (uint32_t)(seed.nodeOffset - g.nodeOffset[node]);
+			it.reserved = 0;
+			ref.item[1] = (int32_t)items.size();
+			items.push_back(it);
+		}
+		return ref;
+	}
+
+	// getAlignmentFromSeed (GraphAligner.h:567-626) from the two K1 results; `sequence` points at the
+	// characters the seed positions refer to (whole read or fragment).  Returns false if both failed.
+	bool buildAlignment(const char* sequence, const GcSeedHit& seed, const ExtRef& ref, const gcgpu_ext_result* results, const uint64_t* traces, GcAlnItem& out) const
+	{
+		bool haveB = ref.item[0] >= 0 && results[ref.item[0]].status == GCGPU_ITEM_OK;
+		bool haveF = ref.item[1] >= 0 && results[ref.item[1]].status == GCGPU_ITEM_OK;
+		if (!haveB && !haveF) return false;
+		out.trace.clear();
+		out.traceScore = 0;
+		if (haveB)
+		{
+			// fixReverseTraceSeqPosAndOrder (GraphAligner.h:543-565): order = the kernel's order (alignment end
+			// first on the reverse strand = read start first), seed cell last
+			const gcgpu_ext_result& rb = results[ref.item[0]];
+			const uint64_t* t = traces + rb.trace_offset;
+			int64_t end = (int64_t)seed.seqPos - 1;
+			out.trace.resize(rb.trace_len);
+			for (uint32_t i = 0; i < rb.trace_len; i++)
+			{
+				uint32_t node = GCGPU_TRACE_NODE(t[i]), off = GCGPU_TRACE_OFFSET(t[i]);
+				int32_t sp = GCGPU_TRACE_SEQPOS(t[i]);
+				GcTraceItem& it = out.trace[i];
+				it.seqPos = end - sp;
+				size_t offset = (size_t)g.nodeOffset[node] + off;
+				auto reversePos = g.reversePosition(g.nodeIDs[node], offset);
+				it.node = reversePos.first;
+				it.nodeOffset = (uint32_t)reversePos.second;
+				it.sequenceCharacter = sequence[it.seqPos];
+				it.graphCharacter = gcpipe::complementChar(g.nodeChar(node, off));
+				it.nodeSwitch = (i + 1 < rb.trace_len) ? GCGPU_TRACE_SWITCH(t[i + 1]) != 0 : false;
+			}
+			out.traceScore = rb.score;
+		}
+		if (haveF)
+		{
+			const gcgpu_ext_result& rf = results[ref.item[1]];
+			const uint64_t* t = traces + rf.trace_offset;
+			size_t base = out.trace.size();
+			if (haveB) { out.trace.pop_back(); base--; out.traceScore += rf.score; } else out.traceScore = rf.score;
+			out.trace.resize(base + rf.trace_len);
+			// the kernel's order reversed: seed cell first (getTwoDirectionalTrace :522), then fixForwardTraceSeqPos (:527-540)
+			for (uint32_t i = 0; i < rf.trace_len; i++)
+			{
+				uint64_t e = t[rf.trace_len - 1 - i];
+				uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
+				GcTraceItem& it = out.trace[base + i];
+				it.seqPos = (int64_t)GCGPU_TRACE_SEQPOS(e) + (int64_t)seed.seqPos + 1;
+				it.node = g.nodeIDs[node];
+				it.nodeOffset = g.nodeOffset[node] + off;
+				it.nodeSwitch = GCGPU_TRACE_SWITCH(e) != 0;
+				it.sequenceCharacter = sequence[it.seqPos];
+				it.graphCharacter = g.nodeChar(node, off);
+			}
+		}
+		out.alignmentScore = (size_t)out.traceScore;
+		out.alignmentStart = (size_t)out.trace[0].seqPos;
+		out.alignmentEnd = (size_t)out.trace.back().seqPos + 1;
+		out.seedGoodness = seed.seedGoodness;
+		return true;
+	}
+};
+
+// ------------------------------------------------------------------------------------------
+inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector<GcReadResult>& out)
+{
+	size_t R = reads.size();
+	out.assign(R, GcReadResult());
+	if (R == 0) return;
+	// ---- encode reads (forward + reverse complement IUPAC masks)
+	Batch b;
+	b.fwdOff.resize(R); b.rcOff.resize(R);
+	{
+		size_t total = 0;
+		for (size_t r = 0; r < R; r++) { b.fwdOff[r] = total; total += reads[r].sequence.size(); b.rcOff[r] = total; total += reads[r].sequence.size(); }
+		b.codes.resize(total + 8);
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t r = 0; r < R; r++)
+		{
+			const std::string& s = reads[r].sequence;
+			size_t L = s.size();
+			for (size_t i = 0; i < L; i++)
+			{
+				uint8_t m = gcEncodeBase(s[i]);
+				b.codes[b.fwdOff[r] + i] = m;
+				b.codes[b.rcOff[r] + (L - 1 - i)] = gcpipe::complementMask(m);
+			}
+		}
+	}
+	// ---- S0: seeds (the reference calls getSeeds + OrderSeeds twice per read with identical results)
+	std::vector<std::vector<GcSeedHit>> seedsOrdered(R);
+	#pragma omp parallel for schedule(dynamic, 4)
+	for (size_t r = 0; r < R; r++)
+	{
+		seedsOrdered[r] = gcseed::getSeeds(g, reads[r].sequence, params.minimizerSeedDensity);
+		out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
+		if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]);
+	}
+	std::vector<gcgpu_ext_item> items;
+	std::vector<gcgpu_ext_result> results;
+	std::vector<uint64_t> traces;
+	auto runExtend = [&]()
+	{
+		results.resize(items.size());
+		uint64_t cap = 0;
+		for (const auto& it : items) cap += 2 * (uint64_t)it.seq_len + 72;
+		if (traces.size() < cap) traces.resize(cap);
+		uint64_t used = 0;
+		int rc = gcgpu_extend(ctx, b.codes.data(), b.codes.size(), items.data(), (uint32_t)items.size(), results.data(), traces.data(), traces.size(), &used);
+		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_extend");
+		stats.k1Items += items.size();
+		stats.k1Ms += gcgpu_last_kernel_ms(ctx);
+		stats.k1Launches++;
+		for (const auto& r : results) stats.k1Columns += r.columns;
+	};
+
+	// ---- S1: whole-read alignment, AlignOneWay(seeds, sloppy=true) in rounds (GraphAligner.h:114-203)
+	struct S1State { size_t i = 0; std::vector<GcAlnItem> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; GcSeedHit seed; ExtRef ref; };
+	std::vector<S1State> s1(R);
+	for (size_t r = 0; r < R; r++) if (seedsOrdered[r].empty()) s1[r].done = true;
+	while (true)
+	{
+		items.clear();
+		std::vector<size_t> active;
+		for (size_t r = 0; r < R; r++)
+		{
+			S1State& st = s1[r];
+			if (st.done) continue;
+			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
+			bool pending = false;
+			for (; st.i < seedHits.size(); st.i++)
+			{
+				if (seedHits[st.i].seedGoodness < st.seedScoreForEndToEndAln) { st.i = seedHits.size(); break; }
+				const GcSeedHit& seed = seedHits[st.i];
+				if (seed.seedClusterSize < params.seedClusterMinSize) continue;
+				bool found = false;
+				for (const auto& aln : st.alns)
+					if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) { found = true; break; }
+				if (found) continue;
+				bool assertion = false;
+				for (const auto& aln : st.alns) if (gcpipe::exactAlignmentPart(aln, seed, assertion)) { found = true; break; }
+				if (assertion) { out[r].dropped = true; st.i = seedHits.size(); break; }
+				if (found) continue;
+				st.seedsExtended += 1;
+				st.seed = seed;
+				st.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seed, items);
+				pending = true;
+				break;
+			}
+			if (pending) active.push_back(r); else st.done = true;
+		}
+		if (active.empty()) break;
+		stats.s1Rounds++;
+		runExtend();
+		#pragma omp parallel for schedule(dynamic, 4)
+		for (size_t k = 0; k < active.size(); k++)
+		{
+			size_t r = active[k];
+			S1State& st = s1[r];
+			GcAlnItem item;
+			bool ok = buildAlignment(reads[r].sequence.data(), st.seed, st.ref, results.data(), traces.data(), item);
+			for (int d = 0; d < 2; d++) if (st.ref.item[d] >= 0 && results[st.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
+			st.i++;
+			if (!ok || item.alignmentEnd == item.alignmentStart) continue;
+			st.alns.emplace_back(std::move(item));
+			std::sort(st.alns.begin(), st.alns.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+			if (st.alns[0].alignmentStart == 0)
+			{
+				size_t minSeedGoodness = st.alns[0].seedGoodness;
+				size_t contiguousEnd = st.alns[0].alignmentEnd;
+				for (size_t i = 1; i < st.alns.size(); i++)
+				{
+					if (st.alns[i].alignmentStart <= contiguousEnd)
+					{
+						minSeedGoodness = std::min(minSeedGoodness, st.alns[i].seedGoodness);
+						contiguousEnd = std::max(contiguousEnd, st.alns[i].alignmentEnd);
+					}
+				}
+				if (contiguousEnd == reads[r].sequence.size()) st.seedScoreForEndToEndAln = minSeedGoodness;
+			}
+		}
+	}
+	// GreedyLength selection of the GA alignments + their path strings (Aligner.cpp:637-654)
+	std::vector<std::vector<GcAlnItem>> longAlns(R);
+	std::vector<std::string> longPathSeq(R);
+	std::vector<size_t> longSeedsExtended(R, 0);
+	#pragma omp parallel for schedule(dynamic, 4)
+	for (size_t r = 0; r < R; r++)
+	{
+		longSeedsExtended[r] = s1[r].seedsExtended;
+		if (out[r].dropped) { s1[r].alns.clear(); continue; }
+		if (!s1[r].alns.empty()) longAlns[r] = gcpipe::selectGreedyLength(s1[r].alns);
+		s1[r].alns.clear();
+		if (!longAlns[r].empty()) longPathSeq[r] = gcpipe::traceToSequence(g, longAlns[r][0]);
+	}
+
+	// ---- S2: fragment anchoring (Aligner.cpp:656-730); all window seeds extended speculatively
+	struct FragSeed { uint32_t seedIdx; ExtRef ref; };
+	struct Frag { size_t l; size_t firstSeed, numSeeds; };
+	std::vector<std::vector<GcSeedHit>> seedsByPos(R);
+	std::vector<std::vector<Frag>> frags(R);
+	std::vector<std::vector<FragSeed>> fragSeeds(R);
+	items.clear();
+	const size_t len = (size_t)params.colinearSplitLen, sep = (size_t)params.colinearSplitGap;
+	for (size_t r = 0; r < R; r++)
+	{
+		if (seedsOrdered[r].empty()) continue;
+		std::vector<GcSeedHit>& seeds = seedsByPos[r];
+		seeds = seedsOrdered[r];
+		std::sort(seeds.begin(), seeds.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seqPos < right.seqPos; });
+		if (out[r].dropped) continue; // `cont` stays true after an assertion: every fragment is skipped (Aligner.cpp:700-703)
+		const std::string& sequence = reads[r].sequence;
+		size_t sl = 0, sr = 0;
+		for (size_t l = 0; l + len <= sequence.length(); l += sep)
+		{
+			while (sr < seeds.size() && seeds[sr].seqPos + seeds[sr].matchLen <= l + len) sr++;
+			while (sl < sr && seeds[sl].seqPos < l) sl++;
+			if (sl >= sr) continue;
+			Frag f; f.l = l; f.firstSeed = fragSeeds[r].size(); f.numSeeds = sr - sl;
+			for (size_t i = sl; i < sr; i++)
+			{
+				GcSeedHit seed = seeds[i];
+				seed.seqPos -= l;
+				FragSeed fs; fs.seedIdx = (uint32_t)i;
+				fs.ref = makeItems(b, r, sequence.size(), l, len, seed, items);
+				fragSeeds[r].push_back(fs);
+			}
+			frags[r].push_back(f);
+		}
+	}
+	if (!items.empty()) runExtend();
+	// in-order filter + anchors
+	struct AnchorRec { std::vector<size_t> path; size_t x, y; size_t firstNode, firstOffset, lastNode, lastOffset; };
+	std::vector<std::vector<AnchorRec>> anchors(R);
+	std::vector<size_t> s2SeedsExtended(R, 0), lastFragExtended(R, 0);
+	#pragma omp parallel for schedule(dynamic, 4)
+	for (size_t r = 0; r < R; r++)
+	{
+		const std::string& sequence = reads[r].sequence;
+		std::vector<GcAlnItem> kept;
+		for (const Frag& f : frags[r])
+		{
+			kept.clear();
+			size_t before = s2SeedsExtended[r];
+			for (size_t k = 0; k < f.numSeeds; k++)
+			{
+				const FragSeed& fs = fragSeeds[r][f.firstSeed + k];
+				GcSeedHit seed = seedsByPos[r][fs.seedIdx];
+				seed.seqPos -= f.l;
+				if (seed.seedClusterSize < params.seedClusterMinSize) continue;
+				bool found = false, assertion = false;
+				for (const auto& aln : kept) if (gcpipe::exactAlignmentPart(aln, seed, assertion)) { found = true; break; }
+				if (assertion) { out[r].dropped = true; break; }
+				if (found) continue;
+				s2SeedsExtended[r] += 1;
+				for (int d = 0; d < 2; d++) if (fs.ref.item[d] >= 0 && results[fs.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
+				GcAlnItem item;
+				if (!buildAlignment(sequence.data() + f.l, seed, fs.ref, results.data(), traces.data(), item)) continue;
+				if (item.alignmentEnd == item.alignmentStart) continue;
+				kept.emplace_back(std::move(item));
+			}
+			if (out[r].dropped) break;
+			lastFragExtended[r] = s2SeedsExtended[r] - before;
+			for (const GcAlnItem& alignment : kept)
+			{
+				AnchorRec a; a.x = f.l; a.y = f.l + len - 1;
+				for (const GcTraceItem& t : alignment.trace)
+				{
+					size_t node = g.unitigNode(t.node, t.nodeOffset);
+					if (a.path.empty() || node != a.path.back()) a.path.push_back(node);
+				}
+				const GcTraceItem& t0 = alignment.trace[0]; const GcTraceItem& t1 = alignment.trace.back();
+				a.firstNode = g.unitigNode(t0.node, t0.nodeOffset); a.firstOffset = t0.nodeOffset - g.nodeOffset[a.firstNode];
+				a.lastNode = g.unitigNode(t1.node, t1.nodeOffset); a.lastOffset = t1.nodeOffset - g.nodeOffset[a.lastNode];
+				anchors[r].push_back(std::move(a));
+			}
+		}
+		if (out[r].dropped) anchors[r].clear();
+	}
+
+	// ---- S3: chaining (K2)
+	std::vector<gcgpu_anchor> flatAnchors;
+	std::vector<uint64_t> anchorOff(R + 1, 0);
+	for (size_t r = 0; r < R; r++)
+	{
+		for (const AnchorRec& a : anchors[r])
+		{
+			gcgpu_anchor ga; ga.start_node = (uint32_t)a.path[0]; ga.end_node = (uint32_t)a.path.back(); ga.x = (int32_t)a.x; ga.y = (int32_t)a.y;
+			flatAnchors.push_back(ga);
+		}
+		anchorOff[r + 1] = flatAnchors.size();
+	}
+	std::vector<uint32_t> chain(std::max<size_t>(1, flatAnchors.size())), chainLen(R);
+	std::vector<int64_t> chainScore(R);
+	check(gcgpu_chain(ctx, flatAnchors.data(), anchorOff.data(), (uint32_t)R, chain.data(), chainLen.data(), chainScore.data()), "gcgpu_chain");
+	stats.k2Reads += R; stats.k2Anchors += flatAnchors.size(); stats.k2Ms += gcgpu_last_kernel_ms(ctx);
+
+	// ---- S4: chain -> node path (Aligner.cpp:738-831)
+	std::vector<std::vector<gcpipe::MatrixPos>> longest(R);
+	std::vector<std::string> pathSeq(R);
+	#pragma omp parallel
+	{
+		gcpipe::ChainPathScratch scratch;
+		#pragma omp for schedule(dynamic, 4)
+		for (size_t r = 0; r < R; r++)
+		{
+			const std::vector<AnchorRec>& A = anchors[r];
+			std::vector<gcpipe::MatrixPos> tmp;
+			std::vector<size_t> pos_path;
+			std::unordered_set<size_t> nodes;
+			size_t firstNodeOffset = 0, lastNodeOffset = 0;
+			for (uint32_t ci = 0; ci < chainLen[r]; ci++)
+			{
+				const AnchorRec& anchor = A[chain[anchorOff[r] + ci]];
+				if (pos_path.empty())
+				{
+					pos_path = anchor.path;
+					firstNodeOffset = anchor.firstOffset;
+					lastNodeOffset = anchor.lastOffset;
+					for (size_t j : pos_path) nodes.insert(j);
+				}
+				else
+				{
+					bool gap = anchor.path[0] == pos_path.back() && params.colinearGap != -1 && (long long)anchor.firstOffset - (long long)lastNodeOffset > params.colinearGap + 1;
+					std::vector<size_t> path;
+					if (!nodes.count(anchor.path[0]) && pos_path.back() != anchor.firstNode)
+					{
+						long long gapLimit = params.colinearGap;
+						if (gapLimit != -1) gapLimit -= (long long)anchor.firstOffset + (long long)((long long)g.nodeLength[pos_path.back()] - (long long)lastNodeOffset - 1);
+						path = gcpipe::getChainPath(g, scratch, pos_path.back(), anchor.firstNode, gapLimit);
+						if (path.empty()) gap = true;
+					}
+					if (gap)
+					{
+						tmp = gcpipe::pathToTrace(g, pos_path, firstNodeOffset, lastNodeOffset);
+						if (longest[r].size() < tmp.size()) longest[r].swap(tmp);
+						nodes.clear();
+						pos_path.clear();
+						firstNodeOffset = anchor.firstOffset;
+					}
+					else
+						for (size_t j : path) if (!nodes.count(j)) { nodes.insert(j); pos_path.push_back(j); }
+					for (size_t j : anchor.path) if (!nodes.count(j)) { nodes.insert(j); pos_path.push_back(j); }
+					lastNodeOffset = anchor.lastOffset;
+				}
+			}
+			if (!pos_path.empty())
+			{
+				tmp = gcpipe::pathToTrace(g, pos_path, firstNodeOffset, lastNodeOffset);
+				if (longest[r].size() < tmp.size()) longest[r].swap(tmp);
+			}
+			pathSeq[r].reserve(longest[r].size());
+			for (const auto& p : longest[r]) pathSeq[r].push_back(g.nodeChar((uint32_t)p.node, (uint32_t)p.nodeOffset));
+		}
+	}
+
+	// ---- S1b + S5: NW distances (K3), then the edit path only where the chain wins (S6)
+	std::string nwBuf;
+	std::vector<gcgpu_nw_item> nwItems;
+	std::vector<int> gaItem(R, -1), clcItem(R, -1);
+	std::vector<uint64_t> readOffInBuf(R);
+	for (size_t r = 0; r < R; r++)
+	{
+		bool needGa = !longAlns[r].empty();
+		bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
+		if (!needGa && !needClc) continue;
+		readOffInBuf[r] = nwBuf.size();
+		nwBuf += reads[r].sequence;
+		if (needGa)
+		{
+			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)longPathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+			it.k_hint = 0; it.want_path = 0;
+			nwBuf += longPathSeq[r];
+			gaItem[r] = (int)nwItems.size(); nwItems.push_back(it);
+		}
+		if (needClc)
+		{
+			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+			it.k_hint = 0; it.want_path = 0;
+			nwBuf += pathSeq[r];
+			clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
+		}
+	}
+	std::vector<gcgpu_nw_result> nwRes(nwItems.size());
+	uint64_t opsUsed = 0;
+	if (!nwItems.empty())
+	{
+		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
+		stats.k3Items += nwItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
+		for (const auto& x : nwRes) stats.k3Blocks += x.blocks;
+	}
+	// decision (Aligner.cpp:901-920): better = no GA alignment, or long_edit_distance > CLC score (strict)
+	std::vector<gcgpu_nw_item> pathItems;
+	std::vector<size_t> pathRead;
+	for (size_t r = 0; r < R; r++)
+	{
+		GcReadResult& res = out[r];
+		res.anchors = anchors[r].size();
+		res.chained = chainLen[r];
+		res.pathBp = longest[r].size();
+		res.hasLong = gaItem[r] >= 0;
+		if (gaItem[r] >= 0) res.longEditDistance = (size_t)nwRes[gaItem[r]].distance;
+		if (clcItem[r] >= 0) res.clcScore = (size_t)nwRes[clcItem[r]].distance;
+		res.seedsExtended = 0;
+		bool haveClc = clcItem[r] >= 0 && !longest[r].empty();
+		bool better = haveClc && (longAlns[r].empty() || res.longEditDistance > res.clcScore);
+		res.usedChain = better;
+		if (better)
+		{
+			gcgpu_nw_item it = nwItems[clcItem[r]];
+			it.want_path = 1; it.k_hint = nwRes[clcItem[r]].distance;
+			pathItems.push_back(it); pathRead.push_back(r);
+		}
+	}
+	std::vector<gcgpu_nw_result> pathRes(pathItems.size());
+	std::vector<uint8_t> ops;
+	if (!pathItems.empty())
+	{
+		uint64_t cap = 0;
+		for (const auto& it : pathItems) cap += (uint64_t)it.query_len + it.target_len + 8;
+		ops.resize(cap);
+		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), ops.data(), ops.size(), &opsUsed), "gcgpu_nw(path)");
+		stats.k3Items += pathItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
+		for (const auto& x : pathRes) stats.k3Blocks += x.blocks;
+	}
+	// ---- S5 trace conversion (Aligner.cpp:851-897) and final ordering (:1004)
+	#pragma omp parallel for schedule(dynamic, 4)
+	for (size_t k = 0; k < pathRead.size(); k++)
+	{
+		size_t r = pathRead[k];
+		const std::string& sequence = reads[r].sequence;
+		const std::vector<gcpipe::MatrixPos>& lg = longest[r];
+		const uint8_t* op = ops.data() + pathRes[k].ops_offset;
+		size_t n = pathRes[k].ops_len;
+		GcAlnItem item;
+		item.trace.resize(n);
+		std::vector<size_t> splitNode(n);
+		size_t pos_i = 0, seq_i = 0;
+		for (size_t j = 0; j < n; j++)
+		{
+			GcTraceItem& t = item.trace[j];
+			size_t node = lg[pos_i].node, off = lg[pos_i].nodeOffset;
+			splitNode[j] = node;
+			t.seqPos = (int64_t)seq_i;
+			t.sequenceCharacter = seq_i < sequence.size() ? sequence[seq_i] : '-';
+			t.graphCharacter = g.nodeChar((uint32_t)node, (uint32_t)off);
+			t.node = g.nodeIDs[node];
+			t.nodeOffset = (uint32_t)(off + g.nodeOffset[node]);
+			t.nodeSwitch = false;
+			unsigned char c = op[j];
+			if (c == 0 || c == 3) { pos_i++; seq_i++; }
+			else if (c == 1) pos_i++;
+			else if (c == 2) seq_i++;
+			seq_i = std::min(seq_i, sequence.length() - 1);
+			pos_i = std::min(pos_i, lg.size() - 1);
+		}
+		// nodeSwitch compares the SPLIT nodes of consecutive entries (Aligner.cpp:880-884)
+		for (size_t j = 0; j + 1 < n; j++) item.trace[j].nodeSwitch = splitNode[j] != splitNode[j + 1];
+		if (n > 0)
+		{
+			item.traceScore = 0; // the reference leaves trace.score at 0 for the chained alignment
+			item.alignmentScore = out[r].clcScore;
+			item.alignmentStart = (size_t)item.trace[0].seqPos;
+			item.alignmentEnd = (size_t)item.trace.back().seqPos + 1;
+			out[r].alignments.clear();
+			out[r].alignments.push_back(std::move(item));
+		}
+		else out[r].usedChain = false;
+	}
+	for (size_t r = 0; r < R; r++)
+	{
+		GcReadResult& res = out[r];
+		if (!res.usedChain)
+		{
+			res.alignments = std::move(longAlns[r]);
+			res.seedsExtended = res.alignments.empty() ? 0 : longSeedsExtended[r]; // stats.seedsExtended += alignments.seedsExtended (Aligner.cpp:995)
+		}
+		else res.seedsExtended = lastFragExtended[r]; // `alignments` still carries the last fragment's seedsExtended (Aligner.cpp:691,995)
+		res.seedsExtended += s2SeedsExtended[r];
+		std::sort(res.alignments.begin(), res.alignments.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+	}
+}
