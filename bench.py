@@ -1,0 +1,237 @@
+"""bench.py -- aligned read bp/s of the GraphChainer per-read hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2] [--reads R]
+
+One step = one pass of the whole hot path (seeding -> whole-read extension -> fragment anchoring
+-> chaining -> path connection -> NW) over the workload's reads on one GPU.  N > 1 is launched by
+torchrun (one rank per GPU): the graph index is replicated, every rank aligns its own equally
+sized read set (weak scaling, no collective on the data path), the job value is total bp / max
+time over ranks.
+  value  : bp / (sum of the CUDA-event durations of all kernels of the step) -- inputs of every
+           kernel are resident in HBM when its event pair starts.
+  e2e    : bp / wall time of the reference-facing call gcalign_align() on HOST buffers (reads in,
+           GAM records out; every host<->device copy and the host stages are inside).
+--impl reference times the unmodified reference (oracle/_ref/GraphChainer_ref, all host cores)
+on a bounded sample of the same reads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "GraphChainer_ref")
+
+# algorithmic bytes per work unit (DESIGN.md "Kernels"): one unit W = one 64-row Myers column step
+K1_BYTES_PER_W = 2.9   # 184 B per node calculation (16 B sequence + 2 x 72 B slice items + 24 B per incoming edge) / ~64 columns
+K3_BYTES_PER_W = 8.0   # one 8-byte Peq word per block step; block state is register/L1 resident by design
+K1_OPS_PER_W = 44      # int32-equivalent ALU ops of getNextSlice (BVCommon.h:248-260)
+K3_OPS_PER_W = 40      # calculateBlock (edlib.cpp:409-444)
+
+
+def make_inputs(workload: str, n_reads: int, rank: int, tmp: str):
+    from graphchainer_b200 import synth
+    cfg = dict(synth.WORKLOADS[workload])
+    g = synth.SynthGraph(cfg["graph_len"], seed=1, extra_alleles=cfg.get("extra_alleles", 0))
+    gfa = os.path.join(tmp, f"{workload}.gfa")
+    with open(gfa, "w") as f:
+        f.write(g.gfa())
+    reads = list(synth.simulate_reads(g, n_reads, cfg["read_len"], cfg["error"], seed=2 + rank))
+    return gfa, reads
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def time_reference(gfa: str, fasta: str, threads: int):
+    """Align-phase seconds of the unmodified reference: wall clock between its "Align" and
+    "Alignment finished" lines (src/Aligner.cpp:1258,1296); index build excluded."""
+    with tempfile.TemporaryDirectory() as d:
+        p = subprocess.Popen([REFBIN, "-t", str(threads), "-g", gfa, "-f", fasta, "-a", os.path.join(d, "ref.gam")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        t0 = t1 = None
+        for line in p.stdout:
+            if line.startswith("Align") and not line.startswith("Alignment") and t0 is None:
+                t0 = time.perf_counter()
+            elif line.startswith("Alignment finished"):
+                t1 = time.perf_counter()
+        p.wait()
+    if p.returncode != 0 or t0 is None or t1 is None:
+        raise RuntimeError("reference run failed")
+    return t1 - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--reads", type=int, default=None, help="reads per step and GPU (default: the workload's full read set)")
+    ap.add_argument("--cpu-sample", type=int, default=640, help="reads in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from graphchainer_b200 import synth
+    cfg = dict(synth.WORKLOADS[args.workload])
+    n_reads = args.reads or cfg["n_reads"]
+    host_cores = os.cpu_count() or 1
+    config = {"workload": f"{args.workload}: synthetic {cfg['graph_len'] / 1e6:g} Mbp acyclic SNP/indel graph + {n_reads} simulated reads/GPU, length {cfg['read_len']}, {cfg['error'] * 100:g}% error (5% with a novel 400-bp insertion)",
+              "reads_per_gpu": n_reads, "graph_bp": cfg["graph_len"], "l2": "inputs larger than L2: slice/trace workspaces of a step exceed 126 MB",
+              "value_timing": "sum of CUDA-event durations of the step's kernels", "e2e_timing": "wall time of gcalign_align() on host buffers incl. all copies and host stages"}
+    tmp = tempfile.mkdtemp(prefix="gcbench_")
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if not os.path.exists(REFBIN):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/GraphChainer_ref not built"}))
+            return
+        sample = min(args.cpu_sample, n_reads)
+        gfa, reads = make_inputs(args.workload, sample, 0, tmp)
+        fa = os.path.join(tmp, "sample.fa")
+        bp = synth.write_fasta(fa, reads)
+        for _ in range(args.warmup):
+            time_reference(gfa, fa, host_cores)
+        secs = [time_reference(gfa, fa, host_cores) for _ in range(args.steps)]
+        t = sum(secs) / len(secs)
+        v = bp / t
+        line = {"metric": "aligned read bp/sec", "value": v, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": v, "unit": "bp/s", "cores": host_cores, "kind": "reference",
+                                 "sample": f"first {sample} reads of the workload ({bp} bp) per step, unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only"},
+                "e2e": {"value": v, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libgcgpu has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    from graphchainer_b200 import align
+    gfa, reads = make_inputs(args.workload, n_reads, rank, tmp)
+    batch = align.ReadBatch([r[0] for r in reads], [r[1] for r in reads])
+    threads = max(1, host_cores // world)
+    t_index = time.perf_counter()
+    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35)
+    index_s = time.perf_counter() - t_index
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        aligner.align(batch, gam=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    steps = []
+    gam_bytes = 0
+    for _ in range(args.steps):
+        gam, summ, st = aligner.align(batch, gam=True)
+        gam_bytes = len(gam)
+        steps.append(st)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    kernel_ms = sum(s["k1_ms"] + s["k2_ms"] + s["k3_ms"] for s in steps)
+    agg = torch.tensor([wall, kernel_ms / 1e3, float(batch.total_bp * args.steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = agg.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall_max, kern_max, bp_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        wall_max, kern_max, bp_total = float(agg[0]), float(agg[1]), float(agg[2])
+    if rank != 0:
+        return
+    k = args.steps
+    k1_ms = sum(s["k1_ms"] for s in steps) / k
+    k3_ms = sum(s["k3_ms"] for s in steps) / k
+    k2_ms = sum(s["k2_ms"] for s in steps) / k
+    k1_cols = sum(s["k1_columns"] for s in steps) / k
+    k3_blocks = sum(s["k3_blocks"] for s in steps) / k
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    if k3_ms >= k1_ms:
+        dom, dom_ms, dom_bytes, dom_units, dom_ops = "gc_k3_distance_kernel+gc_k3_path_kernel", k3_ms, k3_blocks * K3_BYTES_PER_W, k3_blocks, K3_OPS_PER_W
+    else:
+        dom, dom_ms, dom_bytes, dom_units, dom_ops = "gc_k1_kernel", k1_ms, k1_cols * K1_BYTES_PER_W, k1_cols, K1_OPS_PER_W
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    line = {"metric": "aligned read bp/sec", "value": bp_total / kern_max, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kern_max * 1e3 / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "e2e": {"value": bp_total / wall_max, "unit": "bp/s", "ms_per_step": wall_max * 1e3 / k, "h2d_bytes_per_step": int(batch.seq_buf.nbytes + batch.name_buf.nbytes + batch.seq_off.nbytes * 2),
+                    "d2h_bytes_per_step": int(gam_bytes)},
+            "gpu_launches": int(sum(s["launches"] for s in steps)),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "integer-pipe bound bit-parallel kernel; algorithmic bytes = work units x bytes/unit (DESIGN.md)",
+                         "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
+            "kernels_ms_per_step": {"k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
+            "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
+            "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads}
+    if not args.no_cpu_baseline and os.path.exists(REFBIN):
+        sample = min(args.cpu_sample, n_reads)
+        fa = os.path.join(tmp, "sample.fa")
+        bp = synth.write_fasta(fa, reads[:sample])
+        secs = time_reference(gfa, fa, host_cores)
+        line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": host_cores, "kind": "reference",
+                                "sample": f"first {sample} reads of rank 0's set ({bp} bp), unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only, {secs:.2f} s"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

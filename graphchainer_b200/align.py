@@ -1,0 +1,111 @@
+"""ctypes mirror of libgcalign (include/gcalign.h): the whole per-read pipeline for a batch of
+reads in host memory -> GAM records + per-read summaries.  No fallback: needs libgcgpu + a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgcalign.so")
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("initial_bandwidth", C.c_int32), ("reserved", C.c_int32),
+                ("colinear_gap", C.c_int64), ("colinear_split_len", C.c_int64), ("colinear_split_gap", C.c_int64), ("batch_bp", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("k1_ms", C.c_double), ("k2_ms", C.c_double), ("k3_ms", C.c_double),
+                ("k1_items", C.c_uint64), ("k1_columns", C.c_uint64), ("k2_anchors", C.c_uint64), ("k3_items", C.c_uint64), ("k3_blocks", C.c_uint64),
+                ("launches", C.c_uint64), ("s1_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seeds_found", C.c_uint64), ("seeds_extended", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+SUMMARY = np.dtype([("num_alignments", "<u4"), ("used_chain", "<u4"), ("anchors", "<u4"), ("chained", "<u4"), ("path_bp", "<u8"),
+                    ("clc_score", "<u8"), ("long_edit_distance", "<u8"), ("gam_offset", "<u8"), ("gam_size", "<u8")])
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        lib.gcalign_default_options.argtypes = [C.POINTER(Options)]
+        lib.gcalign_last_error.restype = C.c_char_p
+        lib.gcalign_open.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(C.c_void_p)]
+        lib.gcalign_close.argtypes = [C.c_void_p]
+        lib.gcalign_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(Stats)]
+        _lib = lib
+    return _lib
+
+
+class ReadBatch:
+    """Reads packed into the flat host buffers gcalign_align takes."""
+
+    def __init__(self, names, seqs):
+        self.n = len(seqs)
+        self.seq_buf = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+        self.seq_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in seqs], out=self.seq_off[1:])
+        self.name_buf = np.frombuffer("".join(names).encode(), dtype=np.uint8).copy()
+        self.name_off = np.zeros(self.n + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in names], out=self.name_off[1:])
+        self.total_bp = int(self.seq_off[-1])
+
+    @classmethod
+    def from_fasta(cls, path, limit=None):
+        names, seqs = [], []
+        with open(path) as f:
+            name, parts = None, []
+            for line in f:
+                if line.startswith(">"):
+                    if name is not None:
+                        names.append(name); seqs.append("".join(parts))
+                        if limit and len(seqs) >= limit:
+                            name = None
+                            break
+                    name, parts = line[1:].rstrip("\n"), []
+                else:
+                    parts.append(line.strip())
+            if name is not None:
+                names.append(name); seqs.append("".join(parts))
+        return cls(names, seqs)
+
+
+class Aligner:
+    def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0):
+        self.lib = load()
+        o = Options()
+        self.lib.gcalign_default_options(C.byref(o))
+        o.device, o.host_threads = device, host_threads
+        o.colinear_split_len, o.colinear_split_gap, o.colinear_gap, o.batch_bp = split_len, split_gap, colinear_gap, batch_bp
+        h = C.c_void_p()
+        rc = self.lib.gcalign_open(graph_path.encode(), C.byref(o), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"gcalign_open failed ({rc}): {self.lib.gcalign_last_error().decode()}")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.gcalign_close(self.handle)
+            self.handle = None
+
+    def align(self, batch: ReadBatch, gam: bool = True):
+        """Returns (gam bytes, summaries, stats dict)."""
+        cap = max(1 << 20, batch.total_bp) if gam else 0
+        out = np.zeros(cap, dtype=np.uint8) if gam else None
+        used = C.c_uint64(0)
+        summ = np.zeros(batch.n, dtype=SUMMARY)
+        st = Stats()
+        rc = self.lib.gcalign_align(self.handle, batch.seq_buf.ctypes.data, batch.seq_off.ctypes.data, batch.name_buf.ctypes.data, batch.name_off.ctypes.data, batch.n,
+                                    out.ctypes.data if gam else None, cap, C.byref(used), summ.ctypes.data, C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"gcalign_align failed ({rc}): {self.lib.gcalign_last_error().decode()}")
+        return (out[:used.value].tobytes() if gam else b""), summ, st.as_dict()

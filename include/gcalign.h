@@ -1,0 +1,71 @@
+/* libgcalign -- batch form of the reference's per-read loop body for host callers.
+ *
+ * One gcalign_align() call replaces, for a batch of reads, the body of
+ *   runComponentMappings(...)                      (src/Aligner.cpp:461-1065, colinear mode)
+ * i.e. everything between pulling a FastQ from the input queue (:499-506) and handing the
+ * serialised vg::Alignment records to the writer queue (:1047-1048).  The graph / MPC /
+ * minimizer index it needs replaces getGraph + buildMPC + MinimizerSeeder construction
+ * (src/Aligner.cpp:1137-1167) and is built by gcalign_open from a .gfa, or loaded from the
+ * flat .gcidx form (graphchainer_b200/csrc/gc_index.h).
+ * The DP stages run on the GPU through libgcgpu (include/gcgpu.h); there is no CPU path.
+ * All buffers are caller-owned host memory.  Returns 0 or a negative gcgpu_status.
+ */
+#ifndef GCALIGN_H
+#define GCALIGN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcalign gcalign;
+
+/* AlignerParams fields the path honours (src/Aligner.h:10-63) */
+typedef struct gcalign_options
+{
+	int32_t device;               /* CUDA device index                                   */
+	int32_t host_threads;         /* -t: threads for the host stages                      */
+	int32_t initial_bandwidth;    /* -b, default 10                                       */
+	int32_t reserved;
+	int64_t colinear_gap;         /* --colinear-gap, default 10000                        */
+	int64_t colinear_split_len;   /* --colinear-split-len, default 35                     */
+	int64_t colinear_split_gap;   /* --colinear-split-gap, default 35                     */
+	uint64_t batch_bp;            /* read bases per internal GPU batch (0 = default)      */
+} gcalign_options;
+
+/* per read: the fields of the reference's --short-verbose line (src/Aligner.cpp:909-915) */
+typedef struct gcalign_read_summary
+{
+	uint32_t num_alignments;
+	uint32_t used_chain;          /* 1 = the chained (CLC) alignment was written          */
+	uint32_t anchors, chained;
+	uint64_t path_bp;
+	uint64_t clc_score, long_edit_distance;
+	uint64_t gam_offset, gam_size; /* this read's GAM record inside the output buffer     */
+} gcalign_read_summary;
+
+typedef struct gcalign_stats
+{
+	double k1_ms, k2_ms, k3_ms;          /* CUDA-event kernel time per stage               */
+	uint64_t k1_items, k1_columns;       /* extensions, 64-row Myers column steps          */
+	uint64_t k2_anchors;
+	uint64_t k3_items, k3_blocks;        /* NW alignments, 64-row block column steps       */
+	uint64_t launches;                   /* kernel launches                                */
+	uint64_t s1_rounds;
+	uint64_t h2d_bytes, d2h_bytes;       /* not tracked yet: 0                             */
+	uint64_t seeds_found, seeds_extended;
+} gcalign_stats;
+
+void gcalign_default_options(gcalign_options* opts);
+const char* gcalign_last_error(void);
+/* graph_path: *.gfa (index built here) or *.gcidx (prebuilt index) */
+int gcalign_open(const char* graph_path, const gcalign_options* opts, gcalign** out);
+void gcalign_close(gcalign* h);
+/* reads: seqs[seq_offsets[i] .. seq_offsets[i+1]) and names likewise.  If gam_out != NULL the
+ * reads' GAM records (one gzip member per read with an alignment) are appended to it.       */
+int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_offsets, const char* names, const uint64_t* name_offsets, uint32_t num_reads,
+                  uint8_t* gam_out, uint64_t gam_capacity, uint64_t* gam_used, gcalign_read_summary* summaries, gcalign_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
