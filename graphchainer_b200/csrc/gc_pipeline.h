@@ -16,6 +16,9 @@
 // There is no CPU implementation of K1/K2/K3 here: without libgcgpu nothing aligns.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -72,6 +75,8 @@ struct GcPipelineParams
 	long long colinearSplitLen = 35;
 	long long colinearSplitGap = 35;
 	bool tryAllSeeds = true;
+	size_t s1FirstRoundSeeds = 1;   // S1 speculation: seeds extended per read in the first round ...
+	size_t s1LaterRoundSeeds = 8;   // ... and in every later round
 };
 
 struct GcPipelineStats
@@ -82,6 +87,7 @@ struct GcPipelineStats
 	double k1Ms = 0, k2Ms = 0, k3Ms = 0;
 	double hostSeedMs = 0, hostS1Ms = 0, hostS2Ms = 0, hostConnectMs = 0;
 	uint64_t s1Rounds = 0;
+	uint64_t s1Wasted = 0; // speculative S1 seed extensions whose result was discarded
 };
 
 namespace gcpipe {
@@ -250,6 +256,7 @@ private:
 		std::vector<uint64_t> fwdOff, rcOff; // offsets into codes
 	};
 
+	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
 	void check(int rc, const char* what)
 	{
 		if (rc != GCGPU_OK) throw std::runtime_error(std::string(what) + " failed: " + gcgpu_last_error());
@@ -358,6 +365,10 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	size_t R = reads.size();
 	out.assign(R, GcReadResult());
 	if (R == 0) return;
+	const bool traceOn = getenv("GC_TRACE") != nullptr;
+	auto wallNow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tPhase = wallNow();
+	auto phase = [&](const char* name) { if (traceOn) { double n = wallNow(); fprintf(stderr, "[gc] phase %-10s %.2f ms\n", name, n - tPhase); tPhase = n; } };
 	// ---- encode reads (forward + reverse complement IUPAC masks)
 	Batch b;
 	b.fwdOff.resize(R); b.rcOff.resize(R);
@@ -387,6 +398,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
 		if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]);
 	}
+	phase("seed");
 	std::vector<gcgpu_ext_item> items;
 	std::vector<gcgpu_ext_result> results;
 	std::vector<uint64_t> traces;
@@ -402,13 +414,33 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		stats.k1Items += items.size();
 		stats.k1Ms += gcgpu_last_kernel_ms(ctx);
 		stats.k1Launches++;
-		for (const auto& r : results) stats.k1Columns += r.columns;
+		uint64_t cols = 0;
+		for (const auto& r : results) cols += r.columns;
+		stats.k1Columns += cols;
+		if (traceOn) fprintf(stderr, "[gc] extend items=%zu kernel_ms=%.3f columns=%llu\n", items.size(), (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols);
 	};
 
-	// ---- S1: whole-read alignment, AlignOneWay(seeds, sloppy=true) in rounds (GraphAligner.h:114-203)
-	struct S1State { size_t i = 0; std::vector<GcAlnItem> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; GcSeedHit seed; ExtRef ref; };
+	// ---- S1: whole-read alignment, AlignOneWay(seeds, sloppy=true) (GraphAligner.h:114-203).
+	// The reference walks the seeds in goodness order and decides, from the alignments kept so far,
+	// whether to extend each one.  An extension is a pure function of (read, seed), so every ROUND
+	// extends, for every read, the next few seeds that pass the skip rules under the current state;
+	// the results are then consumed strictly in seed order with the rules re-evaluated exactly as
+	// the reference does -- a speculative result whose seed turns out to be skipped is discarded.
+	struct S1Cand { size_t seedIdx; ExtRef ref; };
+	struct S1State { size_t i = 0; std::vector<GcAlnItem> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; };
 	std::vector<S1State> s1(R);
 	for (size_t r = 0; r < R; r++) if (seedsOrdered[r].empty()) s1[r].done = true;
+	// 0 = extend, 1 = skip, 2 = stop the seed loop, 3 = assertion (read dropped)
+	auto seedRule = [&](const S1State& st, const GcSeedHit& seed) -> int
+	{
+		if (seed.seedGoodness < st.seedScoreForEndToEndAln) return 2;
+		if (seed.seedClusterSize < params.seedClusterMinSize) return 1;
+		for (const auto& aln : st.alns)
+			if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) return 1;
+		bool assertion = false;
+		for (const auto& aln : st.alns) { if (gcpipe::exactAlignmentPart(aln, seed, assertion)) return 1; if (assertion) return 3; }
+		return 0;
+	};
 	while (true)
 	{
 		items.clear();
@@ -418,27 +450,25 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			S1State& st = s1[r];
 			if (st.done) continue;
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
-			bool pending = false;
-			for (; st.i < seedHits.size(); st.i++)
+			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : params.s1LaterRoundSeeds;
+			st.cands.clear();
+			for (size_t i = st.i; i < seedHits.size() && st.cands.size() < want; i++)
 			{
-				if (seedHits[st.i].seedGoodness < st.seedScoreForEndToEndAln) { st.i = seedHits.size(); break; }
-				const GcSeedHit& seed = seedHits[st.i];
-				if (seed.seedClusterSize < params.seedClusterMinSize) continue;
-				bool found = false;
-				for (const auto& aln : st.alns)
-					if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) { found = true; break; }
-				if (found) continue;
-				bool assertion = false;
-				for (const auto& aln : st.alns) if (gcpipe::exactAlignmentPart(aln, seed, assertion)) { found = true; break; }
-				if (assertion) { out[r].dropped = true; st.i = seedHits.size(); break; }
-				if (found) continue;
-				st.seedsExtended += 1;
-				st.seed = seed;
-				st.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seed, items);
-				pending = true;
-				break;
+				int rule = seedRule(st, seedHits[i]);
+				if (rule >= 2) break; // decided again, in order, when the results are consumed
+				if (rule == 1) continue;
+				S1Cand c; c.seedIdx = i;
+				c.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seedHits[i], items);
+				st.cands.push_back(c);
 			}
-			if (pending) active.push_back(r); else st.done = true;
+			st.round++;
+			if (st.cands.empty())
+			{
+				// nothing left to extend: finish the seed walk for the assertion-class exit only
+				for (; st.i < seedHits.size(); st.i++) { int rule = seedRule(st, seedHits[st.i]); if (rule == 3) out[r].dropped = true; if (rule >= 2) break; }
+				st.done = true;
+			}
+			else active.push_back(r);
 		}
 		if (active.empty()) break;
 		stats.s1Rounds++;
@@ -448,29 +478,45 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		{
 			size_t r = active[k];
 			S1State& st = s1[r];
-			GcAlnItem item;
-			bool ok = buildAlignment(reads[r].sequence.data(), st.seed, st.ref, results.data(), traces.data(), item);
-			for (int d = 0; d < 2; d++) if (st.ref.item[d] >= 0 && results[st.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
-			st.i++;
-			if (!ok || item.alignmentEnd == item.alignmentStart) continue;
-			st.alns.emplace_back(std::move(item));
-			std::sort(st.alns.begin(), st.alns.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
-			if (st.alns[0].alignmentStart == 0)
+			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
+			size_t next = 0; // next unconsumed speculative result
+			for (; st.i < seedHits.size(); st.i++)
 			{
-				size_t minSeedGoodness = st.alns[0].seedGoodness;
-				size_t contiguousEnd = st.alns[0].alignmentEnd;
-				for (size_t i = 1; i < st.alns.size(); i++)
+				const GcSeedHit& seed = seedHits[st.i];
+				int rule = seedRule(st, seed);
+				if (rule == 3) { out[r].dropped = true; st.i = seedHits.size(); break; }
+				if (rule == 2) { st.i = seedHits.size(); break; }
+				if (rule == 1) continue;
+				while (next < st.cands.size() && st.cands[next].seedIdx < st.i) next++;
+				if (next >= st.cands.size() || st.cands[next].seedIdx != st.i) break; // not extended yet: first seed of the next round
+				const S1Cand& c = st.cands[next++];
+				st.seedsExtended += 1;
+				GcAlnItem item;
+				bool ok = buildAlignment(reads[r].sequence.data(), seed, c.ref, results.data(), traces.data(), item);
+				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && results[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
+				if (!ok || item.alignmentEnd == item.alignmentStart) continue;
+				st.alns.emplace_back(std::move(item));
+				std::sort(st.alns.begin(), st.alns.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+				if (st.alns[0].alignmentStart == 0)
 				{
-					if (st.alns[i].alignmentStart <= contiguousEnd)
+					size_t minSeedGoodness = st.alns[0].seedGoodness;
+					size_t contiguousEnd = st.alns[0].alignmentEnd;
+					for (size_t i = 1; i < st.alns.size(); i++)
 					{
-						minSeedGoodness = std::min(minSeedGoodness, st.alns[i].seedGoodness);
-						contiguousEnd = std::max(contiguousEnd, st.alns[i].alignmentEnd);
+						if (st.alns[i].alignmentStart <= contiguousEnd)
+						{
+							minSeedGoodness = std::min(minSeedGoodness, st.alns[i].seedGoodness);
+							contiguousEnd = std::max(contiguousEnd, st.alns[i].alignmentEnd);
+						}
 					}
+					if (contiguousEnd == reads[r].sequence.size()) st.seedScoreForEndToEndAln = minSeedGoodness;
 				}
-				if (contiguousEnd == reads[r].sequence.size()) st.seedScoreForEndToEndAln = minSeedGoodness;
 			}
+			if (st.i >= seedHits.size()) st.done = true;
+			stats_s1Wasted_add(st.cands.size() - next);
 		}
 	}
+	phase("s1");
 	// GreedyLength selection of the GA alignments + their path strings (Aligner.cpp:637-654)
 	std::vector<std::vector<GcAlnItem>> longAlns(R);
 	std::vector<std::string> longPathSeq(R);
@@ -569,6 +615,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		if (out[r].dropped) anchors[r].clear();
 	}
 
+	phase("s2");
 	// ---- S3: chaining (K2)
 	std::vector<gcgpu_anchor> flatAnchors;
 	std::vector<uint64_t> anchorOff(R + 1, 0);
@@ -586,6 +633,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	check(gcgpu_chain(ctx, flatAnchors.data(), anchorOff.data(), (uint32_t)R, chain.data(), chainLen.data(), chainScore.data()), "gcgpu_chain");
 	stats.k2Reads += R; stats.k2Anchors += flatAnchors.size(); stats.k2Ms += gcgpu_last_kernel_ms(ctx);
 
+	phase("s3");
 	// ---- S4: chain -> node path (Aligner.cpp:738-831)
 	std::vector<std::vector<gcpipe::MatrixPos>> longest(R);
 	std::vector<std::string> pathSeq(R);
@@ -645,6 +693,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		}
 	}
 
+	phase("s4");
 	// ---- S1b + S5: NW distances (K3), then the edit path only where the chain wins (S6)
 	std::string nwBuf;
 	std::vector<gcgpu_nw_item> nwItems;
@@ -714,6 +763,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		stats.k3Items += pathItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : pathRes) stats.k3Blocks += x.blocks;
 	}
+	phase("nw");
 	// ---- S5 trace conversion (Aligner.cpp:851-897) and final ordering (:1004)
 	#pragma omp parallel for schedule(dynamic, 4)
 	for (size_t k = 0; k < pathRead.size(); k++)
@@ -770,4 +820,6 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		res.seedsExtended += s2SeedsExtended[r];
 		std::sort(res.alignments.begin(), res.alignments.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
 	}
+	phase("final");
+	if (traceOn) fprintf(stderr, "[gc] batch reads=%zu s1_rounds=%llu s1_wasted=%llu\n", R, (unsigned long long)stats.s1Rounds, (unsigned long long)stats.s1Wasted);
 }

@@ -11,9 +11,11 @@
 #include "gc_k1.cuh"
 #include "gc_k2.cuh"
 #include "gc_k3.cuh"
+#include "gc_k3w.cuh"
 #include "gc_host_graph.h"
 
 #define GCGPU_VERSION 1
+#define GC_K1_LONG_ITEM 96   // sequence length from which a K1 item gets a warp of its own
 
 static thread_local std::string g_lastError;
 static int setError(int code, const std::string& msg) { g_lastError = msg; return code; }
@@ -100,6 +102,29 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 {
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
+	GcK1Desc d = descs[t];
+	GcK1Workspace ws;
+	uint8_t* base = arena + d.wsOff;
+	ws.slices = (GcSliceMeta*)base;
+	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
+	ws.items = (GcNodeItem*)(base + slicesBytes);
+	ws.heap = (uint64_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem));
+	ws.itemCap = d.itemCap;
+	ws.heapCap = d.heapCap;
+	GcK1Result res;
+	gc_k1_extend(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, traceArena + d.traceOff, d.traceCap, res);
+	results[d.resultIndex] = res;
+}
+
+// Long work items (whole-read extensions, thousands of dependent column steps): one WARP per item,
+// lane 0 walks the item.  A thread-per-item launch would serialise 32 divergent walks inside each
+// warp; with a private warp every walk issues at the full single-warp rate and the scheduler
+// interleaves up to 64 of them per SM.
+__global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results)
+{
+	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (t >= n || (threadIdx.x & 31) != 0) return;
 	GcK1Desc d = descs[t];
 	GcK1Workspace ws;
 	uint8_t* base = arena + d.wsOff;
@@ -259,9 +284,20 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		CUDA_TRY(ctx->descBuf.ensure(descs.size() * sizeof(GcK1Desc)));
 		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), descs.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
 		uint32_t m = (uint32_t)descs.size();
+		// todo is sorted longest first: the first mLong items go to the warp-per-item kernel
+		uint32_t mLong = 0;
+		while (mLong < m && descs[mLong].seqLen >= GC_K1_LONG_ITEM) mLong++;
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		gc_k1_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, (GcK1Result*)ctx->resBuf.p);
-		ctx->launches++;
+		if (mLong)
+		{
+			gc_k1_long_kernel<<<(mLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, mLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, (GcK1Result*)ctx->resBuf.p);
+			ctx->launches++;
+		}
+		if (m > mLong)
+		{
+			gc_k1_kernel<<<(m - mLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p + mLong, m - mLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, (GcK1Result*)ctx->resBuf.p);
+			ctx->launches++;
+		}
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		CUDA_TRY(cudaMemcpyAsync(hres.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost, ctx->stream));
@@ -374,6 +410,101 @@ __global__ void __launch_bounds__(64) gc_k3_distance_kernel(const uint8_t* __res
 	out[d.resultIndex] = o;
 }
 
+
+// ---- warp form (gc_k3w.cuh): one warp = one NW distance, lanes = groups of NB 64-row blocks on a
+// skewed wavefront, block state in registers, one shuffle per column step.
+template <int NB>
+__device__ __forceinline__ uint32_t gc_k3w_run_pass(const GcK3wPass& p, GcK3Block* blocksOut)
+{
+	int lane = threadIdx.x & 31;
+	GcK3wLane<NB> s;
+	gc_k3w_lane_init(p, s, lane);
+	uint32_t send = 0;
+	for (int32_t tau = 0; tau <= p.tauEnd; tau++)
+	{
+		uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, (lane + 31) & 31);
+		send = gc_k3w_lane_step(p, s, tau, recv, blocksOut);
+	}
+	__syncwarp();
+	return s.work;
+}
+
+#define GC_K3W_NEED_LARGER (-2)
+// CLASS 0: NB in {1,2} (cutoff bands up to ~4000 diagonals); CLASS 1: NB in {3,4,6,8,12,16} (up to ~31.7k)
+template <int CLASS>
+__device__ __forceinline__ int gc_k3w_round_nb(int nb)
+{
+	if (CLASS == 0) return nb <= 1 ? 1 : (nb <= 2 ? 2 : 0);
+	return nb <= 3 ? 3 : nb <= 4 ? 4 : nb <= 6 ? 6 : nb <= 8 ? 8 : nb <= 12 ? 12 : nb <= 16 ? 16 : 0;
+}
+template <int CLASS>
+__device__ __forceinline__ uint32_t gc_k3w_dispatch(const GcK3wPass& p, int NB, GcK3Block* blocksOut)
+{
+	if (CLASS == 0) return NB == 1 ? gc_k3w_run_pass<1>(p, blocksOut) : gc_k3w_run_pass<2>(p, blocksOut);
+	switch (NB)
+	{
+		case 3: return gc_k3w_run_pass<3>(p, blocksOut);
+		case 4: return gc_k3w_run_pass<4>(p, blocksOut);
+		case 6: return gc_k3w_run_pass<6>(p, blocksOut);
+		case 8: return gc_k3w_run_pass<8>(p, blocksOut);
+		case 12: return gc_k3w_run_pass<12>(p, blocksOut);
+		default: return gc_k3w_run_pass<16>(p, blocksOut);
+	}
+}
+
+// one warp = one edlib NW distance (k doubling of edlib.cpp:193-212 from the item's first cutoff)
+template <int CLASS>
+__global__ void __launch_bounds__(128) gc_k3w_distance_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK3Out* out)
+{
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int lane = threadIdx.x & 31;
+	if (w >= n) return;
+	GcK3Desc d = descs[w];
+	int32_t q = d.q, t = d.t;
+	int32_t nb = (q + 63) / 64; if (nb < 1) nb = 1;
+	uint64_t* peq = (uint64_t*)(arena + d.wsOff);
+	GcK3Block* blocks = (GcK3Block*)(peq + 4 * (size_t)nb);
+	const uint8_t* query = seq + d.qOff;
+	const uint8_t* target = seq + d.tOff;
+	for (int32_t b = lane; b < nb; b += 32)
+	{
+		uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+		int32_t lim = q - b * 64; if (lim > 64) lim = 64;
+		for (int32_t i = 0; i < lim; i++)
+		{
+			uint8_t c = query[b * 64 + i];
+			uint64_t bit = 1ULL << i;
+			e0 |= c == 0 ? bit : 0; e1 |= c == 1 ? bit : 0; e2 |= c == 2 ? bit : 0; e3 |= c == 3 ? bit : 0;
+		}
+		peq[b] = e0; peq[nb + b] = e1; peq[2 * (size_t)nb + b] = e2; peq[3 * (size_t)nb + b] = e3;
+	}
+	__syncwarp();
+	GcK3Out o; o.status = GC_OK; o.opsLen = 0; o.pad = 0; o.blocks = 0; o.distance = -1;
+	uint32_t work = 0;
+	if (q == 0 || t == 0) o.distance = q > t ? q : t;
+	else
+	{
+		int32_t k = d.kHint < 64 ? 64 : d.kHint;
+		int32_t diff = q > t ? q - t : t - q, mx = q > t ? q : t;
+		while (true)
+		{
+			if (k >= diff)
+			{
+				int32_t kk = k > mx ? mx : k;
+				int NB = gc_k3w_round_nb<CLASS>(gc_k3w_blocks_per_lane(q, t, kk));
+				if (NB == 0) { o.distance = GC_K3W_NEED_LARGER; o.pad = (uint32_t)k; break; }
+				GcK3wPass p = gc_k3w_make_pass(peq, nb, 0, q, target, 0, 1, t, kk, t - 1, NB);
+				work += gc_k3w_dispatch<CLASS>(p, NB, blocks);
+				int32_t v = gc_k3_cell(blocks[(q - 1) >> 6], q - 1);
+				if (v <= kk) { o.distance = v; break; }
+			}
+			k *= 2;
+		}
+	}
+	for (int off = 16; off > 0; off >>= 1) work += __shfl_down_sync(0xFFFFFFFFu, work, off);
+	if (lane == 0) { o.blocks = work; out[d.resultIndex] = o; }
+}
+
 // one thread = one edlib NW path (Hirschberg + leaf tracebacks) for a known distance
 __global__ void __launch_bounds__(64) gc_k3_path_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint8_t* opsArena, GcK3Out* out)
 {
@@ -462,7 +593,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(ctx->descBuf.ensure((size_t)n * sizeof(GcK3Desc)));
 	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK3Out)));
 	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
-	gc_k3_distance_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+	gc_k3w_distance_kernel<0><<<(n + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -471,6 +602,33 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
+	// items whose cutoff band outgrew the register budget of the launched class: wider class, then the thread form
+	for (int cls = 1; cls <= 2; cls++)
+	{
+		std::vector<GcK3Desc> rd;
+		for (uint32_t k = 0; k < n; k++)
+		{
+			const GcK3Out& o = hout[descs[k].resultIndex];
+			if (o.distance == GC_K3W_NEED_LARGER) { GcK3Desc d = descs[k]; d.kHint = (int32_t)o.pad; rd.push_back(d); }
+		}
+		if (rd.empty()) break;
+		uint32_t m = (uint32_t)rd.size();
+		uint64_t blocksBefore = 0; // work of the aborted attempts is kept in the item's counter
+		(void)blocksBefore;
+		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), (size_t)m * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+		if (cls == 1) gc_k3w_distance_kernel<1><<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		else gc_k3_distance_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		ctx->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+		std::vector<GcK3Out> prev = hout;
+		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		ctx->lastKernelMs += ms;
+		for (const GcK3Desc& d : rd) hout[d.resultIndex].blocks += prev[d.resultIndex].blocks;
+	}
 	// ---- path pass for the items that asked for it
 	std::vector<uint32_t> want;
 	for (uint32_t k = 0; k < n; k++) if (items[order[k]].want_path && items[order[k]].query_len > 0 && items[order[k]].target_len > 0) want.push_back(order[k]);

@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../graphchainer_b200/csrc/gc_host_graph.h"
 #include "../../graphchainer_b200/csrc/gc_k3.cuh"
+#include "../../graphchainer_b200/csrc/gc_k3w.cuh"
 #include "../../graphchainer_b200/csrc/gc_k2.cuh"
 #include <numeric>
 #include <algorithm>
@@ -100,6 +101,150 @@ static int k3Main(const char* stagesPath)
 	return bad == 0 ? 0 : 1;
 }
 
+
+// ---- warp form of the K3 pass (gc_k3w.cuh) with 32 emulated lanes: the shuffle of the device
+// kernel (lane L reads what lane L-1 returned from the previous step) becomes an array copy.
+template <int NB>
+static uint64_t k3wPassSim(const GcK3wPass& p, GcK3Block* blocksOut)
+{
+	GcK3wLane<NB> lanes[32];
+	uint32_t send[32], recv[32];
+	for (int l = 0; l < 32; l++) { gc_k3w_lane_init(p, lanes[l], l); send[l] = 0; }
+	for (int32_t tau = 0; tau <= p.tauEnd; tau++)
+	{
+		for (int l = 0; l < 32; l++) recv[l] = send[(l + 31) & 31];
+		for (int l = 0; l < 32; l++) send[l] = gc_k3w_lane_step(p, lanes[l], tau, recv[l], blocksOut);
+	}
+	uint64_t work = 0;
+	for (int l = 0; l < 32; l++) work += lanes[l].work;
+	return work;
+}
+static uint64_t k3wPassSimNB(const GcK3wPass& p, int NB, GcK3Block* blocksOut)
+{
+	switch (NB)
+	{
+		case 1: return k3wPassSim<1>(p, blocksOut);
+		case 2: return k3wPassSim<2>(p, blocksOut);
+		case 3: return k3wPassSim<3>(p, blocksOut);
+		case 4: return k3wPassSim<4>(p, blocksOut);
+		default: return k3wPassSim<8>(p, blocksOut);
+	}
+}
+static int roundNB(int nb) { return nb <= 4 ? nb : 8; }
+// edit distance through the warp form; extraNB > 0 forces a larger group size than necessary
+static int32_t k3wDistanceSim(const uint64_t* peq, int32_t nb, int32_t Q, const uint8_t* t, int32_t T, int32_t kStart, int extraNB, uint64_t& work)
+{
+	if (Q == 0 || T == 0) return Q > T ? Q : T;
+	std::vector<GcK3Block> blocks(nb + 1);
+	int32_t k = kStart < 64 ? 64 : kStart;
+	int32_t diff = Q > T ? Q - T : T - Q, mx = Q > T ? Q : T;
+	while (true)
+	{
+		if (k >= diff)
+		{
+			int32_t kk = k > mx ? mx : k;
+			int NB = roundNB(gc_k3w_blocks_per_lane(Q, T, kk) + extraNB);
+			GcK3wPass p = gc_k3w_make_pass(peq, nb, 0, Q, t, 0, 1, T, kk, T - 1, NB);
+			work += k3wPassSimNB(p, NB, blocks.data());
+			int32_t v = gc_k3_cell(blocks[(Q - 1) >> 6], Q - 1);
+			if (v <= kk) return v;
+		}
+		k *= 2;
+	}
+}
+
+// random pairs (substitutions + indels) checked against the thread form, plus sub-query /
+// reversed / stop-column passes as the Hirschberg recursion issues them
+static int k3wMain(const char* stagesPath)
+{
+	size_t total = 0, bad = 0; uint64_t work = 0, workRef = 0;
+	auto check = [&](const std::vector<uint8_t>& q, const std::vector<uint8_t>& t, int extraNB, int kStart)
+	{
+		int32_t Q = (int32_t)q.size(), T = (int32_t)t.size();
+		int32_t nb = (Q + 63) / 64; if (nb < 1) nb = 1;
+		std::vector<uint64_t> peq(4 * (size_t)nb);
+		gc_k3_build_peq(q.data(), Q, peq.data(), nb);
+		std::vector<GcK3Block> ba(nb + 1);
+		int32_t want = gc_k3_distance(peq.data(), nb, Q, t.data(), T, ba.data(), 64, workRef);
+		int32_t got = k3wDistanceSim(peq.data(), nb, Q, t.data(), T, kStart, extraNB, work);
+		total++;
+		if (got != want) { bad++; if (bad <= 5) std::cerr << "K3W mismatch q=" << Q << " t=" << T << " extraNB=" << extraNB << " kStart=" << kStart << ": got " << got << " want " << want << std::endl; }
+		// a Hirschberg-style half pass on a sub-query with a non-aligned offset, forward and reversed
+		if (Q > 200 && T > 200 && want > 0)
+		{
+			int32_t qOff = 37 + (Q / 7), q2 = Q - qOff - 11, tOff = T / 9, t2 = T - tOff - 5;
+			for (int rev = 0; rev < 2; rev++)
+			{
+				std::vector<uint8_t> rq(q.rbegin(), q.rend());
+				std::vector<uint64_t> rpeq(4 * (size_t)nb);
+				gc_k3_build_peq(rq.data(), Q, rpeq.data(), nb);
+				const uint64_t* pq = rev ? rpeq.data() : peq.data();
+				int32_t qo = rev ? Q - qOff - q2 : qOff;
+				int64_t tBase = rev ? (int64_t)tOff + t2 - 1 : tOff; int32_t tStep = rev ? -1 : 1;
+				int32_t k2 = want + 40; int32_t mx2 = q2 > t2 ? q2 : t2; if (k2 > mx2) k2 = mx2;
+				int32_t d2 = q2 > t2 ? q2 - t2 : t2 - q2; if (k2 < d2) k2 = d2;
+				int32_t stop = t2 / 2;
+				std::vector<GcK3Block> refBlocks(nb + 1), gotBlocks(nb + 1);
+				gc_k3_pass(pq, nb, qo, q2, t.data(), tBase, tStep, t2, k2, stop, refBlocks.data(), nullptr, nullptr);
+				int NB = roundNB(gc_k3w_blocks_per_lane(q2, t2, k2) + extraNB);
+				GcK3wPass p = gc_k3w_make_pass(pq, nb, qo, q2, t.data(), tBase, tStep, t2, k2, stop, NB);
+				k3wPassSimNB(p, NB, gotBlocks.data());
+				GcK3Band band = gc_k3_band(q2, t2, k2);
+				int32_t fb = gc_k3_first_block(band, stop), lb = gc_k3_last_block(band, q2, stop);
+				int32_t f2, l2; gc_k3w_stop_blocks(p, NB, f2, l2);
+				total++;
+				bool ok = f2 <= fb && l2 >= lb;
+				// inside the strict band the warp form may only be tighter (its band is a superset), and every
+				// value that is part of a <= k2 path must agree: compare cells whose reference value is <= k2
+				for (int32_t r = fb * 64; ok && r <= std::min(q2 - 1, lb * 64 + 63); r++)
+				{
+					int32_t a = gc_k3_cell(refBlocks[r >> 6], r), b = gc_k3_cell(gotBlocks[r >> 6], r);
+					if (b > a) ok = false;
+				}
+				if (!ok) { bad++; if (bad <= 5) std::cerr << "K3W half-pass mismatch q2=" << q2 << " t2=" << t2 << " rev=" << rev << " NB=" << NB << std::endl; }
+			}
+		}
+	};
+	uint64_t rng = 88172645463325252ULL;
+	auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+	const int lens[] = { 1, 5, 63, 64, 65, 130, 700, 2049, 4100, 9000, 12500 };
+	const double errs[] = { 0.0, 0.02, 0.15, 0.35 };
+	for (int len : lens) for (double e : errs) for (int extra = 0; extra < 2; extra++)
+	{
+		std::vector<uint8_t> q(len), t;
+		for (auto& c : q) c = (uint8_t)(next() & 3);
+		for (int i = 0; i < len; i++)
+		{
+			double u = (double)(next() % 100000) / 100000.0;
+			if (u < e / 3) continue;                                   // deletion
+			if (u < 2 * e / 3) { t.push_back((uint8_t)(next() & 3)); continue; } // substitution
+			t.push_back(q[i]);
+			if (u < e) for (int z = (int)(next() % 6); z > 0; z--) t.push_back((uint8_t)(next() & 3)); // insertion
+		}
+		if (len == 700 && e == 0.02) t.push_back(4); // a non-ACGT target symbol matches nothing
+		check(q, t, extra, 0);
+		if (extra == 0) check(q, t, 0, 3000); // a generous upper bound as first cutoff: one pass
+	}
+	// the golden NW items as well
+	std::ifstream in(stagesPath);
+	std::string line, readSeq;
+	while (std::getline(in, line))
+	{
+		if (line.compare(0, 5, "READ ") == 0) { std::istringstream ss(line); std::string tag, name; ss >> tag >> name >> readSeq; }
+		else if (line.compare(0, 11, "GA_PATHSEQ ") == 0 || line.compare(0, 8, "PATHSEQ ") == 0)
+		{
+			std::istringstream ss(line); std::string tag, ps; ss >> tag >> ps;
+			if (ps == "-") continue;
+			std::vector<uint8_t> q(ps.size()), t(readSeq.size());
+			for (size_t i = 0; i < q.size(); i++) q[i] = k3code(ps[i]);
+			for (size_t i = 0; i < t.size(); i++) t[i] = k3code(readSeq[i]);
+			check(q, t, 0, 0);
+		}
+	}
+	std::cout << "{\"mode\":\"k3w\",\"items\":" << total << ",\"mismatches\":" << bad << ",\"columns\":" << work << ",\"columns_thread_form\":" << workRef << "}" << std::endl;
+	return bad == 0 ? 0 : 1;
+}
+
 static GcMpcView mpcView(const GcHostGraph& hg)
 {
 	GcMpcView m;
@@ -149,6 +294,7 @@ int main(int argc, char** argv)
 	if (argc < 4) { std::cerr << "usage: host_sim k1 index.gcidx stages.txt [maxItems]" << std::endl; return 2; }
 	std::string mode = argv[1];
 	if (mode == "k3") return k3Main(argv[3]);
+	if (mode == "k3w") return k3wMain(argv[3]);
 	GcIndexFile idx; idx.load(argv[2]);
 	GcHostGraph hg; hg.fromIndex(idx);
 	if (mode == "k2") return k2Main(hg, argv[3]);
