@@ -1,6 +1,7 @@
 // libgcalign: the host pipeline behind a C ABI (include/gcalign.h).
 #include <omp.h>
 #include <cstring>
+#include <memory>
 #include <string>
 #include "../../include/gcalign.h"
 #include "gc_pipeline.h"
@@ -16,6 +17,7 @@ struct gcalign
 	gcgpu_ctx* ctx = nullptr;
 	gcalign_options opts;
 	GcPipelineParams pipe;
+	std::unique_ptr<GcPipeline> pipeline; // persistent: its page-locked buffers are reused by every call
 };
 
 extern "C" void gcalign_default_options(gcalign_options* o)
@@ -62,6 +64,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 extern "C" void gcalign_close(gcalign* h)
 {
 	if (!h) return;
+	h->pipeline.reset();
 	if (h->ctx) gcgpu_destroy(h->ctx);
 	delete h;
 }
@@ -78,7 +81,9 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	uint64_t used = 0;
 	try
 	{
-		GcPipeline pipeline(h->graph, h->ctx, h->pipe);
+		if (!h->pipeline) h->pipeline.reset(new GcPipeline(h->graph, h->ctx, h->pipe));
+		GcPipeline& pipeline = *h->pipeline;
+		pipeline.stats = GcPipelineStats();
 		std::vector<GcRead> batch;
 		std::vector<GcReadResult> results;
 		for (uint32_t first = 0; first < num_reads; )

@@ -40,6 +40,8 @@ struct GcK3wPass
 	int32_t nb;            // blocks of the sub-query
 	int32_t numGroups;     // ceil(nb / NB)
 	int32_t tauEnd;        // last wavefront step
+	GcK3Block* store;      // leaf traceback: block b of column c -> store[c * storeStride + b] (null: not kept)
+	int32_t storeStride;
 };
 
 GC_HD int32_t gc_k3w_blocks_per_lane(int32_t q, int32_t t, int32_t k)
@@ -61,6 +63,7 @@ GC_HD GcK3wPass gc_k3w_make_pass(const uint64_t* peq, int32_t nbTotal, int32_t q
 	int32_t gLast = (stopCol + p.dhi) / (64 * NB);
 	if (gLast > p.numGroups - 1) gLast = p.numGroups - 1;
 	p.tauEnd = stopCol + gLast;
+	p.store = nullptr; p.storeStride = 0;
 	return p;
 }
 
@@ -143,6 +146,13 @@ GC_HD uint32_t gc_k3w_lane_step(const GcK3wPass& p, GcK3wLane<NB>& s, int32_t ta
 		}
 		s.work += (uint32_t)s.nbHere;
 		send = ((uint32_t)lastScore << 2) | (uint32_t)(hin + 1);
+		if (p.store)
+		{
+			GcK3Block* dst = p.store + (int64_t)c * p.storeStride + s.g * NB;
+			GC_UNROLL
+			for (int i = 0; i < NB; i++)
+				if (i < s.nbHere) { GcK3Block bl; bl.P = s.P[i]; bl.M = s.M[i]; bl.score = s.score[i]; bl.pad = 0; dst[i] = bl; }
+		}
 		if (c == p.stopCol)
 		{
 			GC_UNROLL
@@ -163,4 +173,165 @@ GC_HD void gc_k3w_stop_blocks(const GcK3wPass& p, int32_t NB, int32_t& first, in
 	int32_t gLo = (lo >> 6) / NB, gHi = (hi >> 6) / NB;
 	first = gLo * NB;
 	last = gHi * NB + NB - 1; if (last > p.nb - 1) last = p.nb - 1;
+}
+
+// blocks [first, last] that a pass computes in column c (group-granular superset of the band)
+GC_HD void gc_k3w_column_blocks(const GcK3wPass& p, int32_t NB, int32_t c, int32_t& first, int32_t& last)
+{
+	int32_t lo = c + p.dlo; if (lo < 0) lo = 0;
+	int32_t hi = c + p.dhi; if (hi > p.q - 1) hi = p.q - 1;
+	int32_t gLo = (lo >> 6) / NB, gHi = (hi >> 6) / NB;
+	first = gLo * NB;
+	last = gHi * NB + NB - 1; if (last > p.nb - 1) last = p.nb - 1;
+}
+
+// ------------------------------------------------------------------ alignment path, warp form
+// Same recursion as gc_k3_path (obtainAlignment / obtainAlignmentHirschberg / obtainAlignmentTraceback,
+// edlib.cpp:1164-1399, 945-1144) with every banded pass run by the warp.  `Exec` supplies the
+// warp primitives: on the device they are shuffles/ballots (gcgpu.cu), in tests/hostsim an
+// emulation with 32 lanes.  Control flow is warp-uniform; only the leader lane writes.
+struct GcK3wPathWorkspace
+{
+	const uint64_t* peq;    // [4 * nbTotal]
+	const uint64_t* rpeq;   // [4 * nbTotal] profile of the reversed query
+	int32_t nbTotal, qTotal, tTotal;
+	GcK3Block* blocksA;     // [nbTotal]
+	GcK3Block* blocksB;     // [nbTotal]
+	GcK3Block* store;       // [storeCap] leaf columns, full layout column-major
+	uint32_t storeCap;
+	GcK3Frame* stack;       // [stackCap]
+	uint32_t stackCap;
+	int32_t maxNB;          // largest group size the executor supports
+};
+
+// leaf: canonical traceback (up, then left, then diagonal) over the stored columns (leader lane only)
+GC_HD bool gc_k3w_leaf_traceback(const GcK3wPass& p, int32_t NB, const GcK3Frame& f, uint8_t* ops, uint32_t& nOps, uint32_t opsCap)
+{
+	int32_t q = f.q, t = f.t;
+	uint32_t start = nOps;
+	int32_t i = q - 1, j = t - 1;
+	const int32_t INF = 1 << 29;
+	int32_t cachedCol = -1, cf = 0, cl = -1;
+	auto cell = [&](int32_t ii, int32_t jj) -> int32_t
+	{
+		if (ii < 0 && jj < 0) return 0;
+		if (ii < 0) return jj + 1;
+		if (jj < 0) return ii + 1;
+		if (jj != cachedCol) { gc_k3w_column_blocks(p, NB, jj, cf, cl); cachedCol = jj; }
+		int32_t b = ii >> 6;
+		if (b < cf || b > cl) return INF;
+		return gc_k3_cell(p.store[(int64_t)jj * p.storeStride + b], ii);
+	};
+	int32_t cur = cell(i, j);
+	if (cur != f.best) return false;
+	while (i >= 0 || j >= 0)
+	{
+		if (nOps >= opsCap) return false;
+		if (j < 0) { ops[nOps++] = 1; i--; continue; }
+		if (i < 0) { ops[nOps++] = 2; j--; continue; }
+		int32_t u = cell(i - 1, j);
+		if (u + 1 == cur) { ops[nOps++] = 1; i--; cur = u; continue; }
+		int32_t l = cell(i, j - 1);
+		if (l + 1 == cur) { ops[nOps++] = 2; j--; cur = l; continue; }
+		int32_t ul = cell(i - 1, j - 1);
+		if (ul == cur) ops[nOps++] = 0;
+		else if (ul + 1 == cur) ops[nOps++] = 3;
+		else return false;
+		i--; j--; cur = ul;
+	}
+	for (uint32_t a = start, b = nOps; a + 1 < b; a++, b--) { uint8_t tmp = ops[a]; ops[a] = ops[b - 1]; ops[b - 1] = tmp; }
+	return true;
+}
+
+GC_HD int32_t gc_k3w_round_nb_path(int32_t nb) { return nb <= 1 ? 1 : nb <= 2 ? 2 : nb <= 4 ? 4 : nb <= 8 ? 8 : 0; }
+
+template <class Exec>
+GC_HD bool gc_k3w_path(Exec& ex, const GcK3wPathWorkspace& w, const uint8_t* target, int32_t best, uint8_t* ops, uint32_t& nOps, uint32_t opsCap, uint64_t& work)
+{
+	nOps = 0;
+	uint32_t sp = 0;
+	if (ex.leader()) { GcK3Frame f0; f0.qOff = 0; f0.q = w.qTotal; f0.tOff = 0; f0.t = w.tTotal; f0.best = best; w.stack[0] = f0; }
+	sp = 1;
+	ex.sync();
+	while (sp > 0)
+	{
+		GcK3Frame f = w.stack[--sp];
+		ex.sync(); // every lane has read the frame before the leader may overwrite the slot
+		if (f.q == 0 || f.t == 0)
+		{
+			uint32_t n = (uint32_t)(f.q + f.t);
+			if (nOps + n > opsCap) return false;
+			if (ex.leader()) for (uint32_t x = 0; x < n; x++) ops[nOps + x] = f.q == 0 ? 2 : 1;
+			nOps += n;
+			continue;
+		}
+		int32_t q = f.q, t = f.t, k = f.best;
+		int32_t mx = q > t ? q : t;
+		if (k > mx) k = mx;
+		int32_t NB = gc_k3w_round_nb_path(gc_k3w_blocks_per_lane(q, t, k));
+		if (NB == 0 || NB > w.maxNB) return false;
+		int64_t nb = (q + 63) / 64;
+		int64_t alignmentDataSize = (2LL * 8 + 4) * nb * t + 2LL * 4 * t;
+		if (alignmentDataSize < 1024 * 1024)
+		{
+			if ((uint64_t)nb * (uint64_t)t > w.storeCap) return false;
+			GcK3wPass p = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, t - 1, NB);
+			p.store = w.store; p.storeStride = (int32_t)nb;
+			work += ex.pass(p, NB, w.blocksA);
+			uint32_t n2 = nOps;
+			bool ok = true;
+			if (ex.leader()) ok = gc_k3w_leaf_traceback(p, NB, f, ops, n2, opsCap);
+			ok = ex.fromLeader((uint32_t)ok) != 0;
+			nOps = ex.fromLeader(n2);
+			if (!ok) return false;
+			continue;
+		}
+		// ---- Hirschberg split (edlib.cpp:1234-1399)
+		int32_t leftW = t / 2, rightW = t - leftW;
+		GcK3wPass pf = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, leftW - 1, NB);
+		work += ex.pass(pf, NB, w.blocksA);
+		int32_t rqOff = w.qTotal - f.qOff - q;
+		GcK3wPass pr = gc_k3w_make_pass(w.rpeq, w.nbTotal, rqOff, q, target, (int64_t)f.tOff + t - 1, -1, t, k, rightW - 1, NB);
+		work += ex.pass(pr, NB, w.blocksB);
+		int32_t lfb, llb, rfb, rlb;
+		gc_k3w_stop_blocks(pf, NB, lfb, llb);
+		gc_k3w_stop_blocks(pr, NB, rfb, rlb);
+		int32_t row = ex.firstSplitRow(w.blocksA, lfb, llb, w.blocksB, rfb, rlb, q, f.best);
+		const int32_t INF = 1 << 29;
+		int32_t leftScore = -1, rightScore = -1;
+		if (row >= 0)
+		{
+			leftScore = gc_k3_cell(w.blocksA[row >> 6], row);
+			int32_t rr = q - 1 - (row + 1);
+			rightScore = gc_k3_cell(w.blocksB[rr >> 6], rr);
+		}
+		else
+		{
+			row = -2;
+			{
+				int32_t rr = q - 1; int32_t b = rr >> 6;
+				int32_t rs = (b < rfb || b > rlb) ? INF : gc_k3_cell(w.blocksB[b], rr);
+				if (leftW + rs == f.best) { row = -1; leftScore = leftW; rightScore = rs; }
+			}
+			if (row == -2)
+			{
+				int32_t b = (q - 1) >> 6;
+				int32_t ls = (b < lfb || b > llb) ? INF : gc_k3_cell(w.blocksA[b], q - 1);
+				if (ls + rightW == f.best) { row = q - 1; leftScore = ls; rightScore = rightW; }
+			}
+			if (row == -2) return false;
+		}
+		int32_t ulHeight = row + 1, lrHeight = q - ulHeight;
+		if (sp + 2 > w.stackCap) return false;
+		if (ex.leader())
+		{
+			GcK3Frame lr; lr.qOff = f.qOff + ulHeight; lr.q = lrHeight; lr.tOff = f.tOff + leftW; lr.t = rightW; lr.best = rightScore;
+			GcK3Frame ul; ul.qOff = f.qOff; ul.q = ulHeight; ul.tOff = f.tOff; ul.t = leftW; ul.best = leftScore;
+			w.stack[sp] = lr; // processed after ul
+			w.stack[sp + 1] = ul;
+		}
+		sp += 2;
+		ex.sync();
+	}
+	return true;
 }

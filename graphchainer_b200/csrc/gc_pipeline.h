@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_set>
@@ -54,6 +55,29 @@ struct GcAlnItem
 	size_t alignmentStart = 0, alignmentEnd = 0;
 	size_t alignmentScore = 0;
 	size_t seedGoodness = 0;
+};
+
+
+// One seed extension (getAlignmentFromSeed, GraphAligner.h:567-626) as the two K1 traces the kernel
+// wrote, still packed: the merged GraphAligner trace is only materialised for alignments that
+// survive selection.  Merged order = backward part (kernel order; its last entry, the seed cell,
+// is dropped when a forward part exists, GraphAligner.h:599) then the forward part reversed.
+struct GcPackedAln
+{
+	const uint64_t* bwd = nullptr; uint32_t bwdLen = 0;
+	const uint64_t* fwd = nullptr; uint32_t fwdLen = 0;
+	int32_t bwdScore = 0, fwdScore = 0;
+	int64_t seedPos = 0;          // seed.seqPos in the coordinates of the aligned sequence
+	int32_t traceScore = 0;
+	size_t alignmentStart = 0, alignmentEnd = 0, alignmentScore = 0, seedGoodness = 0;
+	uint32_t bwdUsed() const { return bwdLen ? (fwdLen ? bwdLen - 1 : bwdLen) : 0; }
+	uint32_t size() const { return bwdUsed() + fwdLen; }
+	int64_t seqPosAt(uint32_t k) const
+	{
+		uint32_t nb = bwdUsed();
+		if (k < nb) return (seedPos - 1) - (int64_t)GCGPU_TRACE_SEQPOS(bwd[k]);
+		return (int64_t)GCGPU_TRACE_SEQPOS(fwd[fwdLen - 1 - (k - nb)]) + seedPos + 1;
+	}
 };
 
 struct GcReadResult
@@ -105,25 +129,58 @@ inline char complementChar(char c)
 }
 inline uint8_t complementMask(uint8_t m) { return (uint8_t)(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)); }
 
-// exactAlignmentPart (GraphAligner.h:407-461): is the seed cell on the trace of `aln`?
-inline bool exactAlignmentPart(const GcAlnItem& aln, const GcSeedHit& seed, bool& assertion)
+// digraph node id + offset in the original node of merged-trace entry k
+inline void packedNodePos(const GcHostGraph& g, const GcPackedAln& a, uint32_t k, int& node, size_t& nodeOffset)
 {
-	const std::vector<GcTraceItem>& trace = aln.trace;
-	if (trace.empty() || !(trace.back().seqPos > trace[0].seqPos)) { assertion = true; return false; }
+	uint32_t nb = a.bwdUsed();
+	if (k < nb)
+	{
+		uint64_t e = a.bwd[k];
+		uint32_t sn = GCGPU_TRACE_NODE(e);
+		auto rp = g.reversePosition(g.nodeIDs[sn], (size_t)g.nodeOffset[sn] + GCGPU_TRACE_OFFSET(e));
+		node = rp.first; nodeOffset = rp.second;
+	}
+	else
+	{
+		uint64_t e = a.fwd[a.fwdLen - 1 - (k - nb)];
+		uint32_t sn = GCGPU_TRACE_NODE(e);
+		node = g.nodeIDs[sn]; nodeOffset = (size_t)g.nodeOffset[sn] + GCGPU_TRACE_OFFSET(e);
+	}
+}
+// split node of merged-trace entry k (= GetUnitigNode(node, nodeOffset))
+inline size_t packedSplitNode(const GcHostGraph& g, const GcPackedAln& a, uint32_t k)
+{
+	uint32_t nb = a.bwdUsed();
+	if (k >= nb) return GCGPU_TRACE_NODE(a.fwd[a.fwdLen - 1 - (k - nb)]);
+	int node; size_t off;
+	packedNodePos(g, a, k, node, off);
+	return g.unitigNode(node, off);
+}
+
+// exactAlignmentPart (GraphAligner.h:407-461): is the seed cell on the trace of `aln`?
+inline bool exactAlignmentPart(const GcHostGraph& g, const GcPackedAln& aln, const GcSeedHit& seed, bool& assertion)
+{
+	uint32_t n = aln.size();
+	if (n == 0 || !(aln.seqPosAt(n - 1) > aln.seqPosAt(0))) { assertion = true; return false; }
 	int64_t sp = (int64_t)seed.seqPos;
-	if (trace.back().seqPos < sp) return false;
-	if (trace[0].seqPos > sp) return false;
+	if (aln.seqPosAt(n - 1) < sp) return false;
+	if (aln.seqPosAt(0) > sp) return false;
 	// seqPos is non-decreasing with unit steps: find the run of items at seqPos == sp
-	size_t lo = 0, hi = trace.size();
-	while (lo < hi) { size_t mid = (lo + hi) / 2; if (trace[mid].seqPos < sp) lo = mid + 1; else hi = mid; }
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (aln.seqPosAt(mid) < sp) lo = mid + 1; else hi = mid; }
 	int compareNode = seed.nodeID * 2 + (seed.reverse ? 1 : 0);
-	for (size_t i = lo; i < trace.size() && trace[i].seqPos == sp; i++)
-		if (trace[i].node == compareNode && trace[i].nodeOffset == seed.nodeOffset) return true;
+	for (uint32_t i = lo; i < n && aln.seqPosAt(i) == sp; i++)
+	{
+		int node; size_t off;
+		packedNodePos(g, aln, i, node, off);
+		if (node == compareNode && off == seed.nodeOffset) return true;
+	}
 	return false;
 }
 
 // AlignmentSelection::alignmentIncompatible (AlignmentSelection.cpp:13-31)
-inline bool alignmentIncompatible(const GcAlnItem& left, const GcAlnItem& right)
+template <typename Aln>
+inline bool alignmentIncompatible(const Aln& left, const Aln& right)
 {
 	const float OverlapIncompatibleFractionCutoff = 0.05;
 	auto minOverlapLen = std::min((left.alignmentEnd - left.alignmentStart), (right.alignmentEnd - right.alignmentStart)) * OverlapIncompatibleFractionCutoff;
@@ -134,22 +191,23 @@ inline bool alignmentIncompatible(const GcAlnItem& left, const GcAlnItem& right)
 	return overlap > minOverlapLen;
 }
 // GreedySelectAlignments with alignmentLengthCompare (AlignmentSelection.h:36-55, .cpp:45-51)
-inline std::vector<GcAlnItem> selectGreedyLength(const std::vector<GcAlnItem>& alignments)
+template <typename Aln>
+inline std::vector<Aln> selectGreedyLength(const std::vector<Aln>& alignments)
 {
 	std::vector<size_t> items;
 	for (size_t i = 0; i < alignments.size(); i++) items.push_back(i);
 	std::sort(items.begin(), items.end(), [&alignments](size_t l, size_t r)
 	{
-		const GcAlnItem& left = alignments[l]; const GcAlnItem& right = alignments[r];
+		const Aln& left = alignments[l]; const Aln& right = alignments[r];
 		if ((left.alignmentEnd - left.alignmentStart) > (right.alignmentEnd - right.alignmentStart)) return true;
 		if ((right.alignmentEnd - right.alignmentStart) > (left.alignmentEnd - left.alignmentStart)) return false;
 		if (left.alignmentScore < right.alignmentScore) return true;
 		return false;
 	});
-	std::vector<GcAlnItem> result;
+	std::vector<Aln> result;
 	for (auto i : items)
 	{
-		if (!std::any_of(result.begin(), result.end(), [&alignments, i](const GcAlnItem& existing) { return alignmentIncompatible(existing, alignments[i]); }))
+		if (!std::any_of(result.begin(), result.end(), [&alignments, i](const Aln& existing) { return alignmentIncompatible(existing, alignments[i]); }))
 			result.push_back(alignments[i]);
 	}
 	return result;
@@ -252,9 +310,32 @@ private:
 	struct ExtRef { int32_t item[2]; }; // indices of the backward / forward work items, -1 if absent
 	struct Batch
 	{
-		std::vector<uint8_t> codes;          // per read: forward masks then reverse-complement masks
+		uint8_t* codes = nullptr;            // per read: forward masks then reverse-complement masks (page-locked)
+		size_t codesBytes = 0;
 		std::vector<uint64_t> fwdOff, rcOff; // offsets into codes
 	};
+
+	// page-locked host buffers for the kernel outputs, grow-only, reused across batches:
+	// tracePool[k] receives the packed traces of the k-th gcgpu_extend call of a batch and stays
+	// valid until the packed alignments that point into it have been consumed
+	struct Pinned
+	{
+		void* p = nullptr; size_t cap = 0;
+		void ensure(size_t bytes)
+		{
+			if (bytes <= cap) return;
+			if (p) gcgpu_host_free(p);
+			cap = bytes + bytes / 4 + (1 << 20);
+			p = gcgpu_host_alloc(cap);
+			if (!p) { cap = 0; throw std::runtime_error("gcgpu_host_alloc failed"); }
+		}
+		~Pinned() { if (p) gcgpu_host_free(p); }
+		Pinned() = default;
+		Pinned(const Pinned&) = delete;
+		Pinned& operator=(const Pinned&) = delete;
+	};
+	std::vector<std::unique_ptr<Pinned>> tracePool;
+	Pinned codesBuf;
 
 	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
 	void check(int rc, const char* what)
@@ -297,65 +378,61 @@ private:
 		return ref;
 	}
 
-	// getAlignmentFromSeed (GraphAligner.h:567-626) from the two K1 results; `sequence` points at the
-	// characters the seed positions refer to (whole read or fragment).  Returns false if both failed.
-	bool buildAlignment(const char* sequence, const GcSeedHit& seed, const ExtRef& ref, const gcgpu_ext_result* results, const uint64_t* traces, GcAlnItem& out) const
+	// getAlignmentFromSeed (GraphAligner.h:567-626) from the two K1 results, kept packed.  `seed.seqPos` is in
+	// the coordinates of the aligned sequence (whole read or fragment).  Returns false if both failed.
+	bool buildAlignment(const GcSeedHit& seed, const ExtRef& ref, const gcgpu_ext_result* results, const uint64_t* traces, GcPackedAln& out) const
 	{
 		bool haveB = ref.item[0] >= 0 && results[ref.item[0]].status == GCGPU_ITEM_OK;
 		bool haveF = ref.item[1] >= 0 && results[ref.item[1]].status == GCGPU_ITEM_OK;
 		if (!haveB && !haveF) return false;
-		out.trace.clear();
-		out.traceScore = 0;
-		if (haveB)
-		{
-			// fixReverseTraceSeqPosAndOrder (GraphAligner.h:543-565): order = the kernel's order (alignment end
-			// first on the reverse strand = read start first), seed cell last
-			const gcgpu_ext_result& rb = results[ref.item[0]];
-			const uint64_t* t = traces + rb.trace_offset;
-			int64_t end = (int64_t)seed.seqPos - 1;
-			out.trace.resize(rb.trace_len);
-			for (uint32_t i = 0; i < rb.trace_len; i++)
-			{
-				uint32_t node = GCGPU_TRACE_NODE(t[i]), off = GCGPU_TRACE_OFFSET(t[i]);
-				int32_t sp = GCGPU_TRACE_SEQPOS(t[i]);
-				GcTraceItem& it = out.trace[i];
-				it.seqPos = end - sp;
-				size_t offset = (size_t)g.nodeOffset[node] + off;
-				auto reversePos = g.reversePosition(g.nodeIDs[node], offset);
-				it.node = reversePos.first;
-				it.nodeOffset = (uint32_t)reversePos.second;
-				it.sequenceCharacter = sequence[it.seqPos];
-				it.graphCharacter = gcpipe::complementChar(g.nodeChar(node, off));
-				it.nodeSwitch = (i + 1 < rb.trace_len) ? GCGPU_TRACE_SWITCH(t[i + 1]) != 0 : false;
-			}
-			out.traceScore = rb.score;
-		}
-		if (haveF)
-		{
-			const gcgpu_ext_result& rf = results[ref.item[1]];
-			const uint64_t* t = traces + rf.trace_offset;
-			size_t base = out.trace.size();
-			if (haveB) { out.trace.pop_back(); base--; out.traceScore += rf.score; } else out.traceScore = rf.score;
-			out.trace.resize(base + rf.trace_len);
-			// the kernel's order reversed: seed cell first (getTwoDirectionalTrace :522), then fixForwardTraceSeqPos (:527-540)
-			for (uint32_t i = 0; i < rf.trace_len; i++)
-			{
-				uint64_t e = t[rf.trace_len - 1 - i];
-				uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
-				GcTraceItem& it = out.trace[base + i];
-				it.seqPos = (int64_t)GCGPU_TRACE_SEQPOS(e) + (int64_t)seed.seqPos + 1;
-				it.node = g.nodeIDs[node];
-				it.nodeOffset = g.nodeOffset[node] + off;
-				it.nodeSwitch = GCGPU_TRACE_SWITCH(e) != 0;
-				it.sequenceCharacter = sequence[it.seqPos];
-				it.graphCharacter = g.nodeChar(node, off);
-			}
-		}
+		out = GcPackedAln();
+		out.seedPos = (int64_t)seed.seqPos;
+		if (haveB) { const gcgpu_ext_result& rb = results[ref.item[0]]; out.bwd = traces + rb.trace_offset; out.bwdLen = rb.trace_len; out.bwdScore = rb.score; }
+		if (haveF) { const gcgpu_ext_result& rf = results[ref.item[1]]; out.fwd = traces + rf.trace_offset; out.fwdLen = rf.trace_len; out.fwdScore = rf.score; }
+		out.traceScore = (haveB ? out.bwdScore : 0) + (haveF ? out.fwdScore : 0);
 		out.alignmentScore = (size_t)out.traceScore;
-		out.alignmentStart = (size_t)out.trace[0].seqPos;
-		out.alignmentEnd = (size_t)out.trace.back().seqPos + 1;
+		out.alignmentStart = (size_t)out.seqPosAt(0);
+		out.alignmentEnd = (size_t)out.seqPosAt(out.size() - 1) + 1;
 		out.seedGoodness = seed.seedGoodness;
 		return true;
+	}
+
+	// the merged GraphAligner trace of a packed alignment: fixReverseTraceSeqPosAndOrder (GraphAligner.h:543-565),
+	// getTwoDirectionalTrace (:522), fixForwardTraceSeqPos (:527-540)
+	void materialize(const char* sequence, const GcPackedAln& a, GcAlnItem& out) const
+	{
+		uint32_t nb = a.bwdUsed(), n = a.size();
+		out.trace.resize(n);
+		for (uint32_t i = 0; i < nb; i++)
+		{
+			uint64_t e = a.bwd[i];
+			uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
+			GcTraceItem& it = out.trace[i];
+			it.seqPos = (a.seedPos - 1) - (int64_t)GCGPU_TRACE_SEQPOS(e);
+			auto reversePos = g.reversePosition(g.nodeIDs[node], (size_t)g.nodeOffset[node] + off);
+			it.node = reversePos.first;
+			it.nodeOffset = (uint32_t)reversePos.second;
+			it.sequenceCharacter = sequence[it.seqPos];
+			it.graphCharacter = gcpipe::complementChar(g.nodeChar(node, off));
+			it.nodeSwitch = (i + 1 < a.bwdLen) ? GCGPU_TRACE_SWITCH(a.bwd[i + 1]) != 0 : false;
+		}
+		for (uint32_t i = 0; i < a.fwdLen; i++)
+		{
+			uint64_t e = a.fwd[a.fwdLen - 1 - i];
+			uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
+			GcTraceItem& it = out.trace[nb + i];
+			it.seqPos = (int64_t)GCGPU_TRACE_SEQPOS(e) + a.seedPos + 1;
+			it.node = g.nodeIDs[node];
+			it.nodeOffset = g.nodeOffset[node] + off;
+			it.nodeSwitch = GCGPU_TRACE_SWITCH(e) != 0;
+			it.sequenceCharacter = sequence[it.seqPos];
+			it.graphCharacter = g.nodeChar(node, off);
+		}
+		out.traceScore = a.traceScore;
+		out.alignmentScore = a.alignmentScore;
+		out.alignmentStart = a.alignmentStart;
+		out.alignmentEnd = a.alignmentEnd;
+		out.seedGoodness = a.seedGoodness;
 	}
 };
 
@@ -375,7 +452,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	{
 		size_t total = 0;
 		for (size_t r = 0; r < R; r++) { b.fwdOff[r] = total; total += reads[r].sequence.size(); b.rcOff[r] = total; total += reads[r].sequence.size(); }
-		b.codes.resize(total + 8);
+		codesBuf.ensure(total + 8);
+		b.codes = (uint8_t*)codesBuf.p; b.codesBytes = total + 8;
+		memset(b.codes + total, 0, 8);
 		#pragma omp parallel for schedule(dynamic, 16)
 		for (size_t r = 0; r < R; r++)
 		{
@@ -401,23 +480,29 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	phase("seed");
 	std::vector<gcgpu_ext_item> items;
 	std::vector<gcgpu_ext_result> results;
-	std::vector<uint64_t> traces;
+	const uint64_t* traces = nullptr;
+	size_t extendCalls = 0;
 	auto runExtend = [&]()
 	{
 		results.resize(items.size());
 		uint64_t cap = 0;
 		for (const auto& it : items) cap += 2 * (uint64_t)it.seq_len + 72;
-		if (traces.size() < cap) traces.resize(cap);
+		if (tracePool.size() <= extendCalls) tracePool.emplace_back(new Pinned());
+		Pinned& buf = *tracePool[extendCalls];
+		buf.ensure(cap * 8);
 		uint64_t used = 0;
-		int rc = gcgpu_extend(ctx, b.codes.data(), b.codes.size(), items.data(), (uint32_t)items.size(), results.data(), traces.data(), traces.size(), &used);
+		// the read codes are uploaded by the first call of the batch and stay resident (seq == NULL afterwards)
+		int rc = gcgpu_extend(ctx, extendCalls == 0 ? b.codes : nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), (uint64_t*)buf.p, cap, &used);
 		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_extend");
+		traces = (const uint64_t*)buf.p;
+		extendCalls++;
 		stats.k1Items += items.size();
 		stats.k1Ms += gcgpu_last_kernel_ms(ctx);
 		stats.k1Launches++;
 		uint64_t cols = 0;
 		for (const auto& r : results) cols += r.columns;
 		stats.k1Columns += cols;
-		if (traceOn) fprintf(stderr, "[gc] extend items=%zu kernel_ms=%.3f columns=%llu\n", items.size(), (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols);
+		if (traceOn) fprintf(stderr, "[gc] extend items=%zu kernel_ms=%.3f columns=%llu trace_MB=%.1f\n", items.size(), (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols, used * 8 / 1e6);
 	};
 
 	// ---- S1: whole-read alignment, AlignOneWay(seeds, sloppy=true) (GraphAligner.h:114-203).
@@ -427,7 +512,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	// the results are then consumed strictly in seed order with the rules re-evaluated exactly as
 	// the reference does -- a speculative result whose seed turns out to be skipped is discarded.
 	struct S1Cand { size_t seedIdx; ExtRef ref; };
-	struct S1State { size_t i = 0; std::vector<GcAlnItem> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; };
+	struct S1State { size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; };
 	std::vector<S1State> s1(R);
 	for (size_t r = 0; r < R; r++) if (seedsOrdered[r].empty()) s1[r].done = true;
 	// 0 = extend, 1 = skip, 2 = stop the seed loop, 3 = assertion (read dropped)
@@ -438,7 +523,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		for (const auto& aln : st.alns)
 			if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) return 1;
 		bool assertion = false;
-		for (const auto& aln : st.alns) { if (gcpipe::exactAlignmentPart(aln, seed, assertion)) return 1; if (assertion) return 3; }
+		for (const auto& aln : st.alns) { if (gcpipe::exactAlignmentPart(g, aln, seed, assertion)) return 1; if (assertion) return 3; }
 		return 0;
 	};
 	while (true)
@@ -491,12 +576,12 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				if (next >= st.cands.size() || st.cands[next].seedIdx != st.i) break; // not extended yet: first seed of the next round
 				const S1Cand& c = st.cands[next++];
 				st.seedsExtended += 1;
-				GcAlnItem item;
-				bool ok = buildAlignment(reads[r].sequence.data(), seed, c.ref, results.data(), traces.data(), item);
+				GcPackedAln item;
+				bool ok = buildAlignment(seed, c.ref, results.data(), traces, item);
 				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && results[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
 				if (!ok || item.alignmentEnd == item.alignmentStart) continue;
-				st.alns.emplace_back(std::move(item));
-				std::sort(st.alns.begin(), st.alns.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+				st.alns.emplace_back(item);
+				std::sort(st.alns.begin(), st.alns.end(), [](const GcPackedAln& left, const GcPackedAln& right) { return left.alignmentStart < right.alignmentStart; });
 				if (st.alns[0].alignmentStart == 0)
 				{
 					size_t minSeedGoodness = st.alns[0].seedGoodness;
@@ -526,7 +611,12 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	{
 		longSeedsExtended[r] = s1[r].seedsExtended;
 		if (out[r].dropped) { s1[r].alns.clear(); continue; }
-		if (!s1[r].alns.empty()) longAlns[r] = gcpipe::selectGreedyLength(s1[r].alns);
+		if (!s1[r].alns.empty())
+		{
+			std::vector<GcPackedAln> sel = gcpipe::selectGreedyLength(s1[r].alns);
+			longAlns[r].resize(sel.size());
+			for (size_t k = 0; k < sel.size(); k++) materialize(reads[r].sequence.data(), sel[k], longAlns[r][k]);
+		}
 		s1[r].alns.clear();
 		if (!longAlns[r].empty()) longPathSeq[r] = gcpipe::traceToSequence(g, longAlns[r][0]);
 	}
@@ -565,6 +655,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			frags[r].push_back(f);
 		}
 	}
+	extendCalls = extendCalls ? 1 : 0; // S1's trace buffers are free again (codes stay resident after the first call)
 	if (!items.empty()) runExtend();
 	// in-order filter + anchors
 	struct AnchorRec { std::vector<size_t> path; size_t x, y; size_t firstNode, firstOffset, lastNode, lastOffset; };
@@ -574,7 +665,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	for (size_t r = 0; r < R; r++)
 	{
 		const std::string& sequence = reads[r].sequence;
-		std::vector<GcAlnItem> kept;
+		std::vector<GcPackedAln> kept;
 		for (const Frag& f : frags[r])
 		{
 			kept.clear();
@@ -586,29 +677,32 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				seed.seqPos -= f.l;
 				if (seed.seedClusterSize < params.seedClusterMinSize) continue;
 				bool found = false, assertion = false;
-				for (const auto& aln : kept) if (gcpipe::exactAlignmentPart(aln, seed, assertion)) { found = true; break; }
+				for (const auto& aln : kept) if (gcpipe::exactAlignmentPart(g, aln, seed, assertion)) { found = true; break; }
 				if (assertion) { out[r].dropped = true; break; }
 				if (found) continue;
 				s2SeedsExtended[r] += 1;
 				for (int d = 0; d < 2; d++) if (fs.ref.item[d] >= 0 && results[fs.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
-				GcAlnItem item;
-				if (!buildAlignment(sequence.data() + f.l, seed, fs.ref, results.data(), traces.data(), item)) continue;
+				GcPackedAln item;
+				if (!buildAlignment(seed, fs.ref, results.data(), traces, item)) continue;
 				if (item.alignmentEnd == item.alignmentStart) continue;
-				kept.emplace_back(std::move(item));
+				kept.emplace_back(item);
 			}
 			if (out[r].dropped) break;
 			lastFragExtended[r] = s2SeedsExtended[r] - before;
-			for (const GcAlnItem& alignment : kept)
+			for (const GcPackedAln& alignment : kept)
 			{
 				AnchorRec a; a.x = f.l; a.y = f.l + len - 1;
-				for (const GcTraceItem& t : alignment.trace)
+				uint32_t n = alignment.size();
+				for (uint32_t k = 0; k < n; k++)
 				{
-					size_t node = g.unitigNode(t.node, t.nodeOffset);
+					size_t node = gcpipe::packedSplitNode(g, alignment, k);
 					if (a.path.empty() || node != a.path.back()) a.path.push_back(node);
 				}
-				const GcTraceItem& t0 = alignment.trace[0]; const GcTraceItem& t1 = alignment.trace.back();
-				a.firstNode = g.unitigNode(t0.node, t0.nodeOffset); a.firstOffset = t0.nodeOffset - g.nodeOffset[a.firstNode];
-				a.lastNode = g.unitigNode(t1.node, t1.nodeOffset); a.lastOffset = t1.nodeOffset - g.nodeOffset[a.lastNode];
+				int n0, n1; size_t o0, o1;
+				gcpipe::packedNodePos(g, alignment, 0, n0, o0);
+				gcpipe::packedNodePos(g, alignment, n - 1, n1, o1);
+				a.firstNode = a.path[0]; a.firstOffset = o0 - g.nodeOffset[a.firstNode];
+				a.lastNode = a.path.back(); a.lastOffset = o1 - g.nodeOffset[a.lastNode];
 				anchors[r].push_back(std::move(a));
 			}
 		}
@@ -706,17 +800,27 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		if (!needGa && !needClc) continue;
 		readOffInBuf[r] = nwBuf.size();
 		nwBuf += reads[r].sequence;
+		// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
+		// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a
+		// starting point -- the kernel doubles the cutoff until the pass succeeds, like edlib does from 64.
+		int32_t kHint = 0;
+		if (needGa)
+		{
+			const GcAlnItem& a0 = longAlns[r][0];
+			size_t ub = a0.alignmentScore + a0.alignmentStart + (reads[r].sequence.size() - a0.alignmentEnd);
+			if (ub <= reads[r].sequence.size() / 4) kHint = (int32_t)ub;
+		}
 		if (needGa)
 		{
 			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)longPathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-			it.k_hint = 0; it.want_path = 0;
+			it.k_hint = kHint; it.want_path = 0;
 			nwBuf += longPathSeq[r];
 			gaItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 		}
 		if (needClc)
 		{
 			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-			it.k_hint = 0; it.want_path = 0;
+			it.k_hint = kHint; it.want_path = 0;
 			nwBuf += pathSeq[r];
 			clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 		}

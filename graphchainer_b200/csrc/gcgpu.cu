@@ -69,7 +69,8 @@ struct gcgpu_ctx
 	uint32_t* d_pathsStart = nullptr; uint32_t* d_pathsK = nullptr; uint32_t* d_backStart = nullptr; uint32_t* d_backNode = nullptr; uint32_t* d_backK = nullptr;
 	bool haveMpc = false;
 	GcMpcView mpc;
-	DevBuf seqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc;
+	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc;
+	uint64_t seqResident = ~0ULL; // bytes of the K1 sequence buffer currently on the device
 	float lastKernelMs = 0;
 	uint64_t launches = 0;
 };
@@ -162,7 +163,7 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt);
 	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
 	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
-	ctx->seqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
+	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -229,6 +230,14 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	return GCGPU_OK;
 }
 
+extern "C" void* gcgpu_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+extern "C" void gcgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" float gcgpu_last_kernel_ms(gcgpu_ctx* ctx) { return ctx ? ctx->lastKernelMs : 0.f; }
 extern "C" uint64_t gcgpu_launch_count(gcgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -245,8 +254,13 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		if (items[i].seq_len < 0 || items[i].seq_offset + (uint64_t)items[i].seq_len > seq_bytes || items[i].node >= ctx->numNodes || items[i].seq_len >= (1 << 24))
 			return setError(GCGPU_ERR_ARG, "gcgpu_extend: item " + std::to_string(i) + " out of range");
 	}
-	CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
-	if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (seq)
+	{
+		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
+		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->seqResident = seq_bytes;
+	}
+	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_extend: seq == NULL but no sequence buffer of this size is resident");
 	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK1Result)));
 
 	// work list, longest first so that the threads of a warp carry similar loads
@@ -541,6 +555,112 @@ __global__ void __launch_bounds__(64) gc_k3_path_kernel(const uint8_t* __restric
 	out[d.resultIndex] = o;
 }
 
+
+// ---- warp form of the edit path (gc_k3w_path): one warp = one alignment, fetched from a shared counter
+struct GcK3wDeviceExec
+{
+	int lane;
+	__device__ __forceinline__ bool leader() const { return lane == 0; }
+	__device__ __forceinline__ void sync() const { __syncwarp(); }
+	__device__ __forceinline__ uint32_t fromLeader(uint32_t v) const { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+	__device__ __noinline__ uint64_t pass(const GcK3wPass& p, int NB, GcK3Block* out)
+	{
+		uint32_t w;
+		switch (NB)
+		{
+			case 1: w = gc_k3w_run_pass<1>(p, out); break;
+			case 2: w = gc_k3w_run_pass<2>(p, out); break;
+			case 4: w = gc_k3w_run_pass<4>(p, out); break;
+			default: w = gc_k3w_run_pass<8>(p, out); break;
+		}
+		for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, off);
+		return w;
+	}
+	// first row r in [0, q-2] with left[r] + right[r+1] == best (edlib.cpp:1330-1337), -1 if none
+	__device__ __forceinline__ int32_t firstSplitRow(const GcK3Block* A, int32_t lfb, int32_t llb, const GcK3Block* B, int32_t rfb, int32_t rlb, int32_t q, int32_t best) const
+	{
+		const int32_t INF = 1 << 29;
+		for (int32_t base = 0; base <= q - 2; base += 32)
+		{
+			int32_t r = base + lane;
+			bool ok = false;
+			if (r <= q - 2)
+			{
+				int32_t b = r >> 6; int32_t ls = (b < lfb || b > llb) ? INF : gc_k3_cell(A[b], r);
+				int32_t rr = q - 1 - (r + 1); int32_t rb = rr >> 6; int32_t rs = (rb < rfb || rb > rlb) ? INF : gc_k3_cell(B[rb], rr);
+				ok = ls + rs == best;
+			}
+			uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+			if (m) return base + __ffs(m) - 1;
+		}
+		return -1;
+	}
+};
+
+static const uint32_t K3W_STORE_CAP = 52432, K3W_STACK_CAP = 96;
+static size_t k3wPathSlotBytes(int32_t maxQ)
+{
+	size_t nb = (size_t)(maxQ + 63) / 64 + 1;
+	return alignUp(2 * nb * 4 * 8 + 2 * nb * sizeof(GcK3Block) + (size_t)K3W_STORE_CAP * sizeof(GcK3Block) + (size_t)K3W_STACK_CAP * sizeof(GcK3Frame) + 64, 128);
+}
+
+__global__ void __launch_bounds__(128) gc_k3w_path_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* slots, size_t slotBytes, int32_t maxQ,
+	uint8_t* opsArena, GcK3Out* out, uint32_t* counter)
+{
+	int lane = threadIdx.x & 31;
+	uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint8_t* base = slots + (size_t)slot * slotBytes;
+	size_t nbMax = (size_t)(maxQ + 63) / 64 + 1;
+	uint64_t* peq = (uint64_t*)base;
+	uint64_t* rpeq = peq + 4 * nbMax;
+	GcK3Block* blocksA = (GcK3Block*)(rpeq + 4 * nbMax);
+	GcK3Block* blocksB = blocksA + nbMax;
+	GcK3Block* store = blocksB + nbMax;
+	GcK3Frame* stack = (GcK3Frame*)(store + K3W_STORE_CAP);
+	while (true)
+	{
+		uint32_t w = 0;
+		if (lane == 0) w = atomicAdd(counter, 1u);
+		w = __shfl_sync(0xFFFFFFFFu, w, 0);
+		if (w >= n) return;
+		GcK3Desc d = descs[w];
+		int32_t q = d.q, t = d.t;
+		int32_t nb = (q + 63) / 64; if (nb < 1) nb = 1;
+		const uint8_t* query = seq + d.qOff;
+		for (int32_t b = lane; b < nb; b += 32)
+		{
+			uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+			int32_t lim = q - b * 64; if (lim > 64) lim = 64;
+			for (int32_t i = 0; i < lim; i++)
+			{
+				uint8_t c = query[b * 64 + i];
+				uint8_t rc = query[q - 1 - (b * 64 + i)];
+				uint64_t bit = 1ULL << i;
+				e0 |= c == 0 ? bit : 0; e1 |= c == 1 ? bit : 0; e2 |= c == 2 ? bit : 0; e3 |= c == 3 ? bit : 0;
+				f0 |= rc == 0 ? bit : 0; f1 |= rc == 1 ? bit : 0; f2 |= rc == 2 ? bit : 0; f3 |= rc == 3 ? bit : 0;
+			}
+			peq[b] = e0; peq[nb + b] = e1; peq[2 * (size_t)nb + b] = e2; peq[3 * (size_t)nb + b] = e3;
+			rpeq[b] = f0; rpeq[nb + b] = f1; rpeq[2 * (size_t)nb + b] = f2; rpeq[3 * (size_t)nb + b] = f3;
+		}
+		__syncwarp();
+		GcK3wPathWorkspace ws;
+		ws.peq = peq; ws.rpeq = rpeq; ws.nbTotal = nb; ws.qTotal = q; ws.tTotal = t; ws.blocksA = blocksA; ws.blocksB = blocksB;
+		ws.store = store; ws.storeCap = K3W_STORE_CAP; ws.stack = stack; ws.stackCap = K3W_STACK_CAP; ws.maxNB = 8;
+		GcK3wDeviceExec ex; ex.lane = lane;
+		uint64_t work = 0; uint32_t nOps = 0;
+		bool ok = gc_k3w_path(ex, ws, seq + d.tOff, d.best, opsArena + d.opsOff, nOps, d.opsCap, work);
+		if (lane == 0)
+		{
+			GcK3Out o = out[d.resultIndex];
+			o.opsLen = ok ? nOps : 0;
+			o.pad = ok ? 0u : 1u; // 1 = the warp form gave up (band wider than its register budget): the host re-runs the item in the thread form
+			o.blocks += work;
+			out[d.resultIndex] = o;
+		}
+		__syncwarp();
+	}
+}
+
 struct GcByteCopyDesc { uint64_t src; uint64_t dst; uint32_t len; uint32_t pad; };
 __global__ void gc_bytes_gather_kernel(const GcByteCopyDesc* __restrict__ descs, uint32_t n, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst)
 {
@@ -565,13 +685,13 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		if (it.query_len < 0 || it.target_len < 0 || it.query_offset + (uint64_t)it.query_len > seq_bytes || it.target_offset + (uint64_t)it.target_len > seq_bytes)
 			return setError(GCGPU_ERR_ARG, "gcgpu_nw: item " + std::to_string(i) + " out of range");
 	}
-	CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
+	CUDA_TRY(ctx->nwSeqBuf.ensure(seq_bytes + 16));
 	float ms = 0;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (seq_bytes)
 	{
-		CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		gc_k3_encode_kernel<<<1184, 256, 0, ctx->stream>>>((uint8_t*)ctx->seqBuf.p, seq_bytes);
+		CUDA_TRY(cudaMemcpyAsync(ctx->nwSeqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		gc_k3_encode_kernel<<<1184, 256, 0, ctx->stream>>>((uint8_t*)ctx->nwSeqBuf.p, seq_bytes);
 		ctx->launches++;
 	}
 	// ---- distance pass, longest first
@@ -593,7 +713,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(ctx->descBuf.ensure((size_t)n * sizeof(GcK3Desc)));
 	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK3Out)));
 	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
-	gc_k3w_distance_kernel<0><<<(n + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+	gc_k3w_distance_kernel<0><<<(n + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -617,8 +737,8 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		(void)blocksBefore;
 		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), (size_t)m * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		if (cls == 1) gc_k3w_distance_kernel<1><<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
-		else gc_k3_distance_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		if (cls == 1) gc_k3w_distance_kernel<1><<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		else gc_k3_distance_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -636,7 +756,8 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	if (!want.empty())
 	{
 		std::vector<GcK3Desc> pd(want.size());
-		size_t ws = 0; uint64_t opsTotal = 0;
+		uint64_t opsTotal = 0;
+		int32_t maxQ = 1;
 		for (size_t k = 0; k < want.size(); k++)
 		{
 			const gcgpu_nw_item& it = items[want[k]];
@@ -645,15 +766,22 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			d.resultIndex = want[k];
 			d.opsCap = (uint32_t)(it.query_len + it.target_len + 8);
 			d.opsOff = opsTotal; opsOffOfItem[want[k]] = opsTotal; opsTotal += d.opsCap;
-			d.wsOff = ws; ws += k3PathWorkspaceBytes(it.query_len);
+			d.wsOff = 0;
+			if (it.query_len > maxQ) maxQ = it.query_len;
 		}
-		CUDA_TRY(ctx->arena.ensure(ws));
+		uint32_t m = (uint32_t)pd.size();
+		// persistent warps: one workspace slot per resident warp, items fetched from a counter (longest first)
+		uint32_t ctas = std::min<uint32_t>((m + 3) / 4, 148 * 4);
+		size_t slotBytes = k3wPathSlotBytes(maxQ);
+		size_t slotsTotal = slotBytes * ctas * 4;
+		CUDA_TRY(ctx->arena.ensure(slotsTotal + 256));
 		CUDA_TRY(ctx->traceArena.ensure(opsTotal + 16));
 		CUDA_TRY(ctx->descBuf.ensure(pd.size() * sizeof(GcK3Desc)));
 		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
-		uint32_t m = (uint32_t)pd.size();
+		uint32_t* counter = (uint32_t*)((uint8_t*)ctx->arena.p + slotsTotal);
+		CUDA_TRY(cudaMemsetAsync(counter, 0, 4, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		gc_k3_path_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
+		gc_k3w_path_kernel<<<ctas, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, slotBytes, maxQ, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p, counter);
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -661,6 +789,26 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
+		// items the warp form gave up on (band beyond its register budget): thread form
+		std::vector<GcK3Desc> rd;
+		for (const GcK3Desc& d : pd) if (hout[d.resultIndex].pad == 1) rd.push_back(d);
+		if (!rd.empty())
+		{
+			size_t ws = 0;
+			for (GcK3Desc& d : rd) { d.wsOff = ws; ws += k3PathWorkspaceBytes(d.q); }
+			CUDA_TRY(ctx->arena.ensure(ws));
+			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+			uint32_t m2 = (uint32_t)rd.size();
+			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+			gc_k3_path_kernel<<<(m2 + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m2, (uint8_t*)ctx->arena.p, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
+			ctx->launches++;
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+			CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+			ctx->lastKernelMs += ms;
+		}
 	}
 	uint64_t used = 0;
 	bool internal = false;

@@ -126,7 +126,9 @@ typedef struct gcgpu_ext_result
 #define GCGPU_TRACE_SWITCH(t) ((int)(((t) >> 38) & 1))
 #define GCGPU_TRACE_SEQPOS(t) ((int32_t)(((t) >> 39) & 0x1FFFFFF) - 1)
 
-/* results[n]; traces[trace_capacity] receives all traces back to back; *trace_used = entries
+/* `seq` may be NULL: the sequence buffer uploaded by the previous gcgpu_extend call on this ctx is
+ * reused (a batch of reads is extended in several calls; its codes cross PCIe once).
+ * results[n]; traces[trace_capacity] receives all traces back to back; *trace_used = entries
  * written (if it exceeds trace_capacity the call fails with GCGPU_ERR_ARG and *trace_used
  * tells the required size).  All buffers are host memory.                                  */
 int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
@@ -183,6 +185,11 @@ typedef struct gcgpu_anchor
 
 int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* read_offsets, uint32_t num_reads,
                 uint32_t* chain, uint32_t* chain_len, int64_t* chain_score);
+
+/* Page-locked host memory for the caller-owned buffers above (cudaHostAlloc): copies to and from
+ * such buffers run at full PCIe rate and asynchronously.  Plain malloc'd buffers work too. */
+void* gcgpu_host_alloc(size_t bytes);
+void gcgpu_host_free(void* p);
 
 /* device time of the kernels of the last call on this ctx, in milliseconds (CUDA events) */
 float gcgpu_last_kernel_ms(gcgpu_ctx* ctx);

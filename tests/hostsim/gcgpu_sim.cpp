@@ -6,6 +6,7 @@
 // reference's golden output.  It lives under tests/, is never built into the package and
 // never shipped: the product (libgcgpu.so) has no CPU path.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ struct gcgpu_ctx
 	int bandwidth;
 	uint32_t numNodes;
 	uint64_t launches = 0;
+	std::vector<uint8_t> seqCopy;
 };
 static std::string g_err;
 
@@ -46,8 +48,13 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* c) { delete c; }
 extern "C" float gcgpu_last_kernel_ms(gcgpu_ctx*) { return 0; }
 extern "C" uint64_t gcgpu_launch_count(gcgpu_ctx* c) { return c->launches; }
 
-extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t, const gcgpu_ext_item* items, uint32_t n, gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used)
+extern "C" void* gcgpu_host_alloc(size_t bytes) { return malloc(bytes); }
+extern "C" void gcgpu_host_free(void* p) { free(p); }
+
+extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seqIn, uint64_t seqBytes, const gcgpu_ext_item* items, uint32_t n, gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used)
 {
+	if (seqIn) ctx->seqCopy.assign(seqIn, seqIn + seqBytes); // "resident" buffer of the real library
+	const uint8_t* seq = ctx->seqCopy.data();
 	std::vector<std::vector<uint64_t>> tr(n);
 	bool internal = false;
 	#pragma omp parallel for schedule(dynamic, 64)

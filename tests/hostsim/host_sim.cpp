@@ -130,6 +130,47 @@ static uint64_t k3wPassSimNB(const GcK3wPass& p, int NB, GcK3Block* blocksOut)
 		default: return k3wPassSim<8>(p, blocksOut);
 	}
 }
+
+struct K3wHostExec
+{
+	bool leader() const { return true; }
+	void sync() const {}
+	uint32_t fromLeader(uint32_t v) const { return v; }
+	uint64_t pass(const GcK3wPass& p, int NB, GcK3Block* out) { return k3wPassSimNB(p, NB, out); }
+	int32_t firstSplitRow(const GcK3Block* A, int32_t lfb, int32_t llb, const GcK3Block* B, int32_t rfb, int32_t rlb, int32_t q, int32_t best)
+	{
+		const int32_t INF = 1 << 29;
+		for (int32_t r = 0; r <= q - 2; r++)
+		{
+			int32_t b = r >> 6; int32_t ls = (b < lfb || b > llb) ? INF : gc_k3_cell(A[b], r);
+			int32_t rr = q - 1 - (r + 1); int32_t rb = rr >> 6; int32_t rs = (rb < rfb || rb > rlb) ? INF : gc_k3_cell(B[rb], rr);
+			if (ls + rs == best) return r;
+		}
+		return -1;
+	}
+};
+// the edit path through the warp form; returns "" on internal failure
+static std::string k3wPathSim(const std::vector<uint8_t>& q, const std::vector<uint8_t>& t, int32_t best, uint64_t& work)
+{
+	int32_t Q = (int32_t)q.size(), T = (int32_t)t.size();
+	int32_t nb = (Q + 63) / 64; if (nb < 1) nb = 1;
+	std::vector<uint64_t> peq(4 * (size_t)nb), rpeq(4 * (size_t)nb);
+	gc_k3_build_peq(q.data(), Q, peq.data(), nb);
+	std::vector<uint8_t> rq(q.rbegin(), q.rend());
+	gc_k3_build_peq(rq.data(), Q, rpeq.data(), nb);
+	std::vector<GcK3Block> ba(nb + 1), bb(nb + 1), store(60000);
+	std::vector<GcK3Frame> stack(128);
+	GcK3wPathWorkspace w;
+	w.peq = peq.data(); w.rpeq = rpeq.data(); w.nbTotal = nb; w.qTotal = Q; w.tTotal = T; w.blocksA = ba.data(); w.blocksB = bb.data();
+	w.store = store.data(); w.storeCap = (uint32_t)store.size(); w.stack = stack.data(); w.stackCap = (uint32_t)stack.size(); w.maxNB = 8;
+	std::vector<uint8_t> ops((size_t)Q + T + 8);
+	uint32_t nOps = 0;
+	K3wHostExec ex;
+	if (!gc_k3w_path(ex, w, t.data(), best, ops.data(), nOps, (uint32_t)ops.size(), work)) return "!";
+	std::string got(nOps, '0');
+	for (uint32_t i = 0; i < nOps; i++) got[i] = (char)('0' + ops[i]);
+	return got;
+}
 static int roundNB(int nb) { return nb <= 4 ? nb : 8; }
 // edit distance through the warp form; extraNB > 0 forces a larger group size than necessary
 static int32_t k3wDistanceSim(const uint64_t* peq, int32_t nb, int32_t Q, const uint8_t* t, int32_t T, int32_t kStart, int extraNB, uint64_t& work)
@@ -169,6 +210,23 @@ static int k3wMain(const char* stagesPath)
 		int32_t got = k3wDistanceSim(peq.data(), nb, Q, t.data(), T, kStart, extraNB, work);
 		total++;
 		if (got != want) { bad++; if (bad <= 5) std::cerr << "K3W mismatch q=" << Q << " t=" << T << " extraNB=" << extraNB << " kStart=" << kStart << ": got " << got << " want " << want << std::endl; }
+		if (Q > 0 && T > 0 && extraNB == 0 && kStart == 0)
+		{
+			// edit path: warp form vs thread form (the latter is pinned against edlib's op strings by mode k3)
+			std::vector<uint8_t> rq(q.rbegin(), q.rend());
+			std::vector<uint64_t> rpeq(4 * (size_t)nb);
+			gc_k3_build_peq(rq.data(), Q, rpeq.data(), nb);
+			std::vector<GcK3Block> bb(nb + 1), store(60000); std::vector<uint32_t> colStart((size_t)T + 1); std::vector<GcK3Frame> stack(128);
+			GcK3PathWorkspace w;
+			w.peq = peq.data(); w.rpeq = rpeq.data(); w.nbTotal = nb; w.qTotal = Q; w.tTotal = T; w.blocksA = ba.data(); w.blocksB = bb.data();
+			w.store = store.data(); w.storeCap = (uint32_t)store.size(); w.colStart = colStart.data(); w.colCap = (uint32_t)colStart.size(); w.stack = stack.data(); w.stackCap = (uint32_t)stack.size();
+			std::vector<uint8_t> ops((size_t)Q + T + 8); uint32_t nOps = 0; uint64_t wk = 0;
+			bool okRef = gc_k3_path(w, t.data(), want, ops.data(), nOps, (uint32_t)ops.size(), wk);
+			std::string ref(nOps, '0'); for (uint32_t i = 0; i < nOps; i++) ref[i] = (char)('0' + ops[i]);
+			std::string gotPath = k3wPathSim(q, t, want, work);
+			total++;
+			if (!okRef || gotPath != ref) { bad++; if (bad <= 5) std::cerr << "K3W path mismatch q=" << Q << " t=" << T << " d=" << want << " (ref ok " << okRef << ", got len " << gotPath.size() << " ref len " << ref.size() << ")" << std::endl; }
+		}
 		// a Hirschberg-style half pass on a sub-query with a non-aligned offset, forward and reversed
 		if (Q > 200 && T > 200 && want > 0)
 		{
@@ -228,6 +286,7 @@ static int k3wMain(const char* stagesPath)
 	// the golden NW items as well
 	std::ifstream in(stagesPath);
 	std::string line, readSeq;
+	std::vector<uint8_t> lastQ, lastT;
 	while (std::getline(in, line))
 	{
 		if (line.compare(0, 5, "READ ") == 0) { std::istringstream ss(line); std::string tag, name; ss >> tag >> name >> readSeq; }
@@ -239,6 +298,17 @@ static int k3wMain(const char* stagesPath)
 			for (size_t i = 0; i < q.size(); i++) q[i] = k3code(ps[i]);
 			for (size_t i = 0; i < t.size(); i++) t[i] = k3code(readSeq[i]);
 			check(q, t, 0, 0);
+			lastQ = q; lastT = t;
+		}
+		else if (line.compare(0, 6, "EDLIB ") == 0)
+		{
+			std::istringstream ss(line); std::string tag, first; ss >> tag >> first;
+			if (first == "ERR") continue;
+			int d = atoi(first.c_str()), len, st, en; std::string ops;
+			ss >> len >> st >> en >> ops;
+			std::string got = k3wPathSim(lastQ, lastT, d, work);
+			total++;
+			if (got != ops) { bad++; if (bad <= 5) std::cerr << "K3W golden path mismatch d=" << d << std::endl; }
 		}
 	}
 	std::cout << "{\"mode\":\"k3w\",\"items\":" << total << ",\"mismatches\":" << bad << ",\"columns\":" << work << ",\"columns_thread_form\":" << workRef << "}" << std::endl;

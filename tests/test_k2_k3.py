@@ -12,7 +12,7 @@ from conftest import REFDUMP
 import stages
 
 
-@pytest.mark.parametrize("mode", ["k2", "k3"])
+@pytest.mark.parametrize("mode", ["k2", "k3", "k3w"])
 def test_logic_on_cpu_matches_golden(hostsim, golden_files, mode):
     for name, (idx, st) in golden_files.items():
         out = subprocess.run([hostsim, mode, idx, st], capture_output=True, text=True)
