@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libgcalign.so")
 
 
 class Options(C.Structure):
-    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("initial_bandwidth", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("initial_bandwidth", C.c_int32), ("streams", C.c_int32),
                 ("colinear_gap", C.c_int64), ("colinear_split_len", C.c_int64), ("colinear_split_gap", C.c_int64), ("batch_bp", C.c_uint64)]
 
 
@@ -80,11 +80,11 @@ class ReadBatch:
 
 
 class Aligner:
-    def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0):
+    def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0, streams: int = 0):
         self.lib = load()
         o = Options()
         self.lib.gcalign_default_options(C.byref(o))
-        o.device, o.host_threads = device, host_threads
+        o.device, o.host_threads, o.streams = device, host_threads, streams
         o.colinear_split_len, o.colinear_split_gap, o.colinear_gap, o.batch_bp = split_len, split_gap, colinear_gap, batch_bp
         h = C.c_void_p()
         rc = self.lib.gcalign_open(graph_path.encode(), C.byref(o), C.byref(h))

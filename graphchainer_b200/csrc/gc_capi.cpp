@@ -1,7 +1,10 @@
 // libgcalign: the host pipeline behind a C ABI (include/gcalign.h).
 #include <omp.h>
+#include <atomic>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include "../../include/gcalign.h"
 #include "gc_pipeline.h"
@@ -11,19 +14,25 @@
 static thread_local std::string g_alignError;
 static int fail(int code, const std::string& msg) { g_alignError = msg; return code; }
 
+// one batch in flight: a libgcgpu context (own stream + workspaces) and a pipeline whose page-locked
+// buffers persist across calls
+struct GcAlignWorker
+{
+	gcgpu_ctx* ctx = nullptr;
+	std::unique_ptr<GcPipeline> pipeline;
+};
 struct gcalign
 {
 	GcHostGraph graph;
-	gcgpu_ctx* ctx = nullptr;
+	std::vector<GcAlignWorker> workers;
 	gcalign_options opts;
 	GcPipelineParams pipe;
-	std::unique_ptr<GcPipeline> pipeline; // persistent: its page-locked buffers are reused by every call
 };
 
 extern "C" void gcalign_default_options(gcalign_options* o)
 {
 	memset(o, 0, sizeof(*o));
-	o->device = 0; o->host_threads = 0; o->initial_bandwidth = 10;
+	o->device = 0; o->host_threads = 0; o->initial_bandwidth = 10; o->streams = 0;
 	o->colinear_gap = 10000; o->colinear_split_len = 35; o->colinear_split_gap = 35; o->batch_bp = 0;
 }
 extern "C" const char* gcalign_last_error(void) { return g_alignError.c_str(); }
@@ -54,8 +63,13 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	gg.comp_map = g.compMap.data(); gg.comp_idx = g.compIdx.data(); gg.comp_start = g.compStart.data(); gg.topo_ids = g.topoIds.data();
 	gg.paths_start = g.pathsStart.data(); gg.paths_k = g.pathsK.data(); gg.back_start = g.backStart.data(); gg.back_node = g.backNode.data(); gg.back_k = g.backK.data();
 	gcgpu_params gp; gp.initial_bandwidth = h->opts.initial_bandwidth;
-	int rc = gcgpu_create(h->opts.device, &gg, &gp, &h->ctx);
-	if (rc != GCGPU_OK) { std::string msg = gcgpu_last_error(); delete h; return fail(rc, "gcalign_open: " + msg); }
+	int streams = h->opts.streams > 0 ? h->opts.streams : 4;
+	h->workers.resize(streams);
+	for (int w = 0; w < streams; w++)
+	{
+		int rc = gcgpu_create(h->opts.device, &gg, &gp, &h->workers[w].ctx);
+		if (rc != GCGPU_OK) { std::string msg = gcgpu_last_error(); gcalign_close(h); return fail(rc, "gcalign_open: " + msg); }
+	}
 	h->pipe.colinearGap = h->opts.colinear_gap; h->pipe.colinearSplitLen = h->opts.colinear_split_len; h->pipe.colinearSplitGap = h->opts.colinear_split_gap;
 	*out = h;
 	return GCGPU_OK;
@@ -64,8 +78,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 extern "C" void gcalign_close(gcalign* h)
 {
 	if (!h) return;
-	h->pipeline.reset();
-	if (h->ctx) gcgpu_destroy(h->ctx);
+	for (auto& w : h->workers) { w.pipeline.reset(); if (w.ctx) gcgpu_destroy(w.ctx); }
 	delete h;
 }
 
@@ -75,73 +88,112 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	if (!h || (num_reads && (!seqs || !seq_offsets))) return fail(GCGPU_ERR_ARG, "gcalign_align: null argument");
 	if (gam_used) *gam_used = 0;
 	if (stats) memset(stats, 0, sizeof(*stats));
-	if (h->opts.host_threads > 0) omp_set_num_threads(h->opts.host_threads);
+	int hostThreads = h->opts.host_threads > 0 ? h->opts.host_threads : omp_get_max_threads();
 	uint64_t batchBp = h->opts.batch_bp ? h->opts.batch_bp : (8u << 20);
-	uint64_t launches0 = gcgpu_launch_count(h->ctx);
-	uint64_t used = 0;
-	try
+	// batches of ~batch_bp read bases, handed to the workers in order
+	std::vector<std::pair<uint32_t, uint32_t>> batches;
+	for (uint32_t first = 0; first < num_reads; )
 	{
-		if (!h->pipeline) h->pipeline.reset(new GcPipeline(h->graph, h->ctx, h->pipe));
-		GcPipeline& pipeline = *h->pipeline;
-		pipeline.stats = GcPipelineStats();
-		std::vector<GcRead> batch;
-		std::vector<GcReadResult> results;
-		for (uint32_t first = 0; first < num_reads; )
+		uint64_t bp = 0;
+		uint32_t r = first;
+		for (; r < num_reads && (bp < batchBp || r == first); r++) bp += seq_offsets[r + 1] - seq_offsets[r];
+		batches.emplace_back(first, r);
+		first = r;
+	}
+	size_t W = std::min(h->workers.size(), std::max<size_t>(1, batches.size()));
+	int threadsPerWorker = std::max(1, hostThreads / (int)W);
+	std::vector<std::vector<std::string>> records(batches.size());
+	std::vector<std::vector<GcReadResult>> allResults(batches.size());
+	std::vector<uint64_t> launches0(W);
+	std::atomic<size_t> nextBatch(0);
+	std::mutex errMutex; std::string error;
+	GcPipelineStats total;
+	auto work = [&](size_t w)
+	{
+		omp_set_num_threads(threadsPerWorker);
+		GcAlignWorker& wk = h->workers[w];
+		try
 		{
-			batch.clear();
-			uint64_t bp = 0;
-			uint32_t r = first;
-			for (; r < num_reads && (bp < batchBp || r == first); r++)
+			if (!wk.pipeline) wk.pipeline.reset(new GcPipeline(h->graph, wk.ctx, h->pipe));
+			GcPipeline& pipeline = *wk.pipeline;
+			pipeline.stats = GcPipelineStats();
+			std::vector<GcRead> batch;
+			while (true)
 			{
-				GcRead rd;
-				rd.sequence.assign(seqs + seq_offsets[r], seq_offsets[r + 1] - seq_offsets[r]);
-				if (names && name_offsets) rd.name.assign(names + name_offsets[r], name_offsets[r + 1] - name_offsets[r]);
-				else rd.name = "read_" + std::to_string(r);
-				bp += rd.sequence.size();
-				batch.push_back(std::move(rd));
-			}
-			pipeline.alignBatch(batch, results);
-			std::vector<std::string> records(batch.size());
-			if (gam_out)
-			{
-				#pragma omp parallel for schedule(dynamic, 4)
-				for (size_t i = 0; i < batch.size(); i++)
+				size_t bi = nextBatch.fetch_add(1);
+				if (bi >= batches.size()) break;
+				{ std::lock_guard<std::mutex> lock(errMutex); if (!error.empty()) break; }
+				batch.clear();
+				for (uint32_t r = batches[bi].first; r < batches[bi].second; r++)
 				{
-					if (results[i].alignments.empty()) continue;
-					std::vector<gcout::Alignment> alns;
-					for (const GcAlnItem& item : results[i].alignments) alns.push_back(gcout::toAlignment(h->graph, batch[i].name, batch[i].sequence, item));
-					records[i] = gcout::gamRecord(alns);
+					GcRead rd;
+					rd.sequence.assign(seqs + seq_offsets[r], seq_offsets[r + 1] - seq_offsets[r]);
+					if (names && name_offsets) rd.name.assign(names + name_offsets[r], name_offsets[r + 1] - name_offsets[r]);
+					else rd.name = "read_" + std::to_string(r);
+					batch.push_back(std::move(rd));
 				}
-			}
-			for (size_t i = 0; i < batch.size(); i++)
-			{
-				const GcReadResult& res = results[i];
-				if (summaries)
+				std::vector<GcReadResult>& results = allResults[bi];
+				pipeline.alignBatch(batch, results);
+				records[bi].resize(batch.size());
+				if (gam_out)
 				{
-					gcalign_read_summary& s = summaries[first + i];
-					s.num_alignments = (uint32_t)res.alignments.size(); s.used_chain = res.usedChain ? 1 : 0; s.anchors = (uint32_t)res.anchors; s.chained = (uint32_t)res.chained;
-					s.path_bp = res.pathBp; s.clc_score = res.clcScore; s.long_edit_distance = res.hasLong ? res.longEditDistance : (uint64_t)-1;
-					s.gam_offset = used; s.gam_size = records[i].size();
+					#pragma omp parallel for schedule(dynamic, 4)
+					for (size_t i = 0; i < batch.size(); i++)
+					{
+						if (results[i].alignments.empty()) continue;
+						std::vector<gcout::Alignment> alns;
+						for (const GcAlnItem& item : results[i].alignments) alns.push_back(gcout::toAlignment(h->graph, batch[i].name, batch[i].sequence, item));
+						records[bi][i] = gcout::gamRecord(alns);
+					}
 				}
-				if (stats) { stats->seeds_found += res.seedsFound; if (!res.alignments.empty()) stats->seeds_extended += res.seedsExtended; }
-				if (gam_out && !records[i].empty())
-				{
-					if (used + records[i].size() > gam_capacity) return fail(GCGPU_ERR_ARG, "gcalign_align: GAM buffer too small");
-					memcpy(gam_out + used, records[i].data(), records[i].size());
-					used += records[i].size();
-				}
+				// the traces are not needed past this point: keep only what the summaries read
+				for (auto& res : results) for (auto& a : res.alignments) { std::vector<GcTraceItem>().swap(a.trace); }
 			}
-			first = r;
+			std::lock_guard<std::mutex> lock(errMutex);
+			const GcPipelineStats& ps = pipeline.stats;
+			total.k1Ms += ps.k1Ms; total.k2Ms += ps.k2Ms; total.k3Ms += ps.k3Ms; total.k1Items += ps.k1Items; total.k1Columns += ps.k1Columns; total.k2Anchors += ps.k2Anchors;
+			total.k3Items += ps.k3Items; total.k3Blocks += ps.k3Blocks; total.s1Rounds += ps.s1Rounds; total.s1Wasted += ps.s1Wasted;
 		}
-		if (stats)
+		catch (const std::exception& e) { std::lock_guard<std::mutex> lock(errMutex); error = e.what(); }
+	};
+	for (size_t w = 0; w < W; w++) launches0[w] = gcgpu_launch_count(h->workers[w].ctx);
+	{
+		std::vector<std::thread> threads;
+		for (size_t w = 1; w < W; w++) threads.emplace_back(work, w);
+		work(0);
+		for (auto& t : threads) t.join();
+	}
+	if (!error.empty()) return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + error);
+	uint64_t used = 0;
+	for (size_t bi = 0; bi < batches.size(); bi++)
+	{
+		uint32_t first = batches[bi].first;
+		for (size_t i = 0; i < allResults[bi].size(); i++)
 		{
-			stats->k1_ms = pipeline.stats.k1Ms; stats->k2_ms = pipeline.stats.k2Ms; stats->k3_ms = pipeline.stats.k3Ms;
-			stats->k1_items = pipeline.stats.k1Items; stats->k1_columns = pipeline.stats.k1Columns; stats->k2_anchors = pipeline.stats.k2Anchors;
-			stats->k3_items = pipeline.stats.k3Items; stats->k3_blocks = pipeline.stats.k3Blocks; stats->s1_rounds = pipeline.stats.s1Rounds;
-			stats->launches = gcgpu_launch_count(h->ctx) - launches0;
+			const GcReadResult& res = allResults[bi][i];
+			if (summaries)
+			{
+				gcalign_read_summary& s = summaries[first + i];
+				s.num_alignments = (uint32_t)res.alignments.size(); s.used_chain = res.usedChain ? 1 : 0; s.anchors = (uint32_t)res.anchors; s.chained = (uint32_t)res.chained;
+				s.path_bp = res.pathBp; s.clc_score = res.clcScore; s.long_edit_distance = res.hasLong ? res.longEditDistance : (uint64_t)-1;
+				s.gam_offset = used; s.gam_size = records[bi][i].size();
+			}
+			if (stats) { stats->seeds_found += res.seedsFound; if (!res.alignments.empty()) stats->seeds_extended += res.seedsExtended; }
+			if (gam_out && !records[bi][i].empty())
+			{
+				if (used + records[bi][i].size() > gam_capacity) return fail(GCGPU_ERR_ARG, "gcalign_align: GAM buffer too small");
+				memcpy(gam_out + used, records[bi][i].data(), records[bi][i].size());
+				used += records[bi][i].size();
+			}
 		}
 	}
-	catch (const std::exception& e) { return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + e.what()); }
+	if (stats)
+	{
+		stats->k1_ms = total.k1Ms; stats->k2_ms = total.k2Ms; stats->k3_ms = total.k3Ms;
+		stats->k1_items = total.k1Items; stats->k1_columns = total.k1Columns; stats->k2_anchors = total.k2Anchors;
+		stats->k3_items = total.k3Items; stats->k3_blocks = total.k3Blocks; stats->s1_rounds = total.s1Rounds;
+		for (size_t w = 0; w < W; w++) stats->launches += gcgpu_launch_count(h->workers[w].ctx) - launches0[w];
+	}
 	if (gam_used) *gam_used = used;
 	return GCGPU_OK;
 }

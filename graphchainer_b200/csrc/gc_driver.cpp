@@ -29,6 +29,7 @@ struct DriverParams
 	std::string outGam, outJson;
 	size_t threads = 1;
 	int gpus = 1;
+	int streams = 4;
 	int firstDevice = 0;
 	int bandwidth = 10;
 	bool shortVerbose = false;
@@ -57,6 +58,7 @@ static void usage()
 		"  --short-verbose               print the per-read progress line\n"
 		"B200 parameters:\n"
 		"  --gc-gpus N                   GPUs to use (reads are partitioned in length-balanced batches)\n"
+		"  --gc-streams N                read batches in flight per GPU [default 4]\n"
 		"  --gc-index file.gcidx         load a prebuilt graph/MPC/minimizer index\n"
 		"  --gc-save-index file.gcidx    store the index built from -g\n"
 		"  --gc-batch-bp N               read bases per GPU batch [default 8388608]\n";
@@ -83,6 +85,7 @@ static DriverParams parseArgs(int argc, char** argv)
 		else if (a == "--sampling-step") p.samplingStep = std::stod(next()); // README contract: a double (the reference parses long long)
 		else if (a == "--short-verbose") p.shortVerbose = true;
 		else if (a == "--gc-gpus") p.gpus = std::stoi(next());
+		else if (a == "--gc-streams") p.streams = std::max(1, std::stoi(next()));
 		else if (a == "--gc-device") p.firstDevice = std::stoi(next());
 		else if (a == "--gc-index") p.indexFile = next();
 		else if (a == "--gc-save-index") p.saveIndexFile = next();
@@ -226,10 +229,12 @@ int main(int argc, char** argv)
 	gg.paths_start = graph.pathsStart.data(); gg.paths_k = graph.pathsK.data(); gg.back_start = graph.backStart.data(); gg.back_node = graph.backNode.data(); gg.back_k = graph.backK.data();
 	gcgpu_params gp; gp.initial_bandwidth = params.bandwidth;
 	std::vector<gcgpu_ctx*> ctxs;
-	for (int d = 0; d < params.gpus; d++)
+	// one context (stream + workspaces) per batch in flight: worker w runs on device w % gpus
+	const int numWorkers = params.gpus * params.streams;
+	for (int d = 0; d < numWorkers; d++)
 	{
 		gcgpu_ctx* ctx = nullptr;
-		if (gcgpu_create(params.firstDevice + d, &gg, &gp, &ctx) != GCGPU_OK) { std::cerr << "gcgpu_create(device " << params.firstDevice + d << ") failed: " << gcgpu_last_error() << std::endl; return 1; }
+		if (gcgpu_create(params.firstDevice + d % params.gpus, &gg, &gp, &ctx) != GCGPU_OK) { std::cerr << "gcgpu_create(device " << params.firstDevice + d << ") failed: " << gcgpu_last_error() << std::endl; return 1; }
 		ctxs.push_back(ctx);
 	}
 
@@ -272,6 +277,7 @@ int main(int argc, char** argv)
 	};
 	auto worker = [&](int d)
 	{
+		omp_set_num_threads(std::max<int>(1, (int)params.threads / numWorkers));
 		GcPipeline pipeline(graph, ctxs[d], params.pipe);
 		std::vector<GcRead> batch;
 		std::vector<GcReadResult> results;
@@ -326,7 +332,7 @@ int main(int argc, char** argv)
 	};
 	std::vector<std::thread> workers;
 	std::string workerError;
-	for (int d = 0; d < params.gpus; d++) workers.emplace_back([&, d]() { try { worker(d); } catch (const std::exception& e) { std::lock_guard<std::mutex> lock(outMutex); workerError = e.what(); } });
+	for (int d = 0; d < numWorkers; d++) workers.emplace_back([&, d]() { try { worker(d); } catch (const std::exception& e) { std::lock_guard<std::mutex> lock(outMutex); workerError = e.what(); } });
 	for (auto& w : workers) w.join();
 	if (!workerError.empty()) { std::cerr << "fatal: " << workerError << std::endl; return 1; }
 	if (params.outGam != "" && !wroteAny) { std::string empty = gcout::gamRecord({}); gamOut.write(empty.data(), empty.size()); } // Aligner.cpp:228-240

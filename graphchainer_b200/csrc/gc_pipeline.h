@@ -629,6 +629,10 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	std::vector<std::vector<FragSeed>> fragSeeds(R);
 	items.clear();
 	const size_t len = (size_t)params.colinearSplitLen, sep = (size_t)params.colinearSplitGap;
+	// work items are generated per read in parallel (indices local to the read), then concatenated
+	std::vector<std::vector<gcgpu_ext_item>> localItems(R);
+	std::vector<size_t> itemBase(R + 1, 0);
+	#pragma omp parallel for schedule(dynamic, 4)
 	for (size_t r = 0; r < R; r++)
 	{
 		if (seedsOrdered[r].empty()) continue;
@@ -649,11 +653,19 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				GcSeedHit seed = seeds[i];
 				seed.seqPos -= l;
 				FragSeed fs; fs.seedIdx = (uint32_t)i;
-				fs.ref = makeItems(b, r, sequence.size(), l, len, seed, items);
+				fs.ref = makeItems(b, r, sequence.size(), l, len, seed, localItems[r]);
 				fragSeeds[r].push_back(fs);
 			}
 			frags[r].push_back(f);
 		}
+	}
+	for (size_t r = 0; r < R; r++) itemBase[r + 1] = itemBase[r] + localItems[r].size();
+	items.resize(itemBase[R]);
+	#pragma omp parallel for schedule(dynamic, 16)
+	for (size_t r = 0; r < R; r++)
+	{
+		if (!localItems[r].empty()) memcpy(items.data() + itemBase[r], localItems[r].data(), localItems[r].size() * sizeof(gcgpu_ext_item));
+		std::vector<gcgpu_ext_item>().swap(localItems[r]);
 	}
 	extendCalls = extendCalls ? 1 : 0; // S1's trace buffers are free again (codes stay resident after the first call)
 	if (!items.empty()) runExtend();
@@ -681,9 +693,10 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				if (assertion) { out[r].dropped = true; break; }
 				if (found) continue;
 				s2SeedsExtended[r] += 1;
-				for (int d = 0; d < 2; d++) if (fs.ref.item[d] >= 0 && results[fs.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
+				const gcgpu_ext_result* readResults = results.data() + itemBase[r];
+				for (int d = 0; d < 2; d++) if (fs.ref.item[d] >= 0 && readResults[fs.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
 				GcPackedAln item;
-				if (!buildAlignment(seed, fs.ref, results.data(), traces, item)) continue;
+				if (!buildAlignment(seed, fs.ref, readResults, traces, item)) continue;
 				if (item.alignmentEnd == item.alignmentStart) continue;
 				kept.emplace_back(item);
 			}
@@ -820,7 +833,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		if (needClc)
 		{
 			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-			it.k_hint = kHint; it.want_path = 0;
+			it.k_hint = kHint + (kHint * 3) / 10; it.want_path = 0; // the chained path usually costs 5-40 % more than the whole-read alignment
 			nwBuf += pathSeq[r];
 			clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 		}
@@ -832,6 +845,17 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
 		stats.k3Items += nwItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : nwRes) stats.k3Blocks += x.blocks;
+		if (traceOn)
+		{
+			size_t zero = 0, ok = 0, fail = 0; double sumHint = 0, sumD = 0;
+			for (size_t i = 0; i < nwItems.size(); i++)
+			{
+				if (nwItems[i].k_hint <= 0) zero++;
+				else if (nwRes[i].distance <= nwItems[i].k_hint) { ok++; sumHint += nwItems[i].k_hint; sumD += nwRes[i].distance; }
+				else { fail++; if (fail <= 12) fprintf(stderr, "[gc]   hint %d distance %d\n", nwItems[i].k_hint, nwRes[i].distance); }
+			}
+			fprintf(stderr, "[gc] nw hints: none=%zu ok=%zu (mean hint %.0f, mean distance %.0f) too_small=%zu\n", zero, ok, ok ? sumHint / ok : 0.0, ok ? sumD / ok : 0.0, fail);
+		}
 	}
 	// decision (Aligner.cpp:901-920): better = no GA alignment, or long_edit_distance > CLC score (strict)
 	std::vector<gcgpu_nw_item> pathItems;

@@ -1,8 +1,10 @@
 // libgcgpu: C ABI + CUDA kernels (sm_100a) of the GraphChainer alignment hot path.
 // Interface and the reference seams each entry point replaces: include/gcgpu.h.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +20,8 @@
 #define GC_K1_LONG_ITEM 96   // sequence length from which a K1 item gets a warp of its own
 
 static thread_local std::string g_lastError;
+static const bool g_trace = getenv("GCGPU_TRACE") != nullptr;
+#define GC_TRACE_MS(name, count) do { if (g_trace) fprintf(stderr, "[gcgpu] %-28s n=%-8u %.3f ms\n", name, (unsigned)(count), ms); } while (0)
 static int setError(int code, const std::string& msg) { g_lastError = msg; return code; }
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return setError(_e == cudaErrorMemoryAllocation ? GCGPU_ERR_NOMEM : GCGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
@@ -75,7 +79,7 @@ struct gcgpu_ctx
 	uint64_t launches = 0;
 };
 
-// ------------------------------------------------------------------ K1 kernel
+// ------------------------------------------------------------------ K1 kernels
 struct GcK1Desc
 {
 	uint64_t seqOff;
@@ -97,13 +101,9 @@ static size_t k1WorkspaceBytes(uint32_t numSlices, uint32_t itemCap, uint32_t he
 	return alignUp((size_t)(numSlices + 2) * sizeof(GcSliceMeta), 16) + (size_t)itemCap * sizeof(GcNodeItem) + (size_t)heapCap * 8;
 }
 
-// One thread = one extension work item (see gc_k1.cuh for the design rationale).
-__global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results)
+__device__ __forceinline__ void gc_k1_run_item(const GcGraphView& g, const GcViterbiTables* vt, const GcK1Params& prm, const uint8_t* seq, const GcK1Desc& d,
+	uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
 {
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
-	GcK1Desc d = descs[t];
 	GcK1Workspace ws;
 	uint8_t* base = arena + d.wsOff;
 	ws.slices = (GcSliceMeta*)base;
@@ -115,6 +115,34 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	GcK1Result res;
 	gc_k1_extend(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, traceArena + d.traceOff, d.traceCap, res);
 	results[d.resultIndex] = res;
+	traceOffOfItem[d.resultIndex] = d.traceOff;
+	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+}
+
+// Short work items (35-bp fragments: one or two slices): one thread = one item; the millions of
+// independent items of a batch supply the parallelism.  Workspaces and trace slots are uniform, so
+// the kernel derives them from the item index -- the host uploads nothing but the items themselves.
+struct GcK1ShortLayout
+{
+	uint64_t wsBase, wsStride;      // bytes
+	uint64_t traceBase;             // entries
+	uint32_t traceStride;           // entries
+	uint32_t itemCap, heapCap, numSlices;
+};
+__global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
+	uint64_t* traceOffOfItem, uint32_t* overflow)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	uint32_t idx = shortIdx ? shortIdx[t] : t;
+	gcgpu_ext_item it = items[idx];
+	GcK1Desc d;
+	d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
+	d.wsOff = lay.wsBase + (uint64_t)t * lay.wsStride;
+	d.traceOff = lay.traceBase + (uint64_t)t * lay.traceStride;
+	d.itemCap = lay.itemCap; d.heapCap = lay.heapCap; d.traceCap = lay.traceStride; d.numSlices = lay.numSlices; d.resultIndex = idx;
+	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow);
 }
 
 // Long work items (whole-read extensions, thousands of dependent column steps): one WARP per item,
@@ -122,33 +150,41 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 // warp; with a private warp every walk issues at the full single-warp rate and the scheduler
 // interleaves up to 64 of them per SM.
 __global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results)
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
 {
 	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (t >= n || (threadIdx.x & 31) != 0) return;
 	GcK1Desc d = descs[t];
-	GcK1Workspace ws;
-	uint8_t* base = arena + d.wsOff;
-	ws.slices = (GcSliceMeta*)base;
-	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
-	ws.items = (GcNodeItem*)(base + slicesBytes);
-	ws.heap = (uint64_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem));
-	ws.itemCap = d.itemCap;
-	ws.heapCap = d.heapCap;
-	GcK1Result res;
-	gc_k1_extend(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, traceArena + d.traceOff, d.traceCap, res);
-	results[d.resultIndex] = res;
+	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow);
 }
 
-// gather the per-item traces into one dense buffer: one warp per item
-struct GcCopyDesc { uint64_t src; uint64_t dst; uint32_t len; uint32_t pad; };
-__global__ void gc_trace_gather_kernel(const GcCopyDesc* __restrict__ descs, uint32_t n, const uint64_t* __restrict__ traceArena, uint64_t* __restrict__ out)
+// trace lengths of the finished items (input of the exclusive scan that places them in the dense buffer)
+__global__ void gc_k1_lengths_kernel(const GcK1Result* __restrict__ results, uint32_t n, uint64_t* __restrict__ lens)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	GcK1Result r = results[i];
+	lens[i] = r.status == GC_OK ? r.traceLen : 0;
+}
+// one warp per item: copy its trace to its place in the dense buffer, write the public result record
+__global__ void gc_k1_gather_kernel(const GcK1Result* __restrict__ results, const uint64_t* __restrict__ traceOffOfItem, const uint64_t* __restrict__ offs, uint32_t n,
+	const uint64_t* __restrict__ traceArena, uint64_t* __restrict__ dense, gcgpu_ext_result* __restrict__ pub, uint64_t* total)
 {
 	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t lane = threadIdx.x & 31;
 	if (warp >= n) return;
-	GcCopyDesc d = descs[warp];
-	for (uint32_t i = lane; i < d.len; i += 32) out[d.dst + i] = traceArena[d.src + i];
+	GcK1Result r = results[warp];
+	uint32_t len = r.status == GC_OK ? r.traceLen : 0;
+	uint64_t dst = offs[warp], src = traceOffOfItem[warp];
+	for (uint32_t i = lane; i < len; i += 32) dense[dst + i] = traceArena[src + i];
+	if (lane == 0)
+	{
+		gcgpu_ext_result o;
+		o.status = r.status == GC_OK ? GCGPU_ITEM_OK : (r.status == GC_FAILED ? GCGPU_ITEM_FAILED : GCGPU_ITEM_INTERNAL);
+		o.score = r.score; o.trace_len = len; o.reserved = 0; o.trace_offset = dst; o.columns = r.columns;
+		pub[warp] = o;
+		if (warp == n - 1) *total = dst + len;
+	}
 }
 
 // ------------------------------------------------------------------ C ABI
@@ -249,10 +285,34 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	ctx->lastKernelMs = 0;
 	if (n == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	for (uint32_t i = 0; i < n; i++)
+	// ---- validate, split into long (warp per item, longest first) and short (thread per item) work
+	int bad = -1;
+	int32_t maxShort = 0;
+	std::vector<uint32_t> longIdx;
 	{
-		if (items[i].seq_len < 0 || items[i].seq_offset + (uint64_t)items[i].seq_len > seq_bytes || items[i].node >= ctx->numNodes || items[i].seq_len >= (1 << 24))
-			return setError(GCGPU_ERR_ARG, "gcgpu_extend: item " + std::to_string(i) + " out of range");
+		uint32_t numNodes = ctx->numNodes;
+		#pragma omp parallel
+		{
+			std::vector<uint32_t> mine; int32_t myMax = 0; int myBad = -1;
+			#pragma omp for schedule(static) nowait
+			for (uint32_t i = 0; i < n; i++)
+			{
+				const gcgpu_ext_item& it = items[i];
+				if (it.seq_len < 0 || it.seq_offset + (uint64_t)it.seq_len > seq_bytes || it.node >= numNodes || it.seq_len >= (1 << 24)) { myBad = (int)i; continue; }
+				if (it.seq_len >= GC_K1_LONG_ITEM) mine.push_back(i); else if (it.seq_len > myMax) myMax = it.seq_len;
+			}
+			#pragma omp critical
+			{ longIdx.insert(longIdx.end(), mine.begin(), mine.end()); if (myMax > maxShort) maxShort = myMax; if (myBad >= 0) bad = myBad; }
+		}
+	}
+	if (bad >= 0) return setError(GCGPU_ERR_ARG, "gcgpu_extend: item " + std::to_string(bad) + " out of range");
+	std::sort(longIdx.begin(), longIdx.end(), [items](uint32_t a, uint32_t b) { return items[a].seq_len != items[b].seq_len ? items[a].seq_len > items[b].seq_len : a < b; });
+	uint32_t nLong = (uint32_t)longIdx.size(), nShort = n - nLong;
+	std::vector<uint32_t> shortIdx;
+	if (nLong && nShort)
+	{
+		shortIdx.reserve(nShort);
+		for (uint32_t i = 0; i < n; i++) if (items[i].seq_len < GC_K1_LONG_ITEM) shortIdx.push_back(i);
 	}
 	if (seq)
 	{
@@ -261,120 +321,156 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		ctx->seqResident = seq_bytes;
 	}
 	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_extend: seq == NULL but no sequence buffer of this size is resident");
-	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK1Result)));
 
-	// work list, longest first so that the threads of a warp carry similar loads
-	std::vector<uint32_t> todo(n);
-	for (uint32_t i = 0; i < n; i++) todo[i] = i;
-	std::sort(todo.begin(), todo.end(), [items](uint32_t a, uint32_t b) { return items[a].seq_len != items[b].seq_len ? items[a].seq_len > items[b].seq_len : a < b; });
-	std::vector<GcK1Result> hres(n);
-	std::vector<uint64_t> traceOffOfItem(n, 0);
-	std::vector<GcK1Desc> descs;
-	// trace arena: every item keeps a fixed slot across retries
-	uint64_t traceTotal = 0;
-	for (uint32_t i = 0; i < n; i++) { traceOffOfItem[i] = traceTotal; traceTotal += 2 * (uint64_t)items[i].seq_len + 72; }
-	CUDA_TRY(ctx->traceArena.ensure(traceTotal * 8));
-	uint32_t itemScale = 1, heapScale = 1;
-	GcK1Params prm; prm.bandwidth = ctx->params.initial_bandwidth;
-	for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++)
+	// ---- layout: long items get individual slabs, short items uniform ones
+	std::vector<GcK1Desc> descs(nLong);
+	size_t wsTotal = 0; uint64_t traceTotal = 0;
+	for (uint32_t k = 0; k < nLong; k++)
 	{
-		descs.resize(todo.size());
-		size_t wsTotal = 0;
-		for (size_t k = 0; k < todo.size(); k++)
-		{
-			const gcgpu_ext_item& it = items[todo[k]];
-			GcK1Desc& d = descs[k];
-			d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
-			d.numSlices = (uint32_t)((it.seq_len + 63) / 64);
-			d.itemCap = (24 + 8 * d.numSlices) * itemScale;
-			d.heapCap = 64 * heapScale;
-			d.traceCap = (uint32_t)(2 * (uint64_t)it.seq_len + 72);
-			d.traceOff = traceOffOfItem[todo[k]];
-			d.resultIndex = todo[k];
-			d.wsOff = wsTotal;
-			wsTotal += alignUp(k1WorkspaceBytes(d.numSlices, d.itemCap, d.heapCap), 128);
-		}
-		CUDA_TRY(ctx->arena.ensure(wsTotal));
+		const gcgpu_ext_item& it = items[longIdx[k]];
+		GcK1Desc& d = descs[k];
+		d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
+		d.numSlices = (uint32_t)((it.seq_len + 63) / 64);
+		d.itemCap = 24 + 8 * d.numSlices;
+		d.heapCap = 64;
+		d.traceCap = (uint32_t)(2 * (uint64_t)it.seq_len + 72);
+		d.traceOff = traceTotal; traceTotal += d.traceCap;
+		d.resultIndex = longIdx[k];
+		d.wsOff = wsTotal;
+		wsTotal += alignUp(k1WorkspaceBytes(d.numSlices, d.itemCap, d.heapCap), 128);
+	}
+	GcK1ShortLayout lay;
+	lay.numSlices = (uint32_t)((maxShort + 63) / 64); if (lay.numSlices < 1) lay.numSlices = 1;
+	lay.itemCap = 24 + 8 * lay.numSlices; lay.heapCap = 64;
+	lay.wsBase = wsTotal; lay.wsStride = alignUp(k1WorkspaceBytes(lay.numSlices, lay.itemCap, lay.heapCap), 128);
+	lay.traceBase = traceTotal; lay.traceStride = (uint32_t)(2 * maxShort + 72);
+	wsTotal += (size_t)nShort * lay.wsStride;
+	traceTotal += (uint64_t)nShort * lay.traceStride;
+	// small per-call device arrays: internal results | trace slot of every item | lengths | offsets | public results | scalars
+	size_t offRes = 0, offSlot = alignUp(offRes + (size_t)n * sizeof(GcK1Result), 128), offLens = alignUp(offSlot + (size_t)n * 8, 128), offOffs = alignUp(offLens + (size_t)n * 8, 128);
+	size_t offPub = alignUp(offOffs + (size_t)n * 8, 128), offScalars = alignUp(offPub + (size_t)n * sizeof(gcgpu_ext_result), 128), offItems = offScalars + 128;
+	size_t offShortIdx = alignUp(offItems + (size_t)n * sizeof(gcgpu_ext_item), 128), resEnd = offShortIdx + (size_t)shortIdx.size() * 4;
+	CUDA_TRY(ctx->resBuf.ensure(resEnd));
+	CUDA_TRY(ctx->arena.ensure(wsTotal));
+	CUDA_TRY(ctx->traceArena.ensure(traceTotal * 8));
+	uint8_t* R = (uint8_t*)ctx->resBuf.p;
+	GcK1Result* dRes = (GcK1Result*)(R + offRes); uint64_t* dSlot = (uint64_t*)(R + offSlot); uint64_t* dLens = (uint64_t*)(R + offLens); uint64_t* dOffs = (uint64_t*)(R + offOffs);
+	gcgpu_ext_result* dPub = (gcgpu_ext_result*)(R + offPub); uint32_t* dOverflow = (uint32_t*)(R + offScalars); uint64_t* dTotal = (uint64_t*)(R + offScalars + 8);
+	gcgpu_ext_item* dItems = (gcgpu_ext_item*)(R + offItems); uint32_t* dShortIdx = shortIdx.empty() ? nullptr : (uint32_t*)(R + offShortIdx);
+	CUDA_TRY(cudaMemsetAsync(R + offScalars, 0, 128, ctx->stream));
+	if (nShort) CUDA_TRY(cudaMemcpyAsync(dItems, items, (size_t)n * sizeof(gcgpu_ext_item), cudaMemcpyHostToDevice, ctx->stream));
+	if (!shortIdx.empty()) CUDA_TRY(cudaMemcpyAsync(dShortIdx, shortIdx.data(), shortIdx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (nLong)
+	{
 		CUDA_TRY(ctx->descBuf.ensure(descs.size() * sizeof(GcK1Desc)));
 		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), descs.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
-		uint32_t m = (uint32_t)descs.size();
-		// todo is sorted longest first: the first mLong items go to the warp-per-item kernel
-		uint32_t mLong = 0;
-		while (mLong < m && descs[mLong].seqLen >= GC_K1_LONG_ITEM) mLong++;
-		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		if (mLong)
-		{
-			gc_k1_long_kernel<<<(mLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, mLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, (GcK1Result*)ctx->resBuf.p);
-			ctx->launches++;
-		}
-		if (m > mLong)
-		{
-			gc_k1_kernel<<<(m - mLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p + mLong, m - mLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, (GcK1Result*)ctx->resBuf.p);
-			ctx->launches++;
-		}
-		CUDA_TRY(cudaGetLastError());
-		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(hres.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-		float ms = 0;
-		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-		ctx->lastKernelMs += ms;
-		std::vector<uint32_t> again;
-		bool needItems = false, needHeap = false;
-		for (uint32_t idx : todo)
-		{
-			int st = hres[idx].status;
-			if (st == GC_OVERFLOW_ITEMS) { again.push_back(idx); needItems = true; }
-			else if (st == GC_OVERFLOW_HEAP) { again.push_back(idx); needHeap = true; }
-		}
-		if (needItems) itemScale *= 4;
-		if (needHeap) heapScale *= 4;
-		todo.swap(again);
 	}
-	if (!todo.empty()) return setError(GCGPU_ERR_NOMEM, "gcgpu_extend: " + std::to_string(todo.size()) + " work items still overflow their workspace after 8 attempts");
-
-	// results + dense traces
-	uint64_t used = 0;
-	std::vector<GcCopyDesc> copies;
-	copies.reserve(n);
-	bool internal = false;
-	for (uint32_t i = 0; i < n; i++)
+	GcK1Params prm; prm.bandwidth = ctx->params.initial_bandwidth;
+	float ms = 0;
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (nLong)
 	{
-		const GcK1Result& r = hres[i];
-		results[i].status = r.status == GC_OK ? GCGPU_ITEM_OK : (r.status == GC_FAILED ? GCGPU_ITEM_FAILED : GCGPU_ITEM_INTERNAL);
-		if (results[i].status == GCGPU_ITEM_INTERNAL) internal = true;
-		results[i].score = r.score;
-		results[i].trace_len = r.status == GC_OK ? r.traceLen : 0;
-		results[i].reserved = 0;
-		results[i].trace_offset = used;
-		results[i].columns = r.columns;
-		if (results[i].trace_len)
-		{
-			GcCopyDesc c; c.src = traceOffOfItem[i]; c.dst = used; c.len = results[i].trace_len; c.pad = 0;
-			copies.push_back(c);
-			used += results[i].trace_len;
-		}
+		gc_k1_long_kernel<<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+		ctx->launches++;
 	}
+	if (nShort)
+	{
+		gc_k1_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+		ctx->launches++;
+	}
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	uint32_t overflow = 0;
+	CUDA_TRY(cudaMemcpyAsync(&overflow, dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs += ms;
+	GC_TRACE_MS("k1 (long+short)", n);
+	if (overflow)
+	{
+		// rare: some item outgrew its slab (very wide band).  Re-run those with 4x larger slabs until they fit.
+		std::vector<GcK1Result> hres(n);
+		CUDA_TRY(cudaMemcpy(hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost));
+		std::vector<uint64_t> hslot(n);
+		CUDA_TRY(cudaMemcpy(hslot.data(), dSlot, (size_t)n * 8, cudaMemcpyDeviceToHost));
+		uint32_t itemScale = 1, heapScale = 1;
+		std::vector<uint32_t> todo;
+		for (uint32_t i = 0; i < n; i++) if (hres[i].status == GC_OVERFLOW_ITEMS || hres[i].status == GC_OVERFLOW_HEAP) todo.push_back(i);
+		DevBuf retryArena;
+		for (int attempt = 0; attempt < 8 && !todo.empty(); attempt++)
+		{
+			bool needItems = false, needHeap = false;
+			for (uint32_t i : todo) { if (hres[i].status == GC_OVERFLOW_ITEMS) needItems = true; else needHeap = true; }
+			if (needItems) itemScale *= 4;
+			if (needHeap) heapScale *= 4;
+			std::vector<GcK1Desc> rd(todo.size());
+			size_t ws = 0;
+			for (size_t k = 0; k < todo.size(); k++)
+			{
+				const gcgpu_ext_item& it = items[todo[k]];
+				GcK1Desc& d = rd[k];
+				d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
+				d.numSlices = (uint32_t)((it.seq_len + 63) / 64);
+				d.itemCap = (24 + 8 * d.numSlices) * itemScale; d.heapCap = 64 * heapScale;
+				d.traceCap = (uint32_t)(2 * (uint64_t)it.seq_len + 72);
+				d.traceOff = hslot[todo[k]]; d.resultIndex = todo[k];
+				d.wsOff = ws; ws += alignUp(k1WorkspaceBytes(d.numSlices, d.itemCap, d.heapCap), 128);
+			}
+			cudaError_t e = retryArena.ensure(ws);
+			if (e != cudaSuccess) { retryArena.release(); return setError(GCGPU_ERR_NOMEM, "gcgpu_extend: retry workspace"); }
+			CUDA_TRY(ctx->descBuf.ensure(rd.size() * sizeof(GcK1Desc)));
+			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(cudaMemsetAsync(dOverflow, 0, 4, ctx->stream));
+			uint32_t m = (uint32_t)rd.size();
+			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+			gc_k1_long_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			ctx->launches++;
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+			CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+			ctx->lastKernelMs += ms;
+			CUDA_TRY(cudaMemcpy(hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost));
+			std::vector<uint32_t> again;
+			for (uint32_t i : todo) if (hres[i].status == GC_OVERFLOW_ITEMS || hres[i].status == GC_OVERFLOW_HEAP) again.push_back(i);
+			todo.swap(again);
+		}
+		retryArena.release();
+		if (!todo.empty()) return setError(GCGPU_ERR_NOMEM, "gcgpu_extend: " + std::to_string(todo.size()) + " work items still overflow their workspace after 8 attempts");
+	}
+
+	// ---- dense traces + public results, all on the device: lengths -> exclusive scan -> gather
+	CUDA_TRY(ctx->compact.ensure(traceTotal * 8 > (uint64_t)n * 8 ? (size_t)n * 8 : 8)); // grown to the real size below
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	gc_k1_lengths_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, n, dLens);
+	size_t scanBytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dLens, dOffs, (int)n, ctx->stream);
+	CUDA_TRY(ctx->copyDesc.ensure(scanBytes + 16));
+	cub::DeviceScan::ExclusiveSum(ctx->copyDesc.p, scanBytes, dLens, dOffs, (int)n, ctx->stream);
+	// the dense buffer can never exceed the slots it is gathered from
+	CUDA_TRY(ctx->compact.ensure(traceTotal * 8 + 16));
+	gc_k1_gather_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(dRes, dSlot, dOffs, n, (const uint64_t*)ctx->traceArena.p, (uint64_t*)ctx->compact.p, dPub, dTotal);
+	ctx->launches += 3;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	uint64_t used = 0;
+	CUDA_TRY(cudaMemcpyAsync(&used, dTotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaMemcpyAsync(results, dPub, (size_t)n * sizeof(gcgpu_ext_result), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs += ms;
+	GC_TRACE_MS("k1 scan+gather", n);
 	*trace_used = used;
 	if (used > trace_capacity) return setError(GCGPU_ERR_ARG, "gcgpu_extend: trace buffer too small, need " + std::to_string(used) + " entries");
 	if (used)
 	{
 		if (!traces) return setError(GCGPU_ERR_ARG, "gcgpu_extend: null trace buffer");
-		CUDA_TRY(ctx->compact.ensure(used * 8));
-		CUDA_TRY(ctx->copyDesc.ensure(copies.size() * sizeof(GcCopyDesc)));
-		CUDA_TRY(cudaMemcpyAsync(ctx->copyDesc.p, copies.data(), copies.size() * sizeof(GcCopyDesc), cudaMemcpyHostToDevice, ctx->stream));
-		uint32_t m = (uint32_t)copies.size();
-		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		gc_trace_gather_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const GcCopyDesc*)ctx->copyDesc.p, m, (const uint64_t*)ctx->traceArena.p, (uint64_t*)ctx->compact.p);
-		ctx->launches++;
-		CUDA_TRY(cudaGetLastError());
-		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		CUDA_TRY(cudaMemcpyAsync(traces, ctx->compact.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-		float ms = 0;
-		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-		ctx->lastKernelMs += ms;
 	}
+	bool internal = false;
+	#pragma omp parallel for schedule(static) reduction(||: internal)
+	for (uint32_t i = 0; i < n; i++) if (results[i].status == GCGPU_ITEM_INTERNAL) internal = true;
 	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_extend: a work item reached a state the reference asserts on (see per-item status)");
 	return GCGPU_OK;
 }
@@ -722,6 +818,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
+	GC_TRACE_MS("k3w distance<0>", n);
 	// items whose cutoff band outgrew the register budget of the launched class: wider class, then the thread form
 	for (int cls = 1; cls <= 2; cls++)
 	{
@@ -747,6 +844,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
+		GC_TRACE_MS(cls == 1 ? "k3w distance<1>" : "k3 distance (thread)", m);
 		for (const GcK3Desc& d : rd) hout[d.resultIndex].blocks += prev[d.resultIndex].blocks;
 	}
 	// ---- path pass for the items that asked for it
@@ -789,6 +887,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
+		GC_TRACE_MS("k3w path", m);
 		// items the warp form gave up on (band beyond its register budget): thread form
 		std::vector<GcK3Desc> rd;
 		for (const GcK3Desc& d : pd) if (hout[d.resultIndex].pad == 1) rd.push_back(d);

@@ -25,7 +25,8 @@ typedef struct gcalign_options
 	int32_t device;               /* CUDA device index                                   */
 	int32_t host_threads;         /* -t: threads for the host stages                      */
 	int32_t initial_bandwidth;    /* -b, default 10                                       */
-	int32_t reserved;
+	int32_t streams;              /* read batches in flight per device, each with its own CUDA stream,
+	                                 workspaces and share of the host threads (0 = default 4)     */
 	int64_t colinear_gap;         /* --colinear-gap, default 10000                        */
 	int64_t colinear_split_len;   /* --colinear-split-len, default 35                     */
 	int64_t colinear_split_gap;   /* --colinear-split-gap, default 35                     */
