@@ -135,6 +135,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 				std::vector<GcReadResult>& results = allResults[bi];
 				pipeline.alignBatch(batch, results);
 				records[bi].resize(batch.size());
+				auto tGam0 = std::chrono::steady_clock::now();
 				if (gam_out)
 				{
 					#pragma omp parallel for schedule(dynamic, 4)
@@ -146,6 +147,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 						records[bi][i] = gcout::gamRecord(alns);
 					}
 				}
+				if (getenv("GC_TRACE")) fprintf(stderr, "[gc] phase gam        %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tGam0).count());
 				// the traces are not needed past this point: keep only what the summaries read
 				for (auto& res : results) for (auto& a : res.alignments) { std::vector<GcTraceItem>().swap(a.trace); }
 			}

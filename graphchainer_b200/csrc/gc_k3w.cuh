@@ -165,6 +165,82 @@ GC_HD uint32_t gc_k3w_lane_step(const GcK3wPass& p, GcK3wLane<NB>& s, int32_t ta
 	return send;
 }
 
+
+// ---- fast path.  A lane's control state only changes at a few "event" steps: the first and the
+// last column of its group (block initialisation, hand-over to group g+32, stop-column write) and
+// the step after the group above has left the band.  Between events every lane is either
+// computing with constant settings or idle, so the warp runs whole segments of steps through
+// gc_k3w_lane_fast_step (no control flow besides one predicate) and executes the general
+// gc_k3w_lane_step only at event steps.
+#define GC_K3W_NO_EVENT 0x7FFFFFFF
+template <int NB>
+GC_HD int32_t gc_k3w_next_event(const GcK3wPass& p, const GcK3wLane<NB>& s, int32_t tau)
+{
+	if (s.cFirst > s.cLast) return GC_K3W_NO_EVENT;
+	int32_t ev = GC_K3W_NO_EVENT;
+	int32_t e1 = s.cFirst + s.g; if (e1 >= tau && e1 < ev) ev = e1;
+	int32_t e2 = s.cLast + s.g; if (e2 >= tau && e2 < ev) ev = e2;
+	int32_t e3 = s.aboveLast + 1 + s.g; if (s.aboveLast >= 0 && e3 >= tau && e3 < ev) ev = e3;
+	return ev;
+}
+
+// per-segment constants of a lane
+struct GcK3wSegment
+{
+	bool active;            // the lane computes in every step of the segment
+	bool useRecv;           // the group above is in the band: take its horizontal delta
+	const uint8_t* tptr;    // symbol of the lane's column at the first step of the segment
+};
+template <int NB>
+GC_HD GcK3wSegment gc_k3w_segment(const GcK3wPass& p, const GcK3wLane<NB>& s, int32_t tau)
+{
+	GcK3wSegment seg;
+	int32_t c = tau - s.g;
+	seg.active = c > s.cFirst && c < s.cLast;
+	seg.useRecv = c <= s.aboveLast;
+	seg.tptr = p.target + (seg.active ? p.tBase + (int64_t)c * p.tStep : p.tBase);
+	return seg;
+}
+
+template <int NB, bool STORE>
+GC_HD uint32_t gc_k3w_lane_fast_step(const GcK3wPass& p, GcK3wLane<NB>& s, GcK3wSegment& seg, int32_t tau, uint32_t recv)
+{
+	uint32_t send = 0;
+	if (seg.active)
+	{
+		int hin = seg.useRecv ? (int)(recv & 3u) - 1 : 1;
+		int sym = *seg.tptr;
+		seg.tptr += p.tStep;
+		uint64_t keep = sym < 4 ? ~0ULL : 0ULL;
+		int32_t lastScore = 0;
+		GC_UNROLL
+		for (int i = 0; i < NB; i++)
+		{
+			if (i < s.nbHere)
+			{
+				uint64_t lo = (sym & 1) ? s.eq[i][1] : s.eq[i][0];
+				uint64_t hi = (sym & 1) ? s.eq[i][3] : s.eq[i][2];
+				uint64_t Eq = ((sym & 2) ? hi : lo) & keep;
+				hin = gc_k3_block(s.P[i], s.M[i], Eq, hin);
+				s.score[i] += hin;
+				lastScore = s.score[i];
+			}
+		}
+		s.work += (uint32_t)s.nbHere;
+		send = ((uint32_t)lastScore << 2) | (uint32_t)(hin + 1);
+		if (STORE)
+		{
+			int32_t c = tau - s.g;
+			GcK3Block* dst = p.store + (int64_t)c * p.storeStride + s.g * NB;
+			GC_UNROLL
+			for (int i = 0; i < NB; i++)
+				if (i < s.nbHere) { GcK3Block bl; bl.P = s.P[i]; bl.M = s.M[i]; bl.score = s.score[i]; bl.pad = 0; dst[i] = bl; }
+		}
+	}
+	s.prevRecv = recv;
+	return send;
+}
+
 // blocks [first, last] of the stop column that the pass wrote to blocksOut (group-granular superset of the band)
 GC_HD void gc_k3w_stop_blocks(const GcK3wPass& p, int32_t NB, int32_t& first, int32_t& last)
 {

@@ -523,20 +523,43 @@ __global__ void __launch_bounds__(64) gc_k3_distance_kernel(const uint8_t* __res
 
 // ---- warp form (gc_k3w.cuh): one warp = one NW distance, lanes = groups of NB 64-row blocks on a
 // skewed wavefront, block state in registers, one shuffle per column step.
-template <int NB>
-__device__ __forceinline__ uint32_t gc_k3w_run_pass(const GcK3wPass& p, GcK3Block* blocksOut)
+template <int NB, bool STORE>
+__device__ __forceinline__ uint32_t gc_k3w_run_pass_impl(const GcK3wPass& p, GcK3Block* blocksOut)
 {
 	int lane = threadIdx.x & 31;
+	int src = (lane + 31) & 31;
 	GcK3wLane<NB> s;
 	gc_k3w_lane_init(p, s, lane);
 	uint32_t send = 0;
-	for (int32_t tau = 0; tau <= p.tauEnd; tau++)
+	int32_t tau = 0;
+	while (tau <= p.tauEnd)
 	{
-		uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, (lane + 31) & 31);
-		send = gc_k3w_lane_step(p, s, tau, recv, blocksOut);
+		int32_t ev = __reduce_min_sync(0xFFFFFFFFu, gc_k3w_next_event(p, s, tau));
+		if (ev > tau)
+		{
+			// no lane has an event before `ev`: a segment of plain steps
+			int32_t end = ev <= p.tauEnd ? ev : p.tauEnd + 1;
+			GcK3wSegment seg = gc_k3w_segment(p, s, tau);
+			for (; tau < end; tau++)
+			{
+				uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, src);
+				send = gc_k3w_lane_fast_step<NB, STORE>(p, s, seg, tau, recv);
+			}
+		}
+		else
+		{
+			uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, src);
+			send = gc_k3w_lane_step(p, s, tau, recv, blocksOut);
+			tau++;
+		}
 	}
 	__syncwarp();
 	return s.work;
+}
+template <int NB>
+__device__ __forceinline__ uint32_t gc_k3w_run_pass(const GcK3wPass& p, GcK3Block* blocksOut)
+{
+	return p.store ? gc_k3w_run_pass_impl<NB, true>(p, blocksOut) : gc_k3w_run_pass_impl<NB, false>(p, blocksOut);
 }
 
 #define GC_K3W_NEED_LARGER (-2)

@@ -108,12 +108,30 @@ template <int NB>
 static uint64_t k3wPassSim(const GcK3wPass& p, GcK3Block* blocksOut)
 {
 	GcK3wLane<NB> lanes[32];
+	GcK3wSegment segs[32];
 	uint32_t send[32], recv[32];
 	for (int l = 0; l < 32; l++) { gc_k3w_lane_init(p, lanes[l], l); send[l] = 0; }
-	for (int32_t tau = 0; tau <= p.tauEnd; tau++)
+	int32_t tau = 0;
+	while (tau <= p.tauEnd)
 	{
-		for (int l = 0; l < 32; l++) recv[l] = send[(l + 31) & 31];
-		for (int l = 0; l < 32; l++) send[l] = gc_k3w_lane_step(p, lanes[l], tau, recv[l], blocksOut);
+		int32_t ev = GC_K3W_NO_EVENT;
+		for (int l = 0; l < 32; l++) ev = std::min(ev, gc_k3w_next_event(p, lanes[l], tau));
+		if (ev > tau)
+		{
+			int32_t end = ev <= p.tauEnd ? ev : p.tauEnd + 1;
+			for (int l = 0; l < 32; l++) segs[l] = gc_k3w_segment(p, lanes[l], tau);
+			for (; tau < end; tau++)
+			{
+				for (int l = 0; l < 32; l++) recv[l] = send[(l + 31) & 31];
+				for (int l = 0; l < 32; l++) send[l] = p.store ? gc_k3w_lane_fast_step<NB, true>(p, lanes[l], segs[l], tau, recv[l]) : gc_k3w_lane_fast_step<NB, false>(p, lanes[l], segs[l], tau, recv[l]);
+			}
+		}
+		else
+		{
+			for (int l = 0; l < 32; l++) recv[l] = send[(l + 31) & 31];
+			for (int l = 0; l < 32; l++) send[l] = gc_k3w_lane_step(p, lanes[l], tau, recv[l], blocksOut);
+			tau++;
+		}
 	}
 	uint64_t work = 0;
 	for (int l = 0; l < 32; l++) work += lanes[l].work;
