@@ -138,13 +138,16 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 				auto tGam0 = std::chrono::steady_clock::now();
 				if (gam_out)
 				{
-					#pragma omp parallel for schedule(dynamic, 4)
-					for (size_t i = 0; i < batch.size(); i++)
+					const int level = h->opts.gzip_level > 0 ? h->opts.gzip_level : 1;
+					#pragma omp parallel
 					{
-						if (results[i].alignments.empty()) continue;
-						std::vector<gcout::Alignment> alns;
-						for (const GcAlnItem& item : results[i].alignments) alns.push_back(gcout::toAlignment(h->graph, batch[i].name, batch[i].sequence, item));
-						records[bi][i] = gcout::gamRecord(alns);
+						gcout::GamEncoder enc;
+						#pragma omp for schedule(dynamic, 4)
+						for (size_t i = 0; i < batch.size(); i++)
+						{
+							if (results[i].alignments.empty()) continue;
+							records[bi][i] = gcout::gamRecordDirect(h->graph, batch[i].name, batch[i].sequence, results[i].alignments, level, enc);
+						}
 					}
 				}
 				if (getenv("GC_TRACE")) fprintf(stderr, "[gc] phase gam        %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tGam0).count());

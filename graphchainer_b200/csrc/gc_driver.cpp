@@ -30,6 +30,7 @@ struct DriverParams
 	size_t threads = 1;
 	int gpus = 1;
 	int streams = 4;
+	int gzipLevel = 1;
 	int firstDevice = 0;
 	int bandwidth = 10;
 	bool shortVerbose = false;
@@ -59,6 +60,7 @@ static void usage()
 		"B200 parameters:\n"
 		"  --gc-gpus N                   GPUs to use (reads are partitioned in length-balanced batches)\n"
 		"  --gc-streams N                read batches in flight per GPU [default 4]\n"
+		"  --gc-gzip-level N             zlib level of the GAM gzip members [default 1; the reference's library default is 6]\n"
 		"  --gc-index file.gcidx         load a prebuilt graph/MPC/minimizer index\n"
 		"  --gc-save-index file.gcidx    store the index built from -g\n"
 		"  --gc-batch-bp N               read bases per GPU batch [default 8388608]\n";
@@ -85,6 +87,7 @@ static DriverParams parseArgs(int argc, char** argv)
 		else if (a == "--sampling-step") p.samplingStep = std::stod(next()); // README contract: a double (the reference parses long long)
 		else if (a == "--short-verbose") p.shortVerbose = true;
 		else if (a == "--gc-gpus") p.gpus = std::stoi(next());
+		else if (a == "--gc-gzip-level") p.gzipLevel = std::min(9, std::max(1, std::stoi(next())));
 		else if (a == "--gc-streams") p.streams = std::max(1, std::stoi(next()));
 		else if (a == "--gc-device") p.firstDevice = std::stoi(next());
 		else if (a == "--gc-index") p.indexFile = next();
@@ -286,14 +289,17 @@ int main(int argc, char** argv)
 			// length-balanced: longest reads first inside a batch (the kernels sort their work items the same way)
 			pipeline.alignBatch(batch, results);
 			std::vector<std::string> gamRecords(batch.size()), jsonRecords(batch.size());
-			#pragma omp parallel for schedule(dynamic, 4)
-			for (size_t r = 0; r < batch.size(); r++)
+			#pragma omp parallel
 			{
-				if (results[r].alignments.empty()) continue;
-				std::vector<gcout::Alignment> alns;
-				for (const GcAlnItem& item : results[r].alignments) alns.push_back(gcout::toAlignment(graph, batch[r].name, batch[r].sequence, item));
-				if (params.outGam != "") gamRecords[r] = gcout::gamRecord(alns);
-				if (params.outJson != "") for (const auto& a : alns) { jsonRecords[r] += gcout::jsonLine(a); jsonRecords[r] += '\n'; }
+				gcout::GamEncoder enc;
+				#pragma omp for schedule(dynamic, 4)
+				for (size_t r = 0; r < batch.size(); r++)
+				{
+					if (results[r].alignments.empty()) continue;
+					if (params.outGam != "") gamRecords[r] = gcout::gamRecordDirect(graph, batch[r].name, batch[r].sequence, results[r].alignments, params.gzipLevel, enc);
+					if (params.outJson != "")
+						for (const GcAlnItem& item : results[r].alignments) { jsonRecords[r] += gcout::jsonLine(gcout::toAlignment(graph, batch[r].name, batch[r].sequence, item)); jsonRecords[r] += '\n'; }
+				}
 			}
 			std::lock_guard<std::mutex> lock(outMutex);
 			for (size_t r = 0; r < batch.size(); r++)

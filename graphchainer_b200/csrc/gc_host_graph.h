@@ -36,7 +36,21 @@ struct GcHostGraph
 	std::vector<uint64_t> mzKmers, mzPositions;
 	std::vector<uint32_t> mzKmerStart;
 	uint64_t mzLength = 15, mzWindow = 20, mzMaxCount = 0, mzBuckets = 1;
-	std::unordered_map<uint64_t, uint32_t> mzLookup; // kmer -> index into mzKmers
+	// kmer -> index into mzKmers: open-addressing table (one cache line per probe; the reference's
+	// BBHash + kmerCheck lookup has the same "exact k-mer or nothing" semantics, MinimizerSeeder.cpp:504-519)
+	std::vector<uint64_t> mzTabKey; std::vector<uint32_t> mzTabVal; uint64_t mzTabMask = 0;
+	static uint64_t mzHash(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
+	// returns the index into mzKmers or -1
+	int64_t mzFind(uint64_t kmer) const
+	{
+		if (mzTabKey.empty()) return -1;
+		for (uint64_t h = mzHash(kmer) & mzTabMask; ; h = (h + 1) & mzTabMask)
+		{
+			uint32_t v = mzTabVal[h];
+			if (v == 0xFFFFFFFFu) return -1;
+			if (mzTabKey[h] == kmer) return (int64_t)v;
+		}
+	}
 	uint64_t bpSize = 0;
 
 	size_t numNodes() const { return nodeLength.size(); }
@@ -89,9 +103,16 @@ struct GcHostGraph
 		for (auto id : origIds) if (id > maxId) maxId = id;
 		origIndexOfId.assign((size_t)maxId + 1, -1);
 		for (size_t i = 0; i < origIds.size(); i++) origIndexOfId[origIds[i]] = (int32_t)i;
-		mzLookup.clear();
-		mzLookup.reserve(mzKmers.size() * 2);
-		for (size_t i = 0; i < mzKmers.size(); i++) mzLookup[mzKmers[i]] = (uint32_t)i;
+		uint64_t cap = 16;
+		while (cap < mzKmers.size() * 2 + 2) cap <<= 1;
+		mzTabMask = cap - 1;
+		mzTabKey.assign(cap, 0); mzTabVal.assign(cap, 0xFFFFFFFFu);
+		for (size_t i = 0; i < mzKmers.size(); i++)
+		{
+			uint64_t h = mzHash(mzKmers[i]) & mzTabMask;
+			while (mzTabVal[h] != 0xFFFFFFFFu && mzTabKey[h] != mzKmers[i]) h = (h + 1) & mzTabMask;
+			mzTabKey[h] = mzKmers[i]; mzTabVal[h] = (uint32_t)i; // a repeated key keeps the LAST index, like the map assignment it replaces
+		}
 	}
 
 	GcGraphView view() const

@@ -173,6 +173,135 @@ inline std::string gamRecord(const std::vector<Alignment>& alns)
 	return gzipMember(raw);
 }
 
+
+// ---- direct GAM encoder: the same bytes as serialize(toAlignment(...)) without building the
+// message objects (one pass over the trace, two reusable buffers).  tests/ check both paths
+// against the reference's records.
+struct GamEncoder
+{
+	std::string mm, path, ee, msg;
+	static void putVarintTo(std::string& out, uint64_t v) { while (v >= 0x80) { out.push_back((char)((v & 0x7F) | 0x80)); v >>= 7; } out.push_back((char)v); }
+	void flushEdit(int32_t from, int32_t to, const std::string& seq)
+	{
+		ee.clear();
+		if (from) { ee.push_back((char)0x08); putVarintTo(ee, (uint64_t)(int64_t)from); }
+		if (to) { ee.push_back((char)0x10); putVarintTo(ee, (uint64_t)(int64_t)to); }
+		if (!seq.empty()) { ee.push_back((char)0x1A); putVarintTo(ee, seq.size()); ee += seq; }
+		mm.push_back((char)0x12); putVarintTo(mm, ee.size()); mm += ee;
+	}
+	void beginMapping(const GcHostGraph& g, int digraphNode, size_t offset)
+	{
+		mm.clear();
+		ee.clear(); // position message built in ee
+		int64_t nodeId = digraphNode / 2;
+		if (nodeId) { ee.push_back((char)0x08); putVarintTo(ee, (uint64_t)nodeId); }
+		if (offset) { ee.push_back((char)0x10); putVarintTo(ee, (uint64_t)offset); }
+		if (digraphNode % 2 == 1) { ee.push_back((char)0x20); ee.push_back((char)1); }
+		const std::string& name = g.originalNodeName(digraphNode);
+		if (!name.empty()) { ee.push_back((char)0x2A); putVarintTo(ee, name.size()); ee += name; }
+		mm.push_back((char)0x0A); putVarintTo(mm, ee.size()); mm += ee;
+	}
+	void endMapping(int rank)
+	{
+		if (rank) { mm.push_back((char)0x28); putVarintTo(mm, (uint64_t)rank); }
+		path.push_back((char)0x12); putVarintTo(path, mm.size()); path += mm;
+	}
+	// appends varint32 size + message of one alignment to `out`
+	void encode(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const GcAlnItem& item, std::string& out)
+	{
+		enum EditType { Match, Mismatch, Insertion, Deletion, Empty };
+		const std::vector<GcTraceItem>& trace = item.trace;
+		path.clear();
+		int curNode = trace[0].node; bool curReverse = (trace[0].node % 2) == 1; size_t curOffset = trace[0].nodeOffset;
+		int rank = 0;
+		beginMapping(g, curNode, curOffset);
+		int32_t from = 0, to = 0; std::string eseq;
+		EditType currentEdit = Empty;
+		size_t mismatches = 0, deletions = 0, insertions = 0, matches = 0;
+		if (characterMatch(trace[0].sequenceCharacter, trace[0].graphCharacter)) { currentEdit = Match; from++; to++; matches++; }
+		else { currentEdit = Mismatch; from++; to++; eseq = std::string { sequence[0] }; mismatches++; }
+		auto newEdit = [&]() { flushEdit(from, to, eseq); from = 0; to = 0; eseq.clear(); };
+		for (size_t pos = 1; pos < trace.size(); pos++)
+		{
+			int newNode = trace[pos].node; bool newReverse = (trace[pos].node % 2) == 1; size_t newOffset = trace[pos].nodeOffset;
+			bool insideNode = !trace[pos - 1].nodeSwitch || (newNode == curNode && newReverse == curReverse && newOffset > curOffset);
+			if (!insideNode)
+			{
+				flushEdit(from, to, eseq); from = 0; to = 0; eseq.clear();
+				endMapping(rank);
+				rank++;
+				curNode = newNode; curReverse = newReverse; curOffset = newOffset;
+				beginMapping(g, curNode, curOffset);
+				currentEdit = Empty;
+			}
+			if (trace[pos - 1].seqPos == trace[pos].seqPos)
+			{
+				if (currentEdit == Empty) currentEdit = Deletion;
+				if (currentEdit != Deletion) { newEdit(); currentEdit = Deletion; }
+				from++; deletions++;
+			}
+			else if (insideNode && trace[pos - 1].nodeOffset == trace[pos].nodeOffset)
+			{
+				if (currentEdit == Empty) currentEdit = Insertion;
+				if (currentEdit != Insertion) { newEdit(); currentEdit = Insertion; }
+				to++; eseq += trace[pos].sequenceCharacter; insertions++;
+			}
+			else if (characterMatch(trace[pos].sequenceCharacter, trace[pos].graphCharacter))
+			{
+				if (currentEdit == Empty) currentEdit = Match;
+				if (currentEdit != Match) { newEdit(); currentEdit = Match; }
+				from++; to++; matches++;
+			}
+			else
+			{
+				if (currentEdit == Empty) currentEdit = Mismatch;
+				if (currentEdit != Mismatch) { newEdit(); currentEdit = Mismatch; }
+				from++; to++; eseq += trace[pos].sequenceCharacter; mismatches++;
+			}
+		}
+		flushEdit(from, to, eseq);
+		endMapping(rank);
+		double identity = (double)matches / (double)(matches + mismatches + insertions + deletions);
+		msg.clear();
+		size_t alnLen = item.alignmentEnd - item.alignmentStart;
+		if (alnLen) { msg.push_back((char)0x0A); putVarintTo(msg, alnLen); msg.append(sequence, item.alignmentStart, alnLen); }
+		msg.push_back((char)0x12); putVarintTo(msg, path.size()); msg += path;
+		if (!seq_id.empty()) { msg.push_back((char)0x1A); putVarintTo(msg, seq_id.size()); msg += seq_id; }
+		if (item.traceScore) { msg.push_back((char)0x30); putVarintTo(msg, (uint64_t)(int64_t)item.traceScore); }
+		if ((int32_t)item.alignmentStart) { msg.push_back((char)0x38); putVarintTo(msg, (uint64_t)(int64_t)(int32_t)item.alignmentStart); }
+		uint64_t bits; std::memcpy(&bits, &identity, 8);
+		if (bits != 0) { msg.push_back((char)0x81); msg.push_back((char)0x01); for (int i = 0; i < 8; i++) msg.push_back((char)((bits >> (8 * i)) & 0xFF)); }
+		putVarintTo(out, msg.size());
+		out += msg;
+	}
+};
+
+inline std::string gzipMemberLevel(const std::string& raw, int level)
+{
+	z_stream zs; std::memset(&zs, 0, sizeof(zs));
+	deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+	std::string out;
+	out.resize(deflateBound(&zs, raw.size()) + 32);
+	zs.next_in = (Bytef*)raw.data(); zs.avail_in = (uInt)raw.size();
+	zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
+	deflate(&zs, Z_FINISH);
+	out.resize(out.size() - zs.avail_out);
+	deflateEnd(&zs);
+	return out;
+}
+
+// one read's GAM record straight from the final alignments (writeGAMToQueue, Aligner.cpp:261-281).
+// `level` = zlib level of the gzip member; the reference's GzipOutputStream uses the zlib default (6),
+// decoded records are identical at any level.
+inline std::string gamRecordDirect(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const std::vector<GcAlnItem>& alns, int level, GamEncoder& enc)
+{
+	std::string raw;
+	raw.reserve(sequence.size() * 2 + 256);
+	putVarint(raw, alns.size());
+	for (const GcAlnItem& a : alns) enc.encode(g, seq_id, sequence, a, raw);
+	return gzipMemberLevel(raw, level);
+}
+
 inline std::string jsonEscape(const std::string& s)
 {
 	std::string r = "\"";

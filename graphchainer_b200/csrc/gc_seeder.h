@@ -90,9 +90,9 @@ inline std::vector<GcSeedHit> getSeeds(const GcHostGraph& g, const std::string& 
 	const size_t maxCount = g.mzMaxCount;
 	iterateKmers(sequence, g.mzLength, g.mzWindow, [&](size_t pos, size_t kmer)
 	{
-		auto found = g.mzLookup.find(kmer);
-		if (found == g.mzLookup.end()) return;
-		size_t index = found->second;
+		int64_t found = g.mzFind(kmer);
+		if (found < 0) return;
+		size_t index = (size_t)found;
 		size_t start = g.mzKmerStart[index];
 		size_t end = g.mzKmerStart[index + 1];
 		size_t count = end - start;

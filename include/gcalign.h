@@ -31,6 +31,10 @@ typedef struct gcalign_options
 	int64_t colinear_split_len;   /* --colinear-split-len, default 35                     */
 	int64_t colinear_split_gap;   /* --colinear-split-gap, default 35                     */
 	uint64_t batch_bp;            /* read bases per internal GPU batch (0 = default)      */
+	int32_t gzip_level;           /* zlib level of the GAM gzip members: 0 = default (1, fastest);
+	                                 the reference's GzipOutputStream uses 6; decoded records
+	                                 are identical at every level                            */
+	int32_t reserved;
 } gcalign_options;
 
 /* per read: the fields of the reference's --short-verbose line (src/Aligner.cpp:909-915) */
