@@ -100,7 +100,7 @@ class Aligner:
 
     def align(self, batch: ReadBatch, gam: bool = True):
         """Returns (gam bytes, summaries, stats dict)."""
-        cap = max(1 << 20, batch.total_bp) if gam else 0
+        cap = (2 * batch.total_bp + (1 << 20)) if gam else 0
         out = np.zeros(cap, dtype=np.uint8) if gam else None
         used = C.c_uint64(0)
         summ = np.zeros(batch.n, dtype=SUMMARY)

@@ -125,6 +125,7 @@ struct GcHostGraph
 		v.outStart = outStart.data(); v.outNbr = outNbr.data();
 		v.componentNumber = componentNumber.data();
 		v.linearizable = linearizable.data();
+		v.coopLane = -1;
 		return v;
 	}
 

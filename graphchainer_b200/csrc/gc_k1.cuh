@@ -65,6 +65,7 @@ struct GcK1Workspace
 	GcSliceMeta* slices;   // [numSlices + 1]
 	GcNodeItem* items;     // [itemCap]
 	uint64_t* heap;        // [heapCap]
+	GcWord* cols;          // [64] columns of the node being recomputed (flatten / backtrace)
 	uint32_t itemCap;
 	uint32_t heapCap;
 };
@@ -91,6 +92,15 @@ GC_HD uint32_t gc_item_node(const GcNodeItem& it) { return it.nodeAndFlag & 0x7F
 // binary search of `node` in a slice (items sorted by componentNumber)
 GC_HD const GcNodeItem* gc_find_item(const GcGraphView& g, const GcNodeItem* items, uint32_t n, uint32_t node)
 {
+#if defined(__CUDA_ARCH__)
+	if (g.coopLane >= 0 && n <= 32)
+	{
+		// one probe: lane k holds the node of item k
+		uint32_t mine = ((uint32_t)g.coopLane < n) ? gc_item_node(items[g.coopLane]) : 0xFFFFFFFFu;
+		uint32_t m = __ballot_sync(0xFFFFFFFFu, mine == node);
+		return m ? &items[__ffs(m) - 1] : nullptr;
+	}
+#endif
 	uint32_t key = g.componentNumber[node];
 	uint32_t lo = 0, hi = n;
 	while (lo < hi)
@@ -381,7 +391,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 		int32_t previousQuitScore = pm.minScore + pm.bandwidth;
 		int32_t bandwidth = prm.bandwidth;
 		uint64_t eq[4];
-		gc_eq_vector(seq, seqLen, j, eq);
+		gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
 		// ---- seed the queue from the previous slice (Banded.h:235-277)
 		uint32_t heapSize = 0;
 		for (uint32_t k = 0; k < prevN; k++)
@@ -529,7 +539,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			sliceMinScore = GC_INT_MAX;
 			sliceMinNode = 0xFFFFFFFFu;
 			sliceMinOffset = 0xFFFFFFFFu;
-			GcWord cols[64];
+			GcWord* cols = ws.cols;
 			for (uint32_t s = 0; s < capacity; s++)
 			{
 				uint32_t k = slots[s];
@@ -697,7 +707,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 	}
 	uint32_t currentNode = 0xFFFFFFFFu;
 	int32_t currentSlice = -1;
-	GcWord cols[64];
+	GcWord* cols = ws.cols;
 	uint64_t eq[4];
 	uint32_t guard = 0;
 	uint32_t guardMax = (uint32_t)seqLen * 4 + 1024 + traceCap;
@@ -713,7 +723,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 		int32_t j = (newSlice - 1) * 64;
 		if (newSlice != currentSlice || newNode != currentNode)
 		{
-			if (newSlice != currentSlice) gc_eq_vector(seq, seqLen, j, eq);
+			if (newSlice != currentSlice) gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
 			currentSlice = newSlice;
 			currentNode = newNode;
 			const GcNodeItem* me = gc_find_item(g, cur, cm.numItems, currentNode);

@@ -512,7 +512,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	// the results are then consumed strictly in seed order with the rules re-evaluated exactly as
 	// the reference does -- a speculative result whose seed turns out to be skipped is discarded.
 	struct S1Cand { size_t seedIdx; ExtRef ref; };
-	struct S1State { size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; };
+	struct S1State { size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; std::vector<gcgpu_ext_item> localItems; size_t itemBase = 0; };
 	std::vector<S1State> s1(R);
 	for (size_t r = 0; r < R; r++) if (seedsOrdered[r].empty()) s1[r].done = true;
 	// 0 = extend, 1 = skip, 2 = stop the seed loop, 3 = assertion (read dropped)
@@ -530,6 +530,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	{
 		items.clear();
 		std::vector<size_t> active;
+		// candidates are collected per read in parallel (work items local to the read), then concatenated
+		#pragma omp parallel for schedule(dynamic, 8)
 		for (size_t r = 0; r < R; r++)
 		{
 			S1State& st = s1[r];
@@ -537,13 +539,14 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
 			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : params.s1LaterRoundSeeds;
 			st.cands.clear();
+			st.localItems.clear();
 			for (size_t i = st.i; i < seedHits.size() && st.cands.size() < want; i++)
 			{
 				int rule = seedRule(st, seedHits[i]);
 				if (rule >= 2) break; // decided again, in order, when the results are consumed
 				if (rule == 1) continue;
 				S1Cand c; c.seedIdx = i;
-				c.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seedHits[i], items);
+				c.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seedHits[i], st.localItems);
 				st.cands.push_back(c);
 			}
 			st.round++;
@@ -553,7 +556,14 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				for (; st.i < seedHits.size(); st.i++) { int rule = seedRule(st, seedHits[st.i]); if (rule == 3) out[r].dropped = true; if (rule >= 2) break; }
 				st.done = true;
 			}
-			else active.push_back(r);
+		}
+		for (size_t r = 0; r < R; r++)
+		{
+			S1State& st = s1[r];
+			if (st.done || st.cands.empty()) continue;
+			st.itemBase = items.size();
+			items.insert(items.end(), st.localItems.begin(), st.localItems.end());
+			active.push_back(r);
 		}
 		if (active.empty()) break;
 		stats.s1Rounds++;
@@ -577,8 +587,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				const S1Cand& c = st.cands[next++];
 				st.seedsExtended += 1;
 				GcPackedAln item;
-				bool ok = buildAlignment(seed, c.ref, results.data(), traces, item);
-				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && results[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
+				const gcgpu_ext_result* readResults = results.data() + st.itemBase;
+				bool ok = buildAlignment(seed, c.ref, readResults, traces, item);
+				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && readResults[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
 				if (!ok || item.alignmentEnd == item.alignmentStart) continue;
 				st.alns.emplace_back(item);
 				std::sort(st.alns.begin(), st.alns.end(), [](const GcPackedAln& left, const GcPackedAln& right) { return left.alignmentStart < right.alignmentStart; });

@@ -102,9 +102,10 @@ static size_t k1WorkspaceBytes(uint32_t numSlices, uint32_t itemCap, uint32_t he
 }
 
 __device__ __forceinline__ void gc_k1_run_item(const GcGraphView& g, const GcViterbiTables* vt, const GcK1Params& prm, const uint8_t* seq, const GcK1Desc& d,
-	uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
+	uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, GcWord* cols)
 {
 	GcK1Workspace ws;
+	ws.cols = cols;
 	uint8_t* base = arena + d.wsOff;
 	ws.slices = (GcSliceMeta*)base;
 	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
@@ -142,20 +143,25 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	d.wsOff = lay.wsBase + (uint64_t)t * lay.wsStride;
 	d.traceOff = lay.traceBase + (uint64_t)t * lay.traceStride;
 	d.itemCap = lay.itemCap; d.heapCap = lay.heapCap; d.traceCap = lay.traceStride; d.numSlices = lay.numSlices; d.resultIndex = idx;
-	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow);
+	GcWord cols[64];
+	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, cols);
 }
 
-// Long work items (whole-read extensions, thousands of dependent column steps): one WARP per item,
-// lane 0 walks the item.  A thread-per-item launch would serialise 32 divergent walks inside each
-// warp; with a private warp every walk issues at the full single-warp rate and the scheduler
-// interleaves up to 64 of them per SM.
+// Long work items (whole-read extensions: ~80 slices, tens of thousands of dependent column steps):
+// one WARP per item.  All 32 lanes execute the item in lockstep with identical values (one
+// instruction stream, no divergence), which (a) keeps the walk at the single-warp issue rate instead
+// of serialising 32 divergent walks, (b) lets loop-free lookups use the lanes -- the slice hash
+// lookup becomes one ballot over the slice's items, the Eq masks of a slice eight ballots -- and
+// (c) moves the recomputed node columns from per-thread local memory to shared memory.
 __global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
 {
+	__shared__ GcWord colsShared[4][64];
 	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (t >= n || (threadIdx.x & 31) != 0) return;
+	if (t >= n) return;
+	g.coopLane = (int32_t)(threadIdx.x & 31);
 	GcK1Desc d = descs[t];
-	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow);
+	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, colsShared[threadIdx.x >> 5]);
 }
 
 // trace lengths of the finished items (input of the exclusive scan that places them in the dense buffer)
@@ -259,7 +265,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.numNodes = N;
 	ctx->view.nodeLength = ctx->d_nodeLength; ctx->view.nodeSeq = ctx->d_nodeSeq;
 	ctx->view.inStart = ctx->d_inStart; ctx->view.inNbr = ctx->d_inNbr; ctx->view.outStart = ctx->d_outStart; ctx->view.outNbr = ctx->d_outNbr;
-	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable;
+	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1;
 	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
 	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
 	*out = ctx;

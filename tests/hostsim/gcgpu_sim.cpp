@@ -35,7 +35,7 @@ extern "C" int gcgpu_create(int, const gcgpu_graph* g, const gcgpu_params* p, gc
 	gcgpu_ctx* c = new gcgpu_ctx();
 	c->view.numNodes = g->num_nodes; c->view.nodeLength = g->node_length; c->view.nodeSeq = g->node_seq;
 	c->view.inStart = g->in_start; c->view.inNbr = g->in_nbr; c->view.outStart = g->out_start; c->view.outNbr = g->out_nbr;
-	c->view.componentNumber = g->component_number; c->view.linearizable = g->linearizable;
+	c->view.componentNumber = g->component_number; c->view.linearizable = g->linearizable; c->view.coopLane = -1;
 	c->mpc.compMap = g->comp_map; c->mpc.compIdx = g->comp_idx; c->mpc.compStart = g->comp_start; c->mpc.topoIds = g->topo_ids;
 	c->mpc.pathsStart = g->paths_start; c->mpc.pathsK = g->paths_k; c->mpc.backStart = g->back_start; c->mpc.backNode = g->back_node; c->mpc.backK = g->back_k;
 	c->vt = gcMakeViterbiTables();
@@ -70,7 +70,8 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seqIn, uint64_t seqBy
 			std::vector<GcSliceMeta> slices(numSlices + 2);
 			std::vector<GcNodeItem> nodeItems(itemCap);
 			std::vector<uint64_t> heap(heapCap);
-			GcK1Workspace ws { slices.data(), nodeItems.data(), heap.data(), itemCap, heapCap };
+			GcWord colsBuf[64];
+			GcK1Workspace ws { slices.data(), nodeItems.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { ctx->bandwidth };
 			gc_k1_extend(ctx->view, ctx->vt, prm, seq + items[i].seq_offset, seqLen, items[i].node, items[i].offset, ws, trace.data(), (uint32_t)trace.size(), res);
 			if (res.status == GC_OVERFLOW_ITEMS) { itemCap *= 4; continue; }

@@ -432,7 +432,8 @@ int main(int argc, char** argv)
 			std::vector<GcNodeItem> items(itemCap);
 			std::vector<uint64_t> heap(heapCap);
 			trace.assign(2 * (size_t)seqLen + 256, 0);
-			GcK1Workspace ws { slices.data(), items.data(), heap.data(), itemCap, heapCap };
+			GcWord colsBuf[64];
+			GcK1Workspace ws { slices.data(), items.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { 10 };
 			gc_k1_extend(g, vt, prm, seq.data(), seqLen, node, off, ws, trace.data(), (uint32_t)trace.size(), res);
 			if (res.status == GC_OVERFLOW_ITEMS) { itemCap *= 4; continue; }
