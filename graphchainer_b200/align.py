@@ -9,6 +9,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgcalign.so")
+# tests on the GPU-less box point this at a build of gc_capi.cpp linked against the C-ABI test double
+_LIB_OVERRIDE = os.environ.get("GCALIGN_TEST_LIB")
 
 
 class Options(C.Structure):
@@ -34,9 +36,10 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
-        lib = C.CDLL(LIB_PATH)
+        path = _LIB_OVERRIDE or LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        lib = C.CDLL(path)
         lib.gcalign_default_options.argtypes = [C.POINTER(Options)]
         lib.gcalign_last_error.restype = C.c_char_p
         lib.gcalign_open.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(C.c_void_p)]
@@ -48,6 +51,15 @@ def load():
 
 class ReadBatch:
     """Reads packed into the flat host buffers gcalign_align takes."""
+
+    def subset(self, indices):
+        """The reads `indices` (a rank's shard) as a new batch."""
+        seqs = [bytes(self.seq_buf[int(self.seq_off[i]):int(self.seq_off[i + 1])]).decode() for i in indices]
+        names = [bytes(self.name_buf[int(self.name_off[i]):int(self.name_off[i + 1])]).decode() for i in indices]
+        return ReadBatch(names, seqs)
+
+    def lengths(self):
+        return np.diff(self.seq_off.astype(np.int64))
 
     def __init__(self, names, seqs):
         self.n = len(seqs)

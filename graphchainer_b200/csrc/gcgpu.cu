@@ -164,6 +164,22 @@ __global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const Gc
 	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, colsShared[threadIdx.x >> 5]);
 }
 
+// Experimental: G items per warp on lanes 0..G-1 (plain SIMT sharing of the instruction stream)
+__global__ void __launch_bounds__(128) gc_k1_long_simt_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint32_t G, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
+{
+	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t lane = threadIdx.x & 31;
+	if (lane >= G) return;
+	// item k of the warp = descs[warp + k * numWarps]: the items of one warp have similar lengths (descs are sorted by length)
+	uint32_t numWarps = (n + G - 1) / G;
+	uint32_t t = warp + lane * numWarps;
+	if (warp >= numWarps || t >= n) return;
+	GcK1Desc d = descs[t];
+	GcWord cols[64];
+	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, cols);
+}
+
 // trace lengths of the finished items (input of the exclusive scan that places them in the dense buffer)
 __global__ void gc_k1_lengths_kernel(const GcK1Result* __restrict__ results, uint32_t n, uint64_t* __restrict__ lens)
 {
@@ -376,6 +392,13 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (nLong)
 	{
+		static const int simtG = getenv("GCGPU_K1_SIMT") ? atoi(getenv("GCGPU_K1_SIMT")) : 0;
+		if (simtG > 0)
+		{
+			uint32_t numWarps = (nLong + simtG - 1) / simtG;
+			gc_k1_long_simt_kernel<<<(numWarps + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint32_t)simtG, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+		}
+		else
 		gc_k1_long_kernel<<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		ctx->launches++;
 	}
