@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=640, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="read batches in flight per GPU in the e2e measurement")
+    ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -158,7 +159,7 @@ def main():
     batch = align.ReadBatch([r[0] for r in reads], [r[1] for r in reads])
     threads = max(1, host_cores // world)
     t_index = time.perf_counter()
-    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=args.streams)
+    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=args.streams, batch_bp=args.batch_bp)
     index_s = time.perf_counter() - t_index
 
     def barrier():
@@ -185,7 +186,7 @@ def main():
     aligner.close()
     # ---- kernel time: the same steps with ONE batch in flight, so that every CUDA-event pair brackets a
     # kernel that has the GPU to itself (with several streams the event durations of overlapping kernels add up)
-    aligner1 = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=1)
+    aligner1 = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=1, batch_bp=args.batch_bp)
     for _ in range(args.warmup):
         aligner1.align(batch, gam=False)
     barrier()
@@ -237,7 +238,7 @@ def main():
                          "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
             "kernels_ms_per_step": {"k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
-            "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams}
+            "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp}
     if not args.no_cpu_baseline and os.path.exists(REFBIN):
         sample = min(args.cpu_sample, n_reads)
         fa = os.path.join(tmp, "sample.fa")

@@ -278,8 +278,9 @@ GC_HD uint32_t gc_phmap_normalize_capacity(uint64_t n)
 	while (c < n) c = c * 2 + 1;
 	return c;
 }
-// keys = node ids of items[0..n-1], inserted in that order.  Returns false if scratch is too small.
-GC_HD bool gc_phmap_order(const GcNodeItem* items, uint32_t n, uint32_t reserveN, uint32_t* slots, uint32_t scratchCap, uint32_t* capacityOut)
+// keys = key(0..n-1), inserted in that order.  Returns false if scratch is too small.
+template <typename KeyFn>
+GC_HD bool gc_phmap_order_keys(const KeyFn& key, uint32_t n, uint32_t reserveN, uint32_t* slots, uint32_t scratchCap, uint32_t* capacityOut)
 {
 	// reserve(n): rehash(GrowthToLowerboundCapacity(n)) -> capacity NormalizeCapacity(n + (n-1)/7)
 	uint32_t capacity = 0;
@@ -305,20 +306,31 @@ GC_HD bool gc_phmap_order(const GcNodeItem* items, uint32_t n, uint32_t reserveN
 			for (uint32_t s = 0; s < capacity; s++)
 			{
 				if (slots[s] == 0xFFFFFFFFu) continue;
-				uint32_t t = gc_phmap_find_slot(fresh, newCap, gc_phmap_hash((uint64_t)gc_item_node(items[slots[s]])));
+				uint32_t t = gc_phmap_find_slot(fresh, newCap, gc_phmap_hash(key(slots[s])));
 				fresh[t] = slots[s];
 			}
 			for (uint32_t s = 0; s < newCap; s++) slots[s] = fresh[s];
 			capacity = newCap;
 			growthLeft = (capacity - capacity / 8) - size;
 		}
-		uint32_t t = gc_phmap_find_slot(slots, capacity, gc_phmap_hash((uint64_t)gc_item_node(items[i])));
+		uint32_t t = gc_phmap_find_slot(slots, capacity, gc_phmap_hash(key(i)));
 		slots[t] = i;
 		size++;
 		growthLeft--;
 	}
 	*capacityOut = capacity;
 	return true;
+}
+struct GcItemNodeKey
+{
+	const GcNodeItem* items;
+	GC_HD uint64_t operator()(uint32_t i) const { return (uint64_t)gc_item_node(items[i]); }
+};
+// keys = node ids of items[0..n-1]
+GC_HD bool gc_phmap_order(const GcNodeItem* items, uint32_t n, uint32_t reserveN, uint32_t* slots, uint32_t scratchCap, uint32_t* capacityOut)
+{
+	GcItemNodeKey key; key.items = items;
+	return gc_phmap_order_keys(key, n, reserveN, slots, scratchCap, capacityOut);
 }
 
 // AlignmentCorrectnessEstimationState::NextState (AlignmentCorrectnessEstimation.cpp:105-129)
@@ -347,6 +359,16 @@ struct GcK1Params
 // ------------------------------------------------------------------------------------
 // Forward pass.  Returns the number of slices kept (index of the last slice in ws.slices),
 // after removeWronglyAlignedEnd; <= 0 means the extension failed.
+//
+// Shape of the loop (B200): one thread owns one work item and the 32 items of a warp run in SIMT.
+// The reference's nest "for slice { while queue { node: merge incoming; <=63 column steps; push } }"
+// is flattened into ONE loop whose body is
+//     stage 1  finish the previous node / close and open slices / pop the next node and merge its
+//              incoming columns -- repeated while the popped node is a single column (no column steps)
+//     stage 2  the column steps of that node (gc_node_columns)
+// so that every lane of a warp meets the others at the single column loop once per node, no matter
+// which slice each of them is in.  (In the nested form the lanes wait for each other at every slice
+// end and the one-column SNP nodes occupy a whole column-loop slot: measured 6 of 32 lanes active.)
 GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, const uint8_t* seq, int32_t seqLen, uint32_t startNode, uint32_t startOffset,
 	GcK1Workspace& ws, GcK1Result& res)
 {
@@ -374,60 +396,154 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 		it.endVP = 0; it.endVN = 0; it.endScore = (int32_t)len - 1 - (int32_t)startOffset;
 		it.minScore = 0;
 		it.nodeAndFlag = startNode;
-		uint64_t HN = 0, HP = 0;
-		for (uint32_t i = 1; i <= startOffset; i++) HN |= 1ULL << i;
-		for (uint32_t i = startOffset + 1; i < len; i++) HP |= 1ULL << i;
-		it.HP = HP; it.HN = HN;
+		// HN bits 1..startOffset, HP bits startOffset+1..len-1
+		uint64_t upTo = startOffset >= 63 ? ~0ULL : ((2ULL << startOffset) - 1);
+		uint64_t lenMask = len >= 64 ? ~0ULL : ((1ULL << len) - 1);
+		it.HN = upTo & ~1ULL;
+		it.HP = lenMask & ~upTo;
 		itemsUsed = 1;
 	}
+	const int32_t bandwidth = prm.bandwidth;
 	int32_t lastSlice = 0;
-	for (int32_t slice = 0; slice < numSlices; slice++)
+	int32_t status = GC_OK;
+	uint64_t columns = 0;
+	// ---- state of the slice being filled
+	int32_t slice = -1, j = 0;
+	const GcNodeItem* prevItems = nullptr;
+	uint32_t prevN = 0;
+	int32_t previousMinScore = 0, previousQuitScore = 0;
+	uint64_t eq[4] = { 0, 0, 0, 0 };
+	uint32_t heapSize = 0;
+	uint32_t firstItem = 0, curN = 0;
+	GcNodeItem* curItems = ws.items;
+	int32_t sliceMinScore = 0, currentMinScoreAtEndRow = 0;
+	uint32_t sliceMinNode = 0xFFFFFFFFu, sliceMinOffset = 0xFFFFFFFFu;
+	uint64_t lastKey = ~0ULL;
+	bool needFlatten = false;
+	// ---- state of the node in flight
+	bool pending = false;
+	uint32_t node = 0;
+	GcWord w; w.VP = 0; w.VN = 0; w.scoreEnd = 0;
+	GcWord endW = w;
+	uint64_t HP = 0, HN = 0, prevHP = 0, prevHN = 0;
+	int32_t nodeMin = 0, prevStart = 0;
+	uint32_t nodeMinOffset = 0;
+	bool prevExists = false;
+	bool running = numSlices > 0;
+	while (running)
 	{
-		const GcSliceMeta& pm = ws.slices[lastSlice];
-		const GcNodeItem* prevItems = ws.items + pm.firstItem;
-		uint32_t prevN = pm.numItems;
-		int32_t j = slice * 64;
-		int32_t previousMinScore = pm.minScore;
-		int32_t previousQuitScore = pm.minScore + pm.bandwidth;
-		int32_t bandwidth = prm.bandwidth;
-		uint64_t eq[4];
-		gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
-		// ---- seed the queue from the previous slice (Banded.h:235-277)
-		uint32_t heapSize = 0;
-		for (uint32_t k = 0; k < prevN; k++)
+		// ================= stage 1 =================
+		while (true)
 		{
-			const GcNodeItem& pn = prevItems[k];
-			uint32_t node = gc_item_node(pn);
-			if (j > 0)
+			if (pending)
 			{
-				if (pn.minScore > previousQuitScore) continue;
-				if (g.linearizable[node])
+				// ---- store the node, push its end column to the out-neighbours (Banded.h:363-387); old end = {0,0,INT_MAX}
+				pending = false;
+				GcNodeItem& item = ws.items[itemsUsed++];
+				curN++;
+				item.startVP = w.VP; item.startVN = w.VN; item.startScore = w.scoreEnd;
+				item.endVP = endW.VP; item.endVN = endW.VN; item.endScore = endW.scoreEnd;
+				item.HP = HP; item.HN = HN;
+				item.minScore = nodeMin;
+				if (nodeMin < currentMinScoreAtEndRow) currentMinScoreAtEndRow = nodeMin;
+				int32_t sbsEnd = gc_sbs(endW);
+				uint64_t VP = endW.VP, VN = endW.VN;
+				uint64_t plm = (VP & (VN - VP));
+				plm >>= 1;
+				plm |= 0x8000000000000000ULL & (VN | ~(VN - VP)) & ~VP;
+				int32_t newEndMinScore = sbsEnd;
+				while (plm != 0)
 				{
-					uint32_t nb = g.inNbr[g.inStart[node]];
-					const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
-					if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) continue;
+					uint64_t cm = plm ^ (plm - 1);
+					int32_t sh = sbsEnd + gc_popc(VP & cm) - gc_popc(VN & cm);
+					if (sh < newEndMinScore) newEndMinScore = sh;
+					plm &= ~cm;
 				}
+				uint32_t flag = 0;
+				if (newEndMinScore <= currentMinScoreAtEndRow + bandwidth)
+				{
+					flag = 0x80000000u;
+					for (uint32_t e = g.outStart[node]; e < g.outStart[node + 1]; e++)
+					{
+						uint32_t nb = g.outNbr[e];
+						if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[nb] << 32) | nb)) { status = GC_OVERFLOW_HEAP; running = false; break; }
+					}
+				}
+				item.nodeAndFlag = node | flag;
+				if (nodeMin < sliceMinScore)
+				{
+					sliceMinScore = nodeMin;
+					sliceMinNode = node;
+					sliceMinOffset = nodeMinOffset;
+				}
+				if (!running) break;
 			}
-			if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[node] << 32) | node)) { res.status = GC_OVERFLOW_HEAP; return 0; }
-		}
-		uint32_t firstItem = itemsUsed;
-		uint32_t curN = 0;
-		GcNodeItem* curItems = ws.items + firstItem;
-		int32_t sliceMinScore = GC_INT_MAX - bandwidth - 1;
-		uint32_t sliceMinNode = 0xFFFFFFFFu, sliceMinOffset = 0xFFFFFFFFu;
-		int32_t currentMinScoreAtEndRow = sliceMinScore;
-		uint64_t lastKey = ~0ULL;
-		while (heapSize > 0)
-		{
+			if (heapSize == 0)
+			{
+				if (slice >= 0)
+				{
+					// ---- close the slice (Banded.h:589-607)
+					if (sliceMinNode == 0xFFFFFFFFu) { status = GC_INTERNAL; running = false; break; }
+					if (j + 64 > seqLen) { needFlatten = true; running = false; break; } // partial last slice: flattened below
+					const GcSliceMeta& pm = ws.slices[lastSlice];
+					GcSliceMeta& nm = ws.slices[lastSlice + 1];
+					nm.minScore = sliceMinScore;
+					nm.minScoreNode = sliceMinNode;
+					nm.minScoreNodeOffset = sliceMinOffset;
+					nm.bandwidth = bandwidth;
+					nm.firstItem = firstItem;
+					nm.numItems = curN;
+					gc_viterbi_next(vt, pm, sliceMinScore - previousMinScore, nm);
+					if (!nm.correctFromCorrect) { running = false; break; } // the new slice is dropped
+					lastSlice++;
+					if (slice + 1 >= numSlices) { running = false; break; }
+				}
+				// ---- open the next slice: seed the queue from the previous one (Banded.h:235-277)
+				slice++;
+				j = slice * 64;
+				const GcSliceMeta& pm = ws.slices[lastSlice];
+				prevItems = ws.items + pm.firstItem;
+				prevN = pm.numItems;
+				previousMinScore = pm.minScore;
+				previousQuitScore = pm.minScore + pm.bandwidth;
+				gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
+				for (uint32_t k = 0; k < prevN; k++)
+				{
+					const GcNodeItem& pn = prevItems[k];
+					uint32_t nd = gc_item_node(pn);
+					if (j > 0)
+					{
+						if (pn.minScore > previousQuitScore) continue;
+						if (g.linearizable[nd])
+						{
+							uint32_t nb = g.inNbr[g.inStart[nd]];
+							const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
+							if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) continue;
+						}
+					}
+					if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[nd] << 32) | nd)) { status = GC_OVERFLOW_HEAP; running = false; break; }
+				}
+				if (!running) break;
+				firstItem = itemsUsed;
+				curN = 0;
+				curItems = ws.items + firstItem;
+				sliceMinScore = GC_INT_MAX - bandwidth - 1;
+				sliceMinNode = 0xFFFFFFFFu; sliceMinOffset = 0xFFFFFFFFu;
+				currentMinScoreAtEndRow = sliceMinScore;
+				lastKey = ~0ULL;
+				if (heapSize == 0) continue; // nothing seeded: closed (as an internal error) at the top
+			}
+			// ---- pop the next node, merge its incoming columns (BVCommon.h:903-964)
 			uint64_t key = gc_heap_pop(ws.heap, heapSize);
 			if (key == lastKey) continue;
 			lastKey = key;
-			uint32_t i = (uint32_t)key;
-			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, i);
-			bool prevExists = prevItem != nullptr;
-			int32_t prevStart = prevExists ? prevItem->startScore : 0;
-			// ---- incoming columns (BVCommon.h:903-964)
-			GcWord w; bool hasWs = false;
+			node = (uint32_t)key;
+			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, node);
+			prevExists = prevItem != nullptr;
+			prevStart = prevExists ? prevItem->startScore : 0;
+			prevHP = prevExists ? prevItem->HP : ~0ULL;
+			prevHN = prevExists ? prevItem->HN : 0ULL;
+			bool hasWs = false;
 			w.VP = 0; w.VN = 0; w.scoreEnd = 0;
 			bool seeded = false;
 			if (prevExists)
@@ -436,9 +552,9 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				if (j > 0)
 				{
 					if (prevItem->minScore > previousQuitScore) seeded = false;
-					else if (g.linearizable[i])
+					else if (g.linearizable[node])
 					{
-						uint32_t nb = g.inNbr[g.inStart[i]];
+						uint32_t nb = g.inNbr[g.inStart[node]];
 						const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
 						if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) seeded = false;
 					}
@@ -449,8 +565,8 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				w.VP = ~0ULL; w.VN = 0; w.scoreEnd = prevStart + 64; // getSourceSliceFromScore
 				hasWs = true;
 			}
-			uint64_t Eq0 = eq[gc_node_base(g, i, 0)];
-			for (uint32_t e = g.inStart[i]; e < g.inStart[i + 1]; e++)
+			uint64_t Eq0 = eq[gc_node_base(g, node, 0)];
+			for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
 			{
 				uint32_t p = g.inNbr[e];
 				const GcNodeItem* pit = gc_find_item(g, curItems, curN, p);
@@ -474,95 +590,65 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				}
 				if (!hasWs) { w = nw; hasWs = true; }
 				else w = gc_merge(w, nw);
-				res.columns++;
+				columns++;
 			}
-			if (!hasWs) { res.status = GC_INTERNAL; return 0; }
+			if (!hasWs) { status = GC_INTERNAL; running = false; break; }
 			if (prevExists && gc_sbs(w) > prevStart)
 			{
 				GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
 				w = gc_merge(w, src);
 			}
-			if (itemsUsed >= ws.itemCap) { res.status = GC_OVERFLOW_ITEMS; return 0; }
-			GcNodeItem& item = ws.items[itemsUsed++];
-			curN++;
-			GcWord endW; uint64_t HP, HN; int32_t nodeMin; uint32_t nodeMinOffset;
-			gc_node_columns(g, i, eq, w, prevExists, prevStart, prevExists ? prevItem->HP : ~0ULL, prevExists ? prevItem->HN : 0ULL, endW, HP, HN, nodeMin, nodeMinOffset, nullptr);
-			res.columns += g.nodeLength[i];
-			item.startVP = w.VP; item.startVN = w.VN; item.startScore = w.scoreEnd;
-			item.endVP = endW.VP; item.endVN = endW.VN; item.endScore = endW.scoreEnd;
-			item.HP = HP; item.HN = HN;
-			item.minScore = nodeMin;
-			item.nodeAndFlag = i;
-			if (nodeMin < currentMinScoreAtEndRow) currentMinScoreAtEndRow = nodeMin;
-			// ---- push to the out-neighbours (Banded.h:363-387); old end = {0,0,INT_MAX}
-			{
-				int32_t sbsEnd = gc_sbs(endW);
-				uint64_t VP = endW.VP, VN = endW.VN;
-				uint64_t plm = (VP & (VN - VP));
-				plm >>= 1;
-				plm |= 0x8000000000000000ULL & (VN | ~(VN - VP)) & ~VP;
-				int32_t newEndMinScore = sbsEnd;
-				while (plm != 0)
-				{
-					uint64_t cm = plm ^ (plm - 1);
-					int32_t sh = sbsEnd + gc_popc(VP & cm) - gc_popc(VN & cm);
-					if (sh < newEndMinScore) newEndMinScore = sh;
-					plm &= ~cm;
-				}
-				if (newEndMinScore <= currentMinScoreAtEndRow + bandwidth)
-				{
-					item.nodeAndFlag |= 0x80000000u;
-					for (uint32_t e = g.outStart[i]; e < g.outStart[i + 1]; e++)
-					{
-						uint32_t nb = g.outNbr[e];
-						if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[nb] << 32) | nb)) { res.status = GC_OVERFLOW_HEAP; return 0; }
-					}
-				}
-			}
-			if (nodeMin < sliceMinScore)
-			{
-				sliceMinScore = nodeMin;
-				sliceMinNode = i;
-				sliceMinOffset = nodeMinOffset;
-			}
+			if (itemsUsed >= ws.itemCap) { status = GC_OVERFLOW_ITEMS; running = false; break; }
+			uint32_t len = g.nodeLength[node];
+			columns += len;
+			pending = true;
+			if (len > 1) break; // to the column steps
+			// a single-column node has no column steps (the tail of calculateNodeInner does nothing)
+			endW = w; HP = 0; HN = 0; nodeMin = w.scoreEnd; nodeMinOffset = 0;
 		}
-		if (sliceMinNode == 0xFFFFFFFFu) { res.status = GC_INTERNAL; return 0; }
-		// ---- flattenLastSliceEnd (BVCommon.h:1171-1229) for a partial last slice
-		if (j + 64 > seqLen)
+		if (!running) break;
+		// ================= stage 2 =================
+		gc_node_columns(g, node, eq, w, prevExists, prevStart, prevHP, prevHN, endW, HP, HN, nodeMin, nodeMinOffset, nullptr);
+	}
+	res.columns = columns;
+	res.status = status;
+	if (status != GC_OK) return 0;
+	// ---- flattenLastSliceEnd (BVCommon.h:1171-1229) for a partial last slice, then close it
+	if (needFlatten)
+	{
+		uint32_t rows = (uint32_t)(seqLen - j);
+		uint64_t rowMask = ~(~0ULL << rows);
+		// phmap iteration order of the slice's node map: reserve(previous size), insert in processing order
+		uint32_t* slots = (uint32_t*)ws.heap;
+		uint32_t capacity = 0;
+		if (!gc_phmap_order(curItems, curN, prevN, slots, ws.heapCap * 2, &capacity)) { res.status = GC_OVERFLOW_HEAP; return 0; }
+		sliceMinScore = GC_INT_MAX;
+		sliceMinNode = 0xFFFFFFFFu;
+		sliceMinOffset = 0xFFFFFFFFu;
+		GcWord* cols = ws.cols;
+		for (uint32_t s = 0; s < capacity; s++)
 		{
-			uint32_t rows = (uint32_t)(seqLen - j);
-			uint64_t rowMask = ~(~0ULL << rows);
-			// phmap iteration order of the slice's node map: reserve(previous size), insert in processing order
-			uint32_t* slots = (uint32_t*)ws.heap;
-			uint32_t capacity = 0;
-			if (!gc_phmap_order(curItems, curN, prevN, slots, ws.heapCap * 2, &capacity)) { res.status = GC_OVERFLOW_HEAP; return 0; }
-			sliceMinScore = GC_INT_MAX;
-			sliceMinNode = 0xFFFFFFFFu;
-			sliceMinOffset = 0xFFFFFFFFu;
-			GcWord* cols = ws.cols;
-			for (uint32_t s = 0; s < capacity; s++)
+			uint32_t k = slots[s];
+			if (k == 0xFFFFFFFFu) continue;
+			const GcNodeItem& it = curItems[k];
+			uint32_t nd = gc_item_node(it);
+			const GcNodeItem* old = gc_find_item(g, prevItems, prevN, nd);
+			gc_recalc_node(g, it, eq, old, cols);
+			uint32_t len = g.nodeLength[nd];
+			res.columns += len;
+			for (uint32_t c = 0; c < len; c++)
 			{
-				uint32_t k = slots[s];
-				if (k == 0xFFFFFFFFu) continue;
-				const GcNodeItem& it = curItems[k];
-				uint32_t node = gc_item_node(it);
-				const GcNodeItem* old = gc_find_item(g, prevItems, prevN, node);
-				gc_recalc_node(g, it, eq, old, cols);
-				uint32_t len = g.nodeLength[node];
-				res.columns += len;
-				for (uint32_t c = 0; c < len; c++)
+				// flattenWordSlice (BVCommon.h:265-273)
+				int32_t sc = cols[c].scoreEnd - gc_popc(cols[c].VP & ~rowMask) + gc_popc(cols[c].VN & ~rowMask);
+				if (sc < sliceMinScore)
 				{
-					// flattenWordSlice (BVCommon.h:265-273)
-					int32_t sc = cols[c].scoreEnd - gc_popc(cols[c].VP & ~rowMask) + gc_popc(cols[c].VN & ~rowMask);
-					if (sc < sliceMinScore)
-					{
-						sliceMinScore = sc;
-						sliceMinNode = node;
-						sliceMinOffset = c;
-					}
+					sliceMinScore = sc;
+					sliceMinNode = nd;
+					sliceMinOffset = c;
 				}
 			}
 		}
+		const GcSliceMeta& pm = ws.slices[lastSlice];
 		GcSliceMeta& nm = ws.slices[lastSlice + 1];
 		nm.minScore = sliceMinScore;
 		nm.minScoreNode = sliceMinNode;
@@ -571,8 +657,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 		nm.firstItem = firstItem;
 		nm.numItems = curN;
 		gc_viterbi_next(vt, pm, sliceMinScore - previousMinScore, nm);
-		if (!nm.correctFromCorrect) break; // Banded.h:589-607: the new slice is dropped
-		lastSlice++;
+		if (nm.correctFromCorrect) lastSlice++;
 	}
 	res.itemsUsed = itemsUsed;
 	// ---- removeWronglyAlignedEnd (BVCommon.h:1231-1241)
@@ -732,6 +817,34 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			gc_recalc_node(g, *me, eq, pme, cols);
 			res.columns += g.nodeLength[currentNode];
 		}
+		// inside the node (BVCommon.h:556-597): walk to the node's first column or the slice's first row, then cross below
+		// (one loop iteration = one node visit: recompute, walk, cross -- the lanes of a warp stay in step)
+		if ((tw.seqPos & 63) != 0 && tw.offset != 0)
+		{
+			uint32_t hori = tw.offset;
+			int32_t vert = tw.seqPos - j;
+			while (hori > 0 && vert > 0)
+			{
+				int32_t scoreHere = gc_value(cols[hori], vert);
+				int32_t verticalScore = gc_value(cols[hori], vert - 1);
+				int32_t diagonalScore = gc_value(cols[hori - 1], vert - 1);
+				bool eqc = gc_char_match(seq[vert + j], gc_node_base(g, currentNode, hori));
+				if (verticalScore == scoreHere - 1)
+				{
+					vert--;
+				}
+				else if (diagonalScore == scoreHere - (eqc ? 0 : 1))
+				{
+					hori--;
+					vert--;
+				}
+				else
+				{
+					hori--;
+				}
+				tw.push(currentNode, hori, vert + j, false);
+			}
+		}
 		int32_t quitScore = cm.minScore + cm.bandwidth;
 		int32_t previousQuitScore = pmeta.minScore + pmeta.bandwidth;
 		if ((tw.seqPos & 63) == 0 && tw.offset == 0)
@@ -865,32 +978,6 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			if (sp != tw.seqPos) tw.push(currentNode, 0, sp, false);
 			tw.push(second.node, second.offset, second.seqPos, second.nodeSwitch);
 			continue;
-		}
-		// inside the node (BVCommon.h:556-597)
-		{
-			uint32_t hori = tw.offset;
-			int32_t vert = tw.seqPos - j;
-			while (hori > 0 && vert > 0)
-			{
-				int32_t scoreHere = gc_value(cols[hori], vert);
-				int32_t verticalScore = gc_value(cols[hori], vert - 1);
-				int32_t diagonalScore = gc_value(cols[hori - 1], vert - 1);
-				bool eqc = gc_char_match(seq[vert + j], gc_node_base(g, currentNode, hori));
-				if (verticalScore == scoreHere - 1)
-				{
-					vert--;
-				}
-				else if (diagonalScore == scoreHere - (eqc ? 0 : 1))
-				{
-					hori--;
-					vert--;
-				}
-				else
-				{
-					hori--;
-				}
-				tw.push(currentNode, hori, vert + j, false);
-			}
 		}
 	}
 	// ---- slide left in row -1 (BVCommon.h:508-542); the do/while(false) runs once

@@ -445,7 +445,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	const bool traceOn = getenv("GC_TRACE") != nullptr;
 	auto wallNow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	double tPhase = wallNow();
-	auto phase = [&](const char* name) { if (traceOn) { double n = wallNow(); fprintf(stderr, "[gc] phase %-10s %.2f ms\n", name, n - tPhase); tPhase = n; } };
+	double devMs = 0; // wall time spent inside libgcgpu calls during the current phase
+	auto phase = [&](const char* name) { if (traceOn) { double n = wallNow(); fprintf(stderr, "[gc] phase %-10s %.2f ms (libgcgpu calls %.2f ms, host %.2f ms)\n", name, n - tPhase, devMs, n - tPhase - devMs); tPhase = n; devMs = 0; } };
 	// ---- encode reads (forward + reverse complement IUPAC masks)
 	Batch b;
 	b.fwdOff.resize(R); b.rcOff.resize(R);
@@ -485,15 +486,17 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	auto runExtend = [&]()
 	{
 		results.resize(items.size());
-		uint64_t cap = 0;
-		for (const auto& it : items) cap += 2 * (uint64_t)it.seq_len + 72;
 		if (tracePool.size() <= extendCalls) tracePool.emplace_back(new Pinned());
 		Pinned& buf = *tracePool[extendCalls];
-		buf.ensure(cap * 8);
 		uint64_t used = 0;
-		// the read codes are uploaded by the first call of the batch and stay resident (seq == NULL afterwards)
-		int rc = gcgpu_extend(ctx, extendCalls == 0 ? b.codes : nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), (uint64_t*)buf.p, cap, &used);
+		double tDev = wallNow();
+		// the read codes are uploaded by the first call of the batch and stay resident (seq == NULL afterwards);
+		// two-phase call: the page-locked trace buffer is sized from what the extensions really produced
+		int rc = gcgpu_extend(ctx, extendCalls == 0 ? b.codes : nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), nullptr, 0, &used);
 		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_extend");
+		buf.ensure((used + 1) * 8);
+		check(gcgpu_fetch_traces(ctx, (uint64_t*)buf.p, 0, used), "gcgpu_fetch_traces");
+		devMs += wallNow() - tDev;
 		traces = (const uint64_t*)buf.p;
 		extendCalls++;
 		stats.k1Items += items.size();
@@ -748,7 +751,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	}
 	std::vector<uint32_t> chain(std::max<size_t>(1, flatAnchors.size())), chainLen(R);
 	std::vector<int64_t> chainScore(R);
+	{ double tDev = wallNow();
 	check(gcgpu_chain(ctx, flatAnchors.data(), anchorOff.data(), (uint32_t)R, chain.data(), chainLen.data(), chainScore.data()), "gcgpu_chain");
+	devMs += wallNow() - tDev; }
 	stats.k2Reads += R; stats.k2Anchors += flatAnchors.size(); stats.k2Ms += gcgpu_last_kernel_ms(ctx);
 
 	phase("s3");
@@ -853,7 +858,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	uint64_t opsUsed = 0;
 	if (!nwItems.empty())
 	{
+		double tDev = wallNow();
 		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
+		devMs += wallNow() - tDev;
 		stats.k3Items += nwItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : nwRes) stats.k3Blocks += x.blocks;
 		if (traceOn)
@@ -898,7 +905,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		uint64_t cap = 0;
 		for (const auto& it : pathItems) cap += (uint64_t)it.query_len + it.target_len + 8;
 		ops.resize(cap);
+		double tDev = wallNow();
 		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), ops.data(), ops.size(), &opsUsed), "gcgpu_nw(path)");
+		devMs += wallNow() - tDev;
 		stats.k3Items += pathItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : pathRes) stats.k3Blocks += x.blocks;
 	}

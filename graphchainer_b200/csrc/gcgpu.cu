@@ -77,6 +77,7 @@ struct gcgpu_ctx
 	uint64_t seqResident = ~0ULL; // bytes of the K1 sequence buffer currently on the device
 	float lastKernelMs = 0;
 	uint64_t launches = 0;
+	uint64_t denseTraces = 0; // entries of the last gcgpu_extend call still in `compact`
 };
 
 // ------------------------------------------------------------------ K1 kernels
@@ -164,17 +165,16 @@ __global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const Gc
 	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, colsShared[threadIdx.x >> 5]);
 }
 
-// Experimental: G items per warp on lanes 0..G-1 (plain SIMT sharing of the instruction stream)
+// Long work items, SIMT form: one THREAD per item, the 32 items of a warp are neighbours in the
+// length-sorted list.  gc_k1_forward / gc_k1_backtrace are written so that the lanes meet at one
+// column loop per node visit (see gc_k1.cuh); with tens of thousands of items in a round this form
+// does 32 items per warp where the lock-step kernel above does one, at the price of a longer
+// latency of the single item -- the host picks it when a round has enough items to fill the GPU.
 __global__ void __launch_bounds__(128) gc_k1_long_simt_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint32_t G, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
 {
-	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	uint32_t lane = threadIdx.x & 31;
-	if (lane >= G) return;
-	// item k of the warp = descs[warp + k * numWarps]: the items of one warp have similar lengths (descs are sorted by length)
-	uint32_t numWarps = (n + G - 1) / G;
-	uint32_t t = warp + lane * numWarps;
-	if (warp >= numWarps || t >= n) return;
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
 	GcK1Desc d = descs[t];
 	GcWord cols[64];
 	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, cols);
@@ -392,14 +392,12 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (nLong)
 	{
-		static const int simtG = getenv("GCGPU_K1_SIMT") ? atoi(getenv("GCGPU_K1_SIMT")) : 0;
-		if (simtG > 0)
-		{
-			uint32_t numWarps = (nLong + simtG - 1) / simtG;
-			gc_k1_long_simt_kernel<<<(numWarps + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint32_t)simtG, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
-		}
+		// enough items to fill the GPU with one thread each: SIMT form; otherwise one warp per item (shortest latency)
+		static const uint32_t simtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)atoi(getenv("GCGPU_K1_SIMT_MIN")) : 3000u;
+		if (nLong >= simtMin)
+			gc_k1_long_simt_kernel<<<(nLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		else
-		gc_k1_long_kernel<<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			gc_k1_long_kernel<<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		ctx->launches++;
 	}
 	if (nShort)
@@ -490,6 +488,8 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k1 scan+gather", n);
 	*trace_used = used;
+	ctx->denseTraces = used;
+	if (!traces && trace_capacity == 0) used = 0; // two-phase use: the caller sizes its buffer from *trace_used and calls gcgpu_fetch_traces
 	if (used > trace_capacity) return setError(GCGPU_ERR_ARG, "gcgpu_extend: trace buffer too small, need " + std::to_string(used) + " entries");
 	if (used)
 	{
@@ -501,6 +501,17 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	#pragma omp parallel for schedule(static) reduction(||: internal)
 	for (uint32_t i = 0; i < n; i++) if (results[i].status == GCGPU_ITEM_INTERNAL) internal = true;
 	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_extend: a work item reached a state the reference asserts on (see per-item status)");
+	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t first, uint64_t count)
+{
+	if (!ctx || (!traces && count)) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_traces: null argument");
+	if (first + count > ctx->denseTraces) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_traces: range beyond the traces of the last gcgpu_extend call");
+	if (count == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	CUDA_TRY(cudaMemcpyAsync(traces, (const uint64_t*)ctx->compact.p + first, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 	return GCGPU_OK;
 }
 

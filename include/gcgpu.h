@@ -133,6 +133,11 @@ typedef struct gcgpu_ext_result
  * tells the required size).  All buffers are host memory.                                  */
 int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
                  gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used);
+/* Two-phase form for callers that cannot bound the trace volume in advance: call gcgpu_extend with
+ * traces == NULL and trace_capacity == 0 (results[] and *trace_used are filled, the traces stay on
+ * the device), size a buffer, then copy entries [first, first+count) of the dense trace array of
+ * that call.  Valid until the next gcgpu_extend on the same ctx.                              */
+int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t first, uint64_t count);
 
 
 /* ---- K3: global (NW) sequence alignment, Myers bit-vector ------------------------------

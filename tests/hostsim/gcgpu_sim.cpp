@@ -25,6 +25,7 @@ struct gcgpu_ctx
 	uint32_t numNodes;
 	uint64_t launches = 0;
 	std::vector<uint8_t> seqCopy;
+	std::vector<uint64_t> dense; // traces of the last gcgpu_extend call
 };
 static std::string g_err;
 
@@ -89,13 +90,23 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seqIn, uint64_t seqBy
 	uint64_t used = 0;
 	for (uint32_t i = 0; i < n; i++) { results[i].trace_offset = used; used += results[i].trace_len; if (results[i].status == GCGPU_ITEM_INTERNAL) internal = true; }
 	*trace_used = used;
+	ctx->dense.resize(used);
+	for (uint32_t i = 0; i < n; i++) if (results[i].trace_len) memcpy(ctx->dense.data() + results[i].trace_offset, tr[i].data(), results[i].trace_len * 8);
+	if (!traces && trace_capacity == 0) used = 0; // two-phase form: gcgpu_fetch_traces follows
 	if (used > trace_capacity) { g_err = "trace buffer too small"; return GCGPU_ERR_ARG; }
-	for (uint32_t i = 0; i < n; i++) if (results[i].trace_len) memcpy(traces + results[i].trace_offset, tr[i].data(), results[i].trace_len * 8);
+	if (used) memcpy(traces, ctx->dense.data(), used * 8);
 	ctx->launches++;
 	return internal ? GCGPU_ERR_INTERNAL : GCGPU_OK;
 }
 
 static uint8_t k3code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
+extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t first, uint64_t count)
+{
+	if (first + count > ctx->dense.size()) { g_err = "range beyond the traces of the last call"; return GCGPU_ERR_ARG; }
+	if (count) memcpy(traces, ctx->dense.data() + first, count * 8);
+	return GCGPU_OK;
+}
+
 extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, const gcgpu_nw_item* items, uint32_t n, gcgpu_nw_result* results, uint8_t* ops, uint64_t ops_capacity, uint64_t* ops_used)
 {
 	std::vector<uint8_t> codes(seq_bytes);
