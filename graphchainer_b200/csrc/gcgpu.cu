@@ -392,8 +392,9 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (nLong)
 	{
-		// enough items to fill the GPU with one thread each: SIMT form; otherwise one warp per item (shortest latency)
-		static const uint32_t simtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)atoi(getenv("GCGPU_K1_SIMT_MIN")) : 3000u;
+		// one warp per item (shortest latency) unless GCGPU_K1_SIMT_MIN asks for the thread-per-item form from that many
+		// items on (measured on B200, r01d: 9094 items = 188 ms in SIMT form vs 24 ms in lock-step form -- 2 warps/SM cannot hide the walk's latency)
+		static const uint32_t simtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)atoll(getenv("GCGPU_K1_SIMT_MIN")) : 0xFFFFFFFFu;
 		if (nLong >= simtMin)
 			gc_k1_long_simt_kernel<<<(nLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		else
