@@ -198,7 +198,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     aligner1.close()
-    kernel_ms = sum(s["k1_ms"] + s["k2_ms"] + s["k3_ms"] for s in steps)
+    kernel_ms = sum(s["s0_ms"] + s["k1_ms"] + s["k2_ms"] + s["k3_ms"] for s in steps)
     agg = torch.tensor([wall, kernel_ms / 1e3, float(batch.total_bp * args.steps)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = agg.clone()
@@ -214,6 +214,7 @@ def main():
     k1_ms = sum(s["k1_ms"] for s in steps) / k
     k3_ms = sum(s["k3_ms"] for s in steps) / k
     k2_ms = sum(s["k2_ms"] for s in steps) / k
+    s0_ms = sum(s["s0_ms"] for s in steps) / k
     k1_cols = sum(s["k1_columns"] for s in steps) / k
     k3_blocks = sum(s["k3_blocks"] for s in steps) / k
     peaks = {}
@@ -236,7 +237,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "note": "integer-pipe bound bit-parallel kernel; algorithmic bytes = work units x bytes/unit (DESIGN.md)",
                          "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
-            "kernels_ms_per_step": {"k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
+            "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
             "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp}
     if not args.no_cpu_baseline and os.path.exists(REFBIN):

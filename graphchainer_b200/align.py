@@ -21,7 +21,7 @@ class Options(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("k1_ms", C.c_double), ("k2_ms", C.c_double), ("k3_ms", C.c_double),
                 ("k1_items", C.c_uint64), ("k1_columns", C.c_uint64), ("k2_anchors", C.c_uint64), ("k3_items", C.c_uint64), ("k3_blocks", C.c_uint64),
-                ("launches", C.c_uint64), ("s1_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seeds_found", C.c_uint64), ("seeds_extended", C.c_uint64)]
+                ("launches", C.c_uint64), ("s1_rounds", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("seeds_found", C.c_uint64), ("seeds_extended", C.c_uint64), ("s0_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -68,6 +68,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	for (int w = 0; w < streams; w++)
 	{
 		int rc = gcgpu_create(h->opts.device, &gg, &gp, &h->workers[w].ctx);
+		if (rc == GCGPU_OK) rc = gcUploadMinimizerIndex(h->workers[w].ctx, g);
 		if (rc != GCGPU_OK) { std::string msg = gcgpu_last_error(); gcalign_close(h); return fail(rc, "gcalign_open: " + msg); }
 	}
 	h->pipe.colinearGap = h->opts.colinear_gap; h->pipe.colinearSplitLen = h->opts.colinear_split_len; h->pipe.colinearSplitGap = h->opts.colinear_split_gap;
@@ -156,7 +157,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 			}
 			std::lock_guard<std::mutex> lock(errMutex);
 			const GcPipelineStats& ps = pipeline.stats;
-			total.k1Ms += ps.k1Ms; total.k2Ms += ps.k2Ms; total.k3Ms += ps.k3Ms; total.k1Items += ps.k1Items; total.k1Columns += ps.k1Columns; total.k2Anchors += ps.k2Anchors;
+			total.s0Ms += ps.s0Ms; total.k1Ms += ps.k1Ms; total.k2Ms += ps.k2Ms; total.k3Ms += ps.k3Ms; total.k1Items += ps.k1Items; total.k1Columns += ps.k1Columns; total.k2Anchors += ps.k2Anchors;
 			total.k3Items += ps.k3Items; total.k3Blocks += ps.k3Blocks; total.s1Rounds += ps.s1Rounds; total.s1Wasted += ps.s1Wasted;
 		}
 		catch (const std::exception& e) { std::lock_guard<std::mutex> lock(errMutex); error = e.what(); }
@@ -194,7 +195,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	}
 	if (stats)
 	{
-		stats->k1_ms = total.k1Ms; stats->k2_ms = total.k2Ms; stats->k3_ms = total.k3Ms;
+		stats->s0_ms = total.s0Ms; stats->k1_ms = total.k1Ms; stats->k2_ms = total.k2Ms; stats->k3_ms = total.k3Ms;
 		stats->k1_items = total.k1Items; stats->k1_columns = total.k1Columns; stats->k2_anchors = total.k2Anchors;
 		stats->k3_items = total.k3Items; stats->k3_blocks = total.k3Blocks; stats->s1_rounds = total.s1Rounds;
 		for (size_t w = 0; w < W; w++) stats->launches += gcgpu_launch_count(h->workers[w].ctx) - launches0[w];

@@ -238,6 +238,7 @@ int main(int argc, char** argv)
 	{
 		gcgpu_ctx* ctx = nullptr;
 		if (gcgpu_create(params.firstDevice + d % params.gpus, &gg, &gp, &ctx) != GCGPU_OK) { std::cerr << "gcgpu_create(device " << params.firstDevice + d << ") failed: " << gcgpu_last_error() << std::endl; return 1; }
+		if (gcUploadMinimizerIndex(ctx, graph) != GCGPU_OK) { std::cerr << "gcgpu_set_minimizer_index failed: " << gcgpu_last_error() << std::endl; return 1; }
 		ctxs.push_back(ctx);
 	}
 
@@ -289,6 +290,7 @@ int main(int argc, char** argv)
 			// length-balanced: longest reads first inside a batch (the kernels sort their work items the same way)
 			pipeline.alignBatch(batch, results);
 			std::vector<std::string> gamRecords(batch.size()), jsonRecords(batch.size());
+			auto tGam0 = std::chrono::steady_clock::now();
 			#pragma omp parallel
 			{
 				gcout::GamEncoder enc;
@@ -301,6 +303,7 @@ int main(int argc, char** argv)
 						for (const GcAlnItem& item : results[r].alignments) { jsonRecords[r] += gcout::jsonLine(gcout::toAlignment(graph, batch[r].name, batch[r].sequence, item)); jsonRecords[r] += '\n'; }
 				}
 			}
+			if (getenv("GC_TRACE")) fprintf(stderr, "[gc] phase gam        %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tGam0).count());
 			std::lock_guard<std::mutex> lock(outMutex);
 			for (size_t r = 0; r < batch.size(); r++)
 			{
@@ -331,7 +334,7 @@ int main(int argc, char** argv)
 				if (params.outJson != "") jsonOut << jsonRecords[r];
 			}
 			total.k1Items += pipeline.stats.k1Items; total.k1Columns += pipeline.stats.k1Columns; total.k1Ms += pipeline.stats.k1Ms; total.k1Launches += pipeline.stats.k1Launches;
-			total.k2Ms += pipeline.stats.k2Ms; total.k2Anchors += pipeline.stats.k2Anchors; total.k3Ms += pipeline.stats.k3Ms; total.k3Items += pipeline.stats.k3Items; total.k3Blocks += pipeline.stats.k3Blocks;
+			total.s0Ms += pipeline.stats.s0Ms; total.k2Ms += pipeline.stats.k2Ms; total.k2Anchors += pipeline.stats.k2Anchors; total.k3Ms += pipeline.stats.k3Ms; total.k3Items += pipeline.stats.k3Items; total.k3Blocks += pipeline.stats.k3Blocks;
 			total.s1Rounds += pipeline.stats.s1Rounds;
 			pipeline.stats = GcPipelineStats();
 		}
@@ -357,7 +360,7 @@ int main(int argc, char** argv)
 	if (!params.quiet)
 	{
 		std::cout << "B200: align phase " << alignSec << " s, " << (statBp / alignSec) << " bp/s on " << params.gpus << " GPU(s); K1 " << total.k1Items << " extensions / " << total.k1Columns << " column steps / " << total.k1Ms << " ms, "
-			<< "K2 " << total.k2Anchors << " anchors / " << total.k2Ms << " ms, K3 " << total.k3Items << " alignments / " << total.k3Blocks << " block steps / " << total.k3Ms << " ms, S1 rounds " << total.s1Rounds << std::endl;
+			<< "S0 " << total.s0Ms << " ms, K2 " << total.k2Anchors << " anchors / " << total.k2Ms << " ms, K3 " << total.k3Items << " alignments / " << total.k3Blocks << " block steps / " << total.k3Ms << " ms, S1 rounds " << total.s1Rounds << std::endl;
 	}
 	return 0;
 }

@@ -36,21 +36,6 @@ struct GcHostGraph
 	std::vector<uint64_t> mzKmers, mzPositions;
 	std::vector<uint32_t> mzKmerStart;
 	uint64_t mzLength = 15, mzWindow = 20, mzMaxCount = 0, mzBuckets = 1;
-	// kmer -> index into mzKmers: open-addressing table (one cache line per probe; the reference's
-	// BBHash + kmerCheck lookup has the same "exact k-mer or nothing" semantics, MinimizerSeeder.cpp:504-519)
-	std::vector<uint64_t> mzTabKey; std::vector<uint32_t> mzTabVal; uint64_t mzTabMask = 0;
-	static uint64_t mzHash(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
-	// returns the index into mzKmers or -1
-	int64_t mzFind(uint64_t kmer) const
-	{
-		if (mzTabKey.empty()) return -1;
-		for (uint64_t h = mzHash(kmer) & mzTabMask; ; h = (h + 1) & mzTabMask)
-		{
-			uint32_t v = mzTabVal[h];
-			if (v == 0xFFFFFFFFu) return -1;
-			if (mzTabKey[h] == kmer) return (int64_t)v;
-		}
-	}
 	uint64_t bpSize = 0;
 
 	size_t numNodes() const { return nodeLength.size(); }
@@ -103,16 +88,6 @@ struct GcHostGraph
 		for (auto id : origIds) if (id > maxId) maxId = id;
 		origIndexOfId.assign((size_t)maxId + 1, -1);
 		for (size_t i = 0; i < origIds.size(); i++) origIndexOfId[origIds[i]] = (int32_t)i;
-		uint64_t cap = 16;
-		while (cap < mzKmers.size() * 2 + 2) cap <<= 1;
-		mzTabMask = cap - 1;
-		mzTabKey.assign(cap, 0); mzTabVal.assign(cap, 0xFFFFFFFFu);
-		for (size_t i = 0; i < mzKmers.size(); i++)
-		{
-			uint64_t h = mzHash(mzKmers[i]) & mzTabMask;
-			while (mzTabVal[h] != 0xFFFFFFFFu && mzTabKey[h] != mzKmers[i]) h = (h + 1) & mzTabMask;
-			mzTabKey[h] = mzKmers[i]; mzTabVal[h] = (uint32_t)i; // a repeated key keeps the LAST index, like the map assignment it replaces
-		}
 	}
 
 	GcGraphView view() const
@@ -129,17 +104,28 @@ struct GcHostGraph
 		return v;
 	}
 
-	// AlignmentGraph::GetUnitigNode (AlignmentGraph.cpp:832-848): split node holding `offset` of digraph node `nodeId`
+	// AlignmentGraph::GetUnitigNode (AlignmentGraph.cpp:832-848): split node holding `offset` of digraph node `nodeId`.
+	// The reference starts from a proportional guess and walks to the split node whose range contains the offset;
+	// that node is unique, so any starting guess gives the same answer -- offset/64 is exact for the 64-bp splits.
 	uint32_t unitigNode(int nodeId, size_t offset) const
 	{
 		int32_t oi = origIndexOfId[nodeId];
 		const uint32_t* nodes = origNodes.data() + origStart[oi];
 		size_t n = origStart[oi + 1] - origStart[oi];
-		size_t index = (size_t)(n * ((double)offset / (double)origSize[oi]));
+		size_t index = offset >> 6;
 		if (index >= n) index = n - 1;
 		while (index < n - 1 && (nodeOffset[nodes[index]] + nodeLength[nodes[index]] <= offset)) index++;
 		while (index > 0 && (nodeOffset[nodes[index]] > offset)) index--;
 		return nodes[index];
+	}
+	// consecutive trace entries mostly stay inside one split node: remember its range
+	struct UnitigCache { int nodeId = -1; uint32_t node = 0; size_t lo = 1, hi = 0; };
+	uint32_t unitigNode(int nodeId, size_t offset, UnitigCache& c) const
+	{
+		if (nodeId == c.nodeId && offset >= c.lo && offset < c.hi) return c.node;
+		uint32_t node = unitigNode(nodeId, offset);
+		c.nodeId = nodeId; c.node = node; c.lo = nodeOffset[node]; c.hi = c.lo + nodeLength[node];
+		return node;
 	}
 	// AlignmentGraph::GetReversePosition (AlignmentGraph.cpp:850-868)
 	std::pair<int, size_t> reversePosition(int nodeId, size_t offset) const
@@ -182,6 +168,11 @@ inline GcViterbiTables gcMakeViterbiTables()
 	t.initialFalse = log(0.2);
 	return t;
 }
+
+// read character -> code of the resident sequence buffer: the IUPAC mask, plus bit 4 on characters that match
+// in the DP but are not seeding bases (U/u: Common::ambiguousMatch maps them to T, MinimizerSeeder.cpp:24-43 does not)
+inline uint8_t gcEncodeBase(char c);
+inline uint8_t gcEncodeSeedBase(char c) { uint8_t m = gcEncodeBase(c); return (c == 'U' || c == 'u') ? (uint8_t)(m | 16) : m; }
 
 // read characters -> IUPAC bit masks (bit0 A, bit1 C, bit2 G, bit3 T), Common::ambiguousMatch (GraphAlignerCommon.h:219-296)
 inline uint8_t gcEncodeBase(char c)

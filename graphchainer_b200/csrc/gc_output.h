@@ -276,17 +276,26 @@ struct GamEncoder
 	}
 };
 
+// one gzip member per record; the deflate state (256 KB of tables) is kept per thread and level and only reset
 inline std::string gzipMemberLevel(const std::string& raw, int level)
 {
-	z_stream zs; std::memset(&zs, 0, sizeof(zs));
-	deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+	struct State { z_stream zs; int level = -100; bool live = false; ~State() { if (live) deflateEnd(&zs); } };
+	static thread_local State st;
+	if (!st.live || st.level != level)
+	{
+		if (st.live) deflateEnd(&st.zs);
+		std::memset(&st.zs, 0, sizeof(st.zs));
+		deflateInit2(&st.zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+		st.level = level; st.live = true;
+	}
+	else deflateReset(&st.zs);
+	z_stream& zs = st.zs;
 	std::string out;
 	out.resize(deflateBound(&zs, raw.size()) + 32);
 	zs.next_in = (Bytef*)raw.data(); zs.avail_in = (uInt)raw.size();
 	zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
 	deflate(&zs, Z_FINISH);
 	out.resize(out.size() - zs.avail_out);
-	deflateEnd(&zs);
 	return out;
 }
 

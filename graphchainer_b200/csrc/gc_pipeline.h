@@ -27,6 +27,15 @@
 #include <string>
 #include <unordered_set>
 #include <vector>
+#ifdef GC_PROF
+#include <x86intrin.h>
+static double g_prof[32]; static const char* g_profName[32];
+struct GcProfScope { int id; unsigned long long t0; GcProfScope(int id, const char* n) : id(id), t0(__rdtsc()) { g_profName[id] = n; } ~GcProfScope() { g_prof[id] += (double)(__rdtsc() - t0); } };
+#define GC_PROF_SCOPE(id, name) GcProfScope _prof##id(id, name)
+#else
+#define GC_PROF_SCOPE(id, name)
+#endif
+
 #include "../../include/gcgpu.h"
 #include "gc_host_graph.h"
 #include "gc_seeder.h"
@@ -108,11 +117,20 @@ struct GcPipelineStats
 	uint64_t k1Items = 0, k1Columns = 0, k1Launches = 0;
 	uint64_t k3Items = 0, k3Blocks = 0;
 	uint64_t k2Reads = 0, k2Anchors = 0;
-	double k1Ms = 0, k2Ms = 0, k3Ms = 0;
+	double k1Ms = 0, k2Ms = 0, k3Ms = 0, s0Ms = 0;
 	double hostSeedMs = 0, hostS1Ms = 0, hostS2Ms = 0, hostConnectMs = 0;
 	uint64_t s1Rounds = 0;
 	uint64_t s1Wasted = 0; // speculative S1 seed extensions whose result was discarded
 };
+
+// hands the reference's minimizer index (MinimizerSeeder.h:17-29 as flat arrays) to a libgcgpu context
+inline int gcUploadMinimizerIndex(gcgpu_ctx* ctx, const GcHostGraph& g)
+{
+	gcgpu_minimizer_index mi;
+	mi.k = (uint32_t)g.mzLength; mi.window = (uint32_t)g.mzWindow; mi.max_count = g.mzMaxCount;
+	mi.num_kmers = g.mzKmers.size(); mi.kmers = g.mzKmers.data(); mi.kmer_start = g.mzKmerStart.data();
+	return gcgpu_set_minimizer_index(ctx, &mi);
+}
 
 namespace gcpipe {
 
@@ -148,13 +166,13 @@ inline void packedNodePos(const GcHostGraph& g, const GcPackedAln& a, uint32_t k
 	}
 }
 // split node of merged-trace entry k (= GetUnitigNode(node, nodeOffset))
-inline size_t packedSplitNode(const GcHostGraph& g, const GcPackedAln& a, uint32_t k)
+inline size_t packedSplitNode(const GcHostGraph& g, const GcPackedAln& a, uint32_t k, GcHostGraph::UnitigCache& cache)
 {
 	uint32_t nb = a.bwdUsed();
 	if (k >= nb) return GCGPU_TRACE_NODE(a.fwd[a.fwdLen - 1 - (k - nb)]);
 	int node; size_t off;
 	packedNodePos(g, a, k, node, off);
-	return g.unitigNode(node, off);
+	return g.unitigNode(node, off, cache);
 }
 
 // exactAlignmentPart (GraphAligner.h:407-461): is the seed cell on the trace of `aln`?
@@ -218,9 +236,11 @@ inline std::string traceToSequence(const GcHostGraph& g, const GcAlnItem& aln)
 {
 	std::string ret;
 	size_t lastNode = 0, lastOffset = 0, lastLength = 0;
+	GcHostGraph::UnitigCache ucache;
+	ret.reserve(aln.trace.size() + 64);
 	for (size_t j = 0; j < aln.trace.size(); j++)
 	{
-		size_t node = g.unitigNode(aln.trace[j].node, aln.trace[j].nodeOffset);
+		size_t node = g.unitigNode(aln.trace[j].node, aln.trace[j].nodeOffset, ucache);
 		size_t nodeOffset = aln.trace[j].nodeOffset - g.nodeOffset[node];
 		if (j == 0)
 		{
@@ -335,7 +355,7 @@ private:
 		Pinned& operator=(const Pinned&) = delete;
 	};
 	std::vector<std::unique_ptr<Pinned>> tracePool;
-	Pinned codesBuf;
+	Pinned codesBuf, seedBuf;
 
 	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
 	void check(int rc, const char* what)
@@ -403,15 +423,20 @@ private:
 	{
 		uint32_t nb = a.bwdUsed(), n = a.size();
 		out.trace.resize(n);
+		uint32_t lastNode = 0xFFFFFFFFu; int lastRevId = 0; size_t lastRevEnd = 0; // reversePosition(id, o) = (id ^ 1, origSize - 1 - o): constant per kernel node up to the offset
 		for (uint32_t i = 0; i < nb; i++)
 		{
 			uint64_t e = a.bwd[i];
 			uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
 			GcTraceItem& it = out.trace[i];
 			it.seqPos = (a.seedPos - 1) - (int64_t)GCGPU_TRACE_SEQPOS(e);
-			auto reversePos = g.reversePosition(g.nodeIDs[node], (size_t)g.nodeOffset[node] + off);
-			it.node = reversePos.first;
-			it.nodeOffset = (uint32_t)reversePos.second;
+			if (node != lastNode)
+			{
+				auto reversePos = g.reversePosition(g.nodeIDs[node], (size_t)g.nodeOffset[node]);
+				lastNode = node; lastRevId = reversePos.first; lastRevEnd = reversePos.second;
+			}
+			it.node = lastRevId;
+			it.nodeOffset = (uint32_t)(lastRevEnd - off);
 			it.sequenceCharacter = sequence[it.seqPos];
 			it.graphCharacter = gcpipe::complementChar(g.nodeChar(node, off));
 			it.nodeSwitch = (i + 1 < a.bwdLen) ? GCGPU_TRACE_SWITCH(a.bwd[i + 1]) != 0 : false;
@@ -463,20 +488,39 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			size_t L = s.size();
 			for (size_t i = 0; i < L; i++)
 			{
-				uint8_t m = gcEncodeBase(s[i]);
+				uint8_t m = gcEncodeSeedBase(s[i]);
 				b.codes[b.fwdOff[r] + i] = m;
 				b.codes[b.rcOff[r] + (L - 1 - i)] = gcpipe::complementMask(m);
 			}
 		}
 	}
-	// ---- S0: seeds (the reference calls getSeeds + OrderSeeds twice per read with identical results)
+	// ---- S0: seeds (the reference calls getSeeds + OrderSeeds twice per read with identical results).
+	// k-mer walk + index probes on the device (gcgpu_seed uploads the read codes, which stay resident for K1);
+	// the count sort, density cut, seed-hit expansion and clustering per read on the host
 	std::vector<std::vector<GcSeedHit>> seedsOrdered(R);
-	#pragma omp parallel for schedule(dynamic, 4)
-	for (size_t r = 0; r < R; r++)
 	{
-		seedsOrdered[r] = gcseed::getSeeds(g, reads[r].sequence, params.minimizerSeedDensity);
-		out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
-		if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]);
+		std::vector<gcgpu_seed_read> sr(R);
+		for (size_t r = 0; r < R; r++) { sr[r].seq_offset = b.fwdOff[r]; sr[r].seq_len = (int32_t)reads[r].sequence.size(); sr[r].reserved = 0; }
+		std::vector<uint64_t> matchOff(R + 1, 0);
+		uint64_t used = 0;
+		double tDev = wallNow();
+		check(gcgpu_seed(ctx, b.codes, b.codesBytes, sr.data(), (uint32_t)R, matchOff.data(), nullptr, 0, &used), "gcgpu_seed");
+		seedBuf.ensure((used + 1) * sizeof(gcgpu_seed_match));
+		check(gcgpu_fetch_seed_matches(ctx, (gcgpu_seed_match*)seedBuf.p, 0, used), "gcgpu_fetch_seed_matches");
+		devMs += wallNow() - tDev;
+		stats.s0Ms += gcgpu_last_kernel_ms(ctx);
+		const gcgpu_seed_match* matches = (const gcgpu_seed_match*)seedBuf.p;
+		#pragma omp parallel for schedule(dynamic, 4)
+		for (size_t r = 0; r < R; r++)
+		{
+			std::vector<std::tuple<size_t, size_t, size_t, size_t>> matchIndices;
+			matchIndices.reserve(matchOff[r + 1] - matchOff[r]);
+			for (uint64_t i = matchOff[r]; i < matchOff[r + 1]; i++) matchIndices.emplace_back((size_t)matches[i].pos, (size_t)0, (size_t)matches[i].start, (size_t)matches[i].count);
+			{ GC_PROF_SCOPE(0, "seed.seedsFromMatches"); seedsOrdered[r] = gcseed::seedsFromMatches(g, matchIndices, reads[r].sequence.size(), params.minimizerSeedDensity); }
+			out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
+			GC_PROF_SCOPE(1, "seed.orderSeeds");
+			if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]);
+		}
 	}
 	phase("seed");
 	std::vector<gcgpu_ext_item> items;
@@ -490,9 +534,9 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		Pinned& buf = *tracePool[extendCalls];
 		uint64_t used = 0;
 		double tDev = wallNow();
-		// the read codes are uploaded by the first call of the batch and stay resident (seq == NULL afterwards);
+		// the read codes were uploaded by gcgpu_seed and stay resident (seq == NULL);
 		// two-phase call: the page-locked trace buffer is sized from what the extensions really produced
-		int rc = gcgpu_extend(ctx, extendCalls == 0 ? b.codes : nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), nullptr, 0, &used);
+		int rc = gcgpu_extend(ctx, nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), nullptr, 0, &used);
 		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_extend");
 		buf.ensure((used + 1) * 8);
 		check(gcgpu_fetch_traces(ctx, (uint64_t*)buf.p, 0, used), "gcgpu_fetch_traces");
@@ -539,6 +583,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		{
 			S1State& st = s1[r];
 			if (st.done) continue;
+			GC_PROF_SCOPE(2, "s1.collect");
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
 			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : params.s1LaterRoundSeeds;
 			st.cands.clear();
@@ -575,6 +620,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		for (size_t k = 0; k < active.size(); k++)
 		{
 			size_t r = active[k];
+			GC_PROF_SCOPE(3, "s1.consume");
 			S1State& st = s1[r];
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
 			size_t next = 0; // next unconsumed speculative result
@@ -623,6 +669,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	#pragma omp parallel for schedule(dynamic, 4)
 	for (size_t r = 0; r < R; r++)
 	{
+		GC_PROF_SCOPE(4, "s1.select+materialize+pathseq");
 		longSeedsExtended[r] = s1[r].seedsExtended;
 		if (out[r].dropped) { s1[r].alns.clear(); continue; }
 		if (!s1[r].alns.empty())
@@ -650,6 +697,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	for (size_t r = 0; r < R; r++)
 	{
 		if (seedsOrdered[r].empty()) continue;
+		GC_PROF_SCOPE(5, "s2.items");
 		std::vector<GcSeedHit>& seeds = seedsByPos[r];
 		seeds = seedsOrdered[r];
 		std::sort(seeds.begin(), seeds.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seqPos < right.seqPos; });
@@ -681,7 +729,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		if (!localItems[r].empty()) memcpy(items.data() + itemBase[r], localItems[r].data(), localItems[r].size() * sizeof(gcgpu_ext_item));
 		std::vector<gcgpu_ext_item>().swap(localItems[r]);
 	}
-	extendCalls = extendCalls ? 1 : 0; // S1's trace buffers are free again (codes stay resident after the first call)
+	extendCalls = 0; // S1's trace buffers are free again
 	if (!items.empty()) runExtend();
 	// in-order filter + anchors
 	struct AnchorRec { std::vector<size_t> path; size_t x, y; size_t firstNode, firstOffset, lastNode, lastOffset; };
@@ -691,6 +739,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	for (size_t r = 0; r < R; r++)
 	{
 		const std::string& sequence = reads[r].sequence;
+		GC_PROF_SCOPE(6, "s2.filter+anchors");
 		std::vector<GcPackedAln> kept;
 		for (const Frag& f : frags[r])
 		{
@@ -716,13 +765,15 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			}
 			if (out[r].dropped) break;
 			lastFragExtended[r] = s2SeedsExtended[r] - before;
+			GC_PROF_SCOPE(7, "s2.anchors");
 			for (const GcPackedAln& alignment : kept)
 			{
 				AnchorRec a; a.x = f.l; a.y = f.l + len - 1;
 				uint32_t n = alignment.size();
+				GcHostGraph::UnitigCache ucache;
 				for (uint32_t k = 0; k < n; k++)
 				{
-					size_t node = gcpipe::packedSplitNode(g, alignment, k);
+					size_t node = gcpipe::packedSplitNode(g, alignment, k, ucache);
 					if (a.path.empty() || node != a.path.back()) a.path.push_back(node);
 				}
 				int n0, n1; size_t o0, o1;
@@ -757,20 +808,45 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	stats.k2Reads += R; stats.k2Anchors += flatAnchors.size(); stats.k2Ms += gcgpu_last_kernel_ms(ctx);
 
 	phase("s3");
-	// ---- S4: chain -> node path (Aligner.cpp:738-831)
-	std::vector<std::vector<gcpipe::MatrixPos>> longest(R);
+	// ---- S4: chain -> node path (Aligner.cpp:738-831).  A candidate segment is kept as (node path, first offset,
+	// last offset); its per-base position list (pathToTrace) is only materialised for the reads where the chain wins --
+	// here only its LENGTH (the `longest` comparison, `<` => first wins ties) and its base string are needed.
+	struct PathSeg { std::vector<size_t> path; size_t firstOffset = 0, lastOffset = 0, size = 0; };
+	std::vector<PathSeg> longest(R);
 	std::vector<std::string> pathSeq(R);
+	// number of positions pathToTrace emits (same per-node tests by VALUE as Aligner.cpp:409-424)
+	auto pathTraceSize = [&](const std::vector<size_t>& path, size_t firstNodeOffset, size_t lastNodeOffset)
+	{
+		size_t total = 0;
+		for (size_t node : path)
+		{
+			size_t S = 0, L = g.nodeLength[node];
+			if (node == path[0]) S = firstNodeOffset;
+			else if (node == path.back()) L = lastNodeOffset + 1;
+			if (L > S) total += L - S;
+		}
+		return total;
+	};
 	#pragma omp parallel
 	{
 		gcpipe::ChainPathScratch scratch;
+		// the reference's std::unordered_set<size_t> nodes, as an epoch-stamped array that lives as long as the thread
+		static thread_local std::vector<uint32_t> inPath;
+		static thread_local uint32_t epoch = 0;
+		if (inPath.size() != g.numNodes() || epoch > 0xF0000000u) { inPath.assign(g.numNodes(), 0); epoch = 0; }
 		#pragma omp for schedule(dynamic, 4)
 		for (size_t r = 0; r < R; r++)
 		{
 			const std::vector<AnchorRec>& A = anchors[r];
-			std::vector<gcpipe::MatrixPos> tmp;
+			GC_PROF_SCOPE(8, "s4.all");
 			std::vector<size_t> pos_path;
-			std::unordered_set<size_t> nodes;
 			size_t firstNodeOffset = 0, lastNodeOffset = 0;
+			epoch++;
+			auto closeSegment = [&]()
+			{
+				size_t sz = pathTraceSize(pos_path, firstNodeOffset, lastNodeOffset);
+				if (longest[r].size < sz) { longest[r].path = pos_path; longest[r].firstOffset = firstNodeOffset; longest[r].lastOffset = lastNodeOffset; longest[r].size = sz; }
+			};
 			for (uint32_t ci = 0; ci < chainLen[r]; ci++)
 			{
 				const AnchorRec& anchor = A[chain[anchorOff[r] + ci]];
@@ -779,13 +855,13 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 					pos_path = anchor.path;
 					firstNodeOffset = anchor.firstOffset;
 					lastNodeOffset = anchor.lastOffset;
-					for (size_t j : pos_path) nodes.insert(j);
+					for (size_t j : pos_path) inPath[j] = epoch;
 				}
 				else
 				{
 					bool gap = anchor.path[0] == pos_path.back() && params.colinearGap != -1 && (long long)anchor.firstOffset - (long long)lastNodeOffset > params.colinearGap + 1;
 					std::vector<size_t> path;
-					if (!nodes.count(anchor.path[0]) && pos_path.back() != anchor.firstNode)
+					if (inPath[anchor.path[0]] != epoch && pos_path.back() != anchor.firstNode)
 					{
 						long long gapLimit = params.colinearGap;
 						if (gapLimit != -1) gapLimit -= (long long)anchor.firstOffset + (long long)((long long)g.nodeLength[pos_path.back()] - (long long)lastNodeOffset - 1);
@@ -794,25 +870,28 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 					}
 					if (gap)
 					{
-						tmp = gcpipe::pathToTrace(g, pos_path, firstNodeOffset, lastNodeOffset);
-						if (longest[r].size() < tmp.size()) longest[r].swap(tmp);
-						nodes.clear();
+						closeSegment();
+						epoch++; // nodes.clear()
 						pos_path.clear();
 						firstNodeOffset = anchor.firstOffset;
 					}
 					else
-						for (size_t j : path) if (!nodes.count(j)) { nodes.insert(j); pos_path.push_back(j); }
-					for (size_t j : anchor.path) if (!nodes.count(j)) { nodes.insert(j); pos_path.push_back(j); }
+						for (size_t j : path) if (inPath[j] != epoch) { inPath[j] = epoch; pos_path.push_back(j); }
+					for (size_t j : anchor.path) if (inPath[j] != epoch) { inPath[j] = epoch; pos_path.push_back(j); }
 					lastNodeOffset = anchor.lastOffset;
 				}
 			}
-			if (!pos_path.empty())
+			if (!pos_path.empty()) closeSegment();
+			GC_PROF_SCOPE(9, "s4.pathSeq");
+			const PathSeg& lg = longest[r];
+			pathSeq[r].reserve(lg.size);
+			for (size_t node : lg.path)
 			{
-				tmp = gcpipe::pathToTrace(g, pos_path, firstNodeOffset, lastNodeOffset);
-				if (longest[r].size() < tmp.size()) longest[r].swap(tmp);
+				size_t S = 0, L = g.nodeLength[node];
+				if (node == lg.path[0]) S = lg.firstOffset;
+				else if (node == lg.path.back()) L = lg.lastOffset + 1;
+				for (size_t o = S; o < L; o++) pathSeq[r].push_back(g.nodeChar((uint32_t)node, (uint32_t)o));
 			}
-			pathSeq[r].reserve(longest[r].size());
-			for (const auto& p : longest[r]) pathSeq[r].push_back(g.nodeChar((uint32_t)p.node, (uint32_t)p.nodeOffset));
 		}
 	}
 
@@ -883,12 +962,12 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		GcReadResult& res = out[r];
 		res.anchors = anchors[r].size();
 		res.chained = chainLen[r];
-		res.pathBp = longest[r].size();
+		res.pathBp = longest[r].size;
 		res.hasLong = gaItem[r] >= 0;
 		if (gaItem[r] >= 0) res.longEditDistance = (size_t)nwRes[gaItem[r]].distance;
 		if (clcItem[r] >= 0) res.clcScore = (size_t)nwRes[clcItem[r]].distance;
 		res.seedsExtended = 0;
-		bool haveClc = clcItem[r] >= 0 && !longest[r].empty();
+		bool haveClc = clcItem[r] >= 0 && longest[r].size != 0;
 		bool better = haveClc && (longAlns[r].empty() || res.longEditDistance > res.clcScore);
 		res.usedChain = better;
 		if (better)
@@ -918,7 +997,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	{
 		size_t r = pathRead[k];
 		const std::string& sequence = reads[r].sequence;
-		const std::vector<gcpipe::MatrixPos>& lg = longest[r];
+		const std::vector<gcpipe::MatrixPos> lg = gcpipe::pathToTrace(g, longest[r].path, longest[r].firstOffset, longest[r].lastOffset);
 		const uint8_t* op = ops.data() + pathRes[k].ops_offset;
 		size_t n = pathRes[k].ops_len;
 		GcAlnItem item;
@@ -969,5 +1048,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		std::sort(res.alignments.begin(), res.alignments.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
 	}
 	phase("final");
+#ifdef GC_PROF
+	if (traceOn) for (int i = 0; i < 32; i++) if (g_profName[i]) fprintf(stderr, "[prof] %-32s %.2f ms\n", g_profName[i], g_prof[i] / 2.0e6);
+#endif
 	if (traceOn) fprintf(stderr, "[gc] batch reads=%zu s1_rounds=%llu s1_wasted=%llu\n", R, (unsigned long long)stats.s1Rounds, (unsigned long long)stats.s1Wasted);
 }

@@ -2,9 +2,11 @@
 //   MinimizerSeeder::getSeeds / iterateKmers / addMinimizers / matchToSeedHit
 //       (src/MinimizerSeeder.cpp:60-102, 494-555)
 //   GraphAligner::orderSeedsByChaining  (src/GraphAligner.h:233-295)
-// These run on the host (they are cheap, sequential per read and full of libstdc++
-// std::sort calls with partial keys whose permutation must match the reference's);
-// the same std::sort calls on the same element order are used here.
+// The k-mer walk and the index probes (iterateKmers + addMinimizers) run on the device
+// (gcgpu_seed, gc_seed.cuh); what stays here is sequential per read and full of libstdc++
+// std::sort calls with partial keys whose permutation must match the reference's:
+// the same std::sort calls on the same element order are used.  iterateKmers is kept as the
+// restatement the device form is tested against (tests/hostsim/seed_ref.h).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -14,6 +16,9 @@
 #include <unordered_map>
 #include <vector>
 #include "gc_host_graph.h"
+#ifndef GC_PROF_SCOPE
+#define GC_PROF_SCOPE(id, name)
+#endif
 
 // src/GraphAlignerWrapper.h:11-37
 struct GcSeedHit
@@ -83,24 +88,14 @@ void iterateKmers(const std::string& str, size_t kmerLength, size_t windowSize, 
 	}
 }
 
-// MinimizerSeeder::getSeeds (MinimizerSeeder.cpp:522-544) + addMinimizers (:494-520)
-inline std::vector<GcSeedHit> getSeeds(const GcHostGraph& g, const std::string& sequence, double density)
+// the second half of MinimizerSeeder::getSeeds (MinimizerSeeder.cpp:533-544) + matchToSeedHit (:546-555):
+// sort the matches by count, apply the density cut, expand every kept k-mer into its positions.
+// matchIndices = (k-mer END position, 0, first position index, count) in ascending position order.
+inline std::vector<GcSeedHit> seedsFromMatches(const GcHostGraph& g, std::vector<std::tuple<size_t, size_t, size_t, size_t>>& matchIndices, size_t sequenceSize, double density)
 {
-	std::vector<std::tuple<size_t, size_t, size_t, size_t>> matchIndices;
 	const size_t maxCount = g.mzMaxCount;
-	iterateKmers(sequence, g.mzLength, g.mzWindow, [&](size_t pos, size_t kmer)
-	{
-		int64_t found = g.mzFind(kmer);
-		if (found < 0) return;
-		size_t index = (size_t)found;
-		size_t start = g.mzKmerStart[index];
-		size_t end = g.mzKmerStart[index + 1];
-		size_t count = end - start;
-		if (count >= maxCount) return;
-		matchIndices.emplace_back(pos, (size_t)0, start, count);
-	});
 	std::vector<GcSeedHit> result;
-	size_t maxHits = (size_t)(sequence.size() * density);
+	size_t maxHits = (size_t)(sequenceSize * density);
 	if (density == -1) maxHits = std::numeric_limits<size_t>::max();
 	std::sort(matchIndices.begin(), matchIndices.end(), [](const std::tuple<size_t, size_t, size_t, size_t>& left, const std::tuple<size_t, size_t, size_t, size_t>& right)
 	{
@@ -137,6 +132,7 @@ inline std::vector<GcSeedHit> getSeeds(const GcHostGraph& g, const std::string& 
 	}
 	return result;
 }
+
 
 // GraphAligner::orderSeedsByChaining (GraphAligner.h:233-295)
 inline void orderSeeds(const GcHostGraph& g, std::vector<GcSeedHit>& seedHits)

@@ -14,6 +14,7 @@
 #include "gc_k2.cuh"
 #include "gc_k3.cuh"
 #include "gc_k3w.cuh"
+#include "gc_seed.cuh"
 #include "gc_host_graph.h"
 
 #define GCGPU_VERSION 1
@@ -74,6 +75,12 @@ struct gcgpu_ctx
 	bool haveMpc = false;
 	GcMpcView mpc;
 	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc;
+	// minimizer index (S0)
+	GcMzSlot* d_mzSlots = nullptr;
+	GcMzView mz;
+	bool haveMz = false;
+	DevBuf seedBuf, seedMatches;
+	uint64_t denseMatches = 0;
 	uint64_t seqResident = ~0ULL; // bytes of the K1 sequence buffer currently on the device
 	float lastKernelMs = 0;
 	uint64_t launches = 0;
@@ -220,6 +227,7 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	cudaFree(ctx->d_nodeLength); cudaFree(ctx->d_nodeSeq); cudaFree(ctx->d_inStart); cudaFree(ctx->d_inNbr); cudaFree(ctx->d_outStart); cudaFree(ctx->d_outNbr);
 	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt);
 	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
+	cudaFree(ctx->d_mzSlots); ctx->seedBuf.release(); ctx->seedMatches.release();
 	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
 	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -512,6 +520,136 @@ extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t fir
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	CUDA_TRY(cudaMemcpyAsync(traces, (const uint64_t*)ctx->compact.p + first, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	return GCGPU_OK;
+}
+
+// ------------------------------------------------------------------ S0 kernels
+// One block per read; the block walks the read in tiles of blockDim positions, one position per
+// thread (gc_seed.cuh).  WRITE == false counts the read's matches, WRITE == true writes them in
+// position order at offs[read] (ballot rank inside the warp + running prefix over warps and tiles).
+// HBM-bound gather: 16 code bytes per position from L1 + one 16-byte table slot per emitted k-mer.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) gc_seed_kernel(GcMzView mz, const uint8_t* __restrict__ seq, const gcgpu_seed_read* __restrict__ reads, uint32_t n,
+	uint64_t* __restrict__ counts, const uint64_t* __restrict__ offs, gcgpu_seed_match* __restrict__ out)
+{
+	__shared__ uint32_t warpTotal[8];
+	uint32_t r = blockIdx.x;
+	if (r >= n) return;
+	gcgpu_seed_read rd = reads[r];
+	const uint8_t* codes = seq + rd.seq_offset;
+	uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t running = 0;
+	uint64_t base = WRITE ? offs[r] : 0;
+	for (int32_t tile = 0; tile < rd.seq_len; tile += (int32_t)blockDim.x)
+	{
+		int32_t i = tile + (int32_t)threadIdx.x;
+		uint32_t start = 0, count = 0;
+		bool hit = gc_seed_position(mz, codes, rd.seq_len, i, start, count);
+		uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+		if (lane == 0) warpTotal[warp] = __popc(m);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+		for (uint32_t w = 0; w < (blockDim.x >> 5); w++) { uint32_t t = warpTotal[w]; if (w < warp) before += t; total += t; }
+		if (WRITE && hit)
+		{
+			gcgpu_seed_match o; o.pos = (uint32_t)i; o.start = start; o.count = count;
+			out[base + running + before + __popc(m & ((1u << lane) - 1))] = o;
+		}
+		running += total;
+		__syncthreads();
+	}
+	if (!WRITE && threadIdx.x == 0) { counts[r] = running; if (r == 0) counts[n] = 0; }
+}
+
+extern "C" int gcgpu_set_minimizer_index(gcgpu_ctx* ctx, const gcgpu_minimizer_index* idx)
+{
+	if (!ctx || !idx || (idx->num_kmers && (!idx->kmers || !idx->kmer_start))) return setError(GCGPU_ERR_ARG, "gcgpu_set_minimizer_index: null argument");
+	if (idx->k < 1 || idx->k > 31 || idx->window < idx->k) return setError(GCGPU_ERR_ARG, "gcgpu_set_minimizer_index: need 1 <= k <= 31 and window >= k");
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	uint64_t cap = 16;
+	while (cap < idx->num_kmers * 2 + 2) cap <<= 1;
+	std::vector<GcMzSlot> slots(cap);
+	for (auto& s : slots) { s.key = 0; s.start = 0; s.count = 0xFFFFFFFFu; }
+	for (uint64_t i = 0; i < idx->num_kmers; i++)
+	{
+		uint64_t h = gc_mz_hash(idx->kmers[i]) & (cap - 1);
+		while (slots[h].count != 0xFFFFFFFFu && slots[h].key != idx->kmers[i]) h = (h + 1) & (cap - 1);
+		slots[h].key = idx->kmers[i]; slots[h].start = idx->kmer_start[i]; slots[h].count = idx->kmer_start[i + 1] - idx->kmer_start[i];
+	}
+	if (ctx->d_mzSlots) { cudaFree(ctx->d_mzSlots); ctx->d_mzSlots = nullptr; }
+	CUDA_TRY(uploadArray(slots.data(), slots.size(), &ctx->d_mzSlots));
+	ctx->mz.slots = ctx->d_mzSlots; ctx->mz.mask = cap - 1; ctx->mz.k = idx->k; ctx->mz.realWindow = idx->window - idx->k + 1; ctx->mz.maxCount = idx->max_count;
+	ctx->haveMz = true;
+	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_seed_read* reads, uint32_t n,
+	uint64_t* match_offsets, gcgpu_seed_match* matches, uint64_t capacity, uint64_t* used_out)
+{
+	if (!ctx || (!reads && n) || !match_offsets || !used_out) return setError(GCGPU_ERR_ARG, "gcgpu_seed: null argument");
+	if (!ctx->haveMz) return setError(GCGPU_ERR_ARG, "gcgpu_seed: no minimizer index (gcgpu_set_minimizer_index)");
+	*used_out = 0;
+	ctx->lastKernelMs = 0;
+	ctx->denseMatches = 0;
+	match_offsets[0] = 0;
+	if (n == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	for (uint32_t i = 0; i < n; i++)
+		if (reads[i].seq_len < 0 || reads[i].seq_offset + (uint64_t)reads[i].seq_len > seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_seed: read " + std::to_string(i) + " out of range");
+	if (seq)
+	{
+		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
+		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->seqResident = seq_bytes;
+	}
+	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_seed: seq == NULL but no sequence buffer of this size is resident");
+	// device arrays: reads | counts[n+1] | offsets[n+1] | scan scratch
+	size_t offReads = 0, offCounts = alignUp((size_t)n * sizeof(gcgpu_seed_read), 128), offOffs = alignUp(offCounts + ((size_t)n + 1) * 8, 128), offScan = alignUp(offOffs + ((size_t)n + 1) * 8, 128);
+	size_t scanBytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)n + 1, ctx->stream);
+	CUDA_TRY(ctx->seedBuf.ensure(offScan + scanBytes + 16));
+	uint8_t* B = (uint8_t*)ctx->seedBuf.p;
+	gcgpu_seed_read* dReads = (gcgpu_seed_read*)(B + offReads); uint64_t* dCounts = (uint64_t*)(B + offCounts); uint64_t* dOffs = (uint64_t*)(B + offOffs);
+	CUDA_TRY(cudaMemcpyAsync(dReads, reads, (size_t)n * sizeof(gcgpu_seed_read), cudaMemcpyHostToDevice, ctx->stream));
+	float ms = 0;
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	gc_seed_kernel<false><<<n, 256, 0, ctx->stream>>>(ctx->mz, (const uint8_t*)ctx->seqBuf.p, dReads, n, dCounts, nullptr, nullptr);
+	cub::DeviceScan::ExclusiveSum(B + offScan, scanBytes, dCounts, dOffs, (int)n + 1, ctx->stream);
+	ctx->launches += 2;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(match_offsets, dOffs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	uint64_t used = match_offsets[n];
+	CUDA_TRY(ctx->seedMatches.ensure(used * sizeof(gcgpu_seed_match) + 16));
+	gc_seed_kernel<true><<<n, 256, 0, ctx->stream>>>(ctx->mz, (const uint8_t*)ctx->seqBuf.p, dReads, n, nullptr, dOffs, (gcgpu_seed_match*)ctx->seedMatches.p);
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs = ms;
+	GC_TRACE_MS("s0 seed lookups", n);
+	ctx->denseMatches = used;
+	*used_out = used;
+	if (!matches && capacity == 0) return GCGPU_OK;
+	if (used > capacity) return setError(GCGPU_ERR_ARG, "gcgpu_seed: match buffer too small, need " + std::to_string(used) + " entries");
+	if (used)
+	{
+		if (!matches) return setError(GCGPU_ERR_ARG, "gcgpu_seed: null match buffer");
+		CUDA_TRY(cudaMemcpyAsync(matches, ctx->seedMatches.p, used * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	}
+	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_fetch_seed_matches(gcgpu_ctx* ctx, gcgpu_seed_match* matches, uint64_t first, uint64_t count)
+{
+	if (!ctx || (!matches && count)) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_seed_matches: null argument");
+	if (first + count > ctx->denseMatches) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_seed_matches: range beyond the matches of the last gcgpu_seed call");
+	if (count == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	CUDA_TRY(cudaMemcpyAsync(matches, (const gcgpu_seed_match*)ctx->seedMatches.p + first, count * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 	return GCGPU_OK;
 }

@@ -58,6 +58,7 @@ typedef struct gcalign_stats
 	uint64_t s1_rounds;
 	uint64_t h2d_bytes, d2h_bytes;       /* not tracked yet: 0                             */
 	uint64_t seeds_found, seeds_extended;
+	double s0_ms;                        /* seeding lookups (gcgpu_seed)                   */
 } gcalign_stats;
 
 void gcalign_default_options(gcalign_options* opts);

@@ -140,6 +140,51 @@ int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const g
 int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t first, uint64_t count);
 
 
+/* ---- S0: minimizer seeding lookups ------------------------------------------------------
+ * Replaces, for a batch of reads, the k-mer walk and index probes of
+ *   MinimizerSeeder::getSeeds -> iterateKmers -> addMinimizers
+ * (src/MinimizerSeeder.cpp:522-544, 60-102, 494-520): for every read the list of
+ * (k-mer END position, first index into the positions array, number of positions) of the
+ * looked-up k-mers that are in the index with fewer than max_count positions, in ascending
+ * position order -- the `matchIndices` vector before its sort by count.  The sort, the density cut
+ * and matchToSeedHit (:533-555) stay with the caller (their std::sort tie order is libstdc++'s).
+ * The index is the reference's: kmers[i] occurs at positions[kmer_start[i] .. kmer_start[i+1])
+ * (the union over the MinimizerSeeder buckets; a k-mer lives in exactly one bucket).         */
+typedef struct gcgpu_minimizer_index
+{
+	uint32_t k;                 /* minimizer length (15), <= 31            */
+	uint32_t window;            /* window size (20); realWindow = window-k+1 */
+	uint64_t max_count;         /* MinimizerSeeder::maxCount               */
+	uint64_t num_kmers;
+	const uint64_t* kmers;      /* [num_kmers]                             */
+	const uint32_t* kmer_start; /* [num_kmers + 1]                         */
+} gcgpu_minimizer_index;
+
+typedef struct gcgpu_seed_read
+{
+	uint64_t seq_offset;        /* forward codes of the read inside `seq`  */
+	int32_t seq_len;
+	uint32_t reserved;
+} gcgpu_seed_read;
+
+typedef struct gcgpu_seed_match
+{
+	uint32_t pos;               /* k-mer END position in the read          */
+	uint32_t start;             /* kmer_start[index]                       */
+	uint32_t count;             /* kmer_start[index+1] - kmer_start[index] */
+} gcgpu_seed_match;
+
+int gcgpu_set_minimizer_index(gcgpu_ctx* ctx, const gcgpu_minimizer_index* index);
+/* `seq` = the IUPAC-mask codes of gcgpu_extend, with bit 4 set on bases that are not one of
+ * ACGTacgt for seeding although they match in the DP (U/u); the buffer stays resident for the
+ * following gcgpu_extend calls (pass seq == NULL there).  match_offsets[n+1]; matches of read r are
+ * [match_offsets[r], match_offsets[r+1]).  Two-phase use like gcgpu_extend: matches == NULL and
+ * capacity == 0 leaves them on the device for gcgpu_fetch_seed_matches.                        */
+int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_seed_read* reads, uint32_t n,
+               uint64_t* match_offsets, gcgpu_seed_match* matches, uint64_t capacity, uint64_t* used);
+int gcgpu_fetch_seed_matches(gcgpu_ctx* ctx, gcgpu_seed_match* matches, uint64_t first, uint64_t count);
+
+
 /* ---- K3: global (NW) sequence alignment, Myers bit-vector ------------------------------
  * One item replaces one call of
  *   edlibAlign(query, qlen, target, tlen, edlibNewAlignConfig(-1, EDLIB_MODE_NW, task, NULL, 0))

@@ -15,6 +15,7 @@
 #include "../../graphchainer_b200/csrc/gc_k1.cuh"
 #include "../../graphchainer_b200/csrc/gc_k2.cuh"
 #include "../../graphchainer_b200/csrc/gc_k3.cuh"
+#include "../../graphchainer_b200/csrc/gc_seed.cuh"
 
 struct gcgpu_ctx
 {
@@ -26,6 +27,8 @@ struct gcgpu_ctx
 	uint64_t launches = 0;
 	std::vector<uint8_t> seqCopy;
 	std::vector<uint64_t> dense; // traces of the last gcgpu_extend call
+	std::vector<GcMzSlot> mzSlots; GcMzView mz; bool haveMz = false;
+	std::vector<gcgpu_seed_match> denseMatches;
 };
 static std::string g_err;
 
@@ -169,4 +172,49 @@ extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const ui
 	}
 	ctx->launches++;
 	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_set_minimizer_index(gcgpu_ctx* ctx, const gcgpu_minimizer_index* idx)
+{
+	uint64_t cap = 16;
+	while (cap < idx->num_kmers * 2 + 2) cap <<= 1;
+	ctx->mzSlots.assign(cap, GcMzSlot { 0, 0, 0xFFFFFFFFu });
+	for (uint64_t i = 0; i < idx->num_kmers; i++)
+	{
+		uint64_t h = gc_mz_hash(idx->kmers[i]) & (cap - 1);
+		while (ctx->mzSlots[h].count != 0xFFFFFFFFu && ctx->mzSlots[h].key != idx->kmers[i]) h = (h + 1) & (cap - 1);
+		ctx->mzSlots[h] = GcMzSlot { idx->kmers[i], idx->kmer_start[i], idx->kmer_start[i + 1] - idx->kmer_start[i] };
+	}
+	ctx->mz.slots = ctx->mzSlots.data(); ctx->mz.mask = cap - 1; ctx->mz.k = idx->k; ctx->mz.realWindow = idx->window - idx->k + 1; ctx->mz.maxCount = idx->max_count;
+	ctx->haveMz = true;
+	return 0;
+}
+extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seqIn, uint64_t seqBytes, const gcgpu_seed_read* reads, uint32_t n, uint64_t* match_offsets, gcgpu_seed_match* matches, uint64_t capacity, uint64_t* used)
+{
+	if (!ctx->haveMz) { g_err = "gcgpu_seed: no minimizer index"; return GCGPU_ERR_ARG; }
+	if (seqIn) ctx->seqCopy.assign(seqIn, seqIn + seqBytes);
+	const uint8_t* seq = ctx->seqCopy.data();
+	std::vector<std::vector<gcgpu_seed_match>> per(n);
+	#pragma omp parallel for schedule(dynamic, 4)
+	for (uint32_t r = 0; r < n; r++)
+		for (int32_t i = 0; i < reads[r].seq_len; i++)
+		{
+			uint32_t start, count;
+			if (gc_seed_position(ctx->mz, seq + reads[r].seq_offset, reads[r].seq_len, i, start, count)) per[r].push_back(gcgpu_seed_match { (uint32_t)i, start, count });
+		}
+	ctx->denseMatches.clear();
+	match_offsets[0] = 0;
+	for (uint32_t r = 0; r < n; r++) { ctx->denseMatches.insert(ctx->denseMatches.end(), per[r].begin(), per[r].end()); match_offsets[r + 1] = ctx->denseMatches.size(); }
+	ctx->launches += 3;
+	*used = ctx->denseMatches.size();
+	if (!matches && capacity == 0) return 0;
+	if (*used > capacity) { g_err = "gcgpu_seed: match buffer too small"; return GCGPU_ERR_ARG; }
+	if (*used) memcpy(matches, ctx->denseMatches.data(), *used * sizeof(gcgpu_seed_match));
+	return 0;
+}
+extern "C" int gcgpu_fetch_seed_matches(gcgpu_ctx* ctx, gcgpu_seed_match* matches, uint64_t first, uint64_t count)
+{
+	if (first + count > ctx->denseMatches.size()) { g_err = "gcgpu_fetch_seed_matches: range"; return GCGPU_ERR_ARG; }
+	if (count) memcpy(matches, ctx->denseMatches.data() + first, count * sizeof(gcgpu_seed_match));
+	return 0;
 }
