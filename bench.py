@@ -20,6 +20,9 @@ import argparse
 import json
 import os
 import re
+
+# the in-flight batches share the host cores: idle OpenMP teams (a batch waiting for its kernels) must sleep, not spin
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 import subprocess
 import sys
 import tempfile
@@ -107,6 +110,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="read batches in flight per GPU in the e2e measurement")
     ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
+    ap.add_argument("--threads-per-stream", type=int, default=0, help="host threads per in-flight batch (0 = host threads / streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -159,7 +163,7 @@ def main():
     batch = align.ReadBatch([r[0] for r in reads], [r[1] for r in reads])
     threads = max(1, host_cores // world)
     t_index = time.perf_counter()
-    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=args.streams, batch_bp=args.batch_bp)
+    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=args.streams, batch_bp=args.batch_bp, threads_per_stream=args.threads_per_stream)
     index_s = time.perf_counter() - t_index
 
     def barrier():
@@ -239,7 +243,7 @@ def main():
                          "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
             "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
-            "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp}
+            "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp, "threads_per_stream": args.threads_per_stream}
     if not args.no_cpu_baseline and os.path.exists(REFBIN):
         sample = min(args.cpu_sample, n_reads)
         fa = os.path.join(tmp, "sample.fa")

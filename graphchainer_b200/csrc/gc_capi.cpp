@@ -102,7 +102,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		first = r;
 	}
 	size_t W = std::min(h->workers.size(), std::max<size_t>(1, batches.size()));
-	int threadsPerWorker = std::max(1, hostThreads / (int)W);
+	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::max(1, hostThreads / (int)W);
 	std::vector<std::vector<std::string>> records(batches.size());
 	std::vector<std::vector<GcReadResult>> allResults(batches.size());
 	std::vector<uint64_t> launches0(W);

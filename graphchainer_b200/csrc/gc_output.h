@@ -8,6 +8,7 @@
 // holding varint64 count + {varint32 size, message}* (src/stream.hpp:24-51).
 #pragma once
 #include <zlib.h>
+#include "gc_deflate.h"
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -276,9 +277,16 @@ struct GamEncoder
 	}
 };
 
-// one gzip member per record; the deflate state (256 KB of tables) is kept per thread and level and only reset
+// one gzip member per record.  Level 1 = the driver's own single-pass encoder (gc_deflate.h, ~2x zlib level 1 at the
+// same ratio on GAM records); other levels = zlib, its deflate state (256 KB of tables) kept per thread and only reset
 inline std::string gzipMemberLevel(const std::string& raw, int level)
 {
+	if (level == 1)
+	{
+		static thread_local gcdeflate::Encoder enc;
+		std::string out = enc.gzipMember(raw);
+		if (!out.empty()) return out;
+	}
 	struct State { z_stream zs; int level = -100; bool live = false; ~State() { if (live) deflateEnd(&zs); } };
 	static thread_local State st;
 	if (!st.live || st.level != level)

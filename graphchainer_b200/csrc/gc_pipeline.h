@@ -901,36 +901,49 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	std::vector<gcgpu_nw_item> nwItems;
 	std::vector<int> gaItem(R, -1), clcItem(R, -1);
 	std::vector<uint64_t> readOffInBuf(R);
-	for (size_t r = 0; r < R; r++)
 	{
-		bool needGa = !longAlns[r].empty();
-		bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
-		if (!needGa && !needClc) continue;
-		readOffInBuf[r] = nwBuf.size();
-		nwBuf += reads[r].sequence;
-		// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
-		// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a
-		// starting point -- the kernel doubles the cutoff until the pass succeeds, like edlib does from 64.
-		int32_t kHint = 0;
-		if (needGa)
+		// layout first (serial, a few integers per read), then the character copies in parallel
+		uint64_t total = 0;
+		for (size_t r = 0; r < R; r++)
 		{
-			const GcAlnItem& a0 = longAlns[r][0];
-			size_t ub = a0.alignmentScore + a0.alignmentStart + (reads[r].sequence.size() - a0.alignmentEnd);
-			if (ub <= reads[r].sequence.size() / 4) kHint = (int32_t)ub;
+			bool needGa = !longAlns[r].empty();
+			bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
+			if (!needGa && !needClc) continue;
+			readOffInBuf[r] = total;
+			total += reads[r].sequence.size();
+			// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
+			// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a
+			// starting point -- the kernel doubles the cutoff until the pass succeeds, like edlib does from 64.
+			int32_t kHint = 0;
+			if (needGa)
+			{
+				const GcAlnItem& a0 = longAlns[r][0];
+				size_t ub = a0.alignmentScore + a0.alignmentStart + (reads[r].sequence.size() - a0.alignmentEnd);
+				if (ub <= reads[r].sequence.size() / 4) kHint = (int32_t)ub;
+			}
+			if (needGa)
+			{
+				gcgpu_nw_item it; it.query_offset = total; it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)longPathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+				it.k_hint = kHint; it.want_path = 0;
+				total += longPathSeq[r].size();
+				gaItem[r] = (int)nwItems.size(); nwItems.push_back(it);
+			}
+			if (needClc)
+			{
+				gcgpu_nw_item it; it.query_offset = total; it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+				it.k_hint = kHint + (kHint * 3) / 10; it.want_path = 0; // the chained path usually costs 5-40 % more than the whole-read alignment
+				total += pathSeq[r].size();
+				clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
+			}
 		}
-		if (needGa)
+		nwBuf.resize(total);
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t r = 0; r < R; r++)
 		{
-			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)longPathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-			it.k_hint = kHint; it.want_path = 0;
-			nwBuf += longPathSeq[r];
-			gaItem[r] = (int)nwItems.size(); nwItems.push_back(it);
-		}
-		if (needClc)
-		{
-			gcgpu_nw_item it; it.query_offset = nwBuf.size(); it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-			it.k_hint = kHint + (kHint * 3) / 10; it.want_path = 0; // the chained path usually costs 5-40 % more than the whole-read alignment
-			nwBuf += pathSeq[r];
-			clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
+			if (gaItem[r] < 0 && clcItem[r] < 0) continue;
+			memcpy(&nwBuf[readOffInBuf[r]], reads[r].sequence.data(), reads[r].sequence.size());
+			if (gaItem[r] >= 0) memcpy(&nwBuf[nwItems[gaItem[r]].query_offset], longPathSeq[r].data(), longPathSeq[r].size());
+			if (clcItem[r] >= 0) memcpy(&nwBuf[nwItems[clcItem[r]].query_offset], pathSeq[r].data(), pathSeq[r].size());
 		}
 	}
 	std::vector<gcgpu_nw_result> nwRes(nwItems.size());

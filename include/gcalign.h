@@ -34,7 +34,9 @@ typedef struct gcalign_options
 	int32_t gzip_level;           /* zlib level of the GAM gzip members: 0 = default (1, fastest);
 	                                 the reference's GzipOutputStream uses 6; decoded records
 	                                 are identical at every level                            */
-	int32_t reserved;
+	int32_t threads_per_stream;   /* host threads of each in-flight batch (0 = host_threads / streams); more than
+	                                 that share oversubscribes the cores on purpose: a batch waiting for the GPU
+	                                 leaves its threads idle                                  */
 } gcalign_options;
 
 /* per read: the fields of the reference's --short-verbose line (src/Aligner.cpp:909-915) */
