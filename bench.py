@@ -187,6 +187,10 @@ def main():
         launches += st["launches"]
     barrier()
     wall = time.perf_counter() - t0
+    try:
+        int_peak = aligner.int_peak()
+    except Exception:
+        int_peak = None
     aligner.close()
     # ---- kernel time: the same steps with ONE batch in flight, so that every CUDA-event pair brackets a
     # kernel that has the GPU to itself (with several streams the event durations of overlapping kernels add up)
@@ -240,7 +244,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "note": "integer-pipe bound bit-parallel kernel; algorithmic bytes = work units x bytes/unit (DESIGN.md)",
-                         "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
+                         "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0,
+                         "int32_peak_ops_per_s": int_peak, "int32_frac": (dom_units * dom_ops / (dom_ms / 1e3) / int_peak) if (int_peak and dom_ms > 0) else None,
+                         "int32_peak_source": "measured live: gcgpu_int_peak (independent LOP3+IADD3 chains, best of 4)"},
             "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
             "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp, "threads_per_stream": args.threads_per_stream}

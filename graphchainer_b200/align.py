@@ -44,6 +44,7 @@ def load():
         lib.gcalign_last_error.restype = C.c_char_p
         lib.gcalign_open.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(C.c_void_p)]
         lib.gcalign_close.argtypes = [C.c_void_p]
+        lib.gcalign_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.gcalign_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(Stats)]
         _lib = lib
     return _lib
@@ -106,15 +107,27 @@ class Aligner:
             raise RuntimeError(f"gcalign_open failed ({rc}): {self.lib.gcalign_last_error().decode()}")
         self.handle = h
 
+    def int_peak(self) -> float:
+        """Measured int32 LOP3/IADD3 instruction rate of the device (thread-level ops/s), gcgpu_int_peak."""
+        v = C.c_double(0)
+        rc = self.lib.gcalign_int_peak(self.handle, C.byref(v))
+        if rc != 0:
+            raise RuntimeError(f"gcalign_int_peak failed ({rc}): {self.lib.gcalign_last_error().decode()}")
+        return v.value
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.gcalign_close(self.handle)
             self.handle = None
 
     def align(self, batch: ReadBatch, gam: bool = True):
-        """Returns (gam bytes, summaries, stats dict)."""
+        """Returns (GAM bytes as a uint8 array view, summaries, stats dict).  The GAM buffer belongs to the
+        aligner and is reused by the next call (copy it -- bytes(view) -- to keep it)."""
         cap = (2 * batch.total_bp + (1 << 20)) if gam else 0
-        out = np.zeros(cap, dtype=np.uint8) if gam else None
+        if gam and (getattr(self, "_gam_buf", None) is None or self._gam_buf.size < cap):
+            self._gam_buf = np.empty(cap, dtype=np.uint8)
+        out = self._gam_buf if gam else None
+        cap = out.size if gam else 0
         used = C.c_uint64(0)
         summ = np.zeros(batch.n, dtype=SUMMARY)
         st = Stats()
@@ -122,4 +135,4 @@ class Aligner:
                                     out.ctypes.data if gam else None, cap, C.byref(used), summ.ctypes.data, C.byref(st))
         if rc != 0:
             raise RuntimeError(f"gcalign_align failed ({rc}): {self.lib.gcalign_last_error().decode()}")
-        return (out[:used.value].tobytes() if gam else b""), summ, st.as_dict()
+        return (out[:used.value] if gam else np.empty(0, dtype=np.uint8)), summ, st.as_dict()

@@ -83,6 +83,14 @@ extern "C" void gcalign_close(gcalign* h)
 	delete h;
 }
 
+extern "C" int gcalign_int_peak(gcalign* h, double* v)
+{
+	if (!h || !v || h->workers.empty()) return fail(GCGPU_ERR_ARG, "gcalign_int_peak: null argument");
+	int rc = gcgpu_int_peak(h->workers[0].ctx, v);
+	if (rc != GCGPU_OK) return fail(rc, std::string("gcalign_int_peak: ") + gcgpu_last_error());
+	return GCGPU_OK;
+}
+
 extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_offsets, const char* names, const uint64_t* name_offsets, uint32_t num_reads,
 	uint8_t* gam_out, uint64_t gam_capacity, uint64_t* gam_used, gcalign_read_summary* summaries, gcalign_stats* stats)
 {

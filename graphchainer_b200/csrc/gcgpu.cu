@@ -61,6 +61,7 @@ struct gcgpu_ctx
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t evSync = nullptr; // cudaEventBlockingSync: a host thread waiting for its batch sleeps instead of spinning on a core the other batches need
 	gcgpu_params params;
 	uint32_t numNodes = 0;
 	// device copies of the graph
@@ -86,6 +87,13 @@ struct gcgpu_ctx
 	uint64_t launches = 0;
 	uint64_t denseTraces = 0; // entries of the last gcgpu_extend call still in `compact`
 };
+
+static cudaError_t gcSyncStream(gcgpu_ctx* ctx)
+{
+	cudaError_t e = cudaEventRecord(ctx->evSync, ctx->stream);
+	if (e != cudaSuccess) return e;
+	return cudaEventSynchronize(ctx->evSync);
+}
 
 // ------------------------------------------------------------------ K1 kernels
 struct GcK1Desc
@@ -232,6 +240,7 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->evSync) cudaEventDestroy(ctx->evSync);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -257,6 +266,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	chk(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	chk(cudaEventCreate(&ctx->ev0));
 	chk(cudaEventCreate(&ctx->ev1));
+	chk(cudaEventCreateWithFlags(&ctx->evSync, cudaEventBlockingSync | cudaEventDisableTiming));
 	chk(uploadArray(graph->node_length, N, &ctx->d_nodeLength));
 	chk(uploadArray(graph->node_seq, 2 * (size_t)N, &ctx->d_nodeSeq));
 	chk(uploadArray(graph->in_start, (size_t)N + 1, &ctx->d_inStart));
@@ -418,7 +428,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	uint32_t overflow = 0;
 	CUDA_TRY(cudaMemcpyAsync(&overflow, dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k1 (long+short)", n);
@@ -463,7 +473,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			ctx->launches++;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-			CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+			CUDA_TRY(gcSyncStream(ctx));
 			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 			ctx->lastKernelMs += ms;
 			CUDA_TRY(cudaMemcpy(hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost));
@@ -492,7 +502,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	uint64_t used = 0;
 	CUDA_TRY(cudaMemcpyAsync(&used, dTotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaMemcpyAsync(results, dPub, (size_t)n * sizeof(gcgpu_ext_result), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k1 scan+gather", n);
@@ -504,7 +514,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	{
 		if (!traces) return setError(GCGPU_ERR_ARG, "gcgpu_extend: null trace buffer");
 		CUDA_TRY(cudaMemcpyAsync(traces, ctx->compact.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 	}
 	bool internal = false;
 	#pragma omp parallel for schedule(static) reduction(||: internal)
@@ -520,7 +530,7 @@ extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t fir
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	CUDA_TRY(cudaMemcpyAsync(traces, (const uint64_t*)ctx->compact.p + first, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	return GCGPU_OK;
 }
 
@@ -619,14 +629,14 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 	ctx->launches += 2;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(match_offsets, dOffs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	uint64_t used = match_offsets[n];
 	CUDA_TRY(ctx->seedMatches.ensure(used * sizeof(gcgpu_seed_match) + 16));
 	gc_seed_kernel<true><<<n, 256, 0, ctx->stream>>>(ctx->mz, (const uint8_t*)ctx->seqBuf.p, dReads, n, nullptr, dOffs, (gcgpu_seed_match*)ctx->seedMatches.p);
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs = ms;
 	GC_TRACE_MS("s0 seed lookups", n);
@@ -638,7 +648,7 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 	{
 		if (!matches) return setError(GCGPU_ERR_ARG, "gcgpu_seed: null match buffer");
 		CUDA_TRY(cudaMemcpyAsync(matches, ctx->seedMatches.p, used * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 	}
 	return GCGPU_OK;
 }
@@ -650,7 +660,57 @@ extern "C" int gcgpu_fetch_seed_matches(gcgpu_ctx* ctx, gcgpu_seed_match* matche
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	CUDA_TRY(cudaMemcpyAsync(matches, (const gcgpu_seed_match*)ctx->seedMatches.p + first, count * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	return GCGPU_OK;
+}
+
+// ------------------------------------------------------------------ integer-pipe peak (measurement aid)
+// K1/K3 are bound by the 32-bit integer pipes, not by HBM: this micro-benchmark measures the
+// sustained rate of independent 32-bit logic/add instructions (the mix of a Myers column step: LOP3 and IADD3,
+// 16 independent chains per thread) so that bench.py can state the kernels' int32 op rate as a fraction of it.
+__global__ void __launch_bounds__(256) gc_int_peak_kernel(uint32_t* out, uint32_t iters, uint32_t seed)
+{
+	uint32_t r[16];
+	#pragma unroll
+	for (int i = 0; i < 16; i++) r[i] = seed + threadIdx.x * 16 + i;
+	uint32_t a = seed | 1, b = blockIdx.x + 3;
+	for (uint32_t it = 0; it < iters; it++)
+	{
+		#pragma unroll
+		for (int i = 0; i < 16; i++)
+		{
+			r[i] = (r[i] ^ a) & (r[i] | b); // LOP3
+			r[i] = r[i] + a + b;              // IADD3
+		}
+	}
+	uint32_t x = 0;
+	#pragma unroll
+	for (int i = 0; i < 16; i++) x ^= r[i];
+	if (x == 0x12345678u) out[0] = x; // keeps the chains alive
+}
+
+extern "C" int gcgpu_int_peak(gcgpu_ctx* ctx, double* int32_ops_per_s)
+{
+	if (!ctx || !int32_ops_per_s) return setError(GCGPU_ERR_ARG, "gcgpu_int_peak: null argument");
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+	CUDA_TRY(ctx->seedBuf.ensure(256));
+	const uint32_t iters = 1 << 14;
+	const int blocks = prop.multiProcessorCount * 8, threads = 256;
+	float best = 1e30f;
+	for (int rep = 0; rep < 5; rep++)
+	{
+		float ms = 0;
+		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+		gc_int_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->seedBuf.p, iters, 12345u + rep);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
+		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		if (rep > 0 && ms < best) best = ms;
+	}
+	*int32_ops_per_s = (double)blocks * threads * (double)iters * 32.0 / (best / 1e3);
 	return GCGPU_OK;
 }
 
@@ -1017,7 +1077,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	std::vector<GcK3Out> hout(n);
 	CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k3w distance<0>", n);
@@ -1043,7 +1103,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		std::vector<GcK3Out> prev = hout;
 		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
 		GC_TRACE_MS(cls == 1 ? "k3w distance<1>" : "k3 distance (thread)", m);
@@ -1086,7 +1146,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
 		GC_TRACE_MS("k3w path", m);
@@ -1106,7 +1166,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 			CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
-			CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+			CUDA_TRY(gcSyncStream(ctx));
 			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 			ctx->lastKernelMs += ms;
 		}
@@ -1143,7 +1203,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaMemcpyAsync(ops, ctx->compact.p, used, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 	}
 	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_nw: an alignment path could not be reconstructed");
 	return GCGPU_OK;
@@ -1238,7 +1298,7 @@ extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const ui
 	if (total) CUDA_TRY(cudaMemcpyAsync(chain, A + offCh, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaMemcpyAsync(chain_len, A + offLen, (size_t)num_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(cudaMemcpyAsync(chain_score, A + offScore, (size_t)num_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	float ms = 0;
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs = ms;

@@ -68,6 +68,8 @@ const char* gcalign_last_error(void);
 /* graph_path: *.gfa (index built here) or *.gcidx (prebuilt index) */
 int gcalign_open(const char* graph_path, const gcalign_options* opts, gcalign** out);
 void gcalign_close(gcalign* h);
+/* measurement aid: gcgpu_int_peak() of the handle's device (int32 LOP3/IADD3 instructions per second, thread level) */
+int gcalign_int_peak(gcalign* h, double* int32_ops_per_s);
 /* reads: seqs[seq_offsets[i] .. seq_offsets[i+1]) and names likewise.  If gam_out != NULL the
  * reads' GAM records (one gzip member per read with an alignment) are appended to it.       */
 int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_offsets, const char* names, const uint64_t* name_offsets, uint32_t num_reads,

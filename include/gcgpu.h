@@ -241,6 +241,10 @@ int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* rea
 void* gcgpu_host_alloc(size_t bytes);
 void gcgpu_host_free(void* p);
 
+/* Measurement aid: sustained rate of independent 32-bit LOP3/IADD3 instructions on this device (thread-level
+ * int32 ops per second), the pipe that bounds K1/K3 (SURVEY.md 8d asks for a measured integer peak).  */
+int gcgpu_int_peak(gcgpu_ctx* ctx, double* int32_ops_per_s);
+
 /* device time of the kernels of the last call on this ctx, in milliseconds (CUDA events) */
 float gcgpu_last_kernel_ms(gcgpu_ctx* ctx);
 /* number of kernel launches issued by this ctx so far */

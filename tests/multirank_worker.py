@@ -25,7 +25,7 @@ def main():
     for k, i in enumerate(mine):
         off, size = int(summ[k]["gam_offset"]), int(summ[k]["gam_size"])
         if size:
-            local[int(i)] = blob[off:off + size]
+            local[int(i)] = bytes(blob[off:off + size])
     merged = shard.gather_records(local, rank, world)
     total_bp = sum(int(x) for x in batch.lengths())
     shard_bp = [None] * world
