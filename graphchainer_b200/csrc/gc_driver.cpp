@@ -345,6 +345,9 @@ int main(int argc, char** argv)
 	for (auto& w : workers) w.join();
 	if (!workerError.empty()) { std::cerr << "fatal: " << workerError << std::endl; return 1; }
 	if (params.outGam != "" && !wroteAny) { std::string empty = gcout::gamRecord({}); gamOut.write(empty.data(), empty.size()); } // Aligner.cpp:228-240
+#ifdef GC_PROF
+	if (getenv("GC_TRACE")) for (int i = 13; i < 32; i++) if (g_profName[i]) fprintf(stderr, "[prof] %-32s %.2f ms\n", g_profName[i], g_prof[i] / 2.0e6);
+#endif
 	double alignSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - alignStart).count();
 	for (auto ctx : ctxs) gcgpu_destroy(ctx);
 

@@ -315,7 +315,8 @@ inline std::string gamRecordDirect(const GcHostGraph& g, const std::string& seq_
 	std::string raw;
 	raw.reserve(sequence.size() * 2 + 256);
 	putVarint(raw, alns.size());
-	for (const GcAlnItem& a : alns) enc.encode(g, seq_id, sequence, a, raw);
+	{ GC_PROF_SCOPE(13, "gam.encode"); for (const GcAlnItem& a : alns) enc.encode(g, seq_id, sequence, a, raw); }
+	GC_PROF_SCOPE(14, "gam.deflate");
 	return gzipMemberLevel(raw, level);
 }
 

@@ -559,14 +559,35 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	// the results are then consumed strictly in seed order with the rules re-evaluated exactly as
 	// the reference does -- a speculative result whose seed turns out to be skipped is discarded.
 	struct S1Cand { size_t seedIdx; ExtRef ref; };
-	struct S1State { size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0; std::vector<gcgpu_ext_item> localItems; size_t itemBase = 0; };
+	struct S1State
+	{
+		size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0;
+		std::vector<gcgpu_ext_item> localItems; size_t itemBase = 0;
+		// memo of the skip rules: alignments are only ever added and never change, so "this seed is skipped" is permanent and
+		// "no alignment so far contains this seed cell" only needs the alignments added since it was last asked
+		std::vector<GcPackedAln> alnsAdded;   // insertion order (alns is kept sorted by alignmentStart like the reference's vector)
+		std::vector<uint8_t> skip;            // per seed: 1 = a skip rule fired
+		std::vector<uint32_t> checked;        // per seed: alnsAdded[0..checked) do not contain its cell
+		bool degenerate = false;              // an alignment on which exactAlignmentPart asserts exists: evaluate in reference order
+	};
 	std::vector<S1State> s1(R);
-	for (size_t r = 0; r < R; r++) if (seedsOrdered[r].empty()) s1[r].done = true;
+	for (size_t r = 0; r < R; r++) { if (seedsOrdered[r].empty()) s1[r].done = true; else { s1[r].skip.assign(seedsOrdered[r].size(), 0); s1[r].checked.assign(seedsOrdered[r].size(), 0); } }
 	// 0 = extend, 1 = skip, 2 = stop the seed loop, 3 = assertion (read dropped)
-	auto seedRule = [&](const S1State& st, const GcSeedHit& seed) -> int
+	auto seedRule = [&](S1State& st, const GcSeedHit& seed, size_t idx) -> int
 	{
 		if (seed.seedGoodness < st.seedScoreForEndToEndAln) return 2;
 		if (seed.seedClusterSize < params.seedClusterMinSize) return 1;
+		if (!st.degenerate)
+		{
+			if (st.skip[idx]) return 1;
+			for (const auto& aln : st.alns)
+				if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) { st.skip[idx] = 1; return 1; }
+			bool assertion = false;
+			for (uint32_t k = st.checked[idx]; k < st.alnsAdded.size(); k++)
+				if (gcpipe::exactAlignmentPart(g, st.alnsAdded[k], seed, assertion)) { st.skip[idx] = 1; return 1; }
+			st.checked[idx] = (uint32_t)st.alnsAdded.size();
+			return 0;
+		}
 		for (const auto& aln : st.alns)
 			if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) return 1;
 		bool assertion = false;
@@ -590,7 +611,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			st.localItems.clear();
 			for (size_t i = st.i; i < seedHits.size() && st.cands.size() < want; i++)
 			{
-				int rule = seedRule(st, seedHits[i]);
+				int rule = seedRule(st, seedHits[i], i);
 				if (rule >= 2) break; // decided again, in order, when the results are consumed
 				if (rule == 1) continue;
 				S1Cand c; c.seedIdx = i;
@@ -601,7 +622,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			if (st.cands.empty())
 			{
 				// nothing left to extend: finish the seed walk for the assertion-class exit only
-				for (; st.i < seedHits.size(); st.i++) { int rule = seedRule(st, seedHits[st.i]); if (rule == 3) out[r].dropped = true; if (rule >= 2) break; }
+				for (; st.i < seedHits.size(); st.i++) { int rule = seedRule(st, seedHits[st.i], st.i); if (rule == 3) out[r].dropped = true; if (rule >= 2) break; }
 				st.done = true;
 			}
 		}
@@ -627,7 +648,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			for (; st.i < seedHits.size(); st.i++)
 			{
 				const GcSeedHit& seed = seedHits[st.i];
-				int rule = seedRule(st, seed);
+				int rule = seedRule(st, seed, st.i);
 				if (rule == 3) { out[r].dropped = true; st.i = seedHits.size(); break; }
 				if (rule == 2) { st.i = seedHits.size(); break; }
 				if (rule == 1) continue;
@@ -641,6 +662,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && readResults[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
 				if (!ok || item.alignmentEnd == item.alignmentStart) continue;
 				st.alns.emplace_back(item);
+				st.alnsAdded.emplace_back(item);
+				{ uint32_t n = item.size(); if (n == 0 || !(item.seqPosAt(n - 1) > item.seqPosAt(0))) st.degenerate = true; }
 				std::sort(st.alns.begin(), st.alns.end(), [](const GcPackedAln& left, const GcPackedAln& right) { return left.alignmentStart < right.alignmentStart; });
 				if (st.alns[0].alignmentStart == 0)
 				{

@@ -62,3 +62,26 @@ def test_gpu_pipeline_matches_reference_on_fresh_synthetic(tmp_path):
     assert len(b) == 300
     diffs = gam.diff_gam(a, b)
     assert not diffs, diffs
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_matches_reference_on_ultralong_reads(tmp_path):
+    """BASELINE config-4 shape: 50-100 kb reads at 12 % error (K1 items of ~1500 slices, NW bands of
+    ~8-16 k diagonals, i.e. the widest K3 lane groups, many gap fills); the unmodified reference runs
+    live on the box's CPU, every field of every decoded GAM record must be equal."""
+    if not (os.path.exists(REFBIN) and os.path.exists(REFDUMP)):
+        pytest.skip("oracle/_ref not built")
+    from graphchainer_b200 import synth
+    g = synth.SynthGraph(1_500_000, seed=61)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    with open(gfa, "w") as f:
+        f.write(g.gfa())
+    synth.write_fasta(fa, synth.simulate_reads(g, 10, (50_000, 100_000), 0.12, seed=62, novel_insertion_frac=0.3))
+    idx, ref_gam, out = str(tmp_path / "x.gcidx"), str(tmp_path / "ref.gam"), str(tmp_path / "out.gam")
+    subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "--gc-index", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([REFBIN, "-t", str(os.cpu_count() or 8), "-g", gfa, "-f", fa, "-a", ref_gam], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8))], check=True, stdout=subprocess.DEVNULL)
+    a, b = gam.read_gam(out), gam.read_gam(ref_gam)
+    assert len(b) == 10
+    diffs = gam.diff_gam(a, b)
+    assert not diffs, diffs
