@@ -117,6 +117,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	std::atomic<size_t> nextBatch(0);
 	std::mutex errMutex; std::string error;
 	GcPipelineStats total;
+	auto tCall0 = std::chrono::steady_clock::now();
 	auto work = [&](size_t w)
 	{
 		omp_set_num_threads(threadsPerWorker);
@@ -142,7 +143,9 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 					batch.push_back(std::move(rd));
 				}
 				std::vector<GcReadResult>& results = allResults[bi];
+				auto tB0 = std::chrono::steady_clock::now();
 				pipeline.alignBatch(batch, results);
+				if (getenv("GC_TRACE_CALL")) fprintf(stderr, "[gcalign] worker %zu batch %zu: alignBatch %.1f ms (start +%.1f ms)\n", w, bi, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tB0).count(), std::chrono::duration<double, std::milli>(tB0 - tCall0).count());
 				records[bi].resize(batch.size());
 				auto tGam0 = std::chrono::steady_clock::now();
 				if (gam_out)
@@ -171,6 +174,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		catch (const std::exception& e) { std::lock_guard<std::mutex> lock(errMutex); error = e.what(); }
 	};
 	for (size_t w = 0; w < W; w++) launches0[w] = gcgpu_launch_count(h->workers[w].ctx);
+	tCall0 = std::chrono::steady_clock::now();
 	{
 		std::vector<std::thread> threads;
 		for (size_t w = 1; w < W; w++) threads.emplace_back(work, w);
@@ -178,6 +182,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		for (auto& t : threads) t.join();
 	}
 	if (!error.empty()) return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + error);
+	auto tCall1 = std::chrono::steady_clock::now();
 	uint64_t used = 0;
 	for (size_t bi = 0; bi < batches.size(); bi++)
 	{
@@ -209,5 +214,11 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		for (size_t w = 0; w < W; w++) stats->launches += gcgpu_launch_count(h->workers[w].ctx) - launches0[w];
 	}
 	if (gam_used) *gam_used = used;
+	if (getenv("GC_TRACE_CALL"))
+	{
+		auto tCall2 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[gcalign] batches=%zu workers=%zu threads/worker=%d | workers %.1f ms, gather %.1f ms\n", batches.size(), W, threadsPerWorker,
+			std::chrono::duration<double, std::milli>(tCall1 - tCall0).count(), std::chrono::duration<double, std::milli>(tCall2 - tCall1).count());
+	}
 	return GCGPU_OK;
 }

@@ -146,6 +146,42 @@ GC_HD uint64_t gc_heap_pop(uint64_t* heap, uint32_t& size)
 	return top;
 }
 
+// state of the column loop of one node (registers)
+struct GcColumnRun
+{
+	GcWord ws;
+	uint64_t eq[4];          // Eq masks of the slice, already combined with the first-row rule
+	uint64_t prevHP, prevHN; // horizontal deltas along the last row of the previous slice (bit = column)
+	uint64_t HP, HN;         // this node's horizontal deltas along row 63, shifted in from the top
+	uint64_t chunk0, chunk1; // node sequence, 2 bits per base
+	int32_t minScore; uint32_t minOffset;
+};
+// columns [begin, end) of the node: one getNextSlice step each (BVCommon.h:1118-1161)
+template <bool FORCE>
+GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols)
+{
+	for (uint32_t pos = begin; pos < end; pos++)
+	{
+		uint64_t chunk = pos < 32 ? r.chunk0 : r.chunk1;
+		int base = (int)((chunk >> ((pos & 31) * 2)) & 3);
+		uint64_t hP, hN;
+		r.ws = gc_next_column(r.eq[base], r.ws, (r.prevHP >> pos) & 1, (r.prevHN >> pos) & 1, hP, hN);
+		if (FORCE)
+		{
+			r.ws.VP &= ~1ULL;
+			r.ws.VN |= 1;
+		}
+		if (r.ws.scoreEnd < r.minScore)
+		{
+			r.minScore = r.ws.scoreEnd;
+			r.minOffset = pos;
+		}
+		if (cols) cols[pos] = r.ws;
+		r.HP = (r.HP >> 1) | (hP << 63);
+		r.HN = (r.HN >> 1) | (hN << 63);
+	}
+}
+
 // Columns 1..len-1 of a node from its start column (the tail of calculateNodeInner,
 // BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
 // (recalcNodeWordslice, BVCommon.h:828-852).
@@ -190,34 +226,22 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 	if (cols) cols[0] = ws;
 	uint64_t forceEq = ~0ULL;
 	if (!prevExists) forceEq ^= 1;
-	minScore = ws.scoreEnd;
-	minOffset = 0;
-	uint64_t HP = 0, HN = 0;
-	uint64_t chunk0 = g.nodeSeq[2 * (uint64_t)node], chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
-	for (uint32_t pos = 1; pos < len; pos++)
-	{
-		uint64_t chunk = pos < 32 ? chunk0 : chunk1;
-		int base = (int)((chunk >> ((pos & 31) * 2)) & 3);
-		uint64_t Eq = eq[base] & forceEq;
-		uint64_t hP, hN;
-		ws = gc_next_column(Eq, ws, (prevHP >> pos) & 1, (prevHN >> pos) & 1, hP, hN);
-		if (forceUntil >= pos)
-		{
-			ws.VP &= ~1ULL;
-			ws.VN |= 1;
-		}
-		if (ws.scoreEnd < minScore)
-		{
-			minScore = ws.scoreEnd;
-			minOffset = pos;
-		}
-		if (cols) cols[pos] = ws;
-		HP |= hP << pos;
-		HN |= hN << pos;
-	}
-	endOut = ws;
-	HPout = HP;
-	HNout = HN;
+	GcColumnRun run;
+	run.ws = ws; run.minScore = ws.scoreEnd; run.minOffset = 0; run.HP = 0; run.HN = 0;
+	run.prevHP = prevHP; run.prevHN = prevHN;
+	run.eq[0] = eq[0] & forceEq; run.eq[1] = eq[1] & forceEq; run.eq[2] = eq[2] & forceEq; run.eq[3] = eq[3] & forceEq;
+	run.chunk0 = g.nodeSeq[2 * (uint64_t)node]; run.chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
+	// columns 1..forceUntil have their first row forced (a column cannot start below the previous slice's row), the rest not
+	uint32_t forcedEnd = forceUntil + 1 < len ? forceUntil + 1 : len;
+	if (forcedEnd > 1) gc_columns_range<true>(run, 1, forcedEnd, cols);
+	if (forcedEnd < len) gc_columns_range<false>(run, forcedEnd < 1 ? 1 : forcedEnd, len, cols);
+	// the horizontal bits were shifted in from the top, one per column: bring the bit of column p to bit p
+	if (len > 1) { run.HP >>= (64 - len); run.HN >>= (64 - len); }
+	endOut = run.ws;
+	HPout = run.HP;
+	HNout = run.HN;
+	minScore = run.minScore;
+	minOffset = run.minOffset;
 }
 
 // recalcNodeWordslice (BVCommon.h:828-852): all columns of a stored node
@@ -821,26 +845,36 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 		// (one loop iteration = one node visit: recompute, walk, cross -- the lanes of a warp stay in step)
 		if ((tw.seqPos & 63) != 0 && tw.offset != 0)
 		{
+			// The reference reads three cell values per step (here, above, diagonal: getValue = two 64-bit popcounts each).
+			// Same values, incrementally: along a column value(row-1) = value(row) + VN[row] - VP[row], so the cell above is a
+			// bit test, and the value of the left neighbour column at the current row is carried along and only recomputed
+			// (one getValue) when the walk moves a column to the left.
 			uint32_t hori = tw.offset;
 			int32_t vert = tw.seqPos - j;
+			const uint64_t chunk0 = g.nodeSeq[2 * (uint64_t)currentNode], chunk1 = g.nodeSeq[2 * (uint64_t)currentNode + 1];
+			GcWord cur = cols[hori], left = cols[hori - 1];
+			int32_t scoreHere = gc_value(cur, vert);
+			int32_t leftHere = gc_value(left, vert);
 			while (hori > 0 && vert > 0)
 			{
-				int32_t scoreHere = gc_value(cols[hori], vert);
-				int32_t verticalScore = gc_value(cols[hori], vert - 1);
-				int32_t diagonalScore = gc_value(cols[hori - 1], vert - 1);
-				bool eqc = gc_char_match(seq[vert + j], gc_node_base(g, currentNode, hori));
-				if (verticalScore == scoreHere - 1)
+				int32_t dv = (int32_t)((cur.VN >> vert) & 1) - (int32_t)((cur.VP >> vert) & 1);    // value(cur, vert-1) - value(cur, vert)
+				int32_t dl = (int32_t)((left.VN >> vert) & 1) - (int32_t)((left.VP >> vert) & 1); // the same in the left column
+				int32_t diagonalScore = leftHere + dl;
+				int base = (int)(((hori < 32 ? chunk0 : chunk1) >> ((hori & 31) * 2)) & 3);
+				bool eqc = gc_char_match(seq[vert + j], base);
+				if (dv == -1)
 				{
 					vert--;
-				}
-				else if (diagonalScore == scoreHere - (eqc ? 0 : 1))
-				{
-					hori--;
-					vert--;
+					scoreHere -= 1;
+					leftHere = diagonalScore;
 				}
 				else
 				{
+					if (diagonalScore == scoreHere - (eqc ? 0 : 1)) { vert--; scoreHere = diagonalScore; }
+					else scoreHere = leftHere;
 					hori--;
+					cur = left;
+					if (hori > 0) { left = cols[hori - 1]; leftHere = gc_value(left, vert); }
 				}
 				tw.push(currentNode, hori, vert + j, false);
 			}

@@ -1009,7 +1009,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		if (better)
 		{
 			gcgpu_nw_item it = nwItems[clcItem[r]];
-			it.want_path = 1; it.k_hint = nwRes[clcItem[r]].distance;
+			it.want_path = 2; it.k_hint = nwRes[clcItem[r]].distance; // the distance is known: only the edit path is computed
 			pathItems.push_back(it); pathRead.push_back(r);
 		}
 	}

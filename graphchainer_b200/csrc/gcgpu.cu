@@ -1070,17 +1070,33 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(ctx->arena.ensure(wsTotal));
 	CUDA_TRY(ctx->descBuf.ensure((size_t)n * sizeof(GcK3Desc)));
 	CUDA_TRY(ctx->resBuf.ensure((size_t)n * sizeof(GcK3Out)));
+	// want_path == 2 on every item: the caller already holds the exact distances (an earlier call on the same pairs), the
+	// distance pass would only recompute them
+	bool distancesKnown = true;
+	for (uint32_t i = 0; i < n; i++) if (items[i].want_path != 2 || items[i].k_hint < 0) { distancesKnown = false; break; }
+	std::vector<GcK3Out> hout(n);
+	if (distancesKnown)
+	{
+		for (uint32_t i = 0; i < n; i++) { hout[i].status = GC_OK; hout[i].distance = items[i].k_hint; hout[i].opsLen = 0; hout[i].pad = 0; hout[i].blocks = 0; }
+		CUDA_TRY(cudaMemcpyAsync(ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
+		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		ctx->lastKernelMs += ms;
+	}
+	else
+	{
 	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 	gc_k3w_distance_kernel<0><<<(n + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-	std::vector<GcK3Out> hout(n);
 	CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k3w distance<0>", n);
+	}
 	// items whose cutoff band outgrew the register budget of the launched class: wider class, then the thread form
 	for (int cls = 1; cls <= 2; cls++)
 	{

@@ -200,7 +200,9 @@ typedef struct gcgpu_nw_item
 	int32_t query_len;
 	int32_t target_len;
 	int32_t k_hint;       /* optional first band guess (<= 0: start at 64 like edlib)      */
-	int32_t want_path;
+	int32_t want_path;    /* 0 distance only; 1 distance + edit operations; 2 edit operations for a pair whose
+	                         exact edit distance the caller passes in k_hint (the value an earlier call returned):
+	                         if every item of a call says 2 the distance pass is skipped                        */
 } gcgpu_nw_item;
 
 typedef struct gcgpu_nw_result
