@@ -108,7 +108,7 @@ def main():
     ap.add_argument("--reads", type=int, default=None, help="reads per step and GPU (default: the workload's full read set)")
     ap.add_argument("--cpu-sample", type=int, default=640, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="read batches in flight per GPU in the e2e measurement")
+    ap.add_argument("--streams", type=int, default=6, help="read batches in flight per GPU in the e2e measurement")
     ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
     ap.add_argument("--threads-per-stream", type=int, default=0, help="host threads per in-flight batch (0 = host threads / streams)")
     args = ap.parse_args()

@@ -1,5 +1,6 @@
 // libgcalign: the host pipeline behind a C ABI (include/gcalign.h).
 #include <omp.h>
+#include <malloc.h>
 #include <atomic>
 #include <cstring>
 #include <memory>
@@ -41,6 +42,13 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 {
 	if (!graph_path || !out) return fail(GCGPU_ERR_ARG, "gcalign_open: null argument");
 	*out = nullptr;
+	// The host stages allocate and free gigabytes of per-batch vectors from several threads.  With glibc's defaults every
+	// large block is its own mmap/munmap (page faults on first touch, TLB shootdowns across all threads on release) and the
+	// arenas are trimmed back to the kernel between batches; keeping the memory in the arenas was worth 7 % end to end on
+	// B200 (profiles/r01j).
+	mallopt(M_MMAP_THRESHOLD, 1 << 30);
+	mallopt(M_TRIM_THRESHOLD, -1);
+	mallopt(M_TOP_PAD, 256 << 20);
 	gcalign* h = new gcalign();
 	if (opts) h->opts = *opts; else gcalign_default_options(&h->opts);
 	if (h->opts.colinear_split_gap < 1 || h->opts.colinear_split_len < 1) { delete h; return fail(GCGPU_ERR_ARG, "gcalign_open: split length / gap must be >= 1"); }
@@ -63,7 +71,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	gg.comp_map = g.compMap.data(); gg.comp_idx = g.compIdx.data(); gg.comp_start = g.compStart.data(); gg.topo_ids = g.topoIds.data();
 	gg.paths_start = g.pathsStart.data(); gg.paths_k = g.pathsK.data(); gg.back_start = g.backStart.data(); gg.back_node = g.backNode.data(); gg.back_k = g.backK.data();
 	gcgpu_params gp; gp.initial_bandwidth = h->opts.initial_bandwidth;
-	int streams = h->opts.streams > 0 ? h->opts.streams : 4;
+	int streams = h->opts.streams > 0 ? h->opts.streams : 6;
 	h->workers.resize(streams);
 	for (int w = 0; w < streams; w++)
 	{
@@ -110,7 +118,9 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		first = r;
 	}
 	size_t W = std::min(h->workers.size(), std::max<size_t>(1, batches.size()));
-	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::max(1, hostThreads / (int)W);
+	// default: the batches in flight together hold ~2.25x as many threads as there are host threads -- a batch spends more than half
+	// of its time waiting for its kernels (threads asleep), measured best on B200 with 16 cores (profiles/r01h: 6 streams x 6 threads)
+	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::max(1, (hostThreads * 9 + 4 * (int)W - 1) / (4 * (int)W));
 	std::vector<std::vector<std::string>> records(batches.size());
 	std::vector<std::vector<GcReadResult>> allResults(batches.size());
 	std::vector<uint64_t> launches0(W);

@@ -15,6 +15,7 @@
 #include <sstream>
 #include <thread>
 #include <omp.h>
+#include <malloc.h>
 #include <zlib.h>
 #include "gc_pipeline.h"
 #include "gc_output.h"
@@ -29,7 +30,7 @@ struct DriverParams
 	std::string outGam, outJson;
 	size_t threads = 1;
 	int gpus = 1;
-	int streams = 4;
+	int streams = 6;
 	int gzipLevel = 1;
 	int firstDevice = 0;
 	int bandwidth = 10;
@@ -59,7 +60,7 @@ static void usage()
 		"  --short-verbose               print the per-read progress line\n"
 		"B200 parameters:\n"
 		"  --gc-gpus N                   GPUs to use (reads are partitioned in length-balanced batches)\n"
-		"  --gc-streams N                read batches in flight per GPU [default 4]\n"
+		"  --gc-streams N                read batches in flight per GPU [default 6]\n"
 		"  --gc-gzip-level N             zlib level of the GAM gzip members [default 1; the reference's library default is 6]\n"
 		"  --gc-index file.gcidx         load a prebuilt graph/MPC/minimizer index\n"
 		"  --gc-save-index file.gcidx    store the index built from -g\n"
@@ -187,6 +188,7 @@ struct ReadStream
 int main(int argc, char** argv)
 {
 	DriverParams params = parseArgs(argc, argv);
+	mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, -1); mallopt(M_TOP_PAD, 256 << 20); // keep the per-batch vectors in the arenas (see gc_capi.cpp)
 	omp_set_num_threads((int)params.threads);
 	std::cout << "Co-linear chaining on splits=(" << params.pipe.colinearSplitLen << "," << params.pipe.colinearSplitGap << "," << params.pipe.colinearGap << ")" << std::endl;
 	GcHostGraph graph;
@@ -281,7 +283,8 @@ int main(int argc, char** argv)
 	};
 	auto worker = [&](int d)
 	{
-		omp_set_num_threads(std::max<int>(1, (int)params.threads / numWorkers));
+		// the batches in flight together hold ~2.25x the host threads: a batch waiting for its kernels leaves its threads asleep
+		omp_set_num_threads(std::max<int>(1, ((int)params.threads * 9 + 4 * numWorkers - 1) / (4 * numWorkers)));
 		GcPipeline pipeline(graph, ctxs[d], params.pipe);
 		std::vector<GcRead> batch;
 		std::vector<GcReadResult> results;

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 // of serialising 32 divergent walks, (b) lets loop-free lookups use the lanes -- the slice hash
 // lookup becomes one ballot over the slice's items, the Eq masks of a slice eight ballots -- and
 // (c) moves the recomputed node columns from per-thread local memory to shared memory.
-__global__ void __launch_bounds__(128) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
 {
 	__shared__ GcWord colsShared[4][64];
@@ -416,7 +417,14 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		if (nLong >= simtMin)
 			gc_k1_long_simt_kernel<<<(nLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		else
-			gc_k1_long_kernel<<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+		{
+			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 trades ~150 bytes of spills for 24 warps per SM
+			static const int minBlocks = getenv("GCGPU_K1_LONG_BLOCKS") ? atoi(getenv("GCGPU_K1_LONG_BLOCKS")) : 5;
+			if (minBlocks >= 6)
+				gc_k1_long_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			else
+				gc_k1_long_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+		}
 		ctx->launches++;
 	}
 	if (nShort)
@@ -469,7 +477,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			CUDA_TRY(cudaMemsetAsync(dOverflow, 0, 4, ctx->stream));
 			uint32_t m = (uint32_t)rd.size();
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-			gc_k1_long_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			gc_k1_long_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 			ctx->launches++;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -26,7 +26,7 @@ typedef struct gcalign_options
 	int32_t host_threads;         /* -t: threads for the host stages                      */
 	int32_t initial_bandwidth;    /* -b, default 10                                       */
 	int32_t streams;              /* read batches in flight per device, each with its own CUDA stream,
-	                                 workspaces and share of the host threads (0 = default 4)     */
+	                                 workspaces and share of the host threads (0 = default 6)     */
 	int64_t colinear_gap;         /* --colinear-gap, default 10000                        */
 	int64_t colinear_split_len;   /* --colinear-split-len, default 35                     */
 	int64_t colinear_split_gap;   /* --colinear-split-gap, default 35                     */
@@ -34,7 +34,7 @@ typedef struct gcalign_options
 	int32_t gzip_level;           /* zlib level of the GAM gzip members: 0 = default (1, fastest);
 	                                 the reference's GzipOutputStream uses 6; decoded records
 	                                 are identical at every level                            */
-	int32_t threads_per_stream;   /* host threads of each in-flight batch (0 = host_threads / streams); more than
+	int32_t threads_per_stream;   /* host threads of each in-flight batch (0 = 2.25 * host_threads / streams); more than
 	                                 that share oversubscribes the cores on purpose: a batch waiting for the GPU
 	                                 leaves its threads idle                                  */
 } gcalign_options;
