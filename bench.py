@@ -248,6 +248,8 @@ def main():
                          "int32_peak_ops_per_s": int_peak, "int32_frac": (dom_units * dom_ops / (dom_ms / 1e3) / int_peak) if (int_peak and dom_ms > 0) else None,
                          "int32_peak_source": "measured live: gcgpu_int_peak (independent LOP3+IADD3 chains, best of 4)"},
             "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
+            "gcups": {"k1": 64 * k1_cols / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None, "k3": 64 * k3_blocks / (k3_ms / 1e3) / 1e9 if k3_ms > 0 else None,
+                      "note": "64 DP cells per work unit W (one Myers column step on a 64-row word), SURVEY 8d"},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
             "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp, "threads_per_stream": args.threads_per_stream}
     if not args.no_cpu_baseline and os.path.exists(REFBIN):

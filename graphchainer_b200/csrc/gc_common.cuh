@@ -12,7 +12,7 @@
 #define GC_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define GC_HD inline
-#define GC_HD_NOINLINE
+#define GC_HD_NOINLINE inline __attribute__((noinline))
 #endif
 
 #define GC_INT_MAX 2147483647

@@ -157,8 +157,10 @@ struct GcColumnRun
 	int32_t minScore; uint32_t minOffset;
 };
 // columns [begin, end) of the node: one getNextSlice step each (BVCommon.h:1118-1161)
-template <bool FORCE>
-GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols)
+// FORCE: 1 = every column of the range has its first row forced, 0 = none, 2 = columns up to forceUntil (decided per column:
+// the thread-per-item kernel keeps ONE loop so that the lanes of a warp, whose forced ranges differ, stay in one loop)
+template <int FORCE>
+GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols, uint32_t forceUntil = 0)
 {
 	for (uint32_t pos = begin; pos < end; pos++)
 	{
@@ -166,7 +168,7 @@ GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord
 		int base = (int)((chunk >> ((pos & 31) * 2)) & 3);
 		uint64_t hP, hN;
 		r.ws = gc_next_column(r.eq[base], r.ws, (r.prevHP >> pos) & 1, (r.prevHN >> pos) & 1, hP, hN);
-		if (FORCE)
+		if (FORCE == 1 || (FORCE == 2 && forceUntil >= pos))
 		{
 			r.ws.VP &= ~1ULL;
 			r.ws.VN |= 1;
@@ -232,9 +234,13 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 	run.eq[0] = eq[0] & forceEq; run.eq[1] = eq[1] & forceEq; run.eq[2] = eq[2] & forceEq; run.eq[3] = eq[3] & forceEq;
 	run.chunk0 = g.nodeSeq[2 * (uint64_t)node]; run.chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
 	// columns 1..forceUntil have their first row forced (a column cannot start below the previous slice's row), the rest not
-	uint32_t forcedEnd = forceUntil + 1 < len ? forceUntil + 1 : len;
-	if (forcedEnd > 1) gc_columns_range<true>(run, 1, forcedEnd, cols);
-	if (forcedEnd < len) gc_columns_range<false>(run, forcedEnd < 1 ? 1 : forcedEnd, len, cols);
+	if (g.coopLane >= 0)
+	{
+		uint32_t forcedEnd = forceUntil + 1 < len ? forceUntil + 1 : len;
+		if (forcedEnd > 1) gc_columns_range<1>(run, 1, forcedEnd, cols);
+		if (forcedEnd < len) gc_columns_range<0>(run, forcedEnd < 1 ? 1 : forcedEnd, len, cols);
+	}
+	else gc_columns_range<2>(run, 1, len, cols, forceUntil);
 	// the horizontal bits were shifted in from the top, one per column: bring the bit of column p to bit p
 	if (len > 1) { run.HP >>= (64 - len); run.HN >>= (64 - len); }
 	endOut = run.ws;

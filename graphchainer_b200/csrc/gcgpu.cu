@@ -146,12 +146,8 @@ struct GcK1ShortLayout
 	uint32_t traceStride;           // entries
 	uint32_t itemCap, heapCap, numSlices;
 };
-__global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
-	uint64_t* traceOffOfItem, uint32_t* overflow)
+__device__ __forceinline__ GcK1Desc gc_k1_short_desc(const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t t, const GcK1ShortLayout& lay)
 {
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
 	uint32_t idx = shortIdx ? shortIdx[t] : t;
 	gcgpu_ext_item it = items[idx];
 	GcK1Desc d;
@@ -159,8 +155,43 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	d.wsOff = lay.wsBase + (uint64_t)t * lay.wsStride;
 	d.traceOff = lay.traceBase + (uint64_t)t * lay.traceStride;
 	d.itemCap = lay.itemCap; d.heapCap = lay.heapCap; d.traceCap = lay.traceStride; d.numSlices = lay.numSlices; d.resultIndex = idx;
+	return d;
+}
+__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcWord* cols, GcK1Workspace& ws);
+// forward pass and backtrace are separate launches, as for the long items (instruction footprint, see below)
+__global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
+	uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
 	GcWord cols[64];
-	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, cols);
+	GcK1Workspace ws;
+	gc_k1_workspace(d, arena, cols, ws);
+	GcK1Result res;
+	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
+	if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+	results[d.resultIndex] = res;
+	traceOffOfItem[d.resultIndex] = d.traceOff;
+	lastSlice[t] = last;
+	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+}
+__global__ void __launch_bounds__(128) gc_k1_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq,
+	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
+	const int32_t* __restrict__ lastSlice)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
+	GcK1Result res = results[d.resultIndex];
+	if (res.status != GC_OK) return;
+	GcWord cols[64];
+	GcK1Workspace ws;
+	gc_k1_workspace(d, arena, cols, ws);
+	gc_k1_backtrace(g, seq + d.seqOff, d.seqLen, ws, lastSlice[t], traceArena + d.traceOff, d.traceCap, res);
+	results[d.resultIndex] = res;
 }
 
 // Long work items (whole-read extensions: ~80 slices, tens of thousands of dependent column steps):
@@ -169,16 +200,55 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 // of serialising 32 divergent walks, (b) lets loop-free lookups use the lanes -- the slice hash
 // lookup becomes one ballot over the slice's items, the Eq masks of a slice eight ballots -- and
 // (c) moves the recomputed node columns from per-thread local memory to shared memory.
+// The walk is split into two launches, forward pass (slices, Viterbi cut) and backtrace: at any time all warps of the
+// GPU run the same half of the code (the whole item is ~7 k instructions; with both halves resident `no_instruction` was
+// 16 % of the stall cycles of the single kernel, profiles/r01h) and each half needs fewer registers.
+__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcWord* cols, GcK1Workspace& ws)
+{
+	ws.cols = cols;
+	uint8_t* base = arena + d.wsOff;
+	ws.slices = (GcSliceMeta*)base;
+	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
+	ws.items = (GcNodeItem*)(base + slicesBytes);
+	ws.heap = (uint64_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem));
+	ws.itemCap = d.itemCap;
+	ws.heapCap = d.heapCap;
+}
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
 	__shared__ GcWord colsShared[4][64];
 	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (t >= n) return;
 	g.coopLane = (int32_t)(threadIdx.x & 31);
 	GcK1Desc d = descs[t];
-	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, colsShared[threadIdx.x >> 5]);
+	GcK1Workspace ws;
+	gc_k1_workspace(d, arena, colsShared[threadIdx.x >> 5], ws);
+	GcK1Result res;
+	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
+	if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+	results[d.resultIndex] = res;
+	traceOffOfItem[d.resultIndex] = d.traceOff;
+	lastSlice[t] = last;
+	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+}
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq,
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
+{
+	__shared__ GcWord colsShared[4][64];
+	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (t >= n) return;
+	g.coopLane = (int32_t)(threadIdx.x & 31);
+	GcK1Desc d = descs[t];
+	GcK1Result res = results[d.resultIndex];
+	if (res.status != GC_OK) return;
+	GcK1Workspace ws;
+	gc_k1_workspace(d, arena, colsShared[threadIdx.x >> 5], ws);
+	gc_k1_backtrace(g, seq + d.seqOff, d.seqLen, ws, lastSlice[t], traceArena + d.traceOff, d.traceCap, res);
+	results[d.resultIndex] = res;
 }
 
 // Long work items, SIMT form: one THREAD per item, the 32 items of a warp are neighbours in the
@@ -390,13 +460,14 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	// small per-call device arrays: internal results | trace slot of every item | lengths | offsets | public results | scalars
 	size_t offRes = 0, offSlot = alignUp(offRes + (size_t)n * sizeof(GcK1Result), 128), offLens = alignUp(offSlot + (size_t)n * 8, 128), offOffs = alignUp(offLens + (size_t)n * 8, 128);
 	size_t offPub = alignUp(offOffs + (size_t)n * 8, 128), offScalars = alignUp(offPub + (size_t)n * sizeof(gcgpu_ext_result), 128), offItems = offScalars + 128;
-	size_t offShortIdx = alignUp(offItems + (size_t)n * sizeof(gcgpu_ext_item), 128), resEnd = offShortIdx + (size_t)shortIdx.size() * 4;
+	size_t offShortIdx = alignUp(offItems + (size_t)n * sizeof(gcgpu_ext_item), 128), offLast = alignUp(offShortIdx + (size_t)shortIdx.size() * 4, 128), resEnd = offLast + (size_t)n * 4;
 	CUDA_TRY(ctx->resBuf.ensure(resEnd));
 	CUDA_TRY(ctx->arena.ensure(wsTotal));
 	CUDA_TRY(ctx->traceArena.ensure(traceTotal * 8));
 	uint8_t* R = (uint8_t*)ctx->resBuf.p;
 	GcK1Result* dRes = (GcK1Result*)(R + offRes); uint64_t* dSlot = (uint64_t*)(R + offSlot); uint64_t* dLens = (uint64_t*)(R + offLens); uint64_t* dOffs = (uint64_t*)(R + offOffs);
 	gcgpu_ext_result* dPub = (gcgpu_ext_result*)(R + offPub); uint32_t* dOverflow = (uint32_t*)(R + offScalars); uint64_t* dTotal = (uint64_t*)(R + offScalars + 8);
+	int32_t* dLast = (int32_t*)(R + offLast);
 	gcgpu_ext_item* dItems = (gcgpu_ext_item*)(R + offItems); uint32_t* dShortIdx = shortIdx.empty() ? nullptr : (uint32_t*)(R + offShortIdx);
 	CUDA_TRY(cudaMemsetAsync(R + offScalars, 0, 128, ctx->stream));
 	if (nShort) CUDA_TRY(cudaMemcpyAsync(dItems, items, (size_t)n * sizeof(gcgpu_ext_item), cudaMemcpyHostToDevice, ctx->stream));
@@ -421,16 +492,25 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 trades ~150 bytes of spills for 24 warps per SM
 			static const int minBlocks = getenv("GCGPU_K1_LONG_BLOCKS") ? atoi(getenv("GCGPU_K1_LONG_BLOCKS")) : 5;
 			if (minBlocks >= 6)
-				gc_k1_long_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			{
+				gc_k1_long_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+				gc_k1_long_bt_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			}
 			else
-				gc_k1_long_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
+			{
+				gc_k1_long_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+				gc_k1_long_bt_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			}
+			ctx->launches++; // two launches: forward + backtrace
 		}
 		ctx->launches++;
 	}
 	if (nShort)
 	{
-		gc_k1_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
-		ctx->launches++;
+		// lastSlice entries of the short items follow those of the long items
+		gc_k1_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast + nLong);
+		gc_k1_bt_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast + nLong);
+		ctx->launches += 2;
 	}
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -477,8 +557,9 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			CUDA_TRY(cudaMemsetAsync(dOverflow, 0, 4, ctx->stream));
 			uint32_t m = (uint32_t)rd.size();
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-			gc_k1_long_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
-			ctx->launches++;
+			gc_k1_long_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1_long_bt_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			ctx->launches += 2;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 			CUDA_TRY(gcSyncStream(ctx));
