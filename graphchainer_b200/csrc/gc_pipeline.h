@@ -109,7 +109,8 @@ struct GcPipelineParams
 	long long colinearSplitGap = 35;
 	bool tryAllSeeds = true;
 	size_t s1FirstRoundSeeds = 1;   // S1 speculation: seeds extended per read in the first round ...
-	size_t s1LaterRoundSeeds = 8;   // ... and in every later round
+	size_t s1LaterRoundSeeds = 8;   // ... in the second round ...
+	size_t s1TailRoundSeeds = 32;  // ... and from the third round on: few reads get that far, their rounds cost one extension latency each whatever the item count
 };
 
 struct GcPipelineStats
@@ -606,7 +607,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			if (st.done) continue;
 			GC_PROF_SCOPE(2, "s1.collect");
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
-			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : params.s1LaterRoundSeeds;
+			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : (st.round == 1 ? params.s1LaterRoundSeeds : params.s1TailRoundSeeds);
 			st.cands.clear();
 			st.localItems.clear();
 			for (size_t i = st.i; i < seedHits.size() && st.cands.size() < want; i++)
