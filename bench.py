@@ -262,5 +262,17 @@ def main():
     print(json.dumps(line))
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

@@ -61,6 +61,7 @@ struct gcgpu_ctx
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t stream2 = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr; // side stream for kernels that run beside the main one
 	cudaEvent_t evSync = nullptr; // cudaEventBlockingSync: a host thread waiting for its batch sleeps instead of spinning on a core the other batches need
 	gcgpu_params params;
 	uint32_t numNodes = 0;
@@ -312,6 +313,9 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->evSync) cudaEventDestroy(ctx->evSync);
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -338,6 +342,9 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	chk(cudaEventCreate(&ctx->ev0));
 	chk(cudaEventCreate(&ctx->ev1));
 	chk(cudaEventCreateWithFlags(&ctx->evSync, cudaEventBlockingSync | cudaEventDisableTiming));
+	chk(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+	chk(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+	chk(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
 	chk(uploadArray(graph->node_length, N, &ctx->d_nodeLength));
 	chk(uploadArray(graph->node_seq, 2 * (size_t)N, &ctx->d_nodeSeq));
 	chk(uploadArray(graph->in_start, (size_t)N + 1, &ctx->d_inStart));
@@ -489,18 +496,15 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			gc_k1_long_simt_kernel<<<(nLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
 		else
 		{
-			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 trades ~150 bytes of spills for 24 warps per SM
+			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 / 8 trade spills (~130 / ~300 bytes) for 24 / 32 warps per SM
 			static const int minBlocks = getenv("GCGPU_K1_LONG_BLOCKS") ? atoi(getenv("GCGPU_K1_LONG_BLOCKS")) : 5;
-			if (minBlocks >= 6)
-			{
-				gc_k1_long_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-				gc_k1_long_bt_kernel<6><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
-			}
-			else
-			{
-				gc_k1_long_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-				gc_k1_long_bt_kernel<5><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
-			}
+#define GC_K1_LONG_LAUNCH(MB) do { \
+				gc_k1_long_kernel<MB><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast); \
+				gc_k1_long_bt_kernel<MB><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast); } while (0)
+			if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8);
+			else if (minBlocks >= 6) GC_K1_LONG_LAUNCH(6);
+			else GC_K1_LONG_LAUNCH(5);
+#undef GC_K1_LONG_LAUNCH
 			ctx->launches++; // two launches: forward + backtrace
 		}
 		ctx->launches++;
@@ -1175,16 +1179,52 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	}
 	else
 	{
+	// items whose first cutoff already needs more than two 64-row blocks per lane belong to the wide class: they are few and each
+	// is one long dependent pass, so their kernel runs beside the narrow class on a second stream instead of after it
+	uint32_t nWide = 0;
+	{
+		std::vector<GcK3Desc> wide, narrow;
+		for (const GcK3Desc& d : descs)
+		{
+			bool isWide = false;
+			if (d.q > 0 && d.t > 0)
+			{
+				int32_t k = d.kHint < 64 ? 64 : d.kHint;
+				int32_t diff = d.q > d.t ? d.q - d.t : d.t - d.q, mx = d.q > d.t ? d.q : d.t;
+				while (k < diff) k *= 2;
+				int32_t kk = k > mx ? mx : k;
+				int32_t nbl = gc_k3w_blocks_per_lane(d.q, d.t, kk);
+				isWide = nbl > 2 && nbl <= 16;
+			}
+			(isWide ? wide : narrow).push_back(d);
+		}
+		nWide = (uint32_t)wide.size();
+		descs.clear();
+		descs.insert(descs.end(), wide.begin(), wide.end());
+		descs.insert(descs.end(), narrow.begin(), narrow.end());
+	}
 	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
-	gc_k3w_distance_kernel<0><<<(n + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
-	ctx->launches++;
+	if (nWide)
+	{
+		CUDA_TRY(cudaEventRecord(ctx->evFork, ctx->stream));
+		CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+		gc_k3w_distance_kernel<1><<<(nWide + 3) / 4, 128, 0, ctx->stream2>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		CUDA_TRY(cudaEventRecord(ctx->evJoin, ctx->stream2));
+		ctx->launches++;
+	}
+	if (n > nWide)
+	{
+		gc_k3w_distance_kernel<0><<<(n - nWide + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p + nWide, n - nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		ctx->launches++;
+	}
+	if (nWide) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
-	GC_TRACE_MS("k3w distance<0>", n);
+	GC_TRACE_MS("k3w distance<0|1>", n);
 	}
 	// items whose cutoff band outgrew the register budget of the launched class: wider class, then the thread form
 	for (int cls = 1; cls <= 2; cls++)
