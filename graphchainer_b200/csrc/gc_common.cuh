@@ -42,9 +42,15 @@ struct GcGraphView
 	const uint32_t* outNbr;
 	const uint32_t* componentNumber;  // [N] topological rank (unique per node on a DAG)
 	const uint8_t* linearizable;      // [N]
-	// >= 0: the 32 lanes of a warp execute ONE work item in lockstep (same control flow, same values)
-	// and this is the lane index; helpers may then split loop-free lookups across the lanes.
+	// >= 0: a GROUP of coopWidth (32, 16 or 8) adjacent lanes of a warp executes ONE work item in lockstep (same control
+	// flow, same values) and this is the lane's index inside its group; helpers may then split loop-free lookups across the
+	// group.  coopMask = the group's lanes inside the warp, coopShift = its first lane.  Groups of one warp run different
+	// items and diverge freely (independent thread scheduling); they share the warp's registers-per-lane, which is the point:
+	// an item's state is per lane, so a warp of four groups keeps four items resident for the registers of one.
 	int32_t coopLane;
+	int32_t coopWidth;
+	uint32_t coopMask;
+	uint32_t coopShift;
 };
 
 GC_HD int gc_popc(uint64_t x)
@@ -230,19 +236,22 @@ GC_HD int32_t gc_changed_min_score(const GcWord& w, const GcWord& old)
 // Eq masks of one 64-row slice of the read (GraphAlignerBitvectorCommon.h:280-319).
 // `seq` holds one IUPAC bit mask per read base: bit0 A, bit1 C, bit2 G, bit3 T
 // (so 'N' = 15 matches everything, as Common::characterMatch does).
-GC_HD void gc_eq_vector(const uint8_t* seq, int32_t seqLen, int32_t j, uint64_t eq[4], int32_t coopLane = -1)
+GC_HD void gc_eq_vector(const uint8_t* seq, int32_t seqLen, int32_t j, uint64_t eq[4], int32_t coopLane = -1, int32_t coopWidth = 32, uint32_t coopMask = 0xFFFFFFFFu, uint32_t coopShift = 0)
 {
 #if defined(__CUDA_ARCH__)
 	if (coopLane >= 0)
 	{
-		// lane l looks at rows l and 32+l; one ballot per base and half
-		uint32_t c0 = (j + coopLane < seqLen) ? seq[j + coopLane] : 0u;
-		uint32_t c1 = (j + 32 + coopLane < seqLen) ? seq[j + 32 + coopLane] : 0u;
-		for (int b = 0; b < 4; b++)
+		// lane l of a group of W looks at rows l, W+l, 2W+l ...; one ballot per base and W-row stripe
+		const uint32_t laneBits = coopWidth >= 32 ? 0xFFFFFFFFu : ((1u << coopWidth) - 1u);
+		eq[0] = eq[1] = eq[2] = eq[3] = 0;
+		for (int32_t r = 0; r < 64; r += coopWidth)
 		{
-			uint32_t lo = __ballot_sync(0xFFFFFFFFu, (c0 >> b) & 1u);
-			uint32_t hi = __ballot_sync(0xFFFFFFFFu, (c1 >> b) & 1u);
-			eq[b] = (uint64_t)lo | ((uint64_t)hi << 32);
+			uint32_t c = (j + r + coopLane < seqLen) ? seq[j + r + coopLane] : 0u;
+			for (int b = 0; b < 4; b++)
+			{
+				uint32_t m = (__ballot_sync(coopMask, (c >> b) & 1u) >> coopShift) & laneBits;
+				eq[b] |= (uint64_t)m << r;
+			}
 		}
 		return;
 	}

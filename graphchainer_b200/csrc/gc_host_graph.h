@@ -100,7 +100,7 @@ struct GcHostGraph
 		v.outStart = outStart.data(); v.outNbr = outNbr.data();
 		v.componentNumber = componentNumber.data();
 		v.linearizable = linearizable.data();
-		v.coopLane = -1;
+		v.coopLane = -1; v.coopWidth = 32; v.coopMask = 0xFFFFFFFFu; v.coopShift = 0;
 		return v;
 	}
 

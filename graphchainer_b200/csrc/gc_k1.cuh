@@ -93,11 +93,11 @@ GC_HD uint32_t gc_item_node(const GcNodeItem& it) { return it.nodeAndFlag & 0x7F
 GC_HD const GcNodeItem* gc_find_item(const GcGraphView& g, const GcNodeItem* items, uint32_t n, uint32_t node)
 {
 #if defined(__CUDA_ARCH__)
-	if (g.coopLane >= 0 && n <= 32)
+	if (g.coopLane >= 0 && n <= (uint32_t)g.coopWidth)
 	{
-		// one probe: lane k holds the node of item k
+		// one probe: lane k of the group holds the node of item k
 		uint32_t mine = ((uint32_t)g.coopLane < n) ? gc_item_node(items[g.coopLane]) : 0xFFFFFFFFu;
-		uint32_t m = __ballot_sync(0xFFFFFFFFu, mine == node);
+		uint32_t m = __ballot_sync(g.coopMask, mine == node) >> g.coopShift;
 		return m ? &items[__ffs(m) - 1] : nullptr;
 	}
 #endif
@@ -536,7 +536,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				prevN = pm.numItems;
 				previousMinScore = pm.minScore;
 				previousQuitScore = pm.minScore + pm.bandwidth;
-				gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
+				gc_eq_vector(seq, seqLen, j, eq, g.coopLane, g.coopWidth, g.coopMask, g.coopShift);
 				for (uint32_t k = 0; k < prevN; k++)
 				{
 					const GcNodeItem& pn = prevItems[k];
@@ -838,7 +838,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 		int32_t j = (newSlice - 1) * 64;
 		if (newSlice != currentSlice || newNode != currentNode)
 		{
-			if (newSlice != currentSlice) gc_eq_vector(seq, seqLen, j, eq, g.coopLane);
+			if (newSlice != currentSlice) gc_eq_vector(seq, seqLen, j, eq, g.coopLane, g.coopWidth, g.coopMask, g.coopShift);
 			currentSlice = newSlice;
 			currentNode = newNode;
 			const GcNodeItem* me = gc_find_item(g, cur, cm.numItems, currentNode);

@@ -215,17 +215,26 @@ __device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* aren
 	ws.itemCap = d.itemCap;
 	ws.heapCap = d.heapCap;
 }
-template <int MIN_BLOCKS>
+// W = lanes per item (32, 16 or 8): a warp carries 32 / W items, each executed in lock-step by its own group of lanes
+template <int W>
+__device__ __forceinline__ uint32_t gc_k1_group_setup(GcGraphView& g)
+{
+	g.coopLane = (int32_t)(threadIdx.x & (W - 1));
+	g.coopWidth = W;
+	g.coopShift = (threadIdx.x & 31u) & ~(uint32_t)(W - 1);
+	g.coopMask = (W >= 32 ? 0xFFFFFFFFu : ((1u << W) - 1u)) << g.coopShift;
+	return (blockIdx.x * blockDim.x + threadIdx.x) / W;
+}
+template <int MIN_BLOCKS, int W>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
-	__shared__ GcWord colsShared[4][64];
-	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	__shared__ GcWord colsShared[128 / W][64];
+	uint32_t t = gc_k1_group_setup<W>(g);
 	if (t >= n) return;
-	g.coopLane = (int32_t)(threadIdx.x & 31);
 	GcK1Desc d = descs[t];
 	GcK1Workspace ws;
-	gc_k1_workspace(d, arena, colsShared[threadIdx.x >> 5], ws);
+	gc_k1_workspace(d, arena, colsShared[threadIdx.x / W], ws);
 	GcK1Result res;
 	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
 	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
@@ -235,19 +244,18 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView
 	lastSlice[t] = last;
 	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
 }
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, int W>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
 {
-	__shared__ GcWord colsShared[4][64];
-	uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	__shared__ GcWord colsShared[128 / W][64];
+	uint32_t t = gc_k1_group_setup<W>(g);
 	if (t >= n) return;
-	g.coopLane = (int32_t)(threadIdx.x & 31);
 	GcK1Desc d = descs[t];
 	GcK1Result res = results[d.resultIndex];
 	if (res.status != GC_OK) return;
 	GcK1Workspace ws;
-	gc_k1_workspace(d, arena, colsShared[threadIdx.x >> 5], ws);
+	gc_k1_workspace(d, arena, colsShared[threadIdx.x / W], ws);
 	gc_k1_backtrace(g, seq + d.seqOff, d.seqLen, ws, lastSlice[t], traceArena + d.traceOff, d.traceCap, res);
 	results[d.resultIndex] = res;
 }
@@ -377,7 +385,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.numNodes = N;
 	ctx->view.nodeLength = ctx->d_nodeLength; ctx->view.nodeSeq = ctx->d_nodeSeq;
 	ctx->view.inStart = ctx->d_inStart; ctx->view.inNbr = ctx->d_inNbr; ctx->view.outStart = ctx->d_outStart; ctx->view.outNbr = ctx->d_outNbr;
-	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1;
+	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1; ctx->view.coopWidth = 32; ctx->view.coopMask = 0xFFFFFFFFu; ctx->view.coopShift = 0;
 	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
 	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
 	*out = ctx;
@@ -498,12 +506,16 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		{
 			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 / 8 trade spills (~130 / ~300 bytes) for 24 / 32 warps per SM
 			static const int minBlocks = getenv("GCGPU_K1_LONG_BLOCKS") ? atoi(getenv("GCGPU_K1_LONG_BLOCKS")) : 5;
-#define GC_K1_LONG_LAUNCH(MB) do { \
-				gc_k1_long_kernel<MB><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast); \
-				gc_k1_long_bt_kernel<MB><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast); } while (0)
-			if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8);
-			else if (minBlocks >= 6) GC_K1_LONG_LAUNCH(6);
-			else GC_K1_LONG_LAUNCH(5);
+#define GC_K1_LONG_LAUNCH(MB, W) do { const uint32_t perBlock = 128 / W; \
+				gc_k1_long_kernel<MB, W><<<(nLong + perBlock - 1) / perBlock, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast); \
+				gc_k1_long_bt_kernel<MB, W><<<(nLong + perBlock - 1) / perBlock, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast); } while (0)
+			// lanes per item: GCGPU_K1_LONG_WIDTH = 32 | 16 | 8
+			static const int width = getenv("GCGPU_K1_LONG_WIDTH") ? atoi(getenv("GCGPU_K1_LONG_WIDTH")) : 32;
+			if (width <= 8) { if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 8); else GC_K1_LONG_LAUNCH(5, 8); }
+			else if (width <= 16) { if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 16); else GC_K1_LONG_LAUNCH(5, 16); }
+			else if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 32);
+			else if (minBlocks >= 6) GC_K1_LONG_LAUNCH(6, 32);
+			else GC_K1_LONG_LAUNCH(5, 32);
 #undef GC_K1_LONG_LAUNCH
 			ctx->launches++; // two launches: forward + backtrace
 		}
@@ -561,8 +573,8 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			CUDA_TRY(cudaMemsetAsync(dOverflow, 0, 4, ctx->stream));
 			uint32_t m = (uint32_t)rd.size();
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-			gc_k1_long_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-			gc_k1_long_bt_kernel<5><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			gc_k1_long_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1_long_bt_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
 			ctx->launches += 2;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -39,7 +39,7 @@ extern "C" int gcgpu_create(int, const gcgpu_graph* g, const gcgpu_params* p, gc
 	gcgpu_ctx* c = new gcgpu_ctx();
 	c->view.numNodes = g->num_nodes; c->view.nodeLength = g->node_length; c->view.nodeSeq = g->node_seq;
 	c->view.inStart = g->in_start; c->view.inNbr = g->in_nbr; c->view.outStart = g->out_start; c->view.outNbr = g->out_nbr;
-	c->view.componentNumber = g->component_number; c->view.linearizable = g->linearizable; c->view.coopLane = -1;
+	c->view.componentNumber = g->component_number; c->view.linearizable = g->linearizable; c->view.coopLane = -1; c->view.coopWidth = 32; c->view.coopMask = 0xFFFFFFFFu; c->view.coopShift = 0;
 	c->mpc.compMap = g->comp_map; c->mpc.compIdx = g->comp_idx; c->mpc.compStart = g->comp_start; c->mpc.topoIds = g->topo_ids;
 	c->mpc.pathsStart = g->paths_start; c->mpc.pathsK = g->paths_k; c->mpc.backStart = g->back_start; c->mpc.backNode = g->back_node; c->mpc.backK = g->back_k;
 	c->vt = gcMakeViterbiTables();

@@ -85,3 +85,26 @@ def test_gpu_pipeline_matches_reference_on_ultralong_reads(tmp_path):
     assert len(b) == 10
     diffs = gam.diff_gam(a, b)
     assert not diffs, diffs
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_matches_reference_on_high_width_hifi_reads(tmp_path):
+    """BASELINE config-5 shape: extra haplotype alleles (MPC width 4), 20 kb reads at 1 % error, fragments every 18 bp
+    (what --sampling-step 0.5 sets: overlapping fragments, almost all anchored, the I-type chaining term matters);
+    unmodified reference live on the CPU vs the GPU pipeline, decoded GAM records compared field by field."""
+    if not (os.path.exists(REFBIN) and os.path.exists(REFDUMP)):
+        pytest.skip("oracle/_ref not built")
+    from graphchainer_b200 import synth
+    g = synth.SynthGraph(400_000, seed=71, extra_alleles=2, mean_spacing=25)
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    with open(gfa, "w") as f:
+        f.write(g.gfa())
+    synth.write_fasta(fa, synth.simulate_reads(g, 24, 20_000, 0.01, seed=72, novel_insertion_frac=0.25))
+    idx, ref_gam, out = str(tmp_path / "x.gcidx"), str(tmp_path / "ref.gam"), str(tmp_path / "out.gam")
+    subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "--gc-index", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([REFBIN, "-t", str(os.cpu_count() or 8), "-g", gfa, "-f", fa, "-a", ref_gam, "--colinear-split-gap", "18"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8)), "--sampling-step", "0.5"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    a, b = gam.read_gam(out), gam.read_gam(ref_gam)
+    assert len(b) == 24
+    diffs = gam.diff_gam(a, b)
+    assert not diffs, diffs
