@@ -321,6 +321,85 @@ GC_HD bool gc_k3w_leaf_traceback(const GcK3wPass& p, int32_t NB, const GcK3Frame
 
 GC_HD int32_t gc_k3w_round_nb_path(int32_t nb) { return nb <= 1 ? 1 : nb <= 2 ? 2 : nb <= 4 ? 4 : nb <= 8 ? 8 : 0; }
 
+// One frame of the recursion: either a leaf (its edit operations are appended at ops[nOps..]) or a Hirschberg split
+// (two child frames are returned: ch[0] = upper-left, to be aligned FIRST, ch[1] = lower-right).  The depth-first
+// driver below and the level-parallel kernel (gcgpu.cu: one warp per frame, one launch per recursion level) share it.
+template <class Exec>
+GC_HD bool gc_k3w_path_frame(Exec& ex, const GcK3wPathWorkspace& w, const uint8_t* target, const GcK3Frame& f, uint8_t* ops, uint32_t& nOps, uint32_t opsCap, uint64_t& work,
+	GcK3Frame ch[2], int32_t& nChildren)
+{
+	nChildren = 0;
+	if (f.q == 0 || f.t == 0)
+	{
+		uint32_t n = (uint32_t)(f.q + f.t);
+		if (nOps + n > opsCap) return false;
+		if (ex.leader()) for (uint32_t x = 0; x < n; x++) ops[nOps + x] = f.q == 0 ? 2 : 1;
+		nOps += n;
+		return true;
+	}
+	int32_t q = f.q, t = f.t, k = f.best;
+	int32_t mx = q > t ? q : t;
+	if (k > mx) k = mx;
+	int32_t NB = gc_k3w_round_nb_path(gc_k3w_blocks_per_lane(q, t, k));
+	if (NB == 0 || NB > w.maxNB) return false;
+	int64_t nb = (q + 63) / 64;
+	int64_t alignmentDataSize = (2LL * 8 + 4) * nb * t + 2LL * 4 * t;
+	if (alignmentDataSize < 1024 * 1024)
+	{
+		if ((uint64_t)nb * (uint64_t)t > w.storeCap) return false;
+		GcK3wPass p = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, t - 1, NB);
+		p.store = w.store; p.storeStride = (int32_t)nb;
+		work += ex.pass(p, NB, w.blocksA);
+		uint32_t n2 = nOps;
+		bool ok = true;
+		if (ex.leader()) ok = gc_k3w_leaf_traceback(p, NB, f, ops, n2, opsCap);
+		ok = ex.fromLeader((uint32_t)ok) != 0;
+		nOps = ex.fromLeader(n2);
+		return ok;
+	}
+	// ---- Hirschberg split (edlib.cpp:1234-1399)
+	int32_t leftW = t / 2, rightW = t - leftW;
+	GcK3wPass pf = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, leftW - 1, NB);
+	work += ex.pass(pf, NB, w.blocksA);
+	int32_t rqOff = w.qTotal - f.qOff - q;
+	GcK3wPass pr = gc_k3w_make_pass(w.rpeq, w.nbTotal, rqOff, q, target, (int64_t)f.tOff + t - 1, -1, t, k, rightW - 1, NB);
+	work += ex.pass(pr, NB, w.blocksB);
+	int32_t lfb, llb, rfb, rlb;
+	gc_k3w_stop_blocks(pf, NB, lfb, llb);
+	gc_k3w_stop_blocks(pr, NB, rfb, rlb);
+	int32_t row = ex.firstSplitRow(w.blocksA, lfb, llb, w.blocksB, rfb, rlb, q, f.best);
+	const int32_t INF = 1 << 29;
+	int32_t leftScore = -1, rightScore = -1;
+	if (row >= 0)
+	{
+		leftScore = gc_k3_cell(w.blocksA[row >> 6], row);
+		int32_t rr = q - 1 - (row + 1);
+		rightScore = gc_k3_cell(w.blocksB[rr >> 6], rr);
+	}
+	else
+	{
+		row = -2;
+		{
+			int32_t rr = q - 1; int32_t b = rr >> 6;
+			int32_t rs = (b < rfb || b > rlb) ? INF : gc_k3_cell(w.blocksB[b], rr);
+			if (leftW + rs == f.best) { row = -1; leftScore = leftW; rightScore = rs; }
+		}
+		if (row == -2)
+		{
+			int32_t b = (q - 1) >> 6;
+			int32_t ls = (b < lfb || b > llb) ? INF : gc_k3_cell(w.blocksA[b], q - 1);
+			if (ls + rightW == f.best) { row = q - 1; leftScore = ls; rightScore = rightW; }
+		}
+		if (row == -2) return false;
+	}
+	int32_t ulHeight = row + 1, lrHeight = q - ulHeight;
+	ch[0].qOff = f.qOff; ch[0].q = ulHeight; ch[0].tOff = f.tOff; ch[0].t = leftW; ch[0].best = leftScore;
+	ch[1].qOff = f.qOff + ulHeight; ch[1].q = lrHeight; ch[1].tOff = f.tOff + leftW; ch[1].t = rightW; ch[1].best = rightScore;
+	nChildren = 2;
+	return true;
+}
+
+// depth-first driver: one warp aligns one pair from start to end
 template <class Exec>
 GC_HD bool gc_k3w_path(Exec& ex, const GcK3wPathWorkspace& w, const uint8_t* target, int32_t best, uint8_t* ops, uint32_t& nOps, uint32_t opsCap, uint64_t& work)
 {
@@ -333,81 +412,19 @@ GC_HD bool gc_k3w_path(Exec& ex, const GcK3wPathWorkspace& w, const uint8_t* tar
 	{
 		GcK3Frame f = w.stack[--sp];
 		ex.sync(); // every lane has read the frame before the leader may overwrite the slot
-		if (f.q == 0 || f.t == 0)
+		GcK3Frame ch[2]; int32_t nch = 0;
+		if (!gc_k3w_path_frame(ex, w, target, f, ops, nOps, opsCap, work, ch, nch)) return false;
+		if (nch)
 		{
-			uint32_t n = (uint32_t)(f.q + f.t);
-			if (nOps + n > opsCap) return false;
-			if (ex.leader()) for (uint32_t x = 0; x < n; x++) ops[nOps + x] = f.q == 0 ? 2 : 1;
-			nOps += n;
-			continue;
-		}
-		int32_t q = f.q, t = f.t, k = f.best;
-		int32_t mx = q > t ? q : t;
-		if (k > mx) k = mx;
-		int32_t NB = gc_k3w_round_nb_path(gc_k3w_blocks_per_lane(q, t, k));
-		if (NB == 0 || NB > w.maxNB) return false;
-		int64_t nb = (q + 63) / 64;
-		int64_t alignmentDataSize = (2LL * 8 + 4) * nb * t + 2LL * 4 * t;
-		if (alignmentDataSize < 1024 * 1024)
-		{
-			if ((uint64_t)nb * (uint64_t)t > w.storeCap) return false;
-			GcK3wPass p = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, t - 1, NB);
-			p.store = w.store; p.storeStride = (int32_t)nb;
-			work += ex.pass(p, NB, w.blocksA);
-			uint32_t n2 = nOps;
-			bool ok = true;
-			if (ex.leader()) ok = gc_k3w_leaf_traceback(p, NB, f, ops, n2, opsCap);
-			ok = ex.fromLeader((uint32_t)ok) != 0;
-			nOps = ex.fromLeader(n2);
-			if (!ok) return false;
-			continue;
-		}
-		// ---- Hirschberg split (edlib.cpp:1234-1399)
-		int32_t leftW = t / 2, rightW = t - leftW;
-		GcK3wPass pf = gc_k3w_make_pass(w.peq, w.nbTotal, f.qOff, q, target, f.tOff, 1, t, k, leftW - 1, NB);
-		work += ex.pass(pf, NB, w.blocksA);
-		int32_t rqOff = w.qTotal - f.qOff - q;
-		GcK3wPass pr = gc_k3w_make_pass(w.rpeq, w.nbTotal, rqOff, q, target, (int64_t)f.tOff + t - 1, -1, t, k, rightW - 1, NB);
-		work += ex.pass(pr, NB, w.blocksB);
-		int32_t lfb, llb, rfb, rlb;
-		gc_k3w_stop_blocks(pf, NB, lfb, llb);
-		gc_k3w_stop_blocks(pr, NB, rfb, rlb);
-		int32_t row = ex.firstSplitRow(w.blocksA, lfb, llb, w.blocksB, rfb, rlb, q, f.best);
-		const int32_t INF = 1 << 29;
-		int32_t leftScore = -1, rightScore = -1;
-		if (row >= 0)
-		{
-			leftScore = gc_k3_cell(w.blocksA[row >> 6], row);
-			int32_t rr = q - 1 - (row + 1);
-			rightScore = gc_k3_cell(w.blocksB[rr >> 6], rr);
-		}
-		else
-		{
-			row = -2;
+			if (sp + 2 > w.stackCap) return false;
+			if (ex.leader())
 			{
-				int32_t rr = q - 1; int32_t b = rr >> 6;
-				int32_t rs = (b < rfb || b > rlb) ? INF : gc_k3_cell(w.blocksB[b], rr);
-				if (leftW + rs == f.best) { row = -1; leftScore = leftW; rightScore = rs; }
+				w.stack[sp] = ch[1];     // processed after the upper-left part
+				w.stack[sp + 1] = ch[0];
 			}
-			if (row == -2)
-			{
-				int32_t b = (q - 1) >> 6;
-				int32_t ls = (b < lfb || b > llb) ? INF : gc_k3_cell(w.blocksA[b], q - 1);
-				if (ls + rightW == f.best) { row = q - 1; leftScore = ls; rightScore = rightW; }
-			}
-			if (row == -2) return false;
+			sp += 2;
+			ex.sync();
 		}
-		int32_t ulHeight = row + 1, lrHeight = q - ulHeight;
-		if (sp + 2 > w.stackCap) return false;
-		if (ex.leader())
-		{
-			GcK3Frame lr; lr.qOff = f.qOff + ulHeight; lr.q = lrHeight; lr.tOff = f.tOff + leftW; lr.t = rightW; lr.best = rightScore;
-			GcK3Frame ul; ul.qOff = f.qOff; ul.q = ulHeight; ul.tOff = f.tOff; ul.t = leftW; ul.best = leftScore;
-			w.stack[sp] = lr; // processed after ul
-			w.stack[sp + 1] = ul;
-		}
-		sp += 2;
-		ex.sync();
 	}
 	return true;
 }

@@ -1124,6 +1124,112 @@ __global__ void __launch_bounds__(128) gc_k3w_path_kernel(const uint8_t* __restr
 	}
 }
 
+// ---- edit paths, level-parallel form.  The Hirschberg recursion of one alignment is a tree whose frames of one depth are
+// independent: instead of one warp walking the tree depth-first (gc_k3w_path_kernel: 20 ms for 48 alignments, 6 % of the SMs
+// busy), every recursion LEVEL is one launch with one warp per frame of every alignment.  A frame owns the slice
+// [opsOff, opsOff + q + t) of the operation buffer (the slices of its two children tile it exactly), a leaf writes its
+// operations at the start of its slice, and a final pass squeezes the unused bytes (0xFF) out of every alignment's slice.
+struct GcK3LFrame { GcK3Frame f; uint32_t item; uint32_t pad; uint64_t opsOff; };
+
+// Peq of the query and of the reversed query, once per alignment (warp per alignment)
+__global__ void gc_k3l_peq_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* itemWs)
+{
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int lane = threadIdx.x & 31;
+	if (w >= n) return;
+	GcK3Desc d = descs[w];
+	int32_t q = d.q;
+	int32_t nb = (q + 63) / 64; if (nb < 1) nb = 1;
+	uint64_t* peq = (uint64_t*)(itemWs + d.wsOff);
+	uint64_t* rpeq = peq + 4 * (size_t)nb;
+	const uint8_t* query = seq + d.qOff;
+	for (int32_t b = lane; b < nb; b += 32)
+	{
+		uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+		int32_t lim = q - b * 64; if (lim > 64) lim = 64;
+		for (int32_t i = 0; i < lim; i++)
+		{
+			uint8_t c = query[b * 64 + i];
+			uint8_t rc = query[q - 1 - (b * 64 + i)];
+			uint64_t bit = 1ULL << i;
+			e0 |= c == 0 ? bit : 0; e1 |= c == 1 ? bit : 0; e2 |= c == 2 ? bit : 0; e3 |= c == 3 ? bit : 0;
+			f0 |= rc == 0 ? bit : 0; f1 |= rc == 1 ? bit : 0; f2 |= rc == 2 ? bit : 0; f3 |= rc == 3 ? bit : 0;
+		}
+		peq[b] = e0; peq[nb + b] = e1; peq[2 * (size_t)nb + b] = e2; peq[3 * (size_t)nb + b] = e3;
+		rpeq[b] = f0; rpeq[nb + b] = f1; rpeq[2 * (size_t)nb + b] = f2; rpeq[3 * (size_t)nb + b] = f3;
+	}
+}
+
+// one recursion level: persistent warps take frames from a counter; children go to the next level's frame list
+__global__ void __launch_bounds__(128) gc_k3l_level_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, const GcK3LFrame* __restrict__ in, uint32_t nIn,
+	GcK3LFrame* outFrames, uint32_t outCap, uint32_t* counters, uint8_t* slots, size_t slotBytes, int32_t maxQ, const uint8_t* itemWs, uint8_t* opsArena, GcK3Out* out)
+{
+	int lane = threadIdx.x & 31;
+	uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint8_t* base = slots + (size_t)slot * slotBytes;
+	size_t nbMax = (size_t)(maxQ + 63) / 64 + 1;
+	GcK3Block* blocksA = (GcK3Block*)base;
+	GcK3Block* blocksB = blocksA + nbMax;
+	GcK3Block* store = blocksB + nbMax;
+	while (true)
+	{
+		uint32_t w = 0;
+		if (lane == 0) w = atomicAdd(&counters[0], 1u);
+		w = __shfl_sync(0xFFFFFFFFu, w, 0);
+		if (w >= nIn) return;
+		GcK3LFrame fr = in[w];
+		GcK3Desc d = descs[fr.item];
+		int32_t nb = (d.q + 63) / 64; if (nb < 1) nb = 1;
+		GcK3wPathWorkspace ws;
+		ws.peq = (const uint64_t*)(itemWs + d.wsOff); ws.rpeq = ws.peq + 4 * (size_t)nb; ws.nbTotal = nb; ws.qTotal = d.q; ws.tTotal = d.t;
+		ws.blocksA = blocksA; ws.blocksB = blocksB; ws.store = store; ws.storeCap = K3W_STORE_CAP; ws.stack = nullptr; ws.stackCap = 0; ws.maxNB = 8;
+		GcK3wDeviceExec ex; ex.lane = lane;
+		uint64_t work = 0; uint32_t nOps = 0;
+		GcK3Frame ch[2]; int32_t nch = 0;
+		bool ok = gc_k3w_path_frame(ex, ws, seq + d.tOff, fr.f, opsArena + fr.opsOff, nOps, (uint32_t)(fr.f.q + fr.f.t), work, ch, nch);
+		if (lane == 0)
+		{
+			atomicAdd((unsigned long long*)&out[d.resultIndex].blocks, (unsigned long long)work);
+			if (!ok) out[d.resultIndex].pad = 1u; // the alignment is redone by the depth-first kernel / the thread form
+			else if (nch)
+			{
+				uint32_t idx = atomicAdd(&counters[1], 2u);
+				if (idx + 2 > outCap) out[d.resultIndex].pad = 1u;
+				else
+				{
+					GcK3LFrame a; a.f = ch[0]; a.item = fr.item; a.pad = 0; a.opsOff = fr.opsOff;
+					GcK3LFrame b; b.f = ch[1]; b.item = fr.item; b.pad = 0; b.opsOff = fr.opsOff + (uint64_t)(ch[0].q + ch[0].t);
+					outFrames[idx] = a; outFrames[idx + 1] = b;
+				}
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// squeeze the 0xFF filler out of every alignment's slice (warp per alignment, in place: the write position never passes the read position)
+__global__ void gc_k3l_compact_kernel(const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* opsArena, GcK3Out* out)
+{
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t lane = threadIdx.x & 31;
+	if (w >= n) return;
+	GcK3Desc d = descs[w];
+	if (out[d.resultIndex].pad == 1u) return;
+	uint8_t* base = opsArena + d.opsOff;
+	uint32_t cap = (uint32_t)(d.q + d.t), dst = 0;
+	for (uint32_t tile = 0; tile < cap; tile += 32)
+	{
+		uint32_t i = tile + lane;
+		uint8_t c = i < cap ? base[i] : (uint8_t)0xFF;
+		bool valid = c != 0xFF;
+		uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+		if (valid) base[dst + __popc(m & ((1u << lane) - 1u))] = c;
+		dst += __popc(m);
+		__syncwarp();
+	}
+	if (lane == 0) out[d.resultIndex].opsLen = dst;
+}
+
 struct GcByteCopyDesc { uint64_t src; uint64_t dst; uint32_t len; uint32_t pad; };
 __global__ void gc_bytes_gather_kernel(const GcByteCopyDesc* __restrict__ descs, uint32_t n, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst)
 {
@@ -1287,14 +1393,79 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			if (it.query_len > maxQ) maxQ = it.query_len;
 		}
 		uint32_t m = (uint32_t)pd.size();
+		CUDA_TRY(ctx->traceArena.ensure(opsTotal + 16));
+		static const bool levelForm = !(getenv("GCGPU_K3_PATH_LEVELS") && atoi(getenv("GCGPU_K3_PATH_LEVELS")) == 0);
+		std::vector<GcK3Desc> dfs; // alignments for the depth-first kernel: all of them, or the ones the level form gave up on
+		if (levelForm)
+		{
+			// per alignment: Peq + reversed Peq; per resident warp: two block columns + the leaf store
+			size_t itemWsTotal = 0; uint64_t frameCap = 4096;
+			for (GcK3Desc& d : pd)
+			{
+				size_t nb = (size_t)(d.q + 63) / 64 + 1;
+				d.wsOff = itemWsTotal; itemWsTotal += alignUp(2 * 4 * nb * 8, 128);
+				uint64_t leaves = ((uint64_t)nb * (uint64_t)d.t) / (K3W_STORE_CAP / 4) + 2, p2 = 1;
+				while (p2 < leaves) p2 <<= 1;
+				frameCap += 4 * p2 + 8;
+			}
+			size_t nbMax = (size_t)(maxQ + 63) / 64 + 1;
+			size_t slotBytes = alignUp(2 * nbMax * sizeof(GcK3Block) + (size_t)K3W_STORE_CAP * sizeof(GcK3Block) + 64, 128);
+			const uint32_t ctasMax = 148 * 2;
+			size_t slotsTotal = slotBytes * ctasMax * 4;
+			CUDA_TRY(ctx->arena.ensure(slotsTotal + 256 + itemWsTotal));
+			uint32_t* counters = (uint32_t*)((uint8_t*)ctx->arena.p + slotsTotal);
+			uint8_t* itemWs = (uint8_t*)ctx->arena.p + slotsTotal + 256;
+			CUDA_TRY(ctx->descBuf.ensure(pd.size() * sizeof(GcK3Desc)));
+			CUDA_TRY(ctx->copyDesc.ensure(2 * frameCap * sizeof(GcK3LFrame)));
+			GcK3LFrame* frames[2] = { (GcK3LFrame*)ctx->copyDesc.p, (GcK3LFrame*)ctx->copyDesc.p + frameCap };
+			std::vector<GcK3LFrame> f0(m);
+			for (uint32_t k = 0; k < m; k++) { f0[k].f.qOff = 0; f0[k].f.q = pd[k].q; f0[k].f.tOff = 0; f0[k].f.t = pd[k].t; f0[k].f.best = pd[k].best; f0[k].item = k; f0[k].pad = 0; f0[k].opsOff = pd[k].opsOff; }
+			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(cudaMemcpyAsync(frames[0], f0.data(), (size_t)m * sizeof(GcK3LFrame), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(cudaMemsetAsync(ctx->traceArena.p, 0xFF, opsTotal, ctx->stream));
+			gc_k3l_peq_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, itemWs);
+			ctx->launches++;
+			uint32_t nIn = m; int cur = 0, levels = 0;
+			while (nIn > 0)
+			{
+				if (++levels > 64) return setError(GCGPU_ERR_INTERNAL, "gcgpu_nw: edit path recursion deeper than 64 levels");
+				CUDA_TRY(cudaMemsetAsync(counters, 0, 8, ctx->stream));
+				uint32_t ctas = std::min<uint32_t>((nIn + 3) / 4, ctasMax);
+				gc_k3l_level_kernel<<<ctas, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, frames[cur], nIn, frames[cur ^ 1], (uint32_t)frameCap, counters,
+					(uint8_t*)ctx->arena.p, slotBytes, maxQ, itemWs, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
+				ctx->launches++;
+				CUDA_TRY(cudaGetLastError());
+				uint32_t cnt[2] = { 0, 0 };
+				CUDA_TRY(cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+				CUDA_TRY(gcSyncStream(ctx));
+				nIn = std::min<uint64_t>(cnt[1], frameCap);
+				cur ^= 1;
+			}
+			gc_k3l_compact_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
+			ctx->launches++;
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+			CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(gcSyncStream(ctx));
+			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+			ctx->lastKernelMs += ms;
+			if (g_trace) fprintf(stderr, "[gcgpu] %-28s n=%-8u %.3f ms (%d levels)\n", "k3 path, level-parallel", (unsigned)m, ms, levels);
+			for (const GcK3Desc& d : pd) if (hout[d.resultIndex].pad == 1) { GcK3Desc e = d; e.wsOff = 0; dfs.push_back(e); }
+		}
+		else dfs = pd;
+		if (!dfs.empty())
+		{
+		m = (uint32_t)dfs.size();
+		for (const GcK3Desc& d : dfs) { hout[d.resultIndex].pad = 0; hout[d.resultIndex].opsLen = 0; }
+		CUDA_TRY(cudaMemcpyAsync(ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
 		// persistent warps: one workspace slot per resident warp, items fetched from a counter (longest first)
 		uint32_t ctas = std::min<uint32_t>((m + 3) / 4, 148 * 4);
 		size_t slotBytes = k3wPathSlotBytes(maxQ);
 		size_t slotsTotal = slotBytes * ctas * 4;
 		CUDA_TRY(ctx->arena.ensure(slotsTotal + 256));
-		CUDA_TRY(ctx->traceArena.ensure(opsTotal + 16));
-		CUDA_TRY(ctx->descBuf.ensure(pd.size() * sizeof(GcK3Desc)));
-		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(ctx->descBuf.ensure(dfs.size() * sizeof(GcK3Desc)));
+		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, dfs.data(), dfs.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 		uint32_t* counter = (uint32_t*)((uint8_t*)ctx->arena.p + slotsTotal);
 		CUDA_TRY(cudaMemsetAsync(counter, 0, 4, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1307,9 +1478,10 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
 		GC_TRACE_MS("k3w path", m);
+		}
 		// items the warp form gave up on (band beyond its register budget): thread form
 		std::vector<GcK3Desc> rd;
-		for (const GcK3Desc& d : pd) if (hout[d.resultIndex].pad == 1) rd.push_back(d);
+		for (const GcK3Desc& d : dfs) if (hout[d.resultIndex].pad == 1) rd.push_back(d);
 		if (!rd.empty())
 		{
 			size_t ws = 0;
