@@ -938,12 +938,16 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
 			// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a
 			// starting point -- the kernel doubles the cutoff until the pass succeeds, like edlib does from 64.
-			int32_t kHint = 0;
+			int32_t kHint = 0, clcHint = (int32_t)(reads[r].sequence.size() / 5);
 			if (needGa)
 			{
+				// the whole-read alignment IS a global alignment of (its padded path string, read): its score + the unaligned read
+				// ends + the padding of the first and last node (< 2 x 64 graph characters, traceToPoses) bounds the distance from
+				// above, so one pass at that cutoff always succeeds
 				const GcAlnItem& a0 = longAlns[r][0];
 				size_t ub = a0.alignmentScore + a0.alignmentStart + (reads[r].sequence.size() - a0.alignmentEnd);
-				if (ub <= reads[r].sequence.size() / 4) kHint = (int32_t)ub;
+				kHint = (int32_t)std::min<size_t>(ub + 130, (size_t)1 << 30);
+				clcHint = (int32_t)std::min<size_t>(ub + ub * 3 / 10, reads[r].sequence.size() / 5);
 			}
 			if (needGa)
 			{
@@ -955,7 +959,10 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			if (needClc)
 			{
 				gcgpu_nw_item it; it.query_offset = total; it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
-				it.k_hint = kHint + (kHint * 3) / 10; it.want_path = 0; // the chained path usually costs 5-40 % more than the whole-read alignment
+				// the chained path usually costs 5-40 % more than the whole-read alignment; the first guess is capped at a fifth of
+				// the read (the widest band the two-blocks-per-lane class holds for 10 kb reads) and is also what a read without a
+				// whole-read alignment starts from (edlib's 64 would cost five doubling passes before the answer fits)
+				it.k_hint = clcHint; it.want_path = 0;
 				total += pathSeq[r].size();
 				clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 			}
