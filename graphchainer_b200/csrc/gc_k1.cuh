@@ -468,6 +468,10 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 	int32_t nodeMin = 0, prevStart = 0;
 	uint32_t nodeMinOffset = 0;
 	bool prevExists = false;
+	// out-neighbours of the node in flight with their queue keys: requested when the node is popped, consumed when its end
+	// column is pushed -- the three dependent loads (CSR range, neighbour, component number) complete under the column loop
+	uint32_t outBegin = 0, outEnd = 0;
+	uint64_t outKey[3] = { 0, 0, 0 };
 	bool running = numSlices > 0;
 	while (running)
 	{
@@ -502,10 +506,12 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				if (newEndMinScore <= currentMinScoreAtEndRow + bandwidth)
 				{
 					flag = 0x80000000u;
-					for (uint32_t e = g.outStart[node]; e < g.outStart[node + 1]; e++)
+					for (uint32_t e = outBegin; e < outEnd; e++)
 					{
-						uint32_t nb = g.outNbr[e];
-						if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, ((uint64_t)g.componentNumber[nb] << 32) | nb)) { status = GC_OVERFLOW_HEAP; running = false; break; }
+						uint64_t pushKey;
+						if (e - outBegin < 3) pushKey = outKey[e - outBegin];
+						else { uint32_t nb = g.outNbr[e]; pushKey = ((uint64_t)g.componentNumber[nb] << 32) | nb; }
+						if (!gc_heap_push(ws.heap, heapSize, ws.heapCap, pushKey)) { status = GC_OVERFLOW_HEAP; running = false; break; }
 					}
 				}
 				item.nodeAndFlag = node | flag;
@@ -577,6 +583,16 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			if (key == lastKey) continue;
 			lastKey = key;
 			node = (uint32_t)key;
+			outBegin = g.outStart[node]; outEnd = g.outStart[node + 1];
+			#pragma unroll
+			for (uint32_t i = 0; i < 3; i++)
+				if (outBegin + i < outEnd) { uint32_t nb = g.outNbr[outBegin + i]; outKey[i] = ((uint64_t)g.componentNumber[nb] << 32) | nb; }
+			// everything the visit reads about the node itself, requested together (one memory round trip instead of a chain)
+			const uint32_t inBegin = g.inStart[node], inEnd = g.inStart[node + 1];
+			const uint32_t nodeLen = g.nodeLength[node];
+			const bool nodeLinearizable = g.linearizable[node] != 0;
+			const int firstBase = (int)(g.nodeSeq[2 * (uint64_t)node] & 3);
+			const uint32_t firstIn = inBegin < inEnd ? g.inNbr[inBegin] : 0;
 			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, node);
 			prevExists = prevItem != nullptr;
 			prevStart = prevExists ? prevItem->startScore : 0;
@@ -591,9 +607,9 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				if (j > 0)
 				{
 					if (prevItem->minScore > previousQuitScore) seeded = false;
-					else if (g.linearizable[node])
+					else if (nodeLinearizable)
 					{
-						uint32_t nb = g.inNbr[g.inStart[node]];
+						uint32_t nb = firstIn;
 						const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
 						if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) seeded = false;
 					}
@@ -604,10 +620,10 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				w.VP = ~0ULL; w.VN = 0; w.scoreEnd = prevStart + 64; // getSourceSliceFromScore
 				hasWs = true;
 			}
-			uint64_t Eq0 = eq[gc_node_base(g, node, 0)];
-			for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
+			uint64_t Eq0 = eq[firstBase];
+			for (uint32_t e = inBegin; e < inEnd; e++)
 			{
-				uint32_t p = g.inNbr[e];
+				uint32_t p = e == inBegin ? firstIn : g.inNbr[e];
 				const GcNodeItem* pit = gc_find_item(g, curItems, curN, p);
 				if (!pit || !(pit->nodeAndFlag & 0x80000000u)) continue;
 				GcWord inc = gc_item_end(*pit);
@@ -638,7 +654,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				w = gc_merge(w, src);
 			}
 			if (itemsUsed >= ws.itemCap) { status = GC_OVERFLOW_ITEMS; running = false; break; }
-			uint32_t len = g.nodeLength[node];
+			uint32_t len = nodeLen;
 			columns += len;
 			pending = true;
 			if (len > 1) break; // to the column steps
