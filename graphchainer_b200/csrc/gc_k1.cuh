@@ -68,6 +68,10 @@ struct GcK1Workspace
 	GcWord* cols;          // [64] columns of the node being recomputed (flatten / backtrace)
 	uint32_t itemCap;
 	uint32_t heapCap;
+	// optional (lock-step kernels): node|flag of the first 32 items of the slice being filled and of the previous slice, in
+	// shared memory -- the slice lookups are the most frequent dependent loads of a node visit (9 % of a lone warp's stall samples)
+	uint32_t* keysA = nullptr;
+	uint32_t* keysB = nullptr;
 };
 
 struct GcK1Result
@@ -90,13 +94,13 @@ GC_HD GcWord gc_item_end(const GcNodeItem& it) { GcWord w; w.VP = it.endVP; w.VN
 GC_HD uint32_t gc_item_node(const GcNodeItem& it) { return it.nodeAndFlag & 0x7FFFFFFFu; }
 
 // binary search of `node` in a slice (items sorted by componentNumber)
-GC_HD const GcNodeItem* gc_find_item(const GcGraphView& g, const GcNodeItem* items, uint32_t n, uint32_t node)
+GC_HD const GcNodeItem* gc_find_item(const GcGraphView& g, const GcNodeItem* items, uint32_t n, uint32_t node, const uint32_t* keys = nullptr)
 {
 #if defined(__CUDA_ARCH__)
 	if (g.coopLane >= 0 && n <= (uint32_t)g.coopWidth)
 	{
-		// one probe: lane k of the group holds the node of item k
-		uint32_t mine = ((uint32_t)g.coopLane < n) ? gc_item_node(items[g.coopLane]) : 0xFFFFFFFFu;
+		// one probe: lane k of the group holds the node of item k (from the shared-memory copy of the keys if there is one)
+		uint32_t mine = ((uint32_t)g.coopLane < n) ? (keys ? (keys[g.coopLane] & 0x7FFFFFFFu) : gc_item_node(items[g.coopLane])) : 0xFFFFFFFFu;
 		uint32_t m = __ballot_sync(g.coopMask, mine == node) >> g.coopShift;
 		return m ? &items[__ffs(m) - 1] : nullptr;
 	}
@@ -443,6 +447,9 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 		itemsUsed = 1;
 	}
 	const int32_t bandwidth = prm.bandwidth;
+	uint32_t* keysCur = ws.keysA;   // keys of the slice being filled (the initial slice first)
+	uint32_t* keysPrev = ws.keysB;
+	if (keysCur) keysCur[0] = startNode;
 	int32_t lastSlice = 0;
 	int32_t status = GC_OK;
 	uint64_t columns = 0;
@@ -515,6 +522,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 					}
 				}
 				item.nodeAndFlag = node | flag;
+				if (keysCur && curN <= 32) keysCur[curN - 1] = node | flag;
 				if (nodeMin < sliceMinScore)
 				{
 					sliceMinScore = nodeMin;
@@ -549,6 +557,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 				const GcSliceMeta& pm = ws.slices[lastSlice];
 				prevItems = ws.items + pm.firstItem;
 				prevN = pm.numItems;
+				{ uint32_t* tmp = keysPrev; keysPrev = keysCur; keysCur = tmp; } // the slice just closed is the previous one now
 				previousMinScore = pm.minScore;
 				previousQuitScore = pm.minScore + pm.bandwidth;
 				gc_eq_vector(seq, seqLen, j, eq, g.coopLane, g.coopWidth, g.coopMask, g.coopShift);
@@ -562,7 +571,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 						if (g.linearizable[nd])
 						{
 							uint32_t nb = g.inNbr[g.inStart[nd]];
-							const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
+							const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb, keysPrev);
 							if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) continue;
 						}
 					}
@@ -593,7 +602,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			const bool nodeLinearizable = g.linearizable[node] != 0;
 			const int firstBase = (int)(g.nodeSeq[2 * (uint64_t)node] & 3);
 			const uint32_t firstIn = inBegin < inEnd ? g.inNbr[inBegin] : 0;
-			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, node);
+			const GcNodeItem* prevItem = gc_find_item(g, prevItems, prevN, node, keysPrev);
 			prevExists = prevItem != nullptr;
 			prevStart = prevExists ? prevItem->startScore : 0;
 			prevHP = prevExists ? prevItem->HP : ~0ULL;
@@ -610,7 +619,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 					else if (nodeLinearizable)
 					{
 						uint32_t nb = firstIn;
-						const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb);
+						const GcNodeItem* nbItem = gc_find_item(g, prevItems, prevN, nb, keysPrev);
 						if (nbItem && nbItem->endScore < previousQuitScore && nbItem->minScore < previousQuitScore) seeded = false;
 					}
 				}
@@ -624,7 +633,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			for (uint32_t e = inBegin; e < inEnd; e++)
 			{
 				uint32_t p = e == inBegin ? firstIn : g.inNbr[e];
-				const GcNodeItem* pit = gc_find_item(g, curItems, curN, p);
+				const GcNodeItem* pit = gc_find_item(g, curItems, curN, p, keysCur);
 				if (!pit || !(pit->nodeAndFlag & 0x80000000u)) continue;
 				GcWord inc = gc_item_end(*pit);
 				uint64_t hinP, hinN;
@@ -687,7 +696,7 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			if (k == 0xFFFFFFFFu) continue;
 			const GcNodeItem& it = curItems[k];
 			uint32_t nd = gc_item_node(it);
-			const GcNodeItem* old = gc_find_item(g, prevItems, prevN, nd);
+			const GcNodeItem* old = gc_find_item(g, prevItems, prevN, nd, keysPrev);
 			gc_recalc_node(g, it, eq, old, cols);
 			uint32_t len = g.nodeLength[nd];
 			res.columns += len;

@@ -237,6 +237,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView
 	GcK1Workspace ws;
 	gc_k1_workspace(d, arena, colsShared[threadIdx.x / W], ws);
 	if (ws.heapCap <= 64) ws.heap = heapShared[threadIdx.x / W];
+	__shared__ uint32_t keyShared[128 / W][2][32];
+	ws.keysA = keyShared[threadIdx.x / W][0]; ws.keysB = keyShared[threadIdx.x / W][1];
 	GcK1Result res;
 	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
 	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
