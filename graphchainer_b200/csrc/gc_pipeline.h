@@ -356,7 +356,7 @@ private:
 		Pinned& operator=(const Pinned&) = delete;
 	};
 	std::vector<std::unique_ptr<Pinned>> tracePool;
-	Pinned codesBuf, seedBuf;
+	Pinned codesBuf, seedBuf, nwPinned;
 
 	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
 	void check(int rc, const char* what)
@@ -921,7 +921,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 
 	phase("s4");
 	// ---- S1b + S5: NW distances (K3), then the edit path only where the chain wins (S6)
-	std::string nwBuf;
+	// characters of the reads and path strings of the batch, in page-locked memory (the copy to the device runs at PCIe rate)
+	char* nwBuf = nullptr; size_t nwBufSize = 0;
 	std::vector<gcgpu_nw_item> nwItems;
 	std::vector<int> gaItem(R, -1), clcItem(R, -1);
 	std::vector<uint64_t> readOffInBuf(R);
@@ -967,7 +968,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 			}
 		}
-		nwBuf.resize(total);
+		nwPinned.ensure(total + 16);
+		nwBuf = (char*)nwPinned.p; nwBufSize = total;
 		#pragma omp parallel for schedule(dynamic, 16)
 		for (size_t r = 0; r < R; r++)
 		{
@@ -982,7 +984,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	if (!nwItems.empty())
 	{
 		double tDev = wallNow();
-		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
+		check(gcgpu_nw(ctx, nwBuf, nwBufSize, nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
 		devMs += wallNow() - tDev;
 		stats.k3Items += nwItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : nwRes) stats.k3Blocks += x.blocks;
@@ -1029,7 +1031,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		for (const auto& it : pathItems) cap += (uint64_t)it.query_len + it.target_len + 8;
 		ops.resize(cap);
 		double tDev = wallNow();
-		check(gcgpu_nw(ctx, nwBuf.data(), nwBuf.size(), pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), ops.data(), ops.size(), &opsUsed), "gcgpu_nw(path)");
+		check(gcgpu_nw(ctx, nullptr, nwBufSize, pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), ops.data(), ops.size(), &opsUsed), "gcgpu_nw(path)");
 		devMs += wallNow() - tDev;
 		stats.k3Items += pathItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : pathRes) stats.k3Blocks += x.blocks;

@@ -84,6 +84,7 @@ struct gcgpu_ctx
 	DevBuf seedBuf, seedMatches;
 	uint64_t denseMatches = 0;
 	uint64_t seqResident = ~0ULL; // bytes of the K1 sequence buffer currently on the device
+	uint64_t nwResident = ~0ULL;  // bytes of the K3 sequence buffer currently on the device (already encoded)
 	float lastKernelMs = 0;
 	uint64_t launches = 0;
 	uint64_t denseTraces = 0; // entries of the last gcgpu_extend call still in `compact`
@@ -1258,12 +1259,17 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		if (it.query_len < 0 || it.target_len < 0 || it.query_offset + (uint64_t)it.query_len > seq_bytes || it.target_offset + (uint64_t)it.target_len > seq_bytes)
 			return setError(GCGPU_ERR_ARG, "gcgpu_nw: item " + std::to_string(i) + " out of range");
 	}
-	CUDA_TRY(ctx->nwSeqBuf.ensure(seq_bytes + 16));
 	float ms = 0;
-	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	if (seq_bytes)
+	if (seqs)
 	{
-		CUDA_TRY(cudaMemcpyAsync(ctx->nwSeqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(ctx->nwSeqBuf.ensure(seq_bytes + 16));
+		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->nwSeqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->nwResident = seq_bytes;
+	}
+	else if (ctx->nwResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_nw: seqs == NULL but no sequence buffer of this size is resident");
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); // kernel time: the host-to-device copy above is not part of it
+	if (seqs && seq_bytes)
+	{
 		gc_k3_encode_kernel<<<1184, 256, 0, ctx->stream>>>((uint8_t*)ctx->nwSeqBuf.p, seq_bytes);
 		ctx->launches++;
 	}

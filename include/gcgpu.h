@@ -215,6 +215,8 @@ typedef struct gcgpu_nw_result
 	uint64_t blocks;      /* work counter: 64-row block column steps */
 } gcgpu_nw_result;
 
+/* `seqs` may be NULL: the buffer uploaded by the previous gcgpu_nw call on this ctx (same seq_bytes) is reused -- the edit
+ * paths of a batch are asked for in a second call on the same pairs.                                              */
 int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, const gcgpu_nw_item* items, uint32_t n,
              gcgpu_nw_result* results, uint8_t* ops, uint64_t ops_capacity, uint64_t* ops_used);
 

@@ -25,7 +25,7 @@ struct gcgpu_ctx
 	int bandwidth;
 	uint32_t numNodes;
 	uint64_t launches = 0;
-	std::vector<uint8_t> seqCopy;
+	std::vector<uint8_t> seqCopy, nwCodes;
 	std::vector<uint64_t> dense; // traces of the last gcgpu_extend call
 	std::vector<GcMzSlot> mzSlots; GcMzView mz; bool haveMz = false;
 	std::vector<gcgpu_seed_match> denseMatches;
@@ -112,8 +112,9 @@ extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t fir
 
 extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, const gcgpu_nw_item* items, uint32_t n, gcgpu_nw_result* results, uint8_t* ops, uint64_t ops_capacity, uint64_t* ops_used)
 {
-	std::vector<uint8_t> codes(seq_bytes);
-	for (uint64_t i = 0; i < seq_bytes; i++) codes[i] = k3code(seqs[i]);
+	if (seqs) { ctx->nwCodes.resize(seq_bytes); for (uint64_t i = 0; i < seq_bytes; i++) ctx->nwCodes[i] = k3code(seqs[i]); } // "resident" buffer of the real library
+	else if (ctx->nwCodes.size() != seq_bytes) { g_err = "gcgpu_nw: seqs == NULL but no sequence buffer of this size is resident"; return GCGPU_ERR_ARG; }
+	const std::vector<uint8_t>& codes = ctx->nwCodes;
 	std::vector<std::vector<uint8_t>> allOps(n);
 	bool internal = false;
 	#pragma omp parallel for schedule(dynamic, 1)
