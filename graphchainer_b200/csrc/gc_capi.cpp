@@ -120,7 +120,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	size_t W = std::min(h->workers.size(), std::max<size_t>(1, batches.size()));
 	// default: the batches in flight together hold ~2.25x as many threads as there are host threads -- a batch spends more than half
 	// of its time waiting for its kernels (threads asleep), measured best on B200 with 16 cores (profiles/r01h: 6 streams x 6 threads)
-	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::max(1, (hostThreads * 9 + 4 * (int)W - 1) / (4 * (int)W));
+	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::min(hostThreads, std::max(1, (hostThreads * 9 + 4 * (int)W - 1) / (4 * (int)W)));
 	std::vector<std::vector<std::string>> records(batches.size());
 	std::vector<std::vector<GcReadResult>> allResults(batches.size());
 	std::vector<uint64_t> launches0(W);

@@ -284,7 +284,7 @@ int main(int argc, char** argv)
 	auto worker = [&](int d)
 	{
 		// the batches in flight together hold ~2.25x the host threads: a batch waiting for its kernels leaves its threads asleep
-		omp_set_num_threads(std::max<int>(1, ((int)params.threads * 9 + 4 * numWorkers - 1) / (4 * numWorkers)));
+		omp_set_num_threads(std::min<int>((int)params.threads, std::max<int>(1, ((int)params.threads * 9 + 4 * numWorkers - 1) / (4 * numWorkers))));
 		GcPipeline pipeline(graph, ctxs[d], params.pipe);
 		std::vector<GcRead> batch;
 		std::vector<GcReadResult> results;
