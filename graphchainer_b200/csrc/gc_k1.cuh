@@ -159,11 +159,16 @@ struct GcColumnRun
 	uint64_t HP, HN;         // this node's horizontal deltas along row 63, shifted in from the top
 	uint64_t chunk0, chunk1; // node sequence, 2 bits per base
 	int32_t minScore; uint32_t minOffset;
+	uint64_t flatMask;       // FLAT runs: rows above the last row of the read (flattenWordSlice subtracts their deltas)
 };
+// flattenWordSlice (BVCommon.h:265-273): the column's value at the last row of the read
+GC_HD int32_t gc_flat_score(const GcWord& w, uint64_t flatMask) { return w.scoreEnd - gc_popc(w.VP & flatMask) + gc_popc(w.VN & flatMask); }
 // columns [begin, end) of the node: one getNextSlice step each (BVCommon.h:1118-1161)
 // FORCE: 1 = every column of the range has its first row forced, 0 = none, 2 = columns up to forceUntil (decided per column:
 // the thread-per-item kernel keeps ONE loop so that the lanes of a warp, whose forced ranges differ, stay in one loop)
-template <int FORCE>
+// FLAT: the minimum tracked is that of the FLATTENED column values (last slice of a read that does not fill 64 rows); used
+// by flattenLastSliceEnd, which only needs that minimum -- the columns themselves are not stored
+template <int FORCE, bool FLAT = false>
 GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols, uint32_t forceUntil = 0)
 {
 	// 16 columns at a time: their bases are one 32-bit word that is shifted down two bits per column (the
@@ -185,9 +190,10 @@ GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord
 				r.ws.VP &= ~1ULL;
 				r.ws.VN |= 1;
 			}
-			if (r.ws.scoreEnd < r.minScore)
+			const int32_t tracked = FLAT ? gc_flat_score(r.ws, r.flatMask) : r.ws.scoreEnd;
+			if (tracked < r.minScore)
 			{
-				r.minScore = r.ws.scoreEnd;
+				r.minScore = tracked;
 				r.minOffset = pos;
 			}
 			if (cols) cols[pos] = r.ws;
@@ -201,7 +207,7 @@ GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord
 // BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
 // (recalcNodeWordslice, BVCommon.h:828-852).
 GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t eq[4], GcWord ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
-	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols)
+	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols, uint64_t flatMask = 0)
 {
 	uint32_t len = g.nodeLength[node];
 	uint32_t forceUntil = 0;
@@ -242,12 +248,14 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 	uint64_t forceEq = ~0ULL;
 	if (!prevExists) forceEq ^= 1;
 	GcColumnRun run;
-	run.ws = ws; run.minScore = ws.scoreEnd; run.minOffset = 0; run.HP = 0; run.HN = 0;
+	run.ws = ws; run.minScore = flatMask ? gc_flat_score(ws, flatMask) : ws.scoreEnd; run.minOffset = 0; run.HP = 0; run.HN = 0;
+	run.flatMask = flatMask;
 	run.prevHP = prevHP; run.prevHN = prevHN;
 	run.eq[0] = eq[0] & forceEq; run.eq[1] = eq[1] & forceEq; run.eq[2] = eq[2] & forceEq; run.eq[3] = eq[3] & forceEq;
 	run.chunk0 = g.nodeSeq[2 * (uint64_t)node]; run.chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
 	// columns 1..forceUntil have their first row forced (a column cannot start below the previous slice's row), the rest not
-	if (g.coopLane >= 0)
+	if (flatMask) gc_columns_range<2, true>(run, 1, len, nullptr, forceUntil);
+	else if (g.coopLane >= 0)
 	{
 		uint32_t forcedEnd = forceUntil + 1 < len ? forceUntil + 1 : len;
 		if (forcedEnd > 1) gc_columns_range<1>(run, 1, forcedEnd, cols);
@@ -264,7 +272,8 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 }
 
 // recalcNodeWordslice (BVCommon.h:828-852): all columns of a stored node
-GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const uint64_t eq[4], const GcNodeItem* prev, GcWord* cols)
+// flatMask != 0: nothing is stored; *flatMin / *flatOffset receive the minimum of the flattened column values and its first column
+GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const uint64_t eq[4], const GcNodeItem* prev, GcWord* cols, uint64_t flatMask = 0, int32_t* flatMin = nullptr, uint32_t* flatOffset = nullptr)
 {
 	GcWord ws = gc_item_start(item);
 	bool prevExists = prev != nullptr;
@@ -275,7 +284,8 @@ GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const ui
 		ws = gc_merge(ws, src);
 	}
 	GcWord endOut; uint64_t hp, hn; int32_t ms; uint32_t mo;
-	gc_node_columns(g, gc_item_node(item), eq, ws, prevExists, prevStart, prevExists ? prev->HP : ~0ULL, prevExists ? prev->HN : 0ULL, endOut, hp, hn, ms, mo, cols);
+	gc_node_columns(g, gc_item_node(item), eq, ws, prevExists, prevStart, prevExists ? prev->HP : ~0ULL, prevExists ? prev->HN : 0ULL, endOut, hp, hn, ms, mo, cols, flatMask);
+	if (flatMin) { *flatMin = ms; *flatOffset = mo; }
 }
 
 // phmap::flat_hash_map<size_t,...> slot assignment (phmap.h:487-517,1869-1896,
@@ -689,7 +699,6 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 		sliceMinScore = GC_INT_MAX;
 		sliceMinNode = 0xFFFFFFFFu;
 		sliceMinOffset = 0xFFFFFFFFu;
-		GcWord* cols = ws.cols;
 		for (uint32_t s = 0; s < capacity; s++)
 		{
 			uint32_t k = slots[s];
@@ -697,19 +706,16 @@ GC_HD int32_t gc_k1_forward(const GcGraphView& g, const GcViterbiTables& vt, con
 			const GcNodeItem& it = curItems[k];
 			uint32_t nd = gc_item_node(it);
 			const GcNodeItem* old = gc_find_item(g, prevItems, prevN, nd, keysPrev);
-			gc_recalc_node(g, it, eq, old, cols);
-			uint32_t len = g.nodeLength[nd];
-			res.columns += len;
-			for (uint32_t c = 0; c < len; c++)
+			// the reference recomputes the node's columns, flattens each (flattenWordSlice, BVCommon.h:265-273) and keeps the first
+			// strict minimum in map order; the column run tracks exactly that minimum, so the columns are never stored
+			int32_t nodeFlatMin; uint32_t nodeFlatOffset;
+			gc_recalc_node(g, it, eq, old, nullptr, ~rowMask, &nodeFlatMin, &nodeFlatOffset);
+			res.columns += g.nodeLength[nd];
+			if (nodeFlatMin < sliceMinScore)
 			{
-				// flattenWordSlice (BVCommon.h:265-273)
-				int32_t sc = cols[c].scoreEnd - gc_popc(cols[c].VP & ~rowMask) + gc_popc(cols[c].VN & ~rowMask);
-				if (sc < sliceMinScore)
-				{
-					sliceMinScore = sc;
-					sliceMinNode = nd;
-					sliceMinOffset = c;
-				}
+				sliceMinScore = nodeFlatMin;
+				sliceMinNode = nd;
+				sliceMinOffset = nodeFlatOffset;
 			}
 		}
 		const GcSliceMeta& pm = ws.slices[lastSlice];

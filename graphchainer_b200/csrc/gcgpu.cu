@@ -168,9 +168,8 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
 	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
-	GcWord cols[64];
 	GcK1Workspace ws;
-	gc_k1_workspace(d, arena, cols, ws);
+	gc_k1_workspace(d, arena, nullptr, ws); // the forward pass stores no columns (the last slice is flattened on the fly)
 	GcK1Result res;
 	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
 	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
@@ -230,13 +229,12 @@ template <int MIN_BLOCKS, int W>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
-	__shared__ GcWord colsShared[128 / W][64];
 	__shared__ uint64_t heapShared[128 / W][64]; // the node queue of the slice being filled: a dozen dependent accesses per node visit
 	uint32_t t = gc_k1_group_setup<W>(g);
 	if (t >= n) return;
 	GcK1Desc d = descs[t];
 	GcK1Workspace ws;
-	gc_k1_workspace(d, arena, colsShared[threadIdx.x / W], ws);
+	gc_k1_workspace(d, arena, nullptr, ws); // the forward pass stores no columns (the last slice is flattened on the fly)
 	if (ws.heapCap <= 64) ws.heap = heapShared[threadIdx.x / W];
 	__shared__ uint32_t keyShared[128 / W][2][32];
 	ws.keysA = keyShared[threadIdx.x / W][0]; ws.keysB = keyShared[threadIdx.x / W][1];
