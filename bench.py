@@ -247,9 +247,9 @@ def main():
                          "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0,
                          "int32_peak_ops_per_s": int_peak, "int32_frac": (dom_units * dom_ops / (dom_ms / 1e3) / int_peak) if (int_peak and dom_ms > 0) else None,
                          "int32_peak_source": "measured live: gcgpu_int_peak (independent LOP3+IADD3 chains, best of 4)",
-                         # not live: the committed ncu --set full capture of the dominant launch pair (profiles/r02d_ncu_full_summary.txt)
+                         # not live: the committed ncu --set full capture of the dominant launch pair (profiles/r02h_ncu_full_summary.txt)
                          "ncu_dominant_launch": {"what": "S1 round 2 of an 839-read batch: 8960 warps, 178.8 M column steps (forward + backtrace)",
-                                                 "dram_bytes": 89.3e6 + 277.0e6 + 358.9e6 + 333.5e6, "algorithmic_bytes": 178.75e6 * K1_BYTES_PER_W + 364.2e6,
+                                                 "dram_bytes": 88.3e6 + 277.0e6 + 358.7e6 + 333.1e6, "algorithmic_bytes": 178.75e6 * K1_BYTES_PER_W + 364.2e6,
                                                  "algorithmic_note": "2.9 B per column step (node items, sequences) + 8 B per emitted trace cell",
                                                  "alu_pipe_pct": 81.3, "warp_inst_per_cycle_per_sm": 2.66, "lanes_doing_distinct_work": "1 of 32"}},
             "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
