@@ -10,6 +10,7 @@
 #include "../../include/gcalign.h"
 #include "gc_pipeline.h"
 #include "gc_output.h"
+#include "gc_post_host.h"
 #include "gc_builder.h"
 
 static thread_local std::string g_alignError;
@@ -70,6 +71,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	gg.num_components = (uint32_t)g.compStart.size() - 1;
 	gg.comp_map = g.compMap.data(); gg.comp_idx = g.compIdx.data(); gg.comp_start = g.compStart.data(); gg.topo_ids = g.topoIds.data();
 	gg.paths_start = g.pathsStart.data(); gg.paths_k = g.pathsK.data(); gg.back_start = g.backStart.data(); gg.back_node = g.backNode.data(); gg.back_k = g.backK.data();
+	gcFillOrigArrays(g, gg);
 	gcgpu_params gp; gp.initial_bandwidth = h->opts.initial_bandwidth;
 	int streams = h->opts.streams > 0 ? h->opts.streams : 6;
 	h->workers.resize(streams);
@@ -123,7 +125,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::min(hostThreads, std::max(1, (hostThreads * 9 + 4 * (int)W - 1) / (4 * (int)W)));
 	std::vector<std::vector<std::string>> records(batches.size());
 	std::vector<std::vector<GcReadResult>> allResults(batches.size());
-	std::vector<uint64_t> launches0(W);
+	std::vector<uint64_t> launches0(W), h2d0(W), d2h0(W);
 	std::atomic<size_t> nextBatch(0);
 	std::mutex errMutex; std::string error;
 	GcPipelineStats total;
@@ -173,8 +175,8 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 					}
 				}
 				if (getenv("GC_TRACE")) fprintf(stderr, "[gc] phase gam        %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tGam0).count());
-				// the traces are not needed past this point: keep only what the summaries read
-				for (auto& res : results) for (auto& a : res.alignments) { std::vector<GcTraceItem>().swap(a.trace); }
+				// the edit runs are not needed past this point: keep only what the summaries read
+				for (auto& res : results) for (auto& a : res.alignments) { std::vector<uint32_t>().swap(a.tokens); }
 			}
 			std::lock_guard<std::mutex> lock(errMutex);
 			const GcPipelineStats& ps = pipeline.stats;
@@ -183,7 +185,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		}
 		catch (const std::exception& e) { std::lock_guard<std::mutex> lock(errMutex); error = e.what(); }
 	};
-	for (size_t w = 0; w < W; w++) launches0[w] = gcgpu_launch_count(h->workers[w].ctx);
+	for (size_t w = 0; w < W; w++) { launches0[w] = gcgpu_launch_count(h->workers[w].ctx); gcgpu_transfer_bytes(h->workers[w].ctx, &h2d0[w], &d2h0[w]); }
 	tCall0 = std::chrono::steady_clock::now();
 	{
 		std::vector<std::thread> threads;
@@ -221,7 +223,13 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		stats->s0_ms = total.s0Ms; stats->k1_ms = total.k1Ms; stats->k2_ms = total.k2Ms; stats->k3_ms = total.k3Ms;
 		stats->k1_items = total.k1Items; stats->k1_columns = total.k1Columns; stats->k2_anchors = total.k2Anchors;
 		stats->k3_items = total.k3Items; stats->k3_blocks = total.k3Blocks; stats->s1_rounds = total.s1Rounds;
-		for (size_t w = 0; w < W; w++) stats->launches += gcgpu_launch_count(h->workers[w].ctx) - launches0[w];
+		for (size_t w = 0; w < W; w++)
+		{
+			stats->launches += gcgpu_launch_count(h->workers[w].ctx) - launches0[w];
+			uint64_t a = 0, b = 0;
+			gcgpu_transfer_bytes(h->workers[w].ctx, &a, &b);
+			stats->h2d_bytes += a - h2d0[w]; stats->d2h_bytes += b - d2h0[w];
+		}
 	}
 	if (gam_used) *gam_used = used;
 	if (getenv("GC_TRACE_CALL"))

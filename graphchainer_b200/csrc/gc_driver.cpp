@@ -19,6 +19,7 @@
 #include <zlib.h>
 #include "gc_pipeline.h"
 #include "gc_output.h"
+#include "gc_post_host.h"
 #ifdef GC_HAVE_BUILDER
 #include "gc_builder.h"
 #endif
@@ -232,6 +233,7 @@ int main(int argc, char** argv)
 	gg.num_components = (uint32_t)graph.compStart.size() - 1;
 	gg.comp_map = graph.compMap.data(); gg.comp_idx = graph.compIdx.data(); gg.comp_start = graph.compStart.data(); gg.topo_ids = graph.topoIds.data();
 	gg.paths_start = graph.pathsStart.data(); gg.paths_k = graph.pathsK.data(); gg.back_start = graph.backStart.data(); gg.back_node = graph.backNode.data(); gg.back_k = graph.backK.data();
+	gcFillOrigArrays(graph, gg);
 	gcgpu_params gp; gp.initial_bandwidth = params.bandwidth;
 	std::vector<gcgpu_ctx*> ctxs;
 	// one context (stream + workspaces) per batch in flight: worker w runs on device w % gpus
@@ -315,7 +317,7 @@ int main(int argc, char** argv)
 				readCounter++;
 				statSeedsFound += res.seedsFound;
 				if (res.seedsFound) { statReadsWithSeed += 2; statBpWithSeed += 2 * batch[r].sequence.size(); }
-				if (res.dropped) anyDropped = true;
+				if (res.dropped || res.broke) anyDropped = true;
 				if (params.shortVerbose && res.seedsFound && !res.dropped)
 				{
 					std::string short_id;

@@ -1,5 +1,5 @@
 // S7: final traces -> vg::Alignment messages -> GAM / JSON records.
-//   GraphAlignerVGAlignment::traceToAlignment        (src/GraphAlignerVGAlignment.h:37-165)
+//   GraphAlignerVGAlignment::traceToAlignment        (src/GraphAlignerVGAlignment.h:37-165; the edit runs come from gc_post.cuh)
 //   GraphAligner::AddAlignment                       (src/GraphAligner.h:205-212)
 //   replaceDigraphNodeIdsWithOriginalNodeIds         (src/Aligner.cpp:152-165)
 //   writeGAMToQueue / writeJSONToQueue               (src/Aligner.cpp:261-298)
@@ -22,102 +22,66 @@ struct Edit { int32_t from_length = 0, to_length = 0; std::string sequence; };
 struct Mapping { int64_t node_id = 0, offset = 0; bool is_reverse = false; std::string name; std::vector<Edit> edits; int64_t rank = 0; };
 struct Alignment { std::string sequence, name; std::vector<Mapping> mappings; int32_t score = 0, query_position = 0; double identity = 0; };
 
-inline bool characterMatch(char sequenceCharacter, char graphCharacter)
+// The final alignments arrive as token streams (gc_post.cuh): mapping = {0, digraph node id, offset in the original node},
+// edit = type << 30 | run length.  The characters of mismatch and insertion runs are consecutive read characters starting
+// at alignmentStart; the very first trace entry, when it is a mismatch, takes sequence[0] instead (sic, GraphAlignerVGAlignment.h:75).
+struct TokenReader
 {
-	// Common::characterMatch (GraphAlignerCommon.h:193-217) restricted to graphs without ambiguous bases
-	if (sequenceCharacter == graphCharacter) return true;
-	uint8_t m = gcEncodeBase(sequenceCharacter);
-	int b = graphCharacter == 'A' ? 0 : graphCharacter == 'C' ? 1 : graphCharacter == 'G' ? 2 : graphCharacter == 'T' ? 3 : -1;
-	if (sequenceCharacter == '-' || b < 0) return false;
-	return (m >> b) & 1;
-}
+	const uint32_t* t; size_t n, i = 0;
+	size_t nextChar;      // read position of the next character an edit consumes
+	bool firstEdit = true;
+	TokenReader(const GcAlnItem& item) : t(item.tokens.data()), n(item.tokens.size()), nextChar(item.alignmentStart) {}
+	bool atMapping() const { return i < n && (t[i] & 0x3FFFFFFFu) == 0; }
+	void mapping(int& digraphNode, size_t& offset) { digraphNode = (int)t[i + 1]; offset = t[i + 2]; i += 3; }
+	bool atEdit() const { return i < n && (t[i] & 0x3FFFFFFFu) != 0; }
+	// from/to lengths and the edit's sequence (appended to `seq`)
+	void edit(const std::string& sequence, int32_t& from, int32_t& to, std::string& seq)
+	{
+		uint32_t type = t[i] >> 30, len = t[i] & 0x3FFFFFFFu;
+		i++;
+		from = (type == GC_EDIT_INSERTION) ? 0 : (int32_t)len;
+		to = (type == GC_EDIT_DELETION) ? 0 : (int32_t)len;
+		if (type == GC_EDIT_MISMATCH || type == GC_EDIT_INSERTION)
+		{
+			seq.append(sequence, nextChar, len);
+			if (firstEdit && type == GC_EDIT_MISMATCH) seq[seq.size() - len] = sequence[0];
+		}
+		nextChar += (size_t)to;
+		firstEdit = false;
+	}
+};
 
 // traceToAlignment + AddAlignment + replaceDigraphNodeIdsWithOriginalNodeIds
 inline Alignment toAlignment(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const GcAlnItem& item)
 {
-	enum EditType { Match, Mismatch, Insertion, Deletion, Empty };
-	const std::vector<GcTraceItem>& trace = item.trace;
 	Alignment result;
 	result.name = seq_id;
 	result.score = item.traceScore;
-	int curNode = trace[0].node; bool curReverse = (trace[0].node % 2) == 1; size_t curOffset = trace[0].nodeOffset;
+	TokenReader rd(item);
 	int rank = 0;
-	result.mappings.emplace_back();
-	Mapping* vgmapping = &result.mappings.back();
-	vgmapping->rank = rank;
-	vgmapping->edits.emplace_back();
-	Edit* edit = &vgmapping->edits.back();
-	EditType currentEdit = Empty;
-	size_t mismatches = 0, deletions = 0, insertions = 0, matches = 0;
-	if (characterMatch(trace[0].sequenceCharacter, trace[0].graphCharacter))
+	while (rd.atMapping())
 	{
-		currentEdit = Match; edit->from_length++; edit->to_length++; matches++;
-	}
-	else
-	{
-		currentEdit = Mismatch; edit->from_length++; edit->to_length++;
-		edit->sequence = std::string { sequence[0] }; // sic: sequence[0], GraphAlignerVGAlignment.h:75
-		mismatches++;
-	}
-	vgmapping->node_id = curNode; vgmapping->is_reverse = curReverse; vgmapping->offset = (int64_t)curOffset;
-	for (size_t pos = 1; pos < trace.size(); pos++)
-	{
-		int newNode = trace[pos].node; bool newReverse = (trace[pos].node % 2) == 1; size_t newOffset = trace[pos].nodeOffset;
-		bool insideNode = !trace[pos - 1].nodeSwitch || (newNode == curNode && newReverse == curReverse && newOffset > curOffset);
-		if (!insideNode)
+		int digraphNode; size_t offset;
+		rd.mapping(digraphNode, offset);
+		result.mappings.emplace_back();
+		Mapping& m = result.mappings.back();
+		m.rank = rank++;
+		m.offset = (int64_t)offset;
+		m.is_reverse = (digraphNode % 2) == 1;
+		// replaceDigraphNodeIdsWithOriginalNodeIds (Aligner.cpp:152-165)
+		m.node_id = digraphNode / 2;
+		m.name = g.originalNodeName(digraphNode);
+		while (rd.atEdit())
 		{
-			rank++;
-			curNode = newNode; curReverse = newReverse; curOffset = newOffset;
-			result.mappings.emplace_back();
-			vgmapping = &result.mappings.back();
-			vgmapping->rank = rank;
-			vgmapping->offset = (int64_t)curOffset; vgmapping->node_id = curNode; vgmapping->is_reverse = curReverse;
-			vgmapping->edits.emplace_back();
-			edit = &vgmapping->edits.back();
-			currentEdit = Empty;
-		}
-		if (trace[pos - 1].seqPos == trace[pos].seqPos)
-		{
-			if (currentEdit == Empty) currentEdit = Deletion;
-			if (currentEdit != Deletion) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Deletion; }
-			edit->from_length++;
-			deletions++;
-		}
-		else if (insideNode && trace[pos - 1].nodeOffset == trace[pos].nodeOffset)
-		{
-			if (currentEdit == Empty) currentEdit = Insertion;
-			if (currentEdit != Insertion) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Insertion; }
-			edit->to_length++;
-			edit->sequence += trace[pos].sequenceCharacter;
-			insertions++;
-		}
-		else if (characterMatch(trace[pos].sequenceCharacter, trace[pos].graphCharacter))
-		{
-			if (currentEdit == Empty) currentEdit = Match;
-			if (currentEdit != Match) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Match; }
-			edit->from_length++; edit->to_length++;
-			matches++;
-		}
-		else
-		{
-			if (currentEdit == Empty) currentEdit = Mismatch;
-			if (currentEdit != Mismatch) { vgmapping->edits.emplace_back(); edit = &vgmapping->edits.back(); currentEdit = Mismatch; }
-			edit->from_length++; edit->to_length++;
-			edit->sequence += trace[pos].sequenceCharacter;
-			mismatches++;
+			m.edits.emplace_back();
+			Edit& e = m.edits.back();
+			rd.edit(sequence, e.from_length, e.to_length, e.sequence);
 		}
 	}
-	result.identity = (double)matches / (double)(matches + mismatches + insertions + deletions);
+	result.identity = (double)item.matches / (double)item.steps;
 	// AddAlignment (GraphAligner.h:210-211)
 	result.sequence = sequence.substr(item.alignmentStart, item.alignmentEnd - item.alignmentStart);
 	result.query_position = (int32_t)item.alignmentStart;
-	// replaceDigraphNodeIdsWithOriginalNodeIds (Aligner.cpp:152-165)
-	for (Mapping& m : result.mappings)
-	{
-		int digraphNodeId = (int)m.node_id;
-		m.node_id = digraphNodeId / 2;
-		m.name = g.originalNodeName(digraphNodeId);
-	}
 	return result;
 }
 
@@ -210,59 +174,25 @@ struct GamEncoder
 	// appends varint32 size + message of one alignment to `out`
 	void encode(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const GcAlnItem& item, std::string& out)
 	{
-		enum EditType { Match, Mismatch, Insertion, Deletion, Empty };
-		const std::vector<GcTraceItem>& trace = item.trace;
 		path.clear();
-		int curNode = trace[0].node; bool curReverse = (trace[0].node % 2) == 1; size_t curOffset = trace[0].nodeOffset;
+		TokenReader rd(item);
 		int rank = 0;
-		beginMapping(g, curNode, curOffset);
-		int32_t from = 0, to = 0; std::string eseq;
-		EditType currentEdit = Empty;
-		size_t mismatches = 0, deletions = 0, insertions = 0, matches = 0;
-		if (characterMatch(trace[0].sequenceCharacter, trace[0].graphCharacter)) { currentEdit = Match; from++; to++; matches++; }
-		else { currentEdit = Mismatch; from++; to++; eseq = std::string { sequence[0] }; mismatches++; }
-		auto newEdit = [&]() { flushEdit(from, to, eseq); from = 0; to = 0; eseq.clear(); };
-		for (size_t pos = 1; pos < trace.size(); pos++)
+		std::string eseq;
+		while (rd.atMapping())
 		{
-			int newNode = trace[pos].node; bool newReverse = (trace[pos].node % 2) == 1; size_t newOffset = trace[pos].nodeOffset;
-			bool insideNode = !trace[pos - 1].nodeSwitch || (newNode == curNode && newReverse == curReverse && newOffset > curOffset);
-			if (!insideNode)
+			int digraphNode; size_t offset;
+			rd.mapping(digraphNode, offset);
+			beginMapping(g, digraphNode, offset);
+			while (rd.atEdit())
 			{
-				flushEdit(from, to, eseq); from = 0; to = 0; eseq.clear();
-				endMapping(rank);
-				rank++;
-				curNode = newNode; curReverse = newReverse; curOffset = newOffset;
-				beginMapping(g, curNode, curOffset);
-				currentEdit = Empty;
+				int32_t from, to;
+				eseq.clear();
+				rd.edit(sequence, from, to, eseq);
+				flushEdit(from, to, eseq);
 			}
-			if (trace[pos - 1].seqPos == trace[pos].seqPos)
-			{
-				if (currentEdit == Empty) currentEdit = Deletion;
-				if (currentEdit != Deletion) { newEdit(); currentEdit = Deletion; }
-				from++; deletions++;
-			}
-			else if (insideNode && trace[pos - 1].nodeOffset == trace[pos].nodeOffset)
-			{
-				if (currentEdit == Empty) currentEdit = Insertion;
-				if (currentEdit != Insertion) { newEdit(); currentEdit = Insertion; }
-				to++; eseq += trace[pos].sequenceCharacter; insertions++;
-			}
-			else if (characterMatch(trace[pos].sequenceCharacter, trace[pos].graphCharacter))
-			{
-				if (currentEdit == Empty) currentEdit = Match;
-				if (currentEdit != Match) { newEdit(); currentEdit = Match; }
-				from++; to++; matches++;
-			}
-			else
-			{
-				if (currentEdit == Empty) currentEdit = Mismatch;
-				if (currentEdit != Mismatch) { newEdit(); currentEdit = Mismatch; }
-				from++; to++; eseq += trace[pos].sequenceCharacter; mismatches++;
-			}
+			endMapping(rank++);
 		}
-		flushEdit(from, to, eseq);
-		endMapping(rank);
-		double identity = (double)matches / (double)(matches + mismatches + insertions + deletions);
+		double identity = (double)item.matches / (double)item.steps;
 		msg.clear();
 		size_t alnLen = item.alignmentEnd - item.alignmentStart;
 		if (alnLen) { msg.push_back((char)0x0A); putVarintTo(msg, alnLen); msg.append(sequence, item.alignmentStart, alnLen); }

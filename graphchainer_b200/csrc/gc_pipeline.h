@@ -1,19 +1,22 @@
 // Host driver of the per-read pipeline: the body of runComponentMappings
-// (src/Aligner.cpp:492-1062, colinear mode) re-organised for batches of reads, with the
-// three dynamic-programming stages delegated to libgcgpu through its C ABI:
-//   S0  seeding + clustering               host   (gc_seeder.h)
-//   S1  whole-read seed-and-extend         host seed loop (GraphAligner.h:114-203) in ROUNDS,
-//                                          extensions = gcgpu_extend (K1)
-//   S1b distance(GA path, read)            gcgpu_nw (K3)                     Aligner.cpp:642-654
-//   S2  fragment anchoring                 all window seeds extended speculatively by one
-//                                          gcgpu_extend call, then the reference's in-order
-//                                          exactAlignmentPart filter      Aligner.cpp:668-730
-//   S3  co-linear chaining                 gcgpu_chain (K2)                  Aligner.cpp:735
-//   S4  chain -> node path                 host BFS getChainPath             Aligner.cpp:748-822
-//   S5  NW(path, read)                     gcgpu_nw (K3): distance for every read, the edit
-//                                          path only when the chained alignment wins (S6)
-//   S6  decision, S7 vg::Alignment         host                              Aligner.cpp:880-1013
-// There is no CPU implementation of K1/K2/K3 here: without libgcgpu nothing aligns.
+// (src/Aligner.cpp:492-1062, colinear mode) re-organised for batches of reads.  The DP stages and
+// everything that reads their traces run on the device through libgcgpu's C ABI; the K1 traces of a
+// batch never leave HBM (include/gcgpu.h, "resident batch"):
+//   S0  seeding                            k-mer lookups gcgpu_seed; count sort, density cut, clustering and
+//                                          the goodness sort on the host (gc_seeder.h: libstdc++ tie orders)
+//   S1  whole-read seed-and-extend         host seed loop (GraphAligner.h:114-203) in ROUNDS over alignment
+//                                          extents + seed-coverage bit masks; extensions and exactAlignmentPart
+//                                          = gcgpu_extend_seeds (K1 + coverage kernel)
+//   S1b distance(GA path, read)            path string built on the device (gcgpu_nw_compose), gcgpu_nw (K3)
+//   S2  fragment anchoring                 gcgpu_fragment_anchors: all window seeds extended speculatively,
+//                                          the in-order seed loop per fragment and the anchors on the device
+//   S3  co-linear chaining                 gcgpu_chain_resident (K2) on the device-resident anchors
+//   S4  chain -> node path                 host BFS getChainPath over the chained anchors only
+//   S5  NW(path, read)                     gcgpu_nw (K3): distance for every read, the edit path only when
+//                                          the chained alignment wins (S6)
+//   S6  decision                           host                              Aligner.cpp:880-920
+//   S7  vg::Alignment                      edit runs from gcgpu_encode_alignments; protobuf framing on the host
+// There is no CPU implementation of the device stages here: without libgcgpu nothing aligns.
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -39,6 +42,7 @@ struct GcProfScope { int id; unsigned long long t0; GcProfScope(int id, const ch
 #include "../../include/gcgpu.h"
 #include "gc_host_graph.h"
 #include "gc_seeder.h"
+#include "gc_post.cuh"
 
 struct GcRead
 {
@@ -46,54 +50,24 @@ struct GcRead
 	std::string sequence;
 };
 
-// GraphAlignerCommon::TraceItem (GraphAlignerCommon.h:127-160) after the seqPos/node fix-ups
-struct GcTraceItem
-{
-	int32_t node;          // digraph node id (2*id + strand)
-	uint32_t nodeOffset;   // offset in the original node
-	int64_t seqPos;
-	bool nodeSwitch;
-	char sequenceCharacter;
-	char graphCharacter;
-};
-
+// one alignment of the final output: AlignmentResult::AlignmentItem with its trace already reduced to the
+// mappings and edit runs of the vg::Alignment (token stream of gc_post.cuh)
 struct GcAlnItem
 {
-	std::vector<GcTraceItem> trace;
+	std::vector<uint32_t> tokens;
+	uint32_t matches = 0, steps = 0; // identity = matches / steps
 	int32_t traceScore = 0;       // OnewayTrace::score (what AddAlignment serialises)
 	size_t alignmentStart = 0, alignmentEnd = 0;
 	size_t alignmentScore = 0;
 	size_t seedGoodness = 0;
 };
 
-
-// One seed extension (getAlignmentFromSeed, GraphAligner.h:567-626) as the two K1 traces the kernel
-// wrote, still packed: the merged GraphAligner trace is only materialised for alignments that
-// survive selection.  Merged order = backward part (kernel order; its last entry, the seed cell,
-// is dropped when a forward part exists, GraphAligner.h:599) then the forward part reversed.
-struct GcPackedAln
-{
-	const uint64_t* bwd = nullptr; uint32_t bwdLen = 0;
-	const uint64_t* fwd = nullptr; uint32_t fwdLen = 0;
-	int32_t bwdScore = 0, fwdScore = 0;
-	int64_t seedPos = 0;          // seed.seqPos in the coordinates of the aligned sequence
-	int32_t traceScore = 0;
-	size_t alignmentStart = 0, alignmentEnd = 0, alignmentScore = 0, seedGoodness = 0;
-	uint32_t bwdUsed() const { return bwdLen ? (fwdLen ? bwdLen - 1 : bwdLen) : 0; }
-	uint32_t size() const { return bwdUsed() + fwdLen; }
-	int64_t seqPosAt(uint32_t k) const
-	{
-		uint32_t nb = bwdUsed();
-		if (k < nb) return (seedPos - 1) - (int64_t)GCGPU_TRACE_SEQPOS(bwd[k]);
-		return (int64_t)GCGPU_TRACE_SEQPOS(fwd[fwdLen - 1 - (k - nb)]) + seedPos + 1;
-	}
-};
-
 struct GcReadResult
 {
 	std::vector<GcAlnItem> alignments; // final, sorted by alignmentStart
 	bool usedChain = false;            // S6: the chained (CLC) alignment was strictly better
-	bool dropped = false;              // assertion-class failure: the reference drops the read
+	bool dropped = false;              // assertion-class failure in the whole-read pass: the reference drops the read
+	bool broke = false;                // any assertion-class failure (the run reports "Alignment broke with some reads")
 	// the fields of the reference's --short-verbose line (Aligner.cpp:909-915)
 	size_t anchors = 0, chained = 0, pathBp = 0, clcScore = 0, longEditDistance = 0;
 	bool hasLong = false;
@@ -148,53 +122,14 @@ inline char complementChar(char c)
 }
 inline uint8_t complementMask(uint8_t m) { return (uint8_t)(((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3)); }
 
-// digraph node id + offset in the original node of merged-trace entry k
-inline void packedNodePos(const GcHostGraph& g, const GcPackedAln& a, uint32_t k, int& node, size_t& nodeOffset)
+// Common::characterMatch (GraphAlignerCommon.h:193-217) restricted to graphs without ambiguous bases
+inline bool characterMatch(char sequenceCharacter, char graphCharacter)
 {
-	uint32_t nb = a.bwdUsed();
-	if (k < nb)
-	{
-		uint64_t e = a.bwd[k];
-		uint32_t sn = GCGPU_TRACE_NODE(e);
-		auto rp = g.reversePosition(g.nodeIDs[sn], (size_t)g.nodeOffset[sn] + GCGPU_TRACE_OFFSET(e));
-		node = rp.first; nodeOffset = rp.second;
-	}
-	else
-	{
-		uint64_t e = a.fwd[a.fwdLen - 1 - (k - nb)];
-		uint32_t sn = GCGPU_TRACE_NODE(e);
-		node = g.nodeIDs[sn]; nodeOffset = (size_t)g.nodeOffset[sn] + GCGPU_TRACE_OFFSET(e);
-	}
-}
-// split node of merged-trace entry k (= GetUnitigNode(node, nodeOffset))
-inline size_t packedSplitNode(const GcHostGraph& g, const GcPackedAln& a, uint32_t k, GcHostGraph::UnitigCache& cache)
-{
-	uint32_t nb = a.bwdUsed();
-	if (k >= nb) return GCGPU_TRACE_NODE(a.fwd[a.fwdLen - 1 - (k - nb)]);
-	int node; size_t off;
-	packedNodePos(g, a, k, node, off);
-	return g.unitigNode(node, off, cache);
-}
-
-// exactAlignmentPart (GraphAligner.h:407-461): is the seed cell on the trace of `aln`?
-inline bool exactAlignmentPart(const GcHostGraph& g, const GcPackedAln& aln, const GcSeedHit& seed, bool& assertion)
-{
-	uint32_t n = aln.size();
-	if (n == 0 || !(aln.seqPosAt(n - 1) > aln.seqPosAt(0))) { assertion = true; return false; }
-	int64_t sp = (int64_t)seed.seqPos;
-	if (aln.seqPosAt(n - 1) < sp) return false;
-	if (aln.seqPosAt(0) > sp) return false;
-	// seqPos is non-decreasing with unit steps: find the run of items at seqPos == sp
-	uint32_t lo = 0, hi = n;
-	while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (aln.seqPosAt(mid) < sp) lo = mid + 1; else hi = mid; }
-	int compareNode = seed.nodeID * 2 + (seed.reverse ? 1 : 0);
-	for (uint32_t i = lo; i < n && aln.seqPosAt(i) == sp; i++)
-	{
-		int node; size_t off;
-		packedNodePos(g, aln, i, node, off);
-		if (node == compareNode && off == seed.nodeOffset) return true;
-	}
-	return false;
+	if (sequenceCharacter == graphCharacter) return true;
+	uint8_t m = gcEncodeBase(sequenceCharacter);
+	int b = graphCharacter == 'A' ? 0 : graphCharacter == 'C' ? 1 : graphCharacter == 'G' ? 2 : graphCharacter == 'T' ? 3 : -1;
+	if (sequenceCharacter == '-' || b < 0) return false;
+	return (m >> b) & 1;
 }
 
 // AlignmentSelection::alignmentIncompatible (AlignmentSelection.cpp:13-31)
@@ -230,36 +165,6 @@ inline std::vector<Aln> selectGreedyLength(const std::vector<Aln>& alignments)
 			result.push_back(alignments[i]);
 	}
 	return result;
-}
-
-// traceToPoses + traceToSequence (Aligner.cpp:376-408, 425-428): the padded graph path of a GA alignment
-inline std::string traceToSequence(const GcHostGraph& g, const GcAlnItem& aln)
-{
-	std::string ret;
-	size_t lastNode = 0, lastOffset = 0, lastLength = 0;
-	GcHostGraph::UnitigCache ucache;
-	ret.reserve(aln.trace.size() + 64);
-	for (size_t j = 0; j < aln.trace.size(); j++)
-	{
-		size_t node = g.unitigNode(aln.trace[j].node, aln.trace[j].nodeOffset, ucache);
-		size_t nodeOffset = aln.trace[j].nodeOffset - g.nodeOffset[node];
-		if (j == 0)
-		{
-			lastNode = node; lastOffset = nodeOffset; lastLength = g.nodeLength[node];
-			ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset));
-			lastOffset++;
-		}
-		else
-		{
-			if (node != lastNode)
-			{
-				while (lastOffset < lastLength) { ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset)); lastOffset++; }
-				lastNode = node; lastLength = g.nodeLength[node]; lastOffset = 0;
-			}
-			while (lastOffset <= nodeOffset) { ret.push_back(g.nodeChar((uint32_t)lastNode, (uint32_t)lastOffset)); lastOffset++; }
-		}
-	}
-	return ret;
 }
 
 struct MatrixPos { size_t node; size_t nodeOffset; size_t seqPos; };
@@ -328,17 +233,7 @@ private:
 	gcgpu_ctx* ctx;
 	GcPipelineParams params;
 
-	struct ExtRef { int32_t item[2]; }; // indices of the backward / forward work items, -1 if absent
-	struct Batch
-	{
-		uint8_t* codes = nullptr;            // per read: forward masks then reverse-complement masks (page-locked)
-		size_t codesBytes = 0;
-		std::vector<uint64_t> fwdOff, rcOff; // offsets into codes
-	};
-
-	// page-locked host buffers for the kernel outputs, grow-only, reused across batches:
-	// tracePool[k] receives the packed traces of the k-th gcgpu_extend call of a batch and stays
-	// valid until the packed alignments that point into it have been consumed
+	// page-locked host buffers for what crosses PCIe, grow-only, reused across batches
 	struct Pinned
 	{
 		void* p = nullptr; size_t cap = 0;
@@ -355,110 +250,13 @@ private:
 		Pinned(const Pinned&) = delete;
 		Pinned& operator=(const Pinned&) = delete;
 	};
-	std::vector<std::unique_ptr<Pinned>> tracePool;
-	Pinned codesBuf, seedBuf, nwPinned;
+	Pinned charsBuf, seedBuf, cellBuf, extBuf, tokenBuf, opsBuf;
+	std::vector<std::unique_ptr<Pinned>> coverPool; // seed-coverage masks of the S1 rounds of a batch
 
 	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
 	void check(int rc, const char* what)
 	{
 		if (rc != GCGPU_OK) throw std::runtime_error(std::string(what) + " failed: " + gcgpu_last_error());
-	}
-
-	// the two K1 work items of one seed (getTwoDirectionalTrace, GraphAligner.h:480-525).
-	// seqStart/seqLen delimit `sequence` inside the read (whole read, or one fragment).
-	ExtRef makeItems(const Batch& b, size_t r, size_t readLen, size_t seqStart, size_t seqLen, const GcSeedHit& seed, std::vector<gcgpu_ext_item>& items) const
-	{
-		ExtRef ref; ref.item[0] = ref.item[1] = -1;
-		int forwardNodeId = seed.nodeID * 2 + (seed.reverse ? 1 : 0);
-		if (seed.seqPos > 0)
-		{
-			auto reversePos = g.reversePosition(forwardNodeId, seed.nodeOffset);
-			uint32_t node = g.unitigNode(reversePos.first, reversePos.second);
-			gcgpu_ext_item it;
-			// revcomp(sequence) = rc(read)[readLen - seqStart - seqLen, readLen - seqStart); its last seqPos characters
-			it.seq_offset = b.rcOff[r] + (readLen - seqStart - seed.seqPos);
-			it.seq_len = (int32_t)seed.seqPos;
-			it.node = node;
-			it.offset = (uint32_t)(reversePos.second - g.nodeOffset[node]);
-			it.reserved = 0;
-			ref.item[0] = (int32_t)items.size();
-			items.push_back(it);
-		}
-		if (seed.seqPos < seqLen - 1)
-		{
-			uint32_t node = g.unitigNode(forwardNodeId, seed.nodeOffset);
-			gcgpu_ext_item it;
-			it.seq_offset = b.fwdOff[r] + seqStart + seed.seqPos + 1;
-			it.seq_len = (int32_t)(seqLen - seed.seqPos - 1);
-			it.node = node;
-			it.offset = (uint32_t)(seed.nodeOffset - g.nodeOffset[node]);
-			it.reserved = 0;
-			ref.item[1] = (int32_t)items.size();
-			items.push_back(it);
-		}
-		return ref;
-	}
-
-	// getAlignmentFromSeed (GraphAligner.h:567-626) from the two K1 results, kept packed.  `seed.seqPos` is in
-	// the coordinates of the aligned sequence (whole read or fragment).  Returns false if both failed.
-	bool buildAlignment(const GcSeedHit& seed, const ExtRef& ref, const gcgpu_ext_result* results, const uint64_t* traces, GcPackedAln& out) const
-	{
-		bool haveB = ref.item[0] >= 0 && results[ref.item[0]].status == GCGPU_ITEM_OK;
-		bool haveF = ref.item[1] >= 0 && results[ref.item[1]].status == GCGPU_ITEM_OK;
-		if (!haveB && !haveF) return false;
-		out = GcPackedAln();
-		out.seedPos = (int64_t)seed.seqPos;
-		if (haveB) { const gcgpu_ext_result& rb = results[ref.item[0]]; out.bwd = traces + rb.trace_offset; out.bwdLen = rb.trace_len; out.bwdScore = rb.score; }
-		if (haveF) { const gcgpu_ext_result& rf = results[ref.item[1]]; out.fwd = traces + rf.trace_offset; out.fwdLen = rf.trace_len; out.fwdScore = rf.score; }
-		out.traceScore = (haveB ? out.bwdScore : 0) + (haveF ? out.fwdScore : 0);
-		out.alignmentScore = (size_t)out.traceScore;
-		out.alignmentStart = (size_t)out.seqPosAt(0);
-		out.alignmentEnd = (size_t)out.seqPosAt(out.size() - 1) + 1;
-		out.seedGoodness = seed.seedGoodness;
-		return true;
-	}
-
-	// the merged GraphAligner trace of a packed alignment: fixReverseTraceSeqPosAndOrder (GraphAligner.h:543-565),
-	// getTwoDirectionalTrace (:522), fixForwardTraceSeqPos (:527-540)
-	void materialize(const char* sequence, const GcPackedAln& a, GcAlnItem& out) const
-	{
-		uint32_t nb = a.bwdUsed(), n = a.size();
-		out.trace.resize(n);
-		uint32_t lastNode = 0xFFFFFFFFu; int lastRevId = 0; size_t lastRevEnd = 0; // reversePosition(id, o) = (id ^ 1, origSize - 1 - o): constant per kernel node up to the offset
-		for (uint32_t i = 0; i < nb; i++)
-		{
-			uint64_t e = a.bwd[i];
-			uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
-			GcTraceItem& it = out.trace[i];
-			it.seqPos = (a.seedPos - 1) - (int64_t)GCGPU_TRACE_SEQPOS(e);
-			if (node != lastNode)
-			{
-				auto reversePos = g.reversePosition(g.nodeIDs[node], (size_t)g.nodeOffset[node]);
-				lastNode = node; lastRevId = reversePos.first; lastRevEnd = reversePos.second;
-			}
-			it.node = lastRevId;
-			it.nodeOffset = (uint32_t)(lastRevEnd - off);
-			it.sequenceCharacter = sequence[it.seqPos];
-			it.graphCharacter = gcpipe::complementChar(g.nodeChar(node, off));
-			it.nodeSwitch = (i + 1 < a.bwdLen) ? GCGPU_TRACE_SWITCH(a.bwd[i + 1]) != 0 : false;
-		}
-		for (uint32_t i = 0; i < a.fwdLen; i++)
-		{
-			uint64_t e = a.fwd[a.fwdLen - 1 - i];
-			uint32_t node = GCGPU_TRACE_NODE(e), off = GCGPU_TRACE_OFFSET(e);
-			GcTraceItem& it = out.trace[nb + i];
-			it.seqPos = (int64_t)GCGPU_TRACE_SEQPOS(e) + a.seedPos + 1;
-			it.node = g.nodeIDs[node];
-			it.nodeOffset = g.nodeOffset[node] + off;
-			it.nodeSwitch = GCGPU_TRACE_SWITCH(e) != 0;
-			it.sequenceCharacter = sequence[it.seqPos];
-			it.graphCharacter = g.nodeChar(node, off);
-		}
-		out.traceScore = a.traceScore;
-		out.alignmentScore = a.alignmentScore;
-		out.alignmentStart = a.alignmentStart;
-		out.alignmentEnd = a.alignmentEnd;
-		out.seedGoodness = a.seedGoodness;
 	}
 };
 
@@ -473,39 +271,24 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	double tPhase = wallNow();
 	double devMs = 0; // wall time spent inside libgcgpu calls during the current phase
 	auto phase = [&](const char* name) { if (traceOn) { double n = wallNow(); fprintf(stderr, "[gc] phase %-10s %.2f ms (libgcgpu calls %.2f ms, host %.2f ms)\n", name, n - tPhase, devMs, n - tPhase - devMs); tPhase = n; devMs = 0; } };
-	// ---- encode reads (forward + reverse complement IUPAC masks)
-	Batch b;
-	b.fwdOff.resize(R); b.rcOff.resize(R);
-	{
-		size_t total = 0;
-		for (size_t r = 0; r < R; r++) { b.fwdOff[r] = total; total += reads[r].sequence.size(); b.rcOff[r] = total; total += reads[r].sequence.size(); }
-		codesBuf.ensure(total + 8);
-		b.codes = (uint8_t*)codesBuf.p; b.codesBytes = total + 8;
-		memset(b.codes + total, 0, 8);
-		#pragma omp parallel for schedule(dynamic, 16)
-		for (size_t r = 0; r < R; r++)
-		{
-			const std::string& s = reads[r].sequence;
-			size_t L = s.size();
-			for (size_t i = 0; i < L; i++)
-			{
-				uint8_t m = gcEncodeSeedBase(s[i]);
-				b.codes[b.fwdOff[r] + i] = m;
-				b.codes[b.rcOff[r] + (L - 1 - i)] = gcpipe::complementMask(m);
-			}
-		}
-	}
+	// ---- the reads' characters go to the device once; codes (forward + reverse complement) are derived there
+	std::vector<gcgpu_read> rd(R);
+	uint64_t totalChars = 0;
+	for (size_t r = 0; r < R; r++) { rd[r].char_offset = totalChars; rd[r].len = (int32_t)reads[r].sequence.size(); rd[r].first_cell = 0; rd[r].num_cells = 0; rd[r].reserved = 0; totalChars += reads[r].sequence.size(); }
+	charsBuf.ensure(totalChars + 16);
+	#pragma omp parallel for schedule(dynamic, 16)
+	for (size_t r = 0; r < R; r++) memcpy((char*)charsBuf.p + rd[r].char_offset, reads[r].sequence.data(), reads[r].sequence.size());
+	{ double tDev = wallNow(); check(gcgpu_load_reads(ctx, (const char*)charsBuf.p, totalChars, rd.data(), (uint32_t)R), "gcgpu_load_reads"); devMs += wallNow() - tDev; stats.s0Ms += gcgpu_last_kernel_ms(ctx); }
 	// ---- S0: seeds (the reference calls getSeeds + OrderSeeds twice per read with identical results).
-	// k-mer walk + index probes on the device (gcgpu_seed uploads the read codes, which stay resident for K1);
-	// the count sort, density cut, seed-hit expansion and clustering per read on the host
-	std::vector<std::vector<GcSeedHit>> seedsOrdered(R);
+	// k-mer walk + index probes on the device; the count sort, density cut, seed-hit expansion and clustering per read on the host
+	std::vector<std::vector<GcSeedHit>> seedsOrdered(R), seedsByPos(R);
 	{
 		std::vector<gcgpu_seed_read> sr(R);
-		for (size_t r = 0; r < R; r++) { sr[r].seq_offset = b.fwdOff[r]; sr[r].seq_len = (int32_t)reads[r].sequence.size(); sr[r].reserved = 0; }
+		for (size_t r = 0; r < R; r++) { sr[r].seq_offset = 2 * rd[r].char_offset; sr[r].seq_len = rd[r].len; sr[r].reserved = 0; }
 		std::vector<uint64_t> matchOff(R + 1, 0);
 		uint64_t used = 0;
 		double tDev = wallNow();
-		check(gcgpu_seed(ctx, b.codes, b.codesBytes, sr.data(), (uint32_t)R, matchOff.data(), nullptr, 0, &used), "gcgpu_seed");
+		check(gcgpu_seed(ctx, nullptr, 2 * totalChars, sr.data(), (uint32_t)R, matchOff.data(), nullptr, 0, &used), "gcgpu_seed");
 		seedBuf.ensure((used + 1) * sizeof(gcgpu_seed_match));
 		check(gcgpu_fetch_seed_matches(ctx, (gcgpu_seed_match*)seedBuf.p, 0, used), "gcgpu_fetch_seed_matches");
 		devMs += wallNow() - tDev;
@@ -519,39 +302,40 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			for (uint64_t i = matchOff[r]; i < matchOff[r + 1]; i++) matchIndices.emplace_back((size_t)matches[i].pos, (size_t)0, (size_t)matches[i].start, (size_t)matches[i].count);
 			{ GC_PROF_SCOPE(0, "seed.seedsFromMatches"); seedsOrdered[r] = gcseed::seedsFromMatches(g, matchIndices, reads[r].sequence.size(), params.minimizerSeedDensity); }
 			out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
-			GC_PROF_SCOPE(1, "seed.orderSeeds");
-			if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]);
+			{ GC_PROF_SCOPE(1, "seed.orderSeeds"); if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]); }
+			// the split pass sorts a copy of the ordered seeds by position (Aligner.cpp:667); the same std::sort call on the same
+			// element order gives the reference's permutation.  The device holds the seeds in this order ("cells").
+			GC_PROF_SCOPE(2, "seed.byPos");
+			std::vector<GcSeedHit>& ordered = seedsOrdered[r];
+			for (size_t i = 0; i < ordered.size(); i++) ordered[i].orderedIdx = (uint32_t)i;
+			std::vector<GcSeedHit>& byPos = seedsByPos[r];
+			byPos = ordered;
+			std::sort(byPos.begin(), byPos.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seqPos < right.seqPos; });
+			for (size_t i = 0; i < byPos.size(); i++) { byPos[i].byPosIdx = (uint32_t)i; ordered[byPos[i].orderedIdx].byPosIdx = (uint32_t)i; }
 		}
 	}
-	phase("seed");
-	std::vector<gcgpu_ext_item> items;
-	std::vector<gcgpu_ext_result> results;
-	const uint64_t* traces = nullptr;
-	size_t extendCalls = 0;
-	auto runExtend = [&]()
 	{
-		results.resize(items.size());
-		if (tracePool.size() <= extendCalls) tracePool.emplace_back(new Pinned());
-		Pinned& buf = *tracePool[extendCalls];
-		uint64_t used = 0;
+		uint64_t totalCells = 0;
+		for (size_t r = 0; r < R; r++) { rd[r].first_cell = (uint32_t)totalCells; rd[r].num_cells = (uint32_t)seedsByPos[r].size(); totalCells += seedsByPos[r].size(); }
+		if (totalCells >= 0xFFFFFFFFull) throw std::runtime_error("too many seeds in one batch");
+		cellBuf.ensure((totalCells + 1) * sizeof(gcgpu_seed_cell));
+		gcgpu_seed_cell* cells = (gcgpu_seed_cell*)cellBuf.p;
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t r = 0; r < R; r++)
+		{
+			const std::vector<GcSeedHit>& byPos = seedsByPos[r];
+			for (size_t i = 0; i < byPos.size(); i++)
+			{
+				gcgpu_seed_cell& c = cells[rd[r].first_cell + i];
+				c.seq_pos = (int32_t)byPos[i].seqPos; c.node = (uint32_t)byPos[i].alignmentGraphNodeId; c.read = (uint32_t)r; c.offset = (uint8_t)byPos[i].alignmentGraphNodeOffset;
+				c.flags = byPos[i].seedClusterSize >= params.seedClusterMinSize ? 1 : 0; c.reserved = 0;
+			}
+		}
 		double tDev = wallNow();
-		// the read codes were uploaded by gcgpu_seed and stay resident (seq == NULL);
-		// two-phase call: the page-locked trace buffer is sized from what the extensions really produced
-		int rc = gcgpu_extend(ctx, nullptr, b.codesBytes, items.data(), (uint32_t)items.size(), results.data(), nullptr, 0, &used);
-		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_extend");
-		buf.ensure((used + 1) * 8);
-		check(gcgpu_fetch_traces(ctx, (uint64_t*)buf.p, 0, used), "gcgpu_fetch_traces");
+		check(gcgpu_set_seed_cells(ctx, cells, totalCells, rd.data(), (uint32_t)R), "gcgpu_set_seed_cells");
 		devMs += wallNow() - tDev;
-		traces = (const uint64_t*)buf.p;
-		extendCalls++;
-		stats.k1Items += items.size();
-		stats.k1Ms += gcgpu_last_kernel_ms(ctx);
-		stats.k1Launches++;
-		uint64_t cols = 0;
-		for (const auto& r : results) cols += r.columns;
-		stats.k1Columns += cols;
-		if (traceOn) fprintf(stderr, "[gc] extend items=%zu kernel_ms=%.3f columns=%llu trace_MB=%.1f\n", items.size(), (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols, used * 8 / 1e6);
-	};
+	}
+	phase("seed");
 
 	// ---- S1: whole-read alignment, AlignOneWay(seeds, sloppy=true) (GraphAligner.h:114-203).
 	// The reference walks the seeds in goodness order and decides, from the alignments kept so far,
@@ -559,14 +343,25 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	// extends, for every read, the next few seeds that pass the skip rules under the current state;
 	// the results are then consumed strictly in seed order with the rules re-evaluated exactly as
 	// the reference does -- a speculative result whose seed turns out to be skipped is discarded.
-	struct S1Cand { size_t seedIdx; ExtRef ref; };
+	// The host sees an extension as (start, end, score) + one bit per seed of the read: "this seed's
+	// cell lies on the trace" (exactAlignmentPart, evaluated on the device for all seeds at once).
+	struct S1Aln
+	{
+		uint32_t pair = 0;               // index in trace set 0
+		const uint32_t* cover = nullptr; // bit i: seed i (position order) lies on the trace
+		int32_t traceScore = 0;
+		size_t alignmentStart = 0, alignmentEnd = 0, alignmentScore = 0, seedGoodness = 0;
+		bool degenerate() const { return !(alignmentEnd - 1 > alignmentStart); } // exactAlignmentPart asserts trace.back().seqPos > trace[0].seqPos
+		bool covers(const GcSeedHit& seed) const { return (cover[seed.byPosIdx >> 5] >> (seed.byPosIdx & 31)) & 1; }
+	};
+	struct S1Cand { size_t seedIdx; uint32_t ext; };
 	struct S1State
 	{
-		size_t i = 0; std::vector<GcPackedAln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0;
-		std::vector<gcgpu_ext_item> localItems; size_t itemBase = 0;
+		size_t i = 0; std::vector<S1Aln> alns; size_t seedsExtended = 0; size_t seedScoreForEndToEndAln = 0; bool done = false; std::vector<S1Cand> cands; size_t round = 0;
+		size_t extBase = 0;
 		// memo of the skip rules: alignments are only ever added and never change, so "this seed is skipped" is permanent and
 		// "no alignment so far contains this seed cell" only needs the alignments added since it was last asked
-		std::vector<GcPackedAln> alnsAdded;   // insertion order (alns is kept sorted by alignmentStart like the reference's vector)
+		std::vector<S1Aln> alnsAdded;         // insertion order (alns is kept sorted by alignmentStart like the reference's vector)
 		std::vector<uint8_t> skip;            // per seed: 1 = a skip rule fired
 		std::vector<uint32_t> checked;        // per seed: alnsAdded[0..checked) do not contain its cell
 		bool degenerate = false;              // an alignment on which exactAlignmentPart asserts exists: evaluate in reference order
@@ -583,40 +378,40 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			if (st.skip[idx]) return 1;
 			for (const auto& aln : st.alns)
 				if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) { st.skip[idx] = 1; return 1; }
-			bool assertion = false;
 			for (uint32_t k = st.checked[idx]; k < st.alnsAdded.size(); k++)
-				if (gcpipe::exactAlignmentPart(g, st.alnsAdded[k], seed, assertion)) { st.skip[idx] = 1; return 1; }
+				if (st.alnsAdded[k].covers(seed)) { st.skip[idx] = 1; return 1; }
 			st.checked[idx] = (uint32_t)st.alnsAdded.size();
 			return 0;
 		}
 		for (const auto& aln : st.alns)
 			if (aln.alignmentStart <= seed.seqPos && aln.alignmentEnd >= seed.seqPos && aln.seedGoodness > seed.seedGoodness) return 1;
-		bool assertion = false;
-		for (const auto& aln : st.alns) { if (gcpipe::exactAlignmentPart(g, aln, seed, assertion)) return 1; if (assertion) return 3; }
+		for (const auto& aln : st.alns) { if (aln.degenerate()) return 3; if (aln.covers(seed)) return 1; }
 		return 0;
 	};
+	std::vector<gcgpu_seed_ext> exts;
+	std::vector<gcgpu_pair_brief> brief;
+	std::vector<uint64_t> coverOff;
+	size_t s1Calls = 0;
 	while (true)
 	{
-		items.clear();
+		exts.clear();
 		std::vector<size_t> active;
-		// candidates are collected per read in parallel (work items local to the read), then concatenated
+		// candidates are collected per read in parallel, then concatenated
 		#pragma omp parallel for schedule(dynamic, 8)
 		for (size_t r = 0; r < R; r++)
 		{
 			S1State& st = s1[r];
 			if (st.done) continue;
-			GC_PROF_SCOPE(2, "s1.collect");
+			GC_PROF_SCOPE(3, "s1.collect");
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
 			size_t want = st.round == 0 ? params.s1FirstRoundSeeds : (st.round == 1 ? params.s1LaterRoundSeeds : params.s1TailRoundSeeds);
 			st.cands.clear();
-			st.localItems.clear();
 			for (size_t i = st.i; i < seedHits.size() && st.cands.size() < want; i++)
 			{
 				int rule = seedRule(st, seedHits[i], i);
 				if (rule >= 2) break; // decided again, in order, when the results are consumed
 				if (rule == 1) continue;
-				S1Cand c; c.seedIdx = i;
-				c.ref = makeItems(b, r, reads[r].sequence.size(), 0, reads[r].sequence.size(), seedHits[i], st.localItems);
+				S1Cand c; c.seedIdx = i; c.ext = 0;
 				st.cands.push_back(c);
 			}
 			st.round++;
@@ -627,22 +422,45 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				st.done = true;
 			}
 		}
+		coverOff.clear();
+		uint64_t coverWords = 0;
 		for (size_t r = 0; r < R; r++)
 		{
 			S1State& st = s1[r];
 			if (st.done || st.cands.empty()) continue;
-			st.itemBase = items.size();
-			items.insert(items.end(), st.localItems.begin(), st.localItems.end());
+			st.extBase = exts.size();
+			for (S1Cand& c : st.cands)
+			{
+				c.ext = (uint32_t)exts.size();
+				gcgpu_seed_ext e; e.cell = rd[r].first_cell + seedsOrdered[r][c.seedIdx].byPosIdx; e.frag_start = -1;
+				exts.push_back(e);
+				coverOff.push_back(coverWords);
+				coverWords += (rd[r].num_cells + 31) / 32;
+			}
 			active.push_back(r);
 		}
 		if (active.empty()) break;
+		coverOff.push_back(coverWords);
 		stats.s1Rounds++;
-		runExtend();
+		brief.resize(exts.size());
+		if (coverPool.size() <= s1Calls) coverPool.emplace_back(new Pinned());
+		Pinned& coverBuf = *coverPool[s1Calls];
+		coverBuf.ensure((coverWords + 1) * 4);
+		const uint32_t* cover = (const uint32_t*)coverBuf.p;
+		uint32_t firstPair = 0; uint64_t cols = 0;
+		{
+			double tDev = wallNow();
+			check(gcgpu_extend_seeds(ctx, 0, s1Calls > 0 ? 1 : 0, 0, exts.data(), (uint32_t)exts.size(), brief.data(), (uint32_t*)coverBuf.p, coverOff.data(), &firstPair, &cols), "gcgpu_extend_seeds");
+			devMs += wallNow() - tDev;
+			s1Calls++;
+			stats.k1Items += 2 * exts.size(); stats.k1Ms += gcgpu_last_kernel_ms(ctx); stats.k1Launches++; stats.k1Columns += cols;
+			if (traceOn) fprintf(stderr, "[gc] extend seeds=%zu kernel_ms=%.3f columns=%llu cover_KB=%.1f\n", exts.size(), (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols, coverWords * 4 / 1e3);
+		}
 		#pragma omp parallel for schedule(dynamic, 4)
 		for (size_t k = 0; k < active.size(); k++)
 		{
 			size_t r = active[k];
-			GC_PROF_SCOPE(3, "s1.consume");
+			GC_PROF_SCOPE(4, "s1.consume");
 			S1State& st = s1[r];
 			const std::vector<GcSeedHit>& seedHits = seedsOrdered[r];
 			size_t next = 0; // next unconsumed speculative result
@@ -657,15 +475,16 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				if (next >= st.cands.size() || st.cands[next].seedIdx != st.i) break; // not extended yet: first seed of the next round
 				const S1Cand& c = st.cands[next++];
 				st.seedsExtended += 1;
-				GcPackedAln item;
-				const gcgpu_ext_result* readResults = results.data() + st.itemBase;
-				bool ok = buildAlignment(seed, c.ref, readResults, traces, item);
-				for (int d = 0; d < 2; d++) if (c.ref.item[d] >= 0 && readResults[c.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
-				if (!ok || item.alignmentEnd == item.alignmentStart) continue;
+				const gcgpu_pair_brief& b = brief[c.ext];
+				if (b.flags & GCGPU_PAIR_INTERNAL) out[r].dropped = true;
+				if (!(b.flags & (GCGPU_PAIR_BWD | GCGPU_PAIR_FWD)) || b.end == b.start) continue;
+				S1Aln item;
+				item.pair = firstPair + c.ext; item.cover = cover + coverOff[c.ext];
+				item.traceScore = b.score; item.alignmentScore = (size_t)b.score; item.alignmentStart = (size_t)b.start; item.alignmentEnd = (size_t)b.end; item.seedGoodness = seed.seedGoodness;
 				st.alns.emplace_back(item);
 				st.alnsAdded.emplace_back(item);
-				{ uint32_t n = item.size(); if (n == 0 || !(item.seqPosAt(n - 1) > item.seqPosAt(0))) st.degenerate = true; }
-				std::sort(st.alns.begin(), st.alns.end(), [](const GcPackedAln& left, const GcPackedAln& right) { return left.alignmentStart < right.alignmentStart; });
+				if (item.degenerate()) st.degenerate = true;
+				std::sort(st.alns.begin(), st.alns.end(), [](const S1Aln& left, const S1Aln& right) { return left.alignmentStart < right.alignmentStart; });
 				if (st.alns[0].alignmentStart == 0)
 				{
 					size_t minSeedGoodness = st.alns[0].seedGoodness;
@@ -686,158 +505,85 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		}
 	}
 	phase("s1");
-	// GreedyLength selection of the GA alignments + their path strings (Aligner.cpp:637-654)
-	std::vector<std::vector<GcAlnItem>> longAlns(R);
-	std::vector<std::string> longPathSeq(R);
+	// GreedyLength selection of the GA alignments (Aligner.cpp:637-641)
+	std::vector<std::vector<S1Aln>> longAlns(R);
 	std::vector<size_t> longSeedsExtended(R, 0);
-	#pragma omp parallel for schedule(dynamic, 4)
-	for (size_t r = 0; r < R; r++)
-	{
-		GC_PROF_SCOPE(4, "s1.select+materialize+pathseq");
-		longSeedsExtended[r] = s1[r].seedsExtended;
-		if (out[r].dropped) { s1[r].alns.clear(); continue; }
-		if (!s1[r].alns.empty())
-		{
-			std::vector<GcPackedAln> sel = gcpipe::selectGreedyLength(s1[r].alns);
-			longAlns[r].resize(sel.size());
-			for (size_t k = 0; k < sel.size(); k++) materialize(reads[r].sequence.data(), sel[k], longAlns[r][k]);
-		}
-		s1[r].alns.clear();
-		if (!longAlns[r].empty()) longPathSeq[r] = gcpipe::traceToSequence(g, longAlns[r][0]);
-	}
-
-	// ---- S2: fragment anchoring (Aligner.cpp:656-730); all window seeds extended speculatively
-	struct FragSeed { uint32_t seedIdx; ExtRef ref; };
-	struct Frag { size_t l; size_t firstSeed, numSeeds; };
-	std::vector<std::vector<GcSeedHit>> seedsByPos(R);
-	std::vector<std::vector<Frag>> frags(R);
-	std::vector<std::vector<FragSeed>> fragSeeds(R);
-	items.clear();
-	const size_t len = (size_t)params.colinearSplitLen, sep = (size_t)params.colinearSplitGap;
-	// work items are generated per read in parallel (indices local to the read), then concatenated
-	std::vector<std::vector<gcgpu_ext_item>> localItems(R);
-	std::vector<size_t> itemBase(R + 1, 0);
-	#pragma omp parallel for schedule(dynamic, 4)
-	for (size_t r = 0; r < R; r++)
-	{
-		if (seedsOrdered[r].empty()) continue;
-		GC_PROF_SCOPE(5, "s2.items");
-		std::vector<GcSeedHit>& seeds = seedsByPos[r];
-		seeds = seedsOrdered[r];
-		std::sort(seeds.begin(), seeds.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seqPos < right.seqPos; });
-		if (out[r].dropped) continue; // `cont` stays true after an assertion: every fragment is skipped (Aligner.cpp:700-703)
-		const std::string& sequence = reads[r].sequence;
-		size_t sl = 0, sr = 0;
-		for (size_t l = 0; l + len <= sequence.length(); l += sep)
-		{
-			while (sr < seeds.size() && seeds[sr].seqPos + seeds[sr].matchLen <= l + len) sr++;
-			while (sl < sr && seeds[sl].seqPos < l) sl++;
-			if (sl >= sr) continue;
-			Frag f; f.l = l; f.firstSeed = fragSeeds[r].size(); f.numSeeds = sr - sl;
-			for (size_t i = sl; i < sr; i++)
-			{
-				GcSeedHit seed = seeds[i];
-				seed.seqPos -= l;
-				FragSeed fs; fs.seedIdx = (uint32_t)i;
-				fs.ref = makeItems(b, r, sequence.size(), l, len, seed, localItems[r]);
-				fragSeeds[r].push_back(fs);
-			}
-			frags[r].push_back(f);
-		}
-	}
-	for (size_t r = 0; r < R; r++) itemBase[r + 1] = itemBase[r] + localItems[r].size();
-	items.resize(itemBase[R]);
 	#pragma omp parallel for schedule(dynamic, 16)
 	for (size_t r = 0; r < R; r++)
 	{
-		if (!localItems[r].empty()) memcpy(items.data() + itemBase[r], localItems[r].data(), localItems[r].size() * sizeof(gcgpu_ext_item));
-		std::vector<gcgpu_ext_item>().swap(localItems[r]);
-	}
-	extendCalls = 0; // S1's trace buffers are free again
-	if (!items.empty()) runExtend();
-	// in-order filter + anchors
-	struct AnchorRec { std::vector<size_t> path; size_t x, y; size_t firstNode, firstOffset, lastNode, lastOffset; };
-	std::vector<std::vector<AnchorRec>> anchors(R);
-	std::vector<size_t> s2SeedsExtended(R, 0), lastFragExtended(R, 0);
-	#pragma omp parallel for schedule(dynamic, 4)
-	for (size_t r = 0; r < R; r++)
-	{
-		const std::string& sequence = reads[r].sequence;
-		GC_PROF_SCOPE(6, "s2.filter+anchors");
-		std::vector<GcPackedAln> kept;
-		for (const Frag& f : frags[r])
-		{
-			kept.clear();
-			size_t before = s2SeedsExtended[r];
-			for (size_t k = 0; k < f.numSeeds; k++)
-			{
-				const FragSeed& fs = fragSeeds[r][f.firstSeed + k];
-				GcSeedHit seed = seedsByPos[r][fs.seedIdx];
-				seed.seqPos -= f.l;
-				if (seed.seedClusterSize < params.seedClusterMinSize) continue;
-				bool found = false, assertion = false;
-				for (const auto& aln : kept) if (gcpipe::exactAlignmentPart(g, aln, seed, assertion)) { found = true; break; }
-				if (assertion) { out[r].dropped = true; break; }
-				if (found) continue;
-				s2SeedsExtended[r] += 1;
-				const gcgpu_ext_result* readResults = results.data() + itemBase[r];
-				for (int d = 0; d < 2; d++) if (fs.ref.item[d] >= 0 && readResults[fs.ref.item[d]].status == GCGPU_ITEM_INTERNAL) out[r].dropped = true;
-				GcPackedAln item;
-				if (!buildAlignment(seed, fs.ref, readResults, traces, item)) continue;
-				if (item.alignmentEnd == item.alignmentStart) continue;
-				kept.emplace_back(item);
-			}
-			if (out[r].dropped) break;
-			lastFragExtended[r] = s2SeedsExtended[r] - before;
-			GC_PROF_SCOPE(7, "s2.anchors");
-			for (const GcPackedAln& alignment : kept)
-			{
-				AnchorRec a; a.x = f.l; a.y = f.l + len - 1;
-				uint32_t n = alignment.size();
-				GcHostGraph::UnitigCache ucache;
-				for (uint32_t k = 0; k < n; k++)
-				{
-					size_t node = gcpipe::packedSplitNode(g, alignment, k, ucache);
-					if (a.path.empty() || node != a.path.back()) a.path.push_back(node);
-				}
-				int n0, n1; size_t o0, o1;
-				gcpipe::packedNodePos(g, alignment, 0, n0, o0);
-				gcpipe::packedNodePos(g, alignment, n - 1, n1, o1);
-				a.firstNode = a.path[0]; a.firstOffset = o0 - g.nodeOffset[a.firstNode];
-				a.lastNode = a.path.back(); a.lastOffset = o1 - g.nodeOffset[a.lastNode];
-				anchors[r].push_back(std::move(a));
-			}
-		}
-		if (out[r].dropped) anchors[r].clear();
+		longSeedsExtended[r] = s1[r].seedsExtended;
+		if (out[r].dropped) { out[r].broke = true; s1[r].alns.clear(); continue; }
+		if (!s1[r].alns.empty()) longAlns[r] = gcpipe::selectGreedyLength(s1[r].alns);
+		s1[r].alns.clear();
 	}
 
+	// ---- S2: fragment anchoring (Aligner.cpp:656-730): every window seed of every fragment is extended speculatively, the
+	// in-order seed loop of each fragment and the anchors are evaluated on the device
+	const size_t len = (size_t)params.colinearSplitLen, sep = (size_t)params.colinearSplitGap;
+	std::vector<gcgpu_read_anchors> perRead(R);
+	{
+		std::vector<std::vector<gcgpu_frag>> localFrags(R);
+		std::vector<std::vector<gcgpu_seed_ext>> localExts(R);
+		#pragma omp parallel for schedule(dynamic, 8)
+		for (size_t r = 0; r < R; r++)
+		{
+			if (seedsByPos[r].empty() || out[r].dropped) continue; // `cont` stays true after an assertion in the whole-read pass: every fragment is skipped (Aligner.cpp:700-703)
+			GC_PROF_SCOPE(5, "s2.items");
+			const std::vector<GcSeedHit>& seeds = seedsByPos[r];
+			size_t L = reads[r].sequence.length();
+			size_t sl = 0, sr = 0;
+			for (size_t l = 0; l + len <= L; l += sep)
+			{
+				while (sr < seeds.size() && seeds[sr].seqPos + seeds[sr].matchLen <= l + len) sr++;
+				while (sl < sr && seeds[sl].seqPos < l) sl++;
+				if (sl >= sr) continue;
+				gcgpu_frag f; f.read = (uint32_t)r; f.start = (int32_t)l; f.first_ext = (uint32_t)localExts[r].size(); f.num_exts = (uint32_t)(sr - sl);
+				for (size_t i = sl; i < sr; i++) { gcgpu_seed_ext e; e.cell = rd[r].first_cell + (uint32_t)i; e.frag_start = (int32_t)l; localExts[r].push_back(e); }
+				localFrags[r].push_back(f);
+			}
+		}
+		std::vector<size_t> fragBase(R + 1, 0), extBase(R + 1, 0);
+		for (size_t r = 0; r < R; r++) { fragBase[r + 1] = fragBase[r] + localFrags[r].size(); extBase[r + 1] = extBase[r] + localExts[r].size(); }
+		std::vector<gcgpu_frag> frags(fragBase[R]);
+		extBuf.ensure((extBase[R] + 1) * sizeof(gcgpu_seed_ext));
+		gcgpu_seed_ext* fexts = (gcgpu_seed_ext*)extBuf.p;
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t r = 0; r < R; r++)
+		{
+			for (size_t k = 0; k < localFrags[r].size(); k++) { gcgpu_frag f = localFrags[r][k]; f.first_ext += (uint32_t)extBase[r]; frags[fragBase[r] + k] = f; }
+			if (!localExts[r].empty()) memcpy(fexts + extBase[r], localExts[r].data(), localExts[r].size() * sizeof(gcgpu_seed_ext));
+		}
+		uint64_t cols = 0;
+		double tDev = wallNow();
+		check(gcgpu_fragment_anchors(ctx, 1, (int32_t)len, fexts, (uint32_t)extBase[R], frags.data(), (uint32_t)frags.size(), (uint32_t)R, perRead.data(), &cols), "gcgpu_fragment_anchors");
+		devMs += wallNow() - tDev;
+		stats.k1Items += 2 * extBase[R]; stats.k1Ms += gcgpu_last_kernel_ms(ctx); stats.k1Launches++; stats.k1Columns += cols;
+		if (traceOn) fprintf(stderr, "[gc] fragments=%zu seeds=%zu kernel_ms=%.3f columns=%llu\n", frags.size(), extBase[R], (double)gcgpu_last_kernel_ms(ctx), (unsigned long long)cols);
+	}
 	phase("s2");
-	// ---- S3: chaining (K2)
-	std::vector<gcgpu_anchor> flatAnchors;
-	std::vector<uint64_t> anchorOff(R + 1, 0);
-	for (size_t r = 0; r < R; r++)
-	{
-		for (const AnchorRec& a : anchors[r])
-		{
-			gcgpu_anchor ga; ga.start_node = (uint32_t)a.path[0]; ga.end_node = (uint32_t)a.path.back(); ga.x = (int32_t)a.x; ga.y = (int32_t)a.y;
-			flatAnchors.push_back(ga);
-		}
-		anchorOff[r + 1] = flatAnchors.size();
-	}
-	std::vector<uint32_t> chain(std::max<size_t>(1, flatAnchors.size())), chainLen(R);
+	// ---- S3: chaining (K2) on the anchors the device holds; only the chained anchors come back
+	std::vector<uint32_t> chainLen(R);
 	std::vector<int64_t> chainScore(R);
-	{ double tDev = wallNow();
-	check(gcgpu_chain(ctx, flatAnchors.data(), anchorOff.data(), (uint32_t)R, chain.data(), chainLen.data(), chainScore.data()), "gcgpu_chain");
-	devMs += wallNow() - tDev; }
-	stats.k2Reads += R; stats.k2Anchors += flatAnchors.size(); stats.k2Ms += gcgpu_last_kernel_ms(ctx);
-
+	std::vector<gcgpu_chained_anchor> chained;
+	std::vector<uint32_t> chainedPaths;
+	std::vector<uint64_t> chainedOff(R + 1, 0);
+	{
+		uint64_t nChained = 0, nPathNodes = 0, nAnchors = 0;
+		double tDev = wallNow();
+		check(gcgpu_chain_resident(ctx, (uint32_t)R, chainLen.data(), chainScore.data(), &nChained, &nPathNodes), "gcgpu_chain_resident");
+		stats.k2Ms += gcgpu_last_kernel_ms(ctx);
+		chained.resize(nChained + 1); chainedPaths.resize(nPathNodes + 1);
+		check(gcgpu_fetch_chained(ctx, chained.data(), chainedPaths.data()), "gcgpu_fetch_chained");
+		devMs += wallNow() - tDev;
+		for (size_t r = 0; r < R; r++) { chainedOff[r + 1] = chainedOff[r] + chainLen[r]; nAnchors += perRead[r].anchors; if (perRead[r].dropped) out[r].broke = true; }
+		stats.k2Reads += R; stats.k2Anchors += nAnchors;
+	}
 	phase("s3");
 	// ---- S4: chain -> node path (Aligner.cpp:738-831).  A candidate segment is kept as (node path, first offset,
 	// last offset); its per-base position list (pathToTrace) is only materialised for the reads where the chain wins --
-	// here only its LENGTH (the `longest` comparison, `<` => first wins ties) and its base string are needed.
+	// here only its LENGTH (the `longest` comparison, `<` => first wins ties) is needed; the bases are expanded on the device.
 	struct PathSeg { std::vector<size_t> path; size_t firstOffset = 0, lastOffset = 0, size = 0; };
 	std::vector<PathSeg> longest(R);
-	std::vector<std::string> pathSeq(R);
 	// number of positions pathToTrace emits (same per-node tests by VALUE as Aligner.cpp:409-424)
 	auto pathTraceSize = [&](const std::vector<size_t>& path, size_t firstNodeOffset, size_t lastNodeOffset)
 	{
@@ -861,7 +607,6 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		#pragma omp for schedule(dynamic, 4)
 		for (size_t r = 0; r < R; r++)
 		{
-			const std::vector<AnchorRec>& A = anchors[r];
 			GC_PROF_SCOPE(8, "s4.all");
 			std::vector<size_t> pos_path;
 			size_t firstNodeOffset = 0, lastNodeOffset = 0;
@@ -873,23 +618,24 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			};
 			for (uint32_t ci = 0; ci < chainLen[r]; ci++)
 			{
-				const AnchorRec& anchor = A[chain[anchorOff[r] + ci]];
+				const gcgpu_chained_anchor& anchor = chained[chainedOff[r] + ci];
+				const uint32_t* apath = chainedPaths.data() + anchor.path_first;
 				if (pos_path.empty())
 				{
-					pos_path = anchor.path;
-					firstNodeOffset = anchor.firstOffset;
-					lastNodeOffset = anchor.lastOffset;
+					pos_path.assign(apath, apath + anchor.path_len);
+					firstNodeOffset = anchor.first_offset;
+					lastNodeOffset = anchor.last_offset;
 					for (size_t j : pos_path) inPath[j] = epoch;
 				}
 				else
 				{
-					bool gap = anchor.path[0] == pos_path.back() && params.colinearGap != -1 && (long long)anchor.firstOffset - (long long)lastNodeOffset > params.colinearGap + 1;
+					bool gap = apath[0] == pos_path.back() && params.colinearGap != -1 && (long long)anchor.first_offset - (long long)lastNodeOffset > params.colinearGap + 1;
 					std::vector<size_t> path;
-					if (inPath[anchor.path[0]] != epoch && pos_path.back() != anchor.firstNode)
+					if (inPath[apath[0]] != epoch && pos_path.back() != apath[0])
 					{
 						long long gapLimit = params.colinearGap;
-						if (gapLimit != -1) gapLimit -= (long long)anchor.firstOffset + (long long)((long long)g.nodeLength[pos_path.back()] - (long long)lastNodeOffset - 1);
-						path = gcpipe::getChainPath(g, scratch, pos_path.back(), anchor.firstNode, gapLimit);
+						if (gapLimit != -1) gapLimit -= (long long)anchor.first_offset + (long long)((long long)g.nodeLength[pos_path.back()] - (long long)lastNodeOffset - 1);
+						path = gcpipe::getChainPath(g, scratch, pos_path.back(), apath[0], gapLimit);
 						if (path.empty()) gap = true;
 					}
 					if (gap)
@@ -897,86 +643,93 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 						closeSegment();
 						epoch++; // nodes.clear()
 						pos_path.clear();
-						firstNodeOffset = anchor.firstOffset;
+						firstNodeOffset = anchor.first_offset;
 					}
 					else
 						for (size_t j : path) if (inPath[j] != epoch) { inPath[j] = epoch; pos_path.push_back(j); }
-					for (size_t j : anchor.path) if (inPath[j] != epoch) { inPath[j] = epoch; pos_path.push_back(j); }
-					lastNodeOffset = anchor.lastOffset;
+					for (uint32_t k = 0; k < anchor.path_len; k++) { size_t j = apath[k]; if (inPath[j] != epoch) { inPath[j] = epoch; pos_path.push_back(j); } }
+					lastNodeOffset = anchor.last_offset;
 				}
 			}
 			if (!pos_path.empty()) closeSegment();
-			GC_PROF_SCOPE(9, "s4.pathSeq");
-			const PathSeg& lg = longest[r];
-			pathSeq[r].reserve(lg.size);
-			for (size_t node : lg.path)
-			{
-				size_t S = 0, L = g.nodeLength[node];
-				if (node == lg.path[0]) S = lg.firstOffset;
-				else if (node == lg.path.back()) L = lg.lastOffset + 1;
-				for (size_t o = S; o < L; o++) pathSeq[r].push_back(g.nodeChar((uint32_t)node, (uint32_t)o));
-			}
 		}
 	}
-
 	phase("s4");
-	// ---- S1b + S5: NW distances (K3), then the edit path only where the chain wins (S6)
-	// characters of the reads and path strings of the batch, in page-locked memory (the copy to the device runs at PCIe rate)
-	char* nwBuf = nullptr; size_t nwBufSize = 0;
+	// ---- S1b + S5: NW distances (K3), then the edit path only where the chain wins (S6).  The sequence buffer is put
+	// together on the device: the read, the padded path of the first whole-read alignment, the bases of the chained path.
 	std::vector<gcgpu_nw_item> nwItems;
 	std::vector<int> gaItem(R, -1), clcItem(R, -1);
-	std::vector<uint64_t> readOffInBuf(R);
+	uint64_t nwBufSize = 0;
 	{
-		// layout first (serial, a few integers per read), then the character copies in parallel
-		uint64_t total = 0;
+		std::vector<gcgpu_nw_piece> pieces;
+		std::vector<uint32_t> pathNodes;
+		std::vector<int> readPiece(R, -1), gaPiece(R, -1), clcPiece(R, -1);
 		for (size_t r = 0; r < R; r++)
 		{
 			bool needGa = !longAlns[r].empty();
 			bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
 			if (!needGa && !needClc) continue;
-			readOffInBuf[r] = total;
-			total += reads[r].sequence.size();
+			gcgpu_nw_piece pc; memset(&pc, 0, sizeof(pc));
+			pc.kind = GCGPU_PIECE_READ; pc.index = (uint32_t)r;
+			readPiece[r] = (int)pieces.size(); pieces.push_back(pc);
+			if (needGa)
+			{
+				memset(&pc, 0, sizeof(pc));
+				pc.kind = GCGPU_PIECE_PAIR_PATH; pc.set = 0; pc.index = longAlns[r][0].pair;
+				gaPiece[r] = (int)pieces.size(); pieces.push_back(pc);
+			}
+			if (needClc && !longest[r].path.empty())
+			{
+				memset(&pc, 0, sizeof(pc));
+				pc.kind = GCGPU_PIECE_NODE_PATH; pc.first_node = pathNodes.size(); pc.num_nodes = (uint32_t)longest[r].path.size();
+				pc.first_offset = (uint32_t)longest[r].firstOffset; pc.last_offset = (uint32_t)longest[r].lastOffset;
+				for (size_t node : longest[r].path) pathNodes.push_back((uint32_t)node);
+				clcPiece[r] = (int)pieces.size(); pieces.push_back(pc);
+			}
+		}
+		std::vector<uint64_t> pieceOff(pieces.size() + 1, 0);
+		if (!pieces.empty())
+		{
+			double tDev = wallNow();
+			check(gcgpu_nw_compose(ctx, pieces.data(), (uint32_t)pieces.size(), pathNodes.data(), pathNodes.size(), pieceOff.data()), "gcgpu_nw_compose");
+			devMs += wallNow() - tDev;
+			stats.k3Ms += gcgpu_last_kernel_ms(ctx);
+		}
+		nwBufSize = pieceOff[pieces.size()];
+		for (size_t r = 0; r < R; r++)
+		{
+			if (readPiece[r] < 0) continue;
+			bool needGa = gaPiece[r] >= 0;
+			bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
+			size_t readLen = reads[r].sequence.size();
 			// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
 			// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a
 			// starting point -- the kernel doubles the cutoff until the pass succeeds, like edlib does from 64.
-			int32_t kHint = 0, clcHint = (int32_t)(reads[r].sequence.size() / 5);
+			int32_t kHint = 0, clcHint = (int32_t)(readLen / 5);
 			if (needGa)
 			{
 				// the whole-read alignment IS a global alignment of (its padded path string, read): its score + the unaligned read
 				// ends + the padding of the first and last node (< 2 x 64 graph characters, traceToPoses) bounds the distance from
 				// above, so one pass at that cutoff always succeeds
-				const GcAlnItem& a0 = longAlns[r][0];
-				size_t ub = a0.alignmentScore + a0.alignmentStart + (reads[r].sequence.size() - a0.alignmentEnd);
+				const S1Aln& a0 = longAlns[r][0];
+				size_t ub = a0.alignmentScore + a0.alignmentStart + (readLen - a0.alignmentEnd);
 				kHint = (int32_t)std::min<size_t>(ub + 130, (size_t)1 << 30);
-				clcHint = (int32_t)std::min<size_t>(ub + ub * 3 / 10, reads[r].sequence.size() / 5);
-			}
-			if (needGa)
-			{
-				gcgpu_nw_item it; it.query_offset = total; it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)longPathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+				clcHint = (int32_t)std::min<size_t>(ub + ub * 3 / 10, readLen / 5);
+				gcgpu_nw_item it; it.query_offset = pieceOff[gaPiece[r]]; it.target_offset = pieceOff[readPiece[r]]; it.query_len = (int32_t)(pieceOff[gaPiece[r] + 1] - pieceOff[gaPiece[r]]); it.target_len = (int32_t)readLen;
 				it.k_hint = kHint; it.want_path = 0;
-				total += longPathSeq[r].size();
 				gaItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 			}
 			if (needClc)
 			{
-				gcgpu_nw_item it; it.query_offset = total; it.target_offset = readOffInBuf[r]; it.query_len = (int32_t)pathSeq[r].size(); it.target_len = (int32_t)reads[r].sequence.size();
+				gcgpu_nw_item it; it.target_offset = pieceOff[readPiece[r]]; it.target_len = (int32_t)readLen;
+				if (clcPiece[r] >= 0) { it.query_offset = pieceOff[clcPiece[r]]; it.query_len = (int32_t)(pieceOff[clcPiece[r] + 1] - pieceOff[clcPiece[r]]); }
+				else { it.query_offset = 0; it.query_len = 0; } // no chain: the empty path string
 				// the chained path usually costs 5-40 % more than the whole-read alignment; the first guess is capped at a fifth of
 				// the read (the widest band the two-blocks-per-lane class holds for 10 kb reads) and is also what a read without a
 				// whole-read alignment starts from (edlib's 64 would cost five doubling passes before the answer fits)
 				it.k_hint = clcHint; it.want_path = 0;
-				total += pathSeq[r].size();
 				clcItem[r] = (int)nwItems.size(); nwItems.push_back(it);
 			}
-		}
-		nwPinned.ensure(total + 16);
-		nwBuf = (char*)nwPinned.p; nwBufSize = total;
-		#pragma omp parallel for schedule(dynamic, 16)
-		for (size_t r = 0; r < R; r++)
-		{
-			if (gaItem[r] < 0 && clcItem[r] < 0) continue;
-			memcpy(&nwBuf[readOffInBuf[r]], reads[r].sequence.data(), reads[r].sequence.size());
-			if (gaItem[r] >= 0) memcpy(&nwBuf[nwItems[gaItem[r]].query_offset], longPathSeq[r].data(), longPathSeq[r].size());
-			if (clcItem[r] >= 0) memcpy(&nwBuf[nwItems[clcItem[r]].query_offset], pathSeq[r].data(), pathSeq[r].size());
 		}
 	}
 	std::vector<gcgpu_nw_result> nwRes(nwItems.size());
@@ -984,7 +737,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	if (!nwItems.empty())
 	{
 		double tDev = wallNow();
-		check(gcgpu_nw(ctx, nwBuf, nwBufSize, nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed), "gcgpu_nw");
+		int rc = gcgpu_nw(ctx, nullptr, nwBufSize, nwItems.data(), (uint32_t)nwItems.size(), nwRes.data(), nullptr, 0, &opsUsed);
+		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_nw");
 		devMs += wallNow() - tDev;
 		stats.k3Items += nwItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : nwRes) stats.k3Blocks += x.blocks;
@@ -1006,14 +760,15 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	for (size_t r = 0; r < R; r++)
 	{
 		GcReadResult& res = out[r];
-		res.anchors = anchors[r].size();
+		res.anchors = perRead[r].anchors;
 		res.chained = chainLen[r];
 		res.pathBp = longest[r].size;
 		res.hasLong = gaItem[r] >= 0;
-		if (gaItem[r] >= 0) res.longEditDistance = (size_t)nwRes[gaItem[r]].distance;
+		// edlib's status != OK leaves long_edit_distance at the read length (Aligner.cpp:646-648)
+		if (gaItem[r] >= 0) res.longEditDistance = nwRes[gaItem[r]].status == 0 ? (size_t)nwRes[gaItem[r]].distance : reads[r].sequence.size();
 		if (clcItem[r] >= 0) res.clcScore = (size_t)nwRes[clcItem[r]].distance;
 		res.seedsExtended = 0;
-		bool haveClc = clcItem[r] >= 0 && longest[r].size != 0;
+		bool haveClc = clcItem[r] >= 0 && longest[r].size != 0 && nwRes[clcItem[r]].status == 0;
 		bool better = haveClc && (longAlns[r].empty() || res.longEditDistance > res.clcScore);
 		res.usedChain = better;
 		if (better)
@@ -1024,40 +779,44 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		}
 	}
 	std::vector<gcgpu_nw_result> pathRes(pathItems.size());
-	std::vector<uint8_t> ops;
+	const uint8_t* ops = nullptr;
 	if (!pathItems.empty())
 	{
 		uint64_t cap = 0;
 		for (const auto& it : pathItems) cap += (uint64_t)it.query_len + it.target_len + 8;
-		ops.resize(cap);
+		opsBuf.ensure(cap + 16);
 		double tDev = wallNow();
-		check(gcgpu_nw(ctx, nullptr, nwBufSize, pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), ops.data(), ops.size(), &opsUsed), "gcgpu_nw(path)");
+		// an alignment whose edit path cannot be reconstructed degrades that read only: the reference clears `longest` when
+		// edlib's status is not OK and keeps the whole-read alignment (Aligner.cpp:846-848)
+		int rc = gcgpu_nw(ctx, nullptr, nwBufSize, pathItems.data(), (uint32_t)pathItems.size(), pathRes.data(), (uint8_t*)opsBuf.p, cap, &opsUsed);
+		if (rc != GCGPU_OK && rc != GCGPU_ERR_INTERNAL) check(rc, "gcgpu_nw(path)");
 		devMs += wallNow() - tDev;
+		ops = (const uint8_t*)opsBuf.p;
 		stats.k3Items += pathItems.size(); stats.k3Ms += gcgpu_last_kernel_ms(ctx);
 		for (const auto& x : pathRes) stats.k3Blocks += x.blocks;
 	}
 	phase("nw");
-	// ---- S5 trace conversion (Aligner.cpp:851-897) and final ordering (:1004)
+	// ---- S5 trace conversion (Aligner.cpp:851-897) for the reads where the chain wins
 	#pragma omp parallel for schedule(dynamic, 4)
 	for (size_t k = 0; k < pathRead.size(); k++)
 	{
 		size_t r = pathRead[k];
+		if (pathRes[k].status != 0 || pathRes[k].ops_len == 0) { out[r].usedChain = false; continue; }
 		const std::string& sequence = reads[r].sequence;
 		const std::vector<gcpipe::MatrixPos> lg = gcpipe::pathToTrace(g, longest[r].path, longest[r].firstOffset, longest[r].lastOffset);
-		const uint8_t* op = ops.data() + pathRes[k].ops_offset;
+		const uint8_t* op = ops + pathRes[k].ops_offset;
 		size_t n = pathRes[k].ops_len;
-		GcAlnItem item;
-		item.trace.resize(n);
+		std::vector<GcTokenStep> steps(n);
 		std::vector<size_t> splitNode(n);
 		size_t pos_i = 0, seq_i = 0;
 		for (size_t j = 0; j < n; j++)
 		{
-			GcTraceItem& t = item.trace[j];
+			GcTokenStep& t = steps[j];
 			size_t node = lg[pos_i].node, off = lg[pos_i].nodeOffset;
 			splitNode[j] = node;
-			t.seqPos = (int64_t)seq_i;
-			t.sequenceCharacter = seq_i < sequence.size() ? sequence[seq_i] : '-';
-			t.graphCharacter = g.nodeChar((uint32_t)node, (uint32_t)off);
+			t.seqPos = (int32_t)seq_i;
+			char sequenceCharacter = seq_i < sequence.size() ? sequence[seq_i] : '-';
+			t.match = gcpipe::characterMatch(sequenceCharacter, g.nodeChar((uint32_t)node, (uint32_t)off));
 			t.node = g.nodeIDs[node];
 			t.nodeOffset = (uint32_t)(off + g.nodeOffset[node]);
 			t.nodeSwitch = false;
@@ -1069,29 +828,65 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			pos_i = std::min(pos_i, lg.size() - 1);
 		}
 		// nodeSwitch compares the SPLIT nodes of consecutive entries (Aligner.cpp:880-884)
-		for (size_t j = 0; j + 1 < n; j++) item.trace[j].nodeSwitch = splitNode[j] != splitNode[j + 1];
-		if (n > 0)
-		{
-			item.traceScore = 0; // the reference leaves trace.score at 0 for the chained alignment
-			item.alignmentScore = out[r].clcScore;
-			item.alignmentStart = (size_t)item.trace[0].seqPos;
-			item.alignmentEnd = (size_t)item.trace.back().seqPos + 1;
-			out[r].alignments.clear();
-			out[r].alignments.push_back(std::move(item));
-		}
-		else out[r].usedChain = false;
+		for (size_t j = 0; j + 1 < n; j++) steps[j].nodeSwitch = splitNode[j] != splitNode[j + 1];
+		GcAlnItem item;
+		struct VecSrc { const std::vector<GcTokenStep>* v; GcTokenStep operator()(uint32_t i) const { return (*v)[i]; } } src { &steps };
+		GcTokenCounts cnt = gc_tokenize(src, (uint32_t)n, (uint32_t*)nullptr);
+		item.tokens.resize(cnt.tokens);
+		gc_tokenize(src, (uint32_t)n, item.tokens.data());
+		item.matches = cnt.matches; item.steps = cnt.matches + cnt.mismatches + cnt.insertions + cnt.deletions;
+		item.traceScore = 0; // the reference leaves trace.score at 0 for the chained alignment
+		item.alignmentScore = out[r].clcScore;
+		item.alignmentStart = (size_t)steps[0].seqPos;
+		item.alignmentEnd = (size_t)steps.back().seqPos + 1;
+		out[r].alignments.clear();
+		out[r].alignments.push_back(std::move(item));
 	}
-	for (size_t r = 0; r < R; r++)
+	// ---- S7 for the whole-read alignments that are written: mappings and edit runs from the device
 	{
-		GcReadResult& res = out[r];
-		if (!res.usedChain)
+		std::vector<uint32_t> pairs;
+		std::vector<size_t> firstOfRead(R + 1, 0);
+		for (size_t r = 0; r < R; r++)
 		{
-			res.alignments = std::move(longAlns[r]);
-			res.seedsExtended = res.alignments.empty() ? 0 : longSeedsExtended[r]; // stats.seedsExtended += alignments.seedsExtended (Aligner.cpp:995)
+			firstOfRead[r] = pairs.size();
+			if (!out[r].usedChain) for (const S1Aln& a : longAlns[r]) pairs.push_back(a.pair);
 		}
-		else res.seedsExtended = lastFragExtended[r]; // `alignments` still carries the last fragment's seedsExtended (Aligner.cpp:691,995)
-		res.seedsExtended += s2SeedsExtended[r];
-		std::sort(res.alignments.begin(), res.alignments.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+		firstOfRead[R] = pairs.size();
+		std::vector<gcgpu_aln_tokens> meta(pairs.size());
+		uint64_t used = 0;
+		if (!pairs.empty())
+		{
+			double tDev = wallNow();
+			check(gcgpu_encode_alignments(ctx, 0, pairs.data(), (uint32_t)pairs.size(), meta.data(), &used), "gcgpu_encode_alignments");
+			stats.k1Ms += gcgpu_last_kernel_ms(ctx);
+			tokenBuf.ensure((used + 1) * 4);
+			check(gcgpu_fetch_tokens(ctx, (uint32_t*)tokenBuf.p, 0, used), "gcgpu_fetch_tokens");
+			devMs += wallNow() - tDev;
+		}
+		const uint32_t* tok = (const uint32_t*)tokenBuf.p;
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t r = 0; r < R; r++)
+		{
+			GcReadResult& res = out[r];
+			if (!res.usedChain)
+			{
+				res.alignments.clear();
+				res.alignments.resize(longAlns[r].size());
+				for (size_t k = 0; k < longAlns[r].size(); k++)
+				{
+					const S1Aln& a = longAlns[r][k];
+					const gcgpu_aln_tokens& m = meta[firstOfRead[r] + k];
+					GcAlnItem& item = res.alignments[k];
+					item.tokens.assign(tok + m.token_offset, tok + m.token_offset + m.num_tokens);
+					item.matches = m.matches; item.steps = m.steps;
+					item.traceScore = a.traceScore; item.alignmentScore = a.alignmentScore; item.alignmentStart = a.alignmentStart; item.alignmentEnd = a.alignmentEnd; item.seedGoodness = a.seedGoodness;
+				}
+				res.seedsExtended = res.alignments.empty() ? 0 : longSeedsExtended[r]; // stats.seedsExtended += alignments.seedsExtended (Aligner.cpp:995)
+			}
+			else res.seedsExtended = perRead[r].last_frag_extended; // `alignments` still carries the last fragment's seedsExtended (Aligner.cpp:691,995)
+			res.seedsExtended += perRead[r].seeds_extended;
+			std::sort(res.alignments.begin(), res.alignments.end(), [](const GcAlnItem& left, const GcAlnItem& right) { return left.alignmentStart < right.alignmentStart; });
+		}
 	}
 	phase("final");
 #ifdef GC_PROF

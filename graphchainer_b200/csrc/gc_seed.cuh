@@ -44,6 +44,7 @@ GC_HD uint64_t gc_mz_hash(uint64_t k)
 // seeding base, MinimizerSeeder.cpp:24-43) -> 0..3, or -1
 GC_HD int gc_seed_base(uint8_t code)
 {
+	code &= 0xDF; // bit 5 (not an upper-case A C G T: only K3's byte comparison cares) does not stop seeding, charToInt takes both cases
 	return code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : code == 8 ? 3 : -1;
 }
 

@@ -33,6 +33,8 @@ struct GcSeedHit
 	size_t rawSeedGoodness;
 	size_t seedGoodness;
 	size_t seedClusterSize;
+	uint32_t orderedIdx = 0; // position after OrderSeeds (goodness order)
+	uint32_t byPosIdx = 0;   // position after the split pass's sort by seqPos (Aligner.cpp:667) = index of the seed's cell on the device
 };
 
 namespace gcseed {

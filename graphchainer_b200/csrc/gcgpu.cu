@@ -15,7 +15,9 @@
 #include "gc_k3.cuh"
 #include "gc_k3w.cuh"
 #include "gc_seed.cuh"
+#include "gc_post.cuh"
 #include "gc_host_graph.h"
+#include "gc_post_host.h"
 
 #define GCGPU_VERSION 1
 #define GC_K1_LONG_ITEM 96   // sequence length from which a K1 item gets a warp of its own
@@ -39,8 +41,8 @@ struct DevBuf
 		p = nullptr; cap = 0;
 		size_t want = bytes + bytes / 4 + 4096;
 		cudaError_t e = cudaMalloc(&p, want);
-		if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-		if (e == cudaSuccess) cap = want;
+		if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; } // the failed attempt must not stay behind as the "last error" of the next launch check
+		if (e == cudaSuccess) cap = want; else { cudaGetLastError(); p = nullptr; }
 		return e;
 	}
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -56,6 +58,7 @@ static cudaError_t uploadArray(const T* host, size_t count, T** dev)
 	return cudaMemcpy(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+struct GcResident;
 struct gcgpu_ctx
 {
 	int device = 0;
@@ -76,7 +79,9 @@ struct gcgpu_ctx
 	uint32_t* d_pathsStart = nullptr; uint32_t* d_pathsK = nullptr; uint32_t* d_backStart = nullptr; uint32_t* d_backNode = nullptr; uint32_t* d_backK = nullptr;
 	bool haveMpc = false;
 	GcMpcView mpc;
-	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc;
+	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc, itemsBuf;
+	uint64_t h2dBytes = 0, d2hBytes = 0; // bytes this ctx copied across PCIe (gcgpu_transfer_bytes)
+	GcResident* resident = nullptr;      // state of the resident batch entry points (gcgpu_resident.inl)
 	// minimizer index (S0)
 	GcMzSlot* d_mzSlots = nullptr;
 	GcMzView mz;
@@ -95,6 +100,29 @@ static cudaError_t gcSyncStream(gcgpu_ctx* ctx)
 	cudaError_t e = cudaEventRecord(ctx->evSync, ctx->stream);
 	if (e != cudaSuccess) return e;
 	return cudaEventSynchronize(ctx->evSync);
+}
+
+// every per-call copy across PCIe goes through here (gcgpu_transfer_bytes)
+static cudaError_t gcCopy(gcgpu_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+	if (bytes == 0) return cudaSuccess;
+	if (kind == cudaMemcpyHostToDevice) ctx->h2dBytes += bytes; else if (kind == cudaMemcpyDeviceToHost) ctx->d2hBytes += bytes;
+	return cudaMemcpyAsync(dst, src, bytes, kind, stream);
+}
+// grow a device buffer to `bytes`, keeping its first `keep` bytes
+static cudaError_t growKeep(gcgpu_ctx* ctx, DevBuf& b, size_t bytes, size_t keep)
+{
+	if (bytes <= b.cap) return cudaSuccess;
+	if (keep == 0 || !b.p) return b.ensure(bytes);
+	DevBuf nb;
+	cudaError_t e = nb.ensure(bytes + bytes / 2);
+	if (e != cudaSuccess) return e;
+	e = cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream);
+	if (e != cudaSuccess) { nb.release(); return e; }
+	e = cudaStreamSynchronize(ctx->stream);
+	b.release();
+	b = nb;
+	return e;
 }
 
 // ------------------------------------------------------------------ K1 kernels
@@ -117,25 +145,6 @@ static inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t k1WorkspaceBytes(uint32_t numSlices, uint32_t itemCap, uint32_t heapCap)
 {
 	return alignUp((size_t)(numSlices + 2) * sizeof(GcSliceMeta), 16) + (size_t)itemCap * sizeof(GcNodeItem) + (size_t)heapCap * 8;
-}
-
-__device__ __forceinline__ void gc_k1_run_item(const GcGraphView& g, const GcViterbiTables* vt, const GcK1Params& prm, const uint8_t* seq, const GcK1Desc& d,
-	uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, GcWord* cols)
-{
-	GcK1Workspace ws;
-	ws.cols = cols;
-	uint8_t* base = arena + d.wsOff;
-	ws.slices = (GcSliceMeta*)base;
-	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
-	ws.items = (GcNodeItem*)(base + slicesBytes);
-	ws.heap = (uint64_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem));
-	ws.itemCap = d.itemCap;
-	ws.heapCap = d.heapCap;
-	GcK1Result res;
-	gc_k1_extend(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, traceArena + d.traceOff, d.traceCap, res);
-	results[d.resultIndex] = res;
-	traceOffOfItem[d.resultIndex] = d.traceOff;
-	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
 }
 
 // Short work items (35-bp fragments: one or two slices): one thread = one item; the millions of
@@ -171,7 +180,14 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	GcK1Workspace ws;
 	gc_k1_workspace(d, arena, nullptr, ws); // the forward pass stores no columns (the last slice is flattened on the fly)
 	GcK1Result res;
-	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0; res.columns = 0;
+	if (d.seqLen < 0)
+	{
+		// this direction of the seed does not exist (seed at the first / last position of its sequence)
+		res.status = GC_FAILED;
+		results[d.resultIndex] = res; traceOffOfItem[d.resultIndex] = d.traceOff; lastSlice[t] = 0;
+		return;
+	}
 	int32_t last = gc_k1_forward(g, *vt, prm, seq + d.seqOff, d.seqLen, d.node, d.offset, ws, res);
 	if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
 	results[d.resultIndex] = res;
@@ -215,24 +231,31 @@ __device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* aren
 	ws.itemCap = d.itemCap;
 	ws.heapCap = d.heapCap;
 }
-// W = lanes per item (32, 16 or 8): a warp carries 32 / W items, each executed in lock-step by its own group of lanes
-template <int W>
+// the lanes of the warp execute ONE work item in lock-step
 __device__ __forceinline__ uint32_t gc_k1_group_setup(GcGraphView& g)
 {
-	g.coopLane = (int32_t)(threadIdx.x & (W - 1));
-	g.coopWidth = W;
-	g.coopShift = (threadIdx.x & 31u) & ~(uint32_t)(W - 1);
-	g.coopMask = (W >= 32 ? 0xFFFFFFFFu : ((1u << W) - 1u)) << g.coopShift;
-	return (blockIdx.x * blockDim.x + threadIdx.x) / W;
+	g.coopLane = (int32_t)(threadIdx.x & 31);
+	g.coopWidth = 32;
+	g.coopShift = 0;
+	g.coopMask = 0xFFFFFFFFu;
+	return (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+}
+// sequence offset and start cell of a long item come from the device-resident item (the host lays the slabs out from the lengths alone)
+__device__ __forceinline__ GcK1Desc gc_k1_long_desc(const GcK1Desc* __restrict__ descs, const gcgpu_ext_item* __restrict__ items, uint32_t t)
+{
+	GcK1Desc d = descs[t];
+	gcgpu_ext_item it = items[d.resultIndex];
+	d.seqOff = it.seq_offset; d.node = it.node; d.offset = it.offset;
+	return d;
 }
 template <int MIN_BLOCKS, int W>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
+__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq, const gcgpu_ext_item* __restrict__ items,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
 	__shared__ uint64_t heapShared[128 / W][64]; // the node queue of the slice being filled: a dozen dependent accesses per node visit
-	uint32_t t = gc_k1_group_setup<W>(g);
+	uint32_t t = gc_k1_group_setup(g);
 	if (t >= n) return;
-	GcK1Desc d = descs[t];
+	GcK1Desc d = gc_k1_long_desc(descs, items, t);
 	GcK1Workspace ws;
 	gc_k1_workspace(d, arena, nullptr, ws); // the forward pass stores no columns (the last slice is flattened on the fly)
 	if (ws.heapCap <= 64) ws.heap = heapShared[threadIdx.x / W];
@@ -248,13 +271,13 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_kernel(GcGraphView
 	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
 }
 template <int MIN_BLOCKS, int W>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq,
+__global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq, const gcgpu_ext_item* __restrict__ items,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
 {
 	__shared__ GcWord colsShared[128 / W][64];
-	uint32_t t = gc_k1_group_setup<W>(g);
+	uint32_t t = gc_k1_group_setup(g);
 	if (t >= n) return;
-	GcK1Desc d = descs[t];
+	GcK1Desc d = gc_k1_long_desc(descs, items, t);
 	GcK1Result res = results[d.resultIndex];
 	if (res.status != GC_OK) return;
 	GcK1Workspace ws;
@@ -263,39 +286,28 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphV
 	results[d.resultIndex] = res;
 }
 
-// Long work items, SIMT form: one THREAD per item, the 32 items of a warp are neighbours in the
-// length-sorted list.  gc_k1_forward / gc_k1_backtrace are written so that the lanes meet at one
-// column loop per node visit (see gc_k1.cuh); with tens of thousands of items in a round this form
-// does 32 items per warp where the lock-step kernel above does one, at the price of a longer
-// latency of the single item -- the host picks it when a round has enough items to fill the GPU.
-__global__ void __launch_bounds__(128) gc_k1_long_simt_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow)
-{
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
-	GcK1Desc d = descs[t];
-	GcWord cols[64];
-	gc_k1_run_item(g, vt, prm, seq, d, arena, traceArena, results, traceOffOfItem, overflow, cols);
-}
-
 // trace lengths of the finished items (input of the exclusive scan that places them in the dense buffer)
-__global__ void gc_k1_lengths_kernel(const GcK1Result* __restrict__ results, uint32_t n, uint64_t* __restrict__ lens)
+__global__ void gc_k1_lengths_kernel(const GcK1Result* __restrict__ results, uint32_t n, uint64_t* __restrict__ lens, uint64_t* total)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	GcK1Result r = results[i];
 	lens[i] = r.status == GC_OK ? r.traceLen : 0;
 }
+__global__ void gc_k1_total_kernel(const uint64_t* __restrict__ lens, const uint64_t* __restrict__ offs, uint32_t n, uint64_t* total)
+{
+	*total = offs[n - 1] + lens[n - 1];
+}
 // one warp per item: copy its trace to its place in the dense buffer, write the public result record
 __global__ void gc_k1_gather_kernel(const GcK1Result* __restrict__ results, const uint64_t* __restrict__ traceOffOfItem, const uint64_t* __restrict__ offs, uint32_t n,
-	const uint64_t* __restrict__ traceArena, uint64_t* __restrict__ dense, gcgpu_ext_result* __restrict__ pub, uint64_t* total)
+	const uint64_t* __restrict__ traceArena, uint64_t* __restrict__ dense, uint64_t denseStart, gcgpu_ext_result* __restrict__ pub)
 {
 	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	uint32_t lane = threadIdx.x & 31;
 	if (warp >= n) return;
 	GcK1Result r = results[warp];
 	uint32_t len = r.status == GC_OK ? r.traceLen : 0;
-	uint64_t dst = offs[warp], src = traceOffOfItem[warp];
+	uint64_t dst = denseStart + offs[warp], src = traceOffOfItem[warp];
 	for (uint32_t i = lane; i < len; i += 32) dense[dst + i] = traceArena[src + i];
 	if (lane == 0)
 	{
@@ -303,9 +315,11 @@ __global__ void gc_k1_gather_kernel(const GcK1Result* __restrict__ results, cons
 		o.status = r.status == GC_OK ? GCGPU_ITEM_OK : (r.status == GC_FAILED ? GCGPU_ITEM_FAILED : GCGPU_ITEM_INTERNAL);
 		o.score = r.score; o.trace_len = len; o.reserved = 0; o.trace_offset = dst; o.columns = r.columns;
 		pub[warp] = o;
-		if (warp == n - 1) *total = dst + len;
 	}
 }
+
+static int residentCreate(gcgpu_ctx* ctx, const gcgpu_graph* graph);
+static void residentDestroy(gcgpu_ctx* ctx);
 
 // ------------------------------------------------------------------ C ABI
 extern "C" int gcgpu_version(void) { return GCGPU_VERSION; }
@@ -320,7 +334,8 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
 	cudaFree(ctx->d_mzSlots); ctx->seedBuf.release(); ctx->seedMatches.release();
 	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
-	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release();
+	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release(); ctx->itemsBuf.release();
+	residentDestroy(ctx);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->evSync) cudaEventDestroy(ctx->evSync);
@@ -391,6 +406,8 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1; ctx->view.coopWidth = 32; ctx->view.coopMask = 0xFFFFFFFFu; ctx->view.coopShift = 0;
 	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
 	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
+	int rrc = residentCreate(ctx, graph);
+	if (rrc != GCGPU_OK) { gcgpu_destroy(ctx); return rrc; }
 	*out = ctx;
 	return GCGPU_OK;
 }
@@ -406,63 +423,67 @@ extern "C" void gcgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" float gcgpu_last_kernel_ms(gcgpu_ctx* ctx) { return ctx ? ctx->lastKernelMs : 0.f; }
 extern "C" uint64_t gcgpu_launch_count(gcgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
-	gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used)
+// ---- K1 execution on items that already sit in device memory (uploaded by gcgpu_extend, or generated on the device from
+// seed cells by gcgpu_extend_seeds / gcgpu_fragment_anchors).  The host only needs the items' sequence LENGTHS (slab layout).
+// lens[i] < 0: item i does not exist (a seed at the first / last position of its sequence has one direction only); its
+// result is GC_FAILED.  lens == nullptr: every item is shorter than GC_K1_LONG_ITEM, at most uniformMax long, and the
+// kernel itself skips the absent ones (seq_len < 0 in the device item).
+struct GcK1Run
 {
-	if (!ctx || (!items && n) || (!results && n) || !trace_used) return setError(GCGPU_ERR_ARG, "gcgpu_extend: null argument");
-	*trace_used = 0;
-	ctx->lastKernelMs = 0;
-	if (n == 0) return GCGPU_OK;
-	CUDA_TRY(cudaSetDevice(ctx->device));
-	// ---- validate, split into long (warp per item, longest first) and short (thread per item) work
-	int bad = -1;
-	int32_t maxShort = 0;
-	std::vector<uint32_t> longIdx;
+	uint32_t n = 0;
+	GcK1Result* dRes = nullptr; uint64_t* dSlot = nullptr; uint64_t* dLens = nullptr; uint64_t* dOffs = nullptr;
+	gcgpu_ext_result* dPub = nullptr; uint64_t* dTotal = nullptr;
+	uint64_t traceSlots = 0; // entries of the per-item trace slots (upper bound of the dense size)
+};
+
+__global__ void gc_k1_init_results_kernel(GcK1Result* results, uint64_t* slot, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	GcK1Result r; r.status = GC_FAILED; r.score = GC_INT_MAX; r.traceLen = 0; r.itemsUsed = 0; r.columns = 0;
+	results[i] = r;
+	slot[i] = 0;
+}
+
+static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* lens, uint32_t n, int32_t uniformMax, GcK1Run& run)
+{
+	// ---- split into long (warp per item, longest first) and short (thread per item) work
+	int32_t maxShort = lens ? 0 : uniformMax;
+	std::vector<uint32_t> longIdx, shortIdx;
+	uint32_t nShort = n;
+	bool needInit = false;
+	if (lens)
 	{
-		uint32_t numNodes = ctx->numNodes;
 		#pragma omp parallel
 		{
-			std::vector<uint32_t> mine; int32_t myMax = 0; int myBad = -1;
+			std::vector<uint32_t> mine; int32_t myMax = 0;
 			#pragma omp for schedule(static) nowait
 			for (uint32_t i = 0; i < n; i++)
 			{
-				const gcgpu_ext_item& it = items[i];
-				if (it.seq_len < 0 || it.seq_offset + (uint64_t)it.seq_len > seq_bytes || it.node >= numNodes || it.seq_len >= (1 << 24)) { myBad = (int)i; continue; }
-				if (it.seq_len >= GC_K1_LONG_ITEM) mine.push_back(i); else if (it.seq_len > myMax) myMax = it.seq_len;
+				if (lens[i] >= GC_K1_LONG_ITEM) mine.push_back(i); else if (lens[i] > myMax) myMax = lens[i];
 			}
 			#pragma omp critical
-			{ longIdx.insert(longIdx.end(), mine.begin(), mine.end()); if (myMax > maxShort) maxShort = myMax; if (myBad >= 0) bad = myBad; }
+			{ longIdx.insert(longIdx.end(), mine.begin(), mine.end()); if (myMax > maxShort) maxShort = myMax; }
 		}
+		std::sort(longIdx.begin(), longIdx.end(), [lens](uint32_t a, uint32_t b) { return lens[a] != lens[b] ? lens[a] > lens[b] : a < b; });
+		shortIdx.reserve(n - longIdx.size());
+		for (uint32_t i = 0; i < n; i++) if (lens[i] >= 0 && lens[i] < GC_K1_LONG_ITEM) shortIdx.push_back(i);
+		nShort = (uint32_t)shortIdx.size();
+		needInit = longIdx.size() + shortIdx.size() != n;
+		if (shortIdx.size() == n) shortIdx.clear(); // identity
 	}
-	if (bad >= 0) return setError(GCGPU_ERR_ARG, "gcgpu_extend: item " + std::to_string(bad) + " out of range");
-	std::sort(longIdx.begin(), longIdx.end(), [items](uint32_t a, uint32_t b) { return items[a].seq_len != items[b].seq_len ? items[a].seq_len > items[b].seq_len : a < b; });
-	uint32_t nLong = (uint32_t)longIdx.size(), nShort = n - nLong;
-	std::vector<uint32_t> shortIdx;
-	if (nLong && nShort)
-	{
-		shortIdx.reserve(nShort);
-		for (uint32_t i = 0; i < n; i++) if (items[i].seq_len < GC_K1_LONG_ITEM) shortIdx.push_back(i);
-	}
-	if (seq)
-	{
-		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
-		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		ctx->seqResident = seq_bytes;
-	}
-	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_extend: seq == NULL but no sequence buffer of this size is resident");
-
+	uint32_t nLong = (uint32_t)longIdx.size();
 	// ---- layout: long items get individual slabs, short items uniform ones
 	std::vector<GcK1Desc> descs(nLong);
 	size_t wsTotal = 0; uint64_t traceTotal = 0;
 	for (uint32_t k = 0; k < nLong; k++)
 	{
-		const gcgpu_ext_item& it = items[longIdx[k]];
 		GcK1Desc& d = descs[k];
-		d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
-		d.numSlices = (uint32_t)((it.seq_len + 63) / 64);
+		d.seqOff = 0; d.seqLen = lens[longIdx[k]]; d.node = 0; d.offset = 0; // sequence offset and start cell: from the device item
+		d.numSlices = (uint32_t)((d.seqLen + 63) / 64);
 		d.itemCap = 24 + 8 * d.numSlices;
 		d.heapCap = 64;
-		d.traceCap = (uint32_t)(2 * (uint64_t)it.seq_len + 72);
+		d.traceCap = (uint32_t)(2 * (uint64_t)d.seqLen + 72);
 		d.traceOff = traceTotal; traceTotal += d.traceCap;
 		d.resultIndex = longIdx[k];
 		d.wsOff = wsTotal;
@@ -477,8 +498,8 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	traceTotal += (uint64_t)nShort * lay.traceStride;
 	// small per-call device arrays: internal results | trace slot of every item | lengths | offsets | public results | scalars
 	size_t offRes = 0, offSlot = alignUp(offRes + (size_t)n * sizeof(GcK1Result), 128), offLens = alignUp(offSlot + (size_t)n * 8, 128), offOffs = alignUp(offLens + (size_t)n * 8, 128);
-	size_t offPub = alignUp(offOffs + (size_t)n * 8, 128), offScalars = alignUp(offPub + (size_t)n * sizeof(gcgpu_ext_result), 128), offItems = offScalars + 128;
-	size_t offShortIdx = alignUp(offItems + (size_t)n * sizeof(gcgpu_ext_item), 128), offLast = alignUp(offShortIdx + (size_t)shortIdx.size() * 4, 128), resEnd = offLast + (size_t)n * 4;
+	size_t offPub = alignUp(offOffs + (size_t)n * 8, 128), offScalars = alignUp(offPub + (size_t)n * sizeof(gcgpu_ext_result), 128);
+	size_t offShortIdx = offScalars + 128, offLast = alignUp(offShortIdx + (size_t)shortIdx.size() * 4, 128), resEnd = offLast + (size_t)n * 4;
 	CUDA_TRY(ctx->resBuf.ensure(resEnd));
 	CUDA_TRY(ctx->arena.ensure(wsTotal));
 	CUDA_TRY(ctx->traceArena.ensure(traceTotal * 8));
@@ -486,43 +507,25 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	GcK1Result* dRes = (GcK1Result*)(R + offRes); uint64_t* dSlot = (uint64_t*)(R + offSlot); uint64_t* dLens = (uint64_t*)(R + offLens); uint64_t* dOffs = (uint64_t*)(R + offOffs);
 	gcgpu_ext_result* dPub = (gcgpu_ext_result*)(R + offPub); uint32_t* dOverflow = (uint32_t*)(R + offScalars); uint64_t* dTotal = (uint64_t*)(R + offScalars + 8);
 	int32_t* dLast = (int32_t*)(R + offLast);
-	gcgpu_ext_item* dItems = (gcgpu_ext_item*)(R + offItems); uint32_t* dShortIdx = shortIdx.empty() ? nullptr : (uint32_t*)(R + offShortIdx);
+	uint32_t* dShortIdx = shortIdx.empty() ? nullptr : (uint32_t*)(R + offShortIdx);
+	run.n = n; run.dRes = dRes; run.dSlot = dSlot; run.dLens = dLens; run.dOffs = dOffs; run.dPub = dPub; run.dTotal = dTotal; run.traceSlots = traceTotal;
 	CUDA_TRY(cudaMemsetAsync(R + offScalars, 0, 128, ctx->stream));
-	if (nShort) CUDA_TRY(cudaMemcpyAsync(dItems, items, (size_t)n * sizeof(gcgpu_ext_item), cudaMemcpyHostToDevice, ctx->stream));
-	if (!shortIdx.empty()) CUDA_TRY(cudaMemcpyAsync(dShortIdx, shortIdx.data(), shortIdx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (!shortIdx.empty()) CUDA_TRY(gcCopy(ctx, dShortIdx, shortIdx.data(), shortIdx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (nLong)
 	{
 		CUDA_TRY(ctx->descBuf.ensure(descs.size() * sizeof(GcK1Desc)));
-		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), descs.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, descs.data(), descs.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
 	}
 	GcK1Params prm; prm.bandwidth = ctx->params.initial_bandwidth;
 	float ms = 0;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (needInit) { gc_k1_init_results_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, dSlot, n); ctx->launches++; }
 	if (nLong)
 	{
-		// one warp per item (shortest latency) unless GCGPU_K1_SIMT_MIN asks for the thread-per-item form from that many
-		// items on (measured on B200, r01d: 9094 items = 188 ms in SIMT form vs 24 ms in lock-step form -- 2 warps/SM cannot hide the walk's latency)
-		static const uint32_t simtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)atoll(getenv("GCGPU_K1_SIMT_MIN")) : 0xFFFFFFFFu;
-		if (nLong >= simtMin)
-			gc_k1_long_simt_kernel<<<(nLong + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow);
-		else
-		{
-			// resident blocks per SM: 5 (96 registers) by default; GCGPU_K1_LONG_BLOCKS=6 / 8 trade spills (~130 / ~300 bytes) for 24 / 32 warps per SM
-			static const int minBlocks = getenv("GCGPU_K1_LONG_BLOCKS") ? atoi(getenv("GCGPU_K1_LONG_BLOCKS")) : 5;
-#define GC_K1_LONG_LAUNCH(MB, W) do { const uint32_t perBlock = 128 / W; \
-				gc_k1_long_kernel<MB, W><<<(nLong + perBlock - 1) / perBlock, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast); \
-				gc_k1_long_bt_kernel<MB, W><<<(nLong + perBlock - 1) / perBlock, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast); } while (0)
-			// lanes per item: GCGPU_K1_LONG_WIDTH = 32 | 16 | 8
-			static const int width = getenv("GCGPU_K1_LONG_WIDTH") ? atoi(getenv("GCGPU_K1_LONG_WIDTH")) : 32;
-			if (width <= 8) { if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 8); else GC_K1_LONG_LAUNCH(5, 8); }
-			else if (width <= 16) { if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 16); else GC_K1_LONG_LAUNCH(5, 16); }
-			else if (minBlocks >= 8) GC_K1_LONG_LAUNCH(8, 32);
-			else if (minBlocks >= 6) GC_K1_LONG_LAUNCH(6, 32);
-			else GC_K1_LONG_LAUNCH(5, 32);
-#undef GC_K1_LONG_LAUNCH
-			ctx->launches++; // two launches: forward + backtrace
-		}
-		ctx->launches++;
+		// one warp per item in lock-step; resident blocks per SM: 5 (96 registers)
+		gc_k1_long_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+		gc_k1_long_bt_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+		ctx->launches += 2;
 	}
 	if (nShort)
 	{
@@ -534,7 +537,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	uint32_t overflow = 0;
-	CUDA_TRY(cudaMemcpyAsync(&overflow, dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, &overflow, dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
@@ -543,9 +546,12 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	{
 		// rare: some item outgrew its slab (very wide band).  Re-run those with 4x larger slabs until they fit.
 		std::vector<GcK1Result> hres(n);
-		CUDA_TRY(cudaMemcpy(hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost));
+		CUDA_TRY(gcCopy(ctx, hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost, ctx->stream));
 		std::vector<uint64_t> hslot(n);
-		CUDA_TRY(cudaMemcpy(hslot.data(), dSlot, (size_t)n * 8, cudaMemcpyDeviceToHost));
+		CUDA_TRY(gcCopy(ctx, hslot.data(), dSlot, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		std::vector<gcgpu_ext_item> hitems(n);
+		CUDA_TRY(gcCopy(ctx, hitems.data(), dItems, (size_t)n * sizeof(gcgpu_ext_item), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
 		uint32_t itemScale = 1, heapScale = 1;
 		std::vector<uint32_t> todo;
 		for (uint32_t i = 0; i < n; i++) if (hres[i].status == GC_OVERFLOW_ITEMS || hres[i].status == GC_OVERFLOW_HEAP) todo.push_back(i);
@@ -560,7 +566,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			size_t ws = 0;
 			for (size_t k = 0; k < todo.size(); k++)
 			{
-				const gcgpu_ext_item& it = items[todo[k]];
+				const gcgpu_ext_item& it = hitems[todo[k]];
 				GcK1Desc& d = rd[k];
 				d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
 				d.numSlices = (uint32_t)((it.seq_len + 63) / 64);
@@ -572,19 +578,20 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 			cudaError_t e = retryArena.ensure(ws);
 			if (e != cudaSuccess) { retryArena.release(); return setError(GCGPU_ERR_NOMEM, "gcgpu_extend: retry workspace"); }
 			CUDA_TRY(ctx->descBuf.ensure(rd.size() * sizeof(GcK1Desc)));
-			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK1Desc), cudaMemcpyHostToDevice, ctx->stream));
 			CUDA_TRY(cudaMemsetAsync(dOverflow, 0, 4, ctx->stream));
 			uint32_t m = (uint32_t)rd.size();
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-			gc_k1_long_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-			gc_k1_long_bt_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			gc_k1_long_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1_long_bt_kernel<5, 32><<<(m + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, m, (uint8_t*)retryArena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
 			ctx->launches += 2;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 			CUDA_TRY(gcSyncStream(ctx));
 			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 			ctx->lastKernelMs += ms;
-			CUDA_TRY(cudaMemcpy(hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost));
+			CUDA_TRY(gcCopy(ctx, hres.data(), dRes, (size_t)n * sizeof(GcK1Result), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(gcSyncStream(ctx));
 			std::vector<uint32_t> again;
 			for (uint32_t i : todo) if (hres[i].status == GC_OVERFLOW_ITEMS || hres[i].status == GC_OVERFLOW_HEAP) again.push_back(i);
 			todo.swap(again);
@@ -592,28 +599,76 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		retryArena.release();
 		if (!todo.empty()) return setError(GCGPU_ERR_NOMEM, "gcgpu_extend: " + std::to_string(todo.size()) + " work items still overflow their workspace after 8 attempts");
 	}
+	return GCGPU_OK;
+}
 
-	// ---- dense traces + public results, all on the device: lengths -> exclusive scan -> gather
-	CUDA_TRY(ctx->compact.ensure(traceTotal * 8 > (uint64_t)n * 8 ? (size_t)n * 8 : 8)); // grown to the real size below
+// dense traces + public results, all on the device: lengths -> exclusive scan -> gather into `dense` (grown to fit,
+// contents below denseStart preserved) from entry denseStart on.  *total = entries gathered.
+static int k1Gather(gcgpu_ctx* ctx, const GcK1Run& run, DevBuf& dense, uint64_t denseStart, uint64_t* total)
+{
+	uint32_t n = run.n;
+	float ms = 0;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	gc_k1_lengths_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, n, dLens);
+	gc_k1_lengths_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(run.dRes, n, run.dLens, run.dTotal);
 	size_t scanBytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dLens, dOffs, (int)n, ctx->stream);
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, run.dLens, run.dOffs, (int)n, ctx->stream);
 	CUDA_TRY(ctx->copyDesc.ensure(scanBytes + 16));
-	cub::DeviceScan::ExclusiveSum(ctx->copyDesc.p, scanBytes, dLens, dOffs, (int)n, ctx->stream);
-	// the dense buffer can never exceed the slots it is gathered from
-	CUDA_TRY(ctx->compact.ensure(traceTotal * 8 + 16));
-	gc_k1_gather_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(dRes, dSlot, dOffs, n, (const uint64_t*)ctx->traceArena.p, (uint64_t*)ctx->compact.p, dPub, dTotal);
-	ctx->launches += 3;
+	cub::DeviceScan::ExclusiveSum(ctx->copyDesc.p, scanBytes, run.dLens, run.dOffs, (int)n, ctx->stream);
+	gc_k1_total_kernel<<<1, 1, 0, ctx->stream>>>(run.dLens, run.dOffs, n, run.dTotal);
+	uint64_t used = 0;
+	CUDA_TRY(gcCopy(ctx, &used, run.dTotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	CUDA_TRY(growKeep(ctx, dense, (denseStart + used) * 8 + 16, denseStart * 8));
+	gc_k1_gather_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(run.dRes, run.dSlot, run.dOffs, n, (const uint64_t*)ctx->traceArena.p, (uint64_t*)dense.p, denseStart, run.dPub);
+	ctx->launches += 4;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-	uint64_t used = 0;
-	CUDA_TRY(cudaMemcpyAsync(&used, dTotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaMemcpyAsync(results, dPub, (size_t)n * sizeof(gcgpu_ext_result), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
 	GC_TRACE_MS("k1 scan+gather", n);
+	*total = used;
+	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes, const gcgpu_ext_item* items, uint32_t n,
+	gcgpu_ext_result* results, uint64_t* traces, uint64_t trace_capacity, uint64_t* trace_used)
+{
+	if (!ctx || (!items && n) || (!results && n) || !trace_used) return setError(GCGPU_ERR_ARG, "gcgpu_extend: null argument");
+	*trace_used = 0;
+	ctx->lastKernelMs = 0;
+	if (n == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	int bad = -1;
+	std::vector<int32_t> lens(n);
+	{
+		uint32_t numNodes = ctx->numNodes;
+		#pragma omp parallel for schedule(static)
+		for (uint32_t i = 0; i < n; i++)
+		{
+			const gcgpu_ext_item& it = items[i];
+			if (it.seq_len < 0 || it.seq_offset + (uint64_t)it.seq_len > seq_bytes || it.node >= numNodes || it.seq_len >= (1 << 24)) { _Pragma("omp critical") bad = (int)i; }
+			lens[i] = it.seq_len;
+		}
+	}
+	if (bad >= 0) return setError(GCGPU_ERR_ARG, "gcgpu_extend: item " + std::to_string(bad) + " out of range");
+	if (seq)
+	{
+		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
+		if (seq_bytes) CUDA_TRY(gcCopy(ctx, ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->seqResident = seq_bytes;
+	}
+	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_extend: seq == NULL but no sequence buffer of this size is resident");
+	CUDA_TRY(ctx->itemsBuf.ensure((size_t)n * sizeof(gcgpu_ext_item)));
+	CUDA_TRY(gcCopy(ctx, ctx->itemsBuf.p, items, (size_t)n * sizeof(gcgpu_ext_item), cudaMemcpyHostToDevice, ctx->stream));
+	GcK1Run run;
+	int rc = k1Run(ctx, (const gcgpu_ext_item*)ctx->itemsBuf.p, lens.data(), n, 0, run);
+	if (rc != GCGPU_OK) return rc;
+	uint64_t used = 0;
+	rc = k1Gather(ctx, run, ctx->compact, 0, &used);
+	if (rc != GCGPU_OK) return rc;
+	CUDA_TRY(gcCopy(ctx, results, run.dPub, (size_t)n * sizeof(gcgpu_ext_result), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
 	*trace_used = used;
 	ctx->denseTraces = used;
 	if (!traces && trace_capacity == 0) used = 0; // two-phase use: the caller sizes its buffer from *trace_used and calls gcgpu_fetch_traces
@@ -621,7 +676,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 	if (used)
 	{
 		if (!traces) return setError(GCGPU_ERR_ARG, "gcgpu_extend: null trace buffer");
-		CUDA_TRY(cudaMemcpyAsync(traces, ctx->compact.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, traces, ctx->compact.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 	}
 	bool internal = false;
@@ -637,7 +692,7 @@ extern "C" int gcgpu_fetch_traces(gcgpu_ctx* ctx, uint64_t* traces, uint64_t fir
 	if (first + count > ctx->denseTraces) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_traces: range beyond the traces of the last gcgpu_extend call");
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	CUDA_TRY(cudaMemcpyAsync(traces, (const uint64_t*)ctx->compact.p + first, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, traces, (const uint64_t*)ctx->compact.p + first, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	return GCGPU_OK;
 }
@@ -718,7 +773,7 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 	if (seq)
 	{
 		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
-		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		if (seq_bytes) CUDA_TRY(gcCopy(ctx, ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
 		ctx->seqResident = seq_bytes;
 	}
 	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_seed: seq == NULL but no sequence buffer of this size is resident");
@@ -729,14 +784,14 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 	CUDA_TRY(ctx->seedBuf.ensure(offScan + scanBytes + 16));
 	uint8_t* B = (uint8_t*)ctx->seedBuf.p;
 	gcgpu_seed_read* dReads = (gcgpu_seed_read*)(B + offReads); uint64_t* dCounts = (uint64_t*)(B + offCounts); uint64_t* dOffs = (uint64_t*)(B + offOffs);
-	CUDA_TRY(cudaMemcpyAsync(dReads, reads, (size_t)n * sizeof(gcgpu_seed_read), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, dReads, reads, (size_t)n * sizeof(gcgpu_seed_read), cudaMemcpyHostToDevice, ctx->stream));
 	float ms = 0;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	gc_seed_kernel<false><<<n, 256, 0, ctx->stream>>>(ctx->mz, (const uint8_t*)ctx->seqBuf.p, dReads, n, dCounts, nullptr, nullptr);
 	cub::DeviceScan::ExclusiveSum(B + offScan, scanBytes, dCounts, dOffs, (int)n + 1, ctx->stream);
 	ctx->launches += 2;
 	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpyAsync(match_offsets, dOffs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, match_offsets, dOffs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	uint64_t used = match_offsets[n];
 	CUDA_TRY(ctx->seedMatches.ensure(used * sizeof(gcgpu_seed_match) + 16));
@@ -755,7 +810,7 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 	if (used)
 	{
 		if (!matches) return setError(GCGPU_ERR_ARG, "gcgpu_seed: null match buffer");
-		CUDA_TRY(cudaMemcpyAsync(matches, ctx->seedMatches.p, used * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, matches, ctx->seedMatches.p, used * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 	}
 	return GCGPU_OK;
@@ -767,7 +822,7 @@ extern "C" int gcgpu_fetch_seed_matches(gcgpu_ctx* ctx, gcgpu_seed_match* matche
 	if (first + count > ctx->denseMatches) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_seed_matches: range beyond the matches of the last gcgpu_seed call");
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	CUDA_TRY(cudaMemcpyAsync(matches, (const gcgpu_seed_match*)ctx->seedMatches.p + first, count * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, matches, (const gcgpu_seed_match*)ctx->seedMatches.p + first, count * sizeof(gcgpu_seed_match), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	return GCGPU_OK;
 }
@@ -1261,7 +1316,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	if (seqs)
 	{
 		CUDA_TRY(ctx->nwSeqBuf.ensure(seq_bytes + 16));
-		if (seq_bytes) CUDA_TRY(cudaMemcpyAsync(ctx->nwSeqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		if (seq_bytes) CUDA_TRY(gcCopy(ctx, ctx->nwSeqBuf.p, seqs, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
 		ctx->nwResident = seq_bytes;
 	}
 	else if (ctx->nwResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_nw: seqs == NULL but no sequence buffer of this size is resident");
@@ -1297,7 +1352,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	if (distancesKnown)
 	{
 		for (uint32_t i = 0; i < n; i++) { hout[i].status = GC_OK; hout[i].distance = items[i].k_hint; hout[i].opsLen = 0; hout[i].pad = 0; hout[i].blocks = 0; }
-		CUDA_TRY(cudaMemcpyAsync(ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1329,7 +1384,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		descs.insert(descs.end(), wide.begin(), wide.end());
 		descs.insert(descs.end(), narrow.begin(), narrow.end());
 	}
-	CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 	if (nWide)
 	{
 		CUDA_TRY(cudaEventRecord(ctx->evFork, ctx->stream));
@@ -1346,7 +1401,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	if (nWide) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-	CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
@@ -1365,7 +1420,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		uint32_t m = (uint32_t)rd.size();
 		uint64_t blocksBefore = 0; // work of the aborted attempts is kept in the item's counter
 		(void)blocksBefore;
-		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), (size_t)m * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, rd.data(), (size_t)m * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 		if (cls == 1) gc_k3w_distance_kernel<1><<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		else gc_k3_distance_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
@@ -1373,7 +1428,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 		std::vector<GcK3Out> prev = hout;
-		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
@@ -1429,8 +1484,8 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			std::vector<GcK3LFrame> f0(m);
 			for (uint32_t k = 0; k < m; k++) { f0[k].f.qOff = 0; f0[k].f.q = pd[k].q; f0[k].f.tOff = 0; f0[k].f.t = pd[k].t; f0[k].f.best = pd[k].best; f0[k].item = k; f0[k].pad = 0; f0[k].opsOff = pd[k].opsOff; }
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
-			CUDA_TRY(cudaMemcpyAsync(frames[0], f0.data(), (size_t)m * sizeof(GcK3LFrame), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, pd.data(), pd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, frames[0], f0.data(), (size_t)m * sizeof(GcK3LFrame), cudaMemcpyHostToDevice, ctx->stream));
 			CUDA_TRY(cudaMemsetAsync(ctx->traceArena.p, 0xFF, opsTotal, ctx->stream));
 			gc_k3l_peq_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, itemWs);
 			ctx->launches++;
@@ -1445,7 +1500,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 				ctx->launches++;
 				CUDA_TRY(cudaGetLastError());
 				uint32_t cnt[2] = { 0, 0 };
-				CUDA_TRY(cudaMemcpyAsync(cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+				CUDA_TRY(gcCopy(ctx, cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
 				CUDA_TRY(gcSyncStream(ctx));
 				nIn = std::min<uint64_t>(cnt[1], frameCap);
 				cur ^= 1;
@@ -1454,7 +1509,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			ctx->launches++;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-			CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 			CUDA_TRY(gcSyncStream(ctx));
 			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 			ctx->lastKernelMs += ms;
@@ -1466,14 +1521,14 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		{
 		m = (uint32_t)dfs.size();
 		for (const GcK3Desc& d : dfs) { hout[d.resultIndex].pad = 0; hout[d.resultIndex].opsLen = 0; }
-		CUDA_TRY(cudaMemcpyAsync(ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->resBuf.p, hout.data(), (size_t)n * sizeof(GcK3Out), cudaMemcpyHostToDevice, ctx->stream));
 		// persistent warps: one workspace slot per resident warp, items fetched from a counter (longest first)
 		uint32_t ctas = std::min<uint32_t>((m + 3) / 4, 148 * 4);
 		size_t slotBytes = k3wPathSlotBytes(maxQ);
 		size_t slotsTotal = slotBytes * ctas * 4;
 		CUDA_TRY(ctx->arena.ensure(slotsTotal + 256));
 		CUDA_TRY(ctx->descBuf.ensure(dfs.size() * sizeof(GcK3Desc)));
-		CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, dfs.data(), dfs.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, dfs.data(), dfs.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 		uint32_t* counter = (uint32_t*)((uint8_t*)ctx->arena.p + slotsTotal);
 		CUDA_TRY(cudaMemsetAsync(counter, 0, 4, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1481,7 +1536,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-		CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
@@ -1495,14 +1550,14 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			size_t ws = 0;
 			for (GcK3Desc& d : rd) { d.wsOff = ws; ws += k3PathWorkspaceBytes(d.q); }
 			CUDA_TRY(ctx->arena.ensure(ws));
-			CUDA_TRY(cudaMemcpyAsync(ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, rd.data(), rd.size() * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 			uint32_t m2 = (uint32_t)rd.size();
 			CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 			gc_k3_path_kernel<<<(m2 + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m2, (uint8_t*)ctx->arena.p, (uint8_t*)ctx->traceArena.p, (GcK3Out*)ctx->resBuf.p);
 			ctx->launches++;
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-			CUDA_TRY(cudaMemcpyAsync(hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
 			CUDA_TRY(gcSyncStream(ctx));
 			CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 			ctx->lastKernelMs += ms;
@@ -1534,12 +1589,12 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		if (!ops) return setError(GCGPU_ERR_ARG, "gcgpu_nw: null ops buffer");
 		CUDA_TRY(ctx->compact.ensure(used + 16));
 		CUDA_TRY(ctx->copyDesc.ensure(copies.size() * sizeof(GcByteCopyDesc)));
-		CUDA_TRY(cudaMemcpyAsync(ctx->copyDesc.p, copies.data(), copies.size() * sizeof(GcByteCopyDesc), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ctx->copyDesc.p, copies.data(), copies.size() * sizeof(GcByteCopyDesc), cudaMemcpyHostToDevice, ctx->stream));
 		uint32_t m = (uint32_t)copies.size();
 		gc_bytes_gather_kernel<<<(m + 3) / 4, 128, 0, ctx->stream>>>((const GcByteCopyDesc*)ctx->copyDesc.p, m, (const uint8_t*)ctx->traceArena.p, (uint8_t*)ctx->compact.p);
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
-		CUDA_TRY(cudaMemcpyAsync(ops, ctx->compact.p, used, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcCopy(ctx, ops, ctx->compact.p, used, cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(gcSyncStream(ctx));
 	}
 	if (internal) return setError(GCGPU_ERR_INTERNAL, "gcgpu_nw: an alignment path could not be reconstructed");
@@ -1624,20 +1679,22 @@ extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const ui
 	size_t offCh = alignUp(offPr + total * 4, 128), offLen = alignUp(offCh + total * 4, 128), offScore = alignUp(offLen + (size_t)num_reads * 4, 128), end = offScore + (size_t)num_reads * 8;
 	CUDA_TRY(ctx->arena.ensure(end));
 	uint8_t* A = (uint8_t*)ctx->arena.p;
-	if (total) CUDA_TRY(cudaMemcpyAsync(A + offA, anchors, total * sizeof(GcAnchor), cudaMemcpyHostToDevice, ctx->stream));
-	CUDA_TRY(cudaMemcpyAsync(A + offO, read_offsets, ((size_t)num_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	if (total) CUDA_TRY(gcCopy(ctx, A + offA, anchors, total * sizeof(GcAnchor), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, A + offO, read_offsets, ((size_t)num_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	gc_k2_chain_kernel<<<num_reads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads,
 		(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-	if (total) CUDA_TRY(cudaMemcpyAsync(chain, A + offCh, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaMemcpyAsync(chain_len, A + offLen, (size_t)num_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(cudaMemcpyAsync(chain_score, A + offScore, (size_t)num_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (total) CUDA_TRY(gcCopy(ctx, chain, A + offCh, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, chain_len, A + offLen, (size_t)num_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, chain_score, A + offScore, (size_t)num_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	float ms = 0;
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs = ms;
 	return GCGPU_OK;
 }
+
+#include "gcgpu_resident.inl"

@@ -58,7 +58,7 @@ typedef struct gcalign_stats
 	uint64_t k3_items, k3_blocks;        /* NW alignments, 64-row block column steps       */
 	uint64_t launches;                   /* kernel launches                                */
 	uint64_t s1_rounds;
-	uint64_t h2d_bytes, d2h_bytes;       /* not tracked yet: 0                             */
+	uint64_t h2d_bytes, d2h_bytes;       /* bytes libgcgpu copied across PCIe for this call (gcgpu_transfer_bytes) */
 	uint64_t seeds_found, seeds_extended;
 	double s0_ms;                        /* seeding lookups (gcgpu_seed)                   */
 } gcalign_stats;

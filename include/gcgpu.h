@@ -75,6 +75,19 @@ typedef struct gcgpu_graph
 	const uint32_t* back_start;
 	const uint32_t* back_node;
 	const uint32_t* back_k;
+	/* original (bigraph-doubled) nodes, needed by the resident batch entry points below (may be NULL / 0 otherwise):
+	 *   node_ids[i]    = nodeIDs[i]     digraph node id 2*id+strand of split node i   (AlignmentGraph.h:148)
+	 *   node_offset[i] = nodeOffset[i]  offset of split node i in its original node   (AlignmentGraph.h:147)
+	 *   orig_*         = nodeLookup + originalNodeSize (AlignmentGraph.h:146,149) as CSR: original node o has digraph id
+	 *                    orig_ids[o], length orig_size[o] and the split nodes orig_nodes[orig_start[o] .. orig_start[o+1])
+	 *                    in offset order                                                                              */
+	const int32_t* node_ids;
+	const uint32_t* node_offset;
+	uint32_t num_orig;
+	const int32_t* orig_ids;
+	const uint32_t* orig_start;
+	const uint32_t* orig_nodes;
+	const uint32_t* orig_size;
 } gcgpu_graph;
 
 /* The constants of GraphAlignerCommon::Params the path honours (GraphAlignerCommon.h:92-126);
@@ -239,6 +252,138 @@ typedef struct gcgpu_anchor
 
 int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* read_offsets, uint32_t num_reads,
                 uint32_t* chain, uint32_t* chain_len, int64_t* chain_score);
+
+/* ---- resident batch: everything between the DP kernels, on the device --------------------
+ * The entry points above return every K1 trace to the host (8 bytes per DP cell of every extension, ~66 bytes per read
+ * base), where the reference's per-read logic then walks them.  The entry points below keep the traces of a batch in
+ * HBM ("trace sets") and run that logic where the traces are; the host sees alignment extents, seed-coverage bit
+ * masks, anchor records and edit runs (a few bytes per read base).
+ *
+ * gcgpu_load_reads        the reads' characters -> IUPAC codes (forward + reverse complement, what
+ *                         CommonUtils::ReverseComplement + Common::ambiguousMatch give, GraphAlignerCommon.h:219-296)
+ *                         and the byte codes K3 compares.  Codes of read r: forward at 2*char_offset, reverse
+ *                         complement at 2*char_offset + len of the resident K1 sequence buffer (seq == NULL in
+ *                         gcgpu_seed / gcgpu_extend with seq_bytes = 2 * char_bytes).
+ * gcgpu_set_seed_cells    the batch's seeds (SeedHit, GraphAlignerWrapper.h:11-37) after OrderSeeds, per read in the
+ *                         caller's order; reads[r].first_cell / num_cells delimit read r's cells.
+ * gcgpu_extend_seeds      getAlignmentFromSeed (GraphAligner.h:567-626) for a list of seeds: both K1 extensions of
+ *                         each seed, traces kept in trace set `set` (append != 0: after the pairs already there;
+ *                         *first_pair = index of exts[0]'s pair in the set).  brief[i] = extent and score of the
+ *                         merged alignment.  cover_bits != NULL: for every seed extension that produced an alignment,
+ *                         bit c of the words at cover_word_offsets[i] says whether cell first_cell+c of the same read
+ *                         lies on its trace (exactAlignmentPart, GraphAligner.h:407-461) -- the skip rule of
+ *                         AlignOneWay (:162-173) then needs no trace on the host.
+ * gcgpu_fragment_anchors  Aligner.cpp:668-730 for a batch: every window seed of every fragment extended (K1), the
+ *                         in-order seed loop of AlignOneWay per fragment, anchors (Aligner.cpp:706-729) left on the
+ *                         device for gcgpu_chain_resident.  frags must be grouped by read in ascending start.
+ * gcgpu_chain_resident    gcgpu_chain on the anchors gcgpu_fragment_anchors left; gcgpu_fetch_chained returns the
+ *                         chained anchors only (read order, chain order) with their node paths.
+ * gcgpu_nw_compose        builds the resident K3 sequence buffer from pieces: a read, the padded graph path of a
+ *                         whole-read alignment (traceToSequence, Aligner.cpp:376-408,425-428) or the bases of a
+ *                         chained node path (pathToTrace, Aligner.cpp:409-424); gcgpu_nw(seqs == NULL) then runs on it.
+ * gcgpu_encode_alignments GraphAlignerVGAlignment::traceToAlignment (GraphAlignerVGAlignment.h:37-165) for whole-read
+ *                         alignments of a trace set: mappings and edit runs as a uint32 token stream
+ *                         (mapping: 0, digraph node id, offset; edit: type << 30 | run length, type 0 match,
+ *                         1 mismatch, 2 insertion, 3 deletion).                                                  */
+#define GCGPU_TRACE_SETS 4
+
+typedef struct gcgpu_read
+{
+	uint64_t char_offset;
+	int32_t len;
+	uint32_t first_cell;
+	uint32_t num_cells;
+	uint32_t reserved;
+} gcgpu_read;
+
+typedef struct gcgpu_seed_cell
+{
+	int32_t seq_pos;      /* SeedHit::seqPos (k-mer END position in the read)          */
+	uint32_t node;        /* SeedHit::alignmentGraphNodeId (split node)                */
+	uint32_t read;        /* index of the read in the batch                            */
+	uint8_t offset;       /* SeedHit::alignmentGraphNodeOffset                         */
+	uint8_t flags;        /* bit 0: seedClusterSize >= seedClusterMinSize              */
+	uint16_t reserved;
+} gcgpu_seed_cell;
+
+typedef struct gcgpu_seed_ext
+{
+	uint32_t cell;        /* index into the batch's seed cells                         */
+	int32_t frag_start;   /* first read position of the fragment; < 0: the whole read  */
+} gcgpu_seed_ext;
+
+#define GCGPU_PAIR_BWD 1u       /* the backward extension produced a trace               */
+#define GCGPU_PAIR_FWD 2u       /* the forward extension produced a trace                */
+#define GCGPU_PAIR_INTERNAL 4u  /* an extension hit a state the reference asserts on     */
+typedef struct gcgpu_pair_brief
+{
+	int32_t start, end;   /* AlignmentItem::alignmentStart / alignmentEnd (coordinates of the aligned sequence) */
+	int32_t score;        /* OnewayTrace::score                                        */
+	uint32_t flags;       /* GCGPU_PAIR_*; neither BWD nor FWD: the extension failed   */
+} gcgpu_pair_brief;
+
+typedef struct gcgpu_frag
+{
+	uint32_t read;
+	int32_t start;        /* l of Aligner.cpp:675                                      */
+	uint32_t first_ext;   /* its window seeds exts[first_ext .. first_ext + num_exts)  */
+	uint32_t num_exts;
+} gcgpu_frag;
+
+typedef struct gcgpu_read_anchors
+{
+	uint32_t anchors;            /* A.size()                                                          */
+	uint32_t seeds_extended;     /* sum of alignments.seedsExtended over the fragments (Aligner.cpp:705) */
+	uint32_t last_frag_extended; /* seedsExtended of the last fragment that ran                        */
+	uint32_t dropped;            /* 1: a fragment hit an assertion-class state (cont = true, :695-703); the
+	                                anchors of the fragments before it are kept                          */
+} gcgpu_read_anchors;
+
+typedef struct gcgpu_chained_anchor
+{
+	uint32_t first_offset;  /* Apos[i][0]: offset in the first path node                */
+	uint32_t last_offset;   /* Apos[i][1]: offset in the last path node                 */
+	uint64_t path_first;    /* Anchor::path = path_nodes[path_first .. path_first + path_len) */
+	uint32_t path_len;
+	uint32_t reserved;
+} gcgpu_chained_anchor;
+
+#define GCGPU_PIECE_READ 0u       /* index = read                                           */
+#define GCGPU_PIECE_PAIR_PATH 1u  /* index = pair in trace set `set`                        */
+#define GCGPU_PIECE_NODE_PATH 2u  /* path_nodes[first_node .. first_node + num_nodes), first / last offset */
+typedef struct gcgpu_nw_piece
+{
+	uint32_t kind;
+	uint32_t set;
+	uint32_t index;
+	uint32_t num_nodes;
+	uint64_t first_node;
+	uint32_t first_offset;
+	uint32_t last_offset;
+} gcgpu_nw_piece;
+
+typedef struct gcgpu_aln_tokens
+{
+	uint64_t token_offset;
+	uint32_t num_tokens;
+	uint32_t matches;      /* identity = matches / steps (GraphAlignerVGAlignment.h:150)  */
+	uint32_t steps;
+	uint32_t reserved;
+} gcgpu_aln_tokens;
+
+int gcgpu_load_reads(gcgpu_ctx* ctx, const char* chars, uint64_t char_bytes, const gcgpu_read* reads, uint32_t n);
+int gcgpu_set_seed_cells(gcgpu_ctx* ctx, const gcgpu_seed_cell* cells, uint64_t num_cells, const gcgpu_read* reads, uint32_t n);
+int gcgpu_extend_seeds(gcgpu_ctx* ctx, int set, int append, int32_t frag_len, const gcgpu_seed_ext* exts, uint32_t n, gcgpu_pair_brief* brief,
+                       uint32_t* cover_bits, const uint64_t* cover_word_offsets, uint32_t* first_pair, uint64_t* columns);
+int gcgpu_fragment_anchors(gcgpu_ctx* ctx, int set, int32_t frag_len, const gcgpu_seed_ext* exts, uint32_t num_exts, const gcgpu_frag* frags, uint32_t num_frags,
+                           uint32_t num_reads, gcgpu_read_anchors* per_read, uint64_t* columns);
+int gcgpu_chain_resident(gcgpu_ctx* ctx, uint32_t num_reads, uint32_t* chain_len, int64_t* chain_score, uint64_t* chained_total, uint64_t* path_nodes_total);
+int gcgpu_fetch_chained(gcgpu_ctx* ctx, gcgpu_chained_anchor* anchors, uint32_t* path_nodes);
+int gcgpu_nw_compose(gcgpu_ctx* ctx, const gcgpu_nw_piece* pieces, uint32_t n, const uint32_t* path_nodes, uint64_t num_path_nodes, uint64_t* piece_offsets);
+int gcgpu_encode_alignments(gcgpu_ctx* ctx, int set, const uint32_t* pairs, uint32_t n, gcgpu_aln_tokens* out, uint64_t* tokens_used);
+int gcgpu_fetch_tokens(gcgpu_ctx* ctx, uint32_t* tokens, uint64_t first, uint64_t count);
+/* bytes copied host->device / device->host by this ctx so far */
+void gcgpu_transfer_bytes(gcgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
 
 /* Page-locked host memory for the caller-owned buffers above (cudaHostAlloc): copies to and from
  * such buffers run at full PCIe rate and asynchronously.  Plain malloc'd buffers work too. */
