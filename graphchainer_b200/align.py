@@ -9,8 +9,6 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgcalign.so")
-# tests on the GPU-less box point this at a build of gc_capi.cpp linked against the C-ABI test double
-_LIB_OVERRIDE = os.environ.get("GCALIGN_TEST_LIB")
 
 
 class Options(C.Structure):
@@ -33,10 +31,11 @@ SUMMARY = np.dtype([("num_alignments", "<u4"), ("used_chain", "<u4"), ("anchors"
 _lib = None
 
 
-def load():
+def load(path: str | None = None):
+    """Load libgcalign.so (or an explicitly given build of it) and declare its entry points."""
     global _lib
-    if _lib is None:
-        path = _LIB_OVERRIDE or LIB_PATH
+    if _lib is None or path is not None:
+        path = path or LIB_PATH
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (no CPU fallback exists)")
         lib = C.CDLL(path)
@@ -93,8 +92,9 @@ class ReadBatch:
 
 
 class Aligner:
-    def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0, streams: int = 0, gzip_level: int = 0, threads_per_stream: int = 0):
-        self.lib = load()
+    def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0, streams: int = 0, gzip_level: int = 0, threads_per_stream: int = 0,
+                 lib_path: str | None = None):
+        self.lib = load(lib_path)
         o = Options()
         self.lib.gcalign_default_options(C.byref(o))
         o.device, o.host_threads, o.streams = device, host_threads, streams

@@ -55,6 +55,19 @@ GC_HD void gc_reverse_cell(const GcPostGraph& pg, uint32_t node, uint32_t off, u
 	roff = ro - pg.nodeOffset[rnode];
 }
 
+// consecutive trace entries mostly stay inside one split node: remember the reverse-strand split node the last entry mapped to
+struct GcRevCache { uint32_t rawNode = 0xFFFFFFFFu; uint32_t revLast = 0; uint32_t rnode = 0; uint32_t lo = 1, hi = 0; };
+GC_HD void gc_reverse_cell_cached(const GcPostGraph& pg, uint32_t node, uint32_t off, uint32_t& rnode, uint32_t& roff, GcRevCache& c)
+{
+	if (node == c.rawNode)
+	{
+		uint32_t ro = c.revLast - off;
+		if (ro >= c.lo && ro < c.hi) { rnode = c.rnode; roff = ro - c.lo; return; }
+	}
+	gc_reverse_cell(pg, node, off, rnode, roff);
+	c.rawNode = node; c.revLast = pg.revLast[node]; c.rnode = rnode; c.lo = pg.nodeOffset[rnode]; c.hi = c.lo + pg.nodeLength[rnode];
+}
+
 // one seed of a read (GraphAlignerWrapper.h:11-37 SeedHit, the fields the extension and the skip rules read)
 struct GcSeedCell
 {
@@ -108,7 +121,7 @@ GC_HD uint32_t gc_pair_size(const GcPair& p) { return gc_pair_nb(p) + p.fwdLen; 
 // entry k of the merged trace (backward part in kernel order without its last entry -- the duplicated seed cell,
 // GraphAligner.h:599 -- then the forward part reversed), in forward-strand split-node coordinates
 struct GcMergedEntry { uint32_t node, offset; int32_t seqPos; bool nodeSwitch; bool fromBwd; uint32_t rawNode; uint32_t rawOffset; };
-GC_HD GcMergedEntry gc_pair_entry(const GcPostGraph& pg, const uint64_t* tr, const GcPair& p, uint32_t k)
+GC_HD GcMergedEntry gc_pair_entry(const GcPostGraph& pg, const uint64_t* tr, const GcPair& p, uint32_t k, GcRevCache* cache = nullptr)
 {
 	GcMergedEntry e;
 	uint32_t nb = gc_pair_nb(p);
@@ -116,7 +129,8 @@ GC_HD GcMergedEntry gc_pair_entry(const GcPostGraph& pg, const uint64_t* tr, con
 	{
 		uint64_t t = tr[p.bwdOff + k];
 		e.rawNode = gc_te_node(t); e.rawOffset = gc_te_offset(t);
-		gc_reverse_cell(pg, e.rawNode, e.rawOffset, e.node, e.offset);
+		if (cache) gc_reverse_cell_cached(pg, e.rawNode, e.rawOffset, e.node, e.offset, *cache);
+		else gc_reverse_cell(pg, e.rawNode, e.rawOffset, e.node, e.offset);
 		e.seqPos = (p.seedPos - 1) - gc_te_seqpos(t);
 		e.nodeSwitch = (k + 1 < p.bwdLen) ? gc_te_switch(tr[p.bwdOff + k + 1]) : false; // fixReverseTraceSeqPosAndOrder, GraphAligner.h:543-565
 		e.fromBwd = true;
@@ -224,10 +238,10 @@ GC_HD bool gc_fragment_filter(const GcPostGraph& pg, const uint64_t* tr, const G
 GC_HD uint32_t gc_anchor_path(const GcPostGraph& pg, const uint64_t* tr, const GcPair& p, uint32_t* pathOut, uint32_t& firstOffset, uint32_t& lastOffset)
 {
 	uint32_t n = gc_pair_size(p), len = 0, last = 0xFFFFFFFFu;
-	// backward entries map one raw (reverse-strand) split node to one or two forward-strand ones: convert per entry, cache per raw node run
+	GcRevCache cache;
 	for (uint32_t k = 0; k < n; k++)
 	{
-		GcMergedEntry e = gc_pair_entry(pg, tr, p, k);
+		GcMergedEntry e = gc_pair_entry(pg, tr, p, k, &cache);
 		if (len == 0 || e.node != last) { if (pathOut) pathOut[len] = e.node; len++; last = e.node; }
 		if (k == 0) firstOffset = e.offset;
 		if (k == n - 1) lastOffset = e.offset;
@@ -241,9 +255,10 @@ GC_HD uint32_t gc_pair_path_string(const GcPostGraph& pg, const uint64_t* tr, co
 {
 	uint32_t n = gc_pair_size(p), w = 0;
 	uint32_t lastNode = 0, lastOffset = 0, lastLength = 0;
+	GcRevCache cache;
 	for (uint32_t j = 0; j < n; j++)
 	{
-		GcMergedEntry e = gc_pair_entry(pg, tr, p, j);
+		GcMergedEntry e = gc_pair_entry(pg, tr, p, j, &cache);
 		if (j == 0)
 		{
 			lastNode = e.node; lastOffset = e.offset; lastLength = pg.nodeLength[e.node];

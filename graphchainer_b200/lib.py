@@ -62,7 +62,9 @@ class GraphStruct(C.Structure):
                 ("component_number", C.c_void_p), ("linearizable", C.c_void_p),
                 ("num_components", C.c_uint32),
                 ("comp_map", C.c_void_p), ("comp_idx", C.c_void_p), ("comp_start", C.c_void_p), ("topo_ids", C.c_void_p),
-                ("paths_start", C.c_void_p), ("paths_k", C.c_void_p), ("back_start", C.c_void_p), ("back_node", C.c_void_p), ("back_k", C.c_void_p)]
+                ("paths_start", C.c_void_p), ("paths_k", C.c_void_p), ("back_start", C.c_void_p), ("back_node", C.c_void_p), ("back_k", C.c_void_p),
+                ("node_ids", C.c_void_p), ("node_offset", C.c_void_p), ("num_orig", C.c_uint32),
+                ("orig_ids", C.c_void_p), ("orig_start", C.c_void_p), ("orig_nodes", C.c_void_p), ("orig_size", C.c_void_p)]
 
 
 class ParamsStruct(C.Structure):
@@ -150,6 +152,14 @@ class Context:
             g.back_start = arr("backStart", np.uint32)
             g.back_node = arr("backNode", np.uint32)
             g.back_k = arr("backK", np.uint32)
+        if "origIds" in index and "nodeIDs" in index:
+            g.node_ids = arr("nodeIDs", np.int32)
+            g.node_offset = arr("nodeOffset", np.uint32)
+            g.num_orig = len(index["origIds"])
+            g.orig_ids = arr("origIds", np.int32)
+            g.orig_start = arr("origStart", np.uint32)
+            g.orig_nodes = arr("origNodes", np.uint32)
+            g.orig_size = arr("origSize", np.uint32)
         p = ParamsStruct(bandwidth)
         h = C.c_void_p()
         rc = self.lib.gcgpu_create(device, C.byref(g), C.byref(p), C.byref(h))

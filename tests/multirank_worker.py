@@ -12,13 +12,13 @@ from graphchainer_b200 import align, gam, shard  # noqa: E402
 
 
 def main():
-    idx_path, fasta, golden_gam, out_flag = sys.argv[1:5]
+    idx_path, fasta, golden_gam, out_flag, lib_path = sys.argv[1:6]  # lib_path: libgcalign built against the C-ABI test double
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     batch = align.ReadBatch.from_fasta(fasta)
     mine = shard.length_balanced_shards(batch.lengths(), world)[rank]
     sub = batch.subset(mine)
-    aligner = align.Aligner(idx_path, device=0, host_threads=2, streams=2)
+    aligner = align.Aligner(idx_path, device=0, host_threads=2, streams=2, lib_path=lib_path)
     blob, summ, st = aligner.align(sub, gam=True)
     aligner.close()
     local = {}

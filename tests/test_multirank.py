@@ -28,9 +28,9 @@ def test_two_gloo_ranks_reproduce_golden_gam(golden_files, tmp_path):
                     os.path.join(ROOT, "graphchainer_b200", "csrc", "gc_capi.cpp"), os.path.join(ROOT, "tests", "hostsim", "gcgpu_sim.cpp"), "-lz"], check=True)
     idx, _ = golden_files["tiny"]
     flag = str(tmp_path / "result.txt")
-    env = dict(os.environ, GCALIGN_TEST_LIB=lib, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613",
-           os.path.join(ROOT, "tests", "multirank_worker.py"), idx, os.path.join(GOLDEN, "tiny.fa"), os.path.join(GOLDEN, "tiny.gam"), flag]
+           os.path.join(ROOT, "tests", "multirank_worker.py"), idx, os.path.join(GOLDEN, "tiny.fa"), os.path.join(GOLDEN, "tiny.gam"), flag, lib]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert open(flag).read() == "OK", open(flag).read()
