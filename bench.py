@@ -81,11 +81,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def time_reference(gfa: str, fasta: str, threads: int):
+def time_reference(gfa: str, fasta: str, threads: int, keep_gam: str | None = None):
     """Align-phase seconds of the unmodified reference: wall clock between its "Align" and
-    "Alignment finished" lines (src/Aligner.cpp:1258,1296); index build excluded."""
+    "Alignment finished" lines (src/Aligner.cpp:1258,1296); index build excluded.  keep_gam: where to leave its GAM output."""
     with tempfile.TemporaryDirectory() as d:
-        p = subprocess.Popen([REFBIN, "-t", str(threads), "-g", gfa, "-f", fasta, "-a", os.path.join(d, "ref.gam")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        out = keep_gam or os.path.join(d, "ref.gam")
+        p = subprocess.Popen([REFBIN, "-t", str(threads), "-g", gfa, "-f", fasta, "-a", out], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         t0 = t1 = None
         for line in p.stdout:
             if line.startswith("Align") and not line.startswith("Alignment") and t0 is None:
@@ -98,15 +99,42 @@ def time_reference(gfa: str, fasta: str, threads: int):
     return t1 - t0
 
 
+def write_repeated_fasta(path: str, reads, reps: int) -> int:
+    """The sample `reps` times in one file (names rep<r>_<name>): one reference process then aligns `reps` steps back to
+    back, so its index build, thread start-up and queue sleeps (Aligner.cpp:179,214,252,504) are paid once, not per step."""
+    total = 0
+    with open(path, "w") as f:
+        for r in range(reps):
+            for name, seq in reads:
+                f.write(f">rep{r}_{name}\n{seq}\n")
+                total += len(seq)
+    return total
+
+
+def parity_on_sample(ref_gam_path: str, our_members: dict, names):
+    """Decoded-GAM equality of the reference's output and ours on the sample reads (no speed number
+    counts before it).  our_members: {name: gzip member bytes of that read's record(s)}."""
+    from graphchainer_b200 import gam as gamlib
+    with open(ref_gam_path, "rb") as f:
+        ref = gamlib.read_gam_messages(f.read())
+    ours = {}
+    for name, member in our_members.items():
+        if len(member):
+            ours.update(gamlib.read_gam_messages(member))
+    n, diffs = gamlib.diff_messages(ours, ref, names=names, limit=5)
+    aligned = sum(1 for x in names if x in ref)
+    return {"reads": n, "reads_with_alignment_in_reference": aligned, "diffs": len(diffs), "first": diffs[:3]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default=None, help="c2 (default at --gpus 1: the configuration the metric is quoted on), c3 (default at --gpus > 1: BASELINE.json configs[2]), c4, c5")
     ap.add_argument("--reads", type=int, default=None, help="reads per step and GPU (default: the workload's full read set)")
-    ap.add_argument("--cpu-sample", type=int, default=640, help="reads in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="reads in the CPU baseline sample (per step of the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=6, help="read batches in flight per GPU in the e2e measurement")
     ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
@@ -118,10 +146,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from graphchainer_b200 import synth
+    if args.workload is None:
+        args.workload = "c2" if args.gpus <= 1 else "c3"
     cfg = dict(synth.WORKLOADS[args.workload])
-    n_reads = args.reads or cfg["n_reads"]
+    # c3's full read set (100 k x 15 kb = 1.5 Gbp per GPU) is a 15-s step: the default is a stated tenth of it on the full 51 Mbp graph
+    n_reads = args.reads or (cfg["n_reads"] if args.workload != "c3" else cfg["n_reads"] // 10)
     host_cores = os.cpu_count() or 1
-    config = {"workload": f"{args.workload}: synthetic {cfg['graph_len'] / 1e6:g} Mbp acyclic SNP/indel graph + {n_reads} simulated reads/GPU, length {cfg['read_len']}, {cfg['error'] * 100:g}% error (5% with a novel 400-bp insertion)",
+    read_len = cfg["read_len"] if isinstance(cfg["read_len"], int) else (cfg["read_len"][0] + cfg["read_len"][1]) // 2
+    args.cpu_sample = max(1, min(args.cpu_sample, n_reads, int(args.cpu_sample * 10_000 / read_len)))  # ~40 Mbp of reads per reference step
+    config = {"workload": f"{args.workload}: synthetic {cfg['graph_len'] / 1e6:g} Mbp acyclic SNP/indel graph + {n_reads} simulated reads/GPU, length {cfg['read_len']}, {cfg['error'] * 100:g}% error (5% with a novel 400-bp insertion)" + ("" if n_reads == cfg["n_reads"] else f" [{n_reads} of the configuration's {cfg['n_reads']} reads]"),
               "reads_per_gpu": n_reads, "graph_bp": cfg["graph_len"], "l2": "inputs larger than L2: slice/trace workspaces of a step exceed 126 MB",
               "value_timing": "sum of CUDA-event durations of the step's kernels", "e2e_timing": "wall time of gcalign_align() on host buffers incl. all copies and host stages"}
     tmp = tempfile.mkdtemp(prefix="gcbench_")
@@ -133,19 +166,24 @@ def main():
         if not os.path.exists(REFBIN):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/GraphChainer_ref not built"}))
             return
-        sample = min(args.cpu_sample, n_reads)
+        sample = args.cpu_sample
         gfa, reads = make_inputs(args.workload, sample, 0, tmp)
+        # one process aligns all timed steps back to back (and one before it the warm-up steps): the reference rebuilds its
+        # index in every process (86 s for c3 at -t 8), and a 0.5-s align phase per process would mostly measure its start-up
+        if args.warmup > 0:
+            warm = os.path.join(tmp, "warm.fa")
+            write_repeated_fasta(warm, reads, args.warmup)
+            time_reference(gfa, warm, host_cores)
         fa = os.path.join(tmp, "sample.fa")
-        bp = synth.write_fasta(fa, reads)
-        for _ in range(args.warmup):
-            time_reference(gfa, fa, host_cores)
-        secs = [time_reference(gfa, fa, host_cores) for _ in range(args.steps)]
-        t = sum(secs) / len(secs)
+        bp_total = write_repeated_fasta(fa, reads, args.steps)
+        t_all = time_reference(gfa, fa, host_cores)
+        bp = bp_total // args.steps
+        t = t_all / args.steps
         v = bp / t
         line = {"metric": "aligned read bp/sec", "value": v, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": {"value": v, "unit": "bp/s", "cores": host_cores, "kind": "reference",
-                                 "sample": f"first {sample} reads of the workload ({bp} bp) per step, unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only"},
+                                 "sample": f"first {sample} reads of the workload ({bp} bp) per step, {args.steps} steps back to back in one process, unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only"},
                 "e2e": {"value": v, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -189,6 +227,9 @@ def main():
         pcie_h2d, pcie_d2h = st["h2d_bytes"], st["d2h_bytes"]
     barrier()
     wall = time.perf_counter() - t0
+    # the sample reads' GAM records of the last timed step (the buffer is reused by the next call): parity gate below
+    sample_n = args.cpu_sample if (rank == 0 and not args.no_cpu_baseline) else 0
+    our_members = {reads[i][0]: bytes(gam[int(summ["gam_offset"][i]):int(summ["gam_offset"][i]) + int(summ["gam_size"][i])]) for i in range(sample_n)}
     try:
         int_peak = aligner.int_peak()
     except Exception:
@@ -235,38 +276,55 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     if k3_ms >= k1_ms:
-        dom, dom_ms, dom_bytes, dom_units, dom_ops = "gc_k3_distance_kernel+gc_k3_path_kernel", k3_ms, k3_blocks * K3_BYTES_PER_W, k3_blocks, K3_OPS_PER_W
+        dom, dom_ms, dom_bytes, dom_units, dom_ops = "K3: gc_k3w_distance_kernel + gc_k3l_level_kernel (NW distances and edit paths), all launches of a step", k3_ms, k3_blocks * K3_BYTES_PER_W, k3_blocks, K3_OPS_PER_W
     else:
-        dom, dom_ms, dom_bytes, dom_units, dom_ops = "K1: gc_k1_long_kernel + gc_k1_long_bt_kernel (whole-read extensions) + gc_k1_kernel + gc_k1_bt_kernel (fragments), all launches of a step", k1_ms, k1_cols * K1_BYTES_PER_W, k1_cols, K1_OPS_PER_W
+        dom, dom_ms, dom_bytes, dom_units, dom_ops = "K1: gc_k1s_forward_kernel + gc_k1s_backtrace_kernel (whole-read extensions) + gc_k1_kernel + gc_k1_bt_kernel (fragments), all launches of a step", k1_ms, k1_cols * K1_BYTES_PER_W, k1_cols, K1_OPS_PER_W
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    line = {"metric": "aligned read bp/sec", "value": bp_total / kern_max, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    int_ops = dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+    # DRAM traffic and pipe utilisation of the dominant kernel: from the committed ncu --set full capture (profiles/ncu_dominant_launch.json,
+    # written by profiles/ncu_summary.py from the .ncu-rep of this code state), never typed in
+    ncu_dom = None
+    try:
+        ncu_dom = json.load(open(os.path.join(ROOT, "profiles", "ncu_dominant_launch.json")))
+    except Exception:
+        pass
+    value = bp_total / kern_max
+    e2e_value = bp_total / wall_max
+    line = {"metric": "aligned read bp/sec", "value": value, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kern_max * 1e3 / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
-            "e2e": {"value": bp_total / wall_max, "unit": "bp/s", "ms_per_step": wall_max * 1e3 / k, "h2d_bytes_per_step": int(pcie_h2d), "d2h_bytes_per_step": int(pcie_d2h),
+            "e2e": {"value": e2e_value, "unit": "bp/s", "ms_per_step": wall_max * 1e3 / k, "h2d_bytes_per_step": int(pcie_h2d), "d2h_bytes_per_step": int(pcie_d2h),
                     "pcie_bytes_per_bp": {"h2d": pcie_h2d / batch.total_bp, "d2h": pcie_d2h / batch.total_bp}, "gam_bytes_per_step": int(gam_bytes),
-                    "note": "h2d/d2h = every byte libgcgpu copied across PCIe during one step on rank 0 (gcgpu_transfer_bytes); the caller's buffers (reads in, GAM out) are host memory"},
+                    "e2e_over_value": e2e_value / value if value > 0 else None,
+                    "note": "h2d/d2h = every byte libgcgpu copied across PCIe during one step on rank 0 (gcgpu_transfer_bytes); the caller's buffers (reads in, GAM out) are host memory; "
+                            "e2e_over_value = end-to-end throughput / kernel-only throughput (1.0 = nothing but kernels on the critical path; > 1 = kernels of different batches overlap)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "note": "integer-pipe bound bit-parallel kernel; algorithmic bytes = work units x bytes/unit (DESIGN.md)",
-                         "units_per_step": dom_units, "int32_ops_per_s": dom_units * dom_ops / (dom_ms / 1e3) if dom_ms > 0 else 0.0,
-                         "int32_peak_ops_per_s": int_peak, "int32_frac": (dom_units * dom_ops / (dom_ms / 1e3) / int_peak) if (int_peak and dom_ms > 0) else None,
-                         "int32_peak_source": "measured live: gcgpu_int_peak (independent LOP3+IADD3 chains, best of 4)",
-                         # not live: the committed ncu --set full capture of the dominant launch pair (profiles/r02h_ncu_full_summary.txt)
-                         "ncu_dominant_launch": {"what": "S1 round 2 of an 839-read batch: 8960 warps, 178.8 M column steps (forward + backtrace)",
-                                                 "dram_bytes": 88.3e6 + 277.0e6 + 358.7e6 + 333.1e6, "algorithmic_bytes": 178.75e6 * K1_BYTES_PER_W + 364.2e6,
-                                                 "algorithmic_note": "2.9 B per column step (node items, sequences) + 8 B per emitted trace cell",
-                                                 "alu_pipe_pct": 81.3, "warp_inst_per_cycle_per_sm": 2.66, "lanes_doing_distinct_work": "1 of 32"}},
+            "roofline": {"bound": "int", "kernel": dom, "achieved": int_ops / 1e12, "peak": (int_peak or 0.0) / 1e12, "unit": "T int32-op/s", "frac": (int_ops / int_peak) if int_peak else None,
+                         "traffic": (ncu_dom or {}).get("dram_bytes_per_launch"),
+                         "peak_source": "measured live: gcgpu_int_peak (independent LOP3+IADD3 chains, best of 4; ncu of that kernel: profiles/)",
+                         "note": "integer-pipe bound bit-parallel kernels (SURVEY 8d): achieved = work units x int32-equivalent ops per unit (44 for K1 = getNextSlice BVCommon.h:248-260, 40 for K3 = calculateBlock edlib.cpp:409-444) / kernel time; traffic = dram bytes of the dominant launch from the committed ncu capture",
+                         "units_per_step": dom_units,
+                         "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src, "note": "algorithmic bytes = work units x bytes/unit (DESIGN.md) / kernel time"},
+                         "ncu_dominant_launch": ncu_dom},
             "kernels_ms_per_step": {"s0_seed": s0_ms, "k1_extend": k1_ms, "k2_chain": k2_ms, "k3_nw": k3_ms},
             "gcups": {"k1": 64 * k1_cols / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else None, "k3": 64 * k3_blocks / (k3_ms / 1e3) / 1e9 if k3_ms > 0 else None,
                       "note": "64 DP cells per work unit W (one Myers column step on a 64-row word), SURVEY 8d"},
             "work_per_step": {"k1_column_steps": k1_cols, "k3_block_steps": k3_blocks, "k1_items": steps[0]["k1_items"], "k3_items": steps[0]["k3_items"], "s1_rounds": steps[0]["s1_rounds"]},
             "clocks": sampler.summary(), "index_build_s": index_s, "host_threads_per_rank": threads, "streams": args.streams, "batch_bp": args.batch_bp, "threads_per_stream": args.threads_per_stream}
     if not args.no_cpu_baseline and os.path.exists(REFBIN):
-        sample = min(args.cpu_sample, n_reads)
+        sample = args.cpu_sample
         fa = os.path.join(tmp, "sample.fa")
         bp = synth.write_fasta(fa, reads[:sample])
-        secs = time_reference(gfa, fa, host_cores)
+        ref_gam = os.path.join(tmp, "ref_sample.gam")
+        secs = time_reference(gfa, fa, host_cores, keep_gam=ref_gam)
         line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": host_cores, "kind": "reference",
                                 "sample": f"first {sample} reads of rank 0's set ({bp} bp), unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only, {secs:.2f} s"}
+        # parity gate: the timed workload's own reads, reference output vs the GAM records the timed e2e step produced
+        par = parity_on_sample(ref_gam, our_members, [r[0] for r in reads[:sample]])
+        line["parity_on_sample"] = par
+        if par["diffs"] != 0:
+            line["value"] = None
+            line["e2e"]["value"] = None
+            line["rejected"] = "decoded GAM records of the sample differ from the reference's: no speed number is reported"
     print(json.dumps(line))
 
 

@@ -17,6 +17,16 @@
 
 #define GC_INT_MAX 2147483647
 
+// Warp-wide votes of the lane-per-item kernels (gc_k1s.cuh): every lane of a warp owns one work item and the lanes
+// meet at loop heads whose conditions are warp-uniform.  The CPU instantiation (tests/hostsim) is a warp of one lane.
+#if defined(__CUDA_ARCH__)
+#define GC_WARP_ANY(p) (__any_sync(0xFFFFFFFFu, (p)) != 0)
+#define GC_WARP_MAX(v) __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(v))
+#else
+#define GC_WARP_ANY(p) (p)
+#define GC_WARP_MAX(v) ((uint32_t)(v))
+#endif
+
 // status codes of a work item
 enum GcStatus : int32_t
 {
@@ -31,6 +41,17 @@ enum GcStatus : int32_t
 // Split-node alignment graph, flat arrays in reference node numbering
 // (AlignmentGraph.h:145-172).  Sequences: 2 bits/base, A0 C1 G2 T3, 32 bases per
 // u64 chunk, LSB first (AlignmentGraph.cpp:114-142).
+// Everything a node visit of the lane-per-item K1 kernels reads about the node itself, as ONE 32-byte record (one sector):
+// the nine scattered loads of the flat arrays were two dependent memory round trips per visit.  Derived from the arrays
+// below at gcgpu_create (gcBuildNodeRecs); counts saturate at 255 (then the CSR arrays are consulted).
+struct __attribute__((aligned(32))) GcNodeRec
+{
+	uint64_t seq0, seq1;
+	uint32_t inStart, outStart;
+	uint32_t firstIn;      // inNbr[inStart] (0 if the node has no in-neighbour)
+	uint8_t len, linearizable, inCount, outCount;
+};
+
 struct GcGraphView
 {
 	uint32_t numNodes;
@@ -42,6 +63,8 @@ struct GcGraphView
 	const uint32_t* outNbr;
 	const uint32_t* componentNumber;  // [N] topological rank (unique per node on a DAG)
 	const uint8_t* linearizable;      // [N]
+	const GcNodeRec* nodeRec;         // [N] packed per-node record (lane-per-item kernels)
+	const uint64_t* outKey;           // [out edges] componentNumber[outNbr[e]] << 32 | outNbr[e]: the queue key of the out-neighbour, one load instead of two dependent ones
 	// >= 0: a GROUP of coopWidth (32, 16 or 8) adjacent lanes of a warp executes ONE work item in lockstep (same control
 	// flow, same values) and this is the lane's index inside its group; helpers may then split loop-free lookups across the
 	// group.  coopMask = the group's lanes inside the warp, coopShift = its first lane.  Groups of one warp run different

@@ -11,6 +11,24 @@
 #include "gc_index.h"
 #include "gc_k1.cuh"
 
+// derived per-node records and out-edge queue keys of a graph view (GcNodeRec, GcGraphView::outKey)
+inline void gcBuildNodeRecs(const GcGraphView& v, std::vector<GcNodeRec>& recs, std::vector<uint64_t>& outKey)
+{
+	recs.resize(v.numNodes);
+	outKey.resize(v.outStart[v.numNodes]);
+	for (uint32_t n = 0; n < v.numNodes; n++)
+	{
+		GcNodeRec& r = recs[n];
+		r.seq0 = v.nodeSeq[2 * (size_t)n]; r.seq1 = v.nodeSeq[2 * (size_t)n + 1];
+		r.inStart = v.inStart[n]; r.outStart = v.outStart[n];
+		uint32_t ic = v.inStart[n + 1] - v.inStart[n], oc = v.outStart[n + 1] - v.outStart[n];
+		r.firstIn = ic ? v.inNbr[v.inStart[n]] : 0;
+		r.len = v.nodeLength[n]; r.linearizable = v.linearizable[n];
+		r.inCount = (uint8_t)(ic < 255 ? ic : 255); r.outCount = (uint8_t)(oc < 255 ? oc : 255);
+		for (uint32_t e = v.outStart[n]; e < v.outStart[n + 1]; e++) outKey[e] = ((uint64_t)v.componentNumber[v.outNbr[e]] << 32) | v.outNbr[e];
+	}
+}
+
 struct GcHostGraph
 {
 	// split-node graph (AlignmentGraph.h:145-164)
@@ -101,6 +119,7 @@ struct GcHostGraph
 		v.componentNumber = componentNumber.data();
 		v.linearizable = linearizable.data();
 		v.coopLane = -1; v.coopWidth = 32; v.coopMask = 0xFFFFFFFFu; v.coopShift = 0;
+		v.nodeRec = nullptr; v.outKey = nullptr; // gcBuildNodeRecs, by the caller that runs the lane-per-item form
 		return v;
 	}
 

@@ -168,6 +168,41 @@ GC_HD int32_t gc_flat_score(const GcWord& w, uint64_t flatMask) { return w.score
 // the thread-per-item kernel keeps ONE loop so that the lanes of a warp, whose forced ranges differ, stay in one loop)
 // FLAT: the minimum tracked is that of the FLATTENED column values (last slice of a read that does not fill 64 rows); used
 // by flattenLastSliceEnd, which only needs that minimum -- the columns themselves are not stored
+// eq[base] as selects: a dynamically indexed array would live in local memory, and its load sits at the head of the column step's dependency chain
+GC_HD uint64_t gc_sel4(const uint64_t eq[4], int base)
+{
+	uint64_t lo = (base & 1) ? eq[1] : eq[0];
+	uint64_t hi = (base & 1) ? eq[3] : eq[2];
+	return (base & 2) ? hi : lo;
+}
+// one column of the run: getNextSlice + the bookkeeping of the column loop of calculateNodeInner (BVCommon.h:1118-1161)
+// FLAT: the minimum tracked is that of the FLATTENED column values (last slice of a read that does not fill 64 rows); used
+// by flattenLastSliceEnd, which only needs that minimum -- the columns themselves are not stored
+template <bool FLAT>
+GC_HD void gc_col_step(GcColumnRun& r, uint32_t pos, int base, bool forced)
+{
+	uint64_t hP, hN;
+	r.ws = gc_next_column(gc_sel4(r.eq, base), r.ws, (r.prevHP >> pos) & 1, (r.prevHN >> pos) & 1, hP, hN);
+	if (forced)
+	{
+		r.ws.VP &= ~1ULL;
+		r.ws.VN |= 1;
+	}
+	const int32_t tracked = FLAT ? gc_flat_score(r.ws, r.flatMask) : r.ws.scoreEnd;
+	if (tracked < r.minScore)
+	{
+		r.minScore = tracked;
+		r.minOffset = pos;
+	}
+	r.HP = (r.HP >> 1) | (hP << 63);
+	r.HN = (r.HN >> 1) | (hN << 63);
+}
+// bases of columns pos.. of a node as a rolling word: two bits per column, refilled every 16 columns
+GC_HD uint32_t gc_col_bases(const GcColumnRun& r, uint32_t pos) { return (uint32_t)((pos < 32 ? r.chunk0 : r.chunk1) >> ((pos & 31) * 2)); }
+
+// columns [begin, end) of the node
+// FORCE: 1 = every column of the range has its first row forced, 0 = none, 2 = columns up to forceUntil (decided per column:
+// the thread-per-item kernel keeps ONE loop so that the lanes of a warp, whose forced ranges differ, stay in one loop)
 template <int FORCE, bool FLAT = false>
 GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols, uint32_t forceUntil = 0)
 {
@@ -178,38 +213,22 @@ GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord
 	{
 		uint32_t segEnd = (pos | 15u) + 1;
 		if (segEnd > end) segEnd = end;
-		uint32_t bases = (uint32_t)((pos < 32 ? r.chunk0 : r.chunk1) >> ((pos & 31) * 2));
+		uint32_t bases = gc_col_bases(r, pos);
 		for (; pos < segEnd; pos++)
 		{
-			int base = (int)(bases & 3);
+			gc_col_step<FLAT>(r, pos, (int)(bases & 3), FORCE == 1 || (FORCE == 2 && forceUntil >= pos));
 			bases >>= 2;
-			uint64_t hP, hN;
-			r.ws = gc_next_column(r.eq[base], r.ws, (r.prevHP >> pos) & 1, (r.prevHN >> pos) & 1, hP, hN);
-			if (FORCE == 1 || (FORCE == 2 && forceUntil >= pos))
-			{
-				r.ws.VP &= ~1ULL;
-				r.ws.VN |= 1;
-			}
-			const int32_t tracked = FLAT ? gc_flat_score(r.ws, r.flatMask) : r.ws.scoreEnd;
-			if (tracked < r.minScore)
-			{
-				r.minScore = tracked;
-				r.minOffset = pos;
-			}
 			if (cols) cols[pos] = r.ws;
-			r.HP = (r.HP >> 1) | (hP << 63);
-			r.HN = (r.HN >> 1) | (hN << 63);
 		}
 	}
 }
 
-// Columns 1..len-1 of a node from its start column (the tail of calculateNodeInner,
-// BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
-// (recalcNodeWordslice, BVCommon.h:828-852).
-GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t eq[4], GcWord ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
-	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols, uint64_t flatMask = 0)
+// Start of the column run of a node from its start column (calculateNodeInner, BVCommon.h:1060-1117): the forceUntil
+// fix-up of the previous slice's horizontal deltas, the first-row rule, the run state.  Returns forceUntil: columns
+// 1..forceUntil have their first row forced (a column cannot start below the previous slice's row), the rest not.
+GC_HD uint32_t gc_cols_prepare_seq(uint64_t chunk0, uint64_t chunk1, uint32_t len, const uint64_t eq[4], const GcWord& ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
+	uint64_t flatMask, GcColumnRun& run)
 {
-	uint32_t len = g.nodeLength[node];
 	uint32_t forceUntil = 0;
 	if (prevExists)
 	{
@@ -244,16 +263,33 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 	{
 		forceUntil = len;
 	}
-	if (cols) cols[0] = ws;
 	uint64_t forceEq = ~0ULL;
 	if (!prevExists) forceEq ^= 1;
-	GcColumnRun run;
 	run.ws = ws; run.minScore = flatMask ? gc_flat_score(ws, flatMask) : ws.scoreEnd; run.minOffset = 0; run.HP = 0; run.HN = 0;
 	run.flatMask = flatMask;
 	run.prevHP = prevHP; run.prevHN = prevHN;
 	run.eq[0] = eq[0] & forceEq; run.eq[1] = eq[1] & forceEq; run.eq[2] = eq[2] & forceEq; run.eq[3] = eq[3] & forceEq;
-	run.chunk0 = g.nodeSeq[2 * (uint64_t)node]; run.chunk1 = g.nodeSeq[2 * (uint64_t)node + 1];
-	// columns 1..forceUntil have their first row forced (a column cannot start below the previous slice's row), the rest not
+	run.chunk0 = chunk0; run.chunk1 = chunk1;
+	return forceUntil;
+}
+GC_HD uint32_t gc_cols_prepare(const GcGraphView& g, uint32_t node, uint32_t len, const uint64_t eq[4], const GcWord& ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
+	uint64_t flatMask, GcColumnRun& run)
+{
+	return gc_cols_prepare_seq(g.nodeSeq[2 * (uint64_t)node], g.nodeSeq[2 * (uint64_t)node + 1], len, eq, ws, prevExists, prevStartScore, prevHP, prevHN, flatMask, run);
+}
+// the horizontal bits were shifted in from the top, one per column: bring the bit of column p to bit p
+GC_HD void gc_cols_finish(GcColumnRun& run, uint32_t len) { if (len > 1) { run.HP >>= (64 - len); run.HN >>= (64 - len); } }
+
+// Columns 1..len-1 of a node from its start column (the tail of calculateNodeInner,
+// BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
+// (recalcNodeWordslice, BVCommon.h:828-852).
+GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t eq[4], GcWord ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
+	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols, uint64_t flatMask = 0)
+{
+	uint32_t len = g.nodeLength[node];
+	if (cols) cols[0] = ws;
+	GcColumnRun run;
+	uint32_t forceUntil = gc_cols_prepare(g, node, len, eq, ws, prevExists, prevStartScore, prevHP, prevHN, flatMask, run);
 	if (flatMask) gc_columns_range<2, true>(run, 1, len, nullptr, forceUntil);
 	else if (g.coopLane >= 0)
 	{
@@ -262,8 +298,7 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 		if (forcedEnd < len) gc_columns_range<0>(run, forcedEnd < 1 ? 1 : forcedEnd, len, cols);
 	}
 	else gc_columns_range<2>(run, 1, len, cols, forceUntil);
-	// the horizontal bits were shifted in from the top, one per column: bring the bit of column p to bit p
-	if (len > 1) { run.HP >>= (64 - len); run.HN >>= (64 - len); }
+	gc_cols_finish(run, len);
 	endOut = run.ws;
 	HPout = run.HP;
 	HNout = run.HN;
@@ -764,11 +799,13 @@ struct GcTraceWriter
 struct GcBtPos { uint32_t node; uint32_t offset; int32_t seqPos; bool nodeSwitch; };
 
 // pickBacktraceCorner (BVCommon.h:710-804); scoresNotValid is always false here
-GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t curN, const GcNodeItem* prev, uint32_t prevN, uint32_t node, int32_t j, const uint8_t* seq, int32_t quitScore, int32_t previousQuitScore, GcBtPos& out)
+// findCur / findPrev: node -> const GcNodeItem* in the current / previous slice (nullptr if absent)
+template <typename FindCur, typename FindPrev>
+GC_HD bool gc_bt_corner_with(const GcGraphView& g, const FindCur& findCur, const FindPrev& findPrev, uint32_t node, int32_t j, const uint8_t* seq, int32_t quitScore, int32_t previousQuitScore, GcBtPos& out)
 {
-	const GcNodeItem* me = gc_find_item(g, cur, curN, node);
+	const GcNodeItem* me = findCur(node);
 	int32_t scoreHere = gc_value(gc_item_start(*me), 0);
-	const GcNodeItem* prevMe = gc_find_item(g, prev, prevN, node);
+	const GcNodeItem* prevMe = findPrev(node);
 	if (scoreHere > quitScore)
 	{
 		int32_t smallestFound = scoreHere + 1;
@@ -781,7 +818,7 @@ GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t cu
 		for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
 		{
 			uint32_t nb = g.inNbr[e];
-			const GcNodeItem* pn = gc_find_item(g, prev, prevN, nb);
+			const GcNodeItem* pn = findPrev(nb);
 			if (pn)
 			{
 				if (pn->endScore <= smallestFound)
@@ -790,7 +827,7 @@ GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t cu
 					out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j - 1; out.nodeSwitch = true;
 				}
 			}
-			const GcNodeItem* cn = gc_find_item(g, cur, curN, nb);
+			const GcNodeItem* cn = findCur(nb);
 			if (cn && nb != node)
 			{
 				int32_t v = gc_value(gc_item_end(*cn), 0);
@@ -815,13 +852,13 @@ GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t cu
 	for (uint32_t e = g.inStart[node]; e < g.inStart[node + 1]; e++)
 	{
 		uint32_t nb = g.inNbr[e];
-		const GcNodeItem* cn = gc_find_item(g, cur, curN, nb);
+		const GcNodeItem* cn = findCur(nb);
 		if (cn && gc_value(gc_item_end(*cn), 0) == scoreHere - 1)
 		{
 			out.node = nb; out.offset = g.nodeLength[nb] - 1; out.seqPos = j; out.nodeSwitch = true;
 			return true;
 		}
-		const GcNodeItem* pn = gc_find_item(g, prev, prevN, nb);
+		const GcNodeItem* pn = findPrev(nb);
 		if (pn)
 		{
 			int32_t cornerScore = pn->endScore;
@@ -847,6 +884,13 @@ GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t cu
 		return true;
 	}
 	return false; // the reference asserts here
+}
+
+GC_HD bool gc_bt_corner(const GcGraphView& g, const GcNodeItem* cur, uint32_t curN, const GcNodeItem* prev, uint32_t prevN, uint32_t node, int32_t j, const uint8_t* seq, int32_t quitScore, int32_t previousQuitScore, GcBtPos& out)
+{
+	auto findCur = [&](uint32_t nd) { return gc_find_item(g, cur, curN, nd); };
+	auto findPrev = [&](uint32_t nd) { return gc_find_item(g, prev, prevN, nd); };
+	return gc_bt_corner_with(g, findCur, findPrev, node, j, seq, quitScore, previousQuitScore, out);
 }
 
 GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seqLen, GcK1Workspace& ws, int32_t last, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)

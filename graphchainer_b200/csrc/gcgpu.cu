@@ -11,6 +11,7 @@
 #include "../../include/gcgpu.h"
 #include "gc_common.cuh"
 #include "gc_k1.cuh"
+#include "gc_k1s.cuh"
 #include "gc_k2.cuh"
 #include "gc_k3.cuh"
 #include "gc_k3w.cuh"
@@ -72,6 +73,7 @@ struct gcgpu_ctx
 	uint8_t* d_nodeLength = nullptr; uint64_t* d_nodeSeq = nullptr;
 	uint32_t* d_inStart = nullptr; uint32_t* d_inNbr = nullptr; uint32_t* d_outStart = nullptr; uint32_t* d_outNbr = nullptr;
 	uint32_t* d_componentNumber = nullptr; uint8_t* d_linearizable = nullptr;
+	GcNodeRec* d_nodeRec = nullptr; uint64_t* d_outKey = nullptr;
 	GcViterbiTables* d_vt = nullptr;
 	GcGraphView view;
 	// MPC index (K2)
@@ -80,6 +82,7 @@ struct gcgpu_ctx
 	bool haveMpc = false;
 	GcMpcView mpc;
 	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc, itemsBuf;
+	DevBuf planes; // bit planes of seqBuf (gc_planes_kernel): the Eq masks of any 64 rows in eight loads
 	uint64_t h2dBytes = 0, d2hBytes = 0; // bytes this ctx copied across PCIe (gcgpu_transfer_bytes)
 	GcResident* resident = nullptr;      // state of the resident batch entry points (gcgpu_resident.inl)
 	// minimizer index (S0)
@@ -144,7 +147,7 @@ struct GcK1Desc
 static inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t k1WorkspaceBytes(uint32_t numSlices, uint32_t itemCap, uint32_t heapCap)
 {
-	return alignUp((size_t)(numSlices + 2) * sizeof(GcSliceMeta), 16) + (size_t)itemCap * sizeof(GcNodeItem) + (size_t)heapCap * 8;
+	return alignUp((size_t)(numSlices + 2) * sizeof(GcSliceMeta), 16) + (size_t)itemCap * sizeof(GcNodeItem) + (size_t)heapCap * 8 + (size_t)itemCap * 16 + (size_t)itemCap * 4; // slices | items | heap | item aux | slice keys
 }
 
 // Short work items (35-bp fragments: one or two slices): one thread = one item; the millions of
@@ -286,6 +289,73 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphV
 	results[d.resultIndex] = res;
 }
 
+// Long work items, lane-per-item form (gc_k1s.cuh): the 32 lanes of a warp walk 32 different items and meet at the shared
+// column loop.  Items arrive sorted by length (longest first), so the lanes of a warp finish together.  The node queue of
+// every lane sits in shared memory, entry-major (entry e of thread t at heapShared[e * GC_K1S_THREADS + t]).
+#define GC_K1S_THREADS 64
+#define GC_K1S_HEAP 32
+__device__ __forceinline__ void gc_k1s_workspace(const GcK1Desc& d, uint8_t* arena, uint64_t* heapShared, GcK1SWorkspace& ws)
+{
+	uint8_t* base = arena + d.wsOff;
+	ws.slices = (GcSliceMeta*)base;
+	size_t slicesBytes = ((size_t)(d.numSlices + 2) * sizeof(GcSliceMeta) + 15) / 16 * 16;
+	ws.items = (GcNodeItem*)(base + slicesBytes);
+	ws.scratch = (uint32_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem));
+	ws.scratchCap = d.heapCap * 2;
+	ws.aux = (GcItemAux*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem) + (size_t)d.heapCap * 8);
+	ws.keys = (uint32_t*)(base + slicesBytes + (size_t)d.itemCap * sizeof(GcNodeItem) + (size_t)d.heapCap * 8 + (size_t)d.itemCap * sizeof(GcItemAux));
+	ws.itemCap = d.itemCap;
+	ws.heap.base = heapShared + threadIdx.x; ws.heap.stride = GC_K1S_THREADS; ws.heap.cap = GC_K1S_HEAP;
+}
+__global__ void __launch_bounds__(GC_K1S_THREADS, 1) gc_k1s_forward_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes,
+	const gcgpu_ext_item* __restrict__ items, const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
+{
+	__shared__ uint64_t heapShared[GC_K1S_HEAP * GC_K1S_THREADS];
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool have = t < n; // lanes without an item still take part in the warp votes
+	g.coopLane = -1;
+	GcK1Desc d = gc_k1_long_desc(descs, items, have ? t : 0);
+	GcK1SWorkspace ws;
+	gc_k1s_workspace(d, arena, heapShared, ws);
+	GcK1Result res;
+	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+	int32_t last = gc_k1s_forward(g, *vt, prm, have, seq + d.seqOff, d.seqLen, d.node, d.offset, planes, d.seqOff, ws, res);
+	if (!have) return;
+	if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+	results[d.resultIndex] = res;
+	traceOffOfItem[d.resultIndex] = d.traceOff;
+	lastSlice[t] = last;
+	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+}
+__global__ void __launch_bounds__(GC_K1S_THREADS, 1) gc_k1s_backtrace_kernel(GcGraphView g, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes, const gcgpu_ext_item* __restrict__ items,
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	g.coopLane = -1;
+	GcK1Desc d = gc_k1_long_desc(descs, items, t < n ? t : 0);
+	GcK1Result res = results[d.resultIndex];
+	const bool have = t < n && res.status == GC_OK;
+	GcK1SWorkspace ws;
+	gc_k1s_workspace(d, arena, nullptr, ws);
+	GcWord cols[64];
+	gc_k1s_backtrace(g, have, seq + d.seqOff, d.seqLen, planes, d.seqOff, ws, have ? lastSlice[t] : 0, cols, traceArena + d.traceOff, d.traceCap, res);
+	if (have) results[d.resultIndex] = res;
+}
+// bit planes of the sequence buffer: for every block of 64 codes, four words (bit i of word b = code i has bit b: A C G T)
+__global__ void gc_planes_kernel(const uint8_t* __restrict__ seq, uint64_t bytes, uint64_t blocks, uint64_t* __restrict__ planes)
+{
+	uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= blocks) return;
+	uint64_t w[4] = { 0, 0, 0, 0 };
+	uint64_t first = k * 64;
+	for (uint32_t i = 0; i < 64 && first + i < bytes; i++)
+	{
+		uint64_t c = seq[first + i];
+		w[0] |= (c & 1) << i; w[1] |= ((c >> 1) & 1) << i; w[2] |= ((c >> 2) & 1) << i; w[3] |= ((c >> 3) & 1) << i;
+	}
+	planes[4 * k] = w[0]; planes[4 * k + 1] = w[1]; planes[4 * k + 2] = w[2]; planes[4 * k + 3] = w[3];
+}
+
 // trace lengths of the finished items (input of the exclusive scan that places them in the dense buffer)
 __global__ void gc_k1_lengths_kernel(const GcK1Result* __restrict__ results, uint32_t n, uint64_t* __restrict__ lens, uint64_t* total)
 {
@@ -330,11 +400,11 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->d_nodeLength); cudaFree(ctx->d_nodeSeq); cudaFree(ctx->d_inStart); cudaFree(ctx->d_inNbr); cudaFree(ctx->d_outStart); cudaFree(ctx->d_outNbr);
-	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt);
+	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt); cudaFree(ctx->d_nodeRec); cudaFree(ctx->d_outKey);
 	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
 	cudaFree(ctx->d_mzSlots); ctx->seedBuf.release(); ctx->seedMatches.release();
 	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
-	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release(); ctx->itemsBuf.release();
+	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release(); ctx->itemsBuf.release(); ctx->planes.release();
 	residentDestroy(ctx);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -379,6 +449,16 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	chk(uploadArray(graph->out_nbr, graph->out_start[N], &ctx->d_outNbr));
 	chk(uploadArray(graph->component_number, N, &ctx->d_componentNumber));
 	chk(uploadArray(graph->linearizable, N, &ctx->d_linearizable));
+	{
+		// derived arrays of the lane-per-item K1 kernels: one 32-byte record per node, one queue key per out-edge
+		GcGraphView hv;
+		hv.numNodes = N; hv.nodeLength = graph->node_length; hv.nodeSeq = graph->node_seq; hv.inStart = graph->in_start; hv.inNbr = graph->in_nbr; hv.outStart = graph->out_start; hv.outNbr = graph->out_nbr;
+		hv.componentNumber = graph->component_number; hv.linearizable = graph->linearizable; hv.nodeRec = nullptr; hv.outKey = nullptr;
+		std::vector<GcNodeRec> recs; std::vector<uint64_t> outKeys;
+		gcBuildNodeRecs(hv, recs, outKeys);
+		chk(uploadArray(recs.data(), recs.size(), &ctx->d_nodeRec));
+		chk(uploadArray(outKeys.data(), outKeys.size(), &ctx->d_outKey));
+	}
 	GcViterbiTables vt = gcMakeViterbiTables();
 	chk(uploadArray(&vt, 1, &ctx->d_vt));
 	if (graph->comp_map && graph->comp_idx && graph->comp_start && graph->topo_ids && graph->paths_start && graph->back_start)
@@ -403,6 +483,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.numNodes = N;
 	ctx->view.nodeLength = ctx->d_nodeLength; ctx->view.nodeSeq = ctx->d_nodeSeq;
 	ctx->view.inStart = ctx->d_inStart; ctx->view.inNbr = ctx->d_inNbr; ctx->view.outStart = ctx->d_outStart; ctx->view.outNbr = ctx->d_outNbr;
+	ctx->view.nodeRec = ctx->d_nodeRec; ctx->view.outKey = ctx->d_outKey;
 	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1; ctx->view.coopWidth = 32; ctx->view.coopMask = 0xFFFFFFFFu; ctx->view.coopShift = 0;
 	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
 	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
@@ -444,6 +525,18 @@ __global__ void gc_k1_init_results_kernel(GcK1Result* results, uint64_t* slot, u
 	results[i] = r;
 	slot[i] = 0;
 }
+
+// bit planes of the resident K1 sequence buffer (after every upload / re-encoding of ctx->seqBuf)
+static int buildPlanes(gcgpu_ctx* ctx, uint64_t bytes)
+{
+	uint64_t blocks = bytes / 64 + 2; // one block of padding: gc_eq_from_planes reads the block after the one it starts in
+	CUDA_TRY(ctx->planes.ensure(blocks * 32));
+	gc_planes_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)ctx->seqBuf.p, bytes, blocks, (uint64_t*)ctx->planes.p);
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return GCGPU_OK;
+}
+static const bool g_k1Lockstep = getenv("GCGPU_K1_LOCKSTEP") != nullptr; // A/B switch: long items on the warp-per-item kernels
 
 static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* lens, uint32_t n, int32_t uniformMax, GcK1Run& run)
 {
@@ -522,9 +615,19 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	if (needInit) { gc_k1_init_results_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, dSlot, n); ctx->launches++; }
 	if (nLong)
 	{
-		// one warp per item in lock-step; resident blocks per SM: 5 (96 registers)
-		gc_k1_long_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-		gc_k1_long_bt_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+		if (!g_k1Lockstep)
+		{
+			// lane per item: 32 items per warp, sorted by length
+			uint32_t blocks = (nLong + GC_K1S_THREADS - 1) / GC_K1S_THREADS;
+			gc_k1s_forward_kernel<<<blocks, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1s_backtrace_kernel<<<blocks, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+		}
+		else
+		{
+			// one warp per item in lock-step; resident blocks per SM: 5 (96 registers)
+			gc_k1_long_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1_long_bt_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+		}
 		ctx->launches += 2;
 	}
 	if (nShort)
@@ -657,6 +760,7 @@ extern "C" int gcgpu_extend(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_byt
 		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
 		if (seq_bytes) CUDA_TRY(gcCopy(ctx, ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
 		ctx->seqResident = seq_bytes;
+		{ int prc = buildPlanes(ctx, seq_bytes); if (prc != GCGPU_OK) return prc; }
 	}
 	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_extend: seq == NULL but no sequence buffer of this size is resident");
 	CUDA_TRY(ctx->itemsBuf.ensure((size_t)n * sizeof(gcgpu_ext_item)));
@@ -775,6 +879,7 @@ extern "C" int gcgpu_seed(gcgpu_ctx* ctx, const uint8_t* seq, uint64_t seq_bytes
 		CUDA_TRY(ctx->seqBuf.ensure(seq_bytes + 16));
 		if (seq_bytes) CUDA_TRY(gcCopy(ctx, ctx->seqBuf.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream));
 		ctx->seqResident = seq_bytes;
+		{ int prc = buildPlanes(ctx, seq_bytes); if (prc != GCGPU_OK) return prc; }
 	}
 	else if (ctx->seqResident != seq_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_seed: seq == NULL but no sequence buffer of this size is resident");
 	// device arrays: reads | counts[n+1] | offsets[n+1] | scan scratch

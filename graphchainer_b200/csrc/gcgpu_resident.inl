@@ -131,6 +131,7 @@ extern "C" int gcgpu_load_reads(gcgpu_ctx* ctx, const char* chars, uint64_t char
 	gc_reads_encode_kernel<<<n, 256, 0, ctx->stream>>>(R->d_codeTable, (const uint8_t*)R->chars.p, (const GcReadDesc*)R->reads.p, n, (uint8_t*)ctx->seqBuf.p);
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
+	{ int prc = buildPlanes(ctx, 2 * char_bytes); if (prc != GCGPU_OK) return prc; }
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	float ms = 0;

@@ -108,6 +108,66 @@ def read_gam(path: str) -> dict:
     return out
 
 
+def message_name(msg: bytes) -> str:
+    """`name` (field 3) of a serialized vg.Alignment without decoding the rest (top-level field walk)."""
+    pos, n = 0, len(msg)
+    while pos < n:
+        tag, pos = _varint(msg, pos)
+        f, w = tag >> 3, tag & 7
+        if w == 0:
+            _, pos = _varint(msg, pos)
+        elif w == 1:
+            pos += 8
+        elif w == 5:
+            pos += 4
+        elif w == 2:
+            ln, pos = _varint(msg, pos)
+            if f == 3:
+                return bytes(msg[pos:pos + ln]).decode()
+            pos += ln
+        else:
+            raise ValueError("bad wire type")
+    return ""
+
+
+def read_gam_messages(data) -> dict:
+    """{read name: [serialized message bytes, ...]} of a GAM byte string (messages of a read in file order)."""
+    data = bytes(data)
+    out: dict = {}
+    pos = 0
+    while pos < len(data):
+        d = zlib.decompressobj(31)
+        raw = d.decompress(data[pos:])
+        pos = len(data) - len(d.unused_data)
+        p = 0
+        count, p = _varint(raw, p)
+        for _ in range(count):
+            ln, p = _varint(raw, p)
+            m = raw[p:p + ln]
+            p += ln
+            out.setdefault(message_name(m), []).append(m)
+    return out
+
+
+def diff_messages(a: dict, b: dict, names=None, limit: int = 5):
+    """Compare two {name: [message bytes]} maps over `names` (default: all of both).  Byte-equal messages are equal;
+    the rest are decoded and compared field by field.  Returns (reads compared, list of differences)."""
+    names = sorted(set(a) | set(b)) if names is None else list(names)
+    diffs = []
+    for name in names:
+        x, y = a.get(name), b.get(name)
+        if x == y:
+            continue
+        if x is None or y is None:
+            diffs.append(f"{name}: present only in {'first' if x is not None else 'second'}")
+        else:
+            dx, dy = {name: [decode_alignment(m) for m in x]}, {name: [decode_alignment(m) for m in y]}
+            diffs.extend(diff_gam(dx, dy, limit=1))
+        if len(diffs) >= limit:
+            break
+    return len(names), diffs
+
+
 def diff_gam(a: dict, b: dict, limit: int = 5):
     """Differences between two decoded GAMs; empty list = identical."""
     diffs = []

@@ -13,6 +13,7 @@
 #include "../../include/gcgpu.h"
 #include "../../graphchainer_b200/csrc/gc_host_graph.h"
 #include "../../graphchainer_b200/csrc/gc_k1.cuh"
+#include "../../graphchainer_b200/csrc/gc_k1s.cuh"
 #include "../../graphchainer_b200/csrc/gc_k2.cuh"
 #include "../../graphchainer_b200/csrc/gc_k3.cuh"
 #include "../../graphchainer_b200/csrc/gc_seed.cuh"
@@ -22,6 +23,7 @@
 struct gcgpu_ctx
 {
 	GcGraphView view;
+	std::vector<GcNodeRec> nodeRecs; std::vector<uint64_t> outKeys;
 	GcMpcView mpc;
 	GcViterbiTables vt;
 	int bandwidth;
@@ -51,6 +53,9 @@ extern "C" int gcgpu_create(int, const gcgpu_graph* g, const gcgpu_params* p, gc
 	c->view.numNodes = g->num_nodes; c->view.nodeLength = g->node_length; c->view.nodeSeq = g->node_seq;
 	c->view.inStart = g->in_start; c->view.inNbr = g->in_nbr; c->view.outStart = g->out_start; c->view.outNbr = g->out_nbr;
 	c->view.componentNumber = g->component_number; c->view.linearizable = g->linearizable; c->view.coopLane = -1; c->view.coopWidth = 32; c->view.coopMask = 0xFFFFFFFFu; c->view.coopShift = 0;
+	c->view.nodeRec = nullptr; c->view.outKey = nullptr;
+	gcBuildNodeRecs(c->view, c->nodeRecs, c->outKeys);
+	c->view.nodeRec = c->nodeRecs.data(); c->view.outKey = c->outKeys.data();
 	c->mpc.compMap = g->comp_map; c->mpc.compIdx = g->comp_idx; c->mpc.compStart = g->comp_start; c->mpc.topoIds = g->topo_ids;
 	c->mpc.pathsStart = g->paths_start; c->mpc.pathsK = g->paths_k; c->mpc.backStart = g->back_start; c->mpc.backNode = g->back_node; c->mpc.backK = g->back_k;
 	c->vt = gcMakeViterbiTables();
@@ -99,6 +104,19 @@ static bool simK1(gcgpu_ctx* ctx, const gcgpu_ext_item* items, uint32_t n, gcgpu
 			GcWord colsBuf[64];
 			GcK1Workspace ws { slices.data(), nodeItems.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { ctx->bandwidth };
+			if (seqLen >= 96)
+			{
+				// whole-read extensions: the lane-per-item form the library launches for them (gc_k1s.cuh), as a warp of one lane
+				std::vector<uint32_t> keys(itemCap), scratch(2 * (size_t)heapCap);
+				std::vector<GcItemAux> aux(itemCap);
+				GcK1SWorkspace sw; sw.slices = slices.data(); sw.items = nodeItems.data(); sw.keys = keys.data(); sw.aux = aux.data(); sw.scratch = scratch.data(); sw.scratchCap = (uint32_t)scratch.size(); sw.itemCap = itemCap;
+				sw.heap.base = heap.data(); sw.heap.stride = 1; sw.heap.cap = heapCap;
+				res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+				int32_t last = gc_k1s_forward(ctx->view, ctx->vt, prm, true, seq + items[i].seq_offset, seqLen, items[i].node, items[i].offset, nullptr, 0, sw, res);
+				if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+				if (res.status == GC_OK) gc_k1s_backtrace(ctx->view, true, seq + items[i].seq_offset, seqLen, nullptr, 0, sw, last, colsBuf, trace.data(), (uint32_t)trace.size(), res);
+			}
+			else
 			gc_k1_extend(ctx->view, ctx->vt, prm, seq + items[i].seq_offset, seqLen, items[i].node, items[i].offset, ws, trace.data(), (uint32_t)trace.size(), res);
 			if (res.status == GC_OVERFLOW_ITEMS) { itemCap *= 4; continue; }
 			if (res.status == GC_OVERFLOW_HEAP) { heapCap *= 4; continue; }

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include "../../graphchainer_b200/csrc/gc_host_graph.h"
+#include "../../graphchainer_b200/csrc/gc_k1s.cuh"
 #include "../../graphchainer_b200/csrc/gc_k3.cuh"
 #include "../../graphchainer_b200/csrc/gc_k3w.cuh"
 #include "../../graphchainer_b200/csrc/gc_k2.cuh"
@@ -387,6 +388,9 @@ int main(int argc, char** argv)
 	GcHostGraph hg; hg.fromIndex(idx);
 	if (mode == "k2") return k2Main(hg, argv[3]);
 	GcGraphView g = hg.view();
+	std::vector<GcNodeRec> nodeRecs; std::vector<uint64_t> outKeys;
+	gcBuildNodeRecs(g, nodeRecs, outKeys);
+	g.nodeRec = nodeRecs.data(); g.outKey = outKeys.data();
 	GcViterbiTables vt = gcMakeViterbiTables();
 	std::ifstream in(argv[3]);
 	size_t maxItems = argc > 4 ? strtoull(argv[4], nullptr, 10) : (size_t)-1;
@@ -407,7 +411,7 @@ int main(int argc, char** argv)
 		}
 		if (line.compare(0, 4, "RES ") != 0 || !haveExt) continue;
 		haveExt = false;
-		if (mode != "k1") continue;
+		if (mode != "k1" && mode != "k1s") continue;
 		{
 			std::istringstream ss(line);
 			std::string tag, first; ss >> tag >> first;
@@ -435,6 +439,21 @@ int main(int argc, char** argv)
 			GcWord colsBuf[64];
 			GcK1Workspace ws { slices.data(), items.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { 10 };
+			if (mode == "k1s")
+			{
+				// lane-per-item form (gc_k1s.cuh) as a warp of one lane; bit planes built as gc_planes_kernel does
+				std::vector<uint32_t> keys(itemCap), scratch(2 * (size_t)heapCap);
+				std::vector<GcItemAux> aux(itemCap);
+				std::vector<uint64_t> planes(4 * ((size_t)seqLen / 64 + 3), 0);
+				for (int32_t i = 0; i < seqLen; i++) for (int b = 0; b < 4; b++) if ((seq[i] >> b) & 1) planes[4 * (size_t)(i >> 6) + b] |= 1ULL << (i & 63);
+				GcK1SWorkspace sw; sw.slices = slices.data(); sw.items = items.data(); sw.keys = keys.data(); sw.aux = aux.data(); sw.scratch = scratch.data(); sw.scratchCap = (uint32_t)scratch.size(); sw.itemCap = itemCap;
+				sw.heap.base = heap.data(); sw.heap.stride = 1; sw.heap.cap = heapCap;
+				res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
+				int32_t last = gc_k1s_forward(g, vt, prm, true, seq.data(), seqLen, node, off, (total & 1) ? planes.data() : nullptr, 0, sw, res);
+				if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+				if (res.status == GC_OK) gc_k1s_backtrace(g, true, seq.data(), seqLen, (total & 1) ? planes.data() : nullptr, 0, sw, last, colsBuf, trace.data(), (uint32_t)trace.size(), res);
+			}
+			else
 			gc_k1_extend(g, vt, prm, seq.data(), seqLen, node, off, ws, trace.data(), (uint32_t)trace.size(), res);
 			if (res.status == GC_OVERFLOW_ITEMS) { itemCap *= 4; continue; }
 			if (res.status == GC_OVERFLOW_HEAP) { heapCap *= 4; continue; }

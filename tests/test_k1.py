@@ -14,11 +14,13 @@ from conftest import REFDUMP, ROOT
 import stages
 
 
-def test_k1_logic_on_cpu_matches_golden(hostsim, golden_files):
-    """The device functions, compiled for the host, replay the golden K1 records."""
+@pytest.mark.parametrize("mode", ["k1", "k1s"])
+def test_k1_logic_on_cpu_matches_golden(hostsim, golden_files, mode):
+    """The device functions, compiled for the host, replay the golden K1 records (k1: the thread/warp-per-item form of
+    gc_k1.cuh; k1s: the lane-per-item form of gc_k1s.cuh as a warp of one lane, Eq masks from bit planes for every other item)."""
     assert golden_files, "golden fixtures missing"
     for name, (idx, st) in golden_files.items():
-        out = subprocess.run([hostsim, "k1", idx, st], capture_output=True, text=True)
+        out = subprocess.run([hostsim, mode, idx, st], capture_output=True, text=True)
         assert out.returncode == 0, f"{name}: {out.stdout} {out.stderr}"
         rep = json.loads(out.stdout.strip().splitlines()[-1])
         assert rep["mismatches"] == 0 and rep["items"] > 0
