@@ -536,7 +536,11 @@ static int buildPlanes(gcgpu_ctx* ctx, uint64_t bytes)
 	CUDA_TRY(cudaGetLastError());
 	return GCGPU_OK;
 }
-static const bool g_k1Lockstep = getenv("GCGPU_K1_LOCKSTEP") != nullptr; // A/B switch: long items on the warp-per-item kernels
+// Long items run lane-per-item (gc_k1s_*: 32 items per warp, ~1/12 of the issue slots per column step) when a launch has at
+// least this many of them, warp-per-item in lock-step (gc_k1_long_*: a fifth of the latency of a walk, 32 redundant lanes)
+// below it: a launch of a few hundred items cannot fill the GPU either way and only its latency matters (profiles/r03d).
+// GCGPU_K1_SIMT_MIN=0: always lane-per-item; a huge value: always lock-step.
+static const uint32_t g_k1SimtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)strtoul(getenv("GCGPU_K1_SIMT_MIN"), nullptr, 10) : 4096u;
 
 static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* lens, uint32_t n, int32_t uniformMax, GcK1Run& run)
 {
@@ -615,7 +619,7 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	if (needInit) { gc_k1_init_results_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, dSlot, n); ctx->launches++; }
 	if (nLong)
 	{
-		if (!g_k1Lockstep)
+		if (nLong >= g_k1SimtMin)
 		{
 			// lane per item: 32 items per warp, sorted by length
 			uint32_t blocks = (nLong + GC_K1S_THREADS - 1) / GC_K1S_THREADS;

@@ -573,39 +573,123 @@ __device__ __forceinline__ uint8_t gc_k3_code_of(uint8_t m)
 {
 	return (m & 0x30) ? (uint8_t)4 : (m == 1 ? (uint8_t)0 : m == 2 ? (uint8_t)1 : m == 4 ? (uint8_t)2 : m == 8 ? (uint8_t)3 : (uint8_t)4);
 }
-__global__ void gc_piece_len_kernel(GcPostGraph pg, const gcgpu_nw_piece* __restrict__ pieces, uint32_t n, const GcReadDesc* __restrict__ reads, const GcPair* const* __restrict__ setPairs, const uint64_t* const* __restrict__ setTraces,
-	const uint32_t* __restrict__ pathNodes, uint64_t* __restrict__ lens)
+// One block per piece.  WRITE = false: lens[i] = length of the piece (flags[i] = 1 if the lanes cannot split it, see below);
+// WRITE = true: its codes at out + offs[i].
+//   read        the read's codes, re-coded for K3
+//   pair path   traceToPoses + traceToSequence (Aligner.cpp:376-408, 425-428), gc_pair_path_string: entry k of the merged trace
+//               emits the bases between the previous entry's cell and its own -- a function of entries k-1 and k alone as long as
+//               the offsets inside a node never decrease (true for every trace of a DAG; checked, and a piece that violates it is
+//               expanded by one thread with the sequential code) -- so: per-entry counts, block scan, scattered writes
+//   node path   pathToTrace (Aligner.cpp:409-424), gc_node_path_string: per node a range of bases, same scan
+#define GC_PIECE_THREADS 256
+template <bool WRITE>
+__global__ void __launch_bounds__(GC_PIECE_THREADS) gc_piece_kernel(GcPostGraph pg, const gcgpu_nw_piece* __restrict__ pieces, uint32_t n, const GcReadDesc* __restrict__ reads, const uint8_t* __restrict__ codes,
+	const GcPair* const* __restrict__ setPairs, const uint64_t* const* __restrict__ setTraces, const uint32_t* __restrict__ pathNodes,
+	uint64_t* __restrict__ lens, uint8_t* __restrict__ flags, const uint64_t* __restrict__ offs, uint8_t* __restrict__ out)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > n) return;
-	if (i == n) { lens[i] = 0; return; }
-	gcgpu_nw_piece pc = pieces[i];
-	uint64_t len = 0;
-	if (pc.kind == GCGPU_PIECE_READ) len = (uint64_t)reads[pc.index].len;
-	else if (pc.kind == GCGPU_PIECE_PAIR_PATH) len = gc_pair_path_string(pg, setTraces[pc.set], setPairs[pc.set][pc.index], nullptr);
-	else len = gc_node_path_string(pg, pathNodes + pc.first_node, pc.num_nodes, pc.first_offset, pc.last_offset, nullptr);
-	lens[i] = len;
-}
-__global__ void gc_piece_write_kernel(GcPostGraph pg, const gcgpu_nw_piece* __restrict__ pieces, uint32_t n, const GcPair* const* __restrict__ setPairs, const uint64_t* const* __restrict__ setTraces,
-	const uint32_t* __restrict__ pathNodes, const uint64_t* __restrict__ offs, uint8_t* __restrict__ out)
-{
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	gcgpu_nw_piece pc = pieces[i];
-	if (pc.kind == GCGPU_PIECE_PAIR_PATH) gc_pair_path_string(pg, setTraces[pc.set], setPairs[pc.set][pc.index], out + offs[i]);
-	else if (pc.kind == GCGPU_PIECE_NODE_PATH) gc_node_path_string(pg, pathNodes + pc.first_node, pc.num_nodes, pc.first_offset, pc.last_offset, out + offs[i]);
-}
-// read pieces: warp per piece
-__global__ void __launch_bounds__(128) gc_piece_reads_kernel(const gcgpu_nw_piece* __restrict__ pieces, uint32_t n, const GcReadDesc* __restrict__ reads, const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offs, uint8_t* __restrict__ out)
-{
-	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (w >= n) return;
-	gcgpu_nw_piece pc = pieces[w];
-	if (pc.kind != GCGPU_PIECE_READ) return;
-	GcReadDesc rd = reads[pc.index];
-	const uint8_t* src = codes + 2 * rd.charOffset;
-	uint8_t* dst = out + offs[w];
-	for (int32_t k = lane; k < rd.len; k += 32) dst[k] = gc_k3_code_of(src[k]);
+	typedef cub::BlockScan<uint32_t, GC_PIECE_THREADS> Scan;
+	__shared__ typename Scan::TempStorage scanTmp;
+	__shared__ uint32_t sViolation;
+	const uint32_t i = blockIdx.x, tid = threadIdx.x;
+	if (i >= n) { if (!WRITE && i == n && tid == 0) lens[i] = 0; return; }
+	const gcgpu_nw_piece pc = pieces[i];
+	if (pc.kind == GCGPU_PIECE_READ)
+	{
+		const GcReadDesc rd = reads[pc.index];
+		if (!WRITE) { if (tid == 0) { lens[i] = (uint64_t)rd.len; flags[i] = 0; } return; }
+		const uint8_t* src = codes + 2 * rd.charOffset;
+		uint8_t* dst = out + offs[i];
+		for (int32_t k = tid; k < rd.len; k += GC_PIECE_THREADS) dst[k] = gc_k3_code_of(src[k]);
+		return;
+	}
+	if (tid == 0) sViolation = 0;
+	__syncthreads();
+	uint8_t* dst = WRITE ? out + offs[i] : nullptr;
+	if (WRITE && flags[i])
+	{
+		// sequential form (never taken on a DAG)
+		if (tid == 0)
+		{
+			if (pc.kind == GCGPU_PIECE_PAIR_PATH) gc_pair_path_string(pg, setTraces[pc.set], setPairs[pc.set][pc.index], dst);
+			else gc_node_path_string(pg, pathNodes + pc.first_node, pc.num_nodes, pc.first_offset, pc.last_offset, dst);
+		}
+		return;
+	}
+	uint32_t base = 0;
+	if (pc.kind == GCGPU_PIECE_PAIR_PATH)
+	{
+		const uint64_t* tr = setTraces[pc.set];
+		const GcPair p = setPairs[pc.set][pc.index];
+		const uint32_t m = gc_pair_size(p);
+		for (uint32_t tile = 0; tile < m; tile += GC_PIECE_THREADS)
+		{
+			const uint32_t k = tile + tid;
+			uint32_t cnt = 0, tailNode = 0, tailFrom = 0, tailCnt = 0, headNode = 0, headFrom = 0, headCnt = 0;
+			if (k < m)
+			{
+				GcMergedEntry e = gc_pair_entry(pg, tr, p, k);
+				if (k == 0) { headNode = e.node; headFrom = e.offset; headCnt = 1; }
+				else
+				{
+					GcMergedEntry pe = gc_pair_entry(pg, tr, p, k - 1);
+					if (e.node == pe.node)
+					{
+						if (e.offset < pe.offset) sViolation = 1;
+						else { headNode = e.node; headFrom = pe.offset + 1; headCnt = e.offset - pe.offset; }
+					}
+					else
+					{
+						tailNode = pe.node; tailFrom = pe.offset + 1; tailCnt = pg.nodeLength[pe.node] - pe.offset - 1; // the rest of the node left behind
+						headNode = e.node; headFrom = 0; headCnt = e.offset + 1;                                          // the new node up to the cell entered
+					}
+				}
+				cnt = tailCnt + headCnt;
+			}
+			uint32_t off, total;
+			Scan(scanTmp).ExclusiveSum(cnt, off, total);
+			__syncthreads();
+			if (WRITE)
+			{
+				uint8_t* o = dst + base + off;
+				for (uint32_t c = 0; c < tailCnt; c++) o[c] = (uint8_t)gc_post_base(pg, tailNode, tailFrom + c);
+				o += tailCnt;
+				for (uint32_t c = 0; c < headCnt; c++) o[c] = (uint8_t)gc_post_base(pg, headNode, headFrom + c);
+			}
+			base += total;
+		}
+	}
+	else
+	{
+		const uint32_t* path = pathNodes + pc.first_node;
+		const uint32_t m = pc.num_nodes, first = path[0], lastNode = path[m - 1];
+		for (uint32_t tile = 0; tile < m; tile += GC_PIECE_THREADS)
+		{
+			const uint32_t k = tile + tid;
+			uint32_t node = 0, S = 0, cnt = 0;
+			if (k < m)
+			{
+				node = path[k];
+				uint32_t L = pg.nodeLength[node];
+				if (node == first) S = pc.first_offset; else if (node == lastNode) L = pc.last_offset + 1; // compared by VALUE, as Aligner.cpp:413-416 does
+				cnt = L > S ? L - S : 0;
+			}
+			uint32_t off, total;
+			Scan(scanTmp).ExclusiveSum(cnt, off, total);
+			__syncthreads();
+			if (WRITE) { uint8_t* o = dst + base + off; for (uint32_t c = 0; c < cnt; c++) o[c] = (uint8_t)gc_post_base(pg, node, S + c); }
+			base += total;
+		}
+	}
+	if (!WRITE)
+	{
+		__syncthreads();
+		if (tid == 0)
+		{
+			uint64_t len = base;
+			if (sViolation) len = gc_pair_path_string(pg, setTraces[pc.set], setPairs[pc.set][pc.index], nullptr);
+			lens[i] = len; flags[i] = (uint8_t)sViolation;
+		}
+	}
 }
 
 extern "C" int gcgpu_nw_compose(gcgpu_ctx* ctx, const gcgpu_nw_piece* pieces, uint32_t n, const uint32_t* path_nodes, uint64_t num_path_nodes, uint64_t* piece_offsets)
@@ -630,17 +714,18 @@ extern "C" int gcgpu_nw_compose(gcgpu_ctx* ctx, const gcgpu_nw_piece* pieces, ui
 	for (uint64_t i = 0; i < num_path_nodes; i++) if (path_nodes[i] >= ctx->numNodes) return setError(GCGPU_ERR_ARG, "gcgpu_nw_compose: path node out of range");
 	struct SetPtrs { const GcPair* pairs[GCGPU_TRACE_SETS]; const uint64_t* traces[GCGPU_TRACE_SETS]; } sp;
 	for (int s = 0; s < GCGPU_TRACE_SETS; s++) { sp.pairs[s] = (const GcPair*)R->sets[s].pairs.p; sp.traces[s] = (const uint64_t*)R->sets[s].traces.p; }
-	size_t offPieces = 0, offPtrs = alignUp((size_t)n * sizeof(gcgpu_nw_piece), 128), offLens = alignUp(offPtrs + sizeof(SetPtrs), 128), offOffs = alignUp(offLens + ((size_t)n + 1) * 8, 128), end = offOffs + ((size_t)n + 1) * 8;
+	size_t offPieces = 0, offPtrs = alignUp((size_t)n * sizeof(gcgpu_nw_piece), 128), offLens = alignUp(offPtrs + sizeof(SetPtrs), 128), offOffs = alignUp(offLens + ((size_t)n + 1) * 8, 128), offFlags = offOffs + ((size_t)n + 1) * 8, end = offFlags + n + 16;
 	CUDA_TRY(R->pieces.ensure(end));
 	CUDA_TRY(R->pathNodes.ensure(num_path_nodes * 4 + 16));
 	uint8_t* P = (uint8_t*)R->pieces.p;
 	const GcPair* const* dPairs = (const GcPair* const*)(P + offPtrs); const uint64_t* const* dTraces = (const uint64_t* const*)(P + offPtrs + sizeof(sp.pairs));
-	uint64_t* dLens = (uint64_t*)(P + offLens); uint64_t* dOffs = (uint64_t*)(P + offOffs);
+	uint64_t* dLens = (uint64_t*)(P + offLens); uint64_t* dOffs = (uint64_t*)(P + offOffs); uint8_t* dFlags = P + offFlags;
 	CUDA_TRY(gcCopy(ctx, P + offPieces, pieces, (size_t)n * sizeof(gcgpu_nw_piece), cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(gcCopy(ctx, P + offPtrs, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(gcCopy(ctx, R->pathNodes.p, path_nodes, num_path_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	gc_piece_len_kernel<<<(n + 1 + 63) / 64, 64, 0, ctx->stream>>>(R->pg, (const gcgpu_nw_piece*)(P + offPieces), n, (const GcReadDesc*)R->reads.p, dPairs, dTraces, (const uint32_t*)R->pathNodes.p, dLens);
+	gc_piece_kernel<false><<<n + 1, GC_PIECE_THREADS, 0, ctx->stream>>>(R->pg, (const gcgpu_nw_piece*)(P + offPieces), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p, dPairs, dTraces, (const uint32_t*)R->pathNodes.p,
+		dLens, dFlags, nullptr, nullptr);
 	ctx->launches++;
 	int rc = scanU64(ctx, dLens, dOffs, n); if (rc != GCGPU_OK) return rc;
 	CUDA_TRY(cudaGetLastError());
@@ -648,9 +733,9 @@ extern "C" int gcgpu_nw_compose(gcgpu_ctx* ctx, const gcgpu_nw_piece* pieces, ui
 	CUDA_TRY(gcSyncStream(ctx));
 	uint64_t total = piece_offsets[n];
 	CUDA_TRY(ctx->nwSeqBuf.ensure(total + 16));
-	gc_piece_write_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(R->pg, (const gcgpu_nw_piece*)(P + offPieces), n, dPairs, dTraces, (const uint32_t*)R->pathNodes.p, dOffs, (uint8_t*)ctx->nwSeqBuf.p);
-	gc_piece_reads_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>((const gcgpu_nw_piece*)(P + offPieces), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p, dOffs, (uint8_t*)ctx->nwSeqBuf.p);
-	ctx->launches += 2;
+	gc_piece_kernel<true><<<n, GC_PIECE_THREADS, 0, ctx->stream>>>(R->pg, (const gcgpu_nw_piece*)(P + offPieces), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p, dPairs, dTraces, (const uint32_t*)R->pathNodes.p,
+		dLens, dFlags, dOffs, (uint8_t*)ctx->nwSeqBuf.p);
+	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
@@ -663,20 +748,99 @@ extern "C" int gcgpu_nw_compose(gcgpu_ctx* ctx, const gcgpu_nw_piece* pieces, ui
 }
 
 // ------------------------------------------------------------------ edit runs of whole-read alignments
-__global__ void gc_tokens_kernel(GcPostGraph pg, const GcPair* __restrict__ pairs, const uint64_t* __restrict__ tr, const uint32_t* __restrict__ which, uint32_t n, const GcReadDesc* __restrict__ reads, const uint8_t* __restrict__ codes,
-	const uint64_t* __restrict__ offs, uint32_t* __restrict__ tokens, uint64_t* __restrict__ counts, gcgpu_aln_tokens* __restrict__ meta)
+// One block per alignment (GraphAlignerVGAlignment::traceToAlignment, GraphAlignerVGAlignment.h:37-165, as gc_tokenize states it).
+// Whether a trace step opens a new mapping and which edit type it is are functions of steps pos-1 and pos alone as long as a
+// node switch never re-enters the current original node at or before the mapping's first offset (impossible on a DAG;
+// checked, and an alignment that violates it is tokenized by one thread with the sequential code).  So: per-step flags,
+// one block scan of (mappings opened, runs opened, position of the last run start), scattered token writes.
+// WRITE = false: counts[i] = number of token words, flags[i] = sequential fallback; WRITE = true: tokens + meta.
+#define GC_TOKEN_THREADS 256
+struct GcTokScan { uint32_t b, r; int32_t s; };
+struct GcTokScanOp { __device__ __forceinline__ GcTokScan operator()(const GcTokScan& x, const GcTokScan& y) const { GcTokScan o; o.b = x.b + y.b; o.r = x.r + y.r; o.s = x.s > y.s ? x.s : y.s; return o; } };
+template <bool WRITE>
+__global__ void __launch_bounds__(GC_TOKEN_THREADS) gc_tokens_kernel(GcPostGraph pg, const GcPair* __restrict__ pairs, const uint64_t* __restrict__ tr, const uint32_t* __restrict__ which, uint32_t n, const GcReadDesc* __restrict__ reads, const uint8_t* __restrict__ codes,
+	const uint64_t* __restrict__ offs, uint32_t* __restrict__ tokens, uint64_t* __restrict__ counts, uint8_t* __restrict__ flags, gcgpu_aln_tokens* __restrict__ meta)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i > n) return;
-	if (i == n) { if (!tokens) counts[i] = 0; return; }
-	GcPair p = pairs[which[i]];
+	typedef cub::BlockScan<GcTokScan, GC_TOKEN_THREADS> Scan;
+	__shared__ typename Scan::TempStorage scanTmp;
+	__shared__ uint8_t tileType[GC_TOKEN_THREADS];
+	__shared__ uint32_t sViolation, sCount[4];
+	__shared__ uint8_t sLastType;
+	const uint32_t i = blockIdx.x, tid = threadIdx.x;
+	if (i >= n) { if (!WRITE && i == n && tid == 0) counts[i] = 0; return; }
+	const GcPair p = pairs[which[i]];
 	GcPairTokenSrc src; src.pg = &pg; src.tr = tr; src.p = &p; src.codes = codes + 2 * reads[p.read].charOffset;
-	GcTokenCounts c = gc_tokenize(src, gc_pair_size(p), tokens ? tokens + offs[i] : nullptr);
-	if (!tokens) counts[i] = c.tokens;
-	else
+	const uint32_t m = gc_pair_size(p);
+	uint32_t* out = WRITE ? tokens + offs[i] : nullptr;
+	if (WRITE && flags[i])
 	{
-		gcgpu_aln_tokens m; m.token_offset = offs[i]; m.num_tokens = c.tokens; m.matches = c.matches; m.steps = c.matches + c.mismatches + c.insertions + c.deletions; m.reserved = 0;
-		meta[i] = m;
+		if (tid == 0)
+		{
+			GcTokenCounts c = gc_tokenize(src, m, out);
+			gcgpu_aln_tokens mt; mt.token_offset = offs[i]; mt.num_tokens = c.tokens; mt.matches = c.matches; mt.steps = c.matches + c.mismatches + c.insertions + c.deletions; mt.reserved = 0;
+			meta[i] = mt;
+		}
+		return;
+	}
+	if (tid == 0) { sViolation = 0; sCount[0] = sCount[1] = sCount[2] = sCount[3] = 0; sLastType = 0; }
+	__syncthreads();
+	GcTokScan carry; carry.b = 0; carry.r = 0; carry.s = 0;
+	for (uint32_t tile = 0; tile < m; tile += GC_TOKEN_THREADS)
+	{
+		const uint32_t pos = tile + tid;
+		bool boundary = false;
+		uint32_t t = 0;
+		GcTokenStep e; e.node = 0; e.nodeOffset = 0; e.seqPos = 0; e.nodeSwitch = false; e.match = false;
+		if (pos < m)
+		{
+			e = src(pos);
+			if (pos == 0) { boundary = true; t = e.match ? GC_EDIT_MATCH : GC_EDIT_MISMATCH; }
+			else
+			{
+				GcTokenStep prev = src(pos - 1);
+				boundary = prev.nodeSwitch && e.node != prev.node;
+				if (prev.nodeSwitch && e.node == prev.node && e.nodeOffset <= prev.nodeOffset) sViolation = 1; // would need the mapping's first offset
+				if (!boundary && e.nodeOffset < prev.nodeOffset) sViolation = 1;
+				if (prev.seqPos == e.seqPos) t = GC_EDIT_DELETION;
+				else if (!boundary && prev.nodeOffset == e.nodeOffset) t = GC_EDIT_INSERTION;
+				else t = e.match ? GC_EDIT_MATCH : GC_EDIT_MISMATCH;
+			}
+			atomicAdd(&sCount[t], 1u);
+		}
+		tileType[tid] = (uint8_t)t;
+		__syncthreads();
+		const uint32_t prevType = tid > 0 ? tileType[tid - 1] : sLastType;
+		const bool runStart = pos < m && (pos == 0 || boundary || t != prevType);
+		GcTokScan mine; mine.b = (pos < m && boundary) ? 1u : 0u; mine.r = runStart ? 1u : 0u; mine.s = runStart ? (int32_t)pos : 0;
+		GcTokScan ex, agg, ident; ident.b = 0; ident.r = 0; ident.s = 0;
+		Scan(scanTmp).ExclusiveScan(mine, ex, ident, GcTokScanOp(), agg);
+		ex = GcTokScanOp()(carry, ex);
+		if (WRITE && runStart)
+		{
+			uint32_t w = 3 * ex.b + ex.r; // words before this step's tokens, plus one for the end word of the run that ends here
+			if (pos > 0) out[w - 1] = (prevType << 30) | (pos - (uint32_t)ex.s);
+			if (boundary) { out[w] = 0; out[w + 1] = (uint32_t)e.node; out[w + 2] = e.nodeOffset; }
+		}
+		__syncthreads();
+		carry = GcTokScanOp()(carry, agg);
+		if (tid == GC_TOKEN_THREADS - 1) sLastType = (uint8_t)t;
+		__syncthreads();
+	}
+	if (tid == 0)
+	{
+		uint32_t total = m ? 3 * carry.b + carry.r : 0;
+		if (!WRITE)
+		{
+			uint8_t fl = (uint8_t)sViolation;
+			if (fl) { GcTokenCounts c = gc_tokenize(src, m, (uint32_t*)nullptr); total = c.tokens; }
+			counts[i] = total; flags[i] = fl;
+		}
+		else
+		{
+			if (m) out[total - 1] = ((uint32_t)tileType[(m - 1) % GC_TOKEN_THREADS] << 30) | (m - (uint32_t)carry.s);
+			gcgpu_aln_tokens mt; mt.token_offset = offs[i]; mt.num_tokens = total; mt.matches = sCount[GC_EDIT_MATCH]; mt.steps = sCount[0] + sCount[1] + sCount[2] + sCount[3]; mt.reserved = 0;
+			meta[i] = mt;
+		}
 	}
 }
 
@@ -691,14 +855,14 @@ extern "C" int gcgpu_encode_alignments(gcgpu_ctx* ctx, int set, const uint32_t* 
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	GcTraceSet& S = R->sets[set];
 	for (uint32_t i = 0; i < n; i++) if (pairs[i] >= S.numPairs) return setError(GCGPU_ERR_ARG, "gcgpu_encode_alignments: pair " + std::to_string(i) + " out of range");
-	size_t offWhich = 0, offCnt = alignUp((size_t)n * 4, 128), offOffs = alignUp(offCnt + ((size_t)n + 1) * 8, 128), offMeta = alignUp(offOffs + ((size_t)n + 1) * 8, 128), end = offMeta + (size_t)n * sizeof(gcgpu_aln_tokens);
+	size_t offWhich = 0, offCnt = alignUp((size_t)n * 4, 128), offOffs = alignUp(offCnt + ((size_t)n + 1) * 8, 128), offMeta = alignUp(offOffs + ((size_t)n + 1) * 8, 128), offFlags = offMeta + (size_t)n * sizeof(gcgpu_aln_tokens), end = offFlags + n + 16;
 	CUDA_TRY(R->tokenMeta.ensure(end));
 	uint8_t* T = (uint8_t*)R->tokenMeta.p;
-	uint64_t* dCnt = (uint64_t*)(T + offCnt); uint64_t* dOffs = (uint64_t*)(T + offOffs);
+	uint64_t* dCnt = (uint64_t*)(T + offCnt); uint64_t* dOffs = (uint64_t*)(T + offOffs); uint8_t* dFlags = T + offFlags;
 	CUDA_TRY(gcCopy(ctx, T + offWhich, pairs, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	gc_tokens_kernel<<<(n + 1 + 63) / 64, 64, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(T + offWhich), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
-		nullptr, nullptr, dCnt, nullptr);
+	gc_tokens_kernel<false><<<n + 1, GC_TOKEN_THREADS, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(T + offWhich), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
+		nullptr, nullptr, dCnt, dFlags, nullptr);
 	ctx->launches++;
 	int rc = scanU64(ctx, dCnt, dOffs, n); if (rc != GCGPU_OK) return rc;
 	CUDA_TRY(cudaGetLastError());
@@ -706,8 +870,8 @@ extern "C" int gcgpu_encode_alignments(gcgpu_ctx* ctx, int set, const uint32_t* 
 	CUDA_TRY(gcCopy(ctx, &total, dOffs + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(R->tokens.ensure(total * 4 + 16));
-	gc_tokens_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(T + offWhich), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
-		dOffs, (uint32_t*)R->tokens.p, nullptr, (gcgpu_aln_tokens*)(T + offMeta));
+	gc_tokens_kernel<true><<<n, GC_TOKEN_THREADS, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(T + offWhich), n, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
+		dOffs, (uint32_t*)R->tokens.p, nullptr, dFlags, (gcgpu_aln_tokens*)(T + offMeta));
 	ctx->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
