@@ -44,68 +44,65 @@ inline uint32_t reverseBits(uint32_t v, int len)
 	return r;
 }
 
-// length-limited Huffman code lengths: plain Huffman by repeated pairing, then the standard
-// overflow repair (as zlib's gen_bitlen): symbols deeper than maxLen are lifted, shallower leaves pushed down
+// Length-limited Huffman code lengths of up to 320 symbols, without a heap or an allocation (three codes are built per
+// gzip member, i.e. per read): the used symbols sorted by frequency, the classic two-queue merge (leaves in one sorted
+// queue, internal nodes appear in non-decreasing weight in the other), depths from the parent links, and for codes
+// deeper than maxLen the leaf-moving repair on the per-length counts that keeps the Kraft sum at one; lengths are then
+// handed out longest-first to the rarest symbols.
 inline void buildLengths(const uint32_t* freq, int n, int maxLen, uint8_t* lens)
 {
-	struct Node { uint64_t w; int left, right; };
-	std::vector<Node> nodes;
-	std::vector<int> live;
-	for (int i = 0; i < n; i++) { lens[i] = 0; if (freq[i]) { nodes.push_back(Node { freq[i], -1 - i, -1 }); live.push_back((int)nodes.size() - 1); } }
-	if (live.empty()) return;
-	if (live.size() == 1) { lens[-1 - nodes[live[0]].left] = 1; return; }
-	auto cmp = [&nodes](int a, int b) { return nodes[a].w != nodes[b].w ? nodes[a].w > nodes[b].w : a > b; };
-	std::make_heap(live.begin(), live.end(), cmp);
-	while (live.size() > 1)
+	struct Leaf { uint32_t w; uint16_t sym; };
+	Leaf leaves[320];
+	int m = 0;
+	for (int i = 0; i < n; i++) { lens[i] = 0; if (freq[i]) { leaves[m].w = freq[i]; leaves[m].sym = (uint16_t)i; m++; } }
+	if (m == 0) return;
+	if (m == 1) { lens[leaves[0].sym] = 1; return; }
+	std::sort(leaves, leaves + m, [](const Leaf& a, const Leaf& b) { return a.w != b.w ? a.w < b.w : a.sym < b.sym; });
+	// nodes 0..m-1 = leaves in ascending weight, m..2m-2 = internal nodes in creation order
+	uint64_t weight[640]; int16_t parent[640];
+	for (int i = 0; i < m; i++) weight[i] = leaves[i].w;
+	int nextLeaf = 0, nextInternal = m, made = m;
+	auto take = [&]() -> int
 	{
-		std::pop_heap(live.begin(), live.end(), cmp); int a = live.back(); live.pop_back();
-		std::pop_heap(live.begin(), live.end(), cmp); int b = live.back(); live.pop_back();
-		nodes.push_back(Node { nodes[a].w + nodes[b].w, a, b });
-		live.push_back((int)nodes.size() - 1);
-		std::push_heap(live.begin(), live.end(), cmp);
+		if (nextLeaf < m && (nextInternal >= made || weight[nextLeaf] <= weight[nextInternal])) return nextLeaf++;
+		return nextInternal++;
+	};
+	while (made < 2 * m - 1)
+	{
+		int a = take(), b = take();
+		weight[made] = weight[a] + weight[b];
+		parent[a] = (int16_t)made; parent[b] = (int16_t)made;
+		made++;
 	}
-	// depth of every leaf
-	std::vector<int> depth(nodes.size(), 0);
-	std::vector<int> blCount(64, 0);
-	for (int i = (int)nodes.size() - 1; i >= 0; i--)
+	// depths: the root is the last node; every parent has a larger index than its children
+	uint8_t depth[640];
+	depth[made - 1] = 0;
+	int blCount[64] = { 0 };
+	int overflow = 0;
+	for (int i = made - 2; i >= 0; i--)
 	{
-		if (nodes[i].right == -1 && nodes[i].left < 0) { int d = depth[i]; if (d > maxLen) d = maxLen; lens[-1 - nodes[i].left] = (uint8_t)d; blCount[d]++; }
-		else { depth[nodes[i].left] = depth[i] + 1; depth[nodes[i].right] = depth[i] + 1; }
+		int d = depth[parent[i]] + 1;
+		if (i < m) { if (d > maxLen) { d = maxLen; overflow++; } blCount[d]++; }
+		depth[i] = (uint8_t)(d > 63 ? 63 : d);
 	}
-	// Kraft sum in units of 2^-maxLen must be exactly 2^maxLen
-	uint64_t kraft = 0;
-	for (int l = 1; l <= maxLen; l++) kraft += (uint64_t)blCount[l] << (maxLen - l);
-	const uint64_t full = 1ull << maxLen;
-	if (kraft > full)
+	if (overflow > 0)
 	{
-		// sort symbols by frequency ascending; lengthen the cheapest symbols that are shorter than maxLen
-		std::vector<int> order;
-		for (int i = 0; i < n; i++) if (lens[i]) order.push_back(i);
-		std::sort(order.begin(), order.end(), [&](int a, int b) { return freq[a] != freq[b] ? freq[a] < freq[b] : a < b; });
-		while (kraft > full)
+		// every leaf that was cut to maxLen over-subscribes the code: move a leaf one level down from the deepest level that has
+		// one to spare, which frees room for a pair at the bottom
+		do
 		{
-			bool moved = false;
-			for (int s : order)
-			{
-				if (lens[s] < maxLen) { kraft -= 1ull << (maxLen - lens[s] - 1); lens[s]++; moved = true; if (kraft <= full) break; }
-			}
-			if (!moved) break;
-		}
+			int bits = maxLen - 1;
+			while (blCount[bits] == 0) bits--;
+			blCount[bits]--;
+			blCount[bits + 1] += 2;
+			blCount[maxLen]--;
+			overflow -= 2;
+		} while (overflow > 0);
 	}
-	if (kraft < full)
-	{
-		// spare code space: shorten the most frequent symbols where it fits
-		std::vector<int> order;
-		for (int i = 0; i < n; i++) if (lens[i]) order.push_back(i);
-		std::sort(order.begin(), order.end(), [&](int a, int b) { return freq[a] != freq[b] ? freq[a] > freq[b] : a < b; });
-		bool again = true;
-		while (again && kraft < full)
-		{
-			again = false;
-			for (int s : order)
-				if (lens[s] > 1 && kraft + (1ull << (maxLen - lens[s])) <= full) { kraft += 1ull << (maxLen - lens[s]); lens[s]--; again = true; }
-		}
-	}
+	// longest codes to the rarest symbols (leaves are in ascending weight)
+	int k = 0;
+	for (int bits = maxLen; bits >= 1; bits--)
+		for (int c = blCount[bits]; c > 0; c--) lens[leaves[k++].sym] = (uint8_t)bits;
 }
 
 // canonical codes (RFC 1951 3.2.2), bit-reversed for the LSB-first writer

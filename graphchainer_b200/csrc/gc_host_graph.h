@@ -100,8 +100,14 @@ struct GcHostGraph
 		finish();
 	}
 
+	// per split node, what seed clustering reads (GraphAligner.h:236-245), in one cache line fetch instead of two
+	struct SeedAttr { uint64_t chainApproxPos; uint32_t chainNumber; uint32_t pad; };
+	std::vector<SeedAttr> seedAttr;
+
 	void finish()
 	{
+		seedAttr.resize(chainNumber.size());
+		for (size_t i = 0; i < chainNumber.size(); i++) { seedAttr[i].chainApproxPos = chainApproxPos[i]; seedAttr[i].chainNumber = chainNumber[i]; seedAttr[i].pad = 0; }
 		int32_t maxId = -1;
 		for (auto id : origIds) if (id > maxId) maxId = id;
 		origIndexOfId.assign((size_t)maxId + 1, -1);

@@ -294,24 +294,18 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		devMs += wallNow() - tDev;
 		stats.s0Ms += gcgpu_last_kernel_ms(ctx);
 		const gcgpu_seed_match* matches = (const gcgpu_seed_match*)seedBuf.p;
-		#pragma omp parallel for schedule(dynamic, 4)
-		for (size_t r = 0; r < R; r++)
+		#pragma omp parallel
 		{
-			std::vector<std::tuple<size_t, size_t, size_t, size_t>> matchIndices;
-			matchIndices.reserve(matchOff[r + 1] - matchOff[r]);
-			for (uint64_t i = matchOff[r]; i < matchOff[r + 1]; i++) matchIndices.emplace_back((size_t)matches[i].pos, (size_t)0, (size_t)matches[i].start, (size_t)matches[i].count);
-			{ GC_PROF_SCOPE(0, "seed.seedsFromMatches"); seedsOrdered[r] = gcseed::seedsFromMatches(g, matchIndices, reads[r].sequence.size(), params.minimizerSeedDensity); }
-			out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
-			{ GC_PROF_SCOPE(1, "seed.orderSeeds"); if (!seedsOrdered[r].empty()) gcseed::orderSeeds(g, seedsOrdered[r]); }
-			// the split pass sorts a copy of the ordered seeds by position (Aligner.cpp:667); the same std::sort call on the same
-			// element order gives the reference's permutation.  The device holds the seeds in this order ("cells").
-			GC_PROF_SCOPE(2, "seed.byPos");
-			std::vector<GcSeedHit>& ordered = seedsOrdered[r];
-			for (size_t i = 0; i < ordered.size(); i++) ordered[i].orderedIdx = (uint32_t)i;
-			std::vector<GcSeedHit>& byPos = seedsByPos[r];
-			byPos = ordered;
-			std::sort(byPos.begin(), byPos.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seqPos < right.seqPos; });
-			for (size_t i = 0; i < byPos.size(); i++) { byPos[i].byPosIdx = (uint32_t)i; ordered[byPos[i].orderedIdx].byPosIdx = (uint32_t)i; }
+			gcseed::Scratch scratch;
+			#pragma omp for schedule(dynamic, 4)
+			for (size_t r = 0; r < R; r++)
+			{
+				GC_PROF_SCOPE(0, "seed.seedRead");
+				// count sort + density cut + expansion, clustering, goodness order and the split pass's position order (the device
+				// holds the seeds in position order: "cells")
+				gcseed::seedRead(g, matches + matchOff[r], (size_t)(matchOff[r + 1] - matchOff[r]), reads[r].sequence.size(), params.minimizerSeedDensity, scratch, seedsOrdered[r], seedsByPos[r]);
+				out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
+			}
 		}
 	}
 	{

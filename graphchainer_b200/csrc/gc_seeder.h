@@ -1,178 +1,149 @@
-// Host side of S0: minimizer seeding of a read and seed clustering.
-//   MinimizerSeeder::getSeeds / iterateKmers / addMinimizers / matchToSeedHit
-//       (src/MinimizerSeeder.cpp:60-102, 494-555)
-//   GraphAligner::orderSeedsByChaining  (src/GraphAligner.h:233-295)
-// The k-mer walk and the index probes (iterateKmers + addMinimizers) run on the device
-// (gcgpu_seed, gc_seed.cuh); what stays here is sequential per read and full of libstdc++
-// std::sort calls with partial keys whose permutation must match the reference's:
-// the same std::sort calls on the same element order are used.  iterateKmers is kept as the
-// restatement the device form is tested against (tests/hostsim/seed_ref.h).
+// Host side of S0: from the index answers of a read (gcgpu_seed: which k-mers the reference looks up and what the
+// minimizer index holds for them) to its seeds in the two orders the pipeline walks them.
+//   MinimizerSeeder::getSeeds, second half + matchToSeedHit   (src/MinimizerSeeder.cpp:533-555)
+//   GraphAligner::orderSeedsByChaining                        (src/GraphAligner.h:233-295)
+//   the split pass's sort by position                         (src/Aligner.cpp:667)
+//
+// What of the reference is observable here, and what is not:
+//   * Three std::sort calls decide the ORDER of seeds with equal keys (matches of equal count, seeds of equal goodness,
+//     seeds at the same read position), and that order reaches the output (which seed is extended first).  libstdc++'s
+//     introsort is driven by comparison results and the element count only, so sorting 8-byte (key, index) proxies with the
+//     same comparison on the same initial order yields the reference's permutation without moving 90-byte seed records.
+//   * Everything the clustering computes (seedGoodness, seedClusterSize) is a function of the cluster a seed falls in and
+//     of the SET of read positions in it -- not of the order in which equal diagonals or equal positions are visited -- so
+//     it is computed here on flat arrays: one sort of (chain, diagonal) keys, a scan for the gaps > 100, and per cluster
+//     the sorted positions (the reference: a hash map of per-chain vectors, two sorts of index pairs per cluster).
+//   * The per-hit graph lookups (position list, chain number, approximate chain position) are cache misses into arrays of
+//     tens to hundreds of MB: they are issued as prefetches for all hits of the read before the first one is consumed.
 #pragma once
 #include <algorithm>
 #include <cstdint>
 #include <limits>
 #include <string>
-#include <tuple>
-#include <unordered_map>
 #include <vector>
+#include "../../include/gcgpu.h"
 #include "gc_host_graph.h"
-#ifndef GC_PROF_SCOPE
-#define GC_PROF_SCOPE(id, name)
-#endif
 
-// src/GraphAlignerWrapper.h:11-37
+// the fields of the reference's SeedHit (src/GraphAlignerWrapper.h:11-37) that the per-read pipeline reads
 struct GcSeedHit
 {
-	int nodeID;
-	size_t nodeOffset;
-	size_t seqPos;
-	size_t matchLen;
-	bool reverse;
-	size_t alignmentGraphNodeId;
-	size_t alignmentGraphNodeOffset;
-	size_t rawSeedGoodness;
-	size_t seedGoodness;
-	size_t seedClusterSize;
-	uint32_t orderedIdx = 0; // position after OrderSeeds (goodness order)
-	uint32_t byPosIdx = 0;   // position after the split pass's sort by seqPos (Aligner.cpp:667) = index of the seed's cell on the device
+	uint32_t seqPos;                    // k-mer END position in the read
+	uint32_t alignmentGraphNodeId;      // split node
+	uint32_t seedGoodness;
+	uint32_t seedClusterSize;
+	uint32_t orderedIdx = 0;            // position after OrderSeeds (goodness order)
+	uint32_t byPosIdx = 0;              // position after the split pass's sort by seqPos = index of the seed's cell on the device
+	uint8_t alignmentGraphNodeOffset;
+	uint8_t matchLen;
 };
 
 namespace gcseed {
 
-inline int charToInt(char c)
+// scratch of one host thread, reused from read to read
+struct Scratch
 {
-	switch (c) { case 'a': case 'A': return 0; case 'c': case 'C': return 1; case 'g': case 'G': return 2; case 't': case 'T': return 3; }
-	return -1;
-}
+	struct Key32 { uint32_t key; uint32_t idx; };
+	struct DiagKey { uint64_t diag; uint32_t chain; uint32_t idx; };
+	std::vector<Key32> byCount, byGoodness, byPos;
+	std::vector<DiagKey> diag;
+	std::vector<uint32_t> raw, positions;     // rawSeedGoodness per hit; read positions of one cluster
+	std::vector<GcSeedHit> hits;              // expansion order
+};
 
-// iterateKmers (MinimizerSeeder.cpp:60-102): every k-mer of the read, re-emitted when it
-// changed or the last emission is a whole window back
-template <typename F>
-void iterateKmers(const std::string& str, size_t kmerLength, size_t windowSize, F callback)
+// Seeds of one read.  matches[0..n) = the device's answers in ascending read position.  ordered = the reference's seed
+// vector after OrderSeeds (goodness order), byPos = the same seeds after the split pass's sort by position; the two carry
+// each other's indices.
+inline void seedRead(const GcHostGraph& g, const gcgpu_seed_match* matches, size_t n, size_t sequenceSize, double density, Scratch& s, std::vector<GcSeedHit>& ordered, std::vector<GcSeedHit>& byPos)
 {
-	const size_t realWindow = windowSize - kmerLength + 1;
-	if (str.size() < kmerLength) return;
-	const size_t mask = ~(0xFFFFFFFFFFFFFFFFull << (kmerLength * 2));
-	size_t offset = 0;
-	while (true)
+	ordered.clear(); byPos.clear();
+	// ---- matches by count (MinimizerSeeder.cpp:533-536); ties keep introsort's order from ascending position
+	s.byCount.resize(n);
+	for (size_t i = 0; i < n; i++) { s.byCount[i].key = matches[i].count; s.byCount[i].idx = (uint32_t)i; }
+	std::sort(s.byCount.begin(), s.byCount.end(), [](const Scratch::Key32& left, const Scratch::Key32& right) { return left.key < right.key; });
+	// ---- density cut (:537-544): stop at the first match with more positions than the last accepted one once the budget is spent
+	size_t maxHits = density == -1 ? std::numeric_limits<size_t>::max() : (size_t)(sequenceSize * density);
+	size_t kept = 0, numHits = 0, allowedCount = 0;
+	for (; kept < n; kept++)
 	{
-		while (offset < str.size() && charToInt(str[offset]) < 0) offset++;
-		if (offset + kmerLength > str.size()) return;
-		size_t kmer = 0;
-		bool restart = false;
-		for (size_t i = 0; i < kmerLength; i++)
+		size_t count = s.byCount[kept].key;
+		if (numHits >= maxHits && count > allowedCount) break;
+		allowedCount = count;
+		numHits += count;
+		__builtin_prefetch(&g.mzPositions[matches[s.byCount[kept].idx].start]);
+	}
+	if (numHits == 0) return;
+	// ---- expansion (matchToSeedHit, :546-555): one seed per indexed position of every kept k-mer, in that order
+	s.hits.resize(numHits); s.raw.resize(numHits);
+	const uint32_t maxCount = (uint32_t)g.mzMaxCount;
+	{
+		size_t h = 0;
+		for (size_t k = 0; k < kept; k++)
 		{
-			int v = charToInt(str[offset + i]);
-			if (v < 0) { offset += i; restart = true; break; }
-			kmer <<= 2;
-			kmer |= (size_t)v;
-		}
-		if (restart) continue;
-		callback(offset + kmerLength - 1, kmer);
-		size_t lastKmer = kmer;
-		size_t lastPos = offset + kmerLength - 1;
-		size_t i = kmerLength;
-		for (; offset + i < str.size(); i++)
-		{
-			int v = charToInt(str[offset + i]);
-			if (v < 0) { offset += i; restart = true; break; }
-			kmer <<= 2;
-			kmer &= mask;
-			kmer |= (size_t)v;
-			if (lastKmer != kmer || lastPos <= offset + i - realWindow)
+			const gcgpu_seed_match& m = matches[s.byCount[k].idx];
+			for (uint32_t i = m.start; i < m.start + m.count; i++, h++)
 			{
-				callback(offset + i, kmer);
-				lastKmer = kmer;
-				lastPos = offset + i;
+				uint64_t mergepos = g.mzPositions[i];
+				GcSeedHit& hit = s.hits[h];
+				hit.seqPos = m.pos;
+				hit.alignmentGraphNodeId = (uint32_t)(mergepos >> 6);
+				hit.alignmentGraphNodeOffset = (uint8_t)(mergepos & 63);
+				hit.matchLen = (uint8_t)g.mzLength;
+				s.raw[h] = maxCount - m.count; // rawSeedGoodness
+				__builtin_prefetch(&g.seedAttr[hit.alignmentGraphNodeId]);
 			}
 		}
-		if (!restart) return;
 	}
-}
-
-// the second half of MinimizerSeeder::getSeeds (MinimizerSeeder.cpp:533-544) + matchToSeedHit (:546-555):
-// sort the matches by count, apply the density cut, expand every kept k-mer into its positions.
-// matchIndices = (k-mer END position, 0, first position index, count) in ascending position order.
-inline std::vector<GcSeedHit> seedsFromMatches(const GcHostGraph& g, std::vector<std::tuple<size_t, size_t, size_t, size_t>>& matchIndices, size_t sequenceSize, double density)
-{
-	const size_t maxCount = g.mzMaxCount;
-	std::vector<GcSeedHit> result;
-	size_t maxHits = (size_t)(sequenceSize * density);
-	if (density == -1) maxHits = std::numeric_limits<size_t>::max();
-	std::sort(matchIndices.begin(), matchIndices.end(), [](const std::tuple<size_t, size_t, size_t, size_t>& left, const std::tuple<size_t, size_t, size_t, size_t>& right)
+	// ---- clusters (GraphAligner.h:236-283): per chain, runs of diagonals no more than 100 apart
+	s.diag.resize(numHits);
+	for (size_t h = 0; h < numHits; h++)
 	{
-		return std::get<3>(left) < std::get<3>(right);
-	});
-	size_t seedsHere = 0;
-	size_t allowedCount = 0;
-	for (auto match : matchIndices)
+		const GcHostGraph::SeedAttr& a = g.seedAttr[s.hits[h].alignmentGraphNodeId];
+		s.diag[h].chain = a.chainNumber;
+		s.diag[h].diag = a.chainApproxPos + s.hits[h].alignmentGraphNodeOffset - s.hits[h].seqPos; // size_t arithmetic, as the reference's
+		s.diag[h].idx = (uint32_t)h;
+	}
+	std::sort(s.diag.begin(), s.diag.end(), [](const Scratch::DiagKey& left, const Scratch::DiagKey& right) { return left.chain != right.chain ? left.chain < right.chain : left.diag < right.diag; });
+	const int matchLen = (int)g.mzLength;
+	for (size_t first = 0; first < numHits; )
 	{
-		size_t start = std::get<2>(match);
-		size_t end = start + std::get<3>(match);
-		if (seedsHere >= maxHits && end - start > allowedCount) break;
-		allowedCount = end - start;
-		for (size_t i = start; i < end; i++)
+		size_t last = first + 1;
+		while (last < numHits && s.diag[last].chain == s.diag[first].chain && s.diag[last].diag <= s.diag[last - 1].diag + 100) last++;
+		// bases of the read covered by the cluster's k-mers (:265-272)
+		s.positions.resize(last - first);
+		for (size_t k = first; k < last; k++) s.positions[k - first] = s.hits[s.diag[k].idx].seqPos;
+		std::sort(s.positions.begin(), s.positions.end());
+		size_t matchingBps = 0;
+		int lastEnd = std::numeric_limits<int>::min();
+		for (uint32_t p : s.positions)
 		{
-			size_t mergepos = g.mzPositions[i];
-			size_t node = mergepos >> 6;
-			size_t offset = mergepos & 63;
-			// matchToSeedHit (:546-555)
-			GcSeedHit s;
-			s.nodeID = g.nodeIDs[node] / 2;
-			s.nodeOffset = offset + g.nodeOffset[node];
-			s.seqPos = std::get<0>(match);
-			s.matchLen = g.mzLength;
-			s.rawSeedGoodness = maxCount - (size_t)(int)std::get<3>(match);
-			s.reverse = g.reverse[node] != 0;
-			s.alignmentGraphNodeId = node;
-			s.alignmentGraphNodeOffset = offset;
-			s.seedGoodness = 0;
-			s.seedClusterSize = 0;
-			result.push_back(s);
+			int thisStart = (int)p - matchLen + 1, thisEnd = (int)p;
+			matchingBps += (size_t)(thisEnd - std::max(thisStart, lastEnd));
+			lastEnd = thisEnd;
 		}
-		seedsHere += end - start;
-	}
-	return result;
-}
-
-
-// GraphAligner::orderSeedsByChaining (GraphAligner.h:233-295)
-inline void orderSeeds(const GcHostGraph& g, std::vector<GcSeedHit>& seedHits)
-{
-	std::unordered_map<size_t, std::vector<std::pair<size_t, size_t>>> seedPoses;
-	for (size_t i = 0; i < seedHits.size(); i++)
-	{
-		size_t nodeIndex = seedHits[i].alignmentGraphNodeId;
-		size_t realOffset = seedHits[i].alignmentGraphNodeOffset;
-		seedPoses[g.chainNumber[nodeIndex]].emplace_back(i, g.chainApproxPos[nodeIndex] + realOffset - seedHits[i].seqPos);
-	}
-	for (auto& pair : seedPoses)
-	{
-		std::sort(pair.second.begin(), pair.second.end(), [](std::pair<size_t, size_t> left, std::pair<size_t, size_t> right) { return left.second < right.second; });
-		size_t clusterStart = 0;
-		for (size_t i = 1; i <= pair.second.size(); i++)
+		for (size_t k = first; k < last; k++)
 		{
-			if (i < pair.second.size() && pair.second[i].second <= pair.second[i - 1].second + 100) continue;
-			std::sort(pair.second.begin() + clusterStart, pair.second.begin() + i, [&seedHits](std::pair<size_t, size_t> left, std::pair<size_t, size_t> right) { return seedHits[left.first].seqPos < seedHits[right.first].seqPos; });
-			size_t matchingBps = 0;
-			int lastEnd = std::numeric_limits<int>::min();
-			for (size_t j = clusterStart; j < i; j++)
-			{
-				int thisStart = (int)seedHits[pair.second[j].first].seqPos - (int)seedHits[pair.second[j].first].matchLen + 1;
-				int thisEnd = (int)seedHits[pair.second[j].first].seqPos;
-				matchingBps += (thisEnd - std::max(thisStart, lastEnd));
-				lastEnd = thisEnd;
-			}
-			for (size_t j = clusterStart; j < i; j++)
-			{
-				seedHits[pair.second[j].first].seedGoodness = matchingBps + seedHits[pair.second[j].first].rawSeedGoodness;
-				seedHits[pair.second[j].first].seedClusterSize = i - clusterStart;
-			}
-			clusterStart = i;
+			GcSeedHit& hit = s.hits[s.diag[k].idx];
+			hit.seedGoodness = (uint32_t)(matchingBps + s.raw[s.diag[k].idx]);
+			hit.seedClusterSize = (uint32_t)(last - first);
 		}
+		first = last;
 	}
-	std::sort(seedHits.begin(), seedHits.end(), [](const GcSeedHit& left, const GcSeedHit& right) { return left.seedGoodness < right.seedGoodness; });
-	std::reverse(seedHits.begin(), seedHits.end());
+	// ---- goodness order (:284-285: ascending sort, then reversed)
+	s.byGoodness.resize(numHits);
+	for (size_t h = 0; h < numHits; h++) { s.byGoodness[h].key = s.hits[h].seedGoodness; s.byGoodness[h].idx = (uint32_t)h; }
+	std::sort(s.byGoodness.begin(), s.byGoodness.end(), [](const Scratch::Key32& left, const Scratch::Key32& right) { return left.key < right.key; });
+	ordered.resize(numHits);
+	for (size_t h = 0; h < numHits; h++) { ordered[h] = s.hits[s.byGoodness[numHits - 1 - h].idx]; ordered[h].orderedIdx = (uint32_t)h; }
+	// ---- position order of the split pass (Aligner.cpp:667): std::sort of the ordered vector by seqPos
+	s.byPos.resize(numHits);
+	for (size_t h = 0; h < numHits; h++) { s.byPos[h].key = ordered[h].seqPos; s.byPos[h].idx = (uint32_t)h; }
+	std::sort(s.byPos.begin(), s.byPos.end(), [](const Scratch::Key32& left, const Scratch::Key32& right) { return left.key < right.key; });
+	byPos.resize(numHits);
+	for (size_t h = 0; h < numHits; h++)
+	{
+		ordered[s.byPos[h].idx].byPosIdx = (uint32_t)h;
+		byPos[h] = ordered[s.byPos[h].idx];
+	}
 }
 
 }

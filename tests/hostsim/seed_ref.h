@@ -4,8 +4,61 @@
 // semantics, here an std::unordered_map).  The product does these lookups on the device
 // (gcgpu_seed); tests/test_seed.py compares the two on reads with N/U characters and homopolymers.
 #pragma once
+#include <tuple>
 #include <unordered_map>
 #include "../../graphchainer_b200/csrc/gc_seeder.h"
+
+namespace gcseed {
+inline int charToInt(char c)
+{
+	switch (c) { case 'a': case 'A': return 0; case 'c': case 'C': return 1; case 'g': case 'G': return 2; case 't': case 'T': return 3; }
+	return -1;
+}
+// iterateKmers (MinimizerSeeder.cpp:60-102): every k-mer of the read, re-emitted when it
+// changed or the last emission is a whole window back
+template <typename F>
+void iterateKmers(const std::string& str, size_t kmerLength, size_t windowSize, F callback)
+{
+	const size_t realWindow = windowSize - kmerLength + 1;
+	if (str.size() < kmerLength) return;
+	const size_t mask = ~(0xFFFFFFFFFFFFFFFFull << (kmerLength * 2));
+	size_t offset = 0;
+	while (true)
+	{
+		while (offset < str.size() && charToInt(str[offset]) < 0) offset++;
+		if (offset + kmerLength > str.size()) return;
+		size_t kmer = 0;
+		bool restart = false;
+		for (size_t i = 0; i < kmerLength; i++)
+		{
+			int v = charToInt(str[offset + i]);
+			if (v < 0) { offset += i; restart = true; break; }
+			kmer <<= 2;
+			kmer |= (size_t)v;
+		}
+		if (restart) continue;
+		callback(offset + kmerLength - 1, kmer);
+		size_t lastKmer = kmer;
+		size_t lastPos = offset + kmerLength - 1;
+		size_t i = kmerLength;
+		for (; offset + i < str.size(); i++)
+		{
+			int v = charToInt(str[offset + i]);
+			if (v < 0) { offset += i; restart = true; break; }
+			kmer <<= 2;
+			kmer &= mask;
+			kmer |= (size_t)v;
+			if (lastKmer != kmer || lastPos <= offset + i - realWindow)
+			{
+				callback(offset + i, kmer);
+				lastKmer = kmer;
+				lastPos = offset + i;
+			}
+		}
+		if (!restart) return;
+	}
+}
+}
 
 struct SeedRefIndex
 {
