@@ -82,8 +82,9 @@ inline void buildLengths(const uint32_t* freq, int n, int maxLen, uint8_t* lens)
 	for (int i = made - 2; i >= 0; i--)
 	{
 		int d = depth[parent[i]] + 1;
-		if (i < m) { if (d > maxLen) { d = maxLen; overflow++; } blCount[d]++; }
-		depth[i] = (uint8_t)(d > 63 ? 63 : d);
+		if (d > maxLen) { d = maxLen; overflow++; } // internal nodes too: the count below is what the repair loop needs to restore the Kraft sum
+		depth[i] = (uint8_t)d;
+		if (i < m) blCount[d]++;
 	}
 	if (overflow > 0)
 	{
