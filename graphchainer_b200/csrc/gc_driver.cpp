@@ -87,7 +87,7 @@ static DriverParams parseArgs(int argc, char** argv)
 		else if (a == "--colinear-split-len") p.pipe.colinearSplitLen = std::stoll(next());
 		else if (a == "--colinear-split-gap") { p.pipe.colinearSplitGap = std::stoll(next()); splitGapGiven = true; }
 		else if (a == "--sampling-step") p.samplingStep = std::stod(next()); // README contract: a double (the reference parses long long)
-		else if (a == "--short-verbose") p.shortVerbose = true;
+		else if (a == "--short-verbose") { p.shortVerbose = true; p.pipe.exactProgressLine = true; }
 		else if (a == "--gc-gpus") p.gpus = std::stoi(next());
 		else if (a == "--gc-gzip-level") p.gzipLevel = std::min(9, std::max(1, std::stoi(next())));
 		else if (a == "--gc-streams") p.streams = std::max(1, std::stoi(next()));
@@ -322,9 +322,16 @@ int main(int argc, char** argv)
 				{
 					std::string short_id;
 					for (char c : batch[r].name) { if (isspace(c)) break; short_id += c; }
-					std::cerr << readCounter << " " << short_id << " len=" << batch[r].sequence.length() << " : chained " << res.chained << " / " << res.anchors << " anchors, actual " << res.pathBp << " bps, score=" << res.clcScore
-						<< " long_edit_distance=" << (res.hasLong ? std::to_string(res.longEditDistance) : std::string("NA")) << (res.usedChain ? " CLC" : " GA") << std::endl;
+					// the reference's line (Aligner.cpp:909-915); its three stage times are per-read wall clocks that a batched pipeline does
+					// not have (printed as 0), and it prints an uninitialised long_edit_distance when the read has no whole-read alignment
+					std::cerr << readCounter << " " << short_id << " len=" << batch[r].sequence.length() << " : "
+						<< "chained " << res.chained << " / " << res.anchors << " anchors, actual " << res.pathBp << " bps, "
+						<< "time 0 0 0  "
+						<< "score=" << res.clcScore
+						<< " long_edit_distance=" << (res.hasLong ? res.longEditDistance : batch[r].sequence.length())
+						<< " one_node_overlaps=" << res.oneNodeOverlapsNow << " / " << res.oneNodeOverlapsAll << std::endl;
 				}
+				if (res.dropped) std::cerr << "Read " << batch[r].name << " alignment failed (assertion!)" << std::endl;
 				if (res.alignments.empty()) continue;
 				statSeedsExtended += res.seedsExtended;
 				statReadsWithAln++;

@@ -59,13 +59,26 @@ struct GcViterbiTables
 	double initialCorrect, initialFalse; // log(0.8), log(0.2)
 };
 
+// Columns of the node a backtrace is walking: only the bit vectors are stored (16 B per column); the value at row 63 of
+// column h follows from the node's horizontal deltas along that row, which the node item holds anyway:
+// scoreEnd(h) = scoreEnd(0) + sum over columns 1..h of (HP - HN)  (getNextSlice updates scoreEnd by exactly hout, BVCommon.h:258-259)
+struct __attribute__((aligned(16))) GcColVV { uint64_t VP, VN; };
+struct GcCols { const GcColVV* c; uint64_t HP, HN; int32_t score0; };
+GC_HD GcWord gc_cols_get(const GcCols& cv, uint32_t h)
+{
+	const uint64_t m = (2ULL << h) - 2; // bits 1..h
+	GcWord w; w.VP = cv.c[h].VP; w.VN = cv.c[h].VN;
+	w.scoreEnd = cv.score0 + gc_popc(cv.HP & m) - gc_popc(cv.HN & m);
+	return w;
+}
+
 // per work item memory, carved from one slab by the host (see gcgpu.cu)
 struct GcK1Workspace
 {
 	GcSliceMeta* slices;   // [numSlices + 1]
 	GcNodeItem* items;     // [itemCap]
 	uint64_t* heap;        // [heapCap]
-	GcWord* cols;          // [64] columns of the node being recomputed (flatten / backtrace)
+	GcColVV* cols;         // [64] columns of the node being recomputed (backtrace)
 	uint32_t itemCap;
 	uint32_t heapCap;
 	// optional (lock-step kernels): node|flag of the first 32 items of the slice being filled and of the previous slice, in
@@ -204,7 +217,7 @@ GC_HD uint32_t gc_col_bases(const GcColumnRun& r, uint32_t pos) { return (uint32
 // FORCE: 1 = every column of the range has its first row forced, 0 = none, 2 = columns up to forceUntil (decided per column:
 // the thread-per-item kernel keeps ONE loop so that the lanes of a warp, whose forced ranges differ, stay in one loop)
 template <int FORCE, bool FLAT = false>
-GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord* cols, uint32_t forceUntil = 0)
+GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcColVV* cols, uint32_t forceUntil = 0)
 {
 	// 16 columns at a time: their bases are one 32-bit word that is shifted down two bits per column (the
 	// per-column "which chunk, which bit pair" arithmetic of the obvious form was a fifth of the loop's instructions)
@@ -218,7 +231,7 @@ GC_HD void gc_columns_range(GcColumnRun& r, uint32_t begin, uint32_t end, GcWord
 		{
 			gc_col_step<FLAT>(r, pos, (int)(bases & 3), FORCE == 1 || (FORCE == 2 && forceUntil >= pos));
 			bases >>= 2;
-			if (cols) cols[pos] = r.ws;
+			if (cols) { cols[pos].VP = r.ws.VP; cols[pos].VN = r.ws.VN; }
 		}
 	}
 }
@@ -284,10 +297,10 @@ GC_HD void gc_cols_finish(GcColumnRun& run, uint32_t len) { if (len > 1) { run.H
 // BVCommon.h:1060-1167).  If `cols` is non-null every column is also stored there
 // (recalcNodeWordslice, BVCommon.h:828-852).
 GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t eq[4], GcWord ws, bool prevExists, int32_t prevStartScore, uint64_t prevHP, uint64_t prevHN,
-	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcWord* cols, uint64_t flatMask = 0)
+	GcWord& endOut, uint64_t& HPout, uint64_t& HNout, int32_t& minScore, uint32_t& minOffset, GcColVV* cols, uint64_t flatMask = 0)
 {
 	uint32_t len = g.nodeLength[node];
-	if (cols) cols[0] = ws;
+	if (cols) { cols[0].VP = ws.VP; cols[0].VN = ws.VN; }
 	GcColumnRun run;
 	uint32_t forceUntil = gc_cols_prepare(g, node, len, eq, ws, prevExists, prevStartScore, prevHP, prevHN, flatMask, run);
 	if (flatMask) gc_columns_range<2, true>(run, 1, len, nullptr, forceUntil);
@@ -308,7 +321,7 @@ GC_HD void gc_node_columns(const GcGraphView& g, uint32_t node, const uint64_t e
 
 // recalcNodeWordslice (BVCommon.h:828-852): all columns of a stored node
 // flatMask != 0: nothing is stored; *flatMin / *flatOffset receive the minimum of the flattened column values and its first column
-GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const uint64_t eq[4], const GcNodeItem* prev, GcWord* cols, uint64_t flatMask = 0, int32_t* flatMin = nullptr, uint32_t* flatOffset = nullptr)
+GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const uint64_t eq[4], const GcNodeItem* prev, GcColVV* cols, uint64_t flatMask = 0, int32_t* flatMin = nullptr, uint32_t* flatOffset = nullptr, int32_t* score0 = nullptr)
 {
 	GcWord ws = gc_item_start(item);
 	bool prevExists = prev != nullptr;
@@ -318,6 +331,7 @@ GC_HD void gc_recalc_node(const GcGraphView& g, const GcNodeItem& item, const ui
 		GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
 		ws = gc_merge(ws, src);
 	}
+	if (score0) *score0 = ws.scoreEnd;
 	GcWord endOut; uint64_t hp, hn; int32_t ms; uint32_t mo;
 	gc_node_columns(g, gc_item_node(item), eq, ws, prevExists, prevStart, prevExists ? prev->HP : ~0ULL, prevExists ? prev->HN : 0ULL, endOut, hp, hn, ms, mo, cols, flatMask);
 	if (flatMin) { *flatMin = ms; *flatOffset = mo; }
@@ -906,7 +920,8 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 	}
 	uint32_t currentNode = 0xFFFFFFFFu;
 	int32_t currentSlice = -1;
-	GcWord* cols = ws.cols;
+	GcColVV* cols = ws.cols;
+	GcCols cv; cv.c = cols; cv.HP = 0; cv.HN = 0; cv.score0 = 0;
 	uint64_t eq[4];
 	uint32_t guard = 0;
 	uint32_t guardMax = (uint32_t)seqLen * 4 + 1024 + traceCap;
@@ -928,7 +943,8 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			const GcNodeItem* me = gc_find_item(g, cur, cm.numItems, currentNode);
 			if (!me) { res.status = GC_INTERNAL; return; }
 			const GcNodeItem* pme = gc_find_item(g, prev, pmeta.numItems, currentNode);
-			gc_recalc_node(g, *me, eq, pme, cols);
+			gc_recalc_node(g, *me, eq, pme, cols, 0, nullptr, nullptr, &cv.score0);
+			cv.HP = me->HP; cv.HN = me->HN;
 			res.columns += g.nodeLength[currentNode];
 		}
 		// inside the node (BVCommon.h:556-597): walk to the node's first column or the slice's first row, then cross below
@@ -942,7 +958,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			uint32_t hori = tw.offset;
 			int32_t vert = tw.seqPos - j;
 			const uint64_t chunk0 = g.nodeSeq[2 * (uint64_t)currentNode], chunk1 = g.nodeSeq[2 * (uint64_t)currentNode + 1];
-			GcWord cur = cols[hori], left = cols[hori - 1];
+			GcWord cur = gc_cols_get(cv, hori), left = gc_cols_get(cv, hori - 1);
 			int32_t scoreHere = gc_value(cur, vert);
 			int32_t leftHere = gc_value(left, vert);
 			while (hori > 0 && vert > 0)
@@ -964,7 +980,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 					else scoreHere = leftHere;
 					hori--;
 					cur = left;
-					if (hori > 0) { left = cols[hori - 1]; leftHere = gc_value(left, vert); }
+					if (hori > 0) { left = gc_cols_get(cv, hori - 1); leftHere = gc_value(left, vert); }
 				}
 				tw.push(currentNode, hori, vert + j, false);
 			}
@@ -990,7 +1006,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			uint32_t off = tw.offset;
 			int32_t sp = tw.seqPos;
 			uint32_t origOff = off;
-			while (off > 0 && gc_value(cols[off - 1], 0) == gc_value(cols[off], 0) - 1) off--;
+			while (off > 0 && gc_value(gc_cols_get(cv, off - 1), 0) == gc_value(gc_cols_get(cv, off), 0) - 1) off--;
 			GcBtPos second;
 			if (off == 0)
 			{
@@ -999,7 +1015,7 @@ GC_HD void gc_k1_backtrace(const GcGraphView& g, const uint8_t* seq, int32_t seq
 			else
 			{
 				bool eqc = gc_char_match(seq[sp], gc_node_base(g, currentNode, off));
-				int32_t scoreHere = gc_value(cols[off], 0);
+				int32_t scoreHere = gc_value(gc_cols_get(cv, off), 0);
 				int32_t scoreDiagonal = pme->startScore;
 				for (uint32_t i = 1; i + 1 <= off; i++)
 				{

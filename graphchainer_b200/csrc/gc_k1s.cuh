@@ -529,7 +529,7 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 // next one, repeated through one-column nodes; stage 2 = ONE column loop for the warp that recomputes the nodes in hand
 // (recalcNodeWordslice, BVCommon.h:828-852; columns in per-lane local memory); stage 3 = ONE cell-walk loop for the warp.
 // `cols` = 64 columns of per-lane scratch.  `last` = index of the last kept slice (>= 1) of a lane with `have`.
-GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq, int32_t seqLen, const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, int32_t last, GcWord* cols, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
+GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq, int32_t seqLen, const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, int32_t last, GcColVV* cols, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
 {
 	GcTraceWriter tw;
 	tw.out = traceOut; tw.cap = traceCap; tw.n = 0; tw.overflow = false; tw.node = 0; tw.offset = 0; tw.seqPos = -1;
@@ -557,6 +557,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 	GcColumnRun run;
 	run.ws.VP = run.ws.VN = 0; run.ws.scoreEnd = 0; run.eq[0] = run.eq[1] = run.eq[2] = run.eq[3] = 0; run.prevHP = run.prevHN = run.HP = run.HN = 0; run.chunk0 = run.chunk1 = 0; run.minScore = 0; run.minOffset = 0; run.flatMask = 0;
 	uint64_t chunk0 = 0, chunk1 = 0;
+	GcCols cv; cv.c = cols; cv.HP = 0; cv.HN = 0; cv.score0 = 0;
 	while (true)
 	{
 		// ================= stage 1: one step of every lane that is neither waiting for its columns nor walking =================
@@ -587,7 +588,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 							uint32_t off = tw.offset;
 							int32_t sp = tw.seqPos;
 							uint32_t origOff = off;
-							while (off > 0 && gc_value(cols[off - 1], 0) == gc_value(cols[off], 0) - 1) off--;
+							while (off > 0 && gc_value(gc_cols_get(cv, off - 1), 0) == gc_value(gc_cols_get(cv, off), 0) - 1) off--;
 							GcBtPos second;
 							if (off == 0)
 							{
@@ -597,7 +598,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 							{
 								int base = (int)(((off < 32 ? chunk0 : chunk1) >> ((off & 31) * 2)) & 3);
 								bool eqc = gc_char_match(seq[sp], base);
-								int32_t scoreHere = gc_value(cols[off], 0);
+								int32_t scoreHere = gc_value(gc_cols_get(cv, off), 0);
 								// previous slice's last row: startScore + horizontal deltas of columns 1..off-1 (diagonal) and 1..off (up)
 								uint64_t below = (1ULL << off) - 2; // bits 1..off-1
 								int32_t scoreDiagonal = pme->startScore + gc_popc(pme->HP & below) - gc_popc(pme->HN & below);
@@ -728,7 +729,8 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 					GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
 					sw = gc_merge(sw, src);
 				}
-				cols[0] = sw;
+				cols[0].VP = sw.VP; cols[0].VN = sw.VN;
+				cv.HP = me->HP; cv.HN = me->HN; cv.score0 = sw.scoreEnd;
 				chunk0 = rec.seq0; chunk1 = rec.seq1;
 				if (len > 1)
 				{
@@ -745,7 +747,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 			for (uint32_t pos = 1; pos < maxLen; pos++)
 			{
 				if (pos == 1 || (pos & 15u) == 0) bases = gc_col_bases(run, pos);
-				if (needCols && pos < len) { gc_col_step<false>(run, pos, (int)(bases & 3), forceUntil >= pos); cols[pos] = run.ws; }
+				if (needCols && pos < len) { gc_col_step<false>(run, pos, (int)(bases & 3), forceUntil >= pos); cols[pos].VP = run.ws.VP; cols[pos].VN = run.ws.VN; }
 				bases >>= 2;
 			}
 			if (needCols)
@@ -767,7 +769,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 			if (walking)
 			{
 				hori = tw.offset; vert = tw.seqPos - j;
-				cur = cols[hori]; left = cols[hori - 1];
+				cur = gc_cols_get(cv, hori); left = gc_cols_get(cv, hori - 1);
 				scoreHere = gc_value(cur, vert);
 				leftHere = gc_value(left, vert);
 			}
@@ -791,7 +793,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 					else scoreHere = leftHere;
 					hori--;
 					cur = left;
-					if (hori > 0) { left = cols[hori - 1]; leftHere = gc_value(left, vert); }
+					if (hori > 0) { left = gc_cols_get(cv, hori - 1); leftHere = gc_value(left, vert); }
 				}
 				tw.push(currentNode, hori, vert + j, false);
 				if (!(hori > 0 && vert > 0)) walking = false;

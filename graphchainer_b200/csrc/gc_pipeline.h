@@ -70,6 +70,7 @@ struct GcReadResult
 	bool broke = false;                // any assertion-class failure (the run reports "Alignment broke with some reads")
 	// the fields of the reference's --short-verbose line (Aligner.cpp:909-915)
 	size_t anchors = 0, chained = 0, pathBp = 0, clcScore = 0, longEditDistance = 0;
+	int oneNodeOverlapsNow = 0, oneNodeOverlapsAll = 0; // the reference's progress-line counters (Aligner.cpp:747,768-771,792,820)
 	bool hasLong = false;
 	size_t seedsFound = 0, seedsExtended = 0;
 };
@@ -82,6 +83,11 @@ struct GcPipelineParams
 	long long colinearSplitLen = 35;
 	long long colinearSplitGap = 35;
 	bool tryAllSeeds = true;
+	// The reference's progress line (--short-verbose, Aligner.cpp:909-915) prints, as "actual N bps", the LENGTH OF THE EDIT PATH of the
+	// chained alignment (`longest` is swapped with the converted trace, :875) -- of every read, also where the whole-read alignment is
+	// written.  The edit path is otherwise only computed where the chain wins (the decision needs the distance only); with this set it
+	// is computed for every read so that the line is the reference's.
+	bool exactProgressLine = false;
 	size_t s1FirstRoundSeeds = 1;   // S1 speculation: seeds extended per read in the first round ...
 	size_t s1LaterRoundSeeds = 8;   // ... in the second round ...
 	size_t s1TailRoundSeeds = 32;  // ... and from the third round on: few reads get that far, their rounds cost one extension latency each whatever the item count
@@ -605,10 +611,11 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 			std::vector<size_t> pos_path;
 			size_t firstNodeOffset = 0, lastNodeOffset = 0;
 			epoch++;
+			int overlapsTmp = 0;
 			auto closeSegment = [&]()
 			{
 				size_t sz = pathTraceSize(pos_path, firstNodeOffset, lastNodeOffset);
-				if (longest[r].size < sz) { longest[r].path = pos_path; longest[r].firstOffset = firstNodeOffset; longest[r].lastOffset = lastNodeOffset; longest[r].size = sz; }
+				if (longest[r].size < sz) { longest[r].path = pos_path; longest[r].firstOffset = firstNodeOffset; longest[r].lastOffset = lastNodeOffset; longest[r].size = sz; out[r].oneNodeOverlapsNow = overlapsTmp; }
 			};
 			for (uint32_t ci = 0; ci < chainLen[r]; ci++)
 			{
@@ -623,6 +630,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				}
 				else
 				{
+					if (apath[0] == pos_path.back()) { overlapsTmp++; out[r].oneNodeOverlapsAll++; }
 					bool gap = apath[0] == pos_path.back() && params.colinearGap != -1 && (long long)anchor.first_offset - (long long)lastNodeOffset > params.colinearGap + 1;
 					std::vector<size_t> path;
 					if (inPath[apath[0]] != epoch && pos_path.back() != apath[0])
@@ -765,7 +773,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		bool haveClc = clcItem[r] >= 0 && longest[r].size != 0 && nwRes[clcItem[r]].status == 0;
 		bool better = haveClc && (longAlns[r].empty() || res.longEditDistance > res.clcScore);
 		res.usedChain = better;
-		if (better)
+		if (better || (params.exactProgressLine && haveClc))
 		{
 			gcgpu_nw_item it = nwItems[clcItem[r]];
 			it.want_path = 2; it.k_hint = nwRes[clcItem[r]].distance; // the distance is known: only the edit path is computed
@@ -795,6 +803,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	for (size_t k = 0; k < pathRead.size(); k++)
 	{
 		size_t r = pathRead[k];
+		if (params.exactProgressLine) out[r].pathBp = pathRes[k].status == 0 ? pathRes[k].ops_len : 0; // longest.swap(trace) / longest.clear() (Aligner.cpp:846-875)
+		if (!out[r].usedChain) continue; // edit path computed for the progress line only
 		if (pathRes[k].status != 0 || pathRes[k].ops_len == 0) { out[r].usedChain = false; continue; }
 		const std::string& sequence = reads[r].sequence;
 		const std::vector<gcpipe::MatrixPos> lg = gcpipe::pathToTrace(g, longest[r].path, longest[r].firstOffset, longest[r].lastOffset);

@@ -171,7 +171,7 @@ __device__ __forceinline__ GcK1Desc gc_k1_short_desc(const gcgpu_ext_item* __res
 	d.itemCap = lay.itemCap; d.heapCap = lay.heapCap; d.traceCap = lay.traceStride; d.numSlices = lay.numSlices; d.resultIndex = idx;
 	return d;
 }
-__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcWord* cols, GcK1Workspace& ws);
+__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcColVV* cols, GcK1Workspace& ws);
 // forward pass and backtrace are separate launches, as for the long items (instruction footprint, see below)
 __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq,
 	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) gc_k1_bt_kernel(GcGraphView g, const uint
 	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
 	GcK1Result res = results[d.resultIndex];
 	if (res.status != GC_OK) return;
-	GcWord cols[64];
+	GcColVV cols[64];
 	GcK1Workspace ws;
 	gc_k1_workspace(d, arena, cols, ws);
 	gc_k1_backtrace(g, seq + d.seqOff, d.seqLen, ws, lastSlice[t], traceArena + d.traceOff, d.traceCap, res);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128) gc_k1_bt_kernel(GcGraphView g, const uint
 // The walk is split into two launches, forward pass (slices, Viterbi cut) and backtrace: at any time all warps of the
 // GPU run the same half of the code (the whole item is ~7 k instructions; with both halves resident `no_instruction` was
 // 16 % of the stall cycles of the single kernel, profiles/r01h) and each half needs fewer registers.
-__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcWord* cols, GcK1Workspace& ws)
+__device__ __forceinline__ void gc_k1_workspace(const GcK1Desc& d, uint8_t* arena, GcColVV* cols, GcK1Workspace& ws)
 {
 	ws.cols = cols;
 	uint8_t* base = arena + d.wsOff;
@@ -277,7 +277,7 @@ template <int MIN_BLOCKS, int W>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) gc_k1_long_bt_kernel(GcGraphView g, const uint8_t* __restrict__ seq, const gcgpu_ext_item* __restrict__ items,
 	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
 {
-	__shared__ GcWord colsShared[128 / W][64];
+	__shared__ GcColVV colsShared[128 / W][64];
 	uint32_t t = gc_k1_group_setup(g);
 	if (t >= n) return;
 	GcK1Desc d = gc_k1_long_desc(descs, items, t);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(GC_K1S_THREADS, 1) gc_k1s_backtrace_kernel(GcG
 	const bool have = t < n && res.status == GC_OK;
 	GcK1SWorkspace ws;
 	gc_k1s_workspace(d, arena, nullptr, ws);
-	GcWord cols[64];
+	GcColVV cols[64];
 	gc_k1s_backtrace(g, have, seq + d.seqOff, d.seqLen, planes, d.seqOff, ws, have ? lastSlice[t] : 0, cols, traceArena + d.traceOff, d.traceCap, res);
 	if (have) results[d.resultIndex] = res;
 }
@@ -1422,6 +1422,11 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			return setError(GCGPU_ERR_ARG, "gcgpu_nw: item " + std::to_string(i) + " out of range");
 	}
 	float ms = 0;
+	// GCGPU_K3_FORCE=thread | dfs: run every alignment through a FALLBACK form (the thread-per-alignment kernels that take over
+	// when a band outgrows the warp kernels' register budget; the depth-first warp kernel that takes over from the level-parallel
+	// edit-path kernels) -- how the parity tests reach those kernels
+	const char* k3Force = getenv("GCGPU_K3_FORCE");
+	const bool forceThread = k3Force && !strcmp(k3Force, "thread"), forceDfs = k3Force && !strcmp(k3Force, "dfs");
 	if (seqs)
 	{
 		CUDA_TRY(ctx->nwSeqBuf.ensure(seq_bytes + 16));
@@ -1494,6 +1499,14 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		descs.insert(descs.end(), narrow.begin(), narrow.end());
 	}
 	CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, descs.data(), (size_t)n * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
+	if (forceThread)
+	{
+		gc_k3_distance_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, n, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		ctx->launches++;
+		nWide = 0;
+	}
+	else
+	{
 	if (nWide)
 	{
 		CUDA_TRY(cudaEventRecord(ctx->evFork, ctx->stream));
@@ -1508,6 +1521,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		ctx->launches++;
 	}
 	if (nWide) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+	}
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	CUDA_TRY(gcCopy(ctx, hout.data(), ctx->resBuf.p, (size_t)n * sizeof(GcK3Out), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1566,7 +1580,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		}
 		uint32_t m = (uint32_t)pd.size();
 		CUDA_TRY(ctx->traceArena.ensure(opsTotal + 16));
-		static const bool levelForm = !(getenv("GCGPU_K3_PATH_LEVELS") && atoi(getenv("GCGPU_K3_PATH_LEVELS")) == 0);
+		const bool levelForm = !forceThread && !forceDfs;
 		std::vector<GcK3Desc> dfs; // alignments for the depth-first kernel: all of them, or the ones the level form gave up on
 		if (levelForm)
 		{
@@ -1626,7 +1640,8 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 			for (const GcK3Desc& d : pd) if (hout[d.resultIndex].pad == 1) { GcK3Desc e = d; e.wsOff = 0; dfs.push_back(e); }
 		}
 		else dfs = pd;
-		if (!dfs.empty())
+		if (forceThread) for (const GcK3Desc& d : dfs) hout[d.resultIndex].pad = 1; // straight to the thread form below
+		if (!dfs.empty() && !forceThread)
 		{
 		m = (uint32_t)dfs.size();
 		for (const GcK3Desc& d : dfs) { hout[d.resultIndex].pad = 0; hout[d.resultIndex].opsLen = 0; }

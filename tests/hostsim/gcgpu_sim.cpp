@@ -101,7 +101,7 @@ static bool simK1(gcgpu_ctx* ctx, const gcgpu_ext_item* items, uint32_t n, gcgpu
 			std::vector<GcSliceMeta> slices(numSlices + 2);
 			std::vector<GcNodeItem> nodeItems(itemCap);
 			std::vector<uint64_t> heap(heapCap);
-			GcWord colsBuf[64];
+			GcColVV colsBuf[64];
 			GcK1Workspace ws { slices.data(), nodeItems.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { ctx->bandwidth };
 			if (seqLen >= 96)
@@ -322,6 +322,18 @@ static int simExtend(gcgpu_ctx* ctx, int set, int append, int32_t fragLen, const
 	}
 	std::vector<gcgpu_ext_result> res(2 * (size_t)n);
 	simK1(ctx, items.data(), 2 * n, res.data(), S.traces);
+	// test hook (this file is the TEST DOUBLE): GCGPU_SIM_FAIL=s1:<read> or s2:<read>:<position> turns the forward extension
+	// of that read's whole-read seeds / of its fragments starting at or after <position> into "a state the reference asserts on" (GCGPU_ITEM_INTERNAL)
+	if (const char* inj = getenv("GCGPU_SIM_FAIL"))
+	{
+		unsigned rd = 0; int fs = -1;
+		bool s1 = sscanf(inj, "s1:%u", &rd) == 1, s2 = !s1 && sscanf(inj, "s2:%u:%d", &rd, &fs) == 2;
+		for (uint32_t i = 0; i < n && (s1 || s2); i++)
+		{
+			const GcSeedCell& c = ctx->cells[exts[i].cell];
+			if (c.read == rd && ((s1 && exts[i].frag_start < 0) || (s2 && exts[i].frag_start >= fs))) res[2 * (size_t)i + 1].status = GCGPU_ITEM_INTERNAL;
+		}
+	}
 	uint64_t cols = 0;
 	S.pairs.resize(first + n);
 	for (uint32_t i = 0; i < n; i++)

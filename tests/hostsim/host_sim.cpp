@@ -436,7 +436,7 @@ int main(int argc, char** argv)
 			std::vector<GcNodeItem> items(itemCap);
 			std::vector<uint64_t> heap(heapCap);
 			trace.assign(2 * (size_t)seqLen + 256, 0);
-			GcWord colsBuf[64];
+			GcColVV colsBuf[64];
 			GcK1Workspace ws { slices.data(), items.data(), heap.data(), colsBuf, itemCap, heapCap };
 			GcK1Params prm { 10 };
 			if (mode == "k1s")

@@ -93,3 +93,18 @@ def test_k2_k3_gpu_match_reference_on_high_width_overlapping_fragments(tmp_path)
     nc, bc, nn, bn = replay_k2_k3_on_gpu(idx, st)
     assert nc == 30 and bc == 0
     assert nn >= 30 and bn == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("force", ["thread", "dfs"])
+def test_k3_fallback_kernels_match_golden(golden_files, force):
+    """The K3 fallback forms -- thread-per-alignment distance and edit-path kernels (bands beyond the warp kernels' register
+    budget) and the depth-first warp edit-path kernel (alignments the level-parallel form gives up on) -- forced for every
+    alignment through GCGPU_K3_FORCE: same distances and operation strings as the reference."""
+    os.environ["GCGPU_K3_FORCE"] = force
+    try:
+        for name, (idx, st) in golden_files.items():
+            nc, bc, nn, bn = replay_k2_k3_on_gpu(idx, st)
+            assert nn > 0 and bn == 0, f"{name} ({force}): {bn}/{nn} NW alignments differ from the reference"
+    finally:
+        del os.environ["GCGPU_K3_FORCE"]
