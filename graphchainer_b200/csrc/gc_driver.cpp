@@ -28,7 +28,8 @@ struct DriverParams
 {
 	std::string graphFile, indexFile, saveIndexFile;
 	std::vector<std::string> readFiles;
-	std::string outGam, outJson;
+	std::string outGam, outJson, outGaf;
+	bool cigarMatchMismatchMerge = false;
 	size_t threads = 1;
 	int gpus = 1;
 	int streams = 6;
@@ -49,7 +50,8 @@ static void usage()
 		"Mandatory parameters:\n"
 		"  -g [ --graph ] arg            input graph (.gfa), or a prebuilt index with --gc-index\n"
 		"  -f [ --reads ] arg            input reads (fasta or fastq, uncompressed or gzipped)\n"
-		"  -a [ --alignments-out ] arg   output alignment file (.gam/.json)\n"
+		"  -a [ --alignments-out ] arg   output alignment file (.gaf/.gam/.json)\n"
+		"  --cigar-match-mismatch        use M for matches and mismatches in the GAF cigar instead of = and X\n"
 		"Colinear chaining parameters:\n"
 		"  --sampling-step arg           Sampling step factor (default 1)\n"
 		"  --colinear-split-len arg      fragment length [default 35]\n"
@@ -88,6 +90,7 @@ static DriverParams parseArgs(int argc, char** argv)
 		else if (a == "--colinear-split-gap") { p.pipe.colinearSplitGap = std::stoll(next()); splitGapGiven = true; }
 		else if (a == "--sampling-step") p.samplingStep = std::stod(next()); // README contract: a double (the reference parses long long)
 		else if (a == "--short-verbose") { p.shortVerbose = true; p.pipe.exactProgressLine = true; }
+		else if (a == "--cigar-match-mismatch") p.cigarMatchMismatchMerge = true;
 		else if (a == "--gc-gpus") p.gpus = std::stoi(next());
 		else if (a == "--gc-gzip-level") p.gzipLevel = std::min(9, std::max(1, std::stoi(next())));
 		else if (a == "--gc-streams") p.streams = std::max(1, std::stoi(next()));
@@ -113,7 +116,8 @@ static DriverParams parseArgs(int argc, char** argv)
 	{
 		if (file.size() >= 4 && file.substr(file.size() - 4) == ".gam") p.outGam = file;
 		else if (file.size() >= 5 && file.substr(file.size() - 5) == ".json") p.outJson = file;
-		else { std::cerr << "unknown output alignment format (" << file << "), must be either .gam or .json" << std::endl; paramError = true; }
+		else if (file.size() >= 4 && file.substr(file.size() - 4) == ".gaf") p.outGaf = file;
+		else { std::cerr << "unknown output alignment format (" << file << "), must be either .gaf, .gam or .json" << std::endl; paramError = true; }
 	}
 	if (p.threads < 1) { std::cerr << "number of threads must be >= 1" << std::endl; paramError = true; }
 	if (p.bandwidth < 1) { std::cerr << "default bandwidth must be >= 1" << std::endl; paramError = true; }
@@ -223,6 +227,7 @@ int main(int argc, char** argv)
 	std::cout << "Initial bandwidth " << params.bandwidth << std::endl;
 	if (params.outGam != "") std::cout << "write alignments to " << params.outGam << std::endl;
 	if (params.outJson != "") std::cout << "write alignments to " << params.outJson << std::endl;
+	if (params.outGaf != "") std::cout << "write alignments to " << params.outGaf << std::endl;
 
 	// ---- one libgcgpu context (graph replica) per GPU
 	gcgpu_graph gg; memset(&gg, 0, sizeof(gg));
@@ -249,6 +254,8 @@ int main(int argc, char** argv)
 	std::ofstream gamOut, jsonOut;
 	if (params.outGam != "") gamOut.open(params.outGam, std::ios::binary);
 	if (params.outJson != "") jsonOut.open(params.outJson);
+	std::ofstream gafOut;
+	if (params.outGaf != "") gafOut.open(params.outGaf);
 	std::mutex outMutex, inMutex;
 	bool wroteAny = false;
 	size_t statReads = 0, statBp = 0, statSeedsFound = 0, statSeedsExtended = 0, statReadsWithSeed = 0, statBpWithSeed = 0, statReadsWithAln = 0, statAlns = 0, statBpAln = 0, statFull = 0, statBpFull = 0;
@@ -294,7 +301,7 @@ int main(int argc, char** argv)
 		{
 			// length-balanced: longest reads first inside a batch (the kernels sort their work items the same way)
 			pipeline.alignBatch(batch, results);
-			std::vector<std::string> gamRecords(batch.size()), jsonRecords(batch.size());
+			std::vector<std::string> gamRecords(batch.size()), jsonRecords(batch.size()), gafRecords(batch.size());
 			auto tGam0 = std::chrono::steady_clock::now();
 			#pragma omp parallel
 			{
@@ -306,6 +313,8 @@ int main(int argc, char** argv)
 					if (params.outGam != "") gamRecords[r] = gcout::gamRecordDirect(graph, batch[r].name, batch[r].sequence, results[r].alignments, params.gzipLevel, enc);
 					if (params.outJson != "")
 						for (const GcAlnItem& item : results[r].alignments) { jsonRecords[r] += gcout::jsonLine(gcout::toAlignment(graph, batch[r].name, batch[r].sequence, item)); jsonRecords[r] += '\n'; }
+					if (params.outGaf != "")
+						for (const GcAlnItem& item : results[r].alignments) { gafRecords[r] += gcout::gafLine(graph, batch[r].name, batch[r].sequence, item, params.cigarMatchMismatchMerge); gafRecords[r] += '\n'; }
 				}
 			}
 			if (getenv("GC_TRACE")) fprintf(stderr, "[gc] phase gam        %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tGam0).count());
@@ -344,6 +353,7 @@ int main(int argc, char** argv)
 				}
 				if (params.outGam != "") { gamOut.write(gamRecords[r].data(), gamRecords[r].size()); wroteAny = true; }
 				if (params.outJson != "") jsonOut << jsonRecords[r];
+				if (params.outGaf != "") gafOut << gafRecords[r];
 			}
 			total.k1Items += pipeline.stats.k1Items; total.k1Columns += pipeline.stats.k1Columns; total.k1Ms += pipeline.stats.k1Ms; total.k1Launches += pipeline.stats.k1Launches;
 			total.s0Ms += pipeline.stats.s0Ms; total.k2Ms += pipeline.stats.k2Ms; total.k2Anchors += pipeline.stats.k2Anchors; total.k3Ms += pipeline.stats.k3Ms; total.k3Items += pipeline.stats.k3Items; total.k3Blocks += pipeline.stats.k3Blocks;

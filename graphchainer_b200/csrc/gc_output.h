@@ -250,6 +250,67 @@ inline std::string gamRecordDirect(const GcHostGraph& g, const std::string& seq_
 	return gzipMemberLevel(raw, level);
 }
 
+// ---- GAF line of one alignment (GraphAlignerGAFAlignment::traceToAlignment, src/GraphAlignerGAFAlignment.h:37-205), from the
+// same token stream as the GAM record: a token "mapping" is exactly a node of the GAF path (same inside-the-node rule,
+// :103 vs GraphAlignerVGAlignment.h), the edit runs are the CIGAR once the runs of equal type on both sides of a mapping
+// boundary are joined (the GAF writer does not flush its run at a node change).  Offsets: inside a mapping every
+// match / mismatch / deletion step advances one base of the original node, an insertion none.
+inline std::string gafLine(const GcHostGraph& g, const std::string& seq_id, const std::string& sequence, const GcAlnItem& item, bool cigarMatchMismatchMerge)
+{
+	std::string nodePath, cigar;
+	size_t nodePathLen = 0, nodePathStart = 0;
+	size_t counts[4] = { 0, 0, 0, 0 };          // by GC_EDIT_* type
+	uint32_t runType = 4; size_t runLen = 0;      // CIGAR run in progress (4 = none)
+	auto flushRun = [&]()
+	{
+		if (runLen == 0) return;
+		cigar += std::to_string(runLen);
+		cigar += runType == GC_EDIT_INSERTION ? 'I' : runType == GC_EDIT_DELETION ? 'D' : cigarMatchMismatchMerge ? 'M' : runType == GC_EDIT_MATCH ? '=' : 'X';
+	};
+	TokenReader rd(item);
+	bool first = true;
+	int prevNode = 0; size_t prevLastOffset = 0;
+	while (rd.atMapping())
+	{
+		int digraphNode; size_t offset;
+		rd.mapping(digraphNode, offset);
+		nodePath += (digraphNode % 2) == 1 ? '<' : '>';
+		const std::string& name = g.originalNodeName(digraphNode);
+		nodePath += name.empty() ? std::to_string(digraphNode / 2) : name;
+		size_t size = g.origSize[g.origIndexOfId[digraphNode]];
+		if (first) { nodePathLen += size; nodePathStart = offset; first = false; }
+		else
+		{
+			size_t skippedBefore = g.origSize[g.origIndexOfId[prevNode]] - 1 - prevLastOffset, skippedAfter = offset;
+			nodePathLen += size - (skippedBefore + skippedAfter);
+		}
+		size_t advancing = 0; // steps of this mapping that move along the node
+		while (rd.atEdit())
+		{
+			uint32_t type = rd.t[rd.i] >> 30, len = rd.t[rd.i] & 0x3FFFFFFFu;
+			rd.i++;
+			counts[type] += len;
+			if (type != GC_EDIT_INSERTION) advancing += len;
+			uint32_t cg = (cigarMatchMismatchMerge && type == GC_EDIT_MISMATCH) ? (uint32_t)GC_EDIT_MATCH : type;
+			if (cg != runType) { flushRun(); runType = cg; runLen = 0; }
+			runLen += len;
+		}
+		prevNode = digraphNode;
+		prevLastOffset = offset + advancing - 1;
+	}
+	flushRun();
+	const size_t matches = counts[GC_EDIT_MATCH], all = counts[0] + counts[1] + counts[2] + counts[3];
+	size_t nodePathEnd = nodePathLen - (g.origSize[g.origIndexOfId[prevNode]] - 1 - prevLastOffset);
+	auto dbl = [](double v) { char b[64]; snprintf(b, sizeof(b), "%g", v); return std::string(b); }; // operator<<(double): precision 6, %g
+	std::string line = seq_id + "\t" + std::to_string(sequence.size()) + "\t" + std::to_string(item.alignmentStart) + "\t" + std::to_string(item.alignmentEnd) + "\t+\t" + nodePath + "\t"
+		+ std::to_string(nodePathLen) + "\t" + std::to_string(nodePathStart) + "\t" + std::to_string(nodePathEnd) + "\t" + std::to_string(matches) + "\t" + std::to_string(all) + "\t255";
+	line += "\tNM:i:" + std::to_string(all - matches);
+	line += "\tdv:f:" + dbl(1.0 - ((double)matches / (double)all));
+	line += "\tid:f:" + dbl((double)matches / (double)all);
+	line += "\tcg:Z:" + cigar;
+	return line;
+}
+
 inline std::string jsonEscape(const std::string& s)
 {
 	std::string r = "\"";

@@ -55,8 +55,39 @@ def kernel(paths):
             print()
 
 
+def dominant_json(paths, out_path, what):
+    """profiles/ncu_dominant_launch.json for bench.py's roofline.traffic: dram bytes, duration and pipe utilisation of the given
+    --set full captures (one launch each: forward + backtrace of the dominant K1 launch), summed."""
+    import json
+    total = {"what": what, "captures": [], "dram_bytes_per_launch": 0.0, "time_ms": 0.0}
+    for p in paths:
+        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        def get(name):
+            return float(vals[hdr.index(name)].replace(",", "")) if name in hdr else None
+        def scaled(name):
+            v = get(name)
+            u = units[hdr.index(name)] if name in hdr else ""
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1)
+            return None if v is None else v * mult
+        rec = {"file": p.split("/")[-1], "kernel": vals[hdr.index("Kernel Name")][:80],
+               "time_ms": scaled("gpu__time_duration.sum"), "dram_read_bytes": scaled("dram__bytes_read.sum"), "dram_write_bytes": scaled("dram__bytes_write.sum"),
+               "alu_pipe_pct": get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "warp_inst_per_cycle_per_sm": get("sm__inst_executed.avg.per_cycle_elapsed"),
+               "active_lanes_per_warp_inst": get("smsp__thread_inst_executed_per_inst_executed.ratio"), "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "registers": get("launch__registers_per_thread"), "grid": get("launch__grid_size"), "block": get("launch__block_size")}
+        total["captures"].append(rec)
+        total["dram_bytes_per_launch"] += (rec["dram_read_bytes"] or 0) + (rec["dram_write_bytes"] or 0)
+        total["time_ms"] += rec["time_ms"] or 0
+    with open(out_path, "w") as f:
+        json.dump(total, f, indent=1)
+    print(json.dumps(total))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "dominant":
+        dominant_json(sys.argv[4:], sys.argv[2], sys.argv[3])
     else:
         kernel(sys.argv[2:])

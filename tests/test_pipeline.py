@@ -72,6 +72,33 @@ def test_host_pipeline_json_and_progress_lines_match_reference(driver_sim, golde
     _json_and_progress_parity(driver_sim, golden_files, tmp_path, name)
 
 
+def _gaf_parity(exe, golden_files, tmp_path, name):
+    """GAF output (GraphAlignerGAFAlignment::traceToAlignment, src/GraphAlignerGAFAlignment.h:37-205): every column of every line
+    (path, path length / start / end, matches, block length, NM, dv, id, CIGAR) against the unmodified reference."""
+    idx, _ = golden_files[name]
+    gfa, fa = os.path.join(GOLDEN, name + ".gfa"), os.path.join(GOLDEN, name + ".fa")
+    ref_gaf, out_gaf = str(tmp_path / "ref.gaf"), str(tmp_path / "out.gaf")
+    subprocess.run([REFBIN, "-t", "1", "-g", gfa, "-f", fa, "-a", ref_gaf], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([exe, "--gc-index", idx, "-f", fa, "-a", out_gaf, "-t", "2"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    a, b = sorted(open(out_gaf).read().splitlines()), sorted(open(ref_gaf).read().splitlines())
+    assert len(b) > 0 and a == b, f"{name}: GAF lines differ ({len(a)} vs {len(b)})"
+
+
+@pytest.mark.parametrize("name", ["c1", "tiny"])
+def test_host_pipeline_gaf_matches_reference(driver_sim, golden_files, tmp_path, name):
+    if not os.path.exists(REFBIN):
+        pytest.skip("oracle/_ref/GraphChainer_ref not built")
+    _gaf_parity(driver_sim, golden_files, tmp_path, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1", "tiny"])
+def test_gpu_pipeline_gaf_matches_reference(golden_files, tmp_path, name):
+    if not os.path.exists(REFBIN):
+        pytest.skip("oracle/_ref/GraphChainer_ref not built")
+    _gaf_parity(DRIVER, golden_files, tmp_path, name)
+
+
 def test_read_that_hits_an_assertion_class_state_is_dropped(driver_sim, golden_files, tmp_path):
     """A work item that reaches a state the reference guards with assert() (GCGPU_ITEM_INTERNAL) in the whole-read pass drops that
     read only, as the reference's catch block does (Aligner.cpp:585-592: alignments cleared, cont = true, every fragment skipped):
