@@ -81,12 +81,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def time_reference(gfa: str, fasta: str, threads: int, keep_gam: str | None = None):
+def time_reference(gfa: str, fasta: str, threads: int, keep_gam: str | None = None, extra=()):
     """Align-phase seconds of the unmodified reference: wall clock between its "Align" and
     "Alignment finished" lines (src/Aligner.cpp:1258,1296); index build excluded.  keep_gam: where to leave its GAM output."""
     with tempfile.TemporaryDirectory() as d:
         out = keep_gam or os.path.join(d, "ref.gam")
-        p = subprocess.Popen([REFBIN, "-t", str(threads), "-g", gfa, "-f", fasta, "-a", out], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        p = subprocess.Popen([REFBIN, "-t", str(threads), "-g", gfa, "-f", fasta, "-a", out, *extra], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         t0 = t1 = None
         for line in p.stdout:
             if line.startswith("Align") and not line.startswith("Alignment") and t0 is None:
@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=6, help="read batches in flight per GPU in the e2e measurement")
     ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
+    ap.add_argument("--value-batch-bp", type=int, default=0, help="read bases per GPU batch in the kernel-time (value) measurement (0 = the whole read set in one batch)")
     ap.add_argument("--threads-per-stream", type=int, default=0, help="host threads per in-flight batch (0 = host threads / streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -152,11 +153,13 @@ def main():
     # c3's full read set (100 k x 15 kb = 1.5 Gbp per GPU) is a 15-s step: the default is a stated tenth of it on the full 51 Mbp graph
     n_reads = args.reads or (cfg["n_reads"] if args.workload != "c3" else cfg["n_reads"] // 10)
     host_cores = os.cpu_count() or 1
+    split_gap = int(cfg.get("split_gap", 35))
+    ref_extra = ("--colinear-split-gap", str(split_gap)) if split_gap != 35 else ()
     read_len = cfg["read_len"] if isinstance(cfg["read_len"], int) else (cfg["read_len"][0] + cfg["read_len"][1]) // 2
     args.cpu_sample = max(1, min(args.cpu_sample, n_reads, int(args.cpu_sample * 10_000 / read_len)))  # ~40 Mbp of reads per reference step
     config = {"workload": f"{args.workload}: synthetic {cfg['graph_len'] / 1e6:g} Mbp acyclic SNP/indel graph + {n_reads} simulated reads/GPU, length {cfg['read_len']}, {cfg['error'] * 100:g}% error (5% with a novel 400-bp insertion)" + ("" if n_reads == cfg["n_reads"] else f" [{n_reads} of the configuration's {cfg['n_reads']} reads]"),
-              "reads_per_gpu": n_reads, "graph_bp": cfg["graph_len"], "l2": "inputs larger than L2: slice/trace workspaces of a step exceed 126 MB",
-              "value_timing": "sum of CUDA-event durations of the step's kernels", "e2e_timing": "wall time of gcalign_align() on host buffers incl. all copies and host stages"}
+              "reads_per_gpu": n_reads, "graph_bp": cfg["graph_len"], "colinear_split_gap": split_gap, "l2": "inputs larger than L2: slice/trace workspaces of a step exceed 126 MB",
+              "value_timing": "sum of CUDA-event durations of the step's kernels, the read set as one GPU batch, one batch in flight", "e2e_timing": "wall time of gcalign_align() on host buffers incl. all copies and host stages"}
     tmp = tempfile.mkdtemp(prefix="gcbench_")
 
     # ------------------------------------------------------------------ reference arm
@@ -173,10 +176,10 @@ def main():
         if args.warmup > 0:
             warm = os.path.join(tmp, "warm.fa")
             write_repeated_fasta(warm, reads, args.warmup)
-            time_reference(gfa, warm, host_cores)
+            time_reference(gfa, warm, host_cores, extra=ref_extra)
         fa = os.path.join(tmp, "sample.fa")
         bp_total = write_repeated_fasta(fa, reads, args.steps)
-        t_all = time_reference(gfa, fa, host_cores)
+        t_all = time_reference(gfa, fa, host_cores, extra=ref_extra)
         bp = bp_total // args.steps
         t = t_all / args.steps
         v = bp / t
@@ -201,7 +204,7 @@ def main():
     batch = align.ReadBatch([r[0] for r in reads], [r[1] for r in reads])
     threads = max(1, host_cores // world)
     t_index = time.perf_counter()
-    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=args.streams, batch_bp=args.batch_bp, threads_per_stream=args.threads_per_stream)
+    aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=split_gap, streams=args.streams, batch_bp=args.batch_bp, threads_per_stream=args.threads_per_stream)
     index_s = time.perf_counter() - t_index
 
     def barrier():
@@ -237,7 +240,10 @@ def main():
     aligner.close()
     # ---- kernel time: the same steps with ONE batch in flight, so that every CUDA-event pair brackets a
     # kernel that has the GPU to itself (with several streams the event durations of overlapping kernels add up)
-    aligner1 = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=35, streams=1, batch_bp=args.batch_bp)
+    # ... and the whole read set as ONE batch: the kernels then see the launch sizes they are built for (a 16 Mbp batch gives the
+    # lane-per-item K1 kernels a few hundred warps; its kernel-time sum measures launch latency, not throughput)
+    value_batch_bp = args.value_batch_bp or (batch.total_bp + 1)
+    aligner1 = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=split_gap, streams=1, batch_bp=value_batch_bp)
     for _ in range(args.warmup):
         aligner1.align(batch, gam=False)
     barrier()
@@ -315,7 +321,7 @@ def main():
         fa = os.path.join(tmp, "sample.fa")
         bp = synth.write_fasta(fa, reads[:sample])
         ref_gam = os.path.join(tmp, "ref_sample.gam")
-        secs = time_reference(gfa, fa, host_cores, keep_gam=ref_gam)
+        secs = time_reference(gfa, fa, host_cores, keep_gam=ref_gam, extra=ref_extra)
         line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": host_cores, "kind": "reference",
                                 "sample": f"first {sample} reads of rank 0's set ({bp} bp), unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only, {secs:.2f} s"}
         # parity gate: the timed workload's own reads, reference output vs the GAM records the timed e2e step produced

@@ -108,7 +108,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	if (gam_used) *gam_used = 0;
 	if (stats) memset(stats, 0, sizeof(*stats));
 	int hostThreads = h->opts.host_threads > 0 ? h->opts.host_threads : omp_get_max_threads();
-	uint64_t batchBp = h->opts.batch_bp ? h->opts.batch_bp : (8u << 20);
+	uint64_t batchBp = h->opts.batch_bp ? h->opts.batch_bp : (16u << 20); // the lane-per-item K1 kernels want thousands of whole-read extensions per launch (profiles/r03f: 8 -> 16 Mbp batches, e2e +17 %)
 	// batches of ~batch_bp read bases, handed to the workers in order
 	std::vector<std::pair<uint32_t, uint32_t>> batches;
 	for (uint32_t first = 0; first < num_reads; )

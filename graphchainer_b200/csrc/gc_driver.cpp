@@ -38,7 +38,7 @@ struct DriverParams
 	int bandwidth = 10;
 	bool shortVerbose = false;
 	bool quiet = false;
-	size_t batchBp = 8u << 20;
+	size_t batchBp = 16u << 20;
 	size_t maxReads = (size_t)-1;
 	GcPipelineParams pipe;
 	double samplingStep = 1;

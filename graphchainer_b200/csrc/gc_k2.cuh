@@ -35,6 +35,7 @@ struct GcMpcView
 	const uint32_t* backStart;  // [N+1]
 	const uint32_t* backNode;   // component-local node index
 	const uint32_t* backK;
+	const uint32_t* pathBase;   // [C+1] first global path id of every component (device only: derived at gcgpu_create)
 };
 
 struct GcAnchor

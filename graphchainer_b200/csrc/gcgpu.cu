@@ -2,6 +2,7 @@
 // Interface and the reference seams each entry point replaces: include/gcgpu.h.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -79,8 +80,10 @@ struct gcgpu_ctx
 	// MPC index (K2)
 	uint32_t* d_compMap = nullptr; uint32_t* d_compIdx = nullptr; uint32_t* d_compStart = nullptr; uint32_t* d_topoIds = nullptr;
 	uint32_t* d_pathsStart = nullptr; uint32_t* d_pathsK = nullptr; uint32_t* d_backStart = nullptr; uint32_t* d_backNode = nullptr; uint32_t* d_backK = nullptr;
+	uint32_t* d_pathBase = nullptr; uint32_t totalPaths = 0, maxCompNodes = 0; // first global path id of every component (per-path structures of K2)
 	bool haveMpc = false;
 	GcMpcView mpc;
+	DevBuf k2Work, k2Sort;
 	DevBuf seqBuf, nwSeqBuf, descBuf, resBuf, arena, traceArena, compact, copyDesc, itemsBuf;
 	DevBuf planes; // bit planes of seqBuf (gc_planes_kernel): the Eq masks of any 64 rows in eight loads
 	uint64_t h2dBytes = 0, d2hBytes = 0; // bytes this ctx copied across PCIe (gcgpu_transfer_bytes)
@@ -403,8 +406,8 @@ extern "C" void gcgpu_destroy(gcgpu_ctx* ctx)
 	cudaFree(ctx->d_componentNumber); cudaFree(ctx->d_linearizable); cudaFree(ctx->d_vt); cudaFree(ctx->d_nodeRec); cudaFree(ctx->d_outKey);
 	cudaFree(ctx->d_compMap); cudaFree(ctx->d_compIdx); cudaFree(ctx->d_compStart); cudaFree(ctx->d_topoIds);
 	cudaFree(ctx->d_mzSlots); ctx->seedBuf.release(); ctx->seedMatches.release();
-	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK);
-	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release(); ctx->itemsBuf.release(); ctx->planes.release();
+	cudaFree(ctx->d_pathsStart); cudaFree(ctx->d_pathsK); cudaFree(ctx->d_backStart); cudaFree(ctx->d_backNode); cudaFree(ctx->d_backK); cudaFree(ctx->d_pathBase);
+	ctx->seqBuf.release(); ctx->nwSeqBuf.release(); ctx->descBuf.release(); ctx->resBuf.release(); ctx->arena.release(); ctx->traceArena.release(); ctx->compact.release(); ctx->copyDesc.release(); ctx->itemsBuf.release(); ctx->planes.release(); ctx->k2Work.release(); ctx->k2Sort.release();
 	residentDestroy(ctx);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -472,6 +475,20 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 		chk(uploadArray(graph->back_start, (size_t)N + 1, &ctx->d_backStart));
 		chk(uploadArray(graph->back_node, graph->back_start[N], &ctx->d_backNode));
 		chk(uploadArray(graph->back_k, graph->back_start[N], &ctx->d_backK));
+		{
+			// global path ids: component c owns [pathBase[c], pathBase[c + 1]) (its MPC width = 1 + the largest path id on its nodes)
+			std::vector<uint32_t> pathBase((size_t)graph->num_components + 1, 0);
+			for (uint32_t c = 0; c < graph->num_components; c++)
+			{
+				uint32_t width = 0;
+				for (uint32_t gidx = graph->comp_start[c]; gidx < graph->comp_start[c + 1]; gidx++)
+					for (uint32_t q = graph->paths_start[gidx]; q < graph->paths_start[gidx + 1]; q++) if (graph->paths_k[q] + 1 > width) width = graph->paths_k[q] + 1;
+				pathBase[c + 1] = pathBase[c] + width;
+				if (graph->comp_start[c + 1] - graph->comp_start[c] > ctx->maxCompNodes) ctx->maxCompNodes = graph->comp_start[c + 1] - graph->comp_start[c];
+			}
+			ctx->totalPaths = pathBase[graph->num_components];
+			chk(uploadArray(pathBase.data(), pathBase.size(), &ctx->d_pathBase));
+		}
 		ctx->haveMpc = true;
 	}
 	if (err != cudaSuccess)
@@ -486,7 +503,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->view.nodeRec = ctx->d_nodeRec; ctx->view.outKey = ctx->d_outKey;
 	ctx->view.componentNumber = ctx->d_componentNumber; ctx->view.linearizable = ctx->d_linearizable; ctx->view.coopLane = -1; ctx->view.coopWidth = 32; ctx->view.coopMask = 0xFFFFFFFFu; ctx->view.coopShift = 0;
 	ctx->mpc.compMap = ctx->d_compMap; ctx->mpc.compIdx = ctx->d_compIdx; ctx->mpc.compStart = ctx->d_compStart; ctx->mpc.topoIds = ctx->d_topoIds;
-	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK;
+	ctx->mpc.pathsStart = ctx->d_pathsStart; ctx->mpc.pathsK = ctx->d_pathsK; ctx->mpc.backStart = ctx->d_backStart; ctx->mpc.backNode = ctx->d_backNode; ctx->mpc.backK = ctx->d_backK; ctx->mpc.pathBase = ctx->d_pathBase;
 	int rrc = residentCreate(ctx, graph);
 	if (rrc != GCGPU_OK) { gcgpu_destroy(ctx); return rrc; }
 	*out = ctx;
@@ -1725,11 +1742,89 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	return GCGPU_OK;
 }
 
-// ------------------------------------------------------------------ K2 kernel
-// One block = one read.  Anchors are evaluated by increasing y; for each anchor the threads
-// stride over its candidate predecessors and a block-wide max picks (value, index).
+// ------------------------------------------------------------------ K2 kernels
+// One block = one read.  Two forms of the same closed form (gc_k2.cuh):
+//
+// (1) sweep form (the default).  The reference keeps, per MPC path k, search trees over the anchors that END on path k, and asks
+//     them, for every backward link (v, k) of an anchor's start node, for the best anchor ending on k at or before v
+//     (AlignmentGraph.cpp:1777-1846).  Here every (anchor, path through its end node) pair of the whole batch becomes one entry
+//     keyed (read, global path id, topological index of the end node); ONE device radix sort (CUB) puts the entries of a
+//     (read, path) next to each other in path order, and a Fenwick max-tree lies over each such segment.  The block sweeps the
+//     read's anchors by increasing read end y: an anchor is inserted into the trees of its paths as soon as it can no longer
+//     overlap the anchors being evaluated (y_i <= x_j - 1: fragments have one length, so x_j grows with the sweep); an anchor
+//     being evaluated asks, per link (v, k), for the prefix maximum of segment (read, k) up to topo(v) -- two binary searches
+//     and O(log n) tree steps -- and, per path through its own start node, for the prefix up to that node itself (anchors that
+//     end on the start node).  The few anchors still overlapping it (x_j <= y_i < y_j: the I-type term) are tested directly.
+//     Work per read: O(N (K log N + overlap)) instead of the O(N^2 K^2) of form (2).
+// (2) pairwise form: every earlier anchor is tested against every later one.  Used for reads whose anchors do not all have the
+//     same length (a caller of gcgpu_chain may pass anything) and when the key fields would overflow; GCGPU_K2_FORCE=pairwise.
 #define GC_K2_THREADS 128
-__global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m, const GcAnchor* __restrict__ anchors, const uint64_t* __restrict__ readOffsets, uint32_t numReads,
+#define GC_K2_READ_BITS 18
+#define GC_K2_PATH_BITS 18
+#define GC_K2_TOPO_BITS 28
+__device__ __forceinline__ uint64_t gc_k2_entry_key(uint32_t read, uint32_t gpath, uint32_t topo) { return ((uint64_t)read << (GC_K2_PATH_BITS + GC_K2_TOPO_BITS)) | ((uint64_t)gpath << GC_K2_TOPO_BITS) | topo; }
+
+struct GcK2Sweep
+{
+	const uint64_t* pairStart;   // [total + 1] entries of anchor a (batch-global index): [pairStart[a], pairStart[a + 1])
+	const uint32_t* posOf;       // [entries] sorted position of entry q
+	const uint64_t* keys;        // [entries] sorted keys
+	const uint32_t* segLo;       // [entries] first / one-past-last sorted position of the segment (read, path) an entry lies in
+	const uint32_t* segHi;
+	long long* tree;             // [entries] Fenwick max-trees over the segments, keys gc_k2_key(score, anchor)
+	uint64_t entries;
+};
+
+__global__ void gc_k2_pair_count_kernel(GcMpcView m, const GcAnchor* __restrict__ a, uint64_t total, uint64_t* __restrict__ cnt)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > total) return;
+	if (i == total) { cnt[i] = 0; return; }
+	uint32_t e = a[i].endNode;
+	uint32_t gidx = m.compStart[m.compMap[e]] + m.compIdx[e];
+	cnt[i] = m.pathsStart[gidx + 1] - m.pathsStart[gidx];
+}
+__global__ void gc_k2_pair_emit_kernel(GcMpcView m, const GcAnchor* __restrict__ a, const uint64_t* __restrict__ readOffsets, uint32_t numReads, uint64_t total, const uint64_t* __restrict__ pairStart,
+	uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	uint32_t lo = 0, hi = numReads; // read of anchor i: last r with readOffsets[r] <= i
+	while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (readOffsets[mid] <= i) lo = mid; else hi = mid; }
+	uint32_t e = a[i].endNode, c = m.compMap[e];
+	uint32_t gidx = m.compStart[c] + m.compIdx[e];
+	uint32_t topo = m.topoIds[gidx];
+	uint64_t q = pairStart[i];
+	for (uint32_t p = m.pathsStart[gidx]; p < m.pathsStart[gidx + 1]; p++, q++) { keys[q] = gc_k2_entry_key(lo, m.pathBase[c] + m.pathsK[p], topo); vals[q] = (uint32_t)q; }
+}
+__global__ void gc_k2_segments_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ sortedQ, uint64_t entries, uint32_t* __restrict__ posOf, uint32_t* __restrict__ segLo, uint32_t* __restrict__ segHi)
+{
+	uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= entries) return;
+	posOf[sortedQ[e]] = (uint32_t)e;
+	const uint64_t seg = keys[e] >> GC_K2_TOPO_BITS;
+	uint64_t lo = 0, hi = e; // first position whose (read, path) equals this one's
+	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if ((keys[mid] >> GC_K2_TOPO_BITS) < seg) lo = mid + 1; else hi = mid; }
+	segLo[e] = (uint32_t)lo;
+	lo = e + 1; hi = entries;
+	while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if ((keys[mid] >> GC_K2_TOPO_BITS) <= seg) lo = mid + 1; else hi = mid; }
+	segHi[e] = (uint32_t)lo;
+}
+
+// block-wide maximum of `best`, returned to every thread
+__device__ __forceinline__ long long gc_k2_block_max(long long best, long long* warpBest)
+{
+	for (int off = 16; off > 0; off >>= 1) { long long o = __shfl_down_sync(0xFFFFFFFFu, best, off); if (o > best) best = o; }
+	__syncthreads(); // the previous round's readers are done with warpBest
+	if ((threadIdx.x & 31) == 0) warpBest[threadIdx.x >> 5] = best;
+	__syncthreads();
+	long long b = warpBest[0];
+	for (int w = 1; w < GC_K2_THREADS / 32; w++) if (warpBest[w] > b) b = warpBest[w];
+	return b;
+}
+
+template <bool SWEEP>
+__global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m, const GcAnchor* __restrict__ anchors, const uint64_t* __restrict__ readOffsets, uint32_t numReads, GcK2Sweep sw,
 	uint32_t* order, int32_t* score, int32_t* pred, uint32_t* chain, uint32_t* chainLen, int64_t* chainScore)
 {
 	uint32_t r = blockIdx.x;
@@ -1741,43 +1836,119 @@ __global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m,
 	int32_t* sc = score + base;
 	int32_t* pr = pred + base;
 	__shared__ long long warpBest[GC_K2_THREADS / 32];
-	__shared__ long long blockBest;
+	__shared__ int sUniform;
 	// rank sort by (y, index)
+	if (threadIdx.x == 0) sUniform = 1;
+	__syncthreads();
 	for (uint32_t j = threadIdx.x; j < n; j += blockDim.x)
 	{
 		uint32_t rank = 0;
 		int32_t yj = a[j].y;
 		for (uint32_t i = 0; i < n; i++) { int32_t yi = a[i].y; rank += (yi < yj || (yi == yj && i < j)) ? 1 : 0; }
 		ord[rank] = j;
+		if (a[j].y - a[j].x != a[0].y - a[0].x) sUniform = 0;
 	}
 	__syncthreads();
-	for (uint32_t oj = 0; oj < n; oj++)
+	if (SWEEP && sUniform && n > 0)
 	{
-		uint32_t j = ord[oj];
-		GcAnchor aj = a[j];
-		uint32_t cj = m.compMap[aj.endNode];
-		long long best = gc_k2_key(aj.y - aj.x + 1, -1);
-		for (uint32_t oi = threadIdx.x; oi < oj; oi += blockDim.x)
+		const int32_t len = a[0].y - a[0].x + 1;
+		// entries of this read in the sorted array
+		uint64_t eLo, eHi;
 		{
-			uint32_t i = ord[oi];
-			GcAnchor ai = a[i];
-			if (ai.y >= aj.y) continue;
-			if (m.compMap[ai.endNode] != cj) continue;
-			long long key = gc_k2_candidate(m, ai, aj, i, sc[i]);
-			if (key > best) best = key;
+			uint64_t lo = 0, hi = sw.entries, want = (uint64_t)r << (GC_K2_PATH_BITS + GC_K2_TOPO_BITS);
+			while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sw.keys[mid] < want) lo = mid + 1; else hi = mid; }
+			eLo = lo; hi = sw.entries; want = (uint64_t)(r + 1) << (GC_K2_PATH_BITS + GC_K2_TOPO_BITS);
+			while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sw.keys[mid] < want) lo = mid + 1; else hi = mid; }
+			eHi = lo;
 		}
-		for (int off = 16; off > 0; off >>= 1) { long long o = __shfl_down_sync(0xFFFFFFFFu, best, off); if (o > best) best = o; }
-		if ((threadIdx.x & 31) == 0) warpBest[threadIdx.x >> 5] = best;
-		__syncthreads();
-		if (threadIdx.x == 0)
+		// prefix maximum of segment (r, gpath) over the entries with topological index <= topo
+		auto query = [&](uint32_t gpath, uint32_t topo) -> long long
 		{
-			long long b = warpBest[0];
-			for (int w = 1; w < GC_K2_THREADS / 32; w++) if (warpBest[w] > b) b = warpBest[w];
-			blockBest = b;
-			sc[j] = (int32_t)(b >> 32);
-			pr[j] = (int32_t)(uint32_t)(b & 0xFFFFFFFFu) - 1;
+			uint64_t lo = eLo, hi = eHi, want = gc_k2_entry_key(r, gpath, 0);
+			while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sw.keys[mid] < want) lo = mid + 1; else hi = mid; }
+			const uint64_t s0 = lo;
+			hi = eHi; want = gc_k2_entry_key(r, gpath, topo);
+			while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sw.keys[mid] <= want) lo = mid + 1; else hi = mid; }
+			long long best = (long long)0x8000000000000000LL;
+			for (uint64_t idx = lo - s0; idx > 0; idx -= idx & (~idx + 1)) { long long v = sw.tree[s0 + idx - 1]; if (v > best) best = v; }
+			return best;
+		};
+		uint32_t ins = 0; // ord[0 .. ins) are in the trees
+		for (uint32_t oj = 0; oj < n; oj++)
+		{
+			const uint32_t j = ord[oj];
+			const GcAnchor aj = a[j];
+			// ---- anchors that can no longer overlap the one being evaluated go into the trees of their paths
+			uint32_t insEnd = ins;
+			while (insEnd < oj && a[ord[insEnd]].y <= aj.x - 1) insEnd++;
+			if (insEnd > ins)
+			{
+				for (uint32_t oi = ins + threadIdx.x; oi < insEnd; oi += blockDim.x)
+				{
+					const uint32_t i = ord[oi];
+					const long long key = gc_k2_key(sc[i], (int32_t)i);
+					for (uint64_t q = sw.pairStart[base + i]; q < sw.pairStart[base + i + 1]; q++)
+					{
+						const uint32_t e = sw.posOf[q], s0 = sw.segLo[e], segLen = sw.segHi[e] - s0;
+						for (uint32_t idx = e - s0 + 1; idx <= segLen; idx += idx & (~idx + 1)) atomicMax(&sw.tree[s0 + idx - 1], key);
+					}
+				}
+				ins = insEnd;
+				__syncthreads();
+			}
+			// ---- candidates: through the links of the start node, on the paths through the start node itself, and the overlapping anchors
+			const uint32_t cs = m.compMap[aj.startNode], cj = m.compMap[aj.endNode];
+			const uint32_t gs = m.compStart[cs] + m.compIdx[aj.startNode];
+			long long best = (long long)0x8000000000000000LL;
+			if (cs == cj)
+			{
+				const uint32_t nLinks = m.backStart[gs + 1] - m.backStart[gs], nOwn = m.pathsStart[gs + 1] - m.pathsStart[gs];
+				for (uint32_t t = threadIdx.x; t < nLinks + nOwn; t += blockDim.x)
+				{
+					long long v;
+					if (t < nLinks) { uint32_t b = m.backStart[gs] + t; v = query(m.pathBase[cs] + m.backK[b], m.topoIds[m.compStart[cs] + m.backNode[b]]); }
+					else v = query(m.pathBase[cs] + m.pathsK[m.pathsStart[gs] + (t - nLinks)], m.topoIds[gs]);
+					if (v > best) best = v;
+				}
+			}
+			if (best != (long long)0x8000000000000000LL) best += (long long)len << 32; // val = len_j + C[i]  (y_i <= x_j - 1)
+			for (uint32_t oi = ins + threadIdx.x; oi < oj; oi += blockDim.x)
+			{
+				const uint32_t i = ord[oi];
+				const GcAnchor ai = a[i];
+				if (ai.y >= aj.y) continue;
+				if (m.compMap[ai.endNode] != cj) continue;
+				long long key = gc_k2_candidate(m, ai, aj, i, sc[i]);
+				if (key > best) best = key;
+			}
+			long long own = gc_k2_key(len, -1);
+			if (own > best) best = own;
+			long long b = gc_k2_block_max(best, warpBest);
+			if (threadIdx.x == 0) { sc[j] = (int32_t)(b >> 32); pr[j] = (int32_t)(uint32_t)(b & 0xFFFFFFFFu) - 1; }
+			__syncthreads();
 		}
-		__syncthreads();
+	}
+	else
+	{
+		for (uint32_t oj = 0; oj < n; oj++)
+		{
+			uint32_t j = ord[oj];
+			GcAnchor aj = a[j];
+			uint32_t cj = m.compMap[aj.endNode];
+			long long best = gc_k2_key(aj.y - aj.x + 1, -1);
+			for (uint32_t oi = threadIdx.x; oi < oj; oi += blockDim.x)
+			{
+				uint32_t i = ord[oi];
+				GcAnchor ai = a[i];
+				if (ai.y >= aj.y) continue;
+				if (m.compMap[ai.endNode] != cj) continue;
+				long long key = gc_k2_candidate(m, ai, aj, i, sc[i]);
+				if (key > best) best = key;
+			}
+			long long b = gc_k2_block_max(best, warpBest);
+			if (threadIdx.x == 0) { sc[j] = (int32_t)(b >> 32); pr[j] = (int32_t)(uint32_t)(b & 0xFFFFFFFFu) - 1; }
+			__syncthreads();
+		}
 	}
 	if (threadIdx.x == 0)
 	{
@@ -1785,6 +1956,57 @@ __global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m,
 		chainLen[r] = gc_k2_select(m, a, n, sc, pr, chain + base, (int64_t*)&bs);
 		chainScore[r] = bs;
 	}
+}
+
+// chaining of `total` anchors of `numReads` reads that sit in device memory (dAnchors, dReadOff[numReads + 1])
+static int k2Run(gcgpu_ctx* ctx, const GcAnchor* dAnchors, const uint64_t* dReadOff, uint32_t numReads, uint64_t total,
+	uint32_t* dOrder, int32_t* dScore, int32_t* dPred, uint32_t* dChain, uint32_t* dChainLen, int64_t* dChainScore)
+{
+	const char* force = getenv("GCGPU_K2_FORCE");
+	bool sweep = !(force && !strcmp(force, "pairwise")) && total > 0 && numReads < (1u << GC_K2_READ_BITS) && ctx->totalPaths < (1u << GC_K2_PATH_BITS) && ctx->maxCompNodes < (1u << GC_K2_TOPO_BITS);
+	GcK2Sweep sw; memset(&sw, 0, sizeof(sw));
+	if (sweep)
+	{
+		// (anchor, path) entries: count, scan, emit, sort, segment bounds
+		size_t offCnt = 0, offStart = alignUp(offCnt + (total + 1) * 8, 128);
+		CUDA_TRY(ctx->k2Work.ensure(offStart + (total + 1) * 8 + 128));
+		uint8_t* W = (uint8_t*)ctx->k2Work.p;
+		uint64_t* dCnt = (uint64_t*)(W + offCnt); uint64_t* dStart = (uint64_t*)(W + offStart);
+		gc_k2_pair_count_kernel<<<(unsigned)((total + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->mpc, dAnchors, total, dCnt);
+		ctx->launches++;
+		size_t scanBytes = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dCnt, dStart, (int)(total + 1), ctx->stream);
+		CUDA_TRY(ctx->copyDesc.ensure(scanBytes + 16));
+		cub::DeviceScan::ExclusiveSum(ctx->copyDesc.p, scanBytes, dCnt, dStart, (int)(total + 1), ctx->stream);
+		ctx->launches++;
+		uint64_t entries = 0;
+		CUDA_TRY(gcCopy(ctx, &entries, dStart + total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(gcSyncStream(ctx));
+		if (entries == 0 || entries >= 0xFFFFFFFFull) sweep = false;
+		else
+		{
+			size_t oKeysA = 0, oKeysB = alignUp(oKeysA + entries * 8, 128), oValsA = alignUp(oKeysB + entries * 8, 128), oValsB = alignUp(oValsA + entries * 4, 128);
+			size_t oPos = alignUp(oValsB + entries * 4, 128), oLo = alignUp(oPos + entries * 4, 128), oHi = alignUp(oLo + entries * 4, 128), oTree = alignUp(oHi + entries * 4, 128), end = oTree + entries * 8;
+			CUDA_TRY(ctx->k2Sort.ensure(end));
+			uint8_t* S = (uint8_t*)ctx->k2Sort.p;
+			uint64_t* keysA = (uint64_t*)(S + oKeysA); uint64_t* keysB = (uint64_t*)(S + oKeysB); uint32_t* valsA = (uint32_t*)(S + oValsA); uint32_t* valsB = (uint32_t*)(S + oValsB);
+			gc_k2_pair_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->mpc, dAnchors, dReadOff, numReads, total, dStart, keysA, valsA);
+			size_t sortBytes = 0;
+			cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keysA, keysB, valsA, valsB, (int)entries, 0, 64, ctx->stream);
+			CUDA_TRY(ctx->copyDesc.ensure(sortBytes + 16));
+			cub::DeviceRadixSort::SortPairs(ctx->copyDesc.p, sortBytes, keysA, keysB, valsA, valsB, (int)entries, 0, 64, ctx->stream);
+			gc_k2_segments_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, ctx->stream>>>(keysB, valsB, entries, (uint32_t*)(S + oPos), (uint32_t*)(S + oLo), (uint32_t*)(S + oHi));
+			CUDA_TRY(cudaMemsetAsync(S + oTree, 0x80, entries * 8, ctx->stream)); // every tree node "minus infinity"
+			ctx->launches += 3;
+			sw.pairStart = dStart; sw.posOf = (const uint32_t*)(S + oPos); sw.keys = keysB; sw.segLo = (const uint32_t*)(S + oLo); sw.segHi = (const uint32_t*)(S + oHi);
+			sw.tree = (long long*)(S + oTree); sw.entries = entries;
+		}
+	}
+	if (sweep) gc_k2_chain_kernel<true><<<numReads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, dAnchors, dReadOff, numReads, sw, dOrder, dScore, dPred, dChain, dChainLen, dChainScore);
+	else gc_k2_chain_kernel<false><<<numReads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, dAnchors, dReadOff, numReads, sw, dOrder, dScore, dPred, dChain, dChainLen, dChainScore);
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return GCGPU_OK;
 }
 
 extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const uint64_t* read_offsets, uint32_t num_reads, uint32_t* chain, uint32_t* chain_len, int64_t* chain_score)
@@ -1806,10 +2028,11 @@ extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const ui
 	if (total) CUDA_TRY(gcCopy(ctx, A + offA, anchors, total * sizeof(GcAnchor), cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(gcCopy(ctx, A + offO, read_offsets, ((size_t)num_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	gc_k2_chain_kernel<<<num_reads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads,
-		(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
-	ctx->launches++;
-	CUDA_TRY(cudaGetLastError());
+	{
+		int krc = k2Run(ctx, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads, total,
+			(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
+		if (krc != GCGPU_OK) return krc;
+	}
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
 	if (total) CUDA_TRY(gcCopy(ctx, chain, A + offCh, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcCopy(ctx, chain_len, A + offLen, (size_t)num_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));

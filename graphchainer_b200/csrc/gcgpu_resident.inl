@@ -525,10 +525,13 @@ extern "C" int gcgpu_chain_resident(gcgpu_ctx* ctx, uint32_t num_reads, uint32_t
 	uint64_t* dOffC = (uint64_t*)(A + offOff); uint64_t* dOffP = dOffC + ((size_t)num_reads + 1);
 	const uint64_t* dReadOff = (const uint64_t*)R->readAnchorOff.p;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-	gc_k2_chain_kernel<<<num_reads, GC_K2_THREADS, 0, ctx->stream>>>(ctx->mpc, (const GcAnchor*)R->anchors.p, dReadOff, num_reads,
-		(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
+	{
+		int krc = k2Run(ctx, (const GcAnchor*)R->anchors.p, dReadOff, num_reads, total,
+			(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
+		if (krc != GCGPU_OK) return krc;
+	}
 	gc_chained_count_kernel<<<(num_reads + 1 + 127) / 128, 128, 0, ctx->stream>>>(dReadOff, num_reads, (const uint32_t*)(A + offCh), (const uint32_t*)(A + offLen), (const gcgpu_chained_anchor*)R->anchorMeta.p, dCntC, dCntP);
-	ctx->launches += 2;
+	ctx->launches += 1;
 	int rc = scanU64(ctx, dCntC, dOffC, num_reads); if (rc != GCGPU_OK) return rc;
 	rc = scanU64(ctx, dCntP, dOffP, num_reads); if (rc != GCGPU_OK) return rc;
 	CUDA_TRY(cudaGetLastError());

@@ -170,7 +170,8 @@ WORKLOADS = {
     "c2": dict(graph_len=5_000_000, n_reads=10_000, read_len=10_000, error=0.15),
     "c3": dict(graph_len=51_000_000, n_reads=100_000, read_len=15_000, error=0.10),
     "c4": dict(graph_len=51_000_000, n_reads=2_000, read_len=(50_000, 100_000), error=0.12),
-    "c5": dict(graph_len=5_000_000, n_reads=5_000, read_len=20_000, error=0.01, extra_alleles=2),
+    # --sampling-step 0.5 of BASELINE config 5 = fragments every 18 bp (the reference cannot parse that flag, AlignerMain.cpp:43,233: --colinear-split-gap 18)
+    "c5": dict(graph_len=5_000_000, n_reads=5_000, read_len=20_000, error=0.01, extra_alleles=2, split_gap=18),
 }
 
 

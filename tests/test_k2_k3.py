@@ -108,3 +108,51 @@ def test_k3_fallback_kernels_match_golden(golden_files, force):
             assert nn > 0 and bn == 0, f"{name} ({force}): {bn}/{nn} NW alignments differ from the reference"
     finally:
         del os.environ["GCGPU_K3_FORCE"]
+
+
+@pytest.mark.gpu
+def test_k2_pairwise_form_matches_golden(golden_files):
+    """The pairwise form of K2 (the fallback for reads whose anchors have different lengths) forced for every read."""
+    os.environ["GCGPU_K2_FORCE"] = "pairwise"
+    try:
+        for name, (idx, st) in golden_files.items():
+            nc, bc, nn, bn = replay_k2_k3_on_gpu(idx, st)
+            assert nc > 0 and bc == 0, f"{name}: {bc}/{nc} chains differ from the reference"
+    finally:
+        del os.environ["GCGPU_K2_FORCE"]
+
+
+def _live_k2_k3(tmp_path, graph, reads, extra=()):
+    from graphchainer_b200 import synth
+    gfa, fa = str(tmp_path / "g.gfa"), str(tmp_path / "r.fa")
+    with open(gfa, "w") as f:
+        f.write(graph.gfa())
+    synth.write_fasta(fa, reads)
+    idx, st = str(tmp_path / "x.gcidx"), str(tmp_path / "x.stages")
+    subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "-f", fa, *extra, "--gc-index", idx, "--gc-stages", st], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return replay_k2_k3_on_gpu(idx, st)
+
+
+@pytest.mark.gpu
+def test_k2_gpu_matches_reference_at_mpc_width_16(tmp_path):
+    """16 parallel alleles per variant site (MPC width 16 per strand): every anchor start has 16 backward links, every shared node
+    lies on 16 paths -- the per-path trees of the sweep form carry the chaining; overlapping fragments (--colinear-split-gap 18)."""
+    if not os.path.exists(REFDUMP):
+        pytest.skip("oracle/_ref/gc_refdump not built")
+    from graphchainer_b200 import synth
+    g = synth.SynthGraph(120_000, seed=91, extra_alleles=14, mean_spacing=30)
+    nc, bc, nn, bn = _live_k2_k3(tmp_path, g, synth.simulate_reads(g, 20, 10_000, 0.02, seed=92, novel_insertion_frac=0.2), ("--colinear-split-gap", "18"))
+    assert nc == 20 and bc == 0, f"{bc}/{nc} chains differ from the reference"
+    assert bn == 0
+
+
+@pytest.mark.gpu
+def test_k2_gpu_matches_reference_on_ultralong_anchor_sets(tmp_path):
+    """BASELINE config-4 shape for K2: 70-90 kb reads, ~2 k anchors per read."""
+    if not os.path.exists(REFDUMP):
+        pytest.skip("oracle/_ref/gc_refdump not built")
+    from graphchainer_b200 import synth
+    g = synth.SynthGraph(1_200_000, seed=93)
+    nc, bc, nn, bn = _live_k2_k3(tmp_path, g, synth.simulate_reads(g, 6, (70_000, 90_000), 0.10, seed=94, novel_insertion_frac=0.3))
+    assert nc == 6 and bc == 0, f"{bc}/{nc} chains differ from the reference"
+    assert bn == 0
