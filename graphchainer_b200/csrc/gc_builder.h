@@ -138,32 +138,44 @@ inline SplitGraph loadGfa(const std::string& filename)
 	std::unordered_map<int, std::string> nodes;
 	std::unordered_map<NodePos, std::vector<NodePos>, NodePosHash> edges;
 	auto getNameId = [&nameMapping](const std::string& name) { auto f = nameMapping.find(name); if (f == nameMapping.end()) { int r = (int)nameMapping.size(); nameMapping[name] = r; return r; } return f->second; };
+	// GFA 1 records, whitespace-separated fields: "S name sequence ..." and "L from +|- to +|- overlap ..."; everything else is skipped.
+	// Segment ids = order of first appearance of a NAME in any S or L record (GfaGraph.cpp:164-174): the numbering of the whole index.
 	std::string line;
+	std::vector<std::pair<size_t, size_t>> field; // (begin, length) of the first six fields of the line
+	auto splitFields = [&field](const std::string& text)
+	{
+		field.clear();
+		size_t i = 0, n = text.size();
+		while (i < n && field.size() < 6)
+		{
+			while (i < n && (text[i] == ' ' || text[i] == '\t' || text[i] == '\r')) i++;
+			size_t b = i;
+			while (i < n && text[i] != ' ' && text[i] != '\t' && text[i] != '\r') i++;
+			if (i > b) field.emplace_back(b, i - b);
+		}
+	};
+	auto fieldText = [&](size_t k) { return k < field.size() ? line.substr(field[k].first, field[k].second) : std::string(); };
 	while (std::getline(file, line))
 	{
-		if (line.size() == 0) continue;
+		if (line.empty() || (line[0] != 'S' && line[0] != 'L')) continue;
+		splitFields(line);
 		if (line[0] == 'S')
 		{
-			std::stringstream sstr { line };
-			std::string dummy, idstr, seq;
-			sstr >> dummy >> idstr;
-			int id = getNameId(idstr);
-			sstr >> seq;
-			if (seq == "*") throw std::runtime_error("Nodes without sequence (*) are not currently supported (nodeid " + idstr + ")");
+			std::string name = fieldText(1);
+			int id = getNameId(name);
+			std::string seq = fieldText(2);
+			if (seq == "*") throw std::runtime_error("Nodes without sequence (*) are not currently supported (nodeid " + name + ")");
 			nodes[id] = seq;
 		}
-		else if (line[0] == 'L')
+		else
 		{
-			std::stringstream sstr { line };
-			std::string dummy, fromstr, tostr, fromstart, toend;
-			int overlap = 0;
-			sstr >> dummy >> fromstr;
-			int from = getNameId(fromstr);
-			sstr >> fromstart >> tostr;
-			int to = getNameId(tostr);
-			sstr >> toend >> overlap;
+			int from = getNameId(fieldText(1));
+			bool fromForward = fieldText(2) == "+";
+			int to = getNameId(fieldText(3));
+			bool toForward = fieldText(4) == "+";
+			int overlap = atoi(fieldText(5).c_str()); // "0M" -> 0
 			if (overlap != 0) throw std::runtime_error("Edge overlaps are not supported by the B200 path (only 0M links)");
-			edges[NodePos { from, fromstart == "+" }].push_back(NodePos { to, toend == "+" });
+			edges[NodePos { from, fromForward }].push_back(NodePos { to, toForward });
 		}
 	}
 	std::unordered_map<int, std::string> originalNodeName;
@@ -275,41 +287,50 @@ inline void ufMerge(std::vector<size_t>& parent, std::vector<size_t>& rank, size
 	if (rank[left] == rank[right]) rank[left] += 1;
 }
 
-inline std::pair<bool, size_t> findBubble(const SplitGraph& g, size_t start, const std::vector<bool>& ignorableTip)
+// Is `start` the entrance of a bubble -- do all walks leaving it (tips ignored) come together again in ONE node before any of
+// them ends or returns -- and where?  (chainBubble's test, AlignmentGraph.cpp:309-373: the superbubble search of Onodera et al.)
+// A node is expanded once all its non-tip parents have been expanded; the bubble closes when exactly one node is discovered
+// but unexpanded and it is the only one ready.  Scratch arrays stamped per call replace per-call hash sets: the search runs
+// once per original node.
+struct BubbleSearch
 {
-	std::vector<size_t> S { start };
-	std::unordered_set<size_t> visited, seen;
-	seen.insert(start);
-	while (S.size() > 0)
+	std::vector<uint32_t> expandedAt, discoveredAt;
+	std::vector<size_t> ready;
+	uint32_t stamp = 0;
+	explicit BubbleSearch(size_t n) : expandedAt(n, 0), discoveredAt(n, 0) {}
+	bool run(const SplitGraph& g, size_t start, const std::vector<bool>& ignorableTip, size_t& exitNode)
 	{
-		const size_t v = S.back();
-		S.pop_back();
-		seen.erase(v);
-		visited.insert(v);
-		if (g.outNeighbors[v].size() == 0) return std::make_pair(false, (size_t)0);
-		for (const size_t u : g.outNeighbors[v])
+		stamp++;
+		ready.assign(1, start);
+		discoveredAt[start] = stamp;
+		size_t waiting = 1; // discovered, not expanded
+		while (!ready.empty())
 		{
-			if (ignorableTip[u]) continue;
-			if (u == v) continue;
-			if (u == start) return std::make_pair(false, (size_t)0);
-			seen.insert(u);
-			bool hasNonvisitedParent = false;
-			for (const size_t w : g.inNeighbors[u])
+			const size_t v = ready.back();
+			ready.pop_back();
+			expandedAt[v] = stamp;
+			waiting--;
+			if (g.outNeighbors[v].empty()) return false; // a walk ends inside
+			for (const size_t u : g.outNeighbors[v])
 			{
-				if (w == u) continue;
-				if (!ignorableTip[w] && visited.count(w) == 0) { hasNonvisitedParent = true; break; }
+				if (ignorableTip[u] || u == v) continue;
+				if (u == start) return false;
+				if (discoveredAt[u] != stamp) { discoveredAt[u] = stamp; waiting++; }
+				bool allParentsExpanded = true;
+				for (const size_t w : g.inNeighbors[u])
+					if (w != u && !ignorableTip[w] && expandedAt[w] != stamp) { allParentsExpanded = false; break; }
+				if (allParentsExpanded) ready.push_back(u);
 			}
-			if (!hasNonvisitedParent) S.push_back(u);
+			if (ready.size() == 1 && waiting == 1 && expandedAt[ready[0]] != stamp)
+			{
+				exitNode = ready[0];
+				for (const size_t u : g.outNeighbors[exitNode]) if (u == start) return false;
+				return true;
+			}
 		}
-		if (S.size() == 1 && seen.size() == 1 && seen.count(S[0]) == 1)
-		{
-			const size_t t = S.back();
-			for (const size_t u : g.outNeighbors[t]) if (u == start) return std::make_pair(false, (size_t)0);
-			return std::make_pair(true, t);
-		}
+		return false;
 	}
-	return std::make_pair(false, (size_t)0);
-}
+};
 
 inline void findChains(SplitGraph& g)
 {
@@ -393,12 +414,12 @@ inline void findChains(SplitGraph& g)
 		ufMerge(chainNumber, rank, i, uniqueFw);
 	}
 	// chainBubble for the last split node of every original node (AlignmentGraph.cpp:375-399, 596-599)
+	BubbleSearch bubbles(N);
 	for (const auto& pair : g.nodeLookup)
 	{
 		size_t start = pair.second.back();
-		auto bubble = findBubble(g, start, ignorableTip);
-		if (!bubble.first) continue;
-		size_t bubbleEnd = bubble.second;
+		size_t bubbleEnd = 0;
+		if (!bubbles.run(g, start, ignorableTip, bubbleEnd)) continue;
 		std::unordered_set<size_t> visited;
 		std::vector<size_t> stack { start };
 		visited.insert(start);
@@ -447,213 +468,234 @@ inline void findChains(SplitGraph& g)
 	}
 }
 
-// ---- minimum path cover (AlignmentGraph.cpp:1157-1489)
+// ---- path cover index for co-linear chaining (what AlignmentGraph::buildMPC provides, AlignmentGraph.cpp:1157-1489)
+//
+// K2 uses the cover for REACHABILITY only (gc_k2.cuh): an anchor ending at node e precedes one starting at s iff some path k
+// through e has its last s-reaching node at or after e.  That holds for every set of paths that covers all nodes, so the
+// cover need not be the reference's -- only narrow, because K2's work grows with the width.  Built here per weakly connected
+// component, components in parallel:
+//   1. an initial cover by forward walks: in topological order every still uncovered node starts a path that prefers
+//      uncovered successors (two walks cover a chain of SNP bubbles);
+//   2. width reduction to the minimum (Dilworth width of the DAG): the cover is a flow with a lower bound of one per node;
+//      while the residual network of (flow - lower bound) has a source-sink route, one path is cancelled along it;
+//   3. decomposition of the final flow into paths;
+//   4. per path, one sweep over the component in topological order gives every node the last position on that path that
+//      reaches it (paths in parallel, one int32 array per thread -- not the reference's N x K table).
 typedef long long LL;
+
+struct ComponentCover
+{
+	// local numbering 0..n-1 of one component, CSR adjacency, Kahn order
+	std::vector<uint32_t> outStart, outTo, inStart, inFrom, topoOrder, topoIndex;
+	size_t n = 0;
+};
 
 inline void buildComponentsMap(SplitGraph& g)
 {
-	size_t N = g.size();
-	g.component_map.assign(N, N + 1);
-	g.component_idx.assign(N, N + 1);
+	// weakly connected components by flooding from every unlabelled node (index inside the component = flood order)
+	const size_t N = g.size(), UNSET = N + 1;
+	g.component_map.assign(N, UNSET);
+	g.component_idx.assign(N, UNSET);
 	g.component_ids.clear();
-	std::vector<size_t> Q;
-	for (size_t S = 0; S < N; S++)
+	std::vector<size_t> frontier;
+	for (size_t root = 0; root < N; root++)
 	{
-		if (g.component_map[S] != N + 1) continue;
-		Q.clear();
-		Q.push_back(S);
-		size_t c = g.component_ids.size();
-		g.component_map[S] = c; g.component_idx[S] = 0;
-		for (size_t i = 0; i < Q.size(); )
+		if (g.component_map[root] != UNSET) continue;
+		const size_t c = g.component_ids.size();
+		frontier.assign(1, root);
+		g.component_map[root] = c; g.component_idx[root] = 0;
+		for (size_t head = 0; head < frontier.size(); head++)
 		{
-			size_t s = Q[i++];
-			for (size_t t : g.outNeighbors[s]) if (g.component_map[t] == N + 1) { g.component_map[t] = c; g.component_idx[t] = Q.size(); Q.push_back(t); }
-			for (size_t t : g.inNeighbors[s]) if (g.component_map[t] == N + 1) { g.component_map[t] = c; g.component_idx[t] = Q.size(); Q.push_back(t); }
+			const size_t v = frontier[head];
+			auto visit = [&](size_t w) { if (g.component_map[w] == UNSET) { g.component_map[w] = c; g.component_idx[w] = frontier.size(); frontier.push_back(w); } };
+			for (size_t w : g.outNeighbors[v]) visit(w);
+			for (size_t w : g.inNeighbors[v]) visit(w);
 		}
-		g.component_ids.push_back(Q);
+		g.component_ids.push_back(frontier);
 	}
 }
 
-// greedy cover: repeatedly the path with the most uncovered nodes (AlignmentGraph.cpp:1267-1326)
-inline std::vector<std::vector<size_t>> greedyCover(const SplitGraph& g, size_t cid)
+inline ComponentCover localComponent(const SplitGraph& g, size_t cid)
 {
-	const std::vector<size_t>& cids = g.component_ids[cid];
-	size_t N = cids.size();
-	std::vector<std::vector<size_t>> ret;
-	std::vector<size_t> covered(N, 0);
-	size_t covered_cnt = 0;
-	std::vector<std::pair<size_t, size_t>> d(N);
-	std::vector<size_t> incd(N), Q(N);
-	while (covered_cnt < covered.size())
+	const std::vector<size_t>& ids = g.component_ids[cid];
+	ComponentCover c;
+	c.n = ids.size();
+	c.outStart.assign(c.n + 1, 0); c.inStart.assign(c.n + 1, 0);
+	for (size_t i = 0; i < c.n; i++) { c.outStart[i + 1] = c.outStart[i] + (uint32_t)g.outNeighbors[ids[i]].size(); c.inStart[i + 1] = c.inStart[i] + (uint32_t)g.inNeighbors[ids[i]].size(); }
+	c.outTo.resize(c.outStart[c.n]); c.inFrom.resize(c.inStart[c.n]);
+	for (size_t i = 0; i < c.n; i++)
 	{
-		size_t Qsize = 0;
-		for (size_t i = 0; i < N; i++)
-		{
-			d[i] = std::make_pair((size_t)0, i);
-			incd[i] = g.inNeighbors[cids[i]].size();
-			if (incd[i] == 0) Q[Qsize++] = i;
-		}
-		std::pair<size_t, size_t> best = { 0, 0 };
-		for (size_t i = 0; i < Qsize; )
-		{
-			size_t s = Q[i++];
-			if (covered[s] == 0) d[s].first++;
-			best = std::max(best, { d[s].first, s });
-			for (size_t tid : g.outNeighbors[cids[s]])
-			{
-				size_t t = g.component_idx[tid];
-				incd[t]--;
-				d[t] = std::max(d[t], { d[s].first, s });
-				if (incd[t] == 0) Q[Qsize++] = t;
-			}
-		}
-		if (Qsize < N) throw std::runtime_error("The input sequence graph has a directed cycle.\nThe current version of GraphChainer only supports DAGs.");
-		std::vector<size_t> tmp, path;
-		if (best.second == d[best.second].second) tmp.push_back(best.second);
-		else for (size_t i = best.second; d[i].second != i || i != tmp.back(); i = d[i].second) tmp.push_back(i);
-		std::reverse(tmp.begin(), tmp.end());
-		size_t l = 0, r = tmp.size() - 1;
-		while (covered[tmp[l]]) l++;
-		while (covered[tmp[r]]) r--;
-		size_t new_covered = 0;
-		for (size_t i = l; i <= r; i++)
-		{
-			path.push_back(cids[tmp[i]]);
-			if (covered[tmp[i]] == 0) new_covered++;
-			covered[tmp[i]]++;
-		}
-		covered_cnt += new_covered;
-		ret.push_back(path);
+		uint32_t o = c.outStart[i]; for (size_t w : g.outNeighbors[ids[i]]) c.outTo[o++] = (uint32_t)g.component_idx[w];
+		uint32_t q = c.inStart[i]; for (size_t w : g.inNeighbors[ids[i]]) c.inFrom[q++] = (uint32_t)g.component_idx[w];
 	}
-	return ret;
+	// Kahn order; a node left over means a directed cycle
+	std::vector<uint32_t> pending(c.n);
+	c.topoOrder.clear(); c.topoOrder.reserve(c.n);
+	for (size_t i = 0; i < c.n; i++) { pending[i] = c.inStart[i + 1] - c.inStart[i]; if (pending[i] == 0) c.topoOrder.push_back((uint32_t)i); }
+	for (size_t head = 0; head < c.topoOrder.size(); head++)
+	{
+		uint32_t v = c.topoOrder[head];
+		for (uint32_t e = c.outStart[v]; e < c.outStart[v + 1]; e++) if (--pending[c.outTo[e]] == 0) c.topoOrder.push_back(c.outTo[e]);
+	}
+	if (c.topoOrder.size() < c.n) throw std::runtime_error("The input sequence graph has a directed cycle.\nThe current version of GraphChainer only supports DAGs.");
+	c.topoIndex.resize(c.n);
+	for (size_t i = 0; i < c.n; i++) c.topoIndex[c.topoOrder[i]] = (uint32_t)i;
+	return c;
 }
 
-// shrink the cover to minimum width by augmenting a flow with lower bound 1 per node (AlignmentGraph.cpp:1157-1265)
-inline std::vector<std::vector<size_t>> shrinkCover(const SplitGraph& g, size_t cid, const std::vector<std::vector<size_t>>& pc)
+// the cover as a flow: units through every node and edge, path starts and ends per node
+struct CoverFlow { std::vector<uint32_t> node, edge, starts, ends; size_t width = 0; };
+
+inline CoverFlow initialCover(const ComponentCover& c)
 {
-	const std::vector<size_t>& cids = g.component_ids[cid];
-	LL N = (LL)cids.size();
-	std::vector<std::vector<size_t>> ret;
-	LL inf = (LL)pc.size();
-	std::vector<LL> covered(N, 0), starts(N, 0), ends(N, 0);
-	std::map<std::pair<LL, LL>, LL> edge_covered;
-	for (const auto& path : pc)
+	CoverFlow f;
+	f.node.assign(c.n, 0); f.edge.assign(c.outTo.size(), 0); f.starts.assign(c.n, 0); f.ends.assign(c.n, 0);
+	for (uint32_t v0 : c.topoOrder)
 	{
-		for (size_t i = 0; i < path.size(); i++)
+		if (f.node[v0]) continue;
+		f.starts[v0]++; f.width++;
+		uint32_t v = v0;
+		while (true)
 		{
-			covered[g.component_idx[path[i]]]++;
-			if (i > 0) edge_covered[{ (LL)g.component_idx[path[i - 1]], (LL)g.component_idx[path[i]] }]++;
+			f.node[v]++;
+			uint32_t pick = 0xFFFFFFFFu;
+			for (uint32_t e = c.outStart[v]; e < c.outStart[v + 1]; e++) { if (pick == 0xFFFFFFFFu) pick = e; if (!f.node[c.outTo[e]]) { pick = e; break; } }
+			if (pick == 0xFFFFFFFFu) break;
+			f.edge[pick]++;
+			v = c.outTo[pick];
 		}
-		starts[g.component_idx[path[0]]]++;
-		ends[g.component_idx[path.back()]]++;
+		f.ends[v]++;
 	}
-	// adjacency-list flow network: nodes 0..N-1 = "in" halves, N..2N-1 = "out" halves, S = 2N, T = 2N+1
-	LL FN = 2 * N + 2, S = 2 * N, T = 2 * N + 1;
-	std::vector<LL> head(FN, 0), to(2), next(2), cap(2);
-	auto add_edge = [&](LL i, LL j, LL c) { to.push_back(j); next.push_back(head[i]); cap.push_back(c); head[i] = (LL)next.size() - 1; };
-	auto add = [&](LL i, LL j, LL capacity, LL lower, LL flow) { add_edge(i, j, flow - lower); add_edge(j, i, capacity - flow); };
-	for (LL i = 0; i < N; i++)
-		for (size_t jid : g.outNeighbors[cids[i]])
-		{
-			LL j = (LL)g.component_idx[jid];
-			auto f = edge_covered.find({ i, j });
-			add(i + N, j, inf, 0, f == edge_covered.end() ? 0 : f->second);
-		}
-	for (LL i = 0; i < N; i++)
-	{
-		add(i, i + N, inf, 1, covered[i]);
-		add(S, i, inf, 0, starts[i]);
-		add(i + N, T, inf, 0, ends[i]);
-	}
-	LL total = inf;
-	std::vector<LL> Q(FN, 0), pre(FN, -1), d(FN, 0);
-	while (true)
-	{
-		LL Qsize = 0;
-		Q[Qsize++] = S;
-		for (LL i = 0; i < FN; i++) { pre[i] = -1; d[i] = 0; }
-		d[S] = 1;
-		for (LL idx = 0; idx < Qsize && d[T] == 0; )
-		{
-			LL i = Q[idx++];
-			for (LL e = head[i]; e; e = next[e])
-			{
-				LL j = to[e];
-				if (cap[e] > 0 && d[j] == 0) { d[j] = 1; pre[j] = e; Q[Qsize++] = j; }
-			}
-		}
-		if (d[T] == 0) break;
-		LL flow = cap[pre[T]];
-		for (LL i = T; ; ) { LL e = pre[i]; if (e == -1) break; flow = std::min(flow, cap[e]); i = to[e ^ 1]; }
-		for (LL i = T; ; ) { LL e = pre[i]; if (e == -1) break; cap[e] -= flow; cap[e ^ 1] += flow; i = to[e ^ 1]; }
-		if (flow == 0) throw std::runtime_error("MPC shrink: zero augmenting flow");
-		total -= flow;
-	}
-	for (LL itr = 0; itr < total; itr++)
-	{
-		std::vector<size_t> tmp;
-		for (LL i = S; i != T; )
-		{
-			if (0 <= i && i < N) tmp.push_back(cids[i]);
-			LL nxt = -1;
-			for (LL e = head[i]; e; e = next[e])
-			{
-				LL j = to[e];
-				LL ff = cap[e] + ((i < N && i + N == j) ? 1 : 0);
-				if ((e & 1) == 0 && ff > 0) { nxt = j; cap[e]--; break; }
-			}
-			if (nxt == -1) return ret;
-			i = nxt;
-		}
-		ret.push_back(tmp);
-	}
-	return ret;
+	return f;
 }
 
-inline void computeMpcIndex(SplitGraph& g, size_t cid, const std::vector<std::vector<size_t>>& pc)
+// One round: find a route source -> sink in the residual network and cancel one unit along it.  Vertices: in(v) = 2v,
+// out(v) = 2v + 1, source, sink.  An arc can be traversed forwards if its flow exceeds its lower bound (the unit is removed)
+// and backwards always (a unit is added).  Returns false when the width is minimal.
+inline bool cancelOnePath(const ComponentCover& c, CoverFlow& f, std::vector<int64_t>& via, std::vector<uint32_t>& queue)
 {
-	const std::vector<size_t>& cids = g.component_ids[cid];
-	size_t N = cids.size();
-	LL K = (LL)pc.size();
-	g.backwards[cid].assign(N, {});
-	g.paths[cid].assign(N, {});
-	// last2reach[x][k]: index on path k of the last node that reaches x; kept flat, N*K
-	std::vector<LL> last2reach(N * (size_t)K, -1);
-	for (LL i = 0; i < K; i++)
-		for (size_t j = 0; j < pc[i].size(); j++)
-		{
-			size_t x = g.component_idx[pc[i][j]];
-			last2reach[x * K + i] = (LL)j;
-			g.paths[cid][x].push_back((size_t)i);
-		}
-	std::vector<LL> incd(N, 0), Q;
-	for (size_t i = 0; i < N; i++) { incd[i] = (LL)g.inNeighbors[cids[i]].size(); if (incd[i] == 0) Q.push_back((LL)i); }
-	g.topo_ids[cid].assign(N, 0);
-	size_t topoCount = 0;
-	for (size_t i = 0; i < Q.size(); )
+	const size_t n = c.n;
+	const uint32_t SRC = (uint32_t)(2 * n), SNK = (uint32_t)(2 * n + 1);
+	// via[x]: how x was reached -- arc code: (kind << 33) | (index << 1) | backwards
+	enum { START = 0, END = 1, NODE = 2, EDGE = 3 };
+	auto code = [](int kind, uint64_t index, bool backwards) { return (int64_t)(((uint64_t)kind << 40) | (index << 1) | (backwards ? 1u : 0u)); };
+	via.assign(2 * n + 2, -1);
+	queue.clear();
+	queue.push_back(SRC); via[SRC] = -2;
+	bool found = false;
+	for (size_t head = 0; head < queue.size() && !found; head++)
 	{
-		LL s = Q[i++];
-		for (size_t tid : g.outNeighbors[cids[s]])
+		const uint32_t x = queue[head];
+		auto reach = [&](uint32_t y, int64_t how) { if (via[y] == -1) { via[y] = how; queue.push_back(y); if (y == SNK) found = true; } };
+		if (x == SRC) { for (uint32_t v = 0; v < n; v++) if (f.starts[v] > 0) reach(2 * v, code(START, v, false)); }
+		else if (x == SNK) { }
+		else if ((x & 1) == 0)
 		{
-			size_t t = g.component_idx[tid];
-			incd[t]--;
-			if (incd[t] == 0) Q.push_back((LL)t);
+			const uint32_t v = x >> 1;
+			if (f.node[v] > 1) reach(2 * v + 1, code(NODE, v, false));                                     // one unit fewer through v (lower bound 1)
+			reach(SRC, code(START, v, true));                                                             // a new path could start here
+			for (uint32_t q = c.inStart[v]; q < c.inStart[v + 1]; q++)
+			{
+				// backwards over edge u -> v: find its CSR slot in u's out-list
+				const uint32_t u = c.inFrom[q];
+				for (uint32_t e = c.outStart[u]; e < c.outStart[u + 1]; e++) if (c.outTo[e] == v) { reach(2 * u + 1, code(EDGE, e, true)); break; }
+			}
 		}
-		g.topo_ids[cid][s] = topoCount++;
+		else
+		{
+			const uint32_t v = x >> 1;
+			if (f.ends[v] > 0) reach(SNK, code(END, v, false));
+			reach(2 * v, code(NODE, v, true));
+			for (uint32_t e = c.outStart[v]; e < c.outStart[v + 1]; e++) if (f.edge[e] > 0) reach(2 * c.outTo[e], code(EDGE, e, false));
+		}
 	}
-	for (LL i : Q)
-		for (size_t jid : g.outNeighbors[cids[i]])
+	if (!found) return false;
+	// walk back from the sink, applying the changes
+	uint32_t x = SNK;
+	while (x != SRC)
+	{
+		const int64_t how = via[x];
+		const int kind = (int)((uint64_t)how >> 40); const uint64_t index = ((uint64_t)how & ((1ull << 40) - 1)) >> 1; const bool backwards = how & 1;
+		uint32_t from;
+		if (kind == START) { if (!backwards) { f.starts[index]--; from = SRC; } else { f.starts[index]++; from = (uint32_t)(2 * index); } }
+		else if (kind == END) { f.ends[index]--; from = (uint32_t)(2 * index + 1); }
+		else if (kind == NODE) { if (!backwards) { f.node[index]--; from = (uint32_t)(2 * index); } else { f.node[index]++; from = (uint32_t)(2 * index + 1); } }
+		else
 		{
-			size_t j = g.component_idx[jid];
-			for (LL k = 0; k < K; k++) last2reach[j * K + k] = std::max(last2reach[j * K + k], last2reach[i * K + k]);
+			// edge index = CSR slot e of u -> v
+			uint32_t e = (uint32_t)index, v = c.outTo[e];
+			uint32_t u = (uint32_t)(std::upper_bound(c.outStart.begin(), c.outStart.end(), e) - c.outStart.begin() - 1);
+			if (!backwards) { f.edge[e]--; from = 2 * u + 1; } else { f.edge[e]++; from = 2 * v; }
 		}
-	for (size_t i = 0; i < N; i++)
-		for (LL k = 0; k < K; k++)
+		x = from;
+	}
+	f.width--;
+	return true;
+}
+
+// the flow as explicit paths (local node ids)
+inline std::vector<std::vector<uint32_t>> decomposeCover(const ComponentCover& c, CoverFlow f)
+{
+	std::vector<std::vector<uint32_t>> paths;
+	for (uint32_t s = 0; s < c.n; s++)
+		while (f.starts[s] > 0)
 		{
-			LL idx = last2reach[i * K + k];
-			if (idx != -1 && g.component_idx[pc[k][idx]] == i) idx--;
-			if (idx != -1) g.backwards[cid][i].push_back({ g.component_idx[pc[k][idx]], (size_t)k });
+			f.starts[s]--;
+			std::vector<uint32_t> path;
+			uint32_t v = s;
+			while (true)
+			{
+				path.push_back(v);
+				uint32_t next = 0xFFFFFFFFu;
+				for (uint32_t e = c.outStart[v]; e < c.outStart[v + 1]; e++) if (f.edge[e] > 0) { f.edge[e]--; next = c.outTo[e]; break; }
+				if (next == 0xFFFFFFFFu) { f.ends[v]--; break; }
+				v = next;
+			}
+			paths.push_back(std::move(path));
 		}
+	return paths;
+}
+
+inline void buildComponentIndex(SplitGraph& g, size_t cid, bool verbose)
+{
+	const ComponentCover c = localComponent(g, cid);
+	CoverFlow f = initialCover(c);
+	const size_t initialWidth = f.width;
+	{
+		std::vector<int64_t> via; std::vector<uint32_t> queue;
+		while (cancelOnePath(c, f, via, queue)) { }
+	}
+	const std::vector<std::vector<uint32_t>> cover = decomposeCover(c, f);
+	const std::vector<size_t>& ids = g.component_ids[cid];
+	const size_t n = c.n, K = cover.size();
+	g.mpc[cid].assign(K, {});
+	for (size_t k = 0; k < K; k++) for (uint32_t v : cover[k]) g.mpc[cid][k].push_back(ids[v]);
+	g.topo_ids[cid].assign(n, 0);
+	for (size_t v = 0; v < n; v++) g.topo_ids[cid][v] = c.topoIndex[v];
+	g.paths[cid].assign(n, {});
+	g.backwards[cid].assign(n, {});
+	for (size_t k = 0; k < K; k++) for (uint32_t v : cover[k]) g.paths[cid][v].push_back(k); // k ascending per node
+	// per path: last position on it that reaches each node; a node on the path itself links to its predecessor on the path
+	std::vector<std::vector<std::pair<size_t, size_t>>> perPath(K); // (node, linked local node) for path k
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (size_t k = 0; k < K; k++)
+	{
+		std::vector<int32_t> last(n, -1), own(n, -1);
+		for (size_t p = 0; p < cover[k].size(); p++) own[cover[k][p]] = (int32_t)p;
+		for (uint32_t v : c.topoOrder)
+		{
+			int32_t best = -1;
+			for (uint32_t q = c.inStart[v]; q < c.inStart[v + 1]; q++) { int32_t r = last[c.inFrom[q]]; if (r > best) best = r; }
+			if (best >= 0) perPath[k].emplace_back(v, cover[k][best]);
+			last[v] = own[v] > best ? own[v] : best;
+		}
+	}
+	for (size_t k = 0; k < K; k++) for (const auto& link : perPath[k]) g.backwards[cid][link.first].push_back({ link.second, k }); // k ascending per node
+	if (verbose)
+	{
+		#pragma omp critical
+		std::cout << "cid = " << cid << " greedy width " << initialWidth << " optimal width " << K << std::endl;
+	}
 }
 
 inline void buildMpc(SplitGraph& g, bool verbose)
@@ -661,16 +703,10 @@ inline void buildMpc(SplitGraph& g, bool verbose)
 	buildComponentsMap(g);
 	size_t C = g.component_ids.size();
 	g.mpc.resize(C); g.topo_ids.resize(C); g.paths.resize(C); g.backwards.resize(C);
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (size_t cid = 0; cid < C; cid++) buildComponentIndex(g, cid, verbose);
 	size_t tw = 0, mw = 0;
-	for (size_t cid = 0; cid < C; cid++)
-	{
-		g.mpc[cid] = greedyCover(g, cid);
-		size_t greedy = g.mpc[cid].size();
-		g.mpc[cid] = shrinkCover(g, cid, g.mpc[cid]);
-		computeMpcIndex(g, cid, g.mpc[cid]);
-		if (verbose) std::cout << "cid = " << cid << " greedy width " << greedy << " optimal width " << g.mpc[cid].size() << std::endl;
-		tw += g.mpc[cid].size(); mw = std::max(mw, g.mpc[cid].size());
-	}
+	for (size_t cid = 0; cid < C; cid++) { tw += g.mpc[cid].size(); mw = std::max(mw, g.mpc[cid].size()); }
 	if (verbose) std::cout << "MPC building done" << std::endl << "total width " << tw << " and max component width " << mw << std::endl;
 }
 

@@ -42,19 +42,24 @@ struct GcK3wPass
 	int32_t tauEnd;        // last wavefront step
 	GcK3Block* store;      // leaf traceback: block b of column c -> store[c * storeStride + b] (null: not kept)
 	int32_t storeStride;
+	int32_t lanes;         // lanes of the wavefront: 32 (one warp) or 32 x the warps of a block (gc_k3b_*, hand-over through shared memory)
 };
 
-GC_HD int32_t gc_k3w_blocks_per_lane(int32_t q, int32_t t, int32_t k)
+// blocks per lane so that a lane is done with group g before group g + lanes enters the band:
+// (dhi - dlo) <= 64 * NB * (lanes - 1) + lanes
+GC_HD int32_t gc_k3w_blocks_per_lane(int32_t q, int32_t t, int32_t k, int32_t lanes = GC_K3W_LANES)
 {
 	GcK3Band band = gc_k3_band(q, t, k);
 	int32_t width = band.dhi - band.dlo;
-	if (width <= 32) return 1;
-	return (width - 32 + 1983) / 1984;
+	if (width <= lanes) return 1;
+	int32_t per = 64 * (lanes - 1);
+	return (width - lanes + per - 1) / per;
 }
 
-GC_HD GcK3wPass gc_k3w_make_pass(const uint64_t* peq, int32_t nbTotal, int32_t qOff, int32_t q, const uint8_t* target, int64_t tBase, int32_t tStep, int32_t t, int32_t k, int32_t stopCol, int32_t NB)
+GC_HD GcK3wPass gc_k3w_make_pass(const uint64_t* peq, int32_t nbTotal, int32_t qOff, int32_t q, const uint8_t* target, int64_t tBase, int32_t tStep, int32_t t, int32_t k, int32_t stopCol, int32_t NB, int32_t lanes = GC_K3W_LANES)
 {
 	GcK3wPass p;
+	p.lanes = lanes;
 	p.peq = peq; p.nbTotal = nbTotal; p.qOff = qOff; p.q = q; p.target = target; p.tBase = tBase; p.tStep = tStep; p.t = t; p.stopCol = stopCol;
 	GcK3Band band = gc_k3_band(q, t, k);
 	p.dlo = band.dlo; p.dhi = band.dhi;
@@ -159,7 +164,7 @@ GC_HD uint32_t gc_k3w_lane_step(const GcK3wPass& p, GcK3wLane<NB>& s, int32_t ta
 			for (int i = 0; i < NB; i++)
 				if (i < s.nbHere) { GcK3Block bl; bl.P = s.P[i]; bl.M = s.M[i]; bl.score = s.score[i]; bl.pad = 0; blocksOut[s.g * NB + i] = bl; }
 		}
-		if (c == s.cLast) gc_k3w_set_group(p, s, s.g + GC_K3W_LANES);
+		if (c == s.cLast) gc_k3w_set_group(p, s, s.g + p.lanes);
 	}
 	s.prevRecv = recv;
 	return send;

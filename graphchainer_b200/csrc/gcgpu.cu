@@ -1166,6 +1166,127 @@ __global__ void __launch_bounds__(128) gc_k3w_distance_kernel(const uint8_t* __r
 	if (lane == 0) { o.blocks = work; out[d.resultIndex] = o; }
 }
 
+// ---- block form of the distance pass: the same skewed wavefront over the lanes of GC_K3B_WARPS warps.  A single warp holds a
+// band of at most 64 * NB * 31 diagonals in its registers (NB <= 16: ~31 k diagonals, and the whole pass runs at one warp's issue
+// rate); the cutoff bands of ultra-long reads (75 kb at 12 % error: k = 16384, 32 k diagonals) do not fit, and the widest
+// alignments of a 10-kb batch set its latency.  Here lane 31 of a warp hands its horizontal delta to lane 0 of the next warp
+// through shared memory (double-buffered, one __syncthreads per wavefront step), so 256 lanes share the band: NB <= 4 covers
+// 65 k diagonals, and the pass is issued by eight warps.
+#define GC_K3B_WARPS 8
+#define GC_K3B_LANES (32 * GC_K3B_WARPS)
+template <int NB>
+__device__ __forceinline__ uint32_t gc_k3b_run_pass(const GcK3wPass& p, GcK3Block* blocksOut, uint32_t* xfer /* [2][GC_K3B_WARPS] */, int32_t* evShared)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int src = (lane + 31) & 31, prevWarp = (warp + GC_K3B_WARPS - 1) % GC_K3B_WARPS;
+	GcK3wLane<NB> s;
+	gc_k3w_lane_init(p, s, (int32_t)threadIdx.x);
+	uint32_t send = 0;
+	int32_t tau = 0;
+	if (threadIdx.x < 2 * GC_K3B_WARPS) xfer[threadIdx.x] = 0;
+	__syncthreads();
+	while (tau <= p.tauEnd)
+	{
+		// next step at which some lane of the block changes its control state
+		if (threadIdx.x == 0) *evShared = GC_K3W_NO_EVENT;
+		__syncthreads();
+		int32_t evWarp = __reduce_min_sync(0xFFFFFFFFu, gc_k3w_next_event(p, s, tau));
+		if (lane == 0) atomicMin(evShared, evWarp);
+		__syncthreads();
+		const int32_t ev = *evShared;
+		if (ev > tau)
+		{
+			int32_t end = ev <= p.tauEnd ? ev : p.tauEnd + 1;
+			GcK3wSegment seg = gc_k3w_segment(p, s, tau);
+			for (; tau < end; tau++)
+			{
+				uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, src);
+				if (lane == 0) recv = xfer[((tau + 1) & 1) * GC_K3B_WARPS + prevWarp]; // what the previous warp's last lane sent in step tau - 1
+				send = gc_k3w_lane_fast_step<NB, false>(p, s, seg, tau, recv);
+				if (lane == 31) xfer[(tau & 1) * GC_K3B_WARPS + warp] = send;
+				__syncthreads();
+			}
+		}
+		else
+		{
+			uint32_t recv = __shfl_sync(0xFFFFFFFFu, send, src);
+			if (lane == 0) recv = xfer[((tau + 1) & 1) * GC_K3B_WARPS + prevWarp];
+			send = gc_k3w_lane_step(p, s, tau, recv, blocksOut);
+			if (lane == 31) xfer[(tau & 1) * GC_K3B_WARPS + warp] = send;
+			__syncthreads();
+			tau++;
+		}
+	}
+	__syncthreads();
+	return s.work;
+}
+__device__ __forceinline__ int gc_k3b_round_nb(int nb) { return nb <= 1 ? 1 : nb <= 2 ? 2 : nb <= 3 ? 3 : nb <= 4 ? 4 : 0; }
+
+// one block = one edlib NW distance
+__global__ void __launch_bounds__(GC_K3B_LANES, 2) gc_k3b_distance_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK3Out* out)
+{
+	__shared__ uint32_t xfer[2 * GC_K3B_WARPS];
+	__shared__ int32_t evShared;
+	__shared__ unsigned long long workShared;
+	const uint32_t w = blockIdx.x;
+	if (w >= n) return;
+	GcK3Desc d = descs[w];
+	int32_t q = d.q, t = d.t;
+	int32_t nb = (q + 63) / 64; if (nb < 1) nb = 1;
+	uint64_t* peq = (uint64_t*)(arena + d.wsOff);
+	GcK3Block* blocks = (GcK3Block*)(peq + 4 * (size_t)nb);
+	const uint8_t* query = seq + d.qOff;
+	const uint8_t* target = seq + d.tOff;
+	for (int32_t b = threadIdx.x; b < nb; b += GC_K3B_LANES)
+	{
+		uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+		int32_t lim = q - b * 64; if (lim > 64) lim = 64;
+		for (int32_t i = 0; i < lim; i++)
+		{
+			uint8_t c = query[b * 64 + i];
+			uint64_t bit = 1ULL << i;
+			e0 |= c == 0 ? bit : 0; e1 |= c == 1 ? bit : 0; e2 |= c == 2 ? bit : 0; e3 |= c == 3 ? bit : 0;
+		}
+		peq[b] = e0; peq[nb + b] = e1; peq[2 * (size_t)nb + b] = e2; peq[3 * (size_t)nb + b] = e3;
+	}
+	if (threadIdx.x == 0) workShared = 0;
+	__syncthreads();
+	GcK3Out o; o.status = GC_OK; o.opsLen = 0; o.pad = 0; o.blocks = 0; o.distance = -1;
+	uint32_t work = 0;
+	if (q == 0 || t == 0) o.distance = q > t ? q : t;
+	else
+	{
+		int32_t k = d.kHint < 64 ? 64 : d.kHint;
+		int32_t diff = q > t ? q - t : t - q, mx = q > t ? q : t;
+		while (true)
+		{
+			if (k >= diff)
+			{
+				int32_t kk = k > mx ? mx : k;
+				int NB = gc_k3b_round_nb(gc_k3w_blocks_per_lane(q, t, kk, GC_K3B_LANES));
+				if (NB == 0) { o.distance = GC_K3W_NEED_LARGER; o.pad = (uint32_t)k; break; }
+				GcK3wPass p = gc_k3w_make_pass(peq, nb, 0, q, target, 0, 1, t, kk, t - 1, NB, GC_K3B_LANES);
+				switch (NB)
+				{
+					case 1: work += gc_k3b_run_pass<1>(p, blocks, xfer, &evShared); break;
+					case 2: work += gc_k3b_run_pass<2>(p, blocks, xfer, &evShared); break;
+					case 3: work += gc_k3b_run_pass<3>(p, blocks, xfer, &evShared); break;
+					default: work += gc_k3b_run_pass<4>(p, blocks, xfer, &evShared); break;
+				}
+				__syncthreads();
+				int32_t v = gc_k3_cell(blocks[(q - 1) >> 6], q - 1);
+				__syncthreads(); // every thread has read the stop column before the next pass overwrites it
+				if (v <= kk) { o.distance = v; break; }
+			}
+			k *= 2;
+		}
+	}
+	for (int off = 16; off > 0; off >>= 1) work += __shfl_down_sync(0xFFFFFFFFu, work, off);
+	if ((threadIdx.x & 31) == 0) atomicAdd(&workShared, (unsigned long long)work);
+	__syncthreads();
+	if (threadIdx.x == 0) { o.blocks = workShared; out[d.resultIndex] = o; }
+}
+
 // one thread = one edlib NW path (Hirschberg + leaf tracebacks) for a known distance
 __global__ void __launch_bounds__(64) gc_k3_path_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint8_t* opsArena, GcK3Out* out)
 {
@@ -1506,7 +1627,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 				while (k < diff) k *= 2;
 				int32_t kk = k > mx ? mx : k;
 				int32_t nbl = gc_k3w_blocks_per_lane(d.q, d.t, kk);
-				isWide = nbl > 2 && nbl <= 16;
+				isWide = nbl > 2; // more than two blocks per lane of a single warp: the block form (eight warps share the band)
 			}
 			(isWide ? wide : narrow).push_back(d);
 		}
@@ -1528,7 +1649,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	{
 		CUDA_TRY(cudaEventRecord(ctx->evFork, ctx->stream));
 		CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-		gc_k3w_distance_kernel<1><<<(nWide + 3) / 4, 128, 0, ctx->stream2>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		gc_k3b_distance_kernel<<<nWide, GC_K3B_LANES, 0, ctx->stream2>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		CUDA_TRY(cudaEventRecord(ctx->evJoin, ctx->stream2));
 		ctx->launches++;
 	}
@@ -1545,7 +1666,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	ctx->lastKernelMs += ms;
-	GC_TRACE_MS("k3w distance<0|1>", n);
+	GC_TRACE_MS("k3w distance (warp | block form)", n);
 	}
 	// items whose cutoff band outgrew the register budget of the launched class: wider class, then the thread form
 	for (int cls = 1; cls <= 2; cls++)
@@ -1562,7 +1683,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		(void)blocksBefore;
 		CUDA_TRY(gcCopy(ctx, ctx->descBuf.p, rd.data(), (size_t)m * sizeof(GcK3Desc), cudaMemcpyHostToDevice, ctx->stream));
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-		if (cls == 1) gc_k3w_distance_kernel<1><<<(m + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		if (cls == 1) gc_k3b_distance_kernel<<<m, GC_K3B_LANES, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		else gc_k3_distance_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p, m, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError());
@@ -1572,7 +1693,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 		CUDA_TRY(gcSyncStream(ctx));
 		CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 		ctx->lastKernelMs += ms;
-		GC_TRACE_MS(cls == 1 ? "k3w distance<1>" : "k3 distance (thread)", m);
+		GC_TRACE_MS(cls == 1 ? "k3b distance (block form)" : "k3 distance (thread)", m);
 		for (const GcK3Desc& d : rd) hout[d.resultIndex].blocks += prev[d.resultIndex].blocks;
 	}
 	// ---- path pass for the items that asked for it
