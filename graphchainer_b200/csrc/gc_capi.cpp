@@ -47,9 +47,13 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	// large block is its own mmap/munmap (page faults on first touch, TLB shootdowns across all threads on release) and the
 	// arenas are trimmed back to the kernel between batches; keeping the memory in the arenas was worth 7 % end to end on
 	// B200 (profiles/r01j).
-	mallopt(M_MMAP_THRESHOLD, 1 << 30);
-	mallopt(M_TRIM_THRESHOLD, -1);
-	mallopt(M_TOP_PAD, 256 << 20);
+	// This changes the allocator of the whole process: GCALIGN_KEEP_MALLOC=1 leaves it alone.
+	if (!getenv("GCALIGN_KEEP_MALLOC"))
+	{
+		mallopt(M_MMAP_THRESHOLD, 1 << 30);
+		mallopt(M_TRIM_THRESHOLD, -1);
+		mallopt(M_TOP_PAD, 256 << 20);
+	}
 	gcalign* h = new gcalign();
 	if (opts) h->opts = *opts; else gcalign_default_options(&h->opts);
 	if (h->opts.colinear_split_gap < 1 || h->opts.colinear_split_len < 1) { delete h; return fail(GCGPU_ERR_ARG, "gcalign_open: split length / gap must be >= 1"); }
@@ -130,6 +134,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	std::mutex errMutex; std::string error;
 	GcPipelineStats total;
 	auto tCall0 = std::chrono::steady_clock::now();
+	const int callerOmpThreads = omp_get_max_threads(); // worker 0 runs on the caller's thread: its OpenMP setting is restored below
 	auto work = [&](size_t w)
 	{
 		omp_set_num_threads(threadsPerWorker);
@@ -193,6 +198,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		work(0);
 		for (auto& t : threads) t.join();
 	}
+	omp_set_num_threads(callerOmpThreads);
 	if (!error.empty()) return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + error);
 	auto tCall1 = std::chrono::steady_clock::now();
 	uint64_t used = 0;
@@ -212,9 +218,8 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 			if (stats) { stats->seeds_found += res.seedsFound; if (!res.alignments.empty()) stats->seeds_extended += res.seedsExtended; }
 			if (gam_out && !records[bi][i].empty())
 			{
-				if (used + records[bi][i].size() > gam_capacity) return fail(GCGPU_ERR_ARG, "gcalign_align: GAM buffer too small");
-				memcpy(gam_out + used, records[bi][i].data(), records[bi][i].size());
-				used += records[bi][i].size();
+				if (used + records[bi][i].size() <= gam_capacity) memcpy(gam_out + used, records[bi][i].data(), records[bi][i].size());
+				used += records[bi][i].size(); // keeps counting past the capacity: on overflow the caller learns the size it needs
 			}
 		}
 	}
@@ -232,6 +237,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		}
 	}
 	if (gam_used) *gam_used = used;
+	if (gam_out && used > gam_capacity) return fail(GCGPU_ERR_ARG, "gcalign_align: GAM buffer too small, need " + std::to_string(used) + " bytes (*gam_used holds the size)");
 	if (getenv("GC_TRACE_CALL"))
 	{
 		auto tCall2 = std::chrono::steady_clock::now();

@@ -256,6 +256,7 @@ int main(int argc, char** argv)
 	if (params.outJson != "") jsonOut.open(params.outJson);
 	std::ofstream gafOut;
 	if (params.outGaf != "") gafOut.open(params.outGaf);
+	if ((params.outGam != "" && !gamOut.good()) || (params.outJson != "" && !jsonOut.good()) || (params.outGaf != "" && !gafOut.good())) { std::cerr << "cannot open the alignment output file for writing" << std::endl; return 1; }
 	std::mutex outMutex, inMutex;
 	bool wroteAny = false;
 	size_t statReads = 0, statBp = 0, statSeedsFound = 0, statSeedsExtended = 0, statReadsWithSeed = 0, statBpWithSeed = 0, statReadsWithAln = 0, statAlns = 0, statBpAln = 0, statFull = 0, statBpFull = 0;
@@ -382,6 +383,8 @@ int main(int argc, char** argv)
 	std::cout << "Alignments: " << statAlns << " (" << statBpAln << "bp)" << std::endl;
 	std::cout << "End-to-end alignments: " << statFull << " (" << statBpFull << "bp)" << std::endl;
 	if (anyDropped) std::cout << "Alignment broke with some reads. Look at stderr output." << std::endl;
+	gamOut.flush(); jsonOut.flush(); gafOut.flush();
+	if ((params.outGam != "" && !gamOut.good()) || (params.outJson != "" && !jsonOut.good()) || (params.outGaf != "" && !gafOut.good())) { std::cerr << "writing the alignment output failed" << std::endl; return 1; }
 	if (!params.quiet)
 	{
 		std::cout << "B200: align phase " << alignSec << " s, " << (statBp / alignSec) << " bp/s on " << params.gpus << " GPU(s); K1 " << total.k1Items << " extensions / " << total.k1Columns << " column steps / " << total.k1Ms << " ms, "

@@ -282,8 +282,18 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	uint64_t totalChars = 0;
 	for (size_t r = 0; r < R; r++) { rd[r].char_offset = totalChars; rd[r].len = (int32_t)reads[r].sequence.size(); rd[r].first_cell = 0; rd[r].num_cells = 0; rd[r].reserved = 0; totalChars += reads[r].sequence.size(); }
 	charsBuf.ensure(totalChars + 16);
+	// A character outside the IUPAC alphabet makes the reference's CommonUtils::Complement assert (CommonUtils.cpp:131-133) when
+	// AlignOneWay reverse-complements the read (GraphAligner.h:124): the read is dropped (Aligner.cpp:585-592).
+	std::vector<uint8_t> invalidChars(R, 0);
 	#pragma omp parallel for schedule(dynamic, 16)
-	for (size_t r = 0; r < R; r++) memcpy((char*)charsBuf.p + rd[r].char_offset, reads[r].sequence.data(), reads[r].sequence.size());
+	for (size_t r = 0; r < R; r++)
+	{
+		const std::string& sq = reads[r].sequence;
+		memcpy((char*)charsBuf.p + rd[r].char_offset, sq.data(), sq.size());
+		uint8_t all = 0xFF;
+		for (char ch : sq) all &= (uint8_t)(gcEncodeBase(ch) ? 0xFF : 0);
+		invalidChars[r] = all ? 0 : 1;
+	}
 	{ double tDev = wallNow(); check(gcgpu_load_reads(ctx, (const char*)charsBuf.p, totalChars, rd.data(), (uint32_t)R), "gcgpu_load_reads"); devMs += wallNow() - tDev; stats.s0Ms += gcgpu_last_kernel_ms(ctx); }
 	// ---- S0: seeds (the reference calls getSeeds + OrderSeeds twice per read with identical results).
 	// k-mer walk + index probes on the device; the count sort, density cut, seed-hit expansion and clustering per read on the host
@@ -367,7 +377,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		bool degenerate = false;              // an alignment on which exactAlignmentPart asserts exists: evaluate in reference order
 	};
 	std::vector<S1State> s1(R);
-	for (size_t r = 0; r < R; r++) { if (seedsOrdered[r].empty()) s1[r].done = true; else { s1[r].skip.assign(seedsOrdered[r].size(), 0); s1[r].checked.assign(seedsOrdered[r].size(), 0); } }
+	for (size_t r = 0; r < R; r++) { if (seedsOrdered[r].empty()) s1[r].done = true; else if (invalidChars[r]) { s1[r].done = true; out[r].dropped = true; } else { s1[r].skip.assign(seedsOrdered[r].size(), 0); s1[r].checked.assign(seedsOrdered[r].size(), 0); } }
 	// 0 = extend, 1 = skip, 2 = stop the seed loop, 3 = assertion (read dropped)
 	auto seedRule = [&](S1State& st, const GcSeedHit& seed, size_t idx) -> int
 	{

@@ -71,7 +71,11 @@ void gcalign_close(gcalign* h);
 /* measurement aid: gcgpu_int_peak() of the handle's device (int32 LOP3/IADD3 instructions per second, thread level) */
 int gcalign_int_peak(gcalign* h, double* int32_ops_per_s);
 /* reads: seqs[seq_offsets[i] .. seq_offsets[i+1]) and names likewise.  If gam_out != NULL the
- * reads' GAM records (one gzip member per read with an alignment) are appended to it.       */
+ * reads' GAM records (one gzip member per read with an alignment) are appended to it.  If they
+ * do not fit, GCGPU_ERR_ARG is returned and *gam_used holds the number of bytes the records need
+ * (the call can be repeated with a buffer of that size).  The calling thread's OpenMP thread
+ * count is restored on return; gcalign_open tunes the process's malloc arenas unless
+ * GCALIGN_KEEP_MALLOC is set in the environment.                                            */
 int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_offsets, const char* names, const uint64_t* name_offsets, uint32_t num_reads,
                   uint8_t* gam_out, uint64_t gam_capacity, uint64_t* gam_used, gcalign_read_summary* summaries, gcalign_stats* stats);
 

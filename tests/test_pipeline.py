@@ -119,6 +119,16 @@ def test_read_that_hits_an_assertion_class_state_is_dropped(driver_sim, golden_f
     got = gam.read_gam(out)
     assert victim in got and "Alignment broke with some reads" in run.stdout
     assert not gam.diff_gam({k: v for k, v in got.items() if k != victim}, rest)
+    # a character outside the IUPAC alphabet: the reference's Complement() asserts (CommonUtils.cpp:131-133; the unmodified program
+    # aborts as a whole there) -- here that read alone is dropped
+    lines = open(fa).read().split("\n")
+    k = lines.index(">" + victim) + 1
+    lines[k] = lines[k][:300] + "X" + lines[k][301:]
+    bad_fa = str(tmp_path / "bad.fa")
+    open(bad_fa, "w").write("\n".join(lines))
+    run = subprocess.run([driver_sim, "--gc-index", idx, "-f", bad_fa, "-a", out, "-t", "2"], check=True, capture_output=True, text=True)
+    got = gam.read_gam(out)
+    assert victim not in got and not gam.diff_gam(got, rest)
 
 
 @pytest.mark.gpu
