@@ -553,11 +553,24 @@ static int buildPlanes(gcgpu_ctx* ctx, uint64_t bytes)
 	CUDA_TRY(cudaGetLastError());
 	return GCGPU_OK;
 }
-// Long items run lane-per-item (gc_k1s_*: 32 items per warp, ~1/12 of the issue slots per column step) when a launch has at
-// least this many of them, warp-per-item in lock-step (gc_k1_long_*: a fifth of the latency of a walk, 32 redundant lanes)
-// below it: a launch of a few hundred items cannot fill the GPU either way and only its latency matters (profiles/r03d).
-// GCGPU_K1_SIMT_MIN=0: always lane-per-item; a huge value: always lock-step.
-static const uint32_t g_k1SimtMin = getenv("GCGPU_K1_SIMT_MIN") ? (uint32_t)strtoul(getenv("GCGPU_K1_SIMT_MIN"), nullptr, 10) : 4096u;
+// Long items run either lane-per-item (gc_k1s_*: 32 items per warp, ~1/12 of the issue slots per column step, but a walk takes
+// ~280 us per 64-row slice because every lane waits for the slowest lane's bookkeeping) or warp-per-item in lock-step
+// (gc_k1_long_*: ~22 us per slice, 32 redundant lanes: a launch of more than a few thousand items saturates the integer pipe for
+// ~22 ns per item-slice and starves the kernels of the other batches in flight).  Per launch, from the items' slice counts:
+//   lock-step time ~ max(longest item x 22 us, sum of slices x 22 ns);  lane-per-item time ~ longest item x 280 us
+// and the lane-per-item form is taken unless it is estimated more than four times slower (measurements: profiles/r03d, r03f, r03h:
+// c2 round 2 goes lane-per-item, the one-seed-per-read first round and the tail rounds lock-step, ultra-long reads lock-step).
+// GCGPU_K1_FORM=lane | lockstep forces one form.
+static bool k1UseLaneForm(uint32_t nLong, uint64_t sumSlices, uint32_t maxSlices)
+{
+	const char* force = getenv("GCGPU_K1_FORM");
+	if (force && !strcmp(force, "lane")) return true;
+	if (force && !strcmp(force, "lockstep")) return false;
+	if (nLong < 1024) return false;
+	double tLock = std::max((double)maxSlices * 0.022, (double)sumSlices * 2.2e-5);               // ms
+	double tLane = (double)maxSlices * 0.28 * std::max(1.0, (double)nLong / (32.0 * 148 * 8));   // ms
+	return tLane <= 4.0 * tLock;
+}
 
 static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* lens, uint32_t n, int32_t uniformMax, GcK1Run& run)
 {
@@ -636,7 +649,9 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	if (needInit) { gc_k1_init_results_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dRes, dSlot, n); ctx->launches++; }
 	if (nLong)
 	{
-		if (nLong >= g_k1SimtMin)
+		uint64_t sumSlices = 0; uint32_t maxSlices = 0;
+		for (const GcK1Desc& d : descs) { sumSlices += d.numSlices; if (d.numSlices > maxSlices) maxSlices = d.numSlices; }
+		if (k1UseLaneForm(nLong, sumSlices, maxSlices))
 		{
 			// lane per item: 32 items per warp, sorted by length
 			uint32_t blocks = (nLong + GC_K1S_THREADS - 1) / GC_K1S_THREADS;

@@ -60,10 +60,18 @@ def _replay_on_gpu(idx_path, st_path, max_reads=None):
 
 
 @pytest.mark.gpu
-def test_k1_gpu_matches_golden(golden_files):
-    for name, (idx, st) in golden_files.items():
-        n, bad, cols = _replay_on_gpu(idx, st)
-        assert n > 0 and bad == 0, f"{name}: {bad}/{n} extensions differ from the reference"
+@pytest.mark.parametrize("form", ["auto", "lane", "lockstep"])
+def test_k1_gpu_matches_golden(golden_files, form):
+    """form: which kernels take the whole-read extensions -- lane-per-item (gc_k1s_*), warp-per-item in lock-step (gc_k1_long_*),
+    or the library's per-launch choice (GCGPU_K1_FORM)."""
+    if form != "auto":
+        os.environ["GCGPU_K1_FORM"] = form
+    try:
+        for name, (idx, st) in golden_files.items():
+            n, bad, cols = _replay_on_gpu(idx, st)
+            assert n > 0 and bad == 0, f"{name} ({form}): {bad}/{n} extensions differ from the reference"
+    finally:
+        os.environ.pop("GCGPU_K1_FORM", None)
 
 
 @pytest.mark.gpu
@@ -79,5 +87,10 @@ def test_k1_gpu_matches_reference_on_fresh_synthetic(tmp_path):
     synth.write_fasta(fa, synth.simulate_reads(g, 60, 6000, 0.15, seed=22, novel_insertion_frac=0.1))
     idx, st = str(tmp_path / "x.gcidx"), str(tmp_path / "x.stages")
     subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "-f", fa, "--gc-index", idx, "--gc-stages", st], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    n, bad, cols = _replay_on_gpu(idx, st)
-    assert n > 5000 and bad == 0, f"{bad}/{n} extensions differ from the reference"
+    for form in ("lane", "lockstep"):
+        os.environ["GCGPU_K1_FORM"] = form
+        try:
+            n, bad, cols = _replay_on_gpu(idx, st)
+        finally:
+            os.environ.pop("GCGPU_K1_FORM", None)
+        assert n > 5000 and bad == 0, f"{form}: {bad}/{n} extensions differ from the reference"
