@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--streams", type=int, default=6, help="read batches in flight per GPU in the e2e measurement")
     ap.add_argument("--batch-bp", type=int, default=0, help="read bases per internal GPU batch (0 = library default)")
     ap.add_argument("--value-batch-bp", type=int, default=0, help="read bases per GPU batch in the kernel-time (value) measurement (0 = the whole read set in one batch)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads of this rank (0 = all cores / ranks); 4 at --gpus 1 reproduces one rank's share of a 32-core 8-GPU box")
     ap.add_argument("--threads-per-stream", type=int, default=0, help="host threads per in-flight batch (0 = host threads / streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -202,7 +203,7 @@ def main():
     from graphchainer_b200 import align
     gfa, reads = make_inputs(args.workload, n_reads, rank, tmp)
     batch = align.ReadBatch([r[0] for r in reads], [r[1] for r in reads])
-    threads = max(1, host_cores // world)
+    threads = args.host_threads or max(1, host_cores // world)
     t_index = time.perf_counter()
     aligner = align.Aligner(gfa, device=local_rank, host_threads=threads, split_len=35, split_gap=split_gap, streams=args.streams, batch_bp=args.batch_bp, threads_per_stream=args.threads_per_stream)
     index_s = time.perf_counter() - t_index

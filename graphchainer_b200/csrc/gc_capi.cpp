@@ -83,6 +83,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 	{
 		int rc = gcgpu_create(h->opts.device, &gg, &gp, &h->workers[w].ctx);
 		if (rc == GCGPU_OK) rc = gcUploadMinimizerIndex(h->workers[w].ctx, g);
+		if (rc == GCGPU_OK) rc = gcUploadNodeNames(h->workers[w].ctx, g);
 		if (rc != GCGPU_OK) { std::string msg = gcgpu_last_error(); gcalign_close(h); return fail(rc, "gcalign_open: " + msg); }
 	}
 	h->pipe.colinearGap = h->opts.colinear_gap; h->pipe.colinearSplitLen = h->opts.colinear_split_len; h->pipe.colinearSplitGap = h->opts.colinear_split_gap;
@@ -161,6 +162,8 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 				}
 				std::vector<GcReadResult>& results = allResults[bi];
 				auto tB0 = std::chrono::steady_clock::now();
+				// level 1 (the default) = records of the whole-read alignments encoded and compressed on the device; zlib levels stay on the host
+				pipeline.setGamOnDevice(gam_out != nullptr && (h->opts.gzip_level <= 1));
 				pipeline.alignBatch(batch, results);
 				if (getenv("GC_TRACE_CALL")) fprintf(stderr, "[gcalign] worker %zu batch %zu: alignBatch %.1f ms (start +%.1f ms)\n", w, bi, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tB0).count(), std::chrono::duration<double, std::milli>(tB0 - tCall0).count());
 				records[bi].resize(batch.size());
@@ -175,6 +178,7 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 						for (size_t i = 0; i < batch.size(); i++)
 						{
 							if (results[i].alignments.empty()) continue;
+							if (!results[i].gamRecord.empty()) { records[bi][i].swap(results[i].gamRecord); continue; } // made on the device
 							records[bi][i] = gcout::gamRecordDirect(h->graph, batch[i].name, batch[i].sequence, results[i].alignments, level, enc);
 						}
 					}

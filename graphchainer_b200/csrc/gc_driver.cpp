@@ -248,6 +248,7 @@ int main(int argc, char** argv)
 		gcgpu_ctx* ctx = nullptr;
 		if (gcgpu_create(params.firstDevice + d % params.gpus, &gg, &gp, &ctx) != GCGPU_OK) { std::cerr << "gcgpu_create(device " << params.firstDevice + d << ") failed: " << gcgpu_last_error() << std::endl; return 1; }
 		if (gcUploadMinimizerIndex(ctx, graph) != GCGPU_OK) { std::cerr << "gcgpu_set_minimizer_index failed: " << gcgpu_last_error() << std::endl; return 1; }
+		if (gcUploadNodeNames(ctx, graph) != GCGPU_OK) { std::cerr << "gcgpu_set_node_names failed: " << gcgpu_last_error() << std::endl; return 1; }
 		ctxs.push_back(ctx);
 	}
 
@@ -296,6 +297,8 @@ int main(int argc, char** argv)
 		// the batches in flight together hold ~2.25x the host threads: a batch waiting for its kernels leaves its threads asleep
 		omp_set_num_threads(std::min<int>((int)params.threads, std::max<int>(1, ((int)params.threads * 9 + 4 * numWorkers - 1) / (4 * numWorkers))));
 		GcPipeline pipeline(graph, ctxs[d], params.pipe);
+		// GAM only, at the driver's own compression level: the records of the whole-read alignments are made on the device
+		pipeline.setGamOnDevice(params.outGam != "" && params.outJson == "" && params.outGaf == "" && params.gzipLevel == 1);
 		std::vector<GcRead> batch;
 		std::vector<GcReadResult> results;
 		while (nextBatch(batch))
@@ -311,7 +314,7 @@ int main(int argc, char** argv)
 				for (size_t r = 0; r < batch.size(); r++)
 				{
 					if (results[r].alignments.empty()) continue;
-					if (params.outGam != "") gamRecords[r] = gcout::gamRecordDirect(graph, batch[r].name, batch[r].sequence, results[r].alignments, params.gzipLevel, enc);
+					if (params.outGam != "") { if (!results[r].gamRecord.empty()) gamRecords[r].swap(results[r].gamRecord); else gamRecords[r] = gcout::gamRecordDirect(graph, batch[r].name, batch[r].sequence, results[r].alignments, params.gzipLevel, enc); }
 					if (params.outJson != "")
 						for (const GcAlnItem& item : results[r].alignments) { jsonRecords[r] += gcout::jsonLine(gcout::toAlignment(graph, batch[r].name, batch[r].sequence, item)); jsonRecords[r] += '\n'; }
 					if (params.outGaf != "")

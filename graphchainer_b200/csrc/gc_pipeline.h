@@ -70,6 +70,7 @@ struct GcReadResult
 	bool broke = false;                // any assertion-class failure (the run reports "Alignment broke with some reads")
 	// the fields of the reference's --short-verbose line (Aligner.cpp:909-915)
 	size_t anchors = 0, chained = 0, pathBp = 0, clcScore = 0, longEditDistance = 0;
+	std::string gamRecord;   // the read's gzip member when the record was made on the device (gamOnDevice); its alignments then carry no tokens
 	int oneNodeOverlapsNow = 0, oneNodeOverlapsAll = 0; // the reference's progress-line counters (Aligner.cpp:747,768-771,792,820)
 	bool hasLong = false;
 	size_t seedsFound = 0, seedsExtended = 0;
@@ -88,6 +89,9 @@ struct GcPipelineParams
 	// written.  The edit path is otherwise only computed where the chain wins (the decision needs the distance only); with this set it
 	// is computed for every read so that the line is the reference's.
 	bool exactProgressLine = false;
+	// the GAM records of the reads whose whole-read alignments are written are encoded and compressed on the device
+	// (gcgpu_encode_gam): GcReadResult::gamRecord.  Set by callers that write GAM only (JSON / GAF need the token streams here).
+	bool gamOnDevice = false;
 	size_t s1FirstRoundSeeds = 1;   // S1 speculation: seeds extended per read in the first round ...
 	size_t s1LaterRoundSeeds = 8;   // ... in the second round ...
 	size_t s1TailRoundSeeds = 32;  // ... and from the third round on: few reads get that far, their rounds cost one extension latency each whatever the item count
@@ -105,6 +109,15 @@ struct GcPipelineStats
 };
 
 // hands the reference's minimizer index (MinimizerSeeder.h:17-29 as flat arrays) to a libgcgpu context
+// GFA segment names of the original nodes, for the GAM records made on the device (gcgpu_encode_gam)
+inline int gcUploadNodeNames(gcgpu_ctx* ctx, const GcHostGraph& g)
+{
+	std::vector<uint32_t> off(g.origNames.size() + 1, 0);
+	std::string chars;
+	for (size_t i = 0; i < g.origNames.size(); i++) { chars += g.origNames[i]; off[i + 1] = (uint32_t)chars.size(); }
+	return gcgpu_set_node_names(ctx, off.data(), chars.data());
+}
+
 inline int gcUploadMinimizerIndex(gcgpu_ctx* ctx, const GcHostGraph& g)
 {
 	gcgpu_minimizer_index mi;
@@ -233,6 +246,7 @@ public:
 	GcPipelineStats stats;
 
 	void alignBatch(const std::vector<GcRead>& reads, std::vector<GcReadResult>& out);
+	void setGamOnDevice(bool on) { params.gamOnDevice = on; }
 
 private:
 	const GcHostGraph& g;
@@ -256,7 +270,7 @@ private:
 		Pinned(const Pinned&) = delete;
 		Pinned& operator=(const Pinned&) = delete;
 	};
-	Pinned charsBuf, seedBuf, cellBuf, extBuf, tokenBuf, opsBuf;
+	Pinned charsBuf, seedBuf, cellBuf, extBuf, tokenBuf, opsBuf, gamBuf;
 	std::vector<std::unique_ptr<Pinned>> coverPool; // seed-coverage masks of the S1 rounds of a batch
 
 	void stats_s1Wasted_add(size_t n) { if (n) { _Pragma("omp atomic") stats.s1Wasted += n; } }
@@ -856,14 +870,74 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		out[r].alignments.clear();
 		out[r].alignments.push_back(std::move(item));
 	}
-	// ---- S7 for the whole-read alignments that are written: mappings and edit runs from the device
+	// ---- S7 for the whole-read alignments that are written.  GAM only: the records themselves come from the device
+	const bool recordsOnDevice = params.gamOnDevice;
+	std::vector<uint8_t> wantTokens(R, 0); // reads whose token streams are fetched to the host
+	bool tokensForSome = false;
+	if (recordsOnDevice)
+	{
+		std::vector<gcgpu_gam_read> gr;
+		std::vector<gcgpu_gam_aln> ga;
+		std::vector<size_t> grRead;
+		std::string names;
+		for (size_t r = 0; r < R; r++)
+		{
+			GcReadResult& res = out[r];
+			if (res.usedChain || longAlns[r].empty()) continue;
+			// the record lists the alignments in the order of the final sort by alignmentStart (Aligner.cpp:1004, the same std::sort call)
+			std::vector<S1Aln> sorted = longAlns[r];
+			std::sort(sorted.begin(), sorted.end(), [](const S1Aln& left, const S1Aln& right) { return left.alignmentStart < right.alignmentStart; });
+			gcgpu_gam_read g1; g1.read = (uint32_t)r; g1.first_aln = (uint32_t)ga.size(); g1.num_alns = (uint32_t)sorted.size(); g1.name_len = (uint32_t)reads[r].name.size(); g1.name_offset = names.size();
+			names += reads[r].name;
+			res.alignments.clear();
+			for (const S1Aln& a : sorted)
+			{
+				gcgpu_gam_aln x; x.pair = a.pair; x.start = (int32_t)a.alignmentStart; x.end = (int32_t)a.alignmentEnd; x.trace_score = a.traceScore;
+				ga.push_back(x);
+				GcAlnItem item; item.traceScore = a.traceScore; item.alignmentScore = a.alignmentScore; item.alignmentStart = a.alignmentStart; item.alignmentEnd = a.alignmentEnd; item.seedGoodness = a.seedGoodness;
+				res.alignments.push_back(std::move(item));
+			}
+			gr.push_back(g1); grRead.push_back(r);
+		}
+		std::vector<uint64_t> memberOff(gr.size() + 1, 0);
+		uint64_t used = 0;
+		if (!gr.empty())
+		{
+			double tDev = wallNow();
+			check(gcgpu_encode_gam(ctx, 0, gr.data(), (uint32_t)gr.size(), ga.data(), (uint32_t)ga.size(), names.data(), names.size(), memberOff.data(), &used), "gcgpu_encode_gam");
+			stats.k1Ms += gcgpu_last_kernel_ms(ctx);
+			gamBuf.ensure(used + 16);
+			check(gcgpu_fetch_gam(ctx, (uint8_t*)gamBuf.p, 0, used), "gcgpu_fetch_gam");
+			devMs += wallNow() - tDev;
+		}
+		std::vector<uint8_t> needHost(R, 0);
+		bool anyHost = false;
+		#pragma omp parallel for schedule(dynamic, 16)
+		for (size_t k = 0; k < gr.size(); k++)
+		{
+			size_t r = grRead[k];
+			if (memberOff[k + 1] > memberOff[k]) out[r].gamRecord.assign((const char*)gamBuf.p + memberOff[k], memberOff[k + 1] - memberOff[k]);
+			else { needHost[r] = 1; _Pragma("omp atomic write") anyHost = true; }
+		}
+		for (size_t r = 0; r < R; r++)
+		{
+			GcReadResult& res = out[r];
+			if (!res.usedChain) res.seedsExtended = res.alignments.empty() ? 0 : longSeedsExtended[r];
+			else res.seedsExtended = perRead[r].last_frag_extended;
+			res.seedsExtended += perRead[r].seeds_extended;
+		}
+		// a record the device could not encode (no complete Huffman code for its statistics): the token path below, for those reads only
+		if (anyHost) { wantTokens = needHost; tokensForSome = true; }
+	}
+	else { tokensForSome = true; for (size_t r = 0; r < R; r++) wantTokens[r] = out[r].usedChain ? 0 : 1; }
+	if (tokensForSome)
 	{
 		std::vector<uint32_t> pairs;
 		std::vector<size_t> firstOfRead(R + 1, 0);
 		for (size_t r = 0; r < R; r++)
 		{
 			firstOfRead[r] = pairs.size();
-			if (!out[r].usedChain) for (const S1Aln& a : longAlns[r]) pairs.push_back(a.pair);
+			if (wantTokens[r]) for (const S1Aln& a : longAlns[r]) pairs.push_back(a.pair);
 		}
 		firstOfRead[R] = pairs.size();
 		std::vector<gcgpu_aln_tokens> meta(pairs.size());
@@ -882,6 +956,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		for (size_t r = 0; r < R; r++)
 		{
 			GcReadResult& res = out[r];
+			if (recordsOnDevice && !wantTokens[r]) continue; // record made on the device (or chained alignment): nothing to fetch
 			if (!res.usedChain)
 			{
 				res.alignments.clear();

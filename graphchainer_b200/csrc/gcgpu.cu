@@ -18,6 +18,7 @@
 #include "gc_k3w.cuh"
 #include "gc_seed.cuh"
 #include "gc_post.cuh"
+#include "gc_gam.cuh"
 #include "gc_host_graph.h"
 #include "gc_post_host.h"
 

@@ -27,11 +27,17 @@ struct GcResident
 	// K3 composition / tokens
 	DevBuf pieces, pathNodes, tokenSlots, tokens, tokenMeta;
 	uint64_t tokensUsed = 0;
+	// GAM records on the device
+	std::vector<int32_t> hostOrigIds;
+	int32_t* d_origIndexOfId = nullptr; uint32_t* d_nameOff = nullptr; uint8_t* d_nameChars = nullptr; GcDeflateTables* d_gamTables = nullptr;
+	bool haveNames = false;
+	DevBuf gamIn, gamWork, gamArena, gamOut;
+	uint64_t gamBytes = 0;
 	void release()
 	{
-		cudaFree(d_nodeIDs); cudaFree(d_nodeOffset); cudaFree(d_revFirst); cudaFree(d_revCount); cudaFree(d_revLast); cudaFree(d_origNodes); cudaFree(d_codeTable);
+		cudaFree(d_nodeIDs); cudaFree(d_nodeOffset); cudaFree(d_revFirst); cudaFree(d_revCount); cudaFree(d_revLast); cudaFree(d_origNodes); cudaFree(d_codeTable); cudaFree(d_origIndexOfId); cudaFree(d_nameOff); cudaFree(d_nameChars); cudaFree(d_gamTables);
 		DevBuf* all[] = { &chars, &reads, &cells, &exts, &brief, &cover, &coverOff, &frags, &kept, &fragOut, &readFrag, &perRead, &counts, &offsets, &anchors, &anchorMeta, &anchorPaths, &readAnchorOff,
-			&chainWork, &chainOut, &chainedMeta, &chainedPaths, &pieces, &pathNodes, &tokenSlots, &tokens, &tokenMeta };
+			&chainWork, &chainOut, &chainedMeta, &chainedPaths, &pieces, &pathNodes, &tokenSlots, &tokens, &tokenMeta, &gamIn, &gamWork, &gamArena, &gamOut };
 		for (DevBuf* b : all) b->release();
 		for (auto& s : sets) { s.traces.release(); s.pairs.release(); }
 	}
@@ -62,6 +68,7 @@ static int residentInitGraph(gcgpu_ctx* ctx, const gcgpu_graph* g)
 	R->pg.nodeIDs = R->d_nodeIDs; R->pg.nodeOffset = R->d_nodeOffset; R->pg.nodeLength = ctx->d_nodeLength; R->pg.nodeSeq = ctx->d_nodeSeq;
 	R->pg.revFirst = R->d_revFirst; R->pg.revCount = R->d_revCount; R->pg.revLast = R->d_revLast; R->pg.origNodes = R->d_origNodes;
 	R->havePost = true;
+	R->hostOrigIds.assign(g->orig_ids, g->orig_ids + g->num_orig);
 	return GCGPU_OK;
 }
 
@@ -898,6 +905,181 @@ extern "C" int gcgpu_fetch_tokens(gcgpu_ctx* ctx, uint32_t* tokens, uint64_t fir
 	if (count == 0) return GCGPU_OK;
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	CUDA_TRY(gcCopy(ctx, tokens, (const uint32_t*)R->tokens.p + first, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	return GCGPU_OK;
+}
+
+// ------------------------------------------------------------------ GAM records on the device (gc_gam.cuh)
+extern "C" int gcgpu_set_node_names(gcgpu_ctx* ctx, const uint32_t* name_offsets, const char* names)
+{
+	GC_NEED_RESIDENT("gcgpu_set_node_names");
+	GcResident* R = ctx->resident;
+	if (!name_offsets || (!names && name_offsets[R->hostOrigIds.size()] > 0)) return setError(GCGPU_ERR_ARG, "gcgpu_set_node_names: null argument");
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	size_t numOrig = R->hostOrigIds.size();
+	int32_t maxId = -1;
+	for (int32_t id : R->hostOrigIds) if (id > maxId) maxId = id;
+	std::vector<int32_t> indexOfId((size_t)maxId + 2, -1);
+	for (size_t o = 0; o < numOrig; o++) if (R->hostOrigIds[o] >= 0) indexOfId[R->hostOrigIds[o]] = (int32_t)o;
+	GcDeflateTables tables; gcBuildGamTables(tables);
+	cudaFree(R->d_origIndexOfId); cudaFree(R->d_nameOff); cudaFree(R->d_nameChars); cudaFree(R->d_gamTables);
+	R->d_origIndexOfId = nullptr; R->d_nameOff = nullptr; R->d_nameChars = nullptr; R->d_gamTables = nullptr;
+	cudaError_t err = cudaSuccess;
+	auto chk = [&err](cudaError_t x) { if (err == cudaSuccess) err = x; };
+	chk(uploadArray(indexOfId.data(), indexOfId.size(), &R->d_origIndexOfId));
+	chk(uploadArray(name_offsets, numOrig + 1, &R->d_nameOff));
+	chk(uploadArray((const uint8_t*)names, (size_t)name_offsets[numOrig] + 1, &R->d_nameChars));
+	chk(uploadArray(&tables, 1, &R->d_gamTables));
+	if (err != cudaSuccess) return setError(err == cudaErrorMemoryAllocation ? GCGPU_ERR_NOMEM : GCGPU_ERR_CUDA, std::string("gcgpu_set_node_names: ") + cudaGetErrorString(err));
+	R->haveNames = true;
+	return GCGPU_OK;
+}
+
+struct GcGamSlot { uint64_t rawOff, gzOff, wsOff; uint32_t rawLen, gzCap; };
+__global__ void gc_gam_alns_kernel(const gcgpu_gam_aln* __restrict__ in, const gcgpu_aln_tokens* __restrict__ meta, uint32_t n, GcGamAln* __restrict__ out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	GcGamAln a; a.tokenOff = meta[i].token_offset; a.numTokens = meta[i].num_tokens; a.start = in[i].start; a.end = in[i].end; a.traceScore = in[i].trace_score; a.matches = meta[i].matches; a.steps = meta[i].steps;
+	out[i] = a;
+}
+// bytes every record needs: the raw record, the gzip member (worst case) and the encoder's workspace
+__global__ void gc_gam_size_kernel(GcNameTable nt, const gcgpu_gam_read* __restrict__ reads, uint32_t n, const GcGamAln* __restrict__ alns, const uint32_t* __restrict__ tokens, uint32_t* __restrict__ rawLen, uint64_t* __restrict__ slotBytes)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	if (i == n) { slotBytes[i] = 0; return; }
+	gcgpu_gam_read rd = reads[i];
+	uint32_t len = gc_gam_record_size(nt, alns + rd.first_aln, rd.num_alns, tokens, rd.name_len);
+	rawLen[i] = len;
+	slotBytes[i] = (((uint64_t)len + 16 + 127) / 128 + ((uint64_t)len * 2 + 1024 + 127) / 128 + (gc_deflate_ws_bytes(len) + 127) / 128) * 128;
+}
+// one thread = one record: proto3 bytes, then the gzip member
+__global__ void __launch_bounds__(64) gc_gam_kernel(GcNameTable nt, const GcDeflateTables* __restrict__ tables, const gcgpu_gam_read* __restrict__ reads, uint32_t n, const GcGamAln* __restrict__ alns, const uint32_t* __restrict__ tokens,
+	const GcReadDesc* __restrict__ readDescs, const uint8_t* __restrict__ chars, const uint8_t* __restrict__ names, const uint32_t* __restrict__ rawLen, const uint64_t* __restrict__ slotOff, uint8_t* arena, uint64_t* __restrict__ memberLen)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	if (i == n) { memberLen[i] = 0; return; }
+	gcgpu_gam_read rd = reads[i];
+	const uint32_t len = rawLen[i];
+	uint8_t* raw = arena + slotOff[i];
+	uint8_t* gz = raw + ((uint64_t)len + 16 + 127) / 128 * 128;
+	const uint32_t gzCap = len * 2 + 1024;
+	uint8_t* wsBase = gz + ((uint64_t)gzCap + 127) / 128 * 128;
+	GcDeflateWs ws; ws.head = (int32_t*)wsBase; ws.tokens = (uint32_t*)(wsBase + ((size_t)4 << GC_DEFLATE_HASH_BITS)); ws.tokenCap = len + 16;
+	uint32_t written = gc_gam_write_record(nt, chars + readDescs[rd.read].charOffset, names + rd.name_offset, rd.name_len, alns + rd.first_aln, rd.num_alns, tokens, raw);
+	uint32_t size = written == len ? gc_gzip_member(*tables, raw, len, ws, gz, gzCap) : 0;
+	memberLen[i] = size;
+}
+__global__ void gc_gam_gather_kernel(const uint64_t* __restrict__ slotOff, const uint32_t* __restrict__ rawLen, const uint64_t* __restrict__ memberLen, const uint64_t* __restrict__ memberOff, uint32_t n, const uint8_t* __restrict__ arena, uint8_t* __restrict__ out)
+{
+	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (w >= n) return;
+	const uint8_t* gz = arena + slotOff[w] + ((uint64_t)rawLen[w] + 16 + 127) / 128 * 128;
+	uint8_t* dst = out + memberOff[w];
+	for (uint64_t k = lane; k < memberLen[w]; k += 32) dst[k] = gz[k];
+}
+
+extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* reads, uint32_t n, const gcgpu_gam_aln* alns, uint32_t num_alns,
+	const char* names, uint64_t name_bytes, uint64_t* member_offsets, uint64_t* bytes_used)
+{
+	GC_NEED_RESIDENT("gcgpu_encode_gam");
+	GcResident* R = ctx->resident;
+	if (!R->haveNames) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: gcgpu_set_node_names was not called");
+	if (set < 0 || set >= GCGPU_TRACE_SETS || (!reads && n) || (!alns && num_alns) || !member_offsets || !bytes_used || (!names && name_bytes)) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: bad argument");
+	*bytes_used = 0; R->gamBytes = 0; member_offsets[0] = 0;
+	ctx->lastKernelMs = 0;
+	if (n == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	GcTraceSet& S = R->sets[set];
+	uint32_t nextAln = 0;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const gcgpu_gam_read& rd = reads[i];
+		if (rd.read >= R->numReads || rd.first_aln != nextAln || rd.num_alns == 0 || (uint64_t)rd.first_aln + rd.num_alns > num_alns || rd.name_offset + rd.name_len > name_bytes) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: read " + std::to_string(i) + " out of range");
+		nextAln += rd.num_alns;
+	}
+	if (nextAln != num_alns) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: alignments outside the reads");
+	std::vector<uint32_t> pairs(num_alns);
+	for (uint32_t k = 0; k < num_alns; k++)
+	{
+		if (alns[k].pair >= S.numPairs || alns[k].start < 0 || alns[k].end <= alns[k].start) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: alignment " + std::to_string(k) + " out of range");
+		pairs[k] = alns[k].pair;
+	}
+	for (uint32_t i = 0; i < n; i++) for (uint32_t k = 0; k < reads[i].num_alns; k++) if (alns[reads[i].first_aln + k].end > R->hostReads[reads[i].read].len) return setError(GCGPU_ERR_ARG, "gcgpu_encode_gam: alignment beyond its read");
+	// ---- inputs
+	size_t oReads = 0, oAlns = alignUp((size_t)n * sizeof(gcgpu_gam_read), 128), oPairs = alignUp(oAlns + (size_t)num_alns * sizeof(gcgpu_gam_aln), 128), oNames = alignUp(oPairs + (size_t)num_alns * 4, 128), inEnd = oNames + name_bytes + 16;
+	CUDA_TRY(R->gamIn.ensure(inEnd));
+	uint8_t* I = (uint8_t*)R->gamIn.p;
+	CUDA_TRY(gcCopy(ctx, I + oReads, reads, (size_t)n * sizeof(gcgpu_gam_read), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, I + oAlns, alns, (size_t)num_alns * sizeof(gcgpu_gam_aln), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(gcCopy(ctx, I + oPairs, pairs.data(), (size_t)num_alns * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (name_bytes) CUDA_TRY(gcCopy(ctx, I + oNames, names, name_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	// ---- work arrays: token counts / offsets / meta | GcGamAln | rawLen | slot bytes / offsets | member lengths / offsets
+	size_t oCnt = 0, oOffs = alignUp(oCnt + ((size_t)num_alns + 1) * 8, 128), oMeta = alignUp(oOffs + ((size_t)num_alns + 1) * 8, 128), oFlags = alignUp(oMeta + (size_t)num_alns * sizeof(gcgpu_aln_tokens), 128);
+	size_t oGAln = alignUp(oFlags + num_alns + 16, 128), oRaw = alignUp(oGAln + (size_t)num_alns * sizeof(GcGamAln), 128), oSlotB = alignUp(oRaw + (size_t)n * 4, 128), oSlotO = alignUp(oSlotB + ((size_t)n + 1) * 8, 128);
+	size_t oMemL = alignUp(oSlotO + ((size_t)n + 1) * 8, 128), oMemO = alignUp(oMemL + ((size_t)n + 1) * 8, 128), workEnd = oMemO + ((size_t)n + 1) * 8;
+	CUDA_TRY(R->gamWork.ensure(workEnd));
+	uint8_t* W = (uint8_t*)R->gamWork.p;
+	uint64_t* dCnt = (uint64_t*)(W + oCnt); uint64_t* dOffs = (uint64_t*)(W + oOffs); gcgpu_aln_tokens* dMeta = (gcgpu_aln_tokens*)(W + oMeta); uint8_t* dFlags = W + oFlags;
+	GcGamAln* dGAln = (GcGamAln*)(W + oGAln); uint32_t* dRawLen = (uint32_t*)(W + oRaw); uint64_t* dSlotB = (uint64_t*)(W + oSlotB); uint64_t* dSlotO = (uint64_t*)(W + oSlotO);
+	uint64_t* dMemL = (uint64_t*)(W + oMemL); uint64_t* dMemO = (uint64_t*)(W + oMemO);
+	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+	// ---- edit-run tokens of the alignments (as gcgpu_encode_alignments)
+	gc_tokens_kernel<false><<<num_alns + 1, GC_TOKEN_THREADS, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(I + oPairs), num_alns, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
+		nullptr, nullptr, dCnt, dFlags, nullptr);
+	ctx->launches++;
+	int rc = scanU64(ctx, dCnt, dOffs, num_alns); if (rc != GCGPU_OK) return rc;
+	CUDA_TRY(cudaGetLastError());
+	uint64_t totalTokens = 0;
+	CUDA_TRY(gcCopy(ctx, &totalTokens, dOffs + num_alns, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	CUDA_TRY(R->tokens.ensure(totalTokens * 4 + 16));
+	gc_tokens_kernel<true><<<num_alns, GC_TOKEN_THREADS, 0, ctx->stream>>>(R->pg, (const GcPair*)S.pairs.p, (const uint64_t*)S.traces.p, (const uint32_t*)(I + oPairs), num_alns, (const GcReadDesc*)R->reads.p, (const uint8_t*)ctx->seqBuf.p,
+		dOffs, (uint32_t*)R->tokens.p, nullptr, dFlags, dMeta);
+	gc_gam_alns_kernel<<<(num_alns + 127) / 128, 128, 0, ctx->stream>>>((const gcgpu_gam_aln*)(I + oAlns), dMeta, num_alns, dGAln);
+	GcNameTable nt; nt.origIndexOfId = R->d_origIndexOfId; nt.nameOff = R->d_nameOff; nt.nameChars = R->d_nameChars;
+	gc_gam_size_kernel<<<(n + 1 + 127) / 128, 128, 0, ctx->stream>>>(nt, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, dRawLen, dSlotB);
+	ctx->launches += 3;
+	rc = scanU64(ctx, dSlotB, dSlotO, n); if (rc != GCGPU_OK) return rc;
+	CUDA_TRY(cudaGetLastError());
+	uint64_t arenaBytes = 0;
+	CUDA_TRY(gcCopy(ctx, &arenaBytes, dSlotO + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	CUDA_TRY(R->gamArena.ensure(arenaBytes + 256));
+	gc_gam_kernel<<<(n + 1 + 63) / 64, 64, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
+		I + oNames, dRawLen, dSlotO, (uint8_t*)R->gamArena.p, dMemL);
+	ctx->launches++;
+	rc = scanU64(ctx, dMemL, dMemO, n); if (rc != GCGPU_OK) return rc;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(gcCopy(ctx, member_offsets, dMemO, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	uint64_t total = member_offsets[n];
+	CUDA_TRY(R->gamOut.ensure(total + 16));
+	gc_gam_gather_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(dSlotO, dRawLen, dMemL, dMemO, n, (const uint8_t*)R->gamArena.p, (uint8_t*)R->gamOut.p);
+	ctx->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+	CUDA_TRY(gcSyncStream(ctx));
+	float ms = 0;
+	CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	ctx->lastKernelMs = ms;
+	GC_TRACE_MS("s7 gam records", n);
+	R->gamBytes = total;
+	*bytes_used = total;
+	return GCGPU_OK;
+}
+
+extern "C" int gcgpu_fetch_gam(gcgpu_ctx* ctx, uint8_t* out, uint64_t first, uint64_t count)
+{
+	GC_NEED_RESIDENT("gcgpu_fetch_gam");
+	GcResident* R = ctx->resident;
+	if (!out && count) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_gam: null argument");
+	if (first + count > R->gamBytes) return setError(GCGPU_ERR_ARG, "gcgpu_fetch_gam: range beyond the members of the last gcgpu_encode_gam call");
+	if (count == 0) return GCGPU_OK;
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	CUDA_TRY(gcCopy(ctx, out, (const uint8_t*)R->gamOut.p + first, count, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	return GCGPU_OK;
 }

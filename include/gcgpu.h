@@ -371,6 +371,30 @@ typedef struct gcgpu_aln_tokens
 	uint32_t reserved;
 } gcgpu_aln_tokens;
 
+/* GAM records on the device (writeGAMToQueue, src/Aligner.cpp:261-281): for every listed read one gzip member holding
+ * varint count + {varint size, vg::Alignment}* of its listed whole-read alignments, in the given order -- the proto3 bytes the
+ * reference's AddAlignment + replaceDigraphNodeIdsWithOriginalNodeIds + SerializeToString produce (sequence = the read's characters
+ * as passed to gcgpu_load_reads).  gcgpu_set_node_names provides the GFA segment names of the original nodes (in the order of
+ * gcgpu_graph.orig_ids).  member_offsets[n + 1]: the member of reads[i] is [member_offsets[i], member_offsets[i + 1]) of the
+ * device buffer gcgpu_fetch_gam copies from; an empty range means this record has to be encoded by the caller. */
+typedef struct gcgpu_gam_aln
+{
+	uint32_t pair;         /* seed extension in the trace set                         */
+	int32_t start, end;    /* AlignmentItem::alignmentStart / alignmentEnd             */
+	int32_t trace_score;   /* vg::Alignment::score                                      */
+} gcgpu_gam_aln;
+typedef struct gcgpu_gam_read
+{
+	uint32_t read;         /* index in the batch of gcgpu_load_reads                   */
+	uint32_t first_aln, num_alns;
+	uint32_t name_len;
+	uint64_t name_offset;  /* the read's name inside `names`                           */
+} gcgpu_gam_read;
+int gcgpu_set_node_names(gcgpu_ctx* ctx, const uint32_t* name_offsets, const char* names);
+int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* reads, uint32_t n, const gcgpu_gam_aln* alns, uint32_t num_alns,
+                     const char* names, uint64_t name_bytes, uint64_t* member_offsets, uint64_t* bytes_used);
+int gcgpu_fetch_gam(gcgpu_ctx* ctx, uint8_t* out, uint64_t first, uint64_t count);
+
 int gcgpu_load_reads(gcgpu_ctx* ctx, const char* chars, uint64_t char_bytes, const gcgpu_read* reads, uint32_t n);
 int gcgpu_set_seed_cells(gcgpu_ctx* ctx, const gcgpu_seed_cell* cells, uint64_t num_cells, const gcgpu_read* reads, uint32_t n);
 int gcgpu_extend_seeds(gcgpu_ctx* ctx, int set, int append, int32_t frag_len, const gcgpu_seed_ext* exts, uint32_t n, gcgpu_pair_brief* brief,

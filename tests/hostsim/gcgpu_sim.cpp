@@ -19,6 +19,7 @@
 #include "../../graphchainer_b200/csrc/gc_seed.cuh"
 #include "../../graphchainer_b200/csrc/gc_post.cuh"
 #include "../../graphchainer_b200/csrc/gc_post_host.h"
+#include "../../graphchainer_b200/csrc/gc_gam.cuh"
 
 struct gcgpu_ctx
 {
@@ -41,6 +42,8 @@ struct gcgpu_ctx
 	std::vector<GcAnchor> anchors; std::vector<gcgpu_chained_anchor> anchorMeta; std::vector<uint32_t> anchorPaths; std::vector<uint64_t> readAnchorOff;
 	std::vector<gcgpu_chained_anchor> chainedMeta; std::vector<uint32_t> chainedPaths;
 	std::vector<uint32_t> tokens;
+	std::vector<char> charsCopy; std::vector<int32_t> origIds, origIndexOfId; std::vector<uint32_t> nameOff; std::vector<uint8_t> nameChars; bool haveNames = false; GcDeflateTables gamTables;
+	std::vector<uint8_t> gamOut;
 	uint64_t h2d = 0, d2h = 0;
 };
 static std::string g_err;
@@ -69,6 +72,7 @@ extern "C" int gcgpu_create(int, const gcgpu_graph* g, const gcgpu_params* p, gc
 		c->pg.nodeIDs = c->nodeIDs.data(); c->pg.nodeOffset = c->nodeOffset.data(); c->pg.nodeLength = g->node_length; c->pg.nodeSeq = g->node_seq;
 		c->pg.revFirst = c->rev.revFirst.data(); c->pg.revCount = c->rev.revCount.data(); c->pg.revLast = c->rev.revLast.data(); c->pg.origNodes = c->origNodes.data();
 		gcBuildCodeTable(c->codeTable);
+		c->origIds.assign(g->orig_ids, g->orig_ids + g->num_orig);
 		c->havePost = true;
 	}
 	*out = c;
@@ -279,6 +283,7 @@ extern "C" int gcgpu_load_reads(gcgpu_ctx* ctx, const char* chars, uint64_t char
 	ctx->cells.clear();
 	for (auto& s : ctx->sets) { s.traces.clear(); s.pairs.clear(); }
 	ctx->seqCopy.assign(2 * char_bytes + 16, 0);
+	ctx->charsCopy.assign(chars, chars + char_bytes);
 	for (uint32_t r = 0; r < n; r++)
 		for (int32_t i = 0; i < reads[r].len; i++)
 		{
@@ -516,6 +521,68 @@ extern "C" int gcgpu_fetch_tokens(gcgpu_ctx* ctx, uint32_t* tokens, uint64_t fir
 	if (first + count > ctx->tokens.size()) { g_err = "gcgpu_fetch_tokens: range"; return GCGPU_ERR_ARG; }
 	if (count) memcpy(tokens, ctx->tokens.data() + first, count * 4);
 	ctx->d2h += count * 4;
+	return 0;
+}
+extern "C" int gcgpu_set_node_names(gcgpu_ctx* ctx, const uint32_t* name_offsets, const char* names)
+{
+	SIM_NEED_POST("gcgpu_set_node_names");
+	size_t numOrig = ctx->origIds.size();
+	int32_t maxId = -1;
+	for (int32_t id : ctx->origIds) if (id > maxId) maxId = id;
+	ctx->origIndexOfId.assign((size_t)maxId + 2, -1);
+	for (size_t o = 0; o < numOrig; o++) if (ctx->origIds[o] >= 0) ctx->origIndexOfId[ctx->origIds[o]] = (int32_t)o;
+	ctx->nameOff.assign(name_offsets, name_offsets + numOrig + 1);
+	ctx->nameChars.assign((const uint8_t*)names, (const uint8_t*)names + name_offsets[numOrig]);
+	ctx->nameChars.push_back(0);
+	gcBuildGamTables(ctx->gamTables);
+	ctx->haveNames = true;
+	return 0;
+}
+extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* reads, uint32_t n, const gcgpu_gam_aln* alns, uint32_t num_alns,
+	const char* names, uint64_t name_bytes, uint64_t* member_offsets, uint64_t* bytes_used)
+{
+	SIM_NEED_POST("gcgpu_encode_gam");
+	if (!ctx->haveNames) { g_err = "gcgpu_encode_gam: gcgpu_set_node_names was not called"; return GCGPU_ERR_ARG; }
+	const gcgpu_ctx::Set& S = ctx->sets[set];
+	// tokens of every alignment (as gcgpu_encode_alignments), then one record per read with the device functions of gc_gam.cuh
+	std::vector<uint32_t> tokens; std::vector<GcGamAln> ga(num_alns);
+	for (uint32_t k = 0; k < num_alns; k++)
+	{
+		if (alns[k].pair >= S.pairs.size()) { g_err = "gcgpu_encode_gam: pair out of range"; return GCGPU_ERR_ARG; }
+		const GcPair& p = S.pairs[alns[k].pair];
+		GcPairTokenSrc src; src.pg = &ctx->pg; src.tr = S.traces.data(); src.p = &p; src.codes = ctx->seqCopy.data() + 2 * ctx->reads[p.read].charOffset;
+		GcTokenCounts c = gc_tokenize(src, gc_pair_size(p), (uint32_t*)nullptr);
+		size_t at = tokens.size();
+		tokens.resize(at + c.tokens);
+		gc_tokenize(src, gc_pair_size(p), tokens.data() + at);
+		ga[k].tokenOff = at; ga[k].numTokens = c.tokens; ga[k].start = alns[k].start; ga[k].end = alns[k].end; ga[k].traceScore = alns[k].trace_score;
+		ga[k].matches = c.matches; ga[k].steps = c.matches + c.mismatches + c.insertions + c.deletions;
+	}
+	GcNameTable nt; nt.origIndexOfId = ctx->origIndexOfId.data(); nt.nameOff = ctx->nameOff.data(); nt.nameChars = ctx->nameChars.data();
+	ctx->gamOut.clear();
+	member_offsets[0] = 0;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const gcgpu_gam_read& rd = reads[i];
+		uint32_t len = gc_gam_record_size(nt, ga.data() + rd.first_aln, rd.num_alns, tokens.data(), rd.name_len);
+		std::vector<uint8_t> raw(len + 16), gz((size_t)len * 2 + 1024), wsBuf(gc_deflate_ws_bytes(len));
+		GcDeflateWs ws; ws.head = (int32_t*)wsBuf.data(); ws.tokens = (uint32_t*)(wsBuf.data() + ((size_t)4 << GC_DEFLATE_HASH_BITS)); ws.tokenCap = len + 16;
+		uint32_t written = gc_gam_write_record(nt, (const uint8_t*)ctx->charsCopy.data() + ctx->reads[rd.read].charOffset, (const uint8_t*)names + rd.name_offset, rd.name_len, ga.data() + rd.first_aln, rd.num_alns, tokens.data(), raw.data());
+		uint32_t size = written == len ? gc_gzip_member(ctx->gamTables, raw.data(), len, ws, gz.data(), (uint32_t)gz.size()) : 0;
+		ctx->gamOut.insert(ctx->gamOut.end(), gz.begin(), gz.begin() + size);
+		member_offsets[i + 1] = ctx->gamOut.size();
+	}
+	*bytes_used = ctx->gamOut.size();
+	ctx->launches += 6;
+	ctx->h2d += (uint64_t)n * sizeof(gcgpu_gam_read) + (uint64_t)num_alns * sizeof(gcgpu_gam_aln) + name_bytes;
+	ctx->d2h += ((uint64_t)n + 1) * 8;
+	return 0;
+}
+extern "C" int gcgpu_fetch_gam(gcgpu_ctx* ctx, uint8_t* out, uint64_t first, uint64_t count)
+{
+	if (first + count > ctx->gamOut.size()) { g_err = "gcgpu_fetch_gam: range"; return GCGPU_ERR_ARG; }
+	if (count) memcpy(out, ctx->gamOut.data() + first, count);
+	ctx->d2h += count;
 	return 0;
 }
 extern "C" void gcgpu_transfer_bytes(gcgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = ctx->h2d; if (d2h) *d2h = ctx->d2h; }
