@@ -1896,6 +1896,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 // (2) pairwise form: every earlier anchor is tested against every later one.  Used for reads whose anchors do not all have the
 //     same length (a caller of gcgpu_chain may pass anything) and when the key fields would overflow; GCGPU_K2_FORCE=pairwise.
 #define GC_K2_THREADS 128
+#define GC_K2_PAIRWISE_MAX 384   // c2: ~145 anchors per 10-kb read -> pairwise (1.3 ms per 839 reads vs 6.4 ms swept); c4 / c5: 1-3 k anchors -> sweep
 #define GC_K2_READ_BITS 18
 #define GC_K2_PATH_BITS 18
 #define GC_K2_TOPO_BITS 28
@@ -1986,7 +1987,8 @@ __global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m,
 		if (a[j].y - a[j].x != a[0].y - a[0].x) sUniform = 0;
 	}
 	__syncthreads();
-	if (SWEEP && sUniform && n > 0)
+	// few anchors: testing every earlier anchor directly is cheaper than the per-anchor tree queries and barriers of the sweep
+	if (SWEEP && sUniform && n > GC_K2_PAIRWISE_MAX)
 	{
 		const int32_t len = a[0].y - a[0].x + 1;
 		// entries of this read in the sorted array
@@ -2096,11 +2098,11 @@ __global__ void __launch_bounds__(GC_K2_THREADS) gc_k2_chain_kernel(GcMpcView m,
 }
 
 // chaining of `total` anchors of `numReads` reads that sit in device memory (dAnchors, dReadOff[numReads + 1])
-static int k2Run(gcgpu_ctx* ctx, const GcAnchor* dAnchors, const uint64_t* dReadOff, uint32_t numReads, uint64_t total,
+static int k2Run(gcgpu_ctx* ctx, const GcAnchor* dAnchors, const uint64_t* dReadOff, uint32_t numReads, uint64_t total, uint64_t maxPerRead,
 	uint32_t* dOrder, int32_t* dScore, int32_t* dPred, uint32_t* dChain, uint32_t* dChainLen, int64_t* dChainScore)
 {
 	const char* force = getenv("GCGPU_K2_FORCE");
-	bool sweep = !(force && !strcmp(force, "pairwise")) && total > 0 && numReads < (1u << GC_K2_READ_BITS) && ctx->totalPaths < (1u << GC_K2_PATH_BITS) && ctx->maxCompNodes < (1u << GC_K2_TOPO_BITS);
+	bool sweep = !(force && !strcmp(force, "pairwise")) && total > 0 && maxPerRead > GC_K2_PAIRWISE_MAX && numReads < (1u << GC_K2_READ_BITS) && ctx->totalPaths < (1u << GC_K2_PATH_BITS) && ctx->maxCompNodes < (1u << GC_K2_TOPO_BITS);
 	GcK2Sweep sw; memset(&sw, 0, sizeof(sw));
 	if (sweep)
 	{
@@ -2166,7 +2168,9 @@ extern "C" int gcgpu_chain(gcgpu_ctx* ctx, const gcgpu_anchor* anchors, const ui
 	CUDA_TRY(gcCopy(ctx, A + offO, read_offsets, ((size_t)num_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	{
-		int krc = k2Run(ctx, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads, total,
+		uint64_t maxPerRead = 0;
+		for (uint32_t r = 0; r < num_reads; r++) maxPerRead = std::max<uint64_t>(maxPerRead, read_offsets[r + 1] - read_offsets[r]);
+		int krc = k2Run(ctx, (const GcAnchor*)(A + offA), (const uint64_t*)(A + offO), num_reads, total, maxPerRead,
 			(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
 		if (krc != GCGPU_OK) return krc;
 	}

@@ -22,7 +22,7 @@ struct GcResident
 	DevBuf exts, brief, cover, coverOff, frags, kept, fragOut, readFrag, perRead, counts, offsets;
 	// anchors of the batch (gcgpu_fragment_anchors) and their chains
 	DevBuf anchors, anchorMeta, anchorPaths, readAnchorOff, chainWork, chainOut, chainedMeta, chainedPaths;
-	uint64_t numAnchors = 0, numAnchorPathNodes = 0, numChained = 0, numChainedPathNodes = 0;
+	uint64_t numAnchors = 0, numAnchorPathNodes = 0, numChained = 0, numChainedPathNodes = 0, maxAnchorsPerRead = 0;
 	uint32_t anchorReads = 0;
 	// K3 composition / tokens
 	DevBuf pieces, pathNodes, tokenSlots, tokens, tokenMeta;
@@ -463,6 +463,8 @@ extern "C" int gcgpu_fragment_anchors(gcgpu_ctx* ctx, int set, int32_t frag_len,
 	CUDA_TRY(gcCopy(ctx, per_read, R->perRead.p, (size_t)num_reads * sizeof(gcgpu_read_anchors), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	R->numAnchors = totals[0]; R->numAnchorPathNodes = totals[1];
+	R->maxAnchorsPerRead = 0;
+	for (uint32_t r = 0; r < num_reads; r++) if (per_read[r].anchors > R->maxAnchorsPerRead) R->maxAnchorsPerRead = per_read[r].anchors;
 	CUDA_TRY(R->anchors.ensure(R->numAnchors * sizeof(GcAnchor) + 16));
 	CUDA_TRY(R->anchorMeta.ensure(R->numAnchors * sizeof(gcgpu_chained_anchor) + 16));
 	CUDA_TRY(R->anchorPaths.ensure(R->numAnchorPathNodes * 4 + 16));
@@ -533,7 +535,7 @@ extern "C" int gcgpu_chain_resident(gcgpu_ctx* ctx, uint32_t num_reads, uint32_t
 	const uint64_t* dReadOff = (const uint64_t*)R->readAnchorOff.p;
 	CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
 	{
-		int krc = k2Run(ctx, (const GcAnchor*)R->anchors.p, dReadOff, num_reads, total,
+		int krc = k2Run(ctx, (const GcAnchor*)R->anchors.p, dReadOff, num_reads, total, R->maxAnchorsPerRead,
 			(uint32_t*)(A + offOrd), (int32_t*)(A + offSc), (int32_t*)(A + offPr), (uint32_t*)(A + offCh), (uint32_t*)(A + offLen), (int64_t*)(A + offScore));
 		if (krc != GCGPU_OK) return krc;
 	}
@@ -954,11 +956,14 @@ __global__ void gc_gam_size_kernel(GcNameTable nt, const gcgpu_gam_read* __restr
 	rawLen[i] = len;
 	slotBytes[i] = (((uint64_t)len + 16 + 127) / 128 + ((uint64_t)len * 2 + 1024 + 127) / 128 + (gc_deflate_ws_bytes(len) + 127) / 128) * 128;
 }
-// one thread = one record: proto3 bytes, then the gzip member
+// one record = one warp of which lane 0 works: the walk of a record is a chain of data-dependent branches (literal or match, code
+// lengths, ...), so 32 records in the lanes of one warp serialise (61 ms per 1587 records); alone in its warp a walk runs at the
+// single-thread rate (~5 ms) and the launch still holds only a dozen warps per SM.
 __global__ void __launch_bounds__(64) gc_gam_kernel(GcNameTable nt, const GcDeflateTables* __restrict__ tables, const gcgpu_gam_read* __restrict__ reads, uint32_t n, const GcGamAln* __restrict__ alns, const uint32_t* __restrict__ tokens,
 	const GcReadDesc* __restrict__ readDescs, const uint8_t* __restrict__ chars, const uint8_t* __restrict__ names, const uint32_t* __restrict__ rawLen, const uint64_t* __restrict__ slotOff, uint8_t* arena, uint64_t* __restrict__ memberLen)
 {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (threadIdx.x & 31) return;
+	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (i > n) return;
 	if (i == n) { memberLen[i] = 0; return; }
 	gcgpu_gam_read rd = reads[i];
@@ -1048,7 +1053,7 @@ extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* r
 	CUDA_TRY(gcCopy(ctx, &arenaBytes, dSlotO + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(R->gamArena.ensure(arenaBytes + 256));
-	gc_gam_kernel<<<(n + 1 + 63) / 64, 64, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
+	gc_gam_kernel<<<(n + 1 + 1) / 2, 64, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
 		I + oNames, dRawLen, dSlotO, (uint8_t*)R->gamArena.p, dMemL);
 	ctx->launches++;
 	rc = scanU64(ctx, dMemL, dMemO, n); if (rc != GCGPU_OK) return rc;
