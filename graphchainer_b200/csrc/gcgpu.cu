@@ -1107,30 +1107,14 @@ __device__ __forceinline__ uint32_t gc_k3w_run_pass(const GcK3wPass& p, GcK3Bloc
 }
 
 #define GC_K3W_NEED_LARGER (-2)
-// CLASS 0: NB in {1,2} (cutoff bands up to ~4000 diagonals); CLASS 1: NB in {3,4,6,8,12,16} (up to ~31.7k)
-template <int CLASS>
-__device__ __forceinline__ int gc_k3w_round_nb(int nb)
-{
-	if (CLASS == 0) return nb <= 1 ? 1 : (nb <= 2 ? 2 : 0);
-	return nb <= 3 ? 3 : nb <= 4 ? 4 : nb <= 6 ? 6 : nb <= 8 ? 8 : nb <= 12 ? 12 : nb <= 16 ? 16 : 0;
-}
-template <int CLASS>
+// the warp form holds one or two blocks per lane (cutoff bands up to ~4000 diagonals); wider bands go to the block form (gc_k3b_*)
+__device__ __forceinline__ int gc_k3w_round_nb(int nb) { return nb <= 1 ? 1 : (nb <= 2 ? 2 : 0); }
 __device__ __forceinline__ uint32_t gc_k3w_dispatch(const GcK3wPass& p, int NB, GcK3Block* blocksOut)
 {
-	if (CLASS == 0) return NB == 1 ? gc_k3w_run_pass<1>(p, blocksOut) : gc_k3w_run_pass<2>(p, blocksOut);
-	switch (NB)
-	{
-		case 3: return gc_k3w_run_pass<3>(p, blocksOut);
-		case 4: return gc_k3w_run_pass<4>(p, blocksOut);
-		case 6: return gc_k3w_run_pass<6>(p, blocksOut);
-		case 8: return gc_k3w_run_pass<8>(p, blocksOut);
-		case 12: return gc_k3w_run_pass<12>(p, blocksOut);
-		default: return gc_k3w_run_pass<16>(p, blocksOut);
-	}
+	return NB == 1 ? gc_k3w_run_pass<1>(p, blocksOut) : gc_k3w_run_pass<2>(p, blocksOut);
 }
 
 // one warp = one edlib NW distance (k doubling of edlib.cpp:193-212 from the item's first cutoff)
-template <int CLASS>
 __global__ void __launch_bounds__(128) gc_k3w_distance_kernel(const uint8_t* __restrict__ seq, const GcK3Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK3Out* out)
 {
 	uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1168,10 +1152,10 @@ __global__ void __launch_bounds__(128) gc_k3w_distance_kernel(const uint8_t* __r
 			if (k >= diff)
 			{
 				int32_t kk = k > mx ? mx : k;
-				int NB = gc_k3w_round_nb<CLASS>(gc_k3w_blocks_per_lane(q, t, kk));
+				int NB = gc_k3w_round_nb(gc_k3w_blocks_per_lane(q, t, kk));
 				if (NB == 0) { o.distance = GC_K3W_NEED_LARGER; o.pad = (uint32_t)k; break; }
 				GcK3wPass p = gc_k3w_make_pass(peq, nb, 0, q, target, 0, 1, t, kk, t - 1, NB);
-				work += gc_k3w_dispatch<CLASS>(p, NB, blocks);
+				work += gc_k3w_dispatch(p, NB, blocks);
 				int32_t v = gc_k3_cell(blocks[(q - 1) >> 6], q - 1);
 				if (v <= kk) { o.distance = v; break; }
 			}
@@ -1671,7 +1655,7 @@ extern "C" int gcgpu_nw(gcgpu_ctx* ctx, const char* seqs, uint64_t seq_bytes, co
 	}
 	if (n > nWide)
 	{
-		gc_k3w_distance_kernel<0><<<(n - nWide + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p + nWide, n - nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
+		gc_k3w_distance_kernel<<<(n - nWide + 3) / 4, 128, 0, ctx->stream>>>((const uint8_t*)ctx->nwSeqBuf.p, (const GcK3Desc*)ctx->descBuf.p + nWide, n - nWide, (uint8_t*)ctx->arena.p, (GcK3Out*)ctx->resBuf.p);
 		ctx->launches++;
 	}
 	if (nWide) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
