@@ -202,12 +202,14 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 		work(0);
 		for (auto& t : threads) t.join();
 	}
-	omp_set_num_threads(callerOmpThreads);
-	if (!error.empty()) return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + error);
+	if (!error.empty()) { omp_set_num_threads(callerOmpThreads); return fail(GCGPU_ERR_INTERNAL, std::string("gcalign_align: ") + error); }
 	auto tCall1 = std::chrono::steady_clock::now();
+	// where every read's record goes in the caller's buffer (input order), then the copies with all host threads (~15 bytes per read base)
 	uint64_t used = 0;
+	std::vector<uint64_t> batchOffset(batches.size() + 1, 0);
 	for (size_t bi = 0; bi < batches.size(); bi++)
 	{
+		batchOffset[bi] = used;
 		uint32_t first = batches[bi].first;
 		for (size_t i = 0; i < allResults[bi].size(); i++)
 		{
@@ -220,13 +222,23 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 				s.gam_offset = used; s.gam_size = records[bi][i].size();
 			}
 			if (stats) { stats->seeds_found += res.seedsFound; if (!res.alignments.empty()) stats->seeds_extended += res.seedsExtended; }
-			if (gam_out && !records[bi][i].empty())
-			{
-				if (used + records[bi][i].size() <= gam_capacity) memcpy(gam_out + used, records[bi][i].data(), records[bi][i].size());
-				used += records[bi][i].size(); // keeps counting past the capacity: on overflow the caller learns the size it needs
-			}
+			used += records[bi][i].size(); // keeps counting past the capacity: on overflow the caller learns the size it needs
 		}
 	}
+	if (gam_out && used <= gam_capacity)
+	{
+		omp_set_num_threads(hostThreads);
+		for (size_t bi = 0; bi < batches.size(); bi++)
+		{
+			const std::vector<std::string>& recs = records[bi];
+			std::vector<uint64_t> at(recs.size());
+			uint64_t o = batchOffset[bi];
+			for (size_t i = 0; i < recs.size(); i++) { at[i] = o; o += recs[i].size(); }
+			#pragma omp parallel for schedule(static)
+			for (size_t i = 0; i < recs.size(); i++) if (!recs[i].empty()) memcpy(gam_out + at[i], recs[i].data(), recs[i].size());
+		}
+	}
+	omp_set_num_threads(callerOmpThreads);
 	if (stats)
 	{
 		stats->s0_ms = total.s0Ms; stats->k1_ms = total.k1Ms; stats->k2_ms = total.k2Ms; stats->k3_ms = total.k3Ms;

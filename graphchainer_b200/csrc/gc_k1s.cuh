@@ -14,6 +14,10 @@
 //             variation graph) finish inside this stage.
 //   stage 2   ONE column loop for the whole warp (BVCommon.h:1118-1161): trip count = the longest node among the lanes,
 //             a lane whose node is shorter idles for the rest.  This loop is where the column steps -- the work -- are.
+//             (Cutting the loop into rounds of 16 columns, so that lanes with short nodes go on while a 64-column node is
+//             finished over four rounds, raises the active lanes per instruction but makes every launch slower -- r03n,
+//             68-74 ms instead of 48-50: a launch lasts as long as its longest item, and that item then pays the
+//             bookkeeping stage of the whole warp four times per long node.)
 // The partial last slice of every item (flattenLastSliceEnd, BVCommon.h:1171-1229) is handled the same way after the
 // main loop: the lanes recompute their slices' nodes in phmap slot order with a shared column loop.
 // The backtrace (BVCommon.h:392-544) has the same two stages: per path node a lookup / crossing stage and a shared
@@ -111,54 +115,87 @@ GC_HD void gc_eq_from_planes(const uint64_t* planes, uint64_t bit, int32_t rows,
 	}
 }
 
-// ------------------------------------------------------------------------------------
-// Forward pass (the lane-per-item twin of gc_k1_forward: same slices, items and Viterbi states, written to the same slab
-// layout).  `have` = this lane has an item; lanes without one only take part in the votes.
-// Returns the index of the last kept slice after removeWronglyAlignedEnd; <= 0 means the extension failed.
-GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, bool have, const uint8_t* seq, int32_t seqLen, uint32_t startNode, uint32_t startOffset,
-	const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, GcK1Result& res)
+// The same lookup for a node expected at or just before index `hint` (an in-neighbour of the node last stored; the node a
+// backtrace steps to): the scan runs from `hint` down to 0 in groups of 8 independent loads, then over the entries after `hint`.
+// A node sits at most once in a slice, so the result is that of gc_find_key.
+GC_HD int32_t gc_find_key_near(const uint32_t* keys, uint32_t n, uint32_t node, uint32_t hint)
 {
-	const uint32_t NONE = 0xFFFFFFFFu;
-	res.status = GC_OK;
-	res.columns = 0;
-	uint32_t itemsUsed = 0;
-	const int32_t numSlices = have ? (seqLen + 63) / 64 : 0;
-	int32_t status = GC_OK;
-	bool running = have && numSlices > 0;
-	// ---- getInitialSliceExactPosition (BVCommon.h:1243-1279)
-	if (have)
+	if (n == 0) return -1;
+	if (hint >= n) hint = n - 1;
+	for (int32_t top = (int32_t)hint; top >= 0; top -= 8)
 	{
-		if (ws.itemCap < 1) { status = GC_OVERFLOW_ITEMS; running = false; }
-		else
+		const int32_t low = top >= 7 ? top - 7 : 0;
+		int32_t found = -1;
+		for (int32_t k = top; k >= low; k--) if ((keys[k] & 0x7FFFFFFFu) == node) found = k;
+		if (found >= 0) return found;
+	}
+	for (uint32_t base = hint + 1; base < n; base += 8)
+	{
+		uint32_t end = base + 8 < n ? base + 8 : n;
+		int32_t found = -1;
+		for (uint32_t k = base; k < end; k++) if ((keys[k] & 0x7FFFFFFFu) == node) found = (int32_t)k;
+		if (found >= 0) return found;
+	}
+	return -1;
+}
+
+// The warp's shared column loop, one window of 16 columns: every lane with `mine` computes columns [pos0, pos0 + 16) of
+// its node (pos0 a multiple of 16; column 0 is the start column, the node ends at len), one getNextSlice step each
+// (BVCommon.h:1118-1161).  The trip count is the longest window among the lanes.  The 16 bases of a window are one 32-bit
+// word, and the unrolled body leaves one uniform exit test and one lane predicate per column (r03f: the loop head and the
+// per-column base arithmetic of the rolled form were 21 % of the forward kernel's instructions).
+// STORE: the columns are also written to `cols` (recalcNodeWordslice, BVCommon.h:828-852).
+template <bool FLAT, bool STORE>
+GC_HD void gc_k1s_columns16(GcColumnRun& run, bool mine, uint32_t pos0, uint32_t len, uint32_t forceUntil, GcColVV* cols)
+{
+	const uint32_t myTrip = mine ? (len - pos0 < 16u ? len - pos0 : 16u) : 0u;
+	const uint32_t trip = GC_WARP_MAX(myTrip);
+	const uint32_t bases = gc_col_bases(run, pos0 & 48u);
+	#pragma unroll
+	for (uint32_t u = 0; u < 16; u++)
+	{
+		if (u >= trip) break;
+		const uint32_t pos = pos0 + u;
+		if (u < myTrip && pos >= 1)
 		{
-			GcSliceMeta& m = ws.slices[0];
-			m.correctLogOdds = vt.initialCorrect;
-			m.falseLogOdds = vt.initialFalse;
-			m.correctFromCorrect = 0;
-			m.falseFromCorrect = 0;
-			m.minScore = 0;
-			m.minScoreNode = startNode;
-			m.minScoreNodeOffset = startOffset;
-			m.bandwidth = 1;
-			m.firstItem = 0;
-			m.numItems = 1;
-			GcNodeItem& it = ws.items[0];
-			uint32_t len0 = g.nodeLength[startNode];
-			it.startVP = 0; it.startVN = 0; it.startScore = (int32_t)startOffset;
-			it.endVP = 0; it.endVN = 0; it.endScore = (int32_t)len0 - 1 - (int32_t)startOffset;
-			it.minScore = 0;
-			it.nodeAndFlag = startNode;
-			uint64_t upTo = startOffset >= 63 ? ~0ULL : ((2ULL << startOffset) - 1);
-			uint64_t lenMask = len0 >= 64 ? ~0ULL : ((1ULL << len0) - 1);
-			it.HN = upTo & ~1ULL;
-			it.HP = lenMask & ~upTo;
-			ws.keys[0] = startNode;
-			GcItemAux a; a.comp = g.componentNumber[startNode]; a.minScore = 0; a.endScore = it.endScore; a.linIdx = -2; // slice -1 seeds slice 0 without the skip tests (j == 0)
-			ws.aux[0] = a;
-			itemsUsed = 1;
+			gc_col_step<FLAT>(run, pos, (int)((bases >> (2 * u)) & 3), forceUntil >= pos);
+			if (STORE) { cols[pos].VP = run.ws.VP; cols[pos].VN = run.ws.VN; }
 		}
 	}
+}
+// all the columns of the nodes in hand (trip count = the longest node)
+template <bool FLAT, bool STORE>
+GC_HD void gc_k1s_columns(GcColumnRun& run, bool mine, uint32_t len, uint32_t forceUntil, GcColVV* cols)
+{
+	const uint32_t maxLen = GC_WARP_MAX(mine ? len : 0u);
+	for (uint32_t pos0 = 0; pos0 < maxLen; pos0 += 16) gc_k1s_columns16<FLAT, STORE>(run, mine && pos0 < len, pos0, len, forceUntil, cols);
+}
+
+// ------------------------------------------------------------------------------------
+// Forward pass (the lane-per-item twin of gc_k1_forward: same slices, items and Viterbi states, written to the same slab
+// layout).  A lane works through items one after the other: when its item ends -- many extensions are cut after a few
+// slices -- it takes the next one from `src`, so the lanes of a warp stay busy until the launch runs out of items
+// (r03f, fixed 32 items per warp: 18.6 of 32 lanes still had an item on average).
+//   src.next(item, ws)   the lane's next work item and its slab (false: none left)
+//   src.done(res, last)  its result; last = index of the last kept slice after removeWronglyAlignedEnd, <= 0: the extension failed
+struct GcK1SItem
+{
+	const uint8_t* seq;
+	int32_t seqLen;
+	uint32_t startNode, startOffset;
+	uint64_t planeBit;     // where the item's sequence starts in the bit planes
+};
+template <class Source>
+GC_HD void gc_k1s_forward_items(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, const uint64_t* planes, GcK1SWorkspace& ws, Source& src)
+{
+	const uint32_t NONE = 0xFFFFFFFFu;
 	const int32_t bandwidth = prm.bandwidth;
+	bool have = false, exhausted = false;
+	GcK1SItem it; it.seq = nullptr; it.seqLen = 0; it.startNode = 0; it.startOffset = 0; it.planeBit = 0;
+	uint32_t itemsUsed = 0;
+	int32_t numSlices = 0;
+	int32_t status = GC_OK;
+	bool running = false;
 	int32_t lastSlice = 0;
 	uint64_t columns = 0;
 	// ---- the slice being filled and the one before it (the last KEPT slice: its extent and scores stay in registers)
@@ -173,6 +210,9 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 	int32_t sliceMinScore = 0, currentMinScoreAtEndRow = 0;
 	uint32_t sliceMinNode = NONE, sliceMinOffset = NONE;
 	uint64_t lastKey = ~0ULL;
+	// The previous slice's items lie in queue-key order (they were stored as they were popped) and the pops of this slice come
+	// in the same order: one cursor walks the previous slice once per slice instead of one search per pop
+	uint32_t prevCursor = 0; uint64_t prevCursorKey = ~0ULL;
 	bool needFlatten = false;
 	// ---- the node in hand
 	bool pending = false;   // computed, not stored yet
@@ -192,6 +232,57 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 	run.ws = w; run.eq[0] = run.eq[1] = run.eq[2] = run.eq[3] = 0; run.prevHP = run.prevHN = run.HP = run.HN = 0; run.chunk0 = run.chunk1 = 0; run.minScore = 0; run.minOffset = 0; run.flatMask = 0;
 	while (true)
 	{
+		// ================= stage 0: a lane without an item takes the next one =================
+		if (!have && !exhausted)
+		{
+			if (!src.next(it, ws)) exhausted = true;
+			else
+			{
+				have = true;
+				status = GC_OK;
+				columns = 0;
+				itemsUsed = 0;
+				numSlices = (it.seqLen + 63) / 64;
+				running = numSlices > 0;
+				// ---- getInitialSliceExactPosition (BVCommon.h:1243-1279)
+				if (ws.itemCap < 1) { status = GC_OVERFLOW_ITEMS; running = false; }
+				else
+				{
+					GcSliceMeta& m = ws.slices[0];
+					m.correctLogOdds = vt.initialCorrect;
+					m.falseLogOdds = vt.initialFalse;
+					m.correctFromCorrect = 0;
+					m.falseFromCorrect = 0;
+					m.minScore = 0;
+					m.minScoreNode = it.startNode;
+					m.minScoreNodeOffset = it.startOffset;
+					m.bandwidth = 1;
+					m.firstItem = 0;
+					m.numItems = 1;
+					GcNodeItem& first = ws.items[0];
+					uint32_t len0 = g.nodeLength[it.startNode];
+					first.startVP = 0; first.startVN = 0; first.startScore = (int32_t)it.startOffset;
+					first.endVP = 0; first.endVN = 0; first.endScore = (int32_t)len0 - 1 - (int32_t)it.startOffset;
+					first.minScore = 0;
+					first.nodeAndFlag = it.startNode;
+					uint64_t upTo = it.startOffset >= 63 ? ~0ULL : ((2ULL << it.startOffset) - 1);
+					uint64_t lenMask = len0 >= 64 ? ~0ULL : ((1ULL << len0) - 1);
+					first.HN = upTo & ~1ULL;
+					first.HP = lenMask & ~upTo;
+					ws.keys[0] = it.startNode;
+					GcItemAux a; a.comp = g.componentNumber[it.startNode]; a.minScore = 0; a.endScore = first.endScore; a.linIdx = -2; // slice -1 seeds slice 0 without the skip tests (j == 0)
+					ws.aux[0] = a;
+					itemsUsed = 1;
+				}
+				lastSlice = 0;
+				slice = -1; j = 0;
+				keptFirst = 0; keptN = 1; keptMin = 0; keptBandwidth = 1;
+				keptCorrect = vt.initialCorrect; keptFalse = vt.initialFalse;
+				heapSize = 0;
+				needFlatten = false; pending = false; needCols = false;
+			}
+		}
+		if (!GC_WARP_ANY(have)) break; // no lane has an item and none could get one
 		// ================= stage 1: one bookkeeping step of every lane that has no multi-column node in hand =================
 		if (running && !needCols)
 		{
@@ -248,7 +339,7 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 				{
 					// ---- close the slice (Banded.h:589-607)
 					if (sliceMinNode == NONE) { status = GC_INTERNAL; running = false; go = false; }
-					else if (j + 64 > seqLen) { needFlatten = true; running = false; go = false; } // partial last slice: flattened below
+					else if (j + 64 > it.seqLen) { needFlatten = true; running = false; go = false; } // partial last slice: flattened below
 					else
 					{
 						GcSliceMeta pm; pm.correctLogOdds = keptCorrect; pm.falseLogOdds = keptFalse;
@@ -280,8 +371,8 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 					prevN = keptN;
 					previousMinScore = keptMin;
 					previousQuitScore = keptMin + keptBandwidth;
-					if (planes) gc_eq_from_planes(planes, planeBit + (uint64_t)j, seqLen - j, eq);
-					else gc_eq_vector(seq, seqLen, j, eq);
+					if (planes) gc_eq_from_planes(planes, it.planeBit + (uint64_t)j, it.seqLen - j, eq);
+					else gc_eq_vector(it.seq, it.seqLen, j, eq);
 					const uint32_t* prevKeys = ws.keys + prevFirst;
 					const GcItemAux* prevAux = ws.aux + prevFirst;
 					for (uint32_t k = 0; k < prevN; k++)
@@ -300,6 +391,8 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 					sliceMinNode = NONE; sliceMinOffset = NONE;
 					currentMinScoreAtEndRow = sliceMinScore;
 					lastKey = ~0ULL;
+					prevCursor = 0;
+					prevCursorKey = prevN > 0 ? (((uint64_t)prevAux[0].comp << 32) | (prevKeys[0] & 0x7FFFFFFFu)) : ~0ULL;
 					if (heapSize == 0) go = false; // nothing seeded: closed (as an internal error) in the next step
 				}
 			}
@@ -307,6 +400,7 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 			{
 				// ---- pop the next node, merge its incoming columns (BVCommon.h:903-964)
 				uint64_t key = gc_sheap_pop(ws.heap, heapSize);
+				while (key == lastKey && heapSize > 0) key = gc_sheap_pop(ws.heap, heapSize); // queued again by another in-neighbour or by the previous slice (a third of the pops, r03f)
 				if (key != lastKey)
 				{
 					lastKey = key;
@@ -315,7 +409,12 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 					const GcNodeRec rec = g.nodeRec[node];
 					const uint32_t* prevKeys = ws.keys + prevFirst;
 					const uint32_t* curKeys = ws.keys + firstItem;
-					const int32_t pi = gc_find_key(prevKeys, prevN, node);
+					while (prevCursorKey < key)
+					{
+						prevCursor++;
+						prevCursorKey = prevCursor < prevN ? (((uint64_t)ws.aux[prevFirst + prevCursor].comp << 32) | (prevKeys[prevCursor] & 0x7FFFFFFFu)) : ~0ULL;
+					}
+					const int32_t pi = prevCursorKey == key ? (int32_t)prevCursor : -1;
 					uint32_t inCount = rec.inCount, oc = rec.outCount;
 					if (inCount == 255) inCount = g.inStart[node + 1] - g.inStart[node];
 					if (oc == 255) oc = g.outStart[node + 1] - g.outStart[node];
@@ -326,8 +425,8 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 					len = rec.len;
 					// in-neighbours: where they sit in the slice being filled (the first two looked up and loaded together)
 					const uint32_t in1 = inCount > 1 ? g.inNbr[rec.inStart + 1] : 0;
-					const int32_t ci0 = inCount > 0 ? gc_find_key(curKeys, curN, rec.firstIn) : -1;
-					const int32_t ci1 = inCount > 1 ? gc_find_key(curKeys, curN, in1) : -1;
+					const int32_t ci0 = inCount > 0 ? gc_find_key_near(curKeys, curN, rec.firstIn, curN) : -1;
+					const int32_t ci1 = inCount > 1 ? gc_find_key_near(curKeys, curN, in1, curN) : -1;
 					const bool use0 = ci0 >= 0 && (curKeys[ci0] & 0x80000000u), use1 = ci1 >= 0 && (curKeys[ci1] & 0x80000000u);
 					GcWord inc0, inc1; inc0.VP = inc0.VN = 0; inc0.scoreEnd = 0; inc1 = inc0;
 					if (use0) inc0 = gc_item_end(ws.items[firstItem + ci0]);
@@ -363,7 +462,7 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 						else if (e == 1) { if (!use1) continue; inc = inc1; }
 						else
 						{
-							int32_t ci = gc_find_key(curKeys, curN, g.inNbr[rec.inStart + e]);
+							int32_t ci = gc_find_key_near(curKeys, curN, g.inNbr[rec.inStart + e], curN);
 							if (ci < 0 || !(curKeys[ci] & 0x80000000u)) continue;
 							inc = gc_item_end(ws.items[firstItem + ci]);
 						}
@@ -392,8 +491,8 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 					{
 						if (prevExists && gc_sbs(w) > prevStart)
 						{
-							GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
-							w = gc_merge(w, src);
+							GcWord src2; src2.VP = ~0ULL; src2.VN = 0; src2.scoreEnd = prevStart + 64;
+							w = gc_merge(w, src2);
 						}
 						if (itemsUsed >= ws.itemCap) { status = GC_OVERFLOW_ITEMS; running = false; }
 						else
@@ -411,116 +510,130 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 				}
 			}
 		}
-		if (!GC_WARP_ANY(running)) break;
 		// ================= stage 2: the column steps of the nodes in hand, one loop for the warp =================
+		gc_k1s_columns<false, false>(run, needCols, len, forceUntil, nullptr);
+		if (needCols)
 		{
-			const uint32_t maxLen = GC_WARP_MAX(needCols ? len : 0u);
-			uint32_t bases = 0;
-			for (uint32_t pos = 1; pos < maxLen; pos++)
-			{
-				if (pos == 1 || (pos & 15u) == 0) bases = gc_col_bases(run, pos);
-				if (needCols && pos < len) gc_col_step<false>(run, pos, (int)(bases & 3), forceUntil >= pos);
-				bases >>= 2;
-			}
-			if (needCols)
-			{
-				gc_cols_finish(run, len);
-				endW = run.ws; HP = run.HP; HN = run.HN; nodeMin = run.minScore; nodeMinOffset = run.minOffset;
-				needCols = false;
-			}
+			gc_cols_finish(run, len);
+			endW = run.ws; HP = run.HP; HN = run.HN; nodeMin = run.minScore; nodeMinOffset = run.minOffset;
+			needCols = false;
 		}
-	}
-	// ---- flattenLastSliceEnd (BVCommon.h:1171-1229) for a partial last slice, then close it.  The reference recomputes every
-	// node of the slice, flattens each column (flattenWordSlice, BVCommon.h:265-273) and keeps the first strict minimum in the
-	// iteration order of its phmap node map; the column run tracks exactly that minimum, so no column is stored.
-	{
-		bool flat = needFlatten && status == GC_OK;
-		uint32_t capacity = 0, slot = 0;
-		uint64_t flatMask = 0;
-		if (flat)
+		// ================= stage 3: lanes whose item ended in a partial last slice =================
+		// flattenLastSliceEnd (BVCommon.h:1171-1229), then close the slice.  The reference recomputes every node of the slice,
+		// flattens each column (flattenWordSlice, BVCommon.h:265-273) and keeps the first strict minimum in the iteration order
+		// of its phmap node map; the column run tracks exactly that minimum, so no column is stored.
+		const bool wantFlat = have && !running && needFlatten && status == GC_OK;
+		if (GC_WARP_ANY(wantFlat))
 		{
-			uint32_t rows = (uint32_t)(seqLen - j);
-			flatMask = ~0ULL << rows;
-			GcItemNodeKey keyFn; keyFn.items = ws.items + firstItem;
-			if (!gc_phmap_order_keys(keyFn, curN, prevN, ws.scratch, ws.scratchCap, &capacity)) { status = GC_OVERFLOW_HEAP; flat = false; }
-			sliceMinScore = GC_INT_MAX;
-			sliceMinNode = NONE;
-			sliceMinOffset = NONE;
-		}
-		bool flatCols = false;
-		while (GC_WARP_ANY(flat))
-		{
-			// next occupied slot; one-column nodes are finished here
+			bool flat = wantFlat;
+			uint32_t capacity = 0, slot = 0;
+			uint64_t flatMask = 0;
 			if (flat)
 			{
-				while (slot < capacity && ws.scratch[slot] == NONE) slot++;
-				if (slot >= capacity) flat = false;
+				uint32_t rows = (uint32_t)(it.seqLen - j);
+				flatMask = ~0ULL << rows;
+				GcItemNodeKey keyFn; keyFn.items = ws.items + firstItem;
+				if (!gc_phmap_order_keys(keyFn, curN, prevN, ws.scratch, ws.scratchCap, &capacity)) { status = GC_OVERFLOW_HEAP; flat = false; }
+				sliceMinScore = GC_INT_MAX;
+				sliceMinNode = NONE;
+				sliceMinOffset = NONE;
 			}
-			if (flat)
+			bool flatCols = false;
+			while (GC_WARP_ANY(flat))
 			{
-				const GcNodeItem& it = ws.items[firstItem + ws.scratch[slot]];
-				slot++;
-				node = gc_item_node(it);
-				len = g.nodeLength[node];
-				columns += len;
-				const int32_t pi = gc_find_key(ws.keys + prevFirst, prevN, node);
-				const bool prevExists = pi >= 0;
-				int32_t prevStart = 0; uint64_t prevHP = ~0ULL, prevHN = 0;
-				if (prevExists) { const GcNodeItem& p = ws.items[prevFirst + pi]; prevStart = p.startScore; prevHP = p.HP; prevHN = p.HN; }
-				GcWord sw = gc_item_start(it);
-				if (prevExists && gc_sbs(sw) > prevStart)
+				// next occupied slot; one-column nodes are finished here
+				if (flat)
 				{
-					GcWord src; src.VP = ~0ULL; src.VN = 0; src.scoreEnd = prevStart + 64;
-					sw = gc_merge(sw, src);
+					while (slot < capacity && ws.scratch[slot] == NONE) slot++;
+					if (slot >= capacity) flat = false;
 				}
-				forceUntil = gc_cols_prepare(g, node, len, eq, sw, prevExists, prevStart, prevHP, prevHN, flatMask, run);
-				if (len > 1) flatCols = true;
-				else if (run.minScore < sliceMinScore) { sliceMinScore = run.minScore; sliceMinNode = node; sliceMinOffset = 0; }
+				if (flat)
+				{
+					const GcNodeItem& fi = ws.items[firstItem + ws.scratch[slot]];
+					slot++;
+					node = gc_item_node(fi);
+					len = g.nodeLength[node];
+					columns += len;
+					const int32_t pi = gc_find_key(ws.keys + prevFirst, prevN, node);
+					const bool prevExists = pi >= 0;
+					int32_t prevStart = 0; uint64_t prevHP = ~0ULL, prevHN = 0;
+					if (prevExists) { const GcNodeItem& p = ws.items[prevFirst + pi]; prevStart = p.startScore; prevHP = p.HP; prevHN = p.HN; }
+					GcWord sw = gc_item_start(fi);
+					if (prevExists && gc_sbs(sw) > prevStart)
+					{
+						GcWord src2; src2.VP = ~0ULL; src2.VN = 0; src2.scoreEnd = prevStart + 64;
+						sw = gc_merge(sw, src2);
+					}
+					forceUntil = gc_cols_prepare(g, node, len, eq, sw, prevExists, prevStart, prevHP, prevHN, flatMask, run);
+					if (len > 1) flatCols = true;
+					else if (run.minScore < sliceMinScore) { sliceMinScore = run.minScore; sliceMinNode = node; sliceMinOffset = 0; }
+				}
+				gc_k1s_columns<true, false>(run, flatCols, len, forceUntil, nullptr);
+				if (flatCols)
+				{
+					if (run.minScore < sliceMinScore) { sliceMinScore = run.minScore; sliceMinNode = node; sliceMinOffset = run.minOffset; }
+					flatCols = false;
+				}
 			}
-			const uint32_t maxLen = GC_WARP_MAX(flatCols ? len : 0u);
-			uint32_t bases = 0;
-			for (uint32_t pos = 1; pos < maxLen; pos++)
+			if (wantFlat && status == GC_OK)
 			{
-				if (pos == 1 || (pos & 15u) == 0) bases = gc_col_bases(run, pos);
-				if (flatCols && pos < len) gc_col_step<true>(run, pos, (int)(bases & 3), forceUntil >= pos);
-				bases >>= 2;
-			}
-			if (flatCols)
-			{
-				if (run.minScore < sliceMinScore) { sliceMinScore = run.minScore; sliceMinNode = node; sliceMinOffset = run.minOffset; }
-				flatCols = false;
+				const GcSliceMeta& pm = ws.slices[lastSlice];
+				GcSliceMeta& nm = ws.slices[lastSlice + 1];
+				nm.minScore = sliceMinScore;
+				nm.minScoreNode = sliceMinNode;
+				nm.minScoreNodeOffset = sliceMinOffset;
+				nm.bandwidth = bandwidth;
+				nm.firstItem = firstItem;
+				nm.numItems = curN;
+				gc_viterbi_next(vt, pm, sliceMinScore - previousMinScore, nm);
+				if (nm.correctFromCorrect) lastSlice++;
 			}
 		}
-		if (needFlatten && status == GC_OK)
+		// ================= the item is over: removeWronglyAlignedEnd (BVCommon.h:1231-1241), hand the result over =================
+		if (have && !running)
 		{
-			const GcSliceMeta& pm = ws.slices[lastSlice];
-			GcSliceMeta& nm = ws.slices[lastSlice + 1];
-			nm.minScore = sliceMinScore;
-			nm.minScoreNode = sliceMinNode;
-			nm.minScoreNodeOffset = sliceMinOffset;
-			nm.bandwidth = bandwidth;
-			nm.firstItem = firstItem;
-			nm.numItems = curN;
-			gc_viterbi_next(vt, pm, sliceMinScore - previousMinScore, nm);
-			if (nm.correctFromCorrect) lastSlice++;
+			GcK1Result res;
+			res.score = GC_INT_MAX; res.traceLen = 0;
+			res.columns = columns;
+			res.status = status;
+			res.itemsUsed = itemsUsed;
+			int32_t last = 0;
+			if (status == GC_OK)
+			{
+				int32_t count = lastSlice + 1;
+				bool currentlyCorrect = ws.slices[count - 1].correctLogOdds > ws.slices[count - 1].falseLogOdds;
+				while (!currentlyCorrect)
+				{
+					currentlyCorrect = ws.slices[count - 1].falseFromCorrect;
+					count--;
+					if (count == 0) break;
+				}
+				last = count - 1;
+			}
+			src.done(res, last);
+			have = false;
 		}
 	}
-	res.columns = columns;
-	res.status = status;
-	res.itemsUsed = itemsUsed;
-	if (status != GC_OK || !have) return 0;
-	// ---- removeWronglyAlignedEnd (BVCommon.h:1231-1241)
-	int32_t count = lastSlice + 1;
-	{
-		bool currentlyCorrect = ws.slices[count - 1].correctLogOdds > ws.slices[count - 1].falseLogOdds;
-		while (!currentlyCorrect)
-		{
-			currentlyCorrect = ws.slices[count - 1].falseFromCorrect;
-			count--;
-			if (count == 0) break;
-		}
-	}
-	return count - 1;
+}
+
+// one item, a warp of one lane: the form the host-side simulations (tests/hostsim) call
+struct GcK1SSingle
+{
+	GcK1SItem item; GcK1SWorkspace slab; bool taken; GcK1Result res; int32_t last;
+	GC_HD bool next(GcK1SItem& it, GcK1SWorkspace& ws) { if (taken) return false; taken = true; it = item; ws = slab; return true; }
+	GC_HD void done(const GcK1Result& r, int32_t l) { res = r; last = l; }
+};
+GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, const GcK1Params& prm, bool have, const uint8_t* seq, int32_t seqLen, uint32_t startNode, uint32_t startOffset,
+	const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, GcK1Result& res)
+{
+	GcK1SSingle one;
+	one.item.seq = seq; one.item.seqLen = seqLen; one.item.startNode = startNode; one.item.startOffset = startOffset; one.item.planeBit = planeBit;
+	one.slab = ws; one.taken = !have; one.last = 0;
+	one.res.status = GC_OK; one.res.score = GC_INT_MAX; one.res.traceLen = 0; one.res.itemsUsed = 0; one.res.columns = 0;
+	GcK1SWorkspace lane = ws;
+	gc_k1s_forward_items(g, vt, prm, planes, lane, one);
+	res.status = one.res.status; res.columns = one.res.columns; res.itemsUsed = one.res.itemsUsed;
+	return one.last;
 }
 
 // ------------------------------------------------------------------------------------
@@ -529,27 +642,25 @@ GC_HD int32_t gc_k1s_forward(const GcGraphView& g, const GcViterbiTables& vt, co
 // next one, repeated through one-column nodes; stage 2 = ONE column loop for the warp that recomputes the nodes in hand
 // (recalcNodeWordslice, BVCommon.h:828-852; columns in per-lane local memory); stage 3 = ONE cell-walk loop for the warp.
 // `cols` = 64 columns of per-lane scratch.  `last` = index of the last kept slice (>= 1) of a lane with `have`.
-GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq, int32_t seqLen, const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, int32_t last, GcColVV* cols, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
+// A lane works through items one after the other (as in the forward pass): src.next() hands out the items whose forward pass
+// succeeded -- (item, slab, last kept slice >= 1, trace buffer, the forward result) -- and src.done() takes the finished result.
+template <class Source>
+GC_HD void gc_k1s_backtrace_items(const GcGraphView& g, const uint64_t* planes, GcK1SWorkspace& ws, GcColVV* cols, Source& src)
 {
+	bool have = false, exhausted = false, active = false;
+	GcK1SItem it; it.seq = nullptr; it.seqLen = 0; it.startNode = 0; it.startOffset = 0; it.planeBit = 0;
+	GcK1Result res; res.status = GC_OK; res.score = 0; res.traceLen = 0; res.itemsUsed = 0; res.columns = 0;
 	GcTraceWriter tw;
-	tw.out = traceOut; tw.cap = traceCap; tw.n = 0; tw.overflow = false; tw.node = 0; tw.offset = 0; tw.seqPos = -1;
-	bool active = have;
-	if (have)
-	{
-		const GcSliceMeta& lm = ws.slices[last];
-		res.score = lm.minScore;
-		int32_t sp = (last - 1) * 64 + 63;
-		if (sp > seqLen - 1) sp = seqLen - 1;
-		tw.push(lm.minScoreNode, lm.minScoreNodeOffset, sp, false);
-	}
+	tw.out = nullptr; tw.cap = 0; tw.n = 0; tw.overflow = false; tw.node = 0; tw.offset = 0; tw.seqPos = -1;
 	uint32_t currentNode = 0xFFFFFFFFu;
 	int32_t currentSlice = -1;
 	uint64_t eq[4] = { 0, 0, 0, 0 };
 	uint32_t guard = 0;
-	const uint32_t guardMax = have ? (uint32_t)seqLen * 4 + 1024 + traceCap : 0;
+	uint32_t guardMax = 0;
 	uint64_t columns = 0;
 	// the slice pair the walk is in
 	uint32_t curFirst = 0, curN = 0, prevFirst = 0, prevN = 0;
+	uint32_t curHint = 0, prevHint = 0; // where the last lookups in the two slices hit
 	int32_t quitScore = 0, previousQuitScore = 0, j = 0;
 	// stage 2 / 3 state
 	bool needCols = false, walking = false;
@@ -560,12 +671,36 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 	GcCols cv; cv.c = cols; cv.HP = 0; cv.HN = 0; cv.score0 = 0;
 	while (true)
 	{
+		// ================= stage 0: a lane without an item takes the next one =================
+		if (!have && !exhausted)
+		{
+			int32_t last = 0; uint64_t* traceOut = nullptr; uint32_t traceCap = 0;
+			if (!src.next(it, ws, last, traceOut, traceCap, res)) exhausted = true;
+			else
+			{
+				have = true; active = true;
+				tw.out = traceOut; tw.cap = traceCap; tw.n = 0; tw.overflow = false; tw.node = 0; tw.offset = 0; tw.seqPos = -1;
+				const GcSliceMeta& lm = ws.slices[last];
+				res.score = lm.minScore;
+				int32_t sp = (last - 1) * 64 + 63;
+				if (sp > it.seqLen - 1) sp = it.seqLen - 1;
+				tw.push(lm.minScoreNode, lm.minScoreNodeOffset, sp, false);
+				currentNode = 0xFFFFFFFFu;
+				currentSlice = -1;
+				guard = 0;
+				guardMax = (uint32_t)it.seqLen * 4 + 1024 + traceCap;
+				columns = 0;
+				needCols = false; walking = false;
+			}
+		}
+		if (!GC_WARP_ANY(have)) break; // no lane has an item and none could get one
 		// ================= stage 1: one step of every lane that is neither waiting for its columns nor walking =================
 		// (a) the crossing out of the node in hand (its columns are in `cols`), (b) lookup of the node the trace is in now
 		if (active && !needCols && !walking)
 		{
-			auto findCur = [&](uint32_t nd) -> const GcNodeItem* { int32_t i = gc_find_key(ws.keys + curFirst, curN, nd); return i >= 0 ? &ws.items[curFirst + i] : nullptr; };
-			auto findPrev = [&](uint32_t nd) -> const GcNodeItem* { int32_t i = gc_find_key(ws.keys + prevFirst, prevN, nd); return i >= 0 ? &ws.items[prevFirst + i] : nullptr; };
+			// the walk moves against the edges and the items of a slice lie in topological order: what is looked up sits at or just before the last hit
+			auto findCur = [&](uint32_t nd) -> const GcNodeItem* { int32_t i = gc_find_key_near(ws.keys + curFirst, curN, nd, curHint); if (i < 0) return nullptr; curHint = (uint32_t)i; return &ws.items[curFirst + i]; };
+			auto findPrev = [&](uint32_t nd) -> const GcNodeItem* { int32_t i = gc_find_key_near(ws.keys + prevFirst, prevN, nd, prevHint); if (i < 0) return nullptr; prevHint = (uint32_t)i; return &ws.items[prevFirst + i]; };
 			do
 			{
 				if (++guard > guardMax) { res.status = GC_INTERNAL; active = false; break; }
@@ -575,7 +710,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 					if ((tw.seqPos & 63) == 0 && tw.offset == 0)
 					{
 						GcBtPos bt;
-						if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, seq, quitScore, previousQuitScore, bt)) { res.status = GC_INTERNAL; active = false; break; }
+						if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, it.seq, quitScore, previousQuitScore, bt)) { res.status = GC_INTERNAL; active = false; break; }
 						tw.push(bt.node, bt.offset, bt.seqPos, bt.nodeSwitch);
 					}
 					else if ((tw.seqPos & 63) == 0)
@@ -592,12 +727,12 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 							GcBtPos second;
 							if (off == 0)
 							{
-								if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; active = false; break; }
+								if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, it.seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; active = false; break; }
 							}
 							else
 							{
 								int base = (int)(((off < 32 ? chunk0 : chunk1) >> ((off & 31) * 2)) & 3);
-								bool eqc = gc_char_match(seq[sp], base);
+								bool eqc = gc_char_match(it.seq[sp], base);
 								int32_t scoreHere = gc_value(gc_cols_get(cv, off), 0);
 								// previous slice's last row: startScore + horizontal deltas of columns 1..off-1 (diagonal) and 1..off (up)
 								uint64_t below = (1ULL << off) - 2; // bits 1..off-1
@@ -635,11 +770,11 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 						GcBtPos second;
 						if (offset == 0)
 						{
-							if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; active = false; break; }
+							if (!gc_bt_corner_with(g, findCur, findPrev, currentNode, j, it.seq, quitScore, previousQuitScore, second)) { res.status = GC_INTERNAL; active = false; break; }
 						}
 						else
 						{
-							bool eqc = gc_char_match(seq[sp], (int)(chunk0 & 3));
+							bool eqc = gc_char_match(it.seq[sp], (int)(chunk0 & 3));
 							int32_t scoreHere = gc_value(startSlice, offset);
 							bool found = false;
 							if (scoreHere > quitScore)
@@ -706,12 +841,14 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 				{
 					const GcSliceMeta& cm = ws.slices[newSlice];
 					const GcSliceMeta& pmeta = ws.slices[newSlice - 1];
+					curHint = (newSlice == currentSlice - 1) ? prevHint : cm.numItems; // one slice down: the old previous slice is the current one now
+					prevHint = pmeta.numItems;
 					curFirst = cm.firstItem; curN = cm.numItems; prevFirst = pmeta.firstItem; prevN = pmeta.numItems;
 					quitScore = cm.minScore + cm.bandwidth;
 					previousQuitScore = pmeta.minScore + pmeta.bandwidth;
 					j = (newSlice - 1) * 64;
-					if (planes) gc_eq_from_planes(planes, planeBit + (uint64_t)j, seqLen - j, eq);
-					else gc_eq_vector(seq, seqLen, j, eq);
+					if (planes) gc_eq_from_planes(planes, it.planeBit + (uint64_t)j, it.seqLen - j, eq);
+					else gc_eq_vector(it.seq, it.seqLen, j, eq);
 				}
 				currentSlice = newSlice;
 				currentNode = newNode;
@@ -739,17 +876,9 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 				}
 			} while (false);
 		}
-		if (!GC_WARP_ANY(active)) break;
 		// ================= stage 2: recompute the nodes in hand =================
 		{
-			const uint32_t maxLen = GC_WARP_MAX(needCols ? len : 0u);
-			uint32_t bases = 0;
-			for (uint32_t pos = 1; pos < maxLen; pos++)
-			{
-				if (pos == 1 || (pos & 15u) == 0) bases = gc_col_bases(run, pos);
-				if (needCols && pos < len) { gc_col_step<false>(run, pos, (int)(bases & 3), forceUntil >= pos); cols[pos].VP = run.ws.VP; cols[pos].VN = run.ws.VN; }
-				bases >>= 2;
-			}
+			gc_k1s_columns<false, true>(run, needCols, len, forceUntil, cols);
 			if (needCols)
 			{
 				needCols = false;
@@ -780,7 +909,7 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 				int32_t dl = (int32_t)((left.VN >> vert) & 1) - (int32_t)((left.VP >> vert) & 1); // the same in the left column
 				int32_t diagonalScore = leftHere + dl;
 				int base = (int)(((hori < 32 ? chunk0 : chunk1) >> ((hori & 31) * 2)) & 3);
-				bool eqc = gc_char_match(seq[vert + j], base);
+				bool eqc = (gc_sel4(eq, base) >> vert) & 1; // gc_char_match(seq[vert + j], base): the slice's Eq masks are in registers
 				if (dv == -1)
 				{
 					vert--;
@@ -799,39 +928,64 @@ GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq,
 				if (!(hori > 0 && vert > 0)) walking = false;
 			}
 		}
-	}
-	res.columns += columns;
-	if (!have || res.status != GC_OK) return;
-	// ---- slide left in row -1 (BVCommon.h:508-542); the do/while(false) runs once
-	{
-		const GcSliceMeta& m0 = ws.slices[0];
-		int32_t ii = gc_find_key(ws.keys + m0.firstItem, m0.numItems, tw.node);
-		if (ii < 0) { res.status = GC_INTERNAL; return; }
-		const GcNodeItem* it = &ws.items[m0.firstItem + ii];
-		uint32_t off = tw.offset;
-		int32_t here = it->startScore + gc_popc(it->HP & ((2ULL << off) - 2)) - gc_popc(it->HN & ((2ULL << off) - 2));
-		while (here != 0 && off > 0)
+		// ================= the walk is over: slide left in row -1 (BVCommon.h:508-542), hand the result over =================
+		if (have && !active)
 		{
-			int32_t before = here - (int32_t)((it->HP >> off) & 1) + (int32_t)((it->HN >> off) & 1);
-			if (before != here - 1) break;
-			off--;
-			here = before;
-			tw.push(tw.node, off, tw.seqPos, false);
-		}
-		if (off == 0 && here != 0)
-		{
-			for (uint32_t e = g.inStart[tw.node]; e < g.inStart[tw.node + 1]; e++)
+			res.columns += columns;
+			if (res.status == GC_OK)
 			{
-				uint32_t nb = g.inNbr[e];
-				int32_t ni = gc_find_key(ws.keys + m0.firstItem, m0.numItems, nb);
-				if (ni >= 0 && gc_sbs(gc_item_end(ws.items[m0.firstItem + ni])) == here - 1)
+				const GcSliceMeta& m0 = ws.slices[0];
+				int32_t ii = gc_find_key(ws.keys + m0.firstItem, m0.numItems, tw.node);
+				if (ii < 0) res.status = GC_INTERNAL;
+				else
 				{
-					tw.push(nb, g.nodeLength[nb] - 1, tw.seqPos, true);
-					break;
+					const GcNodeItem* first = &ws.items[m0.firstItem + ii];
+					uint32_t off = tw.offset;
+					int32_t here = first->startScore + gc_popc(first->HP & ((2ULL << off) - 2)) - gc_popc(first->HN & ((2ULL << off) - 2));
+					while (here != 0 && off > 0)
+					{
+						int32_t before = here - (int32_t)((first->HP >> off) & 1) + (int32_t)((first->HN >> off) & 1);
+						if (before != here - 1) break;
+						off--;
+						here = before;
+						tw.push(tw.node, off, tw.seqPos, false);
+					}
+					if (off == 0 && here != 0)
+					{
+						for (uint32_t e = g.inStart[tw.node]; e < g.inStart[tw.node + 1]; e++)
+						{
+							uint32_t nb = g.inNbr[e];
+							int32_t ni = gc_find_key(ws.keys + m0.firstItem, m0.numItems, nb);
+							if (ni >= 0 && gc_sbs(gc_item_end(ws.items[m0.firstItem + ni])) == here - 1)
+							{
+								tw.push(nb, g.nodeLength[nb] - 1, tw.seqPos, true);
+								break;
+							}
+						}
+					}
+					res.traceLen = tw.n;
+					if (tw.overflow) res.status = GC_OVERFLOW_TRACE;
 				}
 			}
+			src.done(res);
+			have = false;
 		}
 	}
-	res.traceLen = tw.n;
-	if (tw.overflow) res.status = GC_OVERFLOW_TRACE;
+}
+
+// one item, a warp of one lane (tests/hostsim)
+struct GcK1SSingleBt
+{
+	GcK1SItem item; GcK1SWorkspace slab; bool taken; int32_t last; uint64_t* traceOut; uint32_t traceCap; GcK1Result res;
+	GC_HD bool next(GcK1SItem& it, GcK1SWorkspace& ws, int32_t& l, uint64_t*& out, uint32_t& cap, GcK1Result& r) { if (taken) return false; taken = true; it = item; ws = slab; l = last; out = traceOut; cap = traceCap; r = res; return true; }
+	GC_HD void done(const GcK1Result& r) { res = r; }
+};
+GC_HD void gc_k1s_backtrace(const GcGraphView& g, bool have, const uint8_t* seq, int32_t seqLen, const uint64_t* planes, uint64_t planeBit, GcK1SWorkspace& ws, int32_t last, GcColVV* cols, uint64_t* traceOut, uint32_t traceCap, GcK1Result& res)
+{
+	GcK1SSingleBt one;
+	one.item.seq = seq; one.item.seqLen = seqLen; one.item.startNode = 0; one.item.startOffset = 0; one.item.planeBit = planeBit;
+	one.slab = ws; one.taken = !have; one.last = last; one.traceOut = traceOut; one.traceCap = traceCap; one.res = res;
+	GcK1SWorkspace lane = ws;
+	gc_k1s_backtrace_items(g, planes, lane, cols, one);
+	res = one.res;
 }

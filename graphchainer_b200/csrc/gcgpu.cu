@@ -65,6 +65,7 @@ struct GcResident;
 struct gcgpu_ctx
 {
 	int device = 0;
+	int numSMs = 148;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaStream_t stream2 = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr; // side stream for kernels that run beside the main one
@@ -311,39 +312,84 @@ __device__ __forceinline__ void gc_k1s_workspace(const GcK1Desc& d, uint8_t* are
 	ws.itemCap = d.itemCap;
 	ws.heap.base = heapShared + threadIdx.x; ws.heap.stride = GC_K1S_THREADS; ws.heap.cap = GC_K1S_HEAP;
 }
-__global__ void __launch_bounds__(GC_K1S_THREADS, 1) gc_k1s_forward_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes,
-	const gcgpu_ext_item* __restrict__ items, const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
+// The launch's items are handed out one at a time (longest first, `next` = a counter in global memory): a lane whose item
+// ends takes the next one.  `lanes` = lanes per warp that take items at all: a launch with fewer items than resident lanes
+// spreads them over all the warps it can have resident instead of filling a few warps to 32.
+struct GcK1SForwardQueue
+{
+	const GcK1Desc* descs; const gcgpu_ext_item* items; uint32_t n; uint32_t* next_; uint32_t lanes;
+	const uint8_t* seq; uint8_t* arena; uint64_t* heapShared;
+	GcK1Result* results; uint64_t* traceOffOfItem; uint32_t* overflow; int32_t* lastSlice;
+	uint32_t t; GcK1Desc d;
+	__device__ __forceinline__ bool next(GcK1SItem& it, GcK1SWorkspace& ws)
+	{
+		if ((threadIdx.x & 31) >= lanes) return false;
+		t = atomicAdd(next_, 1u);
+		if (t >= n) return false;
+		d = gc_k1_long_desc(descs, items, t);
+		gc_k1s_workspace(d, arena, heapShared, ws);
+		it.seq = seq + d.seqOff; it.seqLen = d.seqLen; it.startNode = d.node; it.startOffset = d.offset; it.planeBit = d.seqOff;
+		return true;
+	}
+	__device__ __forceinline__ void done(GcK1Result res, int32_t last)
+	{
+		if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
+		results[d.resultIndex] = res;
+		traceOffOfItem[d.resultIndex] = d.traceOff;
+		lastSlice[t] = last;
+		if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+	}
+};
+// 6 resident blocks per SM: 168 registers (the compiler takes 188 unbounded; same speed alone -- r03o -- and one more block for the launches of other batches)
+__global__ void __launch_bounds__(GC_K1S_THREADS, 6) gc_k1s_forward_kernel(GcGraphView g, const GcViterbiTables* __restrict__ vt, GcK1Params prm, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes,
+	const gcgpu_ext_item* __restrict__ items, const GcK1Desc* __restrict__ descs, uint32_t n, uint32_t* next, uint32_t lanes, uint8_t* arena, GcK1Result* results, uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
 	__shared__ uint64_t heapShared[GC_K1S_HEAP * GC_K1S_THREADS];
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool have = t < n; // lanes without an item still take part in the warp votes
 	g.coopLane = -1;
-	GcK1Desc d = gc_k1_long_desc(descs, items, have ? t : 0);
+	GcK1SForwardQueue q;
+	q.descs = descs; q.items = items; q.n = n; q.next_ = next; q.lanes = lanes; q.seq = seq; q.arena = arena; q.heapShared = heapShared;
+	q.results = results; q.traceOffOfItem = traceOffOfItem; q.overflow = overflow; q.lastSlice = lastSlice; q.t = 0;
 	GcK1SWorkspace ws;
-	gc_k1s_workspace(d, arena, heapShared, ws);
-	GcK1Result res;
-	res.score = GC_INT_MAX; res.traceLen = 0; res.itemsUsed = 0;
-	int32_t last = gc_k1s_forward(g, *vt, prm, have, seq + d.seqOff, d.seqLen, d.node, d.offset, planes, d.seqOff, ws, res);
-	if (!have) return;
-	if (res.status == GC_OK && last < 1) res.status = GC_FAILED;
-	results[d.resultIndex] = res;
-	traceOffOfItem[d.resultIndex] = d.traceOff;
-	lastSlice[t] = last;
-	if (res.status == GC_OVERFLOW_ITEMS || res.status == GC_OVERFLOW_HEAP) atomicAdd(overflow, 1u);
+	ws.slices = nullptr; ws.items = nullptr; ws.keys = nullptr; ws.aux = nullptr; ws.scratch = nullptr; ws.scratchCap = 0; ws.itemCap = 0;
+	ws.heap.base = heapShared + threadIdx.x; ws.heap.stride = GC_K1S_THREADS; ws.heap.cap = GC_K1S_HEAP;
+	gc_k1s_forward_items(g, *vt, prm, planes, ws, q);
 }
-__global__ void __launch_bounds__(GC_K1S_THREADS, 1) gc_k1s_backtrace_kernel(GcGraphView g, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes, const gcgpu_ext_item* __restrict__ items,
-	const GcK1Desc* __restrict__ descs, uint32_t n, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
+struct GcK1SBacktraceQueue
 {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const GcK1Desc* descs; const gcgpu_ext_item* items; uint32_t n; uint32_t* next_; uint32_t lanes;
+	const uint8_t* seq; uint8_t* arena; uint64_t* traceArena;
+	GcK1Result* results; const int32_t* lastSlice;
+	GcK1Desc d;
+	__device__ __forceinline__ bool next(GcK1SItem& it, GcK1SWorkspace& ws, int32_t& last, uint64_t*& traceOut, uint32_t& traceCap, GcK1Result& res)
+	{
+		if ((threadIdx.x & 31) >= lanes) return false;
+		while (true)
+		{
+			uint32_t t = atomicAdd(next_, 1u);
+			if (t >= n) return false;
+			d = gc_k1_long_desc(descs, items, t);
+			res = results[d.resultIndex];
+			if (res.status != GC_OK) continue; // the forward pass failed: no trace
+			gc_k1s_workspace(d, arena, nullptr, ws);
+			it.seq = seq + d.seqOff; it.seqLen = d.seqLen; it.startNode = d.node; it.startOffset = d.offset; it.planeBit = d.seqOff;
+			last = lastSlice[t];
+			traceOut = traceArena + d.traceOff; traceCap = d.traceCap;
+			return true;
+		}
+	}
+	__device__ __forceinline__ void done(const GcK1Result& res) { results[d.resultIndex] = res; }
+};
+__global__ void __launch_bounds__(GC_K1S_THREADS, 8) gc_k1s_backtrace_kernel(GcGraphView g, const uint8_t* __restrict__ seq, const uint64_t* __restrict__ planes, const gcgpu_ext_item* __restrict__ items,
+	const GcK1Desc* __restrict__ descs, uint32_t n, uint32_t* next, uint32_t lanes, uint8_t* arena, uint64_t* traceArena, GcK1Result* results, const int32_t* __restrict__ lastSlice)
+{
 	g.coopLane = -1;
-	GcK1Desc d = gc_k1_long_desc(descs, items, t < n ? t : 0);
-	GcK1Result res = results[d.resultIndex];
-	const bool have = t < n && res.status == GC_OK;
+	GcK1SBacktraceQueue q;
+	q.descs = descs; q.items = items; q.n = n; q.next_ = next; q.lanes = lanes; q.seq = seq; q.arena = arena; q.traceArena = traceArena; q.results = results; q.lastSlice = lastSlice;
 	GcK1SWorkspace ws;
-	gc_k1s_workspace(d, arena, nullptr, ws);
+	ws.slices = nullptr; ws.items = nullptr; ws.keys = nullptr; ws.aux = nullptr; ws.scratch = nullptr; ws.scratchCap = 0; ws.itemCap = 0;
+	ws.heap.base = nullptr; ws.heap.stride = 0; ws.heap.cap = 0;
 	GcColVV cols[64];
-	gc_k1s_backtrace(g, have, seq + d.seqOff, d.seqLen, planes, d.seqOff, ws, have ? lastSlice[t] : 0, cols, traceArena + d.traceOff, d.traceCap, res);
-	if (have) results[d.resultIndex] = res;
+	gc_k1s_backtrace_items(g, planes, ws, cols, q);
 }
 // bit planes of the sequence buffer: for every block of 64 codes, four words (bit i of word b = code i has bit b: A C G T)
 __global__ void gc_planes_kernel(const uint8_t* __restrict__ seq, uint64_t bytes, uint64_t blocks, uint64_t* __restrict__ planes)
@@ -438,6 +484,7 @@ extern "C" int gcgpu_create(int device, const gcgpu_graph* graph, const gcgpu_pa
 	ctx->numNodes = N;
 	cudaError_t err = cudaSuccess;
 	auto chk = [&err](cudaError_t x) { if (err == cudaSuccess) err = x; };
+	chk(cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device));
 	chk(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	chk(cudaEventCreate(&ctx->ev0));
 	chk(cudaEventCreate(&ctx->ev1));
@@ -562,6 +609,14 @@ static int buildPlanes(gcgpu_ctx* ctx, uint64_t bytes)
 // and the lane-per-item form is taken unless it is estimated more than four times slower (measurements: profiles/r03d, r03f, r03h:
 // c2 round 2 goes lane-per-item, the one-seed-per-read first round and the tail rounds lock-step, ultra-long reads lock-step).
 // GCGPU_K1_FORM=lane | lockstep forces one form.
+// Fewest lanes per warp that take items in a lane-per-item launch (GCGPU_K1_LANES overrides).  32: a launch lasts as long as
+// its longest item whatever the number of warps (r03m: 47.6 / 49.7 / 49.9 / 49.4 ms at 32 / 16 / 8 / 4 lanes), and a launch
+// spread over more warps leaves fewer SM slots to the launches of the other batches in flight (e2e 199.6 vs 174.4 Mbp/s at 32 vs 16)
+static uint32_t k1MinLanes()
+{
+	static const uint32_t v = [] { const char* e = getenv("GCGPU_K1_LANES"); int x = e ? atoi(e) : 32; return (uint32_t)(x < 1 ? 1 : (x > 32 ? 32 : x)); }();
+	return v;
+}
 static bool k1UseLaneForm(uint32_t nLong, uint64_t sumSlices, uint32_t maxSlices)
 {
 	const char* force = getenv("GCGPU_K1_FORM");
@@ -654,10 +709,31 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 		for (const GcK1Desc& d : descs) { sumSlices += d.numSlices; if (d.numSlices > maxSlices) maxSlices = d.numSlices; }
 		if (k1UseLaneForm(nLong, sumSlices, maxSlices))
 		{
-			// lane per item: 32 items per warp, sorted by length
-			uint32_t blocks = (nLong + GC_K1S_THREADS - 1) / GC_K1S_THREADS;
-			gc_k1s_forward_kernel<<<blocks, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, dRes, dSlot, dOverflow, dLast);
-			gc_k1s_backtrace_kernel<<<blocks, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			// lane per item: persistent warps whose lanes take items (sorted by length, longest first) from a counter until none is left
+			struct Resident { int fwd = 1, bt = 1; };
+			static const Resident resident = [] { // initialised once, by whichever host thread gets here first
+				Resident r;
+				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.fwd, gc_k1s_forward_kernel, GC_K1S_THREADS, 0) != cudaSuccess || r.fwd < 1) r.fwd = 1;
+				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.bt, gc_k1s_backtrace_kernel, GC_K1S_THREADS, 0) != cudaSuccess || r.bt < 1) r.bt = 1;
+				return r;
+			}();
+			const int fwdPerSM = resident.fwd, btPerSM = resident.bt;
+			uint32_t* dNext = (uint32_t*)(R + offScalars + 16); // two counters, zeroed with the scalars above
+			const uint32_t warpsPerBlock = GC_K1S_THREADS / 32;
+			auto shape = [&](int perSM, uint32_t& blocks, uint32_t& lanes)
+			{
+				const uint32_t maxBlocks = (uint32_t)ctx->numSMs * (uint32_t)perSM;
+				lanes = (nLong + maxBlocks * warpsPerBlock - 1) / (maxBlocks * warpsPerBlock);
+				if (lanes < k1MinLanes()) lanes = k1MinLanes();
+				if (lanes > 32) lanes = 32;
+				blocks = (nLong + lanes * warpsPerBlock - 1) / (lanes * warpsPerBlock);
+				if (blocks > maxBlocks) blocks = maxBlocks;
+			};
+			uint32_t blocksF, lanesF, blocksB, lanesB;
+			shape(fwdPerSM, blocksF, lanesF);
+			shape(btPerSM, blocksB, lanesB);
+			gc_k1s_forward_kernel<<<blocksF, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, dNext, lanesF, (uint8_t*)ctx->arena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1s_backtrace_kernel<<<blocksB, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, dNext + 1, lanesB, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
 		}
 		else
 		{

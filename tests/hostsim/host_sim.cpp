@@ -398,6 +398,7 @@ int main(int argc, char** argv)
 	size_t total = 0, bad = 0;
 	uint64_t columns = 0;
 	Ext cur; bool haveExt = false;
+	std::vector<Ext> queued; // k1q: every item of the file goes through ONE lane, one after the other (the way a lane of the GPU kernels takes items)
 	while (std::getline(in, line))
 	{
 		if (line.compare(0, 4, "EXT ") == 0)
@@ -411,7 +412,7 @@ int main(int argc, char** argv)
 		}
 		if (line.compare(0, 4, "RES ") != 0 || !haveExt) continue;
 		haveExt = false;
-		if (mode != "k1" && mode != "k1s") continue;
+		if (mode != "k1" && mode != "k1s" && mode != "k1q") continue;
 		{
 			std::istringstream ss(line);
 			std::string tag, first; ss >> tag >> first;
@@ -420,6 +421,7 @@ int main(int argc, char** argv)
 		}
 		if (total >= maxItems) break;
 		total++;
+		if (mode == "k1q") { queued.push_back(cur); continue; }
 		// ---- run the work item
 		uint32_t node = hg.unitigNode(cur.bigraphNode, cur.offset);
 		uint32_t off = (uint32_t)(cur.offset - hg.nodeOffset[node]);
@@ -482,6 +484,67 @@ int main(int argc, char** argv)
 					break;
 				}
 			}
+		}
+	}
+	if (mode == "k1q")
+	{
+		struct Slab
+		{
+			std::vector<uint8_t> seq; std::vector<uint64_t> planes; std::vector<GcSliceMeta> slices; std::vector<GcNodeItem> items; std::vector<uint32_t> keys, scratch; std::vector<GcItemAux> aux;
+			std::vector<uint64_t> trace; GcK1SItem item; GcK1SWorkspace ws; GcK1Result res; int32_t last = 0;
+		};
+		std::vector<Slab> slabs(queued.size());
+		std::vector<uint64_t> heap(4096);
+		for (size_t k = 0; k < queued.size(); k++)
+		{
+			const Ext& e = queued[k]; Slab& sl = slabs[k];
+			uint32_t node = hg.unitigNode(e.bigraphNode, e.offset);
+			sl.seq.resize(e.seq.size());
+			for (size_t i = 0; i < sl.seq.size(); i++) sl.seq[i] = gcEncodeBase(e.seq[i]);
+			int32_t seqLen = (int32_t)sl.seq.size(), numSlices = (seqLen + 63) / 64;
+			uint32_t itemCap = 1024 + 256 * numSlices;
+			sl.planes.assign(4 * ((size_t)seqLen / 64 + 3), 0);
+			for (int32_t i = 0; i < seqLen; i++) for (int b = 0; b < 4; b++) if ((sl.seq[i] >> b) & 1) sl.planes[4 * (size_t)(i >> 6) + b] |= 1ULL << (i & 63);
+			sl.slices.resize(numSlices + 2); sl.items.resize(itemCap); sl.keys.resize(itemCap); sl.aux.resize(itemCap); sl.scratch.resize(2 * heap.size()); sl.trace.assign(2 * (size_t)seqLen + 256, 0);
+			sl.item.seq = sl.seq.data(); sl.item.seqLen = seqLen; sl.item.startNode = node; sl.item.startOffset = (uint32_t)(e.offset - hg.nodeOffset[node]); sl.item.planeBit = 0;
+			sl.ws.slices = sl.slices.data(); sl.ws.items = sl.items.data(); sl.ws.keys = sl.keys.data(); sl.ws.aux = sl.aux.data(); sl.ws.scratch = sl.scratch.data(); sl.ws.scratchCap = (uint32_t)sl.scratch.size(); sl.ws.itemCap = itemCap;
+			sl.ws.heap.base = heap.data(); sl.ws.heap.stride = 1; sl.ws.heap.cap = (uint32_t)heap.size();
+			sl.res.status = GC_OK; sl.res.score = GC_INT_MAX; sl.res.traceLen = 0; sl.res.itemsUsed = 0; sl.res.columns = 0;
+		}
+		struct Fwd
+		{
+			std::vector<Slab>* slabs; size_t at = 0, cur = 0;
+			bool next(GcK1SItem& it, GcK1SWorkspace& ws) { if (at >= slabs->size()) return false; cur = at++; it = (*slabs)[cur].item; ws = (*slabs)[cur].ws; return true; }
+			void done(GcK1Result r, int32_t last) { if (r.status == GC_OK && last < 1) r.status = GC_FAILED; Slab& sl = (*slabs)[cur]; sl.res.status = r.status; sl.res.columns = r.columns; sl.res.itemsUsed = r.itemsUsed; sl.last = last; }
+		} fwd; fwd.slabs = &slabs;
+		struct Bwd
+		{
+			std::vector<Slab>* slabs; size_t at = 0, cur = 0;
+			bool next(GcK1SItem& it, GcK1SWorkspace& ws, int32_t& last, uint64_t*& out, uint32_t& cap, GcK1Result& r)
+			{
+				while (at < slabs->size() && (*slabs)[at].res.status != GC_OK) at++;
+				if (at >= slabs->size()) return false;
+				cur = at++; Slab& sl = (*slabs)[cur]; it = sl.item; ws = sl.ws; last = sl.last; out = sl.trace.data(); cap = (uint32_t)sl.trace.size(); r = sl.res; return true;
+			}
+			void done(const GcK1Result& r) { (*slabs)[cur].res = r; }
+		} bwd; bwd.slabs = &slabs;
+		GcK1Params prm { 10 };
+		GcK1SWorkspace lane; lane.slices = nullptr; lane.items = nullptr; lane.keys = nullptr; lane.aux = nullptr; lane.scratch = nullptr; lane.scratchCap = 0; lane.itemCap = 0; lane.heap.base = heap.data(); lane.heap.stride = 1; lane.heap.cap = (uint32_t)heap.size();
+		GcColVV colsBuf[64];
+		gc_k1s_forward_items(g, vt, prm, (const uint64_t*)nullptr, lane, fwd);
+		gc_k1s_backtrace_items(g, (const uint64_t*)nullptr, lane, colsBuf, bwd);
+		for (size_t k = 0; k < queued.size(); k++)
+		{
+			const Ext& e = queued[k]; const Slab& sl = slabs[k];
+			columns += sl.res.columns;
+			bool ok = true;
+			if (e.failed) ok = sl.res.status == GC_FAILED;
+			else
+			{
+				ok = sl.res.status == GC_OK && sl.res.score == e.score && sl.res.traceLen == e.trace.size();
+				for (size_t i = 0; ok && i < e.trace.size(); i++) ok = sl.trace[i] == e.trace[i];
+			}
+			if (!ok) { bad++; if (bad <= 5) std::cerr << "MISMATCH queued item " << k << " status " << sl.res.status << " score " << sl.res.score << " len " << sl.res.traceLen << std::endl; }
 		}
 	}
 	std::cout << "{\"mode\":\"" << mode << "\",\"items\":" << total << ",\"mismatches\":" << bad << ",\"columns\":" << columns << "}" << std::endl;

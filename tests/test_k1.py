@@ -14,10 +14,11 @@ from conftest import REFDUMP, ROOT
 import stages
 
 
-@pytest.mark.parametrize("mode", ["k1", "k1s"])
+@pytest.mark.parametrize("mode", ["k1", "k1s", "k1q"])
 def test_k1_logic_on_cpu_matches_golden(hostsim, golden_files, mode):
     """The device functions, compiled for the host, replay the golden K1 records (k1: the thread/warp-per-item form of
-    gc_k1.cuh; k1s: the lane-per-item form of gc_k1s.cuh as a warp of one lane, Eq masks from bit planes for every other item)."""
+    gc_k1.cuh; k1s: the lane-per-item form of gc_k1s.cuh as a warp of one lane, Eq masks from bit planes for every other item;
+    k1q: all records of a file through ONE lane one after the other, the way a lane of the GPU kernels takes item after item)."""
     assert golden_files, "golden fixtures missing"
     for name, (idx, st) in golden_files.items():
         out = subprocess.run([hostsim, mode, idx, st], capture_output=True, text=True)
