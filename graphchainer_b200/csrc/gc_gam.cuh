@@ -1,16 +1,15 @@
 // S7 on the device: one read's GAM record -- the vg::Alignment messages of its alignments in proto3 wire format, packed
-// into one gzip member -- written by ONE thread from the alignment token streams that gc_post.cuh leaves in HBM.
+// into one gzip member -- made by ONE warp from the alignment token streams that gc_post.cuh leaves in HBM.
 //   GraphAlignerVGAlignment::traceToAlignment + AddAlignment + replaceDigraphNodeIdsWithOriginalNodeIds
 //       (src/GraphAlignerVGAlignment.h:37-165, src/GraphAligner.h:205-212, src/Aligner.cpp:152-165)
 //   writeGAMToQueue: varint64 count, {varint32 size, message}*, one gzip member per read (src/Aligner.cpp:261-281, stream.hpp:24-51)
 //
-// Why a thread per record: encoding and compressing the records was the largest host stage left (36 of ~63 ns per read base and
+// Why on the device: encoding and compressing the records was the largest host stage left (36 of ~63 ns per read base and
 // core; gc_output.h / gc_deflate.h), every record is independent, and the device idles between the DP launches of a batch.
-// A record is ~3.4 bytes per read base; the DEFLATE encoder is the host's design (greedy LZ77 with one hash probe per position,
-// one dynamic-Huffman block from the record's own statistics) restated on raw pointers so that the same functions run in a
-// kernel (gc_gam_kernel, gcgpu_resident.inl) and, compiled for the host, in the C-ABI test double -- where zlib inflates their
-// output in the CPU tests.  Thousands of records are in flight per launch; a thread's walk is latency-bound (~25-40 ms for a
-// 10-kb read's record), which the other batches' kernels hide.
+// A record is ~3.4 bytes per read base.  Lane 0 of the warp writes the record (a chain of varint fields whose sizes depend on
+// each other); the DEFLATE encoder is the host's design (greedy LZ77 with one hash probe per position, one dynamic-Huffman block
+// from the record's own statistics) cut into 32 chunks for the 32 lanes -- see gc_gzip_member below.  The same functions,
+// compiled for the host, run in the C-ABI test double and in tests/hostsim/gz_check.cpp, where zlib inflates their output.
 #pragma once
 #include <string.h>
 #include "gc_common.cuh"
@@ -24,6 +23,7 @@ struct GcDeflateTables
 	uint8_t distExtraBits[32]; uint16_t distBase[32];
 	uint8_t symExtraBits[288];
 	uint32_t crc[256];
+	uint32_t x2n[32];   // x^(2^k) modulo the CRC-32 polynomial (reflected): joins the CRCs of a record's chunks
 };
 inline void gcBuildGamTables(GcDeflateTables& T)
 {
@@ -49,6 +49,10 @@ inline void gcBuildGamTables(GcDeflateTables& T)
 		}
 	}
 	for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; T.crc[i] = c; }
+	auto mul = [](uint32_t a, uint32_t b) { uint32_t m = 1u << 31, r = 0; for (;;) { if (a & m) { r ^= b; if ((a & (m - 1)) == 0) break; } m >>= 1; b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1; } return r; };
+	uint32_t x = 1u << 30; // x^1
+	T.x2n[0] = x;
+	for (int k = 1; k < 32; k++) { x = mul(x, x); T.x2n[k] = x; }
 }
 
 // ---------------------------------------------------------------- proto3 wire format of the record
@@ -181,9 +185,8 @@ GC_HD uint32_t gc_gam_write_record(const GcNameTable& nt, const uint8_t* readCha
 
 // ---------------------------------------------------------------- DEFLATE (RFC 1951) in a gzip member (RFC 1952)
 // workspace of one record: hash heads + token buffer
-#define GC_DEFLATE_HASH_BITS 13
-struct GcDeflateWs { int32_t* head; uint32_t* tokens; uint32_t tokenCap; };
-GC_HD size_t gc_deflate_ws_bytes(uint32_t rawBytes) { return ((size_t)4 << GC_DEFLATE_HASH_BITS) + ((size_t)rawBytes + 16) * 4; }
+struct GcDeflateWs { uint32_t* tokens; uint32_t tokenCap; };
+GC_HD size_t gc_deflate_ws_bytes(uint32_t rawBytes) { return ((size_t)rawBytes + 16) * 4; }
 
 struct GcBitWriter
 {
@@ -201,37 +204,6 @@ GC_HD uint32_t gc_deflate_load32(const uint8_t* p) { return (uint32_t)p[0] | ((u
 GC_HD int gc_deflate_dist_sym(const GcDeflateTables& T, uint32_t d) { return d <= 512 ? T.distSymLo[d - 1] : T.distSymHi[(d - 1) >> 7]; }
 
 // token: bits 0-8 literal/length symbol | 9-13 distance symbol (30 = a literal) | 14-18 length extra value | 19-31 distance extra value
-GC_HD uint32_t gc_deflate_tokenize(const GcDeflateTables& T, const uint8_t* p, uint32_t n, GcDeflateWs& ws)
-{
-	const uint32_t H = 1u << GC_DEFLATE_HASH_BITS;
-	for (uint32_t i = 0; i < H; i++) ws.head[i] = -1;
-	uint32_t nt = 0, i = 0;
-	while (i + 4 <= n)
-	{
-		uint32_t v = gc_deflate_load32(p + i);
-		uint32_t h = (v * 2654435761u) >> (32 - GC_DEFLATE_HASH_BITS);
-		int32_t cand = ws.head[h];
-		ws.head[h] = (int32_t)i;
-		if (cand >= 0 && i - (uint32_t)cand <= 32768 && gc_deflate_load32(p + cand) == v)
-		{
-			uint32_t maxLen = n - i < 258 ? n - i : 258;
-			uint32_t len = 4;
-			while (len < maxLen && p[i + len] == p[cand + len]) len++;
-			uint32_t dist = i - (uint32_t)cand;
-			uint32_t ds = (uint32_t)gc_deflate_dist_sym(T, dist);
-			ws.tokens[nt++] = (uint32_t)T.lenSym[len] | (ds << 9) | ((len - T.lenBase[len]) << 14) | ((dist - T.distBase[ds]) << 19);
-			if (i + len + 4 <= n)
-			{
-				uint32_t v2 = gc_deflate_load32(p + i + len - 1);
-				ws.head[(v2 * 2654435761u) >> (32 - GC_DEFLATE_HASH_BITS)] = (int32_t)(i + len - 1);
-			}
-			i += len;
-		}
-		else { ws.tokens[nt++] = (uint32_t)p[i] | (30u << 9); i++; }
-	}
-	for (; i < n; i++) ws.tokens[nt++] = (uint32_t)p[i] | (30u << 9);
-	return nt;
-}
 
 // length-limited Huffman code lengths (two-queue merge over the symbols sorted by frequency; the leaf-moving repair of the per-length
 // counts for codes deeper than maxLen).  n <= 288.
@@ -309,24 +281,20 @@ GC_HD bool gc_deflate_complete(const uint8_t* lens, int n, int maxLen)
 	return kraft == (1ull << maxLen) || (used == 1 && maxLen != 7);
 }
 
-// one final dynamic-Huffman block holding all tokens; false if a code could not be made complete
-GC_HD bool gc_deflate_block(const GcDeflateTables& T, const uint32_t* tokens, uint32_t nTokens, GcBitWriter& bw)
+// the dynamic-Huffman codes of a block from its symbol counts, and the block's header (BFINAL = 1, the code descriptions);
+// false if a code could not be made complete
+GC_HD bool gc_deflate_block_header(uint32_t* litFreq, uint32_t* distFreq, uint8_t* litLens, uint8_t* distLens, uint16_t* litCodes, uint16_t* distCodes, GcBitWriter& bw)
 {
-	uint32_t litFreq[288], distFreq[32];
-	for (int i = 0; i < 288; i++) litFreq[i] = 0;
-	for (int i = 0; i < 32; i++) distFreq[i] = 0;
-	for (uint32_t t = 0; t < nTokens; t++) { litFreq[tokens[t] & 0x1FF]++; distFreq[(tokens[t] >> 9) & 31]++; }
 	distFreq[30] = 0; distFreq[31] = 0;
 	litFreq[256] = 1;
-	uint8_t litLens[288], distLens[32];
 	for (int i = 0; i < 32; i++) distLens[i] = 0;
 	gc_deflate_lengths(litFreq, 286, 15, litLens);
 	gc_deflate_lengths(distFreq, 30, 15, distLens);
+	litLens[286] = litLens[287] = 0;
 	int usedDist = 0;
 	for (int i = 0; i < 30; i++) if (distLens[i]) usedDist++;
 	if (usedDist == 0) distLens[0] = 1; // at least one distance code must be described
 	if (!gc_deflate_complete(litLens, 286, 15) || !gc_deflate_complete(distLens, 30, 15)) return false;
-	uint16_t litCodes[288], distCodes[32];
 	for (int i = 0; i < 32; i++) distCodes[i] = 0;
 	gc_deflate_codes(litLens, 286, litCodes);
 	gc_deflate_codes(distLens, 30, distCodes);
@@ -378,20 +346,6 @@ GC_HD bool gc_deflate_block(const GcDeflateTables& T, const uint32_t* tokens, ui
 		else if (clSym[i] == 17) bw.put(clExtra[i], 3);
 		else if (clSym[i] == 18) bw.put(clExtra[i], 7);
 	}
-	for (uint32_t ti = 0; ti < nTokens; ti++)
-	{
-		uint32_t t = tokens[ti];
-		uint32_t sym = t & 0x1FF, ds = (t >> 9) & 31;
-		uint64_t v = litCodes[sym]; int nb = litLens[sym];
-		v |= (uint64_t)((t >> 14) & 31) << nb; nb += T.symExtraBits[sym];
-		if (ds != 30)
-		{
-			v |= (uint64_t)distCodes[ds] << nb; nb += distLens[ds];
-			v |= (uint64_t)(t >> 19) << nb; nb += T.distExtraBits[ds];
-		}
-		bw.put(v, nb);
-	}
-	bw.put(litCodes[256], litLens[256]);
 	return true;
 }
 
@@ -402,20 +356,217 @@ GC_HD uint32_t gc_crc32(const GcDeflateTables& T, const uint8_t* p, uint32_t n)
 	return c ^ 0xFFFFFFFFu;
 }
 
-// gzip member of raw[0, n) into out (capacity outCap).  Returns its size; 0 if it did not fit or no complete code exists (the
-// caller then encodes that record on the host).
-GC_HD uint32_t gc_gzip_member(const GcDeflateTables& T, const uint8_t* raw, uint32_t n, GcDeflateWs& ws, uint8_t* out, uint32_t outCap)
+GC_HD uint32_t gc_crc_multmodp(uint32_t a, uint32_t b)
 {
-	// worst case of the block: 15 bits per literal + the code descriptions
-	if ((uint64_t)outCap < (uint64_t)n * 2 + 600) return 0;
-	uint32_t nTokens = gc_deflate_tokenize(T, raw, n, ws);
-	const uint8_t header[10] = { 0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4, 3 }; // deflate, no flags, mtime 0, XFL fastest, OS unix
-	for (int i = 0; i < 10; i++) out[i] = header[i];
-	GcBitWriter bw; bw.p = out + 10; bw.acc = 0; bw.n = 0;
-	if (!gc_deflate_block(T, ws.tokens, nTokens, bw)) return 0;
-	uint8_t* end = bw.flush();
-	uint32_t crc = gc_crc32(T, raw, n);
+	uint32_t m = 1u << 31, p = 0;
+	for (;;)
+	{
+		if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+		m >>= 1;
+		b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+	}
+	return p;
+}
+// CRC of A || B from the CRCs of A and B: crc(A) times x^(8 |B|), plus crc(B) (zlib's crc32_combine)
+GC_HD uint32_t gc_crc_shift(const GcDeflateTables& T, uint32_t crc, uint64_t bytesAfter)
+{
+	uint32_t p = 1u << 31; uint32_t k = 3;
+	while (bytesAfter) { if (bytesAfter & 1) p = gc_crc_multmodp(T.x2n[k & 31], p); bytesAfter >>= 1; k++; }
+	return gc_crc_multmodp(p, crc);
+}
+
+// ---------------------------------------------------------------- one gzip member made by the 32 lanes of a warp
+// The record is cut into 32 chunks.  Every lane parses its chunk (greedy LZ77, one hash probe per position, matches inside the chunk:
+// what repeats in a record -- field tags, node name prefixes, edit shapes -- repeats at short range) and counts its symbols into the
+// record's counts; lane 0 makes ONE dynamic-Huffman code for the record and the block header; the lanes' bit counts are scanned
+// and every lane writes its chunk's codes where they belong in the member (32-bit words, the two words a lane shares with its
+// neighbours by atomic OR); the CRCs of the chunks are joined (gc_crc_shift).  Written as per-lane stages: the kernel runs a stage
+// on the 32 lanes and meets at a warp barrier, the host-side test double runs it for lane 0..31 in turn -- same bytes.
+#define GC_GZ_LANES 32
+#define GC_GZ_HASH_BITS 8
+struct GcGzShared // per record: shared memory in the kernel
+{
+	uint16_t head[GC_GZ_LANES << GC_GZ_HASH_BITS];   // hash heads of the lanes' chunks: position in the chunk, 0xFFFF = none
+	uint32_t litFreq[288], distFreq[32];
+	uint16_t litCodes[288], distCodes[32];
+	uint8_t litLens[288], distLens[32];
+	uint8_t header[704]; uint32_t headerBits;        // gzip header, block header, code descriptions: lane 0 emits them before its chunk
+	uint32_t laneTokens[GC_GZ_LANES], laneBits[GC_GZ_LANES], laneStart[GC_GZ_LANES], laneCrc[GC_GZ_LANES];
+	uint32_t ok;
+};
+GC_HD uint32_t gc_gz_chunk(uint32_t n) { return (n + GC_GZ_LANES - 1) / GC_GZ_LANES; }
+GC_HD void gc_gz_count(uint32_t* counter)
+{
+#if defined(__CUDA_ARCH__)
+	atomicAdd(counter, 1u);
+#else
+	(*counter)++;
+#endif
+}
+GC_HD void gc_gz_or(uint32_t* word, uint32_t bits)
+{
+#if defined(__CUDA_ARCH__)
+	atomicOr(word, bits);
+#else
+	*word |= bits;
+#endif
+}
+// stage 0 (every lane): clear the shared counts
+GC_HD void gc_gz_clear(GcGzShared& sh, uint32_t lane)
+{
+	for (uint32_t i = lane; i < 288; i += GC_GZ_LANES) sh.litFreq[i] = 0;
+	if (lane < 32) sh.distFreq[lane] = 0;
+	if (lane == 0) sh.ok = 1;
+}
+// stage 1 (every lane): tokens of the lane's chunk (same token format as above), symbol counts, CRC of the chunk
+GC_HD void gc_gz_tokenize(const GcDeflateTables& T, const uint8_t* p, uint32_t n, uint32_t lane, uint32_t* tokens, GcGzShared& sh)
+{
+	const uint32_t C = gc_gz_chunk(n);
+	const uint32_t begin = lane * C < n ? lane * C : n, end = begin + C < n ? begin + C : n;
+	uint16_t* head = sh.head + (lane << GC_GZ_HASH_BITS);
+	for (uint32_t i = 0; i < (1u << GC_GZ_HASH_BITS); i++) head[i] = 0xFFFFu;
+	uint32_t* out = tokens + begin;
+	uint32_t nt = 0, i = begin;
+	while (i + 4 <= end)
+	{
+		uint32_t v = gc_deflate_load32(p + i);
+		uint32_t h = (v * 2654435761u) >> (32 - GC_GZ_HASH_BITS);
+		uint32_t cand = head[h];
+		head[h] = (uint16_t)(i - begin);
+		if (cand != 0xFFFFu && gc_deflate_load32(p + begin + cand) == v)
+		{
+			const uint32_t c = begin + cand;
+			uint32_t maxLen = end - i < 258 ? end - i : 258;
+			uint32_t len = 4;
+			while (len < maxLen && p[i + len] == p[c + len]) len++;
+			uint32_t dist = i - c;
+			uint32_t ds = (uint32_t)gc_deflate_dist_sym(T, dist);
+			uint32_t sym = T.lenSym[len];
+			out[nt++] = sym | (ds << 9) | ((len - T.lenBase[len]) << 14) | ((dist - T.distBase[ds]) << 19);
+			gc_gz_count(&sh.litFreq[sym]); gc_gz_count(&sh.distFreq[ds]);
+			if (i + len + 4 <= end)
+			{
+				uint32_t v2 = gc_deflate_load32(p + i + len - 1);
+				head[(v2 * 2654435761u) >> (32 - GC_GZ_HASH_BITS)] = (uint16_t)(i + len - 1 - begin);
+			}
+			i += len;
+		}
+		else { out[nt++] = (uint32_t)p[i] | (30u << 9); gc_gz_count(&sh.litFreq[p[i]]); i++; }
+	}
+	for (; i < end; i++) { out[nt++] = (uint32_t)p[i] | (30u << 9); gc_gz_count(&sh.litFreq[p[i]]); }
+	sh.laneTokens[lane] = nt;
+	sh.laneCrc[lane] = gc_crc_shift(T, gc_crc32(T, p + begin, end - begin), n - end);
+}
+// stage 2 (lane 0): the record's codes and everything that precedes the first chunk's codes
+GC_HD void gc_gz_header(GcGzShared& sh)
+{
+	const uint8_t gz[10] = { 0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4, 3 }; // deflate, no flags, mtime 0, XFL fastest, OS unix
+	for (int i = 0; i < 10; i++) sh.header[i] = gz[i];
+	GcBitWriter bw; bw.p = sh.header + 10; bw.acc = 0; bw.n = 0;
+	if (!gc_deflate_block_header(sh.litFreq, sh.distFreq, sh.litLens, sh.distLens, sh.litCodes, sh.distCodes, bw)) { sh.ok = 0; return; }
+	sh.headerBits = (uint32_t)(bw.p - sh.header) * 8 + (uint32_t)bw.n;
+	bw.flush();
+}
+// stage 3 (every lane): bits the lane will write
+GC_HD void gc_gz_bits(const GcDeflateTables& T, uint32_t n, uint32_t lane, const uint32_t* tokens, GcGzShared& sh)
+{
+	const uint32_t C = gc_gz_chunk(n);
+	const uint32_t begin = lane * C < n ? lane * C : n;
+	const uint32_t* tk = tokens + begin;
+	uint32_t bits = lane == 0 ? sh.headerBits : 0;
+	for (uint32_t t = 0; t < sh.laneTokens[lane]; t++)
+	{
+		uint32_t sym = tk[t] & 0x1FF, ds = (tk[t] >> 9) & 31;
+		bits += sh.litLens[sym] + T.symExtraBits[sym];
+		if (ds != 30) bits += sh.distLens[ds] + T.distExtraBits[ds];
+	}
+	if (lane == GC_GZ_LANES - 1) bits += sh.litLens[256]; // end of block
+	sh.laneBits[lane] = bits;
+}
+// 32-bit words of a lane's part of the bit stream: the first and the last word may hold a neighbour's bits as well
+struct GcWordWriter
+{
+	uint32_t* w; uint64_t acc; int n; bool first;
+	GC_HD void word(uint32_t v) { if (first) { gc_gz_or(w, v); first = false; } else *w = v; w++; }
+	GC_HD void put(uint32_t bits, int count) // count <= 32
+	{
+		acc |= (uint64_t)bits << n;
+		n += count;
+		if (n >= 32) { word((uint32_t)acc); acc >>= 32; n -= 32; }
+	}
+	GC_HD void finish() { if (n > 0) gc_gz_or(w, (uint32_t)acc); }
+};
+// stage 4 (every lane, after laneStart = exclusive scan of laneBits): clear the two words the lane may share
+GC_HD void gc_gz_prepare(uint32_t lane, const GcGzShared& sh, uint32_t* out32)
+{
+	const uint32_t s = sh.laneStart[lane], e = s + sh.laneBits[lane];
+	if (e == s) return;
+	out32[s >> 5] = 0;
+	out32[(e - 1) >> 5] = 0;
+}
+// stage 5 (every lane): the lane's codes
+GC_HD void gc_gz_emit(const GcDeflateTables& T, uint32_t n, uint32_t lane, const uint32_t* tokens, const GcGzShared& sh, uint32_t* out32)
+{
+	const uint32_t C = gc_gz_chunk(n);
+	const uint32_t begin = lane * C < n ? lane * C : n;
+	const uint32_t* tk = tokens + begin;
+	const uint32_t s = sh.laneStart[lane];
+	if (sh.laneBits[lane] == 0) return;
+	GcWordWriter ww; ww.w = out32 + (s >> 5); ww.acc = 0; ww.n = (int)(s & 31); ww.first = true;
+	if (lane == 0)
+	{
+		uint32_t full = sh.headerBits >> 3, rest = sh.headerBits & 7;
+		for (uint32_t b = 0; b < full; b++) ww.put(sh.header[b], 8);
+		if (rest) ww.put(sh.header[full] & ((1u << rest) - 1), (int)rest);
+	}
+	for (uint32_t t = 0; t < sh.laneTokens[lane]; t++)
+	{
+		uint32_t tok = tk[t];
+		uint32_t sym = tok & 0x1FF, ds = (tok >> 9) & 31;
+		int nb = sh.litLens[sym];
+		ww.put((uint32_t)sh.litCodes[sym] | (((tok >> 14) & 31) << nb), nb + T.symExtraBits[sym]);
+		if (ds != 30)
+		{
+			int db = sh.distLens[ds];
+			ww.put((uint32_t)sh.distCodes[ds] | ((tok >> 19) << db), db + T.distExtraBits[ds]);
+		}
+	}
+	if (lane == GC_GZ_LANES - 1) ww.put(sh.litCodes[256], sh.litLens[256]);
+	ww.finish();
+}
+// stage 6 (lane 0): CRC-32 and length after the last byte of the block; returns the member's size
+GC_HD uint32_t gc_gz_trailer(uint32_t n, const GcGzShared& sh, uint8_t* out)
+{
+	uint32_t totalBits = sh.laneStart[GC_GZ_LANES - 1] + sh.laneBits[GC_GZ_LANES - 1];
+	uint32_t crc = 0;
+	for (int l = 0; l < GC_GZ_LANES; l++) crc ^= sh.laneCrc[l];
+	uint8_t* end = out + (totalBits + 7) / 8;
 	for (int i = 0; i < 4; i++) *end++ = (uint8_t)(crc >> (8 * i));
 	for (int i = 0; i < 4; i++) *end++ = (uint8_t)(n >> (8 * i));
 	return (uint32_t)(end - out);
+}
+// capacity the member needs in the worst case (15 bits per literal + the code descriptions), and the largest record the chunk
+// positions (16 bits) can address; a record outside either is encoded on the host
+GC_HD bool gc_gz_fits(uint32_t n, uint32_t outCap) { return (uint64_t)outCap >= (uint64_t)n * 2 + 1024 && gc_gz_chunk(n) < 0xFFFFu; }
+
+// the stages in turn for lanes 0..31 on one thread (host-side test double; same bytes as the kernel)
+inline uint32_t gc_gzip_member(const GcDeflateTables& T, const uint8_t* raw, uint32_t n, GcDeflateWs& ws, uint8_t* out, uint32_t outCap)
+{
+	if (!gc_gz_fits(n, outCap)) return 0;
+	GcGzShared* shp = new GcGzShared; GcGzShared& sh = *shp;
+	uint32_t size = 0;
+	for (uint32_t l = 0; l < GC_GZ_LANES; l++) gc_gz_clear(sh, l);
+	for (uint32_t l = 0; l < GC_GZ_LANES; l++) gc_gz_tokenize(T, raw, n, l, ws.tokens, sh);
+	gc_gz_header(sh);
+	if (sh.ok)
+	{
+		for (uint32_t l = 0; l < GC_GZ_LANES; l++) gc_gz_bits(T, n, l, ws.tokens, sh);
+		uint32_t at = 0;
+		for (uint32_t l = 0; l < GC_GZ_LANES; l++) { sh.laneStart[l] = at; at += sh.laneBits[l]; }
+		for (uint32_t l = 0; l < GC_GZ_LANES; l++) gc_gz_prepare(l, sh, (uint32_t*)out);
+		for (uint32_t l = 0; l < GC_GZ_LANES; l++) gc_gz_emit(T, n, l, ws.tokens, sh, (uint32_t*)out);
+		size = gc_gz_trailer(n, sh, out);
+	}
+	delete shp;
+	return size;
 }

@@ -602,21 +602,16 @@ static int buildPlanes(gcgpu_ctx* ctx, uint64_t bytes)
 	return GCGPU_OK;
 }
 // Long items run either lane-per-item (gc_k1s_*: 32 items per warp, ~1/12 of the issue slots per column step, but a walk takes
-// ~280 us per 64-row slice because every lane waits for the slowest lane's bookkeeping) or warp-per-item in lock-step
-// (gc_k1_long_*: ~22 us per slice, 32 redundant lanes: a launch of more than a few thousand items saturates the integer pipe for
-// ~22 ns per item-slice and starves the kernels of the other batches in flight).  Per launch, from the items' slice counts:
-//   lock-step time ~ max(longest item x 22 us, sum of slices x 22 ns);  lane-per-item time ~ longest item x 280 us
-// and the lane-per-item form is taken unless it is estimated more than four times slower (measurements: profiles/r03d, r03f, r03h:
-// c2 round 2 goes lane-per-item, the one-seed-per-read first round and the tail rounds lock-step, ultra-long reads lock-step).
+// ~270 us per 64-row slice because every lane waits for the slowest lane's bookkeeping -- a launch lasts as long as its longest
+// item) or warp-per-item in lock-step (gc_k1_long_*: ~22 us per slice, 32 redundant lanes: a launch of more than a few thousand
+// items saturates the integer pipe for ~22 ns per item-slice and starves the kernels of the other batches in flight).  Per launch,
+// from the items' slice counts:
+//   lock-step time ~ max(longest item x 22 us, sum of slices x 22 ns);  lane-per-item time ~ longest item x 270 us
+// and the lane-per-item form is taken unless it is estimated more than four times slower (measurements: profiles/r03d, r03f, r03h,
+// r03o: c2 round 2 goes lane-per-item, the one-seed-per-read first round and the tail rounds lock-step, ultra-long reads lock-step).
+// Splitting ONE launch between the forms -- its longest items lock-step on a side stream, the rest lane-per-item beside them --
+// does not pay: the two groups slow each other down (r03r: 49-50 ms against 43 ms lane-per-item only, e2e 171 vs 208 Mbp/s).
 // GCGPU_K1_FORM=lane | lockstep forces one form.
-// Fewest lanes per warp that take items in a lane-per-item launch (GCGPU_K1_LANES overrides).  32: a launch lasts as long as
-// its longest item whatever the number of warps (r03m: 47.6 / 49.7 / 49.9 / 49.4 ms at 32 / 16 / 8 / 4 lanes), and a launch
-// spread over more warps leaves fewer SM slots to the launches of the other batches in flight (e2e 199.6 vs 174.4 Mbp/s at 32 vs 16)
-static uint32_t k1MinLanes()
-{
-	static const uint32_t v = [] { const char* e = getenv("GCGPU_K1_LANES"); int x = e ? atoi(e) : 32; return (uint32_t)(x < 1 ? 1 : (x > 32 ? 32 : x)); }();
-	return v;
-}
 static bool k1UseLaneForm(uint32_t nLong, uint64_t sumSlices, uint32_t maxSlices)
 {
 	const char* force = getenv("GCGPU_K1_FORM");
@@ -624,8 +619,16 @@ static bool k1UseLaneForm(uint32_t nLong, uint64_t sumSlices, uint32_t maxSlices
 	if (force && !strcmp(force, "lockstep")) return false;
 	if (nLong < 1024) return false;
 	double tLock = std::max((double)maxSlices * 0.022, (double)sumSlices * 2.2e-5);               // ms
-	double tLane = (double)maxSlices * 0.28 * std::max(1.0, (double)nLong / (32.0 * 148 * 8));   // ms
+	double tLane = (double)maxSlices * 0.27 * std::max(1.0, (double)nLong / (32.0 * 148 * 12));   // ms
 	return tLane <= 4.0 * tLock;
+}
+// Fewest lanes per warp that take items in a lane-per-item launch (GCGPU_K1_LANES overrides).  32: a launch lasts as long as
+// its longest item whatever the number of warps (r03m: 47.6 / 49.7 / 49.9 / 49.4 ms at 32 / 16 / 8 / 4 lanes), and a launch
+// spread over more warps leaves fewer SM slots to the launches of the other batches in flight (e2e 199.6 vs 174.4 Mbp/s at 32 vs 16)
+static uint32_t k1MinLanes()
+{
+	static const uint32_t v = [] { const char* e = getenv("GCGPU_K1_LANES"); int x = e ? atoi(e) : 32; return (uint32_t)(x < 1 ? 1 : (x > 32 ? 32 : x)); }();
+	return v;
 }
 
 static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* lens, uint32_t n, int32_t uniformMax, GcK1Run& run)
@@ -707,6 +710,7 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	{
 		uint64_t sumSlices = 0; uint32_t maxSlices = 0;
 		for (const GcK1Desc& d : descs) { sumSlices += d.numSlices; if (d.numSlices > maxSlices) maxSlices = d.numSlices; }
+		const GcK1Desc* dDescs = (const GcK1Desc*)ctx->descBuf.p;
 		if (k1UseLaneForm(nLong, sumSlices, maxSlices))
 		{
 			// lane per item: persistent warps whose lanes take items (sorted by length, longest first) from a counter until none is left
@@ -717,7 +721,6 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.bt, gc_k1s_backtrace_kernel, GC_K1S_THREADS, 0) != cudaSuccess || r.bt < 1) r.bt = 1;
 				return r;
 			}();
-			const int fwdPerSM = resident.fwd, btPerSM = resident.bt;
 			uint32_t* dNext = (uint32_t*)(R + offScalars + 16); // two counters, zeroed with the scalars above
 			const uint32_t warpsPerBlock = GC_K1S_THREADS / 32;
 			auto shape = [&](int perSM, uint32_t& blocks, uint32_t& lanes)
@@ -730,16 +733,16 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 				if (blocks > maxBlocks) blocks = maxBlocks;
 			};
 			uint32_t blocksF, lanesF, blocksB, lanesB;
-			shape(fwdPerSM, blocksF, lanesF);
-			shape(btPerSM, blocksB, lanesB);
-			gc_k1s_forward_kernel<<<blocksF, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, dNext, lanesF, (uint8_t*)ctx->arena.p, dRes, dSlot, dOverflow, dLast);
-			gc_k1s_backtrace_kernel<<<blocksB, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, dNext + 1, lanesB, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			shape(resident.fwd, blocksF, lanesF);
+			shape(resident.bt, blocksB, lanesB);
+			gc_k1s_forward_kernel<<<blocksF, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, dDescs, nLong, dNext, lanesF, (uint8_t*)ctx->arena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1s_backtrace_kernel<<<blocksB, GC_K1S_THREADS, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, (const uint64_t*)ctx->planes.p, dItems, dDescs, nLong, dNext + 1, lanesB, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
 		}
 		else
 		{
 			// one warp per item in lock-step; resident blocks per SM: 5 (96 registers)
-			gc_k1_long_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
-			gc_k1_long_bt_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, (const GcK1Desc*)ctx->descBuf.p, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
+			gc_k1_long_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dDescs, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast);
+			gc_k1_long_bt_kernel<5, 32><<<(nLong + 3) / 4, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, dDescs, nLong, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast);
 		}
 		ctx->launches += 2;
 	}

@@ -956,26 +956,48 @@ __global__ void gc_gam_size_kernel(GcNameTable nt, const gcgpu_gam_read* __restr
 	rawLen[i] = len;
 	slotBytes[i] = (((uint64_t)len + 16 + 127) / 128 + ((uint64_t)len * 2 + 1024 + 127) / 128 + (gc_deflate_ws_bytes(len) + 127) / 128) * 128;
 }
-// one record = one warp of which lane 0 works: the walk of a record is a chain of data-dependent branches (literal or match, code
-// lengths, ...), so 32 records in the lanes of one warp serialise (61 ms per 1587 records); alone in its warp a walk runs at the
-// single-thread rate (~5 ms) and the launch still holds only a dozen warps per SM.
-__global__ void __launch_bounds__(64) gc_gam_kernel(GcNameTable nt, const GcDeflateTables* __restrict__ tables, const gcgpu_gam_read* __restrict__ reads, uint32_t n, const GcGamAln* __restrict__ alns, const uint32_t* __restrict__ tokens,
+// One record = one warp (a block of 32 threads).  Lane 0 writes the record -- a chain of data-dependent varint fields -- and the 32
+// lanes then make its gzip member together (gc_gam.cuh: chunk-parallel LZ77 parse, one Huffman code, every lane writes its chunk's
+// codes at its bit offset).  r03j, lane 0 doing everything and the other 63 threads of the block idle: ~15 ms per 1678 records and
+// a block's registers held for all of it.
+__global__ void __launch_bounds__(32) gc_gam_kernel(GcNameTable nt, const GcDeflateTables* __restrict__ tables, const gcgpu_gam_read* __restrict__ reads, uint32_t n, const GcGamAln* __restrict__ alns, const uint32_t* __restrict__ tokens,
 	const GcReadDesc* __restrict__ readDescs, const uint8_t* __restrict__ chars, const uint8_t* __restrict__ names, const uint32_t* __restrict__ rawLen, const uint64_t* __restrict__ slotOff, uint8_t* arena, uint64_t* __restrict__ memberLen)
 {
-	if (threadIdx.x & 31) return;
-	uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	__shared__ GcGzShared sh;
+	const uint32_t lane = threadIdx.x, i = blockIdx.x;
 	if (i > n) return;
-	if (i == n) { memberLen[i] = 0; return; }
+	if (i == n) { if (lane == 0) memberLen[i] = 0; return; }
 	gcgpu_gam_read rd = reads[i];
 	const uint32_t len = rawLen[i];
 	uint8_t* raw = arena + slotOff[i];
 	uint8_t* gz = raw + ((uint64_t)len + 16 + 127) / 128 * 128;
 	const uint32_t gzCap = len * 2 + 1024;
-	uint8_t* wsBase = gz + ((uint64_t)gzCap + 127) / 128 * 128;
-	GcDeflateWs ws; ws.head = (int32_t*)wsBase; ws.tokens = (uint32_t*)(wsBase + ((size_t)4 << GC_DEFLATE_HASH_BITS)); ws.tokenCap = len + 16;
-	uint32_t written = gc_gam_write_record(nt, chars + readDescs[rd.read].charOffset, names + rd.name_offset, rd.name_len, alns + rd.first_aln, rd.num_alns, tokens, raw);
-	uint32_t size = written == len ? gc_gzip_member(*tables, raw, len, ws, gz, gzCap) : 0;
-	memberLen[i] = size;
+	uint32_t* lzTokens = (uint32_t*)(gz + ((uint64_t)gzCap + 127) / 128 * 128);
+	uint32_t written = 0;
+	if (lane == 0) written = gc_gam_write_record(nt, chars + readDescs[rd.read].charOffset, names + rd.name_offset, rd.name_len, alns + rd.first_aln, rd.num_alns, tokens, raw);
+	written = __shfl_sync(0xFFFFFFFFu, written, 0);
+	if (written != len || !gc_gz_fits(len, gzCap)) { if (lane == 0) memberLen[i] = 0; return; } // the host encodes this record
+	gc_gz_clear(sh, lane);
+	__syncwarp();
+	gc_gz_tokenize(*tables, raw, len, lane, lzTokens, sh);
+	__syncwarp();
+	if (lane == 0) gc_gz_header(sh);
+	__syncwarp();
+	if (!sh.ok) { if (lane == 0) memberLen[i] = 0; return; }
+	gc_gz_bits(*tables, len, lane, lzTokens, sh);
+	__syncwarp();
+	{
+		const uint32_t bits = sh.laneBits[lane];
+		uint32_t incl = bits;
+		for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
+		sh.laneStart[lane] = incl - bits;
+	}
+	__syncwarp();
+	gc_gz_prepare(lane, sh, (uint32_t*)gz);
+	__syncwarp();
+	gc_gz_emit(*tables, len, lane, lzTokens, sh, (uint32_t*)gz);
+	__syncwarp();
+	if (lane == 0) memberLen[i] = gc_gz_trailer(len, sh, gz);
 }
 __global__ void gc_gam_gather_kernel(const uint64_t* __restrict__ slotOff, const uint32_t* __restrict__ rawLen, const uint64_t* __restrict__ memberLen, const uint64_t* __restrict__ memberOff, uint32_t n, const uint8_t* __restrict__ arena, uint8_t* __restrict__ out)
 {
@@ -1053,7 +1075,7 @@ extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* r
 	CUDA_TRY(gcCopy(ctx, &arenaBytes, dSlotO + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
 	CUDA_TRY(R->gamArena.ensure(arenaBytes + 256));
-	gc_gam_kernel<<<(n + 1 + 1) / 2, 64, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
+	gc_gam_kernel<<<n + 1, 32, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
 		I + oNames, dRawLen, dSlotO, (uint8_t*)R->gamArena.p, dMemL);
 	ctx->launches++;
 	rc = scanU64(ctx, dMemL, dMemO, n); if (rc != GCGPU_OK) return rc;

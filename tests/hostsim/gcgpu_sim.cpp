@@ -566,7 +566,7 @@ extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* r
 		const gcgpu_gam_read& rd = reads[i];
 		uint32_t len = gc_gam_record_size(nt, ga.data() + rd.first_aln, rd.num_alns, tokens.data(), rd.name_len);
 		std::vector<uint8_t> raw(len + 16), gz((size_t)len * 2 + 1024), wsBuf(gc_deflate_ws_bytes(len));
-		GcDeflateWs ws; ws.head = (int32_t*)wsBuf.data(); ws.tokens = (uint32_t*)(wsBuf.data() + ((size_t)4 << GC_DEFLATE_HASH_BITS)); ws.tokenCap = len + 16;
+		GcDeflateWs ws; ws.tokens = (uint32_t*)wsBuf.data(); ws.tokenCap = len + 16;
 		uint32_t written = gc_gam_write_record(nt, (const uint8_t*)ctx->charsCopy.data() + ctx->reads[rd.read].charOffset, (const uint8_t*)names + rd.name_offset, rd.name_len, ga.data() + rd.first_aln, rd.num_alns, tokens.data(), raw.data());
 		uint32_t size = written == len ? gc_gzip_member(ctx->gamTables, raw.data(), len, ws, gz.data(), (uint32_t)gz.size()) : 0;
 		ctx->gamOut.insert(ctx->gamOut.end(), gz.begin(), gz.begin() + size);
