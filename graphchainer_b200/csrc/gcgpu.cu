@@ -33,16 +33,18 @@ static int setError(int code, const std::string& msg) { g_lastError = msg; retur
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return setError(_e == cudaErrorMemoryAllocation ? GCGPU_ERR_NOMEM : GCGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
 
 // growable device buffer
+static const bool g_traceMem = getenv("GCGPU_TRACE_MEM") != nullptr;
 struct DevBuf
 {
 	void* p = nullptr;
 	size_t cap = 0;
-	cudaError_t ensure(size_t bytes)
+	cudaError_t ensure(size_t bytes, int line = __builtin_LINE())
 	{
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 4 + 4096;
+		size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)1 << 30) + 4096; // a quarter of headroom (batches differ by a few per cent), at most 1 GB
+		if (g_traceMem && want >= ((size_t)1 << 30)) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fprintf(stderr, "[gcgpu] device buffer grows to %.2f GB (%.1f of %.1f GB free), libgcgpu source line %d\n", want / 1e9, fr / 1e9, tot / 1e9, line); }
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; } // the failed attempt must not stay behind as the "last error" of the next launch check
 		if (e == cudaSuccess) cap = want; else { cudaGetLastError(); p = nullptr; }
@@ -118,12 +120,12 @@ static cudaError_t gcCopy(gcgpu_ctx* ctx, void* dst, const void* src, size_t byt
 	return cudaMemcpyAsync(dst, src, bytes, kind, stream);
 }
 // grow a device buffer to `bytes`, keeping its first `keep` bytes
-static cudaError_t growKeep(gcgpu_ctx* ctx, DevBuf& b, size_t bytes, size_t keep)
+static cudaError_t growKeep(gcgpu_ctx* ctx, DevBuf& b, size_t bytes, size_t keep, int line = __builtin_LINE())
 {
 	if (bytes <= b.cap) return cudaSuccess;
-	if (keep == 0 || !b.p) return b.ensure(bytes);
+	if (keep == 0 || !b.p) return b.ensure(bytes, line);
 	DevBuf nb;
-	cudaError_t e = nb.ensure(bytes + bytes / 2);
+	cudaError_t e = nb.ensure(bytes, line); // ensure() adds its own quarter of headroom; old and new buffer exist side by side until the copy is done
 	if (e != cudaSuccess) return e;
 	e = cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream);
 	if (e != cudaSuccess) { nb.release(); return e; }
@@ -158,9 +160,11 @@ static size_t k1WorkspaceBytes(uint32_t numSlices, uint32_t itemCap, uint32_t he
 // Short work items (35-bp fragments: one or two slices): one thread = one item; the millions of
 // independent items of a batch supply the parallelism.  Workspaces and trace slots are uniform, so
 // the kernel derives them from the item index -- the host uploads nothing but the items themselves.
+#define GC_K1_SHORT_SLOTS (2u << 20)
 struct GcK1ShortLayout
 {
 	uint64_t wsBase, wsStride;      // bytes
+	uint32_t first;                 // first item of this launch: a batch's items go through the same wsSlots slabs chunk after chunk
 	uint64_t traceBase;             // entries
 	uint32_t traceStride;           // entries
 	uint32_t itemCap, heapCap, numSlices;
@@ -171,7 +175,7 @@ __device__ __forceinline__ GcK1Desc gc_k1_short_desc(const gcgpu_ext_item* __res
 	gcgpu_ext_item it = items[idx];
 	GcK1Desc d;
 	d.seqOff = it.seq_offset; d.seqLen = it.seq_len; d.node = it.node; d.offset = it.offset;
-	d.wsOff = lay.wsBase + (uint64_t)t * lay.wsStride;
+	d.wsOff = lay.wsBase + (uint64_t)(t - lay.first) * lay.wsStride;
 	d.traceOff = lay.traceBase + (uint64_t)t * lay.traceStride;
 	d.itemCap = lay.itemCap; d.heapCap = lay.heapCap; d.traceCap = lay.traceStride; d.numSlices = lay.numSlices; d.resultIndex = idx;
 	return d;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(128) gc_k1_kernel(GcGraphView g, const GcViter
 	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
 	uint64_t* traceOffOfItem, uint32_t* overflow, int32_t* lastSlice)
 {
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t t = lay.first + blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
 	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
 	GcK1Workspace ws;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(128) gc_k1_bt_kernel(GcGraphView g, const uint
 	const gcgpu_ext_item* __restrict__ items, const uint32_t* __restrict__ shortIdx, uint32_t n, GcK1ShortLayout lay, uint8_t* arena, uint64_t* traceArena, GcK1Result* results,
 	const int32_t* __restrict__ lastSlice)
 {
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t t = lay.first + blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
 	GcK1Desc d = gc_k1_short_desc(items, shortIdx, t, lay);
 	GcK1Result res = results[d.resultIndex];
@@ -678,9 +682,17 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	GcK1ShortLayout lay;
 	lay.numSlices = (uint32_t)((maxShort + 63) / 64); if (lay.numSlices < 1) lay.numSlices = 1;
 	lay.itemCap = 24 + 8 * lay.numSlices; lay.heapCap = 64;
-	lay.wsBase = wsTotal; lay.wsStride = alignUp(k1WorkspaceBytes(lay.numSlices, lay.itemCap, lay.heapCap), 128);
+	// slices | items | heap: the thread-per-item kernels keep no per-item seeding records or slice keys (gc_k1_workspace) -- a batch of
+	// HiFi reads is ~10 M fragment items (c5: 25 GB of slabs per 16.8 Mbp batch even so)
+	lay.wsBase = wsTotal; lay.wsStride = alignUp(alignUp((size_t)(lay.numSlices + 2) * sizeof(GcSliceMeta), 16) + (size_t)lay.itemCap * sizeof(GcNodeItem) + (size_t)lay.heapCap * 8, 128);
 	lay.traceBase = traceTotal; lay.traceStride = (uint32_t)(2 * maxShort + 72);
-	wsTotal += (size_t)nShort * lay.wsStride;
+	// the slabs are needed from an item's forward pass to its backtrace only: at most GC_K1_SHORT_SLOTS of them, shared by successive
+	// chunks of the launch (c5: ~9 M fragment items per 16.8 Mbp batch were 20 GB of slabs per batch in flight)
+	const char* slotEnv = getenv("GCGPU_K1_SHORT_SLOTS"); // the override is for tests
+	const uint32_t slotLimit = slotEnv && atol(slotEnv) >= 128 ? (uint32_t)atol(slotEnv) : GC_K1_SHORT_SLOTS;
+	const uint32_t shortSlots = std::min<uint32_t>(nShort, slotLimit);
+	lay.first = 0;
+	wsTotal += (size_t)shortSlots * lay.wsStride;
 	traceTotal += (uint64_t)nShort * lay.traceStride;
 	// small per-call device arrays: internal results | trace slot of every item | lengths | offsets | public results | scalars
 	size_t offRes = 0, offSlot = alignUp(offRes + (size_t)n * sizeof(GcK1Result), 128), offLens = alignUp(offSlot + (size_t)n * 8, 128), offOffs = alignUp(offLens + (size_t)n * 8, 128);
@@ -749,9 +761,14 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 	if (nShort)
 	{
 		// lastSlice entries of the short items follow those of the long items
-		gc_k1_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast + nLong);
-		gc_k1_bt_kernel<<<(nShort + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, nShort, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast + nLong);
-		ctx->launches += 2;
+		for (uint32_t first = 0; first < nShort; first += shortSlots)
+		{
+			const uint32_t upTo = std::min(nShort, first + shortSlots);
+			lay.first = first;
+			gc_k1_kernel<<<(upTo - first + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, ctx->d_vt, prm, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, upTo, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dSlot, dOverflow, dLast + nLong);
+			gc_k1_bt_kernel<<<(upTo - first + 127) / 128, 128, 0, ctx->stream>>>(ctx->view, (const uint8_t*)ctx->seqBuf.p, dItems, dShortIdx, upTo, lay, (uint8_t*)ctx->arena.p, (uint64_t*)ctx->traceArena.p, dRes, dLast + nLong);
+			ctx->launches += 2;
+		}
 	}
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -837,6 +854,9 @@ static int k1Gather(gcgpu_ctx* ctx, const GcK1Run& run, DevBuf& dense, uint64_t 
 	uint64_t used = 0;
 	CUDA_TRY(gcCopy(ctx, &used, run.dTotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
+	// growing the dense buffer holds its old and new copy for a moment: the slabs of the launch that just ended are dead by now, and
+	// when they are tens of GB (ultra-long reads, the whole read set as one batch) they are given back first
+	if ((denseStart + used) * 8 + 16 > dense.cap && ctx->arena.cap > ((size_t)8 << 30)) ctx->arena.release();
 	CUDA_TRY(growKeep(ctx, dense, (denseStart + used) * 8 + 16, denseStart * 8));
 	gc_k1_gather_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(run.dRes, run.dSlot, run.dOffs, n, (const uint64_t*)ctx->traceArena.p, (uint64_t*)dense.p, denseStart, run.dPub);
 	ctx->launches += 4;

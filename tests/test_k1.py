@@ -61,11 +61,14 @@ def _replay_on_gpu(idx_path, st_path, max_reads=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("form", ["auto", "lane", "lockstep"])
+@pytest.mark.parametrize("form", ["auto", "lane", "lockstep", "slots"])
 def test_k1_gpu_matches_golden(golden_files, form):
     """form: which kernels take the whole-read extensions -- lane-per-item (gc_k1s_*), warp-per-item in lock-step (gc_k1_long_*),
-    or the library's per-launch choice (GCGPU_K1_FORM)."""
-    if form != "auto":
+    or the library's per-launch choice (GCGPU_K1_FORM); slots: the fragment items go through a pool of 256 slabs chunk after chunk
+    (GCGPU_K1_SHORT_SLOTS; the default pool of 2 M slabs is only exceeded by HiFi-sized batches)."""
+    if form == "slots":
+        os.environ["GCGPU_K1_SHORT_SLOTS"] = "256"
+    elif form != "auto":
         os.environ["GCGPU_K1_FORM"] = form
     try:
         for name, (idx, st) in golden_files.items():
@@ -73,6 +76,7 @@ def test_k1_gpu_matches_golden(golden_files, form):
             assert n > 0 and bad == 0, f"{name} ({form}): {bad}/{n} extensions differ from the reference"
     finally:
         os.environ.pop("GCGPU_K1_FORM", None)
+        os.environ.pop("GCGPU_K1_SHORT_SLOTS", None)
 
 
 @pytest.mark.gpu
