@@ -113,18 +113,40 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	if (gam_used) *gam_used = 0;
 	if (stats) memset(stats, 0, sizeof(*stats));
 	int hostThreads = h->opts.host_threads > 0 ? h->opts.host_threads : omp_get_max_threads();
-	uint64_t batchBp = h->opts.batch_bp ? h->opts.batch_bp : (16u << 20); // the lane-per-item K1 kernels want thousands of whole-read extensions per launch (profiles/r03f: 8 -> 16 Mbp batches, e2e +17 %)
-	// batches of ~batch_bp read bases, handed to the workers in order
-	std::vector<std::pair<uint32_t, uint32_t>> batches;
-	for (uint32_t first = 0; first < num_reads; )
+	// Batches of read bases, handed to the workers in order.  Default: as many equal batches as there are workers (one round: a
+	// worker that takes a second batch while the others idle costs more than larger batches gain -- c3, 150 Mbp on 6 workers:
+	// 6 x 25 Mbp 167 Mbp/s, 9 x 16.8 Mbp 144, 12 x 12.6 Mbp 137, profiles/r03z), more rounds once a batch would exceed 26 Mbp
+	// (device memory: ~0.5 GB of trace slots per Mbp of HiFi reads), fewer batches when they would fall below 8 Mbp (the K1 launches
+	// of a batch last as long as their longest read whatever the batch size).  opts.batch_bp sets the batch size outright.
+	const uint64_t totalBp = num_reads ? seq_offsets[num_reads] - seq_offsets[0] : 0;
+	// Ultra-long reads: every seed extension reserves slabs and a trace slot for the rest of its read, ~4 GB of device buffers per
+	// Mbp of 50-100 kb reads (c4; 0.6 GB per Mbp of 10-20 kb reads) -- three batches in flight, not six (profiles/r04b: six ran a
+	// 180 GB device out of memory).  Sizing the trace slots after the forward pass would lift this.
+	size_t inFlight = std::max<size_t>(1, h->workers.size());
+	if (num_reads && totalBp / num_reads > 30000) inFlight = std::min<size_t>(inFlight, 3);
+	uint64_t count;
+	if (h->opts.batch_bp) count = std::max<uint64_t>(1, (totalBp + h->opts.batch_bp - 1) / h->opts.batch_bp);
+	else
 	{
-		uint64_t bp = 0;
-		uint32_t r = first;
-		for (; r < num_reads && (bp < batchBp || r == first); r++) bp += seq_offsets[r + 1] - seq_offsets[r];
-		batches.emplace_back(first, r);
-		first = r;
+		const uint64_t workers = inFlight, largest = 26u << 20, smallest = 8u << 20;
+		count = workers * std::max<uint64_t>(1, (totalBp + workers * largest - 1) / (workers * largest));
+		if (count == workers && totalBp / workers < smallest) count = std::min<uint64_t>(workers, std::max<uint64_t>(1, (totalBp + smallest / 2) / smallest));
 	}
-	size_t W = std::min(h->workers.size(), std::max<size_t>(1, batches.size()));
+	// batch k ends with the read that reaches k + 1 shares of the bases
+	std::vector<std::pair<uint32_t, uint32_t>> batches;
+	{
+		uint32_t first = 0;
+		for (uint64_t k = 0; k < count && first < num_reads; k++)
+		{
+			const uint64_t upTo = k + 1 == count ? totalBp : (uint64_t)((double)totalBp * (double)(k + 1) / (double)count);
+			uint32_t r = first + 1;
+			while (r < num_reads && seq_offsets[r] - seq_offsets[0] < upTo) r++;
+			if (k + 1 == count) r = num_reads;
+			batches.emplace_back(first, r);
+			first = r;
+		}
+	}
+	size_t W = std::min(inFlight, std::max<size_t>(1, batches.size()));
 	// default: the batches in flight together hold ~2.25x as many threads as there are host threads -- a batch spends more than half
 	// of its time waiting for its kernels (threads asleep), measured best on B200 with 16 cores (profiles/r01h: 6 streams x 6 threads)
 	int threadsPerWorker = h->opts.threads_per_stream > 0 ? h->opts.threads_per_stream : std::min(hostThreads, std::max(1, (hostThreads * 9 + 4 * (int)W - 1) / (4 * (int)W)));

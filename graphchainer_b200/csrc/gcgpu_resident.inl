@@ -1087,26 +1087,6 @@ extern "C" int gcgpu_encode_gam(gcgpu_ctx* ctx, int set, const gcgpu_gam_read* r
 	uint64_t arenaBytes = 0;
 	CUDA_TRY(gcCopy(ctx, &arenaBytes, dSlotO + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(gcSyncStream(ctx));
-	if (getenv("GCGPU_DEBUG_GAM"))
-	{
-		std::vector<uint32_t> hRaw(n); std::vector<GcGamAln> hA(num_alns); std::vector<gcgpu_aln_tokens> hM(num_alns);
-		CUDA_TRY(gcCopy(ctx, hRaw.data(), dRawLen, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(gcCopy(ctx, hA.data(), dGAln, (size_t)num_alns * sizeof(GcGamAln), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(gcCopy(ctx, hM.data(), dMeta, (size_t)num_alns * sizeof(gcgpu_aln_tokens), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(gcSyncStream(ctx));
-		fprintf(stderr, "[gcgpu] encode_gam: n=%u alns=%u tokens=%llu arena=%llu\n", n, num_alns, (unsigned long long)totalTokens, (unsigned long long)arenaBytes);
-		int shown = 0;
-		for (uint32_t i = 0; i < n && shown < 6; i++)
-		{
-			const gcgpu_gam_read& rd = reads[i];
-			bool odd = hRaw[i] > 8u * R->hostReads[rd.read].len + 4096u;
-			if (!odd && i >= 2) continue;
-			shown++;
-			fprintf(stderr, "[gcgpu]   record %u read %u (len %u) alns %u raw %u:", i, rd.read, (unsigned)R->hostReads[rd.read].len, rd.num_alns, hRaw[i]);
-			for (uint32_t k = 0; k < rd.num_alns && k < 4; k++) { const GcGamAln& a = hA[rd.first_aln + k]; fprintf(stderr, " [%d,%d) tokOff %llu nTok %u (meta off %llu n %u) m %u s %u;", a.start, a.end, (unsigned long long)a.tokenOff, a.numTokens, (unsigned long long)hM[rd.first_aln + k].token_offset, hM[rd.first_aln + k].num_tokens, a.matches, a.steps); }
-			fprintf(stderr, "\n");
-		}
-	}
 	CUDA_TRY(R->gamArena.ensure(arenaBytes + 256));
 	gc_gam_kernel<<<n + 1, 32, 0, ctx->stream>>>(nt, R->d_gamTables, (const gcgpu_gam_read*)(I + oReads), n, dGAln, (const uint32_t*)R->tokens.p, (const GcReadDesc*)R->reads.p, (const uint8_t*)R->chars.p,
 		I + oNames, dRawLen, dSlotO, (uint8_t*)R->gamArena.p, dMemL);

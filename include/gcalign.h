@@ -30,7 +30,7 @@ typedef struct gcalign_options
 	int64_t colinear_gap;         /* --colinear-gap, default 10000                        */
 	int64_t colinear_split_len;   /* --colinear-split-len, default 35                     */
 	int64_t colinear_split_gap;   /* --colinear-split-gap, default 35                     */
-	uint64_t batch_bp;            /* read bases per internal GPU batch (0 = default)      */
+	uint64_t batch_bp;            /* read bases per internal GPU batch (0 = default: one round of equal batches over the streams, 8-26 Mbp each) */
 	int32_t gzip_level;           /* zlib level of the GAM gzip members: 0 = default (1, fastest);
 	                                 the reference's GzipOutputStream uses 6; decoded records
 	                                 are identical at every level                            */
