@@ -30,6 +30,8 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
+#include <cstring>
+#include <zlib.h>
 #include "gc_index.h"
 
 namespace gcbuild {
@@ -211,6 +213,128 @@ inline SplitGraph loadGfa(const std::string& filename)
 			addEdge(g, (int)fromRight, (int)toRight);
 			addEdge(g, (int)toLeft, (int)fromLeft);
 		}
+	}
+	return g;
+}
+
+// ---- .vg input (DirectedGraph::StreamVGGraphFromFile, BigraphToDigraph.cpp:134-179): a stream of vg::Graph messages in the framing of
+// stream.hpp:82-124 -- gzip members (or plain bytes) holding groups "varint64 count, {varint32 size, message}*".  Nodes are added in
+// file order with the digraph ids id*2 / id*2+1 (ConvertVGNodeToNodes, :67-72), then the edges in file order (ConvertVGEdgeToEdges,
+// :74-100).  Only the fields the reference reads are decoded: Graph.node (1), Graph.edge (2); Node.sequence (1), .name (2), .id (3);
+// Edge.from (1), .to (2), .from_start (3), .to_end (4), .overlap (5).
+struct VgReader
+{
+	const uint8_t* p; const uint8_t* end; bool ok = true;
+	VgReader(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
+	bool more() const { return ok && p < end; }
+	uint64_t varint()
+	{
+		uint64_t v = 0; int shift = 0;
+		while (p < end && shift < 64) { uint8_t b = *p++; v |= (uint64_t)(b & 0x7F) << shift; if (!(b & 0x80)) return v; shift += 7; }
+		ok = false; return 0;
+	}
+	VgReader sub() { uint64_t n = varint(); if (!ok || n > (uint64_t)(end - p)) { ok = false; return VgReader(p, p); } VgReader r(p, p + n); p += n; return r; }
+	void skip(uint32_t wire)
+	{
+		if (wire == 0) varint();
+		else if (wire == 1) { if (end - p < 8) ok = false; else p += 8; }
+		else if (wire == 2) sub();
+		else if (wire == 5) { if (end - p < 4) ok = false; else p += 4; }
+		else ok = false;
+	}
+};
+inline std::string vgFileBytes(const std::string& filename)
+{
+	std::ifstream file(filename, std::ios::in | std::ios::binary);
+	if (!file.good()) throw std::runtime_error("No graph file exists");
+	std::string raw((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+	if (raw.size() < 2 || (uint8_t)raw[0] != 0x1f || (uint8_t)raw[1] != 0x8b) return raw;
+	std::string data;
+	size_t at = 0;
+	std::vector<char> buf(1 << 20);
+	while (at < raw.size())
+	{
+		z_stream zs; memset(&zs, 0, sizeof(zs));
+		if (inflateInit2(&zs, 15 + 32) != Z_OK) throw std::runtime_error("zlib: inflateInit2 failed");
+		zs.next_in = (Bytef*)raw.data() + at; zs.avail_in = (uInt)std::min<size_t>(raw.size() - at, 1u << 30);
+		int ret;
+		do
+		{
+			zs.next_out = (Bytef*)buf.data(); zs.avail_out = (uInt)buf.size();
+			ret = inflate(&zs, Z_NO_FLUSH);
+			if (ret != Z_OK && ret != Z_STREAM_END) { inflateEnd(&zs); throw std::runtime_error("the .vg file is not a valid gzip stream"); }
+			data.append(buf.data(), buf.size() - zs.avail_out);
+			if (ret == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) { inflateEnd(&zs); throw std::runtime_error("the .vg file ends inside a gzip member"); }
+		} while (ret != Z_STREAM_END);
+		at = (size_t)((const char*)zs.next_in - raw.data());
+		inflateEnd(&zs);
+	}
+	return data;
+}
+inline SplitGraph loadVg(const std::string& filename)
+{
+	const std::string data = vgFileBytes(filename);
+	struct VgEdge { uint64_t from = 0, to = 0; bool fromStart = false, toEnd = false; int64_t overlap = 0; };
+	std::vector<VgEdge> edges;
+	SplitGraph g;
+	VgReader in((const uint8_t*)data.data(), (const uint8_t*)data.data() + data.size());
+	while (in.more())
+	{
+		uint64_t count = in.varint();
+		for (uint64_t m = 0; m < count && in.ok; m++)
+		{
+			VgReader graph = in.sub();
+			while (graph.more())
+			{
+				uint64_t key = graph.varint();
+				if ((key >> 3) == 1 && (key & 7) == 2)
+				{
+					VgReader node = graph.sub();
+					std::string sequence, name; int64_t id = 0;
+					while (node.more())
+					{
+						uint64_t k = node.varint();
+						if ((k >> 3) == 1 && (k & 7) == 2) { VgReader f = node.sub(); sequence.assign((const char*)f.p, f.end - f.p); }
+						else if ((k >> 3) == 2 && (k & 7) == 2) { VgReader f = node.sub(); name.assign((const char*)f.p, f.end - f.p); }
+						else if ((k >> 3) == 3 && (k & 7) == 0) id = (int64_t)node.varint();
+						else node.skip((uint32_t)(k & 7));
+					}
+					if (!node.ok) { graph.ok = false; break; }
+					if (id < 0 || id + 1 >= std::numeric_limits<int>::max() / 2) throw std::runtime_error("vg node id out of range: " + std::to_string(id));
+					std::string rc;
+					rc.reserve(sequence.size());
+					for (size_t i = sequence.size(); i-- > 0; ) rc += complement(sequence[i]);
+					addNode(g, (int)id * 2, sequence, name, false);
+					addNode(g, (int)id * 2 + 1, rc, name, true);
+				}
+				else if ((key >> 3) == 2 && (key & 7) == 2)
+				{
+					VgReader edge = graph.sub();
+					VgEdge e;
+					while (edge.more())
+					{
+						uint64_t k = edge.varint();
+						if ((k & 7) != 0) { edge.skip((uint32_t)(k & 7)); continue; }
+						uint64_t v = edge.varint();
+						switch (k >> 3) { case 1: e.from = v; break; case 2: e.to = v; break; case 3: e.fromStart = v != 0; break; case 4: e.toEnd = v != 0; break; case 5: e.overlap = (int64_t)v; break; default: break; }
+					}
+					if (!edge.ok) { graph.ok = false; break; }
+					edges.push_back(e);
+				}
+				else graph.skip((uint32_t)(key & 7));
+			}
+			if (!graph.ok) in.ok = false;
+		}
+	}
+	if (!in.ok) throw std::runtime_error("the .vg file is not a stream of vg::Graph messages");
+	for (const VgEdge& e : edges)
+	{
+		if (e.overlap != 0) throw std::runtime_error("Edge overlaps are not supported by the B200 path (only overlap 0)");
+		size_t fromLeft, fromRight, toLeft, toRight;
+		if (e.fromStart) { fromLeft = e.from * 2; fromRight = e.from * 2 + 1; } else { fromLeft = e.from * 2 + 1; fromRight = e.from * 2; }
+		if (e.toEnd) { toLeft = e.to * 2; toRight = e.to * 2 + 1; } else { toLeft = e.to * 2 + 1; toRight = e.to * 2; }
+		addEdge(g, (int)fromRight, (int)toRight);
+		addEdge(g, (int)toLeft, (int)fromLeft);
 	}
 	return g;
 }
@@ -903,7 +1027,8 @@ inline GcIndexFile toIndex(const SplitGraph& g, const MinimizerIndex& mz, size_t
 
 inline GcIndexFile buildIndexFromGfa(const std::string& gfaPath, size_t k, size_t windowSize, double discardMostNumerousFraction, bool verbose)
 {
-	SplitGraph g = loadGfa(gfaPath);
+	const bool vg = gfaPath.size() > 3 && gfaPath.compare(gfaPath.size() - 3, 3, ".vg") == 0; // getGraph, Aligner.cpp:1079-1100
+	SplitGraph g = vg ? loadVg(gfaPath) : loadGfa(gfaPath);
 	if (verbose) std::cout << "Build alignment graph" << std::endl;
 	componentOrder(g);
 	findChains(g);

@@ -48,7 +48,7 @@ static void usage()
 {
 	std::cerr <<
 		"Mandatory parameters:\n"
-		"  -g [ --graph ] arg            input graph (.gfa), or a prebuilt index with --gc-index\n"
+		"  -g [ --graph ] arg            input graph (.gfa / .vg), or a prebuilt index with --gc-index\n"
 		"  -f [ --reads ] arg            input reads (fasta or fastq, uncompressed or gzipped)\n"
 		"  -a [ --alignments-out ] arg   output alignment file (.gaf/.gam/.json)\n"
 		"  --cigar-match-mismatch        use M for matches and mismatches in the GAF cigar instead of = and X\n"

@@ -65,7 +65,7 @@ typedef struct gcalign_stats
 
 void gcalign_default_options(gcalign_options* opts);
 const char* gcalign_last_error(void);
-/* graph_path: *.gfa (index built here) or *.gcidx (prebuilt index) */
+/* graph_path: *.gfa or *.vg (index built here) or *.gcidx (prebuilt index) */
 int gcalign_open(const char* graph_path, const gcalign_options* opts, gcalign** out);
 void gcalign_close(gcalign* h);
 /* measurement aid: gcgpu_int_peak() of the handle's device (int32 LOP3/IADD3 instructions per second, thread level) */

@@ -16,7 +16,7 @@ from graphchainer_b200 import lib
 @pytest.fixture(scope="session")
 def buildindex(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("bld") / "gc_buildindex")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wno-sign-compare", "-o", out, os.path.join(ROOT, "graphchainer_b200", "csrc", "gc_buildindex.cpp")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wno-sign-compare", "-o", out, os.path.join(ROOT, "graphchainer_b200", "csrc", "gc_buildindex.cpp"), "-lz"], check=True)
     return out
 
 
