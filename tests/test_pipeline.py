@@ -32,6 +32,24 @@ def test_host_pipeline_matches_reference_gam(driver_sim, golden_files, tmp_path,
     assert not diffs, diffs
 
 
+def test_vg_graph_input_matches_reference_gam(driver_sim, tmp_path):
+    """The graph given as a .vg stream (tests/golden/tiny_vg.vg: the tiny graph with sparse node ids in two gzip members, made by
+    make_golden.gfa_to_vg): index built by gc_buildindex, GAM identical to the unmodified reference's on the same .vg
+    (StreamVGGraphFromFile, BigraphToDigraph.cpp:134-179) -- vg node ids and names in every Position."""
+    builder = str(tmp_path / "gc_buildindex")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wno-sign-compare", "-o", builder, os.path.join(ROOT, "graphchainer_b200", "csrc", "gc_buildindex.cpp"), "-lz"], check=True)
+    idx, out = str(tmp_path / "tiny_vg.gcidx"), str(tmp_path / "out.gam")
+    subprocess.run([builder, os.path.join(GOLDEN, "tiny_vg.vg"), idx, "--quiet"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([driver_sim, "--gc-index", idx, "-f", os.path.join(GOLDEN, "tiny.fa"), "-a", out, "-t", "4", "--gc-quiet"], check=True, stdout=subprocess.DEVNULL)
+    ours, ref = gam.read_gam(out), gam.read_gam(os.path.join(GOLDEN, "tiny_vg.gam"))
+    assert len(ref) == 8
+    diffs = gam.diff_gam(ours, ref)
+    assert not diffs, diffs
+    # the ids are the .vg's (10, 13, 16, ...), not the dense ids the GFA path gives the same segments
+    node_ids = {int(m.get("node_id", 0)) for alns in ref.values() for a in alns for m in a["mappings"]}
+    assert node_ids and all(i >= 10 and (i - 10) % 3 == 0 for i in node_ids)
+
+
 _PROGRESS = re.compile(r"\d+ (\S+) len=(\d+) : chained (\d+) / (\d+) anchors, actual (\d+) bps, time \S+ \S+ \S+  score=(\d+) long_edit_distance=(\d+) one_node_overlaps=(\d+) / (\d+)")
 
 
