@@ -126,6 +126,28 @@ def parity_on_sample(ref_gam_path: str, our_members: dict, names):
     return {"reads": n, "reads_with_alignment_in_reference": aligned, "diffs": len(diffs), "first": diffs[:3]}
 
 
+def accuracy_on_sample(gfa: str, sample_reads, our_members: dict):
+    """The reference's evaluation table (scripts/summary.py; graphchainer_b200/summary.py) on the first reads of the timed output:
+    reads aligned, path bases per read base, edit distance between a read and the node sequences of its path per read base."""
+    from graphchainer_b200 import gam as gamlib, summary
+    segments = summary.load_gfa(gfa)
+    by_id = {i: s for i, s in enumerate(segments.values())}
+    rows = [["name", "length", "long_pathcnt", "long_path_bps", "long_revcnt", "", "", "", "long_align_rate", "global_ed_read_long", ""]]
+    for name, seq in sample_reads:
+        row = [name, str(len(seq))] + [""] * 9
+        member = our_members.get(name, b"")
+        msgs = gamlib.read_gam_messages(member).get(name, []) if len(member) else []
+        if msgs:
+            p = summary.path_of(gamlib.decode_alignment(msgs[-1]), segments, by_id)
+            row[2:5] = [str(p["path_cnt"]), str(p["path_bps"]), str(p["revcnt"])]
+            row[8] = str(p["path_bps"] / max(1, len(seq)))
+            row[9] = str(summary.edit_distance(seq, p["seq"]))
+        rows.append(row)
+    out = summary.accuracy(rows)
+    out["note"] = "first 100 reads of the timed output; edit distance = read against the whole nodes of its path (scripts/summary.py:79-90)"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,6 +354,7 @@ def main():
             line["value"] = None
             line["e2e"]["value"] = None
             line["rejected"] = "decoded GAM records of the sample differ from the reference's: no speed number is reported"
+        line["accuracy_on_sample"] = accuracy_on_sample(gfa, reads[:100], our_members)
     print(json.dumps(line))
 
 
