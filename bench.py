@@ -111,9 +111,13 @@ def write_repeated_fasta(path: str, reads, reps: int) -> int:
     return total
 
 
-def parity_on_sample(ref_gam_path: str, our_members: dict, names):
+def parity_on_sample(ref_gam_path: str, our_members: dict, names, gfa: str | None = None, reads_by_name: dict | None = None, extra=()):
     """Decoded-GAM equality of the reference's output and ours on the sample reads (no speed number
-    counts before it).  our_members: {name: gzip member bytes of that read's record(s)}."""
+    counts before it).  our_members: {name: gzip member bytes of that read's record(s)}.
+    The reference's multi-threaded runs are not run-to-run deterministic (c2, read_2220 / read_2329: 3 of 6 runs at -t 16 differ
+    from the others and from -t 1 in `identity` and a few edits, profiles/r04h_reference_nondeterminism.txt; our records did not
+    change in 8 M read-steps).  Reads that differ are therefore aligned again by the reference with ONE thread -- its canonical
+    output, the one the golden fixtures hold -- and only what differs from that counts."""
     from graphchainer_b200 import gam as gamlib
     with open(ref_gam_path, "rb") as f:
         ref = gamlib.read_gam_messages(f.read())
@@ -121,9 +125,24 @@ def parity_on_sample(ref_gam_path: str, our_members: dict, names):
     for name, member in our_members.items():
         if len(member):
             ours.update(gamlib.read_gam_messages(member))
-    n, diffs = gamlib.diff_messages(ours, ref, names=names, limit=5)
+    n, diffs = gamlib.diff_messages(ours, ref, names=names, limit=1000)
     aligned = sum(1 for x in names if x in ref)
-    return {"reads": n, "reads_with_alignment_in_reference": aligned, "diffs": len(diffs), "first": diffs[:3]}
+    out = {"reads": n, "reads_with_alignment_in_reference": aligned, "diffs": len(diffs), "first": diffs[:3]}
+    if diffs and gfa and reads_by_name and len(diffs) <= 200:
+        again = sorted({d.split(":")[0].split("[")[0] for d in diffs})
+        with tempfile.TemporaryDirectory() as d:
+            fa, g1 = os.path.join(d, "again.fa"), os.path.join(d, "again.gam")
+            with open(fa, "w") as f:
+                for name in again:
+                    f.write(f">{name}\n{reads_by_name[name]}\n")
+            time_reference(gfa, fa, 1, keep_gam=g1, extra=extra)
+            with open(g1, "rb") as f:
+                ref1 = gamlib.read_gam_messages(f.read())
+        _, diffs1 = gamlib.diff_messages(ours, ref1, names=again, limit=1000)
+        out = {"reads": n, "reads_with_alignment_in_reference": aligned, "diffs": len(diffs1), "first": diffs1[:3],
+               "rechecked": {"reads": again[:20], "differed_from_the_multi_threaded_run": len(diffs), "differ_from_the_single_threaded_run": len(diffs1),
+                             "note": "the reference's multi-threaded output is not run-to-run deterministic; differing reads were aligned again with -t 1"}}
+    return out
 
 
 def accuracy_on_sample(gfa: str, sample_reads, our_members: dict):
@@ -348,7 +367,7 @@ def main():
         line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": host_cores, "kind": "reference",
                                 "sample": f"first {sample} reads of rank 0's set ({bp} bp), unmodified reference sources built with shim headers (oracle/Makefile), -t {host_cores}, align phase only, {secs:.2f} s"}
         # parity gate: the timed workload's own reads, reference output vs the GAM records the timed e2e step produced
-        par = parity_on_sample(ref_gam, our_members, [r[0] for r in reads[:sample]])
+        par = parity_on_sample(ref_gam, our_members, [r[0] for r in reads[:sample]], gfa=gfa, reads_by_name={r[0]: r[1] for r in reads[:sample]}, extra=ref_extra)
         line["parity_on_sample"] = par
         if par["diffs"] != 0:
             line["value"] = None

@@ -34,7 +34,8 @@ _lib = None
 def load(path: str | None = None):
     """Load libgcalign.so (or an explicitly given build of it) and declare its entry points."""
     global _lib
-    if _lib is None or path is not None:
+    explicit = path is not None   # an explicitly given build (tests: the C-ABI test double) never becomes the default
+    if _lib is None or explicit:
         path = path or LIB_PATH
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run __graft_entry__.build() (no CPU fallback exists)")
@@ -45,6 +46,8 @@ def load(path: str | None = None):
         lib.gcalign_close.argtypes = [C.c_void_p]
         lib.gcalign_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.gcalign_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(Stats)]
+        if explicit:
+            return lib
         _lib = lib
     return _lib
 

@@ -43,7 +43,7 @@ struct DevBuf
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)1 << 30) + 4096; // a quarter of headroom (batches differ by a few per cent), at most 1 GB
+		size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)2 << 30) + 4096; // a quarter of headroom (batches differ by a few per cent), at most 2 GB
 		if (g_traceMem && want >= ((size_t)1 << 30)) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fprintf(stderr, "[gcgpu] device buffer grows to %.2f GB (%.1f of %.1f GB free), libgcgpu source line %d\n", want / 1e9, fr / 1e9, tot / 1e9, line); }
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; } // the failed attempt must not stay behind as the "last error" of the next launch check
