@@ -153,7 +153,6 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 	std::vector<std::vector<std::string>> records(batches.size());
 	std::vector<std::vector<GcReadResult>> allResults(batches.size());
 	std::vector<uint64_t> launches0(W), h2d0(W), d2h0(W);
-	std::atomic<size_t> nextBatch(0);
 	std::mutex errMutex; std::string error;
 	GcPipelineStats total;
 	auto tCall0 = std::chrono::steady_clock::now();
@@ -168,10 +167,11 @@ extern "C" int gcalign_align(gcalign* h, const char* seqs, const uint64_t* seq_o
 			GcPipeline& pipeline = *wk.pipeline;
 			pipeline.stats = GcPipelineStats();
 			std::vector<GcRead> batch;
-			while (true)
+			// worker w takes batches w, w + W, ...: the batches are equal, and a worker that sees the same share of the same input again
+			// (a caller streaming similar calls) finds its context's device buffers already the right size -- with a shared counter any
+			// worker got any batch, and a context regrew its multi-GB buffers whenever it met a slightly larger batch than before
+			for (size_t bi = w; bi < batches.size(); bi += W)
 			{
-				size_t bi = nextBatch.fetch_add(1);
-				if (bi >= batches.size()) break;
 				{ std::lock_guard<std::mutex> lock(errMutex); if (!error.empty()) break; }
 				batch.clear();
 				for (uint32_t r = batches[bi].first; r < batches[bi].second; r++)
