@@ -737,7 +737,9 @@ static int k1Run(gcgpu_ctx* ctx, const gcgpu_ext_item* dItems, const int32_t* le
 			const uint32_t warpsPerBlock = GC_K1S_THREADS / 32;
 			auto shape = [&](int perSM, uint32_t& blocks, uint32_t& lanes)
 			{
-				const uint32_t maxBlocks = (uint32_t)ctx->numSMs * (uint32_t)perSM;
+				uint32_t maxBlocks = (uint32_t)ctx->numSMs * (uint32_t)perSM;
+				const char* cap = getenv("GCGPU_K1_BLOCKS"); // tests: a handful of blocks, so that every lane works through many items
+				if (cap && atoi(cap) > 0) maxBlocks = std::min<uint32_t>(maxBlocks, (uint32_t)atoi(cap));
 				lanes = (nLong + maxBlocks * warpsPerBlock - 1) / (maxBlocks * warpsPerBlock);
 				if (lanes < k1MinLanes()) lanes = k1MinLanes();
 				if (lanes > 32) lanes = 32;

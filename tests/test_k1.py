@@ -61,13 +61,18 @@ def _replay_on_gpu(idx_path, st_path, max_reads=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("form", ["auto", "lane", "lockstep", "slots"])
+@pytest.mark.parametrize("form", ["auto", "lane", "lockstep", "slots", "queue"])
 def test_k1_gpu_matches_golden(golden_files, form):
     """form: which kernels take the whole-read extensions -- lane-per-item (gc_k1s_*), warp-per-item in lock-step (gc_k1_long_*),
     or the library's per-launch choice (GCGPU_K1_FORM); slots: the fragment items go through a pool of 256 slabs chunk after chunk
-    (GCGPU_K1_SHORT_SLOTS; the default pool of 2 M slabs is only exceeded by HiFi-sized batches)."""
+    (GCGPU_K1_SHORT_SLOTS; the default pool of 2 M slabs is only exceeded by HiFi-sized batches); queue: see below."""
     if form == "slots":
         os.environ["GCGPU_K1_SHORT_SLOTS"] = "256"
+    elif form == "queue":
+        # lane-per-item kernels on two blocks: 128 lanes take the launch's items one after the other from the counter (what
+        # happens on the full GPU once a launch has more items than resident lanes -- the whole read set as one batch)
+        os.environ["GCGPU_K1_FORM"] = "lane"
+        os.environ["GCGPU_K1_BLOCKS"] = "2"
     elif form != "auto":
         os.environ["GCGPU_K1_FORM"] = form
     try:
@@ -77,6 +82,7 @@ def test_k1_gpu_matches_golden(golden_files, form):
     finally:
         os.environ.pop("GCGPU_K1_FORM", None)
         os.environ.pop("GCGPU_K1_SHORT_SLOTS", None)
+        os.environ.pop("GCGPU_K1_BLOCKS", None)
 
 
 @pytest.mark.gpu
@@ -92,10 +98,13 @@ def test_k1_gpu_matches_reference_on_fresh_synthetic(tmp_path):
     synth.write_fasta(fa, synth.simulate_reads(g, 60, 6000, 0.15, seed=22, novel_insertion_frac=0.1))
     idx, st = str(tmp_path / "x.gcidx"), str(tmp_path / "x.stages")
     subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "-f", fa, "--gc-index", idx, "--gc-stages", st], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    for form in ("lane", "lockstep"):
-        os.environ["GCGPU_K1_FORM"] = form
+    for form in ("lane", "lockstep", "queue"):
+        os.environ["GCGPU_K1_FORM"] = "lane" if form == "queue" else form
+        if form == "queue":
+            os.environ["GCGPU_K1_BLOCKS"] = "3"   # > 5000 items through 192 lanes
         try:
             n, bad, cols = _replay_on_gpu(idx, st)
         finally:
             os.environ.pop("GCGPU_K1_FORM", None)
+            os.environ.pop("GCGPU_K1_BLOCKS", None)
         assert n > 5000 and bad == 0, f"{form}: {bad}/{n} extensions differ from the reference"
