@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libgcalign.so")
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("initial_bandwidth", C.c_int32), ("streams", C.c_int32),
-                ("colinear_gap", C.c_int64), ("colinear_split_len", C.c_int64), ("colinear_split_gap", C.c_int64), ("batch_bp", C.c_uint64), ("gzip_level", C.c_int32), ("threads_per_stream", C.c_int32)]
+                ("colinear_gap", C.c_int64), ("colinear_split_len", C.c_int64), ("colinear_split_gap", C.c_int64), ("batch_bp", C.c_uint64), ("gzip_level", C.c_int32), ("threads_per_stream", C.c_int32), ("no_colinear_chaining", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -96,7 +96,7 @@ class ReadBatch:
 
 class Aligner:
     def __init__(self, graph_path: str, device: int = 0, host_threads: int = 0, split_len: int = 35, split_gap: int = 35, colinear_gap: int = 10000, batch_bp: int = 0, streams: int = 0, gzip_level: int = 0, threads_per_stream: int = 0,
-                 lib_path: str | None = None):
+                 lib_path: str | None = None, colinear_chaining: bool = True):
         self.lib = load(lib_path)
         o = Options()
         self.lib.gcalign_default_options(C.byref(o))
@@ -104,6 +104,7 @@ class Aligner:
         o.colinear_split_len, o.colinear_split_gap, o.colinear_gap, o.batch_bp = split_len, split_gap, colinear_gap, batch_bp
         o.gzip_level = gzip_level
         o.threads_per_stream = threads_per_stream
+        o.no_colinear_chaining = 0 if colinear_chaining else 1
         h = C.c_void_p()
         rc = self.lib.gcalign_open(graph_path.encode(), C.byref(o), C.byref(h))
         if rc != 0:

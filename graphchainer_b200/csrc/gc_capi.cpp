@@ -87,6 +87,7 @@ extern "C" int gcalign_open(const char* graph_path, const gcalign_options* opts,
 		if (rc != GCGPU_OK) { std::string msg = gcgpu_last_error(); gcalign_close(h); return fail(rc, "gcalign_open: " + msg); }
 	}
 	h->pipe.colinearGap = h->opts.colinear_gap; h->pipe.colinearSplitLen = h->opts.colinear_split_len; h->pipe.colinearSplitGap = h->opts.colinear_split_gap;
+	h->pipe.colinearChaining = h->opts.no_colinear_chaining == 0;
 	*out = h;
 	return GCGPU_OK;
 }

@@ -61,6 +61,7 @@ static void usage()
 		"  -t [ --threads ] arg          host threads\n"
 		"  -b [ --bandwidth ] arg        alignment bandwidth [default 10]\n"
 		"  --short-verbose               print the per-read progress line\n"
+		"  --no-colinear-chaining        do not run colinear chaining and align as in GraphAligner, default parameters\n"
 		"B200 parameters:\n"
 		"  --gc-gpus N                   GPUs to use (reads are partitioned in length-balanced batches)\n"
 		"  --gc-streams N                read batches in flight per GPU [default 6]\n"
@@ -90,6 +91,7 @@ static DriverParams parseArgs(int argc, char** argv)
 		else if (a == "--colinear-split-gap") { p.pipe.colinearSplitGap = std::stoll(next()); splitGapGiven = true; }
 		else if (a == "--sampling-step") p.samplingStep = std::stod(next()); // README contract: a double (the reference parses long long)
 		else if (a == "--short-verbose") { p.shortVerbose = true; p.pipe.exactProgressLine = true; }
+		else if (a == "--no-colinear-chaining") p.pipe.colinearChaining = false;
 		else if (a == "--cigar-match-mismatch") p.cigarMatchMismatchMerge = true;
 		else if (a == "--gc-gpus") p.gpus = std::stoi(next());
 		else if (a == "--gc-gzip-level") p.gzipLevel = std::min(9, std::max(1, std::stoi(next())));
@@ -195,7 +197,9 @@ int main(int argc, char** argv)
 	DriverParams params = parseArgs(argc, argv);
 	mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, -1); mallopt(M_TOP_PAD, 256 << 20); // keep the per-batch vectors in the arenas (see gc_capi.cpp)
 	omp_set_num_threads((int)params.threads);
-	std::cout << "Co-linear chaining on splits=(" << params.pipe.colinearSplitLen << "," << params.pipe.colinearSplitGap << "," << params.pipe.colinearGap << ")" << std::endl;
+	std::cout << "Co-linear chaining " << (params.pipe.colinearChaining ? "on" : "off"); // Aligner.cpp:1127-1132
+	if (params.pipe.colinearChaining) std::cout << " splits=(" << params.pipe.colinearSplitLen << "," << params.pipe.colinearSplitGap << "," << params.pipe.colinearGap << ")";
+	std::cout << std::endl;
 	GcHostGraph graph;
 	auto t0 = std::chrono::steady_clock::now();
 	try
@@ -260,6 +264,7 @@ int main(int argc, char** argv)
 	if ((params.outGam != "" && !gamOut.good()) || (params.outJson != "" && !jsonOut.good()) || (params.outGaf != "" && !gafOut.good())) { std::cerr << "cannot open the alignment output file for writing" << std::endl; return 1; }
 	std::mutex outMutex, inMutex;
 	bool wroteAny = false;
+	size_t statAllAlns = 0; // stats.allAlignmentsCount: alignments before the selection of --no-colinear-chaining, the written ones otherwise (Aligner.cpp:924)
 	size_t statReads = 0, statBp = 0, statSeedsFound = 0, statSeedsExtended = 0, statReadsWithSeed = 0, statBpWithSeed = 0, statReadsWithAln = 0, statAlns = 0, statBpAln = 0, statFull = 0, statBpFull = 0;
 	size_t readCounter = 0;
 	bool anyDropped = false;
@@ -329,9 +334,10 @@ int main(int argc, char** argv)
 				statReads++; statBp += batch[r].sequence.size();
 				readCounter++;
 				statSeedsFound += res.seedsFound;
-				if (res.seedsFound) { statReadsWithSeed += 2; statBpWithSeed += 2 * batch[r].sequence.size(); }
+				statAllAlns += params.pipe.colinearChaining ? res.alignments.size() : res.alignmentsBeforeSelection;
+				if (res.seedsFound) { const size_t calls = params.pipe.colinearChaining ? 2 : 1; statReadsWithSeed += calls; statBpWithSeed += calls * batch[r].sequence.size(); } // once per getSeeds call
 				if (res.dropped || res.broke) anyDropped = true;
-				if (params.shortVerbose && res.seedsFound && !res.dropped)
+				if (params.shortVerbose && params.pipe.colinearChaining && res.seedsFound && !res.dropped) // the line is printed by the chaining branch only (Aligner.cpp:909-915)
 				{
 					std::string short_id;
 					for (char c : batch[r].name) { if (isspace(c)) break; short_id += c; }
@@ -383,7 +389,9 @@ int main(int argc, char** argv)
 	std::cout << "Seeds extended: " << statSeedsExtended << std::endl;
 	std::cout << "Reads with a seed: " << statReadsWithSeed << " (" << statBpWithSeed << "bp)" << std::endl;
 	std::cout << "Reads with an alignment: " << statReadsWithAln << std::endl;
-	std::cout << "Alignments: " << statAlns << " (" << statBpAln << "bp)" << std::endl;
+	std::cout << "Alignments: " << statAlns << " (" << statBpAln << "bp)";
+	if (statAllAlns > statAlns) std::cout << " (" << (statAllAlns - statAlns) << " additional alignments discarded)"; // Aligner.cpp:1303
+	std::cout << std::endl;
 	std::cout << "End-to-end alignments: " << statFull << " (" << statBpFull << "bp)" << std::endl;
 	if (anyDropped) std::cout << "Alignment broke with some reads. Look at stderr output." << std::endl;
 	gamOut.flush(); jsonOut.flush(); gafOut.flush();

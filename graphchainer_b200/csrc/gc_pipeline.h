@@ -74,6 +74,7 @@ struct GcReadResult
 	int oneNodeOverlapsNow = 0, oneNodeOverlapsAll = 0; // the reference's progress-line counters (Aligner.cpp:747,768-771,792,820)
 	bool hasLong = false;
 	size_t seedsFound = 0, seedsExtended = 0;
+	size_t alignmentsBeforeSelection = 0; // --no-colinear-chaining: stats.allAlignmentsCount counts the whole-read alignments before GreedyLength (Aligner.cpp:924-930)
 };
 
 struct GcPipelineParams
@@ -84,6 +85,9 @@ struct GcPipelineParams
 	long long colinearSplitLen = 35;
 	long long colinearSplitGap = 35;
 	bool tryAllSeeds = true;
+	// --no-colinear-chaining (AlignerMain.cpp:108,198-199): "align as in GraphAligner" -- the whole-read pass only (align_fn,
+	// Aligner.cpp:596-600), its alignments selected by GreedyLength (:927-930); no fragments, chain or NW distances
+	bool colinearChaining = true;
 	// The reference's progress line (--short-verbose, Aligner.cpp:909-915) prints, as "actual N bps", the LENGTH OF THE EDIT PATH of the
 	// chained alignment (`longest` is swapped with the converted trace, :875) -- of every read, also where the whole-read alignment is
 	// written.  The edit path is otherwise only computed where the chain wins (the decision needs the distance only); with this set it
@@ -334,7 +338,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 				// count sort + density cut + expansion, clustering, goodness order and the split pass's position order (the device
 				// holds the seeds in position order: "cells")
 				gcseed::seedRead(g, matches + matchOff[r], (size_t)(matchOff[r + 1] - matchOff[r]), reads[r].sequence.size(), params.minimizerSeedDensity, scratch, seedsOrdered[r], seedsByPos[r]);
-				out[r].seedsFound = 2 * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
+				out[r].seedsFound = (params.colinearChaining ? 2 : 1) * seedsOrdered[r].size(); // counted in align_fn and again for the split pass (Aligner.cpp:553,663)
 			}
 		}
 	}
@@ -537,6 +541,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	{
 		longSeedsExtended[r] = s1[r].seedsExtended;
 		if (out[r].dropped) { out[r].broke = true; s1[r].alns.clear(); continue; }
+		out[r].alignmentsBeforeSelection = s1[r].alns.size();
 		if (!s1[r].alns.empty()) longAlns[r] = gcpipe::selectGreedyLength(s1[r].alns);
 		s1[r].alns.clear();
 	}
@@ -545,6 +550,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	// in-order seed loop of each fragment and the anchors are evaluated on the device
 	const size_t len = (size_t)params.colinearSplitLen, sep = (size_t)params.colinearSplitGap;
 	std::vector<gcgpu_read_anchors> perRead(R);
+	if (R) memset(perRead.data(), 0, R * sizeof(gcgpu_read_anchors));
+	if (params.colinearChaining)
 	{
 		std::vector<std::vector<gcgpu_frag>> localFrags(R);
 		std::vector<std::vector<gcgpu_seed_ext>> localExts(R);
@@ -591,6 +598,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 	std::vector<gcgpu_chained_anchor> chained;
 	std::vector<uint32_t> chainedPaths;
 	std::vector<uint64_t> chainedOff(R + 1, 0);
+	if (params.colinearChaining)
 	{
 		uint64_t nChained = 0, nPathNodes = 0, nAnchors = 0;
 		double tDev = wallNow();
@@ -692,8 +700,8 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		std::vector<int> readPiece(R, -1), gaPiece(R, -1), clcPiece(R, -1);
 		for (size_t r = 0; r < R; r++)
 		{
-			bool needGa = !longAlns[r].empty();
-			bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
+			bool needGa = params.colinearChaining && !longAlns[r].empty();
+			bool needClc = params.colinearChaining && !seedsOrdered[r].empty() && !out[r].dropped;
 			if (!needGa && !needClc) continue;
 			gcgpu_nw_piece pc; memset(&pc, 0, sizeof(pc));
 			pc.kind = GCGPU_PIECE_READ; pc.index = (uint32_t)r;
@@ -726,7 +734,7 @@ inline void GcPipeline::alignBatch(const std::vector<GcRead>& reads, std::vector
 		{
 			if (readPiece[r] < 0) continue;
 			bool needGa = gaPiece[r] >= 0;
-			bool needClc = !seedsOrdered[r].empty() && !out[r].dropped;
+			bool needClc = params.colinearChaining && !seedsOrdered[r].empty() && !out[r].dropped;
 			size_t readLen = reads[r].sequence.size();
 			// first cutoff of the NW passes: the whole-read alignment bounds its own distance from above
 			// (score + unaligned read ends); the chained path normally lies at the same locus.  Only a

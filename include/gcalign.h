@@ -37,6 +37,8 @@ typedef struct gcalign_options
 	int32_t threads_per_stream;   /* host threads of each in-flight batch (0 = 2.25 * host_threads / streams); more than
 	                                 that share oversubscribes the cores on purpose: a batch waiting for the GPU
 	                                 leaves its threads idle                                  */
+	int32_t no_colinear_chaining; /* --no-colinear-chaining: the whole-read pass and its GreedyLength selection only
+	                                 ("align as in GraphAligner", AlignerMain.cpp:108,198)       */
 } gcalign_options;
 
 /* per read: the fields of the reference's --short-verbose line (src/Aligner.cpp:909-915) */

@@ -7,6 +7,7 @@ build container, where /root/reference exists):
 c1   = the reference's own smoke fixture test/graph.gfa + test/read.fa (BASELINE config 1)
 tiny = synthetic 20 kbp bubble graph + 8 simulated 1.5 kb reads at 15 % error, one of
        them with a novel 400-bp insertion (graphchainer_b200.synth, fixed seeds)
+tiny_nocc = the reference's GAM and stdout for the tiny case with --no-colinear-chaining
 tiny_vg = the tiny graph written as a .vg stream (sparse node ids, two gzip members) and the reference's GAM for the same reads
 Each case stores the reference's index arrays (.gcidx) and its per-stage records
 (.stages) -- every K1 extension with its trace, anchors, chain, path, edlib result and
@@ -104,4 +105,7 @@ if __name__ == "__main__":
     synth.write_fasta(f"{TMP}/tiny_in.fa", synth.simulate_reads(g, 8, 1500, 0.15, seed=12, novel_insertion_frac=0.2))
     run_case("tiny", f"{TMP}/tiny_in.gfa", f"{TMP}/tiny_in.fa")
     run_vg_case("tiny_vg", f"{TMP}/tiny_in.gfa", f"{TMP}/tiny_in.fa")
+    # the reference "as in GraphAligner": GAM and the text it prints (banner, summary)
+    with open(f"{OUT}/tiny_nocc.txt", "w") as log:
+        subprocess.run([REFBIN, "-t", "1", "-g", f"{TMP}/tiny_in.gfa", "-f", f"{TMP}/tiny_in.fa", "-a", f"{OUT}/tiny_nocc.gam", "--no-colinear-chaining"], check=True, stdout=log)
     print("golden vectors written to", OUT)

@@ -32,6 +32,22 @@ def test_host_pipeline_matches_reference_gam(driver_sim, golden_files, tmp_path,
     assert not diffs, diffs
 
 
+def test_no_colinear_chaining_mode_matches_reference(driver_sim, golden_files, tmp_path):
+    """--no-colinear-chaining ("align as in GraphAligner", AlignerMain.cpp:108,198): GAM and the summary text of the unmodified
+    reference in that mode (tests/golden/tiny_nocc.gam / .txt, make_golden.py)."""
+    idx, _ = golden_files["tiny"]
+    out = str(tmp_path / "out.gam")
+    run = subprocess.run([driver_sim, "--gc-index", idx, "-f", os.path.join(GOLDEN, "tiny.fa"), "-a", out, "-t", "4", "--gc-quiet", "--no-colinear-chaining"], check=True, capture_output=True, text=True)
+    ref = gam.read_gam(os.path.join(GOLDEN, "tiny_nocc.gam"))
+    diffs = gam.diff_gam(gam.read_gam(out), ref)
+    assert not diffs, diffs
+    assert gam.diff_gam(ref, gam.read_gam(os.path.join(GOLDEN, "tiny.gam"))), "the mode must change something on this input"
+    want = [l for l in open(os.path.join(GOLDEN, "tiny_nocc.txt")).read().splitlines() if l]
+    got = [l for l in run.stdout.splitlines() if l]
+    assert "Co-linear chaining off" in got
+    assert got[got.index("Alignment finished"):] == want[want.index("Alignment finished"):]
+
+
 def test_vg_graph_input_matches_reference_gam(driver_sim, tmp_path):
     """The graph given as a .vg stream (tests/golden/tiny_vg.vg: the tiny graph with sparse node ids in two gzip members, made by
     make_golden.gfa_to_vg): index built by gc_buildindex, GAM identical to the unmodified reference's on the same .vg
@@ -172,7 +188,8 @@ def test_gpu_pipeline_matches_reference_gam(golden_files, tmp_path, name):
 @pytest.mark.gpu
 def test_gpu_pipeline_matches_reference_on_fresh_synthetic(tmp_path):
     """300 reads x 8 kb at 15 % error (5 % with a novel insertion) on a 1 Mbp bubble graph: the
-    unmodified reference runs live on the box's CPU, the GPU pipeline must give the same GAM."""
+    unmodified reference runs live on the box's CPU (one thread: its multi-threaded runs are not run-to-run deterministic,
+    profiles/r04h_reference_nondeterminism.txt), the GPU pipeline must give the same GAM."""
     if not (os.path.exists(REFBIN) and os.path.exists(REFDUMP)):
         pytest.skip("oracle/_ref not built")
     from graphchainer_b200 import synth
@@ -183,12 +200,20 @@ def test_gpu_pipeline_matches_reference_on_fresh_synthetic(tmp_path):
     synth.write_fasta(fa, synth.simulate_reads(g, 300, 8000, 0.15, seed=52))
     idx, ref_gam, out = str(tmp_path / "x.gcidx"), str(tmp_path / "ref.gam"), str(tmp_path / "out.gam")
     subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "--gc-index", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    subprocess.run([REFBIN, "-t", str(os.cpu_count() or 8), "-g", gfa, "-f", fa, "-a", ref_gam], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([REFBIN, "-t", "1", "-g", gfa, "-f", fa, "-a", ref_gam], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8))], check=True, stdout=subprocess.DEVNULL)
     a, b = gam.read_gam(out), gam.read_gam(ref_gam)
     assert len(b) == 300
     diffs = gam.diff_gam(a, b)
     assert not diffs, diffs
+    # the same reads "as in GraphAligner" (--no-colinear-chaining): the whole-read pass and its GreedyLength selection only
+    subprocess.run([REFBIN, "-t", "1", "-g", gfa, "-f", fa, "-a", ref_gam, "--no-colinear-chaining"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8)), "--no-colinear-chaining"], check=True, stdout=subprocess.DEVNULL)
+    a2, b2 = gam.read_gam(out), gam.read_gam(ref_gam)
+    assert len(b2) >= 290
+    diffs = gam.diff_gam(a2, b2)
+    assert not diffs, diffs
+    assert gam.diff_gam(b2, b), "the mode changes nothing on this input: the comparison above proves nothing"
 
 
 @pytest.mark.gpu
@@ -206,7 +231,7 @@ def test_gpu_pipeline_matches_reference_on_ultralong_reads(tmp_path):
     synth.write_fasta(fa, synth.simulate_reads(g, 10, (50_000, 100_000), 0.12, seed=62, novel_insertion_frac=0.3))
     idx, ref_gam, out = str(tmp_path / "x.gcidx"), str(tmp_path / "ref.gam"), str(tmp_path / "out.gam")
     subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "--gc-index", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    subprocess.run([REFBIN, "-t", str(os.cpu_count() or 8), "-g", gfa, "-f", fa, "-a", ref_gam], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([REFBIN, "-t", "1", "-g", gfa, "-f", fa, "-a", ref_gam], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8))], check=True, stdout=subprocess.DEVNULL)
     a, b = gam.read_gam(out), gam.read_gam(ref_gam)
     assert len(b) == 10
@@ -229,7 +254,7 @@ def test_gpu_pipeline_matches_reference_on_high_width_hifi_reads(tmp_path):
     synth.write_fasta(fa, synth.simulate_reads(g, 24, 20_000, 0.01, seed=72, novel_insertion_frac=0.25))
     idx, ref_gam, out = str(tmp_path / "x.gcidx"), str(tmp_path / "ref.gam"), str(tmp_path / "out.gam")
     subprocess.run([REFDUMP, "-t", "1", "-g", gfa, "--gc-index", idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    subprocess.run([REFBIN, "-t", str(os.cpu_count() or 8), "-g", gfa, "-f", fa, "-a", ref_gam, "--colinear-split-gap", "18"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([REFBIN, "-t", "1", "-g", gfa, "-f", fa, "-a", ref_gam, "--colinear-split-gap", "18"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.run([DRIVER, "--gc-index", idx, "-f", fa, "-a", out, "-t", str(min(32, os.cpu_count() or 8)), "--sampling-step", "0.5"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     a, b = gam.read_gam(out), gam.read_gam(ref_gam)
     assert len(b) == 24
