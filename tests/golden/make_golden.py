@@ -105,6 +105,13 @@ if __name__ == "__main__":
     synth.write_fasta(f"{TMP}/tiny_in.fa", synth.simulate_reads(g, 8, 1500, 0.15, seed=12, novel_insertion_frac=0.2))
     run_case("tiny", f"{TMP}/tiny_in.gfa", f"{TMP}/tiny_in.fa")
     run_vg_case("tiny_vg", f"{TMP}/tiny_in.gfa", f"{TMP}/tiny_in.fa")
+    # edge.fa / edge.fq.gz (committed; made once from tiny.fa: lower case, reads of 10 / 34 / 35 / 36 / 64 / 65 / 100 bases, random and
+    # poly-A reads, a run of N, a name used twice, a name with blanks) against the tiny graph: GAM and the summary lines
+    for fixture, tag in (("edge.fa", "edge"), ("edge.fq.gz", "edge_fq")):
+        with open(f"{TMP}/{tag}.log", "w") as log:
+            subprocess.run([REFBIN, "-t", "1", "-g", f"{TMP}/tiny_in.gfa", "-f", f"{OUT}/{fixture}", "-a", f"{OUT}/{tag}.gam"], check=True, stdout=log)
+        with open(f"{OUT}/{tag}.txt", "w") as f:
+            f.write("".join(open(f"{TMP}/{tag}.log").readlines()[-8:]))
     # the reference "as in GraphAligner": GAM and the text it prints (banner, summary)
     with open(f"{OUT}/tiny_nocc.txt", "w") as log:
         subprocess.run([REFBIN, "-t", "1", "-g", f"{TMP}/tiny_in.gfa", "-f", f"{TMP}/tiny_in.fa", "-a", f"{OUT}/tiny_nocc.gam", "--no-colinear-chaining"], check=True, stdout=log)

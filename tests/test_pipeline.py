@@ -32,6 +32,50 @@ def test_host_pipeline_matches_reference_gam(driver_sim, golden_files, tmp_path,
     assert not diffs, diffs
 
 
+def _edge_case(driver, golden_files, tmp_path, reads, tag):
+    idx, _ = golden_files["tiny"]
+    out = str(tmp_path / "out.gam")
+    run = subprocess.run([driver, "--gc-index", idx, "-f", os.path.join(GOLDEN, reads), "-a", out, "-t", "4"] + (["--gc-quiet"] if "sim" in os.path.basename(driver) else []), check=True, capture_output=True, text=True)
+    ours, ref = gam.read_gam(out), gam.read_gam(os.path.join(GOLDEN, tag + ".gam"))
+    assert sorted(ours) == sorted(ref)          # the same reads get a record (none for the 10-base, random, poly-A ... reads)
+    diffs = gam.diff_gam(ours, ref)
+    assert not diffs, diffs
+    want = [l for l in open(os.path.join(GOLDEN, tag + ".txt")).read().splitlines() if l]
+    got = [l for l in run.stdout.splitlines() if l]
+    assert got[got.index("Alignment finished"):] == want[want.index("Alignment finished"):]
+
+
+@pytest.mark.parametrize("reads,tag", [("edge.fa", "edge"), ("edge.fq.gz", "edge_fq")])
+def test_ragged_reads_match_reference(driver_sim, golden_files, tmp_path, reads, tag):
+    """tests/golden/edge.fa: lower-case reads, reads of 10 / 34 / 35 / 36 / 64 / 65 / 100 bases (around the fragment length and the
+    64-row slice), a random and a poly-A read (no alignment), a run of N inside a read, one name used twice, a name with blanks;
+    edge.fq.gz: the first eight as gzipped FASTQ.  Records and the summary lines of the unmodified reference."""
+    _edge_case(driver_sim, golden_files, tmp_path, reads, tag)
+
+
+@pytest.mark.parametrize("content", ["", ">only_header\n\n>r2\nACGT\n"])
+def test_empty_read_files_match_reference(driver_sim, golden_files, tmp_path, content):
+    """no reads at all / a header without bases and a 4-base read: the (empty) GAM file and the summary of the reference, run live"""
+    if not os.path.exists(REFBIN):
+        pytest.skip("oracle/_ref not built")
+    idx, _ = golden_files["tiny"]
+    fa, out, ref_out = str(tmp_path / "r.fa"), str(tmp_path / "out.gam"), str(tmp_path / "ref.gam")
+    with open(fa, "w") as f:
+        f.write(content)
+    ref = subprocess.run([REFBIN, "-t", "1", "-g", os.path.join(GOLDEN, "tiny.gfa"), "-f", fa, "-a", ref_out], check=True, capture_output=True, text=True)
+    run = subprocess.run([driver_sim, "--gc-index", idx, "-f", fa, "-a", out, "-t", "2", "--gc-quiet"], check=True, capture_output=True, text=True)
+    assert gam.read_gam(out) == gam.read_gam(ref_out) == {}
+    want, got = [l for l in ref.stdout.splitlines() if l], [l for l in run.stdout.splitlines() if l]
+    assert got[got.index("Alignment finished"):] == want[want.index("Alignment finished"):]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reads,tag", [("edge.fa", "edge"), ("edge.fq.gz", "edge_fq")])
+def test_gpu_ragged_reads_match_reference(golden_files, tmp_path, reads, tag):
+    assert os.path.exists(DRIVER), "GraphChainerB200 not built (run __graft_entry__.build())"
+    _edge_case(DRIVER, golden_files, tmp_path, reads, tag)
+
+
 def test_no_colinear_chaining_mode_matches_reference(driver_sim, golden_files, tmp_path):
     """--no-colinear-chaining ("align as in GraphAligner", AlignerMain.cpp:108,198): GAM and the summary text of the unmodified
     reference in that mode (tests/golden/tiny_nocc.gam / .txt, make_golden.py)."""
