@@ -35,7 +35,7 @@ def test_host_pipeline_matches_reference_gam(driver_sim, golden_files, tmp_path,
 def _edge_case(driver, golden_files, tmp_path, reads, tag):
     idx, _ = golden_files["tiny"]
     out = str(tmp_path / "out.gam")
-    run = subprocess.run([driver, "--gc-index", idx, "-f", os.path.join(GOLDEN, reads), "-a", out, "-t", "4"] + (["--gc-quiet"] if "sim" in os.path.basename(driver) else []), check=True, capture_output=True, text=True)
+    run = subprocess.run([driver, "--gc-index", idx, "-f", os.path.join(GOLDEN, reads), "-a", out, "-t", "4", "--gc-quiet"], check=True, capture_output=True, text=True)
     ours, ref = gam.read_gam(out), gam.read_gam(os.path.join(GOLDEN, tag + ".gam"))
     assert sorted(ours) == sorted(ref)          # the same reads get a record (none for the 10-base, random, poly-A ... reads)
     diffs = gam.diff_gam(ours, ref)
